@@ -1,0 +1,355 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see rng.hpp header).
+//
+// CPU restatement of the reference's host control flow around the distance kernels:
+//   src/writer.rs:487-629     Writer::build (fresh-build path)
+//   src/writer.rs:964-976 + src/distance/dot_product.rs:119-165   DotProduct::preprocess
+//   src/writer.rs:474-477     fit_in_descendant
+//   src/writer.rs:1167-1261   make_tree_in_file
+//   src/writer.rs:1310-1326   randomly_split_children
+//   src/writer.rs:1348-1353   split_imbalance
+//   src/writer.rs:1358-1394   target_n_trees
+//   src/parallel.rs:207-255   ConcurrentNodeIds (fresh build: plain counter)
+//   src/reader.rs:317-401     Reader::nns_by_leaf
+//   src/reader.rs:607-640     median_based_top_k
+//   src/node.rs:218-241       NodeCodec::bytes_encode   (+ roaring 0.10.9 serialize_into,
+//                             published portable format, cookie 12346, no run containers)
+// Storage (LMDB/heed) is replaced by in-memory tables; node ids follow the order a
+// 1-thread rayon pool produces (tree tasks run LIFO: SURVEY.md Appendix B.4), which
+// is what the reference's snapshot tests pin (src/tests/mod.rs:94).
+#pragma once
+#include <algorithm>
+#include <atomic>
+#include <cstdint>
+#include <functional>
+#include <map>
+#include <queue>
+#include <stdexcept>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "distance.hpp"
+
+namespace oracle {
+
+struct TreeNode {
+    uint8_t kind = 0;  // 1 = Descendants, 2 = SplitPlaneNormal
+    uint32_t left = 0, right = 0;
+    bool has_normal = false;
+    OwnedLeaf normal;
+    std::vector<uint32_t> descendants;  // item ids, ascending
+};
+
+static inline double split_imbalance(uint64_t l, uint64_t r) {  // writer.rs:1348-1353
+    double ls = (double)l, rs = (double)r;
+    double f = ls / (ls + rs + 2.220446049250313e-16);
+    return f > 1.0 - f ? f : 1.0 - f;  // f64::max
+}
+
+static inline uint64_t target_n_trees(int64_t n_trees_opt, uint64_t dimensions, uint64_t n_items, uint64_t n_roots) {
+    if (n_trees_opt >= 0) return (uint64_t)n_trees_opt;  // writer.rs:1364-1365
+    double nb_vec = (double)n_items;
+    double nb_trees;
+    if (nb_vec < 10000.0) nb_trees = std::pow(2.0, std::log2(nb_vec) - 6.0);
+    else nb_trees = std::pow(2.0, std::log10(nb_vec) + std::log10((double)dimensions) + std::pow(768.0 / (double)dimensions, 4.0));
+    double c = std::ceil(nb_trees);
+    uint64_t n;  // Rust `as u64` saturates, NaN -> 0
+    if (!(c == c) || c <= 0.0) n = 0; else if (c >= 18446744073709551615.0) n = UINT64_MAX; else n = (uint64_t)c;
+    if (n_roots > n) {
+        uint64_t to_remove = n_roots - n;
+        if ((double)to_remove / (double)n < 0.20) n = n_roots;
+    }
+    return n;
+}
+
+// roaring 0.10.9 RoaringBitmap::serialize_into for an ascending id list.
+static inline void roaring_serialize(const std::vector<uint32_t>& ids, std::vector<uint8_t>& out) {
+    struct C { uint16_t key; size_t begin, end; };
+    std::vector<C> cs;
+    for (size_t i = 0; i < ids.size();) {
+        uint16_t key = (uint16_t)(ids[i] >> 16);
+        size_t j = i;
+        while (j < ids.size() && (uint16_t)(ids[j] >> 16) == key) ++j;
+        cs.push_back({key, i, j});
+        i = j;
+    }
+    auto w16 = [&](uint16_t v) { out.push_back((uint8_t)v); out.push_back((uint8_t)(v >> 8)); };
+    auto w32 = [&](uint32_t v) { for (int k = 0; k < 4; ++k) out.push_back((uint8_t)(v >> (8 * k))); };
+    w32(12346u);
+    w32((uint32_t)cs.size());
+    for (auto& c : cs) { w16(c.key); w16((uint16_t)(c.end - c.begin - 1)); }
+    uint32_t offset = 8 + 8 * (uint32_t)cs.size();
+    for (auto& c : cs) {
+        w32(offset);
+        size_t len = c.end - c.begin;
+        offset += len > 4096 ? 8192u : (uint32_t)len * 2u;
+    }
+    for (auto& c : cs) {
+        size_t len = c.end - c.begin;
+        if (len > 4096) {
+            std::vector<uint64_t> bits(1024, 0);
+            for (size_t i = c.begin; i < c.end; ++i) { uint16_t lo = (uint16_t)ids[i]; bits[lo >> 6] |= 1ull << (lo & 63); }
+            for (uint64_t b : bits) for (int k = 0; k < 8; ++k) out.push_back((uint8_t)(b >> (8 * k)));
+        } else {
+            for (size_t i = c.begin; i < c.end; ++i) w16((uint16_t)ids[i]);
+        }
+    }
+}
+
+// NodeCodec::bytes_encode for tree nodes — src/node.rs:229-241
+static inline void encode_tree_node(int metric, size_t d, const TreeNode& n, std::vector<uint8_t>& out) {
+    out.clear();
+    if (n.kind == 1) {
+        out.push_back(1);
+        roaring_serialize(n.descendants, out);
+        return;
+    }
+    out.push_back(2);
+    for (int k = 3; k >= 0; --k) out.push_back((uint8_t)(n.left >> (8 * k)));
+    for (int k = 3; k >= 0; --k) out.push_back((uint8_t)(n.right >> (8 * k)));
+    if (n.has_normal) {
+        const uint8_t* p = reinterpret_cast<const uint8_t*>(&n.normal.h0);
+        out.insert(out.end(), p, p + 4);
+        if (header_floats(metric) == 2) { p = reinterpret_cast<const uint8_t*>(&n.normal.h1); out.insert(out.end(), p, p + 4); }
+        p = reinterpret_cast<const uint8_t*>(n.normal.v.data());
+        out.insert(out.end(), p, p + 4 * d);
+    }
+}
+
+struct Db {
+    int metric;
+    size_t d;
+    // staging area of add_item (small tests)
+    std::map<uint32_t, std::vector<float>> staged;
+    // frozen item table (rows ascending by id)
+    std::vector<uint32_t> ids_own;
+    std::vector<float> vec_own, h0_own, h1_own;
+    const uint32_t* ids = nullptr;
+    const float* vec = nullptr;
+    size_t n = 0;
+    // forest
+    std::vector<TreeNode> nodes;  // index = tree node id
+    std::vector<uint32_t> roots;
+    bool built = false;
+    std::atomic<uint64_t> scanned_rows{0};  // rows that went through side() during build
+
+    Db(int m, size_t dim) : metric(m), d(dim) {}
+
+    int64_t row_of(uint32_t id) const {
+        const uint32_t* p = std::lower_bound(ids, ids + n, id);
+        if (p == ids + n || *p != id) return -1;
+        return p - ids;
+    }
+    Leaf leaf(size_t row) const { return Leaf{h0_own[row], h1_own.empty() ? 0.f : h1_own[row], vec + row * d}; }
+
+    void freeze() {
+        if (!staged.empty() || ids == nullptr) {
+            ids_own.clear(); vec_own.clear();
+            for (auto& kv : staged) { ids_own.push_back(kv.first); vec_own.insert(vec_own.end(), kv.second.begin(), kv.second.end()); }
+            ids = ids_own.data(); vec = vec_own.data(); n = ids_own.size();
+        }
+        // Writer::add_item: header = D::new_header(vector) — writer.rs:388-390
+        h0_own.assign(n, 0.f);
+        h1_own.assign(metric == DOT_PRODUCT ? n : 0, 0.f);
+        if (metric == COSINE) for (size_t r = 0; r < n; ++r) h0_own[r] = norm_no_header(vec + r * d, d);
+    }
+
+    // DotProduct::preprocess — dot_product.rs:119-165
+    void preprocess() {
+        if (metric != DOT_PRODUCT) return;
+        float max_norm = 0.0f;
+        for (size_t r = 0; r < n; ++r) {
+            float nm = norm_no_header(vec + r * d, d);
+            max_norm = (nm != nm) ? max_norm : (max_norm != max_norm ? nm : (max_norm > nm ? max_norm : nm));  // f32::max
+        }
+        for (size_t r = 0; r < n; ++r) {
+            float node_norm = norm_no_header(vec + r * d, d);
+            float diff = (max_norm * max_norm) - (node_norm * node_norm);
+            h1_own[r] = max_norm * max_norm;
+            h0_own[r] = std::sqrt(diff);
+        }
+    }
+
+    struct LocalNode {  // tree-local, post-order; children are local indices; the root is last
+        uint8_t kind; uint32_t left, right; bool has_normal; OwnedLeaf normal; std::vector<uint32_t> rows;
+    };
+
+    // make_tree_in_file — writer.rs:1167-1261. Returns the local index of the node.
+    // is_root: the root id was allocated up front (next_id = Some(..)), so it takes no
+    // post-order number; it is appended last by the caller's convention.
+    uint32_t make_tree(StdRng& rng, const std::vector<uint32_t>& rows, size_t K, std::vector<LocalNode>& out, uint64_t& scanned) {
+        if (rows.size() <= K) {
+            out.push_back(LocalNode{1, 0, 0, false, OwnedLeaf{}, rows});
+            return (uint32_t)out.size() - 1;
+        }
+        SubsetView children{rows.data(), (uint32_t)rows.size(), vec, h0_own.data(), h1_own.empty() ? nullptr : h1_own.data(), d};
+        std::vector<uint32_t> left, right;
+        left.reserve(rows.size()); right.reserve(rows.size());
+        int remaining_attempts = 3;
+        OwnedLeaf normal;
+        for (;;) {
+            left.clear(); right.clear();
+            create_split(metric, rng, children, normal);
+            Leaf nl = normal.view();
+            for (uint32_t r : rows) {
+                if (side_is_right(margin(metric, nl, leaf(r), d))) right.push_back(r); else left.push_back(r);
+            }
+            scanned += rows.size();
+            if (split_imbalance(left.size(), right.size()) < 0.95 || remaining_attempts == 0) break;
+            --remaining_attempts;
+        }
+        bool has_normal = true;
+        if (split_imbalance(left.size(), right.size()) > 0.99) {
+            left.clear(); right.clear();  // randomly_split_children — writer.rs:1310-1326
+            for (uint32_t r : rows) { if (rng.gen_bool()) left.push_back(r); else right.push_back(r); }
+            has_normal = false;
+        }
+        uint32_t l = make_tree(rng, left, K, out, scanned);
+        uint32_t r = make_tree(rng, right, K, out, scanned);
+        LocalNode nd{2, l, r, has_normal, has_normal ? normal : OwnedLeaf{}, {}};
+        out.push_back(std::move(nd));
+        return (uint32_t)out.size() - 1;
+    }
+
+    // Writer::build, fresh-build path (no pre-existing trees) — writer.rs:487-629.
+    // n_trees_opt < 0 => target_n_trees formula; split_after == 0 => dimensions.
+    void build(StdRng& user_rng, int64_t n_trees_opt, size_t split_after, int n_threads) {
+        freeze();
+        preprocess();
+        nodes.clear(); roots.clear(); scanned_rows = 0;
+        const size_t K = split_after ? split_after : d;
+        if (n <= K) {  // clear_db_and_create_a_single_leaf — writer.rs:916-962
+            if (n > 0) {
+                TreeNode t; t.kind = 1; t.descendants.assign(ids, ids + n);
+                nodes.push_back(std::move(t));
+                roots.push_back(0);
+            }
+            built = true;
+            return;
+        }
+        uint64_t T = target_n_trees(n_trees_opt, d, n, 0);
+        for (uint64_t t = 0; t < T; ++t) roots.push_back((uint32_t)t);  // writer.rs:556-561
+        StdRng rng1 = user_rng.fork();                                   // writer.rs:575
+        std::vector<StdRng> tree_rng;
+        for (uint64_t t = 0; t < T; ++t) tree_rng.push_back(rng1.fork());  // writer.rs:795 (IntMap order = ascending roots)
+        std::vector<uint32_t> all(n);
+        for (size_t r = 0; r < n; ++r) all[r] = (uint32_t)r;
+        std::vector<std::vector<LocalNode>> local(T);
+        std::atomic<uint64_t> next{0};
+        auto worker = [&]() {
+            for (;;) {
+                uint64_t t = next.fetch_add(1);
+                if (t >= T) return;
+                uint64_t sc = 0;
+                make_tree(tree_rng[t], all, K, local[t], sc);
+                scanned_rows += sc;
+            }
+        };
+        if (n_threads <= 1) worker();
+        else {
+            std::vector<std::thread> th;
+            for (int i = 0; i < n_threads; ++i) th.emplace_back(worker);
+            for (auto& x : th) x.join();
+        }
+        // id assignment of a 1-thread rayon pool: spawned tree tasks run LIFO, ids come
+        // from one counter starting after the roots, post-order inside each tree.
+        std::vector<uint64_t> base(T);
+        uint64_t counter = T;
+        for (uint64_t k = 0; k < T; ++k) { uint64_t t = T - 1 - k; base[t] = counter; counter += local[t].size() - 1; }
+        nodes.resize(counter);
+        for (uint64_t t = 0; t < T; ++t) {
+            auto& L = local[t];
+            const uint32_t root_local = (uint32_t)L.size() - 1;
+            auto gid = [&](uint32_t li) { return li == root_local ? (uint32_t)t : (uint32_t)(base[t] + li); };
+            for (uint32_t li = 0; li < L.size(); ++li) {
+                TreeNode& o = nodes[gid(li)];
+                o.kind = L[li].kind;
+                if (o.kind == 1) { o.descendants.resize(L[li].rows.size()); for (size_t i = 0; i < L[li].rows.size(); ++i) o.descendants[i] = ids[L[li].rows[i]]; }
+                else { o.left = gid(L[li].left); o.right = gid(L[li].right); o.has_normal = L[li].has_normal; o.normal = std::move(L[li].normal); }
+            }
+            L.clear(); L.shrink_to_fit();
+        }
+        built = true;
+    }
+
+    // Total order of (OrderedFloat<f32>, u32): NaN greatest & all NaN equal, -0 == +0.
+    static bool less_key(float a, uint32_t ia, float b, uint32_t ib) {
+        bool an = a != a, bn = b != b;
+        if (an || bn) { if (an && bn) return ia < ib; return bn; }
+        if (a < b) return true;
+        if (a > b) return false;
+        return ia < ib;
+    }
+
+    // median_based_top_k — reader.rs:607-640 (restated literally; equals sort+truncate)
+    static std::vector<std::pair<float, uint32_t>> median_based_top_k(std::vector<std::pair<float, uint32_t>> v, size_t k) {
+        auto lt = [](const std::pair<float, uint32_t>& x, const std::pair<float, uint32_t>& y) { return less_key(x.first, x.second, y.first, y.second); };
+        std::pair<float, uint32_t> threshold{FLT_MAX, UINT32_MAX};
+        std::vector<std::pair<float, uint32_t>> buffer;
+        if (k == 0) return buffer;  // (the reference would panic in select_nth_unstable; unreachable from nns_by_leaf unless count == 0)
+        buffer.reserve(2 * std::max<size_t>(k, 1));
+        size_t i = 0;
+        for (; i < v.size() && i < 2 * k; ++i) buffer.push_back(v[i]);
+        for (; i < v.size(); ++i) {
+            if (!lt(v[i], threshold)) continue;
+            if (buffer.size() == 2 * k) {
+                std::nth_element(buffer.begin(), buffer.begin() + (k - 1), buffer.end(), lt);
+                threshold = buffer[k - 1];
+                buffer.resize(k);
+            }
+            buffer.push_back(v[i]);
+        }
+        std::sort(buffer.begin(), buffer.end(), lt);
+        if (buffer.size() > k) buffer.resize(k);
+        return buffer;
+    }
+
+    // Reader::nns_by_leaf — reader.rs:317-401.  candidates == nullptr => no filter.
+    // If out_candidates is given, the deduplicated candidate id list that goes into the
+    // re-rank loop (reader.rs:378-379) is stored there.
+    std::vector<std::pair<uint32_t, float>> nns_by_leaf(const Leaf& q, size_t count, size_t search_k_opt, size_t oversampling_opt,
+                                                        const std::vector<uint32_t>* candidates, std::vector<uint32_t>* out_candidates = nullptr) const {
+        std::vector<std::pair<uint32_t, float>> output;
+        if (n == 0) return output;
+        size_t search_k = search_k_opt ? search_k_opt : count * roots.size();
+        {   // saturating_mul
+            size_t mul = oversampling_opt ? oversampling_opt : 1;  // DEFAULT_OVERSAMPLING = 1 (mod.rs:41)
+            unsigned __int128 p = (unsigned __int128)search_k * mul;
+            search_k = p > (unsigned __int128)SIZE_MAX ? SIZE_MAX : (size_t)p;
+        }
+        struct QE { float dist; uint32_t node; };
+        auto cmp = [](const QE& a, const QE& b) { return less_key(a.dist, a.node, b.dist, b.node); };  // max-heap
+        std::priority_queue<QE, std::vector<QE>, decltype(cmp)> queue(cmp);
+        for (uint32_t r : roots) queue.push(QE{INFINITY, r});
+        std::vector<uint32_t> nns;
+        while (nns.size() < search_k) {
+            if (queue.empty()) break;
+            QE top = queue.top(); queue.pop();
+            const TreeNode& node = nodes[top.node];
+            if (node.kind == 1) {
+                if (candidates) {
+                    for (uint32_t id : node.descendants) if (std::binary_search(candidates->begin(), candidates->end(), id)) nns.push_back(id);
+                } else nns.insert(nns.end(), node.descendants.begin(), node.descendants.end());
+            } else {
+                float mg = node.has_normal ? margin(metric, node.normal.view(), q, d) : 0.0f;
+                queue.push(QE{pq_distance(top.dist, mg, false), node.left});
+                queue.push(QE{pq_distance(top.dist, mg, true), node.right});
+            }
+        }
+        std::sort(nns.begin(), nns.end());
+        nns.erase(std::unique(nns.begin(), nns.end()), nns.end());
+        if (out_candidates) *out_candidates = nns;
+        std::vector<std::pair<float, uint32_t>> dists;
+        dists.reserve(nns.size());
+        for (uint32_t id : nns) {
+            int64_t row = row_of(id);
+            dists.push_back({built_distance(metric, q, leaf((size_t)row), d), id});
+        }
+        size_t k = std::min(count, dists.size());
+        auto top = median_based_top_k(std::move(dists), k);
+        for (auto& pr : top) output.push_back({pr.second, normalized_distance(metric, pr.first)});
+        return output;
+    }
+};
+
+}  // namespace oracle
