@@ -1,0 +1,246 @@
+"""ctypes binding of include/arroy_b200.h (libarroy_b200.so, built in-tree by
+__graft_entry__.build()). No fallback: if the library or a CUDA device is missing, calls
+raise — nothing here computes on the CPU."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libarroy_b200.so")
+
+EUCLIDEAN, COSINE, DOT_PRODUCT, MANHATTAN = 0, 1, 2, 3
+METRICS = {"euclidean": 0, "cosine": 1, "dot-product": 2, "manhattan": 3}
+METRIC_NAMES = {v: k for k, v in METRICS.items()}
+
+OK, ERR_CUDA, ERR_INVALID, ERR_CANCELLED, ERR_CAPACITY, ERR_NOT_STAGED, ERR_INTERNAL = range(7)
+
+_f32p = C.POINTER(C.c_float)
+_u32p = C.POINTER(C.c_uint32)
+_u64p = C.POINTER(C.c_uint64)
+_u8p = C.POINTER(C.c_uint8)
+NODE_SINK = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_uint32, _u8p, C.c_uint64)
+CANCEL_FN = C.CFUNCTYPE(C.c_int32, C.c_void_p)
+
+# every symbol include/arroy_b200.h declares: (name, restype, argtypes)
+SIGNATURES = [
+    ("arroy_b200_version", C.c_char_p, []),
+    ("arroy_b200_create", C.c_int32, [C.c_int32, C.POINTER(C.c_void_p)]),
+    ("arroy_b200_destroy", None, [C.c_void_p]),
+    ("arroy_b200_last_error", C.c_char_p, [C.c_void_p]),
+    ("arroy_b200_stage_items", C.c_int32, [C.c_void_p, C.c_int32, C.c_uint32, C.c_uint64, _u32p, C.POINTER(C.c_void_p)]),
+    ("arroy_b200_stage_items_flat", C.c_int32, [C.c_void_p, C.c_int32, C.c_uint32, C.c_uint64, _u32p, C.c_void_p, _f32p, _f32p]),
+    ("arroy_b200_stage_items_device", C.c_int32, [C.c_void_p, C.c_int32, C.c_uint32, C.c_uint64, _u32p, C.c_void_p]),
+    ("arroy_b200_item_headers", C.c_int32, [C.c_void_p, _f32p, _f32p]),
+    ("arroy_b200_dot_preprocess", C.c_int32, [C.c_void_p, _f32p, _f32p]),
+    ("arroy_b200_side_batch", C.c_int32, [C.c_void_p, _f32p, C.c_float, C.c_float, _u32p, C.c_uint64, _u8p, _f32p]),
+    ("arroy_b200_create_split", C.c_int32, [C.c_void_p, _u32p, _u64p, _u32p, C.c_uint64, _f32p, _f32p]),
+    ("arroy_b200_build_trees", C.c_int32, [C.c_void_p, C.c_uint32, C.c_void_p, _u32p, C.c_uint32, C.c_uint32, CANCEL_FN, C.c_void_p, NODE_SINK, C.c_void_p, _u64p]),
+    ("arroy_b200_build_stats", C.c_int32, [C.c_void_p, C.POINTER(C.c_double)]),
+    ("arroy_b200_rerank", C.c_int32, [C.c_void_p, _f32p, C.c_float, C.c_float, _u32p, C.c_uint64, C.c_uint32, _u32p, _f32p, _u32p]),
+    ("arroy_b200_rerank_batch", C.c_int32, [C.c_void_p, C.c_uint32, _f32p, _f32p, _f32p, _u32p, _u64p, C.c_uint32, _u32p, _f32p, _u32p]),
+    ("arroy_b200_synth_device", C.c_int32, [C.c_void_p, _u8p, C.c_uint32, C.c_uint64, C.c_uint64, C.c_float, C.c_void_p]),
+    ("arroy_b200_time_scan", C.c_int32, [C.c_void_p, _f32p, C.c_float, C.c_float, _u32p, C.c_uint64, C.c_int32, C.c_int32, C.c_int32, _f32p, _u64p]),
+    ("arroy_b200_device_ptrs", C.c_int32, [C.c_void_p, C.POINTER(C.c_void_p), _u32p]),
+]
+
+_LIB = None
+
+
+class ArroyB200Error(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__("arroy_b200 error %d: %s" % (code, message))
+        self.code = code
+        self.message = message
+
+
+def load():
+    """Load the shared library (no CUDA call is made by loading)."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError("%s is missing — run `python -c 'import __graft_entry__ as g; g.build()'`" % LIB_PATH)
+        lib = C.CDLL(LIB_PATH)
+        for name, res, args in SIGNATURES:
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _LIB = lib
+    return _LIB
+
+
+def _fp(a):
+    return a.ctypes.data_as(_f32p) if a is not None else None
+
+
+def _up(a):
+    return a.ctypes.data_as(_u32p) if a is not None else None
+
+
+class Context:
+    """One arroy_ctx (one GPU). Thin 1:1 wrapper over the C ABI."""
+
+    def __init__(self, device=0):
+        self.lib = load()
+        h = C.c_void_p()
+        rc = self.lib.arroy_b200_create(device, C.byref(h))
+        if rc != OK:
+            raise ArroyB200Error(rc, "arroy_b200_create failed (no CUDA device / library not built for this GPU)")
+        self.h = h
+        self.device = device
+        self.n = 0
+        self.dim = 0
+        self.metric = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.arroy_b200_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != OK:
+            raise ArroyB200Error(rc, self.lib.arroy_b200_last_error(self.h).decode())
+
+    # -- staging ---------------------------------------------------------------------------
+    def stage_items_flat(self, metric, ids, vectors, hdr0=None, hdr1=None):
+        metric = METRICS[metric] if isinstance(metric, str) else metric
+        ids = np.ascontiguousarray(ids, dtype=np.uint32)
+        if hasattr(vectors, "data_ptr"):  # torch CPU tensor (possibly pinned)
+            n, dim = vectors.shape
+            ptr = vectors.data_ptr()
+            keep = vectors
+        else:
+            vectors = np.ascontiguousarray(vectors, dtype=np.float32)
+            n, dim = vectors.shape
+            ptr = vectors.ctypes.data
+            keep = vectors
+        assert ids.size == n
+        h0 = None if hdr0 is None else np.ascontiguousarray(hdr0, dtype=np.float32)
+        h1 = None if hdr1 is None else np.ascontiguousarray(hdr1, dtype=np.float32)
+        self._ck(self.lib.arroy_b200_stage_items_flat(self.h, metric, dim, n, _up(ids), C.c_void_p(ptr), _fp(h0), _fp(h1)))
+        del keep
+        self.n, self.dim, self.metric = n, dim, metric
+
+    def stage_items_leaf_values(self, metric, dim, ids, values):
+        """values: list of bytes objects = raw stored Leaf values ([0x00][header][dim x f32])."""
+        metric = METRICS[metric] if isinstance(metric, str) else metric
+        ids = np.ascontiguousarray(ids, dtype=np.uint32)
+        n = ids.size
+        bufs = [C.create_string_buffer(v, len(v)) for v in values]
+        arr = (C.c_void_p * max(n, 1))(*[C.cast(b, C.c_void_p) for b in bufs])
+        self._ck(self.lib.arroy_b200_stage_items(self.h, metric, dim, n, _up(ids), arr))
+        self.n, self.dim, self.metric = n, dim, metric
+
+    def stage_items_device(self, metric, ids, dim, device_ptr):
+        metric = METRICS[metric] if isinstance(metric, str) else metric
+        ids = np.ascontiguousarray(ids, dtype=np.uint32)
+        self._ck(self.lib.arroy_b200_stage_items_device(self.h, metric, dim, ids.size, _up(ids), C.c_void_p(device_ptr)))
+        self.n, self.dim, self.metric = ids.size, dim, metric
+
+    def item_headers(self):
+        h0 = np.empty(self.n, dtype=np.float32)
+        h1 = np.empty(self.n, dtype=np.float32)
+        self._ck(self.lib.arroy_b200_item_headers(self.h, _fp(h0), _fp(h1)))
+        return h0, h1
+
+    def dot_preprocess(self):
+        extra = np.empty(self.n, dtype=np.float32)
+        norm = np.empty(self.n, dtype=np.float32)
+        self._ck(self.lib.arroy_b200_dot_preprocess(self.h, _fp(extra), _fp(norm)))
+        return extra, norm
+
+    # -- side / split ------------------------------------------------------------------------
+    def side_batch(self, normal, hdr, rows, want_margin=True):
+        normal = np.ascontiguousarray(normal, dtype=np.float32)
+        rows = np.ascontiguousarray(rows, dtype=np.uint32)
+        side = np.empty(rows.size, dtype=np.uint8)
+        mg = np.empty(rows.size, dtype=np.float32) if want_margin else None
+        self._ck(self.lib.arroy_b200_side_batch(self.h, _fp(normal), hdr[0], hdr[1], _up(rows), rows.size,
+                                                side.ctypes.data_as(_u8p), _fp(mg)))
+        return side, mg
+
+    def create_split(self, key_words, word_pos, rows):
+        key = np.ascontiguousarray(key_words, dtype=np.uint32)
+        rows = np.ascontiguousarray(rows, dtype=np.uint32)
+        pos = C.c_uint64(word_pos)
+        normal = np.empty(self.dim, dtype=np.float32)
+        hdr = np.zeros(2, dtype=np.float32)
+        self._ck(self.lib.arroy_b200_create_split(self.h, _up(key), C.byref(pos), _up(rows), rows.size, _fp(normal), _fp(hdr)))
+        return normal, (float(hdr[0]), float(hdr[1])), pos.value
+
+    # -- forest --------------------------------------------------------------------------------
+    def build_trees(self, tree_seeds, root_ids, first_free_node_id, split_after=0, cancel=None, collect=True):
+        """Returns {node_id: NodeCodec bytes} (or the node count when collect=False)."""
+        n_trees = len(tree_seeds)
+        seeds = (C.c_uint8 * (32 * max(n_trees, 1)))()
+        for t, s in enumerate(tree_seeds):
+            assert len(s) == 32
+            seeds[32 * t:32 * t + 32] = list(s)
+        roots = np.ascontiguousarray(root_ids, dtype=np.uint32)
+        out = {}
+
+        def sink(_arg, node_id, ptr, length):
+            out[node_id] = C.string_at(ptr, length)
+            return 0
+
+        cb = NODE_SINK(sink) if collect else C.cast(None, NODE_SINK)
+        ccb = CANCEL_FN((lambda _a: 1 if cancel() else 0)) if cancel else C.cast(None, CANCEL_FN)
+        n_nodes = C.c_uint64(0)
+        self._ck(self.lib.arroy_b200_build_trees(self.h, n_trees, C.cast(seeds, C.c_void_p), _up(roots), first_free_node_id, split_after,
+                                                 ccb, None, cb, None, C.byref(n_nodes)))
+        return out if collect else n_nodes.value
+
+    def build_stats(self):
+        st = (C.c_double * 8)()
+        self._ck(self.lib.arroy_b200_build_stats(self.h, st))
+        keys = ["scanned_rows", "steps", "create_split_calls", "random_splits", "build_ms", "scan_ms", "nodes", "reserved"]
+        return dict(zip(keys, list(st)))
+
+    # -- re-rank -------------------------------------------------------------------------------
+    def rerank(self, query, qhdr, rows, k):
+        query = np.ascontiguousarray(query, dtype=np.float32)
+        rows = np.ascontiguousarray(rows, dtype=np.uint32)
+        out_rows = np.empty(max(k, 1), dtype=np.uint32)
+        out_dist = np.empty(max(k, 1), dtype=np.float32)
+        out_len = C.c_uint32(0)
+        self._ck(self.lib.arroy_b200_rerank(self.h, _fp(query), qhdr[0], qhdr[1], _up(rows), rows.size, k, _up(out_rows), _fp(out_dist), C.byref(out_len)))
+        return out_rows[:out_len.value].copy(), out_dist[:out_len.value].copy()
+
+    def rerank_batch(self, queries, qhdr0, rows, offsets, k):
+        queries = np.ascontiguousarray(queries, dtype=np.float32)
+        nq = queries.shape[0]
+        rows = np.ascontiguousarray(rows, dtype=np.uint32)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        h0 = None if qhdr0 is None else np.ascontiguousarray(qhdr0, dtype=np.float32)
+        out_rows = np.empty((nq, max(k, 1)), dtype=np.uint32)
+        out_dist = np.empty((nq, max(k, 1)), dtype=np.float32)
+        out_len = np.zeros(nq, dtype=np.uint32)
+        self._ck(self.lib.arroy_b200_rerank_batch(self.h, nq, _fp(queries), _fp(h0), None, _up(rows), offsets.ctypes.data_as(_u64p), k,
+                                                  _up(out_rows), _fp(out_dist), _up(out_len)))
+        return out_rows, out_dist, out_len
+
+    # -- helpers ---------------------------------------------------------------------------------
+    def synth_device(self, seed, dim, row0, rows, centre, device_ptr):
+        s = (C.c_uint8 * 32)(*bytes(seed))
+        self._ck(self.lib.arroy_b200_synth_device(self.h, s, dim, row0, rows, centre, C.c_void_p(device_ptr)))
+
+    def time_scan(self, normal, hdr, n_rows, rows=None, iters=5, flush_l2=True, variant=0):
+        normal = np.ascontiguousarray(normal, dtype=np.float32)
+        r = None if rows is None else np.ascontiguousarray(rows, dtype=np.uint32)
+        ms = C.c_float(0)
+        left = C.c_uint64(0)
+        self._ck(self.lib.arroy_b200_time_scan(self.h, _fp(normal), hdr[0], hdr[1], _up(r), n_rows, variant, iters, 1 if flush_l2 else 0,
+                                               C.byref(ms), C.byref(left)))
+        return ms.value, left.value
+
+    def device_ptrs(self):
+        out = (C.c_void_p * 3)()
+        ld = C.c_uint32(0)
+        self._ck(self.lib.arroy_b200_device_ptrs(self.h, out, C.byref(ld)))
+        return [out[0], out[1], out[2]], ld.value

@@ -1,0 +1,863 @@
+// arroy_b200.cu — context, item staging, forest-build driver, re-rank and the extern "C"
+// boundary declared in include/arroy_b200.h. Product code: there is no CPU fallback and no
+// dependency on oracle/.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/arroy_b200.h"
+#include "build.cuh"
+
+using namespace ab;
+
+namespace {
+
+struct CudaError : std::runtime_error { using std::runtime_error::runtime_error; };
+struct ArgError : std::runtime_error { using std::runtime_error::runtime_error; };
+struct CapacityError : std::runtime_error { using std::runtime_error::runtime_error; };
+struct Cancelled : std::runtime_error { using std::runtime_error::runtime_error; };
+struct NotStaged : std::runtime_error { using std::runtime_error::runtime_error; };
+
+#define CK(call)                                                                                      \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess)                                                                        \
+            throw CudaError(std::string(#call) + ": " + cudaGetErrorString(e_) + " (" __FILE__ ":" + \
+                            std::to_string(__LINE__) + ")");                                          \
+    } while (0)
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    void ensure(size_t bytes) {
+        if (bytes <= cap) return;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        CK(cudaMalloc(&p, want));
+        cap = want;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T* as() { return static_cast<T*>(p); }
+};
+struct PinBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    void ensure(size_t bytes) {
+        if (bytes <= cap) return;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        CK(cudaMallocHost(&p, bytes));
+        cap = bytes;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+    template <class T> T* as() { return static_cast<T*>(p); }
+};
+
+}  // namespace
+
+struct arroy_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    std::mutex mu;
+    std::string err;
+    // staged items
+    bool staged = false;
+    int metric = 0;
+    uint32_t dim = 0, ld = 0;
+    uint64_t n = 0;
+    DevBuf items, h0, h1, norms, maxbits;
+    std::vector<uint32_t> ids;
+    // scratch
+    DevBuf s_rows, s_flags, s_margins, s_normal, s_unit, s_job, s_keys, s_dists, s_q, s_qh0, s_off, s_orows, s_odist, s_olen, s_misc;
+    PinBuf pin;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    bool h1_valid = false;
+};
+
+namespace {
+
+int metric_header_floats(int m) { return m == DOT_PRODUCT ? 2 : 1; }
+
+void set_device(arroy_ctx* c) { CK(cudaSetDevice(c->device)); }
+
+void require_staged(arroy_ctx* c) { if (!c->staged) throw NotStaged("items have not been staged on this context"); }
+
+size_t work_smem(uint32_t ld, int njobs) { return (size_t)ld * 4 + (size_t)(njobs + 1) * 4 + 16; }
+
+void launch_work(arroy_ctx* c, const Job* jobs, int njobs, int grid) {
+    size_t smem = work_smem(c->ld, njobs);
+    static std::atomic<size_t> configured{0};
+    if (smem > 48 * 1024 && smem > configured.load()) {
+        CK(cudaFuncSetAttribute(work_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    work_kernel<<<grid, WORK_THREADS, smem, c->stream>>>(jobs, njobs, c->items.as<float>(), c->h0.as<float>(), c->dim, c->ld, c->metric);
+    CK(cudaGetLastError());
+}
+
+void compute_norms(arroy_ctx* c, bool with_max) {
+    c->norms.ensure(c->n * 4);
+    c->maxbits.ensure(4);
+    if (with_max) CK(cudaMemsetAsync(c->maxbits.p, 0, 4, c->stream));
+    uint64_t warps = (c->n + 3) / 4;
+    int grid = (int)std::min<uint64_t>((warps + 7) / 8, (uint64_t)c->sm_count * 16);
+    if (grid < 1) grid = 1;
+    norms_kernel<<<grid, 256, 0, c->stream>>>(c->items.as<float>(), c->n, c->dim, c->ld, c->norms.as<float>(), with_max ? c->maxbits.as<uint32_t>() : nullptr);
+    CK(cudaGetLastError());
+}
+
+void alloc_items(arroy_ctx* c, int metric, uint32_t dim, uint64_t n, const uint32_t* ids) {
+    if (metric < 0 || metric > 3) throw ArgError("unknown metric");
+    if (dim == 0) throw ArgError("dim must be > 0");
+    if (n > 0xffffffffull) throw ArgError("too many items");
+    for (uint64_t i = 1; i < n; ++i) if (ids[i] <= ids[i - 1]) throw ArgError("ids must be strictly ascending");
+    c->staged = false;
+    c->metric = metric; c->dim = dim; c->ld = (dim + 31u) & ~31u; c->n = n;
+    c->ids.assign(ids, ids + n);
+    c->items.ensure(std::max<size_t>(16, (size_t)n * c->ld * 4));
+    c->h0.ensure(std::max<size_t>(16, n * 4));
+    c->h1.ensure(std::max<size_t>(16, n * 4));
+    CK(cudaMemsetAsync(c->h0.p, 0, std::max<size_t>(16, n * 4), c->stream));
+    CK(cudaMemsetAsync(c->h1.p, 0, std::max<size_t>(16, n * 4), c->stream));
+}
+
+// headers as Writer::add_item stores them: D::new_header(vector) (src/writer.rs:388-390)
+void default_headers(arroy_ctx* c) {
+    if (c->metric == COSINE && c->n > 0) {
+        compute_norms(c, false);
+        CK(cudaMemcpyAsync(c->h0.p, c->norms.p, c->n * 4, cudaMemcpyDeviceToDevice, c->stream));
+    }
+}
+
+// ---- RoaringBitmap::serialize_into (roaring 0.10.9, portable format, no run containers) ------
+void roaring_serialize(const uint32_t* ids, size_t n, std::vector<uint8_t>& out) {
+    struct C { uint16_t key; size_t b, e; };
+    std::vector<C> cs;
+    for (size_t i = 0; i < n;) {
+        uint16_t key = (uint16_t)(ids[i] >> 16);
+        size_t j = i + 1;
+        while (j < n && (uint16_t)(ids[j] >> 16) == key) ++j;
+        cs.push_back({key, i, j});
+        i = j;
+    }
+    size_t header = 8 + 8 * cs.size();
+    size_t total = header;
+    for (auto& c : cs) total += (c.e - c.b > 4096) ? 8192 : (c.e - c.b) * 2;
+    size_t base = out.size();
+    out.resize(base + total);
+    uint8_t* w = out.data() + base;
+    auto p32 = [&](size_t off, uint32_t v) { memcpy(w + off, &v, 4); };
+    auto p16 = [&](size_t off, uint16_t v) { memcpy(w + off, &v, 2); };
+    p32(0, 12346u);
+    p32(4, (uint32_t)cs.size());
+    size_t off = 8;
+    for (auto& c : cs) { p16(off, c.key); p16(off + 2, (uint16_t)(c.e - c.b - 1)); off += 4; }
+    uint32_t data_off = (uint32_t)header;
+    for (auto& c : cs) { p32(off, data_off); off += 4; data_off += (c.e - c.b > 4096) ? 8192u : (uint32_t)(c.e - c.b) * 2u; }
+    for (auto& c : cs) {
+        size_t len = c.e - c.b;
+        if (len > 4096) {
+            memset(w + off, 0, 8192);
+            for (size_t i = c.b; i < c.e; ++i) { uint16_t lo = (uint16_t)ids[i]; w[off + (lo >> 3)] |= (uint8_t)(1u << (lo & 7)); }
+            off += 8192;
+        } else {
+            for (size_t i = c.b; i < c.e; ++i) { p16(off, (uint16_t)ids[i]); off += 2; }
+        }
+    }
+}
+
+struct Wave {
+    DevBuf st, frames, recs, perm0, perm1, flags, unit_left, pool, pool_counter, jobs, scratch, active, error, final_ids, keys;
+    void release() {
+        st.release(); frames.release(); recs.release(); perm0.release(); perm1.release(); flags.release(); unit_left.release();
+        pool.release(); pool_counter.release(); jobs.release(); scratch.release(); active.release(); error.release(); final_ids.release(); keys.release();
+    }
+};
+
+}  // namespace
+
+// ================================================================================================
+// forest build
+// ================================================================================================
+namespace {
+
+struct BuiltTree {
+    std::vector<Record> recs;
+    std::vector<uint32_t> final_rows;  // n entries
+};
+
+void build_wave(arroy_ctx* c, uint32_t t0, uint32_t tw, const uint8_t (*seeds)[32], uint32_t K, uint32_t cap_mult,
+                arroy_b200_cancel_fn cancel, void* cancel_arg, std::vector<BuiltTree>& out_trees, std::vector<float>& out_pool,
+                uint32_t& out_pool_stride) {
+    const uint64_t n = c->n;
+    const uint32_t ld = c->ld;
+    Wave W;
+    struct Guard { Wave& w; ~Guard() { w.release(); } } guard{W};
+    const uint32_t units = (uint32_t)((n + SCAN_UNIT - 1) / SCAN_UNIT);
+    const uint64_t leaves_est = n / std::max<uint32_t>(K, 1) + 1;
+    const uint64_t rec_cap64 = std::min<uint64_t>(2 * n + 2, std::max<uint64_t>(64, 8 * leaves_est * cap_mult));
+    const uint32_t rec_cap = (uint32_t)rec_cap64;
+    const uint64_t pool_cap64 = std::min<uint64_t>((uint64_t)tw * (n + 1), (uint64_t)tw * (4 * leaves_est * cap_mult + 2));
+    if (pool_cap64 > 0xfffffff0ull) throw CapacityError("normal pool too large");
+    const uint32_t pool_cap = (uint32_t)pool_cap64;
+    const uint32_t pool_stride = ld + NORMAL_HDR;
+
+    W.st.ensure(sizeof(TreeState) * tw);
+    W.frames.ensure(sizeof(Frame) * (size_t)MAX_DEPTH * tw);
+    W.recs.ensure(sizeof(Record) * (size_t)rec_cap * tw);
+    W.perm0.ensure(4ull * n * tw);
+    W.perm1.ensure(4ull * n * tw);
+    W.flags.ensure(1ull * n * tw);
+    W.unit_left.ensure(4ull * units * tw);
+    W.pool.ensure(4ull * pool_stride * pool_cap);
+    W.pool_counter.ensure(4);
+    W.jobs.ensure(sizeof(Job) * tw);
+    W.active.ensure(4);
+    W.error.ensure(4);
+    W.keys.ensure(32ull * tw);
+    size_t ws_bytes = 13ull * ld * 4;
+    int use_smem = ws_bytes <= 200 * 1024 ? 1 : 0;
+    if (!use_smem) W.scratch.ensure(ws_bytes * tw);
+
+    BuildParams P{};
+    P.items = c->items.as<float>(); P.ih0 = c->h0.as<float>(); P.ih1 = c->h1.as<float>();
+    P.n = (uint32_t)n; P.d = c->dim; P.ld = ld; P.metric = c->metric; P.K = K; P.n_trees = tw;
+    P.st = W.st.as<TreeState>(); P.frames = W.frames.as<Frame>(); P.recs = W.recs.as<Record>(); P.rec_cap = rec_cap;
+    P.perm[0] = W.perm0.as<uint32_t>(); P.perm[1] = W.perm1.as<uint32_t>();
+    P.flags = W.flags.as<uint8_t>(); P.unit_left = W.unit_left.as<uint32_t>(); P.units_per_tree = units;
+    P.pool = W.pool.as<float>(); P.pool_stride = pool_stride; P.pool_cap = pool_cap; P.pool_counter = W.pool_counter.as<uint32_t>();
+    P.jobs = W.jobs.as<Job>(); P.scratch = W.scratch.as<float>(); P.use_smem_ws = use_smem;
+    P.active = W.active.as<uint32_t>(); P.error = W.error.as<int32_t>();
+
+    // tree keys = the 8 little-endian words of each 32-byte seed (StdRng::from_seed)
+    std::vector<uint32_t> keys((size_t)tw * 8);
+    for (uint32_t t = 0; t < tw; ++t)
+        for (int i = 0; i < 8; ++i) {
+            const uint8_t* s = seeds[t0 + t] + 4 * i;
+            keys[(size_t)t * 8 + i] = (uint32_t)s[0] | ((uint32_t)s[1] << 8) | ((uint32_t)s[2] << 16) | ((uint32_t)s[3] << 24);
+        }
+    CK(cudaMemcpyAsync(W.keys.p, keys.data(), keys.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemsetAsync(W.pool_counter.p, 0, 4, c->stream));
+    CK(cudaMemsetAsync(W.error.p, 0, 4, c->stream));
+    CK(cudaMemcpyAsync(W.active.p, &tw, 4, cudaMemcpyHostToDevice, c->stream));
+    init_trees_kernel<<<tw, 256, 0, c->stream>>>(P, W.keys.as<uint32_t>());
+    CK(cudaGetLastError());
+
+    const size_t ctrl_smem = use_smem ? ws_bytes : 0;
+    if (ctrl_smem > 48 * 1024) CK(cudaFuncSetAttribute(control_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctrl_smem));
+    const size_t wsmem = work_smem(ld, (int)tw);
+    if (wsmem > 48 * 1024) CK(cudaFuncSetAttribute(work_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
+    const int work_grid = c->sm_count * 3;
+
+    auto launch_step = [&](cudaStream_t s) {
+        control_kernel<<<tw, CTRL_THREADS, ctrl_smem, s>>>(P);
+        work_kernel<<<work_grid, WORK_THREADS, wsmem, s>>>(P.jobs, (int)tw, P.items, P.ih0, P.d, P.ld, P.metric);
+    };
+
+    const bool use_graph = getenv("ARROY_B200_NO_GRAPH") == nullptr;
+    const int steps_per_batch = 32;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t gexec = nullptr;
+    if (use_graph) {
+        CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+        for (int i = 0; i < steps_per_batch; ++i) launch_step(c->stream);
+        CK(cudaStreamEndCapture(c->stream, &graph));
+        CK(cudaGraphInstantiate(&gexec, graph, 0));
+    }
+    struct GraphGuard { cudaGraph_t& g; cudaGraphExec_t& e; ~GraphGuard() { if (e) cudaGraphExecDestroy(e); if (g) cudaGraphDestroy(g); } } gg{graph, gexec};
+
+    c->pin.ensure(64);
+    volatile uint32_t* h_active = c->pin.as<uint32_t>();
+    volatile int32_t* h_error = reinterpret_cast<volatile int32_t*>(c->pin.as<uint32_t>() + 1);
+    uint64_t steps = 0;
+    // safety net against a stuck state machine (never hit by a correct build): every step each
+    // live tree completes one attempt or one partition
+    const uint64_t max_steps = 40ull * (8 * leaves_est + 64) + 4096;
+    for (;;) {
+        if (steps > max_steps) throw std::runtime_error("forest build did not converge (internal state machine error)");
+        if (use_graph) CK(cudaGraphLaunch(gexec, c->stream));
+        else { for (int i = 0; i < steps_per_batch; ++i) launch_step(c->stream); CK(cudaGetLastError()); }
+        steps += steps_per_batch;
+        CK(cudaMemcpyAsync((void*)h_active, W.active.p, 4, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaMemcpyAsync((void*)h_error, W.error.p, 4, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        if (*h_error != ERR_NONE) {
+            int e = *h_error;
+            throw CapacityError(e == ERR_DEPTH ? "tree deeper than MAX_DEPTH frames" : e == ERR_RECORDS ? "node record table overflow" : "normal pool overflow");
+        }
+        if (*h_active == 0) break;
+        if (cancel && cancel(cancel_arg)) throw Cancelled("The corresponding build process has been cancelled");
+    }
+    c->stats[1] += (double)steps;
+
+    // results: merge the ping-pong id buffers, then bring everything to the host
+    W.final_ids.ensure(4ull * n * tw);
+    finalize_kernel<<<dim3(64, tw), 256, 0, c->stream>>>(P, W.final_ids.as<uint32_t>());
+    CK(cudaGetLastError());
+    std::vector<TreeState> st(tw);
+    uint32_t pool_used = 0;
+    CK(cudaMemcpyAsync(st.data(), W.st.p, sizeof(TreeState) * tw, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(&pool_used, W.pool_counter.p, 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    out_pool.resize((size_t)pool_used * pool_stride);
+    if (pool_used) CK(cudaMemcpyAsync(out_pool.data(), W.pool.p, (size_t)pool_used * pool_stride * 4, cudaMemcpyDeviceToHost, c->stream));
+    out_pool_stride = pool_stride;
+    out_trees.resize(tw);
+    for (uint32_t t = 0; t < tw; ++t) {
+        out_trees[t].recs.resize(st[t].n_recs);
+        out_trees[t].final_rows.resize(n);
+        CK(cudaMemcpyAsync(out_trees[t].recs.data(), W.recs.as<Record>() + (size_t)t * rec_cap, sizeof(Record) * st[t].n_recs, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaMemcpyAsync(out_trees[t].final_rows.data(), W.final_ids.as<uint32_t>() + (size_t)t * n, 4ull * n, cudaMemcpyDeviceToHost, c->stream));
+        c->stats[0] += (double)st[t].scanned;
+        c->stats[2] += (double)st[t].n_splits_tried;
+        c->stats[3] += (double)st[t].n_random;
+    }
+    CK(cudaStreamSynchronize(c->stream));
+}
+
+void do_build(arroy_ctx* c, uint32_t n_trees, const uint8_t (*seeds)[32], const uint32_t* root_ids, uint32_t first_free, uint32_t split_after,
+              arroy_b200_cancel_fn cancel, void* cancel_arg, arroy_b200_node_sink sink, void* sink_arg, uint64_t* out_n_nodes) {
+    require_staged(c);
+    set_device(c);
+    for (auto& s : c->stats) s = 0;
+    const uint32_t K = split_after ? split_after : c->dim;
+    if (c->n <= K) throw ArgError("build_trees needs more items than split_after (a single Descendants node is the caller's job, src/writer.rs:499-501)");
+    if (n_trees == 0) { if (out_n_nodes) *out_n_nodes = 0; return; }
+    if (cancel && cancel(cancel_arg)) throw Cancelled("The corresponding build process has been cancelled");
+
+    // wave size from free memory
+    size_t free_b = 0, total_b = 0;
+    CK(cudaMemGetInfo(&free_b, &total_b));
+    const uint64_t n = c->n;
+    const uint64_t leaves_est = n / K + 1;
+    const uint64_t per_tree = n * (4 + 4 + 1 + 4) + (n / SCAN_UNIT + 1) * 4 + sizeof(Frame) * (uint64_t)MAX_DEPTH + 16ull * 8 * leaves_est +
+                              4ull * (c->ld + NORMAL_HDR) * 4 * leaves_est + 4096;
+    uint64_t max_wave = (uint64_t)(free_b * 0.7) / std::max<uint64_t>(per_tree, 1);
+    if (const char* e = getenv("ARROY_B200_MAX_WAVE")) max_wave = std::min<uint64_t>(max_wave, (uint64_t)atoi(e));
+    max_wave = std::max<uint64_t>(1, std::min<uint64_t>(max_wave, 256));
+
+    CK(cudaEventRecord(c->ev0, c->stream));
+    std::vector<std::vector<BuiltTree>> waves;
+    std::vector<std::vector<float>> pools;
+    std::vector<uint32_t> wave_t0;
+    uint32_t pool_stride = 0;
+    for (uint32_t t0 = 0; t0 < n_trees;) {
+        uint32_t tw = (uint32_t)std::min<uint64_t>(max_wave, n_trees - t0);
+        std::vector<BuiltTree> trees;
+        std::vector<float> pool;
+        uint32_t cap_mult = 1;
+        for (;;) {
+            try { build_wave(c, t0, tw, seeds, K, cap_mult, cancel, cancel_arg, trees, pool, pool_stride); break; }
+            catch (const CapacityError&) { if (cap_mult >= 64) throw; cap_mult *= 4; }
+        }
+        waves.push_back(std::move(trees));
+        pools.push_back(std::move(pool));
+        wave_t0.push_back(t0);
+        t0 += tw;
+    }
+    CK(cudaEventRecord(c->ev1, c->stream));
+    CK(cudaEventSynchronize(c->ev1));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    c->stats[4] = ms;
+
+    // node ids: roots pre-allocated; the rest numbered as a 1-thread rayon pool would (tree tasks
+    // LIFO => last tree first; post-order inside a tree) — SURVEY.md Appendix B.4
+    std::vector<const BuiltTree*> tree_ptr(n_trees);
+    std::vector<const std::vector<float>*> tree_pool(n_trees);
+    for (size_t w = 0; w < waves.size(); ++w)
+        for (size_t i = 0; i < waves[w].size(); ++i) { tree_ptr[wave_t0[w] + i] = &waves[w][i]; tree_pool[wave_t0[w] + i] = &pools[w]; }
+    std::vector<uint64_t> base(n_trees);
+    uint64_t counter = first_free;
+    for (uint32_t k = 0; k < n_trees; ++k) {
+        uint32_t t = n_trees - 1 - k;
+        base[t] = counter;
+        counter += tree_ptr[t]->recs.size() - 1;
+    }
+    if (counter > 0xffffffffull) throw CapacityError("node ids exceed u32 (Error::DatabaseFull)");
+    uint64_t total_nodes = 0;
+    for (uint32_t t = 0; t < n_trees; ++t) total_nodes += tree_ptr[t]->recs.size();
+    if (out_n_nodes) *out_n_nodes = total_nodes;
+    c->stats[6] = (double)total_nodes;
+    if (!sink) return;
+
+    // encode NodeCodec bytes (src/node.rs:229-241); trees in parallel, sink calls serialised
+    const int hdrf = metric_header_floats(c->metric);
+    const uint32_t d = c->dim;
+    std::mutex sink_mu;
+    std::atomic<uint32_t> next_tree{0};
+    std::atomic<int> abort_flag{0};
+    std::string worker_err;
+    auto worker = [&]() {
+        std::vector<uint8_t> buf;
+        std::vector<uint32_t> ids;
+        try {
+            for (;;) {
+                uint32_t t = next_tree.fetch_add(1);
+                if (t >= n_trees || abort_flag.load()) return;
+                const BuiltTree& T = *tree_ptr[t];
+                const std::vector<float>& pool = *tree_pool[t];
+                const uint32_t root_local = (uint32_t)T.recs.size() - 1;
+                auto gid = [&](uint32_t li) { return li == root_local ? root_ids[t] : (uint32_t)(base[t] + li); };
+                for (uint32_t li = 0; li < T.recs.size(); ++li) {
+                    const Record& r = T.recs[li];
+                    buf.clear();
+                    if (r.kind == REC_DESC) {
+                        buf.push_back(1);
+                        ids.resize(r.b);
+                        for (uint32_t i = 0; i < r.b; ++i) ids[i] = c->ids[T.final_rows[r.a + i]];
+                        roaring_serialize(ids.data(), ids.size(), buf);
+                    } else {
+                        buf.push_back(2);
+                        uint32_t l = gid(r.a), rr = gid(r.b);
+                        for (int k = 3; k >= 0; --k) buf.push_back((uint8_t)(l >> (8 * k)));
+                        for (int k = 3; k >= 0; --k) buf.push_back((uint8_t)(rr >> (8 * k)));
+                        if (r.c != NO_SLOT) {
+                            const float* s = pool.data() + (size_t)r.c * pool_stride;
+                            size_t o = buf.size();
+                            buf.resize(o + 4 * hdrf + 4ull * d);
+                            memcpy(buf.data() + o, s, 4 * hdrf);
+                            memcpy(buf.data() + o + 4 * hdrf, s + NORMAL_HDR, 4ull * d);
+                        }
+                    }
+                    std::lock_guard<std::mutex> lk(sink_mu);
+                    if (abort_flag.load()) return;
+                    if (sink(sink_arg, gid(li), buf.data(), buf.size()) != 0) { abort_flag = 1; return; }
+                }
+            }
+        } catch (const std::exception& e) { std::lock_guard<std::mutex> lk(sink_mu); worker_err = e.what(); abort_flag = 2; }
+    };
+    int nthreads = (int)std::min<uint32_t>(n_trees, std::max(1u, std::min(16u, std::thread::hardware_concurrency())));
+    if (c->n < 100000) nthreads = 1;
+    if (nthreads <= 1) worker();
+    else { std::vector<std::thread> th; for (int i = 0; i < nthreads; ++i) th.emplace_back(worker); for (auto& x : th) x.join(); }
+    if (abort_flag.load() == 1) throw Cancelled("node sink aborted the build");
+    if (abort_flag.load() == 2) throw std::runtime_error(worker_err);
+}
+
+// ================================================================================================
+// side_batch / rerank
+// ================================================================================================
+
+void upload_normal(arroy_ctx* c, const float* normal, float h0, float h1) {
+    const uint32_t ld = c->ld;
+    c->s_normal.ensure((size_t)(ld + NORMAL_HDR) * 4);
+    c->pin.ensure(std::max<size_t>(c->pin.cap, (size_t)(ld + NORMAL_HDR) * 4));
+    float* h = c->pin.as<float>();
+    h[0] = h0; h[1] = h1; h[2] = 0.f; h[3] = 0.f;
+    memcpy(h + NORMAL_HDR, normal, 4ull * c->dim);
+    for (uint32_t i = c->dim; i < ld; ++i) h[NORMAL_HDR + i] = 0.f;
+    CK(cudaMemcpyAsync(c->s_normal.p, h, (size_t)(ld + NORMAL_HDR) * 4, cudaMemcpyHostToDevice, c->stream));
+}
+
+void do_side_batch(arroy_ctx* c, const float* normal, float h0, float h1, const uint32_t* rows, uint64_t n_rows, uint8_t* out_side, float* out_margin) {
+    require_staged(c);
+    set_device(c);
+    if (n_rows == 0) return;
+    if (n_rows > 0xffffffffull) throw ArgError("too many rows");
+    for (uint64_t i = 0; i < n_rows; ++i) if (rows[i] >= c->n) throw ArgError("row index out of range");
+    upload_normal(c, normal, h0, h1);
+    CK(cudaStreamSynchronize(c->stream));  // pinned staging buffer is reused below
+    c->s_rows.ensure(n_rows * 4);
+    c->s_flags.ensure(n_rows);
+    c->s_margins.ensure(n_rows * 4);
+    c->s_unit.ensure(((n_rows + SCAN_UNIT - 1) / SCAN_UNIT) * 4);
+    c->s_job.ensure(sizeof(Job));
+    CK(cudaMemcpyAsync(c->s_rows.p, rows, n_rows * 4, cudaMemcpyHostToDevice, c->stream));
+    Job jb{};
+    jb.kind = JOB_SCAN; jb.len = (uint32_t)n_rows; jb.rows = c->s_rows.as<uint32_t>(); jb.normal = c->s_normal.as<float>();
+    jb.flags = c->s_flags.as<uint8_t>(); jb.margins = out_margin ? c->s_margins.as<float>() : nullptr; jb.unit_left = c->s_unit.as<uint32_t>();
+    CK(cudaMemcpyAsync(c->s_job.p, &jb, sizeof(Job), cudaMemcpyHostToDevice, c->stream));
+    uint64_t units = (n_rows + SCAN_UNIT - 1) / SCAN_UNIT;
+    int grid = (int)std::min<uint64_t>(units, (uint64_t)c->sm_count * 3);
+    launch_work(c, c->s_job.as<Job>(), 1, grid);
+    CK(cudaMemcpyAsync(out_side, c->s_flags.p, n_rows, cudaMemcpyDeviceToHost, c->stream));
+    if (out_margin) CK(cudaMemcpyAsync(out_margin, c->s_margins.p, n_rows * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+}
+
+void do_rerank_batch(arroy_ctx* c, uint32_t nq, const float* queries, const float* qh0, const float* /*qh1*/, const uint32_t* rows,
+                     const uint64_t* offsets, uint32_t k, uint32_t* out_rows, float* out_dist, uint32_t* out_len) {
+    require_staged(c);
+    set_device(c);
+    if (nq == 0) return;
+    if (k == 0) { for (uint32_t q = 0; q < nq; ++q) out_len[q] = 0; return; }
+    if (k > TOPK_CAP / 2) throw ArgError("k larger than the top-k buffer (TOPK_CAP/2 = 2048)");
+    if (nq > 65535) throw ArgError("at most 65535 queries per rerank_batch call");
+    const uint64_t total = offsets[nq];
+    for (uint32_t q = 0; q < nq; ++q) {
+        if (offsets[q + 1] < offsets[q]) throw ArgError("row_offsets must be non-decreasing");
+        if (offsets[q + 1] - offsets[q] > 0xffffffffull) throw ArgError("too many candidates for one query");
+    }
+    for (uint64_t i = 0; i < total; ++i) if (rows[i] >= c->n) throw ArgError("row index out of range");
+    const uint32_t ld = c->ld;
+    c->s_q.ensure((size_t)nq * ld * 4);
+    c->s_qh0.ensure((size_t)nq * 4);
+    c->s_off.ensure((size_t)(nq + 1) * 8);
+    c->s_rows.ensure(std::max<uint64_t>(total, 1) * 4);
+    c->s_keys.ensure(std::max<uint64_t>(total, 1) * 8);
+    c->s_dists.ensure(std::max<uint64_t>(total, 1) * 4);
+    c->s_orows.ensure((size_t)nq * k * 4);
+    c->s_odist.ensure((size_t)nq * k * 4);
+    c->s_olen.ensure((size_t)nq * 4);
+    CK(cudaMemsetAsync(c->s_q.p, 0, (size_t)nq * ld * 4, c->stream));
+    CK(cudaMemcpy2DAsync(c->s_q.p, (size_t)ld * 4, queries, (size_t)c->dim * 4, (size_t)c->dim * 4, nq, cudaMemcpyHostToDevice, c->stream));
+    if (qh0) CK(cudaMemcpyAsync(c->s_qh0.p, qh0, (size_t)nq * 4, cudaMemcpyHostToDevice, c->stream));
+    else CK(cudaMemsetAsync(c->s_qh0.p, 0, (size_t)nq * 4, c->stream));
+    CK(cudaMemcpyAsync(c->s_off.p, offsets, (size_t)(nq + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    if (total) CK(cudaMemcpyAsync(c->s_rows.p, rows, total * 4, cudaMemcpyHostToDevice, c->stream));
+    uint64_t max_c = 0;
+    for (uint32_t q = 0; q < nq; ++q) max_c = std::max<uint64_t>(max_c, offsets[q + 1] - offsets[q]);
+    if (total) {
+        uint64_t per = c->metric == MANHATTAN ? 32 : 4;
+        uint64_t warps = (max_c + per - 1) / per;
+        uint32_t gx = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((warps + 7) / 8, std::max<uint64_t>(1, ((uint64_t)c->sm_count * 8) / std::min<uint32_t>(nq, c->sm_count * 8u))));
+        dim3 grid(gx, nq);
+        distance_kernel<<<grid, 256, 0, c->stream>>>(c->items.as<float>(), c->h0.as<float>(), c->dim, ld, c->metric, c->s_q.as<float>(), c->s_qh0.as<float>(), nq,
+                                                     c->s_rows.as<uint32_t>(), c->s_off.as<uint64_t>(), c->s_dists.as<float>(), c->s_keys.as<unsigned long long>());
+        CK(cudaGetLastError());
+    }
+    topk_kernel<<<nq, TOPK_THREADS, 0, c->stream>>>(c->s_keys.as<unsigned long long>(), c->s_dists.as<float>(), c->s_rows.as<uint32_t>(), c->s_off.as<uint64_t>(), k, c->metric,
+                                                    c->s_orows.as<uint32_t>(), c->s_odist.as<float>(), c->s_olen.as<uint32_t>());
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out_rows, c->s_orows.p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(out_dist, c->s_odist.p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(out_len, c->s_olen.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+}
+
+// single-CTA create_split over a host row list (exposes D::create_split for parity tests and for
+// hosts that keep the DFS on their side)
+__global__ void __launch_bounds__(CTRL_THREADS, 1) create_split_kernel(BuildParams P, const uint32_t* rows, uint32_t len, const uint32_t* key8, uint64_t pos, float* slot, uint64_t* out_pos) {
+    extern __shared__ __align__(16) unsigned char cs_smem[];
+    __shared__ TwoMeansShared TM;
+    __shared__ Rng rng;
+    float* ws = P.use_smem_ws ? reinterpret_cast<float*>(cs_smem) : P.scratch;
+    if (threadIdx.x == 0) rng.init(key8, pos);
+    __syncthreads();
+    create_split_cta(P, rng, rows, len, ws, TM, slot);
+    if (threadIdx.x == 0) *out_pos = rng.pos;
+}
+
+template <class F>
+int32_t guarded(arroy_ctx* c, F&& f) {
+    if (!c) return ARROY_B200_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(c->mu);
+    try { f(); return ARROY_B200_OK; }
+    catch (const CudaError& e) { c->err = e.what(); cudaGetLastError(); return ARROY_B200_ERR_CUDA; }
+    catch (const ArgError& e) { c->err = e.what(); return ARROY_B200_ERR_INVALID; }
+    catch (const CapacityError& e) { c->err = e.what(); return ARROY_B200_ERR_CAPACITY; }
+    catch (const Cancelled& e) { c->err = e.what(); return ARROY_B200_ERR_CANCELLED; }
+    catch (const NotStaged& e) { c->err = e.what(); return ARROY_B200_ERR_NOT_STAGED; }
+    catch (const std::exception& e) { c->err = std::string("internal error: ") + e.what(); return ARROY_B200_ERR_INTERNAL; }
+    catch (...) { c->err = "internal error: unknown exception"; return ARROY_B200_ERR_INTERNAL; }
+}
+
+}  // namespace
+
+// ================================================================================================
+// extern "C"
+// ================================================================================================
+extern "C" {
+
+const char* arroy_b200_version(void) { return "arroy_b200 0.1.0 (sm_100a)"; }
+
+int32_t arroy_b200_create(int32_t device, arroy_ctx** out) {
+    if (!out) return ARROY_B200_ERR_INVALID;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count) { cudaGetLastError(); return ARROY_B200_ERR_CUDA; }
+    arroy_ctx* c = nullptr;
+    try {
+        c = new arroy_ctx();
+        c->device = device;
+        CK(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, device));
+        c->sm_count = prop.multiProcessorCount;
+        CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        CK(cudaEventCreate(&c->ev0));
+        CK(cudaEventCreate(&c->ev1));
+        // fail loudly if the kernels were not built for this device
+        cudaFuncAttributes fa;
+        CK(cudaFuncGetAttributes(&fa, work_kernel));
+    } catch (const std::exception& e) {
+        fprintf(stderr, "arroy_b200_create: %s\n", e.what());
+        delete c;
+        cudaGetLastError();
+        return ARROY_B200_ERR_CUDA;
+    }
+    *out = c;
+    return ARROY_B200_OK;
+}
+
+void arroy_b200_destroy(arroy_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    DevBuf* bufs[] = {&c->items, &c->h0, &c->h1, &c->norms, &c->maxbits, &c->s_rows, &c->s_flags, &c->s_margins, &c->s_normal, &c->s_unit, &c->s_job,
+                      &c->s_keys, &c->s_dists, &c->s_q, &c->s_qh0, &c->s_off, &c->s_orows, &c->s_odist, &c->s_olen, &c->s_misc};
+    for (auto* b : bufs) b->release();
+    c->pin.release();
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+const char* arroy_b200_last_error(arroy_ctx* c) { return c ? c->err.c_str() : "null context"; }
+
+int32_t arroy_b200_stage_items(arroy_ctx* c, int32_t metric, uint32_t dim, uint64_t n, const uint32_t* ids, const uint8_t* const* leaf_values) {
+    return guarded(c, [&] {
+        set_device(c);
+        if (n && (!ids || !leaf_values)) throw ArgError("null ids / leaf_values");
+        alloc_items(c, metric, dim, n, ids);
+        const uint32_t ld = c->ld;
+        const int hf = metric_header_floats(metric);
+        std::vector<float> h0(n), h1(n, 0.f);
+        // decode the unaligned LMDB values into pinned chunks: [tag][Header][dim x f32]
+        const size_t chunk_rows = std::max<size_t>(1, (32u << 20) / ((size_t)ld * 4));
+        c->pin.ensure(2 * chunk_rows * ld * 4);
+        float* bufs[2] = {c->pin.as<float>(), c->pin.as<float>() + chunk_rows * ld};
+        cudaEvent_t done[2];
+        CK(cudaEventCreate(&done[0])); CK(cudaEventCreate(&done[1]));
+        bool used[2] = {false, false};
+        int which = 0;
+        for (uint64_t r0 = 0; r0 < n; r0 += chunk_rows, which ^= 1) {
+            uint64_t rows = std::min<uint64_t>(chunk_rows, n - r0);
+            if (used[which]) CK(cudaEventSynchronize(done[which]));
+            float* b = bufs[which];
+            for (uint64_t i = 0; i < rows; ++i) {
+                const uint8_t* v = leaf_values[r0 + i];
+                if (!v || v[0] != 0) throw ArgError("leaf value does not start with the Leaf tag 0x00");
+                memcpy(&h0[r0 + i], v + 1, 4);
+                if (hf == 2) memcpy(&h1[r0 + i], v + 5, 4);
+                memcpy(b + i * ld, v + 1 + 4 * hf, 4ull * dim);
+                for (uint32_t k = dim; k < ld; ++k) b[i * ld + k] = 0.f;
+            }
+            CK(cudaMemcpyAsync(c->items.as<float>() + r0 * ld, b, rows * ld * 4, cudaMemcpyHostToDevice, c->stream));
+            CK(cudaEventRecord(done[which], c->stream));
+            used[which] = true;
+        }
+        if (n) {
+            CK(cudaMemcpyAsync(c->h0.p, h0.data(), n * 4, cudaMemcpyHostToDevice, c->stream));
+            CK(cudaMemcpyAsync(c->h1.p, h1.data(), n * 4, cudaMemcpyHostToDevice, c->stream));
+        }
+        CK(cudaStreamSynchronize(c->stream));
+        cudaEventDestroy(done[0]); cudaEventDestroy(done[1]);
+        c->staged = true;
+    });
+}
+
+int32_t arroy_b200_stage_items_flat(arroy_ctx* c, int32_t metric, uint32_t dim, uint64_t n, const uint32_t* ids, const float* vectors, const float* hdr0, const float* hdr1) {
+    return guarded(c, [&] {
+        set_device(c);
+        if (n && (!ids || !vectors)) throw ArgError("null ids / vectors");
+        alloc_items(c, metric, dim, n, ids);
+        if (n) {
+            if (c->ld != dim) CK(cudaMemsetAsync(c->items.p, 0, (size_t)n * c->ld * 4, c->stream));
+            CK(cudaMemcpy2DAsync(c->items.p, (size_t)c->ld * 4, vectors, (size_t)dim * 4, (size_t)dim * 4, n, cudaMemcpyHostToDevice, c->stream));
+            if (hdr0) CK(cudaMemcpyAsync(c->h0.p, hdr0, n * 4, cudaMemcpyHostToDevice, c->stream));
+            else default_headers(c);
+            if (hdr1) CK(cudaMemcpyAsync(c->h1.p, hdr1, n * 4, cudaMemcpyHostToDevice, c->stream));
+        }
+        CK(cudaStreamSynchronize(c->stream));
+        c->staged = true;
+    });
+}
+
+int32_t arroy_b200_stage_items_device(arroy_ctx* c, int32_t metric, uint32_t dim, uint64_t n, const uint32_t* ids, const void* device_vectors) {
+    return guarded(c, [&] {
+        set_device(c);
+        if (n && (!ids || !device_vectors)) throw ArgError("null ids / vectors");
+        alloc_items(c, metric, dim, n, ids);
+        if (n) {
+            if (c->ld != dim) CK(cudaMemsetAsync(c->items.p, 0, (size_t)n * c->ld * 4, c->stream));
+            CK(cudaMemcpy2DAsync(c->items.p, (size_t)c->ld * 4, device_vectors, (size_t)dim * 4, (size_t)dim * 4, n, cudaMemcpyDeviceToDevice, c->stream));
+            default_headers(c);
+        }
+        CK(cudaStreamSynchronize(c->stream));
+        c->staged = true;
+    });
+}
+
+int32_t arroy_b200_item_headers(arroy_ctx* c, float* out_hdr0, float* out_hdr1) {
+    return guarded(c, [&] {
+        require_staged(c); set_device(c);
+        if (c->n == 0) return;
+        if (out_hdr0) CK(cudaMemcpyAsync(out_hdr0, c->h0.p, c->n * 4, cudaMemcpyDeviceToHost, c->stream));
+        if (out_hdr1) CK(cudaMemcpyAsync(out_hdr1, c->h1.p, c->n * 4, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    });
+}
+
+int32_t arroy_b200_dot_preprocess(arroy_ctx* c, float* out_extra_dim, float* out_norm) {
+    return guarded(c, [&] {
+        require_staged(c); set_device(c);
+        if (c->metric != DOT_PRODUCT || c->n == 0) return;  // Distance::preprocess default: no-op (src/distance/mod.rs:112-119)
+        compute_norms(c, true);
+        dot_header_kernel<<<(unsigned)((c->n + 255) / 256), 256, 0, c->stream>>>(c->norms.as<float>(), c->n, c->maxbits.as<uint32_t>(), c->h0.as<float>(), c->h1.as<float>());
+        CK(cudaGetLastError());
+        if (out_extra_dim) CK(cudaMemcpyAsync(out_extra_dim, c->h0.p, c->n * 4, cudaMemcpyDeviceToHost, c->stream));
+        if (out_norm) CK(cudaMemcpyAsync(out_norm, c->h1.p, c->n * 4, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    });
+}
+
+int32_t arroy_b200_side_batch(arroy_ctx* c, const float* normal, float hdr0, float hdr1, const uint32_t* rows, uint64_t n_rows, uint8_t* out_side, float* out_margin) {
+    return guarded(c, [&] {
+        if (n_rows && (!normal || !rows || !out_side)) throw ArgError("null argument");
+        do_side_batch(c, normal, hdr0, hdr1, rows, n_rows, out_side, out_margin);
+    });
+}
+
+int32_t arroy_b200_create_split(arroy_ctx* c, const uint32_t rng_key[8], uint64_t* rng_word_pos, const uint32_t* rows, uint64_t n_rows, float* out_normal, float* out_hdr) {
+    return guarded(c, [&] {
+        require_staged(c); set_device(c);
+        if (!rng_key || !rng_word_pos || !rows || !out_normal || !out_hdr) throw ArgError("null argument");
+        if (n_rows < 2 || n_rows > 0xffffffffull) throw ArgError("create_split needs at least two rows");
+        for (uint64_t i = 0; i < n_rows; ++i) { if (rows[i] >= c->n) throw ArgError("row index out of range"); if (i && rows[i] <= rows[i - 1]) throw ArgError("rows must be ascending"); }
+        const uint32_t ld = c->ld;
+        c->s_rows.ensure(n_rows * 4);
+        c->s_normal.ensure((size_t)(ld + NORMAL_HDR) * 4);
+        c->s_misc.ensure(64 + 13ull * ld * 4);
+        CK(cudaMemcpyAsync(c->s_rows.p, rows, n_rows * 4, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(c->s_misc.p, rng_key, 32, cudaMemcpyHostToDevice, c->stream));
+        BuildParams P{};
+        P.items = c->items.as<float>(); P.ih0 = c->h0.as<float>(); P.ih1 = c->h1.as<float>();
+        P.n = (uint32_t)c->n; P.d = c->dim; P.ld = ld; P.metric = c->metric;
+        size_t ws_bytes = 13ull * ld * 4;
+        P.use_smem_ws = ws_bytes <= 200 * 1024;
+        P.scratch = reinterpret_cast<float*>(c->s_misc.as<uint8_t>() + 64);
+        size_t smem = P.use_smem_ws ? ws_bytes : 0;
+        if (smem > 48 * 1024) CK(cudaFuncSetAttribute(create_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        create_split_kernel<<<1, CTRL_THREADS, smem, c->stream>>>(P, c->s_rows.as<uint32_t>(), (uint32_t)n_rows, c->s_misc.as<uint32_t>(), *rng_word_pos,
+                                                                  c->s_normal.as<float>(), reinterpret_cast<uint64_t*>(c->s_misc.as<uint8_t>() + 32));
+        CK(cudaGetLastError());
+        std::vector<float> slot(ld + NORMAL_HDR);
+        uint64_t new_pos = 0;
+        CK(cudaMemcpyAsync(slot.data(), c->s_normal.p, slot.size() * 4, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaMemcpyAsync(&new_pos, c->s_misc.as<uint8_t>() + 32, 8, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        memcpy(out_normal, slot.data() + NORMAL_HDR, 4ull * c->dim);
+        out_hdr[0] = slot[0]; out_hdr[1] = slot[1];
+        *rng_word_pos = new_pos;
+    });
+}
+
+int32_t arroy_b200_build_trees(arroy_ctx* c, uint32_t n_trees, const uint8_t (*tree_seeds)[32], const uint32_t* root_ids, uint32_t first_free_node_id,
+                               uint32_t split_after, arroy_b200_cancel_fn cancel, void* cancel_arg, arroy_b200_node_sink sink, void* sink_arg, uint64_t* out_n_nodes) {
+    return guarded(c, [&] {
+        if (n_trees && (!tree_seeds || !root_ids)) throw ArgError("null seeds / root ids");
+        do_build(c, n_trees, tree_seeds, root_ids, first_free_node_id, split_after, cancel, cancel_arg, sink, sink_arg, out_n_nodes);
+    });
+}
+
+int32_t arroy_b200_build_stats(arroy_ctx* c, double stats[8]) {
+    return guarded(c, [&] { for (int i = 0; i < 8; ++i) stats[i] = c->stats[i]; });
+}
+
+int32_t arroy_b200_rerank(arroy_ctx* c, const float* query, float qhdr0, float qhdr1, const uint32_t* rows, uint64_t n_rows, uint32_t k,
+                          uint32_t* out_rows, float* out_dist, uint32_t* out_len) {
+    return guarded(c, [&] {
+        if (!query || (n_rows && !rows) || !out_len) throw ArgError("null argument");
+        uint64_t offs[2] = {0, n_rows};
+        do_rerank_batch(c, 1, query, &qhdr0, &qhdr1, rows, offs, k, out_rows, out_dist, out_len);
+    });
+}
+
+int32_t arroy_b200_rerank_batch(arroy_ctx* c, uint32_t nq, const float* queries, const float* qhdr0, const float* qhdr1, const uint32_t* rows,
+                                const uint64_t* row_offsets, uint32_t k, uint32_t* out_rows, float* out_dist, uint32_t* out_len) {
+    return guarded(c, [&] {
+        if (nq && (!queries || !row_offsets || !out_len)) throw ArgError("null argument");
+        do_rerank_batch(c, nq, queries, qhdr0, qhdr1, rows, row_offsets, k, out_rows, out_dist, out_len);
+    });
+}
+
+int32_t arroy_b200_synth_device(arroy_ctx* c, const uint8_t seed[32], uint32_t dim, uint64_t row0, uint64_t rows, float centre, void* device_out) {
+    return guarded(c, [&] {
+        set_device(c);
+        if (!seed || !device_out) throw ArgError("null argument");
+        uint32_t key[8];
+        for (int i = 0; i < 8; ++i) key[i] = (uint32_t)seed[4 * i] | ((uint32_t)seed[4 * i + 1] << 8) | ((uint32_t)seed[4 * i + 2] << 16) | ((uint32_t)seed[4 * i + 3] << 24);
+        c->s_misc.ensure(64);
+        CK(cudaMemcpyAsync(c->s_misc.p, key, 32, cudaMemcpyHostToDevice, c->stream));
+        uint64_t blocks = (rows * dim + 15) / 16 + 1;
+        int grid = (int)std::min<uint64_t>((blocks + 255) / 256, (uint64_t)c->sm_count * 32);
+        synth_kernel<<<std::max(grid, 1), 256, 0, c->stream>>>(c->s_misc.as<uint32_t>(), dim, row0, rows, centre, static_cast<float*>(device_out));
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(c->stream));
+    });
+}
+
+int32_t arroy_b200_time_scan(arroy_ctx* c, const float* normal, float hdr0, float hdr1, const uint32_t* rows, uint64_t n_rows, int32_t variant, int32_t iters,
+                             int32_t flush_l2, float* out_ms_avg, uint64_t* out_left_count) {
+    return guarded(c, [&] {
+        require_staged(c); set_device(c);
+        (void)variant;
+        if (!normal || !out_ms_avg || n_rows == 0 || n_rows > c->n || iters <= 0) throw ArgError("bad argument");
+        upload_normal(c, normal, hdr0, hdr1);
+        CK(cudaStreamSynchronize(c->stream));
+        c->s_flags.ensure(n_rows);
+        uint64_t units = (n_rows + SCAN_UNIT - 1) / SCAN_UNIT;
+        c->s_unit.ensure(units * 4);
+        c->s_job.ensure(sizeof(Job));
+        Job jb{};
+        jb.kind = JOB_SCAN; jb.len = (uint32_t)n_rows; jb.rows = nullptr; jb.normal = c->s_normal.as<float>();
+        jb.flags = c->s_flags.as<uint8_t>(); jb.margins = nullptr; jb.unit_left = c->s_unit.as<uint32_t>();
+        if (rows) {
+            c->s_rows.ensure(n_rows * 4);
+            CK(cudaMemcpyAsync(c->s_rows.p, rows, n_rows * 4, cudaMemcpyHostToDevice, c->stream));
+            jb.rows = c->s_rows.as<uint32_t>();
+        }
+        CK(cudaMemcpyAsync(c->s_job.p, &jb, sizeof(Job), cudaMemcpyHostToDevice, c->stream));
+        int grid = (int)std::min<uint64_t>(units, (uint64_t)c->sm_count * 3);
+        const size_t flush_bytes = 256ull << 20;
+        if (flush_l2) c->s_misc.ensure(flush_bytes);
+        launch_work(c, c->s_job.as<Job>(), 1, grid);  // warm-up
+        CK(cudaStreamSynchronize(c->stream));
+        double total_ms = 0;
+        for (int it = 0; it < iters; ++it) {
+            if (flush_l2) CK(cudaMemsetAsync(c->s_misc.p, it & 0xff, flush_bytes, c->stream));
+            CK(cudaEventRecord(c->ev0, c->stream));
+            launch_work(c, c->s_job.as<Job>(), 1, grid);
+            CK(cudaEventRecord(c->ev1, c->stream));
+            CK(cudaEventSynchronize(c->ev1));
+            float ms = 0;
+            CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+            total_ms += ms;
+        }
+        *out_ms_avg = (float)(total_ms / iters);
+        if (out_left_count) {
+            std::vector<uint32_t> ul(units);
+            CK(cudaMemcpyAsync(ul.data(), c->s_unit.p, units * 4, cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaStreamSynchronize(c->stream));
+            uint64_t s = 0;
+            for (auto v : ul) s += v;
+            *out_left_count = s;
+        }
+    });
+}
+
+int32_t arroy_b200_device_ptrs(arroy_ctx* c, void* out[3], uint32_t* out_ld) {
+    return guarded(c, [&] {
+        require_staged(c);
+        out[0] = c->items.p; out[1] = c->h0.p; out[2] = c->h1.p;
+        if (out_ld) *out_ld = c->ld;
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,464 @@
+// build.cuh — device-resident forest build.
+//
+// Restates the per-tree task of the reference (src/writer.rs:660-739 -> make_tree_in_file
+// :1167-1261) as a device state machine. Each tree owns ONE StdRng stream that is consumed in
+// depth-first order (left subtree fully before right, :1235-1254) and the number of draws is
+// data dependent (retries :1193-1216, rejection sampling, random fallback :1220-1227), so a
+// tree is a sequential chain of "attempts" (create_split + side() scan). Concurrency comes from
+// running all trees of a wave side by side: every device step runs
+//     control_kernel   one CTA per tree: finish the previous attempt (count Lefts, imbalance
+//                      test, partition), advance the DFS, draw the RNG, run two_means
+//                      (src/distance/mod.rs:126-171) and create_split, post one scan job;
+//     work_kernel      all SMs: the side() scans (and wide partitions) of all trees.
+// Node records come out tree-local and post-order; the host turns them into NodeCodec bytes.
+#pragma once
+#include "kernels.cuh"
+
+namespace ab {
+
+constexpr int CTRL_THREADS = 256;
+constexpr int MAX_DEPTH = 4096;          // DFS frames per tree
+constexpr uint32_t INLINE_PART_MAX = 8192;  // nodes up to this size are partitioned by the control CTA
+constexpr uint32_t NO_SLOT = 0xffffffffu;
+
+enum : int { PH_START = 0, PH_AWAIT_SCAN = 1, PH_AWAIT_PART = 2, PH_DONE = 3 };
+enum : int { REC_DESC = 1, REC_SPLIT = 2 };
+enum : int { ERR_NONE = 0, ERR_DEPTH = 1, ERR_RECORDS = 2, ERR_POOL = 3 };
+
+struct Frame {
+    uint32_t start, len;     // segment of the tree's id permutation
+    uint32_t left_len;       // number of ids that went Left (valid from stage 1)
+    uint32_t left_id;        // local id of the finished left child (stage 3)
+    uint32_t slot;           // normal pool slot, NO_SLOT = random split ("normal: none")
+    uint8_t parity;          // which of the two ping-pong id buffers holds this node's ids
+    uint8_t stage;           // 0 = new, 1 = split decided + partitioned, 2 = left in progress, 3 = right in progress
+    uint16_t pad;
+};
+
+struct Record {  // tree-local node, in post-order; the root is the last record
+    uint32_t kind;
+    uint32_t a, b, c;  // DESC: start, len, parity   SPLIT: left local id, right local id, slot
+};
+
+struct TreeState {
+    uint32_t key[8];
+    uint64_t pos;            // StdRng words consumed
+    int32_t phase;
+    int32_t sp;              // top frame index
+    int32_t attempts_left;
+    uint32_t cur_slot;       // pool slot holding the current attempt's normal (NO_SLOT = none reserved)
+    uint32_t n_recs;
+    uint32_t n_splits_tried, n_random;
+    uint32_t pad;
+    uint64_t scanned;        // rows that went through side()
+};
+
+struct BuildParams {
+    const float* items; const float* ih0; const float* ih1;
+    uint32_t n, d, ld; int32_t metric; uint32_t K;
+    uint32_t n_trees;
+    TreeState* st; Frame* frames; Record* recs; uint32_t rec_cap;
+    uint32_t* perm[2];       // n_trees x n each
+    uint8_t* flags;          // n_trees x n
+    uint32_t* unit_left;     // n_trees x units_per_tree
+    uint32_t units_per_tree;
+    float* pool; uint32_t pool_stride; uint32_t pool_cap; uint32_t* pool_counter;
+    Job* jobs;
+    float* scratch;          // n_trees x 13 x ld (two_means workspace when it does not fit in smem)
+    int32_t use_smem_ws;
+    uint32_t* active;        // trees not yet done
+    int32_t* error;
+};
+
+__device__ __forceinline__ double split_imbalance_dev(uint32_t l, uint32_t r) {  // src/writer.rs:1348-1353
+    double ls = (double)l, rs = (double)r;
+    double f = ls / (ls + rs + 2.220446049250313e-16);
+    double g = 1.0 - f;
+    return f > g ? f : g;
+}
+
+// ---- two_means + create_split on one CTA ----------------------------------------------------
+// ws: 13 vectors of ld floats: ws[0]=p, ws[1]=q, ws[2..11]=the ten sampled k, ws[12]=normal/bias terms.
+struct TwoMeansShared {
+    uint32_t rows[12];
+    float h0[12], h1[12];
+    float res[4];
+    float php[2], phq[2];   // headers of p and q
+};
+
+__device__ __forceinline__ float nbd_warp(int metric, const float* p, float ph0, float ph1, const float* k, float kh0, float kh1, int d) {
+    // D::non_built_distance — mod.rs:54-56 (= built_distance) except dot_product.rs:58-70
+    if (metric == EUCLIDEAN) return exact_warp<true>(p, k, d);
+    if (metric == MANHATTAN) {
+        float s = 0.0f;
+        if ((threadIdx.x & 31) == 0) for (int i = 0; i < d; ++i) s = __fadd_rn(s, fabsf(__fsub_rn(p[i], k[i])));
+        return __shfl_sync(0xffffffffu, s, 0);
+    }
+    float pq = exact_warp<false>(p, k, d);
+    if (metric == COSINE) return built_finish(COSINE, pq, ph0, kh0);
+    // DOT_PRODUCT
+    float pp = ph1, qq = kh1;
+    pq = __fadd_rn(pq, __fmul_rn(ph0, kh0));
+    float ppqq = __fmul_rn(pp, qq);
+    if (ppqq >= 1.17549435e-38f) return __fsub_rn(2.0f, __fdiv_rn(__fmul_rn(2.0f, pq), __fsqrt_rn(ppqq)));
+    return 2.0f;
+}
+__device__ __forceinline__ float norm_leaf_warp(int metric, const float* v, float h0, int d) {
+    float dot = exact_warp<false>(v, v, d);
+    if (metric == DOT_PRODUCT) return __fsqrt_rn(__fadd_rn(dot, __fmul_rn(h0, h0)));  // dot_product.rs:72-75
+    return __fsqrt_rn(dot);                                                              // mod.rs:70-72
+}
+// D::init — cosine.rs:69-71, dot_product.rs:94-96 (no-op otherwise). Called by one warp.
+__device__ __forceinline__ void init_warp(int metric, const float* v, float* hdr, int d) {
+    if (metric == COSINE) { float x = __fsqrt_rn(exact_warp<false>(v, v, d)); if ((threadIdx.x & 31) == 0) hdr[0] = x; }
+    else if (metric == DOT_PRODUCT) { float x = exact_warp<false>(v, v, d); if ((threadIdx.x & 31) == 0) hdr[1] = x; }
+}
+
+// Draws the RNG exactly like choose_two + 10 x choose (src/parallel.rs:342-367), runs
+// two_means and the metric's create_split, writes the normal into `slot_ptr`
+// ([h0,h1,0,0,v[ld]]). seg = the node's ascending id list.
+__device__ void create_split_cta(const BuildParams& P, Rng& rng /* thread 0 only */, const uint32_t* seg, uint32_t len,
+                                 float* ws, TwoMeansShared& S, float* slot_ptr) {
+    const int d = (int)P.d, ld = (int)P.ld, metric = P.metric;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const bool cosine = (metric == COSINE || metric == DOT_PRODUCT);
+    if (tid == 0) {  // all RNG draws of the attempt first: they do not depend on the data
+        uint32_t a, b;
+        rng.sample2(len, a, b);
+        S.rows[0] = a; S.rows[1] = b;
+        for (int it = 0; it < 10; ++it) S.rows[2 + it] = rng.gen_range_incl(0, len - 1);
+    }
+    __syncthreads();
+    uint32_t my_row = 0;
+    if (tid < 12) my_row = seg[S.rows[tid]];  // RoaringBitmap::select(rank) on the ascending id list
+    __syncthreads();
+    if (tid < 12) S.rows[tid] = my_row;
+    __syncthreads();
+    {   // gather the 12 rows (float4, all loads independent)
+        const int l4 = ld >> 2;
+        for (int i = tid; i < 12 * l4; i += blockDim.x) {
+            int j = i / l4, c = i - j * l4;
+            reinterpret_cast<float4*>(ws + (size_t)j * ld)[c] = __ldg(reinterpret_cast<const float4*>(P.items + (size_t)S.rows[j] * ld) + c);
+        }
+        if (tid < 12) { S.h0[tid] = P.ih0 ? P.ih0[S.rows[tid]] : 0.f; S.h1[tid] = P.ih1 ? P.ih1[S.rows[tid]] : 0.f; }
+    }
+    __syncthreads();
+    float* p = ws; float* q = ws + ld;
+    if (tid == 0) { S.php[0] = S.h0[0]; S.php[1] = S.h1[0]; S.phq[0] = S.h0[1]; S.phq[1] = S.h1[1]; }
+    __syncthreads();
+    if (cosine) {  // D::normalize(p), D::normalize(q) — mod.rs:76-82, dot_product.rs:85-92
+        if (warp == 0) { float x = norm_leaf_warp(metric, p, S.php[0], d); if (lane == 0) S.res[0] = x; }
+        if (warp == 1) { float x = norm_leaf_warp(metric, q, S.phq[0], d); if (lane == 0) S.res[1] = x; }
+        __syncthreads();
+        float np = S.res[0], nq = S.res[1];
+        if (np > 0.0f) for (int i = tid; i < d; i += blockDim.x) p[i] = __fdiv_rn(p[i], np);
+        if (nq > 0.0f) for (int i = tid; i < d; i += blockDim.x) q[i] = __fdiv_rn(q[i], nq);
+        __syncthreads();
+        if (tid == 0 && metric == DOT_PRODUCT) {
+            if (np > 0.0f) S.php[0] = __fdiv_rn(S.php[0], np);
+            if (nq > 0.0f) S.phq[0] = __fdiv_rn(S.phq[0], nq);
+        }
+    }
+    if (warp == 0) init_warp(metric, p, S.php, d);
+    if (warp == 1) init_warp(metric, q, S.phq, d);
+    __syncthreads();
+    float ic = 1.0f, jc = 1.0f;
+    for (int it = 0; it < 10; ++it) {
+        const float* k = ws + (size_t)(2 + it) * ld;
+        const float kh0 = S.h0[2 + it], kh1 = S.h1[2 + it];
+        if (warp == 0) { float x = nbd_warp(metric, p, S.php[0], S.php[1], k, kh0, kh1, d); if (lane == 0) S.res[0] = x; }
+        if (warp == 1) { float x = nbd_warp(metric, q, S.phq[0], S.phq[1], k, kh0, kh1, d); if (lane == 0) S.res[1] = x; }
+        if (warp == 2) { float x = cosine ? norm_leaf_warp(metric, k, kh0, d) : 1.0f; if (lane == 0) S.res[2] = x; }
+        __syncthreads();
+        const float di = __fmul_rn(ic, S.res[0]), dj = __fmul_rn(jc, S.res[1]), norm = S.res[2];
+        __syncthreads();  // everyone has read res before the next iteration overwrites it
+        if (norm != norm || norm <= 0.0f) continue;
+        if (di < dj) {        // update_mean(p, k, norm, ic) — mod.rs:86-94
+            const float c1 = __fadd_rn(ic, 1.0f);
+            for (int i = tid; i < d; i += blockDim.x) p[i] = __fdiv_rn(__fadd_rn(__fmul_rn(p[i], ic), __fdiv_rn(k[i], norm)), c1);
+            __syncthreads();
+            if (warp == 0) init_warp(metric, p, S.php, d);
+            ic = c1;
+            __syncthreads();
+        } else if (dj < di) {
+            const float c1 = __fadd_rn(jc, 1.0f);
+            for (int i = tid; i < d; i += blockDim.x) q[i] = __fdiv_rn(__fadd_rn(__fmul_rn(q[i], jc), __fdiv_rn(k[i], norm)), c1);
+            __syncthreads();
+            if (warp == 0) init_warp(metric, q, S.phq, d);
+            jc = c1;
+            __syncthreads();
+        }
+    }
+    // normal = normalize(p - q) (+ bias / extra_dim) — euclidean.rs:59-75, manhattan.rs:62-78,
+    // cosine.rs:77-83, dot_product.rs:102-111
+    float* nv = ws + (size_t)12 * ld;
+    for (int i = tid; i < ld; i += blockDim.x) nv[i] = i < d ? __fsub_rn(p[i], q[i]) : 0.f;
+    float extra = (metric == DOT_PRODUCT) ? __fsub_rn(S.php[0], S.phq[0]) : 0.f;
+    __syncthreads();
+    if (warp == 0) { float x = norm_leaf_warp(metric, nv, extra, d); if (lane == 0) S.res[0] = x; }
+    __syncthreads();
+    const float nn = S.res[0];
+    float* out = slot_ptr + NORMAL_HDR;
+    if (nn > 0.0f) { for (int i = tid; i < d; i += blockDim.x) nv[i] = __fdiv_rn(nv[i], nn); extra = (metric == DOT_PRODUCT) ? __fdiv_rn(extra, nn) : extra; }
+    __syncthreads();
+    for (int i = tid; i < ld; i += blockDim.x) out[i] = nv[i];
+    if (metric == EUCLIDEAN || metric == MANHATTAN) {
+        // bias = sum over i of ((-n_i) * (p_i + q_i)) / 2, folded left to right from +0.0
+        __syncthreads();
+        for (int i = tid; i < d; i += blockDim.x) nv[i] = __fdiv_rn(__fmul_rn(-nv[i], __fadd_rn(p[i], q[i])), 2.0f);
+        __syncthreads();
+        if (tid == 0) {
+            float bias = 0.0f;
+            for (int i = 0; i < d; ++i) bias = __fadd_rn(bias, nv[i]);
+            slot_ptr[0] = bias; slot_ptr[1] = 0.f; slot_ptr[2] = 0.f; slot_ptr[3] = 0.f;
+        }
+    } else if (tid == 0) {
+        slot_ptr[0] = (metric == DOT_PRODUCT) ? extra : 0.f;  // Cosine normal header: norm = 0.0; Dot: {extra_dim, norm = 0.0}
+        slot_ptr[1] = 0.f; slot_ptr[2] = 0.f; slot_ptr[3] = 0.f;
+    }
+    __syncthreads();
+}
+
+// CTA-wide stable partition of a whole node (any size) by its flags.
+__device__ void partition_inline(const uint32_t* src, const uint8_t* flags, uint32_t* dst, uint32_t len, uint32_t total_left, uint32_t* sm_w) {
+    uint32_t left_before = 0;
+    for (uint32_t base = 0; base < len; base += PART_UNIT) {
+        partition_block(src, flags, dst, base, len, left_before, total_left, sm_w);
+        uint32_t add = 0;
+        for (int w = 0; w < 8; ++w) add += sm_w[w];
+        left_before += add;
+        __syncthreads();
+    }
+}
+
+// exclusive scan (in place) of v[0..n) by one CTA; returns the total to every thread
+__device__ uint32_t cta_exclusive_scan(uint32_t* v, uint32_t n, uint32_t* sm_tmp /* blockDim */) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const uint32_t per = (n + nt - 1) / nt;
+    const uint32_t b = (uint32_t)tid * per, e = (b + per < n) ? b + per : n;
+    uint32_t s = 0;
+    for (uint32_t i = b; i < e; ++i) s += v[i];
+    sm_tmp[tid] = s;
+    __syncthreads();
+    if (tid < 32) {  // warp 0: exclusive scan of the nt partials (nt == 8 * 32)
+        const int per_lane = nt / 32;
+        uint32_t loc = 0;
+        for (int i = 0; i < per_lane; ++i) loc += sm_tmp[tid * per_lane + i];
+        uint32_t inc = loc;
+        for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, inc, o); if (tid >= o) inc += y; }
+        uint32_t run2 = inc - loc;
+        for (int i = 0; i < per_lane; ++i) { uint32_t x = sm_tmp[tid * per_lane + i]; sm_tmp[tid * per_lane + i] = run2; run2 += x; }
+        if (tid == 31) sm_tmp[nt] = inc;
+    }
+    __syncthreads();
+    uint32_t run = sm_tmp[tid];
+    for (uint32_t i = b; i < e; ++i) { uint32_t x = v[i]; v[i] = run; run += x; }
+    uint32_t total = sm_tmp[nt];
+    __syncthreads();
+    return total;
+}
+
+enum : int { ACT_NONE = 0, ACT_SPLIT = 1, ACT_PART_INLINE = 2, ACT_RANDOM = 3, ACT_EXIT = 4 };
+
+__global__ void __launch_bounds__(CTRL_THREADS, 1) control_kernel(BuildParams P) {
+    extern __shared__ __align__(16) unsigned char ctrl_smem[];
+    __shared__ TwoMeansShared TM;
+    __shared__ uint32_t sm_tmp[CTRL_THREADS + 1];
+    __shared__ uint32_t sm_w[16];
+    __shared__ int s_action;
+    __shared__ uint32_t s_total_left;
+    __shared__ Rng s_rng;  // thread 0 only
+
+    constexpr int SMF = 96;  // DFS frames cached in shared memory (deeper ones stay in global)
+    __shared__ Frame sm_frames[SMF];
+    __shared__ TreeState S;
+
+    const uint32_t t = blockIdx.x;
+    Job& job = P.jobs[t];
+    if (P.st[t].phase == PH_DONE) return;  // job.kind already JOB_NONE
+    if (*P.error != ERR_NONE) return;
+    Frame* gframes = P.frames + (size_t)t * MAX_DEPTH;
+    if (threadIdx.x == 0) S = P.st[t];
+    __syncthreads();
+    for (int i = threadIdx.x; i <= S.sp && i < SMF; i += blockDim.x) sm_frames[i] = gframes[i];
+    __syncthreads();
+    auto FR = [&](int i) -> Frame& { return i < SMF ? sm_frames[i] : gframes[i]; };
+    Record* recs = P.recs + (size_t)t * P.rec_cap;
+    uint32_t* perm0 = P.perm[0] + (size_t)t * P.n;
+    uint32_t* perm1 = P.perm[1] + (size_t)t * P.n;
+    uint8_t* flags = P.flags + (size_t)t * P.n;
+    uint32_t* unit_left = P.unit_left + (size_t)t * P.units_per_tree;
+    float* ws = P.use_smem_ws ? reinterpret_cast<float*>(ctrl_smem) : P.scratch + (size_t)t * 13 * P.ld;
+    const int tid = threadIdx.x;
+
+    if (tid == 0) { s_rng.init(S.key, S.pos); job.kind = JOB_NONE; }
+    uint32_t total_left = 0;
+    if (S.phase == PH_AWAIT_SCAN) {
+        const Frame f = FR(S.sp);
+        total_left = cta_exclusive_scan(unit_left, (f.len + SCAN_UNIT - 1) / SCAN_UNIT, sm_tmp);
+    }
+    __syncthreads();
+
+    for (;;) {
+        // ---- thread 0: advance the DFS until CTA-wide work is needed --------------------------
+        if (tid == 0) {
+            int action = ACT_NONE;
+            if (S.phase == PH_START) {
+                Frame r; r.start = 0; r.len = P.n; r.left_len = 0; r.left_id = 0; r.slot = NO_SLOT; r.parity = 0; r.stage = 0; r.pad = 0;
+                FR(0) = r; S.sp = 0; S.phase = PH_AWAIT_PART;  // falls into the descend loop below
+            } else if (S.phase == PH_AWAIT_SCAN) {
+                Frame& f = FR(S.sp);
+                const uint32_t left = total_left, right = f.len - total_left;
+                S.scanned += f.len;
+                const double imb = split_imbalance_dev(left, right);
+                if (imb < 0.95 || S.attempts_left == 0) {            // src/writer.rs:1209-1213
+                    if (imb > 0.99) { action = ACT_RANDOM; }         // :1220-1227
+                    else {
+                        f.slot = S.cur_slot; S.cur_slot = NO_SLOT;   // the normal is kept
+                        f.left_len = left;
+                        if (f.len <= INLINE_PART_MAX) action = ACT_PART_INLINE;
+                        else {  // wide partition by all SMs in this step's work kernel
+                            job.kind = JOB_PARTITION; job.len = f.len;
+                            job.rows = (f.parity ? perm1 : perm0) + f.start;
+                            job.dst = (f.parity ? perm0 : perm1) + f.start;
+                            job.flags = flags + f.start; job.unit_left = unit_left; job.total_left = left;
+                            job.normal = nullptr; job.margins = nullptr;
+                            f.stage = 1; S.phase = PH_AWAIT_PART; action = ACT_EXIT;
+                        }
+                    }
+                } else { S.attempts_left -= 1; action = ACT_SPLIT; }  // :1215
+            }
+            if (action == ACT_NONE) {
+                // descend: emit leaves, close finished splits, stop at the next node to split
+                S.phase = PH_AWAIT_PART;
+                bool have_ret = false; uint32_t ret = 0;
+                for (;;) {
+                    if (have_ret) {
+                        if (S.sp < 0) { S.phase = PH_DONE; atomicSub(P.active, 1u); action = ACT_EXIT; break; }
+                        Frame& par = FR(S.sp);
+                        if (par.stage == 2) {          // left child finished -> open the right child
+                            par.left_id = ret; par.stage = 3; have_ret = false;
+                            if (S.sp + 1 >= MAX_DEPTH) { atomicExch(P.error, ERR_DEPTH); action = ACT_EXIT; break; }
+                            Frame c; c.start = par.start + par.left_len; c.len = par.len - par.left_len; c.left_len = 0; c.left_id = 0;
+                            c.slot = NO_SLOT; c.parity = par.parity ^ 1; c.stage = 0; c.pad = 0;
+                            S.sp += 1; FR(S.sp) = c;
+                        } else {                       // right child finished -> emit the split node (post-order)
+                            if (S.n_recs >= P.rec_cap) { atomicExch(P.error, ERR_RECORDS); action = ACT_EXIT; break; }
+                            Record rc; rc.kind = REC_SPLIT; rc.a = par.left_id; rc.b = ret; rc.c = par.slot;
+                            recs[S.n_recs] = rc; ret = S.n_recs++; S.sp -= 1;
+                        }
+                        continue;
+                    }
+                    Frame& f = FR(S.sp);
+                    if (f.stage == 0) {
+                        if (f.len <= P.K) {            // fit_in_descendant — src/writer.rs:1184-1189
+                            if (S.n_recs >= P.rec_cap) { atomicExch(P.error, ERR_RECORDS); action = ACT_EXIT; break; }
+                            Record rc; rc.kind = REC_DESC; rc.a = f.start; rc.b = f.len; rc.c = f.parity;
+                            recs[S.n_recs] = rc; ret = S.n_recs++; have_ret = true; S.sp -= 1;
+                        } else { S.attempts_left = 3; action = ACT_SPLIT; break; }
+                    } else {                           // stage 1: children are known -> open the left child
+                        f.stage = 2;
+                        if (S.sp + 1 >= MAX_DEPTH) { atomicExch(P.error, ERR_DEPTH); action = ACT_EXIT; break; }
+                        Frame c; c.start = f.start; c.len = f.left_len; c.left_len = 0; c.left_id = 0;
+                        c.slot = NO_SLOT; c.parity = f.parity ^ 1; c.stage = 0; c.pad = 0;
+                        S.sp += 1; FR(S.sp) = c;
+                    }
+                }
+            }
+            if (action == ACT_SPLIT && S.cur_slot == NO_SLOT) {
+                uint32_t s = atomicAdd(P.pool_counter, 1u);
+                if (s >= P.pool_cap) { atomicExch(P.error, ERR_POOL); action = ACT_EXIT; }
+                else S.cur_slot = s;
+            }
+            s_action = action;
+            s_total_left = total_left;
+        }
+        __syncthreads();
+        const int action = s_action;
+        if (action == ACT_EXIT) break;
+        const Frame f = FR(S.sp);
+        const uint32_t* src = (f.parity ? perm1 : perm0) + f.start;
+        uint32_t* dst = (f.parity ? perm0 : perm1) + f.start;
+        if (action == ACT_SPLIT) {
+            float* slot_ptr = P.pool + (size_t)S.cur_slot * P.pool_stride;
+            create_split_cta(P, s_rng, src, f.len, ws, TM, slot_ptr);
+            if (tid == 0) {
+                S.n_splits_tried += 1;
+                job.kind = JOB_SCAN; job.len = f.len; job.rows = src; job.normal = slot_ptr;
+                job.flags = flags + f.start; job.margins = nullptr; job.unit_left = unit_left; job.dst = nullptr; job.total_left = 0;
+                S.phase = PH_AWAIT_SCAN;
+            }
+            break;
+        }
+        if (action == ACT_RANDOM) {
+            // randomly_split_children — src/writer.rs:1310-1326: one gen::<bool>() per id, ascending;
+            // bool = top bit of next_u32 (rand 0.8.5 Standard), true => Left
+            const uint64_t pos0 = s_rng.pos;
+            uint32_t cnt = 0;
+            for (uint32_t i = tid; i < f.len; i += blockDim.x) {
+                uint32_t blk[16];
+                const uint64_t w = pos0 + i;
+                chacha12_block(S.key, w >> 4, blk);
+                const int left = (int)(blk[w & 15] >> 31);
+                flags[f.start + i] = left ? 0 : 1;
+                cnt += left;
+            }
+            sm_tmp[tid] = cnt;
+            __syncthreads();
+            if (tid == 0) {
+                uint32_t tot = 0; for (int i = 0; i < blockDim.x; ++i) tot += sm_tmp[i];
+                s_total_left = tot; s_rng.pos = pos0 + f.len; s_rng.blk_no = ~0ull;
+                S.n_random += 1;
+                FR(S.sp).slot = NO_SLOT; FR(S.sp).left_len = tot;
+                if (S.cur_slot != NO_SLOT) { /* keep the reserved slot for the next split */ }
+            }
+            __syncthreads();
+            partition_inline(src, flags + f.start, dst, f.len, s_total_left, sm_w);
+            if (tid == 0) { FR(S.sp).stage = 1; S.phase = PH_AWAIT_PART; }
+            total_left = 0;
+            __syncthreads();
+            continue;
+        }
+        if (action == ACT_PART_INLINE) {
+            // flags came from the scan; ids keep their ascending order on both sides (writer.rs:1201-1207)
+            partition_inline(src, flags + f.start, dst, f.len, f.left_len, sm_w);
+            if (tid == 0) { FR(S.sp).stage = 1; S.phase = PH_AWAIT_PART; }
+            total_left = 0;
+            __syncthreads();
+            continue;
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i <= S.sp && i < SMF; i += blockDim.x) gframes[i] = sm_frames[i];
+    if (tid == 0) { S.pos = s_rng.pos; P.st[t] = S; }
+}
+
+// Merge the two ping-pong id buffers into `final_ids` following each leaf's parity.
+__global__ void finalize_kernel(BuildParams P, uint32_t* __restrict__ final_ids) {
+    const uint32_t t = blockIdx.y;
+    const TreeState& S = P.st[t];
+    const Record* recs = P.recs + (size_t)t * P.rec_cap;
+    for (uint32_t r = blockIdx.x; r < S.n_recs; r += gridDim.x) {
+        const Record rc = recs[r];
+        if (rc.kind != REC_DESC) continue;
+        const uint32_t* src = P.perm[rc.c & 1] + (size_t)t * P.n + rc.a;
+        uint32_t* dst = final_ids + (size_t)t * P.n + rc.a;
+        for (uint32_t i = threadIdx.x; i < rc.b; i += blockDim.x) dst[i] = src[i];
+    }
+}
+
+__global__ void init_trees_kernel(BuildParams P, const uint32_t* __restrict__ keys /* n_trees x 8 */) {
+    const uint32_t t = blockIdx.x;
+    if (threadIdx.x == 0) {
+        TreeState s;
+        for (int i = 0; i < 8; ++i) s.key[i] = keys[t * 8 + i];
+        s.pos = 0; s.phase = PH_START; s.sp = -1; s.attempts_left = 0; s.cur_slot = NO_SLOT; s.n_recs = 0;
+        s.n_splits_tried = 0; s.n_random = 0; s.pad = 0; s.scanned = 0;
+        P.st[t] = s;
+        P.jobs[t].kind = JOB_NONE;
+    }
+    uint32_t* perm0 = P.perm[0] + (size_t)t * P.n;
+    for (uint32_t i = threadIdx.x; i < P.n; i += blockDim.x) perm0[i] = i;
+}
+
+}  // namespace ab

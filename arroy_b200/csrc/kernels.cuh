@@ -1,0 +1,463 @@
+// kernels.cuh — data-parallel kernels of the hot path (sm_100a):
+//   work_kernel      side()/margin scan over row lists + stable left/right partition of id lists
+//                    (src/writer.rs:1201-1207 and its callers :1424-1430, :1494-1500)
+//   norms_kernel     per-item sqrt(dot(v,v)) (Cosine new_header, cosine.rs:39-41;
+//                    DotProduct::preprocess pass 1, dot_product.rs:132-142)
+//   dot_header_kernel  DotProduct::preprocess pass 2 (dot_product.rs:146-160)
+//   distance_kernel  D::built_distance(query, item) per candidate (src/reader.rs:381-391)
+//   topk_kernel      k smallest by (OrderedFloat(dist), id) + D::normalized_distance (reader.rs:394-399)
+//   synth_kernel     counter-based ChaCha12 synthetic matrix
+// All are HBM-bound streaming kernels: 128-bit coalesced loads, warp-shuffle reductions in the
+// reference's exact summation order (exact.cuh), no tensor cores.
+#pragma once
+#include "exact.cuh"
+
+namespace ab {
+
+constexpr int WORK_THREADS = 256;
+constexpr int SCAN_UNIT = 64;    // rows per scan unit (8 warps x 4 groups x 2 rows)
+constexpr int PART_UNIT = 256;   // ids per partition unit (= 4 scan units)
+
+enum : int { JOB_NONE = 0, JOB_SCAN = 1, JOB_PARTITION = 2 };
+
+// A normal as the kernels read it: [h0, h1, 0, 0, v[ld]] (16-byte aligned vector part).
+constexpr int NORMAL_HDR = 4;
+
+struct Job {
+    int32_t kind;
+    uint32_t len;            // rows in the node
+    const uint32_t* rows;    // scan: ascending row indices (NULL = identity); partition: source ids
+    const float* normal;     // scan: [h0,h1,_,_,v[ld]]
+    uint8_t* flags;          // scan out / partition in: 1 = Right, 0 = Left, per position
+    float* margins;          // scan out, optional
+    uint32_t* unit_left;     // scan out: Left count per SCAN_UNIT; partition in: exclusive prefix of it
+    uint32_t* dst;           // partition out: [0,total_left) lefts then rights, both in source order
+    uint32_t total_left;
+    uint32_t pad;
+};
+
+__device__ __forceinline__ float4 ldg_stream(const float4* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+
+__device__ __forceinline__ float margin_finish(int metric, float dot, float nh0, float item_h0) {
+    // euclidean.rs:79-81 / manhattan.rs:82-84: bias + dot; cosine.rs:87-89: dot;
+    // dot_product.rs:115-117: dot + n.extra_dim * q.extra_dim (two roundings)
+    if (metric == COSINE) return dot;
+    if (metric == DOT_PRODUCT) return __fadd_rn(dot, __fmul_rn(nh0, item_h0));
+    return __fadd_rn(nh0, dot);
+}
+
+// One scan unit: SCAN_UNIT consecutive positions of a job. d >= 32: 8 lanes per row, float4
+// loads, two rows in flight per group. sm_normal: the job's normal vector in shared memory.
+__device__ __forceinline__ void scan_unit(const Job& jb, uint32_t unit, const float* __restrict__ items, const float* __restrict__ ih0,
+                                          uint32_t d, uint32_t ld, int metric, const float* sm_normal, float nh0, uint32_t* sm_count) {
+    const uint32_t base = unit * SCAN_UNIT;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) *sm_count = 0;
+    __syncthreads();
+    if (d >= 32) {
+        const int g8 = lane & 7, grp = lane >> 3;
+        const uint32_t slot = warp * 8 + grp * 2;  // first of the two positions of this group
+        uint32_t pa = base + slot, pb = base + slot + 1;
+        const bool va = pa < jb.len, vb = pb < jb.len;
+        uint32_t ra = 0, rb = 0;
+        if (va) ra = jb.rows ? jb.rows[pa] : pa;
+        if (vb) rb = jb.rows ? jb.rows[pb] : pb;
+        const float4* A = reinterpret_cast<const float4*>(items + (size_t)ra * ld);
+        const float4* B = reinterpret_cast<const float4*>(items + (size_t)rb * ld);
+        const float4* N = reinterpret_cast<const float4*>(sm_normal);
+        float4 acca = make_float4(0.f, 0.f, 0.f, 0.f), accb = acca;
+        const int nch = d >> 5;
+#pragma unroll 4
+        for (int c = 0; c < nch; ++c) {
+            float4 x = ldg_stream(A + c * 8 + g8);
+            float4 z = ldg_stream(B + c * 8 + g8);
+            float4 y = N[c * 8 + g8];
+            acca.x = fmaf(x.x, y.x, acca.x); acca.y = fmaf(x.y, y.y, acca.y);
+            acca.z = fmaf(x.z, y.z, acca.z); acca.w = fmaf(x.w, y.w, acca.w);
+            accb.x = fmaf(z.x, y.x, accb.x); accb.y = fmaf(z.y, y.y, accb.y);
+            accb.z = fmaf(z.z, y.z, accb.z); accb.w = fmaf(z.w, y.w, accb.w);
+        }
+        float da = group8_hsum(acca), db = group8_hsum(accb);
+        const float* rowa = items + (size_t)ra * ld;
+        const float* rowb = items + (size_t)rb * ld;
+        for (uint32_t i = nch * 32; i < d; ++i) {  // len % 32 tail: separately rounded mul, add
+            da = __fadd_rn(da, __fmul_rn(rowa[i], sm_normal[i]));
+            db = __fadd_rn(db, __fmul_rn(rowb[i], sm_normal[i]));
+        }
+        float ma = margin_finish(metric, da, nh0, (metric == DOT_PRODUCT) ? ih0[ra] : 0.f);
+        float mb = margin_finish(metric, db, nh0, (metric == DOT_PRODUCT) ? ih0[rb] : 0.f);
+        int sa = side_of(ma), sb = side_of(mb);
+        const bool leader = g8 == 0;
+        if (leader && va) { if (jb.flags) jb.flags[pa] = (uint8_t)sa; if (jb.margins) jb.margins[pa] = ma; }
+        if (leader && vb) { if (jb.flags) jb.flags[pb] = (uint8_t)sb; if (jb.margins) jb.margins[pb] = mb; }
+        unsigned la = __ballot_sync(0xffffffffu, leader && va && sa == 0);
+        unsigned lb = __ballot_sync(0xffffffffu, leader && vb && sb == 0);
+        if (lane == 0) { int c = __popc(la) + __popc(lb); if (c) atomicAdd(sm_count, (uint32_t)c); }
+    } else {
+        // d < 32: SSE (16..31) or scalar (<16) order, one thread per row
+        int left = 0;
+        if (threadIdx.x < SCAN_UNIT) {
+            uint32_t p = base + threadIdx.x;
+            if (p < jb.len) {
+                uint32_t r = jb.rows ? jb.rows[p] : p;
+                float dt = exact_thread<false>(items + (size_t)r * ld, sm_normal, (int)d);
+                float m = margin_finish(metric, dt, nh0, (metric == DOT_PRODUCT) ? ih0[r] : 0.f);
+                int s = side_of(m);
+                if (jb.flags) jb.flags[p] = (uint8_t)s;
+                if (jb.margins) jb.margins[p] = m;
+                left = (s == 0);
+            }
+        }
+        unsigned l = __ballot_sync(0xffffffffu, left);
+        if (lane == 0 && l) atomicAdd(sm_count, (uint32_t)__popc(l));
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && jb.unit_left) jb.unit_left[unit] = *sm_count;
+}
+
+// Stable partition of one PART_UNIT block of ids. left_before = number of Left flags in all
+// earlier positions of the node. sm_w: 2*8 uint32 scratch.
+__device__ __forceinline__ void partition_block(const uint32_t* __restrict__ src, const uint8_t* __restrict__ flags, uint32_t* __restrict__ dst,
+                                                uint32_t base, uint32_t len, uint32_t left_before, uint32_t total_left, uint32_t* sm_w) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t p = base + threadIdx.x;
+    bool valid = p < len;
+    int f = valid ? flags[p] : 1;
+    uint32_t id = valid ? src[p] : 0;
+    unsigned lm = __ballot_sync(0xffffffffu, valid && f == 0);
+    unsigned rm = __ballot_sync(0xffffffffu, valid && f != 0);
+    if (lane == 0) { sm_w[warp] = __popc(lm); sm_w[8 + warp] = __popc(rm); }
+    __syncthreads();
+    uint32_t lw = 0, rw = 0;
+    for (int w = 0; w < warp; ++w) { lw += sm_w[w]; rw += sm_w[8 + w]; }
+    unsigned below = (1u << lane) - 1u;
+    if (valid) {
+        if (f == 0) dst[left_before + lw + __popc(lm & below)] = id;
+        else dst[total_left + (base - left_before) + rw + __popc(rm & below)] = id;
+    }
+    __syncthreads();
+}
+
+// Persistent-style grid: every CTA strides over the units of all posted jobs.
+// Dynamic shared memory: ld floats (normal) + (njobs + 1) uint32 (unit prefix).
+__global__ void __launch_bounds__(WORK_THREADS, 3)
+work_kernel(const Job* __restrict__ jobs, int njobs, const float* __restrict__ items, const float* __restrict__ ih0,
+            uint32_t d, uint32_t ld, int metric) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* sm_normal = reinterpret_cast<float*>(smem_raw);
+    uint32_t* sm_prefix = reinterpret_cast<uint32_t*>(sm_normal + ld);
+    __shared__ uint32_t sm_count;
+    __shared__ uint32_t sm_w[16];
+    // exclusive prefix of the unit counts over jobs (njobs <= a few hundred)
+    for (int j = threadIdx.x; j < njobs; j += blockDim.x) {
+        const int k = jobs[j].kind;
+        const uint32_t len = jobs[j].len;
+        sm_prefix[j] = k == JOB_SCAN ? (len + SCAN_UNIT - 1) / SCAN_UNIT : (k == JOB_PARTITION ? (len + PART_UNIT - 1) / PART_UNIT : 0u);
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const int per = (njobs + 31) / 32;
+        const int b = threadIdx.x * per, e = min(b + per, njobs);
+        uint32_t loc = 0;
+        for (int i = b; i < e; ++i) loc += sm_prefix[i];
+        uint32_t inc = loc;
+        for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, inc, o); if ((int)threadIdx.x >= o) inc += y; }
+        uint32_t run = inc - loc;
+        for (int i = b; i < e; ++i) { uint32_t x = sm_prefix[i]; sm_prefix[i] = run; run += x; }
+        if (threadIdx.x == 31) sm_prefix[njobs] = inc;
+    }
+    __syncthreads();
+    const uint32_t total = sm_prefix[njobs];
+    int loaded_job = -1;
+    float nh0 = 0.f;
+    for (uint32_t u = blockIdx.x; u < total; u += gridDim.x) {
+        int lo = 0, hi = njobs;  // last j with prefix[j] <= u
+        while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (sm_prefix[mid] <= u) lo = mid; else hi = mid; }
+        const int j = lo;
+        const Job jb = jobs[j];
+        const uint32_t unit = u - sm_prefix[j];
+        if (jb.kind == JOB_SCAN) {
+            if (loaded_job != j) {
+                __syncthreads();
+                for (uint32_t i = threadIdx.x; i < ld; i += blockDim.x) sm_normal[i] = jb.normal[NORMAL_HDR + i];
+                nh0 = jb.normal[0];
+                loaded_job = j;
+                __syncthreads();
+            }
+            scan_unit(jb, unit, items, ih0, d, ld, metric, sm_normal, nh0, &sm_count);
+        } else {
+            partition_block(jb.rows, jb.flags, jb.dst, unit * PART_UNIT, jb.len, jb.unit_left[unit * (PART_UNIT / SCAN_UNIT)], jb.total_left, sm_w);
+        }
+    }
+}
+
+// ---- per-item norms ---------------------------------------------------------------------
+// out[r] = sqrt(dot(v_r, v_r)) in the reference's order; optional atomic max over rows
+// (f32::max semantics: NaN ignored; norms are >= 0 so the uint order equals the float order).
+__global__ void __launch_bounds__(256) norms_kernel(const float* __restrict__ items, uint64_t n, uint32_t d, uint32_t ld, float* __restrict__ out, uint32_t* max_bits) {
+    const int lane = threadIdx.x & 31;
+    uint64_t warp_global = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    uint64_t nwarps = (uint64_t)gridDim.x * (blockDim.x >> 5);
+    for (uint64_t r0 = warp_global * 4; r0 < n; r0 += nwarps * 4) {
+        float res;
+        if (d >= 32) {
+            const int g8 = lane & 7, grp = lane >> 3;
+            uint64_t r = r0 + grp;
+            bool v = r < n;
+            const float4* A = reinterpret_cast<const float4*>(items + (size_t)(v ? r : 0) * ld);
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            const int nch = d >> 5;
+#pragma unroll 4
+            for (int c = 0; c < nch; ++c) {
+                float4 x = ldg_stream(A + c * 8 + g8);
+                acc.x = fmaf(x.x, x.x, acc.x); acc.y = fmaf(x.y, x.y, acc.y); acc.z = fmaf(x.z, x.z, acc.z); acc.w = fmaf(x.w, x.w, acc.w);
+            }
+            float dt = group8_hsum(acc);
+            const float* row = items + (size_t)(v ? r : 0) * ld;
+            for (uint32_t i = nch * 32; i < d; ++i) dt = __fadd_rn(dt, __fmul_rn(row[i], row[i]));
+            res = __fsqrt_rn(dt);
+            if (v && g8 == 0) {
+                out[r] = res;
+                if (max_bits && res == res) atomicMax(max_bits, __float_as_uint(res));
+            }
+        } else {
+            if (lane < 4) {
+                uint64_t r = r0 + lane;
+                if (r < n) {
+                    const float* row = items + (size_t)r * ld;
+                    res = __fsqrt_rn(exact_thread<false>(row, row, (int)d));
+                    out[r] = res;
+                    if (max_bits && res == res) atomicMax(max_bits, __float_as_uint(res));
+                }
+            }
+        }
+    }
+}
+
+// DotProduct::preprocess pass 2 — dot_product.rs:146-160
+__global__ void dot_header_kernel(const float* __restrict__ norms, uint64_t n, const uint32_t* max_bits, float* __restrict__ extra_dim, float* __restrict__ norm_hdr) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float max_norm = __uint_as_float(*max_bits);
+    float node_norm = norms[i];
+    float mm = __fmul_rn(max_norm, max_norm);
+    float diff = __fsub_rn(mm, __fmul_rn(node_norm, node_norm));
+    norm_hdr[i] = mm;
+    extra_dim[i] = __fsqrt_rn(diff);
+}
+
+// ---- re-rank distances --------------------------------------------------------------------
+// One warp handles 4 candidates at a time (8 lanes each). Query vectors in global memory
+// (read through L1/L2; nq*ld floats). keys[q][i] = ordered_key(dist) << 32 | position.
+__device__ __forceinline__ float built_finish(int metric, float acc, float qh0, float item_h0) {
+    if (metric == EUCLIDEAN || metric == MANHATTAN) return acc;      // euclidean.rs:45-47 / manhattan.rs:44-46
+    if (metric == DOT_PRODUCT) return -acc;                          // dot_product.rs:52-56
+    float pnqn = __fmul_rn(qh0, item_h0);                            // cosine.rs:43-59
+    if (pnqn > 1.1920928955078125e-07f) {
+        float c = __fdiv_rn(acc, pnqn);
+        if (c < -1.0f) c = -1.0f;
+        if (c > 1.0f) c = 1.0f;
+        return __fdiv_rn(__fsub_rn(1.0f, c), 2.0f);
+    }
+    return 0.0f;
+}
+
+__global__ void __launch_bounds__(256)
+distance_kernel(const float* __restrict__ items, const float* __restrict__ ih0, uint32_t d, uint32_t ld, int metric,
+                const float* __restrict__ queries, const float* __restrict__ qh0, uint32_t nq,
+                const uint32_t* __restrict__ rows, const uint64_t* __restrict__ offsets,
+                float* __restrict__ dists, unsigned long long* __restrict__ keys) {
+    const uint32_t q = blockIdx.y;
+    const uint64_t beg = offsets[q], end = offsets[q + 1];
+    const float* qv = queries + (size_t)q * ld;
+    const float qhdr = qh0 ? qh0[q] : 0.f;
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp_global = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const uint64_t nwarps = (uint64_t)gridDim.x * (blockDim.x >> 5);
+    if (metric == MANHATTAN) {
+        // strictly sequential scalar sum of |p - q| per candidate (manhattan.rs:44-46): one lane per row
+        for (uint64_t p0 = beg + warp_global * 32; p0 < end; p0 += nwarps * 32) {
+            uint64_t p = p0 + lane;
+            if (p < end) {
+                const float* row = items + (size_t)rows[p] * ld;
+                float s = 0.0f;
+                for (uint32_t i = 0; i < d; ++i) s = __fadd_rn(s, fabsf(__fsub_rn(qv[i], row[i])));
+                dists[p] = s;
+                keys[p] = ((unsigned long long)ordered_key(s) << 32) | (unsigned long long)(uint32_t)(p - beg);
+            }
+        }
+        return;
+    }
+    for (uint64_t p0 = beg + warp_global * 4; p0 < end; p0 += nwarps * 4) {
+        float res;
+        uint64_t p;
+        bool v, writer;
+        uint32_t r = 0;
+        if (d >= 32) {
+            const int g8 = lane & 7, grp = lane >> 3;
+            p = p0 + grp;
+            v = p < end;
+            writer = g8 == 0;
+            if (v) r = rows[p];
+            const float4* A = reinterpret_cast<const float4*>(items + (size_t)r * ld);
+            const float4* Q = reinterpret_cast<const float4*>(qv);
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            const int nch = d >> 5;
+            if (metric == EUCLIDEAN) {
+#pragma unroll 4
+                for (int c = 0; c < nch; ++c) {
+                    float4 x = __ldg(Q + c * 8 + g8);
+                    float4 y = ldg_stream(A + c * 8 + g8);
+                    float t0 = __fsub_rn(x.x, y.x), t1 = __fsub_rn(x.y, y.y), t2 = __fsub_rn(x.z, y.z), t3 = __fsub_rn(x.w, y.w);
+                    acc.x = fmaf(t0, t0, acc.x); acc.y = fmaf(t1, t1, acc.y); acc.z = fmaf(t2, t2, acc.z); acc.w = fmaf(t3, t3, acc.w);
+                }
+            } else {
+#pragma unroll 4
+                for (int c = 0; c < nch; ++c) {
+                    float4 x = __ldg(Q + c * 8 + g8);
+                    float4 y = ldg_stream(A + c * 8 + g8);
+                    acc.x = fmaf(x.x, y.x, acc.x); acc.y = fmaf(x.y, y.y, acc.y); acc.z = fmaf(x.z, y.z, acc.z); acc.w = fmaf(x.w, y.w, acc.w);
+                }
+            }
+            res = group8_hsum(acc);
+            const float* row = items + (size_t)r * ld;
+            for (uint32_t i = nch * 32; i < d; ++i) {
+                if (metric == EUCLIDEAN) { float t = __fsub_rn(qv[i], row[i]); res = __fadd_rn(res, __fmul_rn(t, t)); }
+                else res = __fadd_rn(res, __fmul_rn(qv[i], row[i]));
+            }
+        } else {
+            p = p0 + lane;
+            v = lane < 4 && p < end;
+            writer = true;
+            res = 0.f;
+            if (v) {
+                r = rows[p];
+                const float* row = items + (size_t)r * ld;
+                res = (metric == EUCLIDEAN) ? exact_thread<true>(qv, row, (int)d) : exact_thread<false>(qv, row, (int)d);
+            }
+        }
+        if (v && writer) {
+            float dist = built_finish(metric, res, qhdr, (metric == COSINE) ? ih0[r] : 0.f);
+            dists[p] = dist;
+            keys[p] = ((unsigned long long)ordered_key(dist) << 32) | (unsigned long long)(uint32_t)(p - beg);
+        }
+    }
+}
+
+// ---- top-k ----------------------------------------------------------------------------------
+// One CTA per query. Streaming selection: the CAP-key shared buffer keeps the best k so far in
+// [0,k) (sorted) and is refilled with up to CAP-k new keys that beat the current k-th key, then
+// bitonic-sorted. Equivalent to sort-ascending-take-k on (OrderedFloat, id) — which is what
+// median_based_top_k returns (src/reader.rs:607-640, tests/reader.rs:283-299).
+constexpr int TOPK_CAP = 4096;
+constexpr int TOPK_THREADS = 256;
+
+__device__ __forceinline__ void bitonic_sort_shared(unsigned long long* buf, int n /* power of two */) {
+    for (int size = 2; size <= n; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            __syncthreads();
+            for (int t = threadIdx.x; t < (n >> 1); t += blockDim.x) {
+                int i = 2 * t - (t & (stride - 1));
+                int j = i + stride;
+                bool up = ((i & size) == 0);
+                unsigned long long a = buf[i], b = buf[j];
+                if ((a > b) == up) { buf[i] = b; buf[j] = a; }
+            }
+        }
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ float normalized_distance_dev(int metric, float dist) {
+    if (metric == EUCLIDEAN) return __fsqrt_rn(dist);  // mod.rs:59-61
+    if (metric == COSINE) return dist;                 // cosine.rs:61-63
+    if (metric == DOT_PRODUCT) return -dist;           // dot_product.rs:81-83
+    return (dist != dist) ? 0.0f : (dist > 0.0f ? dist : 0.0f);  // manhattan.rs:48-50 (f32::max)
+}
+
+__global__ void __launch_bounds__(TOPK_THREADS)
+topk_kernel(const unsigned long long* __restrict__ keys, const float* __restrict__ dists, const uint32_t* __restrict__ rows,
+            const uint64_t* __restrict__ offsets, uint32_t k, int metric,
+            uint32_t* __restrict__ out_rows, float* __restrict__ out_dist, uint32_t* __restrict__ out_len) {
+    __shared__ unsigned long long buf[TOPK_CAP];
+    __shared__ uint32_t fill;
+    const uint32_t q = blockIdx.x;
+    const uint64_t beg = offsets[q], end = offsets[q + 1];
+    const uint64_t n = end - beg;
+    const uint32_t kk = (uint32_t)(n < (uint64_t)k ? n : (uint64_t)k);
+    for (int i = threadIdx.x; i < TOPK_CAP; i += blockDim.x) buf[i] = ~0ull;
+    unsigned long long threshold = ~0ull;  // keys >= threshold cannot enter the top k any more
+    uint64_t pos = 0;
+    bool have = false;
+    while (pos < n) {  // host guarantees k <= TOPK_CAP / 2, so every round makes progress
+        const uint32_t base = have ? kk : 0u;
+        const uint64_t room = (uint64_t)(TOPK_CAP - base);
+        const uint32_t take = (uint32_t)(n - pos < room ? n - pos : room);
+        __syncthreads();
+        if (threadIdx.x == 0) fill = base;
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < take; i += blockDim.x) {
+            unsigned long long key = keys[beg + pos + i];
+            if (key < threshold) { uint32_t s = atomicAdd(&fill, 1u); buf[s] = key; }
+        }
+        pos += take;
+        __syncthreads();
+        const uint32_t f = fill;
+        int m = 2;
+        while ((uint32_t)m < f) m <<= 1;
+        for (int i = (int)f + threadIdx.x; i < m; i += blockDim.x) buf[i] = ~0ull;
+        bitonic_sort_shared(buf, m);
+        have = true;
+        threshold = (f >= kk && kk > 0) ? buf[kk - 1] : ~0ull;  // keys are unique, so `<` loses nothing
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) out_len[q] = kk;
+    for (uint32_t i = threadIdx.x; i < kk; i += blockDim.x) {
+        uint32_t p = (uint32_t)(buf[i] & 0xffffffffull);
+        out_rows[(size_t)q * k + i] = rows[beg + p];
+        out_dist[(size_t)q * k + i] = normalized_distance_dev(metric, dists[beg + p]);
+    }
+}
+
+// ---- synthetic matrix -------------------------------------------------------------------------
+// out[(i, j)] = gen::<f32>() number (row0+i)*d + j of StdRng::from_seed(key) minus centre; one
+// thread per ChaCha block (16 words).
+__global__ void synth_kernel(const uint32_t* __restrict__ key8, uint32_t d, uint64_t row0, uint64_t rows, float centre, float* __restrict__ out) {
+    uint32_t key[8];
+    for (int i = 0; i < 8; ++i) key[i] = key8[i];
+    const uint64_t w0 = row0 * d, w1 = (row0 + rows) * d;
+    const uint64_t b0 = w0 >> 4, b1 = (w1 + 15) >> 4;
+    for (uint64_t b = b0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; b < b1; b += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t blk[16];
+        chacha12_block(key, b, blk);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            uint64_t w = (b << 4) + k;
+            if (w >= w0 && w < w1) out[w - w0] = __fsub_rn(__fmul_rn((float)(blk[k] >> 8), 5.9604644775390625e-08f), centre);
+        }
+    }
+}
+
+// copy a dense n x d matrix into the padded n x ld layout (zero fill)
+__global__ void pad_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, uint64_t n, uint32_t d, uint32_t ld) {
+    uint64_t total = n * ld;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t r = i / ld;
+        uint32_t c = (uint32_t)(i - r * ld);
+        dst[i] = c < d ? src[r * d + c] : 0.f;
+    }
+}
+
+__global__ void fill_u32_kernel(uint32_t* p, uint64_t n, uint32_t v) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+__global__ void iota_u32_kernel(uint32_t* p, uint64_t n) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) p[i] = (uint32_t)i;
+}
+
+}  // namespace ab

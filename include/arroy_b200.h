@@ -1,0 +1,183 @@
+/*
+ * arroy_b200.h — C ABI of the B200-native distance / split / re-rank path of arroy.
+ *
+ * This is the drop-in boundary: a fork of the reference binds these
+ * entry points over Rust FFI (`extern "C"`) and calls them where
+ * it iterates over items today. Plain pointers and sizes only; no C++/torch types.
+ *
+ * Conventions
+ *   - every call returns an int32 status: 0 = ARROY_B200_OK, otherwise an error code;
+ *     arroy_b200_last_error(ctx) returns a message for the last failing call on ctx
+ *     (mirrors arroy::Error, src/error.rs:7-86; nothing unwinds across the boundary,
+ *     the way build tasks turn panics into Error::Panic, src/writer.rs:799-827).
+ *   - the caller owns every host buffer passed in or out; the library owns device
+ *     memory and pinned staging inside the context.
+ *   - entry points are thread-safe per context (internally serialised), like the
+ *     reference's Distance trait functions that rayon workers call concurrently.
+ *   - "row" = rank of an item id in the ascending id list given to stage_items
+ *     (RoaringBitmap iteration order of src/writer.rs:1201).
+ *   - header floats per metric (src/node.rs:68-73): Euclidean/Manhattan {bias},
+ *     Cosine {norm}, DotProduct {extra_dim, norm}; passed as hdr0, hdr1.
+ *   - there is no CPU fallback: without a CUDA device every compute call fails with
+ *     ARROY_B200_ERR_CUDA.
+ */
+#ifndef ARROY_B200_H
+#define ARROY_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct arroy_ctx arroy_ctx;
+
+enum {
+    ARROY_B200_OK = 0,
+    ARROY_B200_ERR_CUDA = 1,          /* CUDA runtime / driver failure, no device */
+    ARROY_B200_ERR_INVALID = 2,       /* bad argument (cf. Error::InvalidVecDimension) */
+    ARROY_B200_ERR_CANCELLED = 3,     /* cancel callback returned non-zero (Error::BuildCancelled) */
+    ARROY_B200_ERR_CAPACITY = 4,      /* internal table overflow (node records / normals / DFS stack) */
+    ARROY_B200_ERR_NOT_STAGED = 5,    /* items have not been staged on this context */
+    ARROY_B200_ERR_INTERNAL = 6       /* caught C++ exception (cf. Error::Panic) */
+};
+
+/* Distance implementations of src/distance/{euclidean,cosine,dot_product,manhattan}.rs */
+enum {
+    ARROY_B200_EUCLIDEAN = 0,
+    ARROY_B200_COSINE = 1,
+    ARROY_B200_DOT_PRODUCT = 2,
+    ARROY_B200_MANHATTAN = 3
+};
+
+/* ---- context ----------------------------------------------------------------------- */
+
+/* process start / end. `device` is the CUDA ordinal. */
+int32_t arroy_b200_create(int32_t device, arroy_ctx** out);
+void arroy_b200_destroy(arroy_ctx* ctx);
+const char* arroy_b200_last_error(arroy_ctx* ctx);
+/* library version string and the SM architecture the kernels were compiled for */
+const char* arroy_b200_version(void);
+
+/* ---- item staging: replaces ImmutableLeafs::new (src/parallel.rs:271-293) ------------- */
+
+/* `leaf_values[i]` points at the raw stored value of item ids_ascending[i]:
+ * [tag 0x00][Header POD][dim x f32 native endian], byte aligned only
+ * (src/node.rs:224-228, src/unaligned_vector/f32.rs). The library decodes the unaligned
+ * bytes into pinned host memory and uploads them once into float[n][ld] (ld = dim
+ * rounded up to 32 floats, zero padded) plus header arrays. */
+int32_t arroy_b200_stage_items(arroy_ctx* ctx, int32_t metric, uint32_t dim, uint64_t n,
+                               const uint32_t* ids_ascending, const uint8_t* const* leaf_values);
+
+/* Same, from a dense host matrix (n x dim, row-major f32) and optional header arrays
+ * (NULL = header as Writer::add_item would store it, i.e. D::new_header(vector),
+ * src/writer.rs:388-390). Copies straight from the caller's buffer (pin it for full PCIe rate). */
+int32_t arroy_b200_stage_items_flat(arroy_ctx* ctx, int32_t metric, uint32_t dim, uint64_t n,
+                                    const uint32_t* ids_ascending, const float* vectors,
+                                    const float* hdr0, const float* hdr1);
+
+/* Same, but the matrix already lives in device memory of ctx's device (n x dim f32,
+ * row-major, dense). Used by the multi-GPU path after the NCCL broadcast and by
+ * benchmarks whose inputs are resident in HBM. The data is copied into the library's
+ * padded layout (device to device). */
+int32_t arroy_b200_stage_items_device(arroy_ctx* ctx, int32_t metric, uint32_t dim, uint64_t n,
+                                      const uint32_t* ids_ascending, const void* device_vectors);
+
+/* Read back the item headers as the build sees them (n floats each; hdr1 may be NULL). */
+int32_t arroy_b200_item_headers(arroy_ctx* ctx, float* out_hdr0, float* out_hdr1);
+
+/* ---- D::preprocess: replaces DotProduct::preprocess (src/distance/dot_product.rs:119-165,
+ *      called from src/writer.rs:964-976). Updates the staged headers in place and
+ *      returns them so the caller can write them back to storage. No-op for other metrics. */
+int32_t arroy_b200_dot_preprocess(arroy_ctx* ctx, float* out_extra_dim /* n or NULL */,
+                                  float* out_norm /* n or NULL */);
+
+/* ---- side() loops (src/writer.rs:1201-1207, 1424-1430, 1494-1500) ---------------------- */
+
+/* For each row: margin = D::margin(normal, item) bit-exact with the reference's x86_64
+ * AVX+FMA / SSE / scalar summation order; side = margin.is_sign_positive() ? 1 (Right)
+ * : 0 (Left) (src/distance/mod.rs:103-110). out_margin may be NULL. */
+int32_t arroy_b200_side_batch(arroy_ctx* ctx, const float* normal, float hdr0, float hdr1,
+                              const uint32_t* rows, uint64_t n_rows,
+                              uint8_t* out_side, float* out_margin);
+
+/* ---- D::create_split (two_means + normal) on a row subset — src/distance/mod.rs:126-171
+ *      and the four create_split impls. `rng_key` (8 LE words of the 32-byte StdRng seed)
+ *      and `*rng_word_pos` (how many u32 words of the ChaCha12 stream have been consumed)
+ *      describe the caller's StdRng; *rng_word_pos is advanced exactly as the reference
+ *      would advance it. Rows must be ascending. */
+int32_t arroy_b200_create_split(arroy_ctx* ctx, const uint32_t rng_key[8], uint64_t* rng_word_pos,
+                                const uint32_t* rows, uint64_t n_rows,
+                                float* out_normal /* dim */, float* out_hdr /* 2 */);
+
+/* ---- whole forest: replaces the per-tree tasks of src/writer.rs:568-591 / :660-739 ----- */
+
+/* Called once per produced tree node, in no particular order, with the exact bytes
+ * NodeCodec::bytes_encode would produce (src/node.rs:229-241) — what TmpNodes::put
+ * receives in the reference (src/parallel.rs:130-147). Return non-zero to abort. */
+typedef int32_t (*arroy_b200_node_sink)(void* arg, uint32_t node_id, const uint8_t* bytes, uint64_t len);
+/* Polled between device steps; non-zero cancels (BuildOption::cancel, src/writer.rs:116-124). */
+typedef int32_t (*arroy_b200_cancel_fn)(void* arg);
+
+/* Build `n_trees` trees over all staged items. tree_seeds[t] is the 32-byte seed of tree
+ * t's StdRng (src/writer.rs:795); root_ids[t] its pre-allocated root node id
+ * (src/writer.rs:556-561). Non-root node ids are numbered from first_free_node_id in the
+ * order a 1-thread rayon pool produces (last tree first, post-order inside a tree), so the
+ * result is deterministic and equal to the reference's single-thread snapshots.
+ * split_after = max items per Descendants node (src/writer.rs:474-477; 0 = dim).
+ * `out_n_nodes` (optional) receives the number of emitted nodes. */
+int32_t arroy_b200_build_trees(arroy_ctx* ctx, uint32_t n_trees, const uint8_t (*tree_seeds)[32],
+                               const uint32_t* root_ids, uint32_t first_free_node_id,
+                               uint32_t split_after,
+                               arroy_b200_cancel_fn cancel, void* cancel_arg,
+                               arroy_b200_node_sink sink, void* sink_arg,
+                               uint64_t* out_n_nodes);
+
+/* Statistics of the last build on this context (for roofline accounting):
+ * stats[0] = rows that went through side() (sum over scans, retries included)
+ * stats[1] = device steps, stats[2] = create_split calls, stats[3] = random-fallback splits,
+ * stats[4] = device milliseconds of the build loop (CUDA events), stats[5] = ms in scan kernels
+ * (only measured when ARROY_B200_PROFILE=1), stats[6] = tree nodes emitted, stats[7] reserved. */
+int32_t arroy_b200_build_stats(arroy_ctx* ctx, double stats[8]);
+
+/* ---- re-rank: replaces the loop of src/reader.rs:381-399 ------------------------------- */
+
+/* distance = D::built_distance(query, item) for every row, k smallest by
+ * (OrderedFloat(distance), item id) ascending (NaN greatest, -0 == +0), then
+ * D::normalized_distance. `rows` must be ascending and unique (the reference sorts and
+ * dedups first, src/reader.rs:378-379). Writes min(k, n_rows) results. */
+int32_t arroy_b200_rerank(arroy_ctx* ctx, const float* query, float qhdr0, float qhdr1,
+                          const uint32_t* rows, uint64_t n_rows, uint32_t k,
+                          uint32_t* out_rows, float* out_dist, uint32_t* out_len);
+
+/* nq queries in one launch; query q re-ranks rows[row_offsets[q] .. row_offsets[q+1]).
+ * Results for query q are written at out_*[q*k ..], out_len[q] entries valid. */
+int32_t arroy_b200_rerank_batch(arroy_ctx* ctx, uint32_t nq, const float* queries /* nq x dim */,
+                                const float* qhdr0 /* nq or NULL */, const float* qhdr1 /* nq or NULL */,
+                                const uint32_t* rows, const uint64_t* row_offsets /* nq+1 */, uint32_t k,
+                                uint32_t* out_rows, float* out_dist, uint32_t* out_len);
+
+/* ---- synthetic data + timing helpers (bench / tests; not part of the reference seam) ---- */
+
+/* Fill a device matrix (rows x dim f32, dense) with element (i,j) = n-th gen::<f32>() of
+ * StdRng::from_seed(seed), n = (row0+i)*dim + j, minus `centre`. */
+int32_t arroy_b200_synth_device(arroy_ctx* ctx, const uint8_t seed[32], uint32_t dim, uint64_t row0,
+                                uint64_t rows, float centre, void* device_out);
+
+/* Time `iters` launches of the side()/margin scan kernel over `n_rows` staged rows
+ * (rows == NULL: rows 0..n_rows-1) with CUDA events on the library's stream; optional
+ * L2 flush between launches. Returns the average milliseconds per launch. Results stay on
+ * the device (this measures the kernel, not the boundary). */
+int32_t arroy_b200_time_scan(arroy_ctx* ctx, const float* normal, float hdr0, float hdr1,
+                             const uint32_t* rows, uint64_t n_rows, int32_t variant, int32_t iters,
+                             int32_t flush_l2, float* out_ms_avg, uint64_t* out_left_count);
+
+/* Raw device pointers of the staged items (for the NCCL broadcast of the multi-GPU path):
+ * out[0] = float[n][ld] matrix, out[1] = hdr0[n], out[2] = hdr1[n] (may be 0); *out_ld = ld. */
+int32_t arroy_b200_device_ptrs(arroy_ctx* ctx, void* out[3], uint32_t* out_ld);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ARROY_B200_H */
