@@ -41,6 +41,10 @@ SIGNATURES = [
     ("arroy_b200_rerank_batch", C.c_int32, [C.c_void_p, C.c_uint32, _f32p, _f32p, _f32p, _u32p, _u64p, C.c_uint32, _u32p, _f32p, _u32p]),
     ("arroy_b200_synth_device", C.c_int32, [C.c_void_p, _u8p, C.c_uint32, C.c_uint64, C.c_uint64, C.c_float, C.c_void_p]),
     ("arroy_b200_time_scan", C.c_int32, [C.c_void_p, _f32p, C.c_float, C.c_float, _u32p, C.c_uint64, C.c_int32, C.c_int32, C.c_int32, _f32p, _u64p]),
+    ("arroy_b200_build_breakdown", C.c_int32, [C.c_void_p, C.POINTER(C.c_double)]),
+    ("arroy_b200_counters", C.c_int32, [C.c_void_p, _u64p]),
+    ("arroy_b200_timer_start", C.c_int32, [C.c_void_p]),
+    ("arroy_b200_timer_stop", C.c_int32, [C.c_void_p, _f32p]),
     ("arroy_b200_device_ptrs", C.c_int32, [C.c_void_p, C.POINTER(C.c_void_p), _u32p]),
 ]
 
@@ -238,6 +242,25 @@ class Context:
         self._ck(self.lib.arroy_b200_time_scan(self.h, _fp(normal), hdr[0], hdr[1], _up(r), n_rows, variant, iters, 1 if flush_l2 else 0,
                                                C.byref(ms), C.byref(left)))
         return ms.value, left.value
+
+    def build_breakdown(self):
+        st = (C.c_double * 8)()
+        self._ck(self.lib.arroy_b200_build_breakdown(self.h, st))
+        keys = ["setup_ms", "graph_ms", "loop_ms", "d2h_ms", "encode_ms", "graph_launches", "r6", "r7"]
+        return dict(zip(keys, list(st)))
+
+    def counters(self):
+        out = (C.c_uint64 * 4)()
+        self._ck(self.lib.arroy_b200_counters(self.h, out))
+        return {"launches": out[0], "h2d_bytes": out[1], "d2h_bytes": out[2]}
+
+    def timer_start(self):
+        self._ck(self.lib.arroy_b200_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = C.c_float(0)
+        self._ck(self.lib.arroy_b200_timer_stop(self.h, C.byref(ms)))
+        return ms.value
 
     def device_ptrs(self):
         out = (C.c_void_p * 3)()

@@ -64,6 +64,18 @@ struct PinBuf {
     template <class T> T* as() { return static_cast<T*>(p); }
 };
 
+struct Wave {  // device buffers of one wave of trees; kept across builds
+    DevBuf st, frames, recs, perm0, perm1, flags, unit_left, pool, pool_counter, jobs, scratch, active, error, final_ids, keys;
+    void release() {
+        st.release(); frames.release(); recs.release(); perm0.release(); perm1.release(); flags.release(); unit_left.release();
+        pool.release(); pool_counter.release(); jobs.release(); scratch.release(); active.release(); error.release(); final_ids.release(); keys.release();
+    }
+};
+struct HostWave {  // pinned host copies of one wave's results; kept across builds
+    PinBuf recs, final_rows, pool;
+    void release() { recs.release(); final_rows.release(); pool.release(); }
+};
+
 }  // namespace
 
 struct arroy_ctx {
@@ -84,7 +96,13 @@ struct arroy_ctx {
     PinBuf pin;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    bool h1_valid = false;
+    uint64_t n_launches = 0, h2d_bytes = 0, d2h_bytes = 0;  // since create (arroy_b200_counters)
+    cudaEvent_t tev0 = nullptr, tev1 = nullptr;
+    Wave wave;
+    std::vector<HostWave> host_waves;
+    double breakdown[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    std::vector<cudaStream_t> tree_streams;   // one per tree of a wave (asynchronous per-tree chains)
+    std::vector<cudaEvent_t> tree_events;     // join events, [0] = fork
 };
 
 namespace {
@@ -106,6 +124,7 @@ void launch_work(arroy_ctx* c, const Job* jobs, int njobs, int grid) {
     }
     work_kernel<<<grid, WORK_THREADS, smem, c->stream>>>(jobs, njobs, c->items.as<float>(), c->h0.as<float>(), c->dim, c->ld, c->metric);
     CK(cudaGetLastError());
+    c->n_launches += 1;
 }
 
 void compute_norms(arroy_ctx* c, bool with_max) {
@@ -117,6 +136,7 @@ void compute_norms(arroy_ctx* c, bool with_max) {
     if (grid < 1) grid = 1;
     norms_kernel<<<grid, 256, 0, c->stream>>>(c->items.as<float>(), c->n, c->dim, c->ld, c->norms.as<float>(), with_max ? c->maxbits.as<uint32_t>() : nullptr);
     CK(cudaGetLastError());
+    c->n_launches += 1;
 }
 
 void alloc_items(arroy_ctx* c, int metric, uint32_t dim, uint64_t n, const uint32_t* ids) {
@@ -179,14 +199,6 @@ void roaring_serialize(const uint32_t* ids, size_t n, std::vector<uint8_t>& out)
     }
 }
 
-struct Wave {
-    DevBuf st, frames, recs, perm0, perm1, flags, unit_left, pool, pool_counter, jobs, scratch, active, error, final_ids, keys;
-    void release() {
-        st.release(); frames.release(); recs.release(); perm0.release(); perm1.release(); flags.release(); unit_left.release();
-        pool.release(); pool_counter.release(); jobs.release(); scratch.release(); active.release(); error.release(); final_ids.release(); keys.release();
-    }
-};
-
 }  // namespace
 
 // ================================================================================================
@@ -194,18 +206,20 @@ struct Wave {
 // ================================================================================================
 namespace {
 
-struct BuiltTree {
-    std::vector<Record> recs;
-    std::vector<uint32_t> final_rows;  // n entries
+struct BuiltTree {  // views into the pinned HostWave buffers of the context
+    const Record* recs = nullptr;
+    uint32_t n_recs = 0;
+    const uint32_t* final_rows = nullptr;  // n entries
+    const float* pool = nullptr;
 };
 
-void build_wave(arroy_ctx* c, uint32_t t0, uint32_t tw, const uint8_t (*seeds)[32], uint32_t K, uint32_t cap_mult,
-                arroy_b200_cancel_fn cancel, void* cancel_arg, std::vector<BuiltTree>& out_trees, std::vector<float>& out_pool,
-                uint32_t& out_pool_stride) {
+void build_wave(arroy_ctx* c, size_t wave_no, uint32_t t0, uint32_t tw, const uint8_t (*seeds)[32], uint32_t K, uint32_t cap_mult,
+                arroy_b200_cancel_fn cancel, void* cancel_arg, std::vector<BuiltTree>& out_trees, uint32_t& out_pool_stride) {
     const uint64_t n = c->n;
     const uint32_t ld = c->ld;
-    Wave W;
-    struct Guard { Wave& w; ~Guard() { w.release(); } } guard{W};
+    Wave& W = c->wave;
+    auto t_setup = std::chrono::steady_clock::now();
+    auto ms_since = [](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count(); };
     const uint32_t units = (uint32_t)((n + SCAN_UNIT - 1) / SCAN_UNIT);
     const uint64_t leaves_est = n / std::max<uint32_t>(K, 1) + 1;
     const uint64_t rec_cap64 = std::min<uint64_t>(2 * n + 2, std::max<uint64_t>(64, 8 * leaves_est * cap_mult));
@@ -255,6 +269,7 @@ void build_wave(arroy_ctx* c, uint32_t t0, uint32_t tw, const uint8_t (*seeds)[3
     CK(cudaMemcpyAsync(W.active.p, &tw, 4, cudaMemcpyHostToDevice, c->stream));
     init_trees_kernel<<<tw, 256, 0, c->stream>>>(P, W.keys.as<uint32_t>());
     CK(cudaGetLastError());
+    c->n_launches += 2;  // + finalize_kernel below
 
     const size_t ctrl_smem = use_smem ? ws_bytes : 0;
     if (ctrl_smem > 48 * 1024) CK(cudaFuncSetAttribute(control_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctrl_smem));
@@ -262,26 +277,64 @@ void build_wave(arroy_ctx* c, uint32_t t0, uint32_t tw, const uint8_t (*seeds)[3
     if (wsmem > 48 * 1024) CK(cudaFuncSetAttribute(work_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
     const int work_grid = c->sm_count * 3;
 
-    auto launch_step = [&](cudaStream_t s) {
-        control_kernel<<<tw, CTRL_THREADS, ctrl_smem, s>>>(P);
+    // Two schedules over the same kernels:
+    //  * async (default): every tree is its own chain control -> work -> control -> ... on its own
+    //    stream; all chains of the wave are branches of ONE CUDA graph, so the two_means latency of
+    //    one tree overlaps the scans of the others (trees only share the read-only item matrix).
+    //  * lockstep (ARROY_B200_LOCKSTEP=1, also used by ARROY_B200_PROFILE=1): one control launch
+    //    for all trees, then one work launch for all posted jobs; every kernel runs alone, which is
+    //    what the per-launch roofline measurement needs.
+    const bool profile = getenv("ARROY_B200_PROFILE") != nullptr && atoi(getenv("ARROY_B200_PROFILE")) != 0;
+    const bool lockstep = profile || (getenv("ARROY_B200_LOCKSTEP") != nullptr && atoi(getenv("ARROY_B200_LOCKSTEP")) != 0);
+    const bool use_graph = getenv("ARROY_B200_NO_GRAPH") == nullptr && !profile;
+    const int steps_per_batch = lockstep ? 32 : (getenv("ARROY_B200_BATCH") ? std::max(1, atoi(getenv("ARROY_B200_BATCH"))) : 64);
+    const int tree_grid = c->sm_count;  // work CTAs per tree launch in async mode
+    const size_t wsmem1 = work_smem(ld, 1);
+
+    auto launch_step = [&](cudaStream_t s) {  // lockstep: all trees per launch
+        control_kernel<<<tw, CTRL_THREADS, ctrl_smem, s>>>(P, 0u);
         work_kernel<<<work_grid, WORK_THREADS, wsmem, s>>>(P.jobs, (int)tw, P.items, P.ih0, P.d, P.ld, P.metric);
     };
+    auto launch_tree_step = [&](uint32_t t, cudaStream_t s) {  // async: one tree per launch
+        control_kernel<<<1, CTRL_THREADS, ctrl_smem, s>>>(P, t);
+        work_kernel<<<tree_grid, WORK_THREADS, wsmem1, s>>>(P.jobs + t, 1, P.items, P.ih0, P.d, P.ld, P.metric);
+    };
+    if (!lockstep) {
+        while (c->tree_streams.size() < tw) { cudaStream_t st; CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking)); c->tree_streams.push_back(st); }
+        while (c->tree_events.size() < (size_t)tw + 1) { cudaEvent_t ev; CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); c->tree_events.push_back(ev); }
+    }
 
-    const bool use_graph = getenv("ARROY_B200_NO_GRAPH") == nullptr;
-    const int steps_per_batch = 32;
+    CK(cudaStreamSynchronize(c->stream));
+    c->breakdown[0] += ms_since(t_setup);
+    auto t_graph = std::chrono::steady_clock::now();
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t gexec = nullptr;
     if (use_graph) {
         CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
-        for (int i = 0; i < steps_per_batch; ++i) launch_step(c->stream);
+        if (lockstep) { for (int i = 0; i < steps_per_batch; ++i) launch_step(c->stream); }
+        else {
+            CK(cudaEventRecord(c->tree_events[0], c->stream));
+            for (uint32_t t = 0; t < tw; ++t) {
+                cudaStream_t st = c->tree_streams[t];
+                CK(cudaStreamWaitEvent(st, c->tree_events[0], 0));
+                for (int i = 0; i < steps_per_batch; ++i) launch_tree_step(t, st);
+                CK(cudaEventRecord(c->tree_events[1 + t], st));
+                CK(cudaStreamWaitEvent(c->stream, c->tree_events[1 + t], 0));
+            }
+        }
         CK(cudaStreamEndCapture(c->stream, &graph));
         CK(cudaGraphInstantiate(&gexec, graph, 0));
     }
     struct GraphGuard { cudaGraph_t& g; cudaGraphExec_t& e; ~GraphGuard() { if (e) cudaGraphExecDestroy(e); if (g) cudaGraphDestroy(g); } } gg{graph, gexec};
 
+    c->breakdown[1] += ms_since(t_graph);
+    auto t_loop = std::chrono::steady_clock::now();
     c->pin.ensure(64);
     volatile uint32_t* h_active = c->pin.as<uint32_t>();
     volatile int32_t* h_error = reinterpret_cast<volatile int32_t*>(c->pin.as<uint32_t>() + 1);
+    std::vector<cudaEvent_t> pev;
+    struct EvGuard { std::vector<cudaEvent_t>& v; ~EvGuard() { for (auto e : v) cudaEventDestroy(e); } } evg{pev};
+    if (profile) { pev.resize(2 * steps_per_batch); for (auto& e : pev) CK(cudaEventCreate(&e)); }
     uint64_t steps = 0;
     // safety net against a stuck state machine (never hit by a correct build): every step each
     // live tree completes one attempt or one partition
@@ -289,8 +342,30 @@ void build_wave(arroy_ctx* c, uint32_t t0, uint32_t tw, const uint8_t (*seeds)[3
     for (;;) {
         if (steps > max_steps) throw std::runtime_error("forest build did not converge (internal state machine error)");
         if (use_graph) CK(cudaGraphLaunch(gexec, c->stream));
-        else { for (int i = 0; i < steps_per_batch; ++i) launch_step(c->stream); CK(cudaGetLastError()); }
+        else if (profile) {
+            for (int i = 0; i < steps_per_batch; ++i) {
+                control_kernel<<<tw, CTRL_THREADS, ctrl_smem, c->stream>>>(P, 0u);
+                CK(cudaEventRecord(pev[2 * i], c->stream));
+                work_kernel<<<work_grid, WORK_THREADS, wsmem, c->stream>>>(P.jobs, (int)tw, P.items, P.ih0, P.d, P.ld, P.metric);
+                CK(cudaEventRecord(pev[2 * i + 1], c->stream));
+            }
+            CK(cudaStreamSynchronize(c->stream));
+            for (int i = 0; i < steps_per_batch; ++i) { float ms = 0; CK(cudaEventElapsedTime(&ms, pev[2 * i], pev[2 * i + 1])); c->stats[5] += ms; }
+        }
+        else if (lockstep) { for (int i = 0; i < steps_per_batch; ++i) launch_step(c->stream); CK(cudaGetLastError()); }
+        else {  // async without a graph (debugging): fork / join by events
+            CK(cudaEventRecord(c->tree_events[0], c->stream));
+            for (uint32_t t = 0; t < tw; ++t) {
+                cudaStream_t st = c->tree_streams[t];
+                CK(cudaStreamWaitEvent(st, c->tree_events[0], 0));
+                for (int i = 0; i < steps_per_batch; ++i) launch_tree_step(t, st);
+                CK(cudaEventRecord(c->tree_events[1 + t], st));
+                CK(cudaStreamWaitEvent(c->stream, c->tree_events[1 + t], 0));
+            }
+            CK(cudaGetLastError());
+        }
         steps += steps_per_batch;
+        c->n_launches += 2ull * steps_per_batch * (lockstep ? 1 : tw);
         CK(cudaMemcpyAsync((void*)h_active, W.active.p, 4, cudaMemcpyDeviceToHost, c->stream));
         CK(cudaMemcpyAsync((void*)h_error, W.error.p, 4, cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
@@ -302,8 +377,11 @@ void build_wave(arroy_ctx* c, uint32_t t0, uint32_t tw, const uint8_t (*seeds)[3
         if (cancel && cancel(cancel_arg)) throw Cancelled("The corresponding build process has been cancelled");
     }
     c->stats[1] += (double)steps;
+    c->breakdown[2] += ms_since(t_loop);
+    c->breakdown[5] += (double)(steps / steps_per_batch);
+    auto t_d2h = std::chrono::steady_clock::now();
 
-    // results: merge the ping-pong id buffers, then bring everything to the host
+    // results: merge the ping-pong id buffers, then bring everything to (pinned) host memory
     W.final_ids.ensure(4ull * n * tw);
     finalize_kernel<<<dim3(64, tw), 256, 0, c->stream>>>(P, W.final_ids.as<uint32_t>());
     CK(cudaGetLastError());
@@ -312,20 +390,32 @@ void build_wave(arroy_ctx* c, uint32_t t0, uint32_t tw, const uint8_t (*seeds)[3
     CK(cudaMemcpyAsync(st.data(), W.st.p, sizeof(TreeState) * tw, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaMemcpyAsync(&pool_used, W.pool_counter.p, 4, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
-    out_pool.resize((size_t)pool_used * pool_stride);
-    if (pool_used) CK(cudaMemcpyAsync(out_pool.data(), W.pool.p, (size_t)pool_used * pool_stride * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (c->host_waves.size() <= wave_no) c->host_waves.resize(wave_no + 1);
+    HostWave& H = c->host_waves[wave_no];
+    uint64_t total_recs = 0;
+    for (uint32_t t = 0; t < tw; ++t) total_recs += st[t].n_recs;
+    H.pool.ensure(std::max<size_t>(16, (size_t)pool_used * pool_stride * 4));
+    H.recs.ensure(std::max<size_t>(16, sizeof(Record) * total_recs));
+    H.final_rows.ensure(std::max<size_t>(16, 4ull * n * tw));
+    if (pool_used) CK(cudaMemcpyAsync(H.pool.p, W.pool.p, (size_t)pool_used * pool_stride * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(H.final_rows.p, W.final_ids.p, 4ull * n * tw, cudaMemcpyDeviceToHost, c->stream));
     out_pool_stride = pool_stride;
     out_trees.resize(tw);
+    uint64_t rec_off = 0;
     for (uint32_t t = 0; t < tw; ++t) {
-        out_trees[t].recs.resize(st[t].n_recs);
-        out_trees[t].final_rows.resize(n);
-        CK(cudaMemcpyAsync(out_trees[t].recs.data(), W.recs.as<Record>() + (size_t)t * rec_cap, sizeof(Record) * st[t].n_recs, cudaMemcpyDeviceToHost, c->stream));
-        CK(cudaMemcpyAsync(out_trees[t].final_rows.data(), W.final_ids.as<uint32_t>() + (size_t)t * n, 4ull * n, cudaMemcpyDeviceToHost, c->stream));
+        out_trees[t].recs = H.recs.as<Record>() + rec_off;
+        out_trees[t].n_recs = st[t].n_recs;
+        out_trees[t].final_rows = H.final_rows.as<uint32_t>() + (size_t)t * n;
+        out_trees[t].pool = H.pool.as<float>();
+        CK(cudaMemcpyAsync(H.recs.as<Record>() + rec_off, W.recs.as<Record>() + (size_t)t * rec_cap, sizeof(Record) * st[t].n_recs, cudaMemcpyDeviceToHost, c->stream));
+        rec_off += st[t].n_recs;
         c->stats[0] += (double)st[t].scanned;
         c->stats[2] += (double)st[t].n_splits_tried;
         c->stats[3] += (double)st[t].n_random;
     }
     CK(cudaStreamSynchronize(c->stream));
+    c->d2h_bytes += (uint64_t)pool_used * pool_stride * 4 + sizeof(TreeState) * tw + sizeof(Record) * total_recs + 4ull * n * tw;
+    c->breakdown[3] += ms_since(t_d2h);
 }
 
 void do_build(arroy_ctx* c, uint32_t n_trees, const uint8_t (*seeds)[32], const uint32_t* root_ids, uint32_t first_free, uint32_t split_after,
@@ -349,22 +439,20 @@ void do_build(arroy_ctx* c, uint32_t n_trees, const uint8_t (*seeds)[32], const 
     if (const char* e = getenv("ARROY_B200_MAX_WAVE")) max_wave = std::min<uint64_t>(max_wave, (uint64_t)atoi(e));
     max_wave = std::max<uint64_t>(1, std::min<uint64_t>(max_wave, 256));
 
+    for (auto& b : c->breakdown) b = 0;
     CK(cudaEventRecord(c->ev0, c->stream));
     std::vector<std::vector<BuiltTree>> waves;
-    std::vector<std::vector<float>> pools;
     std::vector<uint32_t> wave_t0;
     uint32_t pool_stride = 0;
     for (uint32_t t0 = 0; t0 < n_trees;) {
         uint32_t tw = (uint32_t)std::min<uint64_t>(max_wave, n_trees - t0);
         std::vector<BuiltTree> trees;
-        std::vector<float> pool;
         uint32_t cap_mult = 1;
         for (;;) {
-            try { build_wave(c, t0, tw, seeds, K, cap_mult, cancel, cancel_arg, trees, pool, pool_stride); break; }
+            try { build_wave(c, waves.size(), t0, tw, seeds, K, cap_mult, cancel, cancel_arg, trees, pool_stride); break; }
             catch (const CapacityError&) { if (cap_mult >= 64) throw; cap_mult *= 4; }
         }
         waves.push_back(std::move(trees));
-        pools.push_back(std::move(pool));
         wave_t0.push_back(t0);
         t0 += tw;
     }
@@ -377,22 +465,22 @@ void do_build(arroy_ctx* c, uint32_t n_trees, const uint8_t (*seeds)[32], const 
     // node ids: roots pre-allocated; the rest numbered as a 1-thread rayon pool would (tree tasks
     // LIFO => last tree first; post-order inside a tree) — SURVEY.md Appendix B.4
     std::vector<const BuiltTree*> tree_ptr(n_trees);
-    std::vector<const std::vector<float>*> tree_pool(n_trees);
     for (size_t w = 0; w < waves.size(); ++w)
-        for (size_t i = 0; i < waves[w].size(); ++i) { tree_ptr[wave_t0[w] + i] = &waves[w][i]; tree_pool[wave_t0[w] + i] = &pools[w]; }
+        for (size_t i = 0; i < waves[w].size(); ++i) tree_ptr[wave_t0[w] + i] = &waves[w][i];
     std::vector<uint64_t> base(n_trees);
     uint64_t counter = first_free;
     for (uint32_t k = 0; k < n_trees; ++k) {
         uint32_t t = n_trees - 1 - k;
         base[t] = counter;
-        counter += tree_ptr[t]->recs.size() - 1;
+        counter += tree_ptr[t]->n_recs - 1;
     }
     if (counter > 0xffffffffull) throw CapacityError("node ids exceed u32 (Error::DatabaseFull)");
     uint64_t total_nodes = 0;
-    for (uint32_t t = 0; t < n_trees; ++t) total_nodes += tree_ptr[t]->recs.size();
+    for (uint32_t t = 0; t < n_trees; ++t) total_nodes += tree_ptr[t]->n_recs;
     if (out_n_nodes) *out_n_nodes = total_nodes;
     c->stats[6] = (double)total_nodes;
     if (!sink) return;
+    auto t_enc = std::chrono::steady_clock::now();
 
     // encode NodeCodec bytes (src/node.rs:229-241); trees in parallel, sink calls serialised
     const int hdrf = metric_header_floats(c->metric);
@@ -409,10 +497,10 @@ void do_build(arroy_ctx* c, uint32_t n_trees, const uint8_t (*seeds)[32], const 
                 uint32_t t = next_tree.fetch_add(1);
                 if (t >= n_trees || abort_flag.load()) return;
                 const BuiltTree& T = *tree_ptr[t];
-                const std::vector<float>& pool = *tree_pool[t];
-                const uint32_t root_local = (uint32_t)T.recs.size() - 1;
+                const float* pool = T.pool;
+                const uint32_t root_local = T.n_recs - 1;
                 auto gid = [&](uint32_t li) { return li == root_local ? root_ids[t] : (uint32_t)(base[t] + li); };
-                for (uint32_t li = 0; li < T.recs.size(); ++li) {
+                for (uint32_t li = 0; li < T.n_recs; ++li) {
                     const Record& r = T.recs[li];
                     buf.clear();
                     if (r.kind == REC_DESC) {
@@ -426,7 +514,7 @@ void do_build(arroy_ctx* c, uint32_t n_trees, const uint8_t (*seeds)[32], const 
                         for (int k = 3; k >= 0; --k) buf.push_back((uint8_t)(l >> (8 * k)));
                         for (int k = 3; k >= 0; --k) buf.push_back((uint8_t)(rr >> (8 * k)));
                         if (r.c != NO_SLOT) {
-                            const float* s = pool.data() + (size_t)r.c * pool_stride;
+                            const float* s = pool + (size_t)r.c * pool_stride;
                             size_t o = buf.size();
                             buf.resize(o + 4 * hdrf + 4ull * d);
                             memcpy(buf.data() + o, s, 4 * hdrf);
@@ -444,6 +532,7 @@ void do_build(arroy_ctx* c, uint32_t n_trees, const uint8_t (*seeds)[32], const 
     if (c->n < 100000) nthreads = 1;
     if (nthreads <= 1) worker();
     else { std::vector<std::thread> th; for (int i = 0; i < nthreads; ++i) th.emplace_back(worker); for (auto& x : th) x.join(); }
+    c->breakdown[4] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_enc).count();
     if (abort_flag.load() == 1) throw Cancelled("node sink aborted the build");
     if (abort_flag.load() == 2) throw std::runtime_error(worker_err);
 }
@@ -533,6 +622,9 @@ void do_rerank_batch(arroy_ctx* c, uint32_t nq, const float* queries, const floa
     topk_kernel<<<nq, TOPK_THREADS, 0, c->stream>>>(c->s_keys.as<unsigned long long>(), c->s_dists.as<float>(), c->s_rows.as<uint32_t>(), c->s_off.as<uint64_t>(), k, c->metric,
                                                     c->s_orows.as<uint32_t>(), c->s_odist.as<float>(), c->s_olen.as<uint32_t>());
     CK(cudaGetLastError());
+    c->n_launches += total ? 2 : 1;
+    c->h2d_bytes += (uint64_t)nq * c->dim * 4 + (uint64_t)nq * 4 + (uint64_t)(nq + 1) * 8 + total * 4;
+    c->d2h_bytes += (uint64_t)nq * k * 8 + (uint64_t)nq * 4;
     CK(cudaMemcpyAsync(out_rows, c->s_orows.p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaMemcpyAsync(out_dist, c->s_odist.p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaMemcpyAsync(out_len, c->s_olen.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, c->stream));
@@ -591,6 +683,8 @@ int32_t arroy_b200_create(int32_t device, arroy_ctx** out) {
         CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         CK(cudaEventCreate(&c->ev0));
         CK(cudaEventCreate(&c->ev1));
+        CK(cudaEventCreate(&c->tev0));
+        CK(cudaEventCreate(&c->tev1));
         // fail loudly if the kernels were not built for this device
         cudaFuncAttributes fa;
         CK(cudaFuncGetAttributes(&fa, work_kernel));
@@ -612,8 +706,14 @@ void arroy_b200_destroy(arroy_ctx* c) {
                       &c->s_keys, &c->s_dists, &c->s_q, &c->s_qh0, &c->s_off, &c->s_orows, &c->s_odist, &c->s_olen, &c->s_misc};
     for (auto* b : bufs) b->release();
     c->pin.release();
+    c->wave.release();
+    for (auto& hw : c->host_waves) hw.release();
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->tev0) cudaEventDestroy(c->tev0);
+    if (c->tev1) cudaEventDestroy(c->tev1);
+    for (auto st : c->tree_streams) cudaStreamDestroy(st);
+    for (auto ev : c->tree_events) cudaEventDestroy(ev);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -640,14 +740,25 @@ int32_t arroy_b200_stage_items(arroy_ctx* c, int32_t metric, uint32_t dim, uint6
             uint64_t rows = std::min<uint64_t>(chunk_rows, n - r0);
             if (used[which]) CK(cudaEventSynchronize(done[which]));
             float* b = bufs[which];
-            for (uint64_t i = 0; i < rows; ++i) {
-                const uint8_t* v = leaf_values[r0 + i];
-                if (!v || v[0] != 0) throw ArgError("leaf value does not start with the Leaf tag 0x00");
-                memcpy(&h0[r0 + i], v + 1, 4);
-                if (hf == 2) memcpy(&h1[r0 + i], v + 5, 4);
-                memcpy(b + i * ld, v + 1 + 4 * hf, 4ull * dim);
-                for (uint32_t k = dim; k < ld; ++k) b[i * ld + k] = 0.f;
+            std::atomic<int> bad{0};
+            auto decode = [&](uint64_t i0, uint64_t i1) {
+                for (uint64_t i = i0; i < i1; ++i) {
+                    const uint8_t* v = leaf_values[r0 + i];
+                    if (!v || v[0] != 0) { bad = 1; return; }
+                    memcpy(&h0[r0 + i], v + 1, 4);
+                    if (hf == 2) memcpy(&h1[r0 + i], v + 5, 4);
+                    memcpy(b + i * ld, v + 1 + 4 * hf, 4ull * dim);
+                    for (uint32_t k = dim; k < ld; ++k) b[i * ld + k] = 0.f;
+                }
+            };
+            const unsigned nt = rows * ld * 4 < (4u << 20) ? 1u : std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+            if (nt <= 1) decode(0, rows);
+            else {
+                std::vector<std::thread> th;
+                for (unsigned t = 0; t < nt; ++t) th.emplace_back(decode, rows * t / nt, rows * (t + 1) / nt);
+                for (auto& x : th) x.join();
             }
+            if (bad.load()) throw ArgError("leaf value does not start with the Leaf tag 0x00");
             CK(cudaMemcpyAsync(c->items.as<float>() + r0 * ld, b, rows * ld * 4, cudaMemcpyHostToDevice, c->stream));
             CK(cudaEventRecord(done[which], c->stream));
             used[which] = true;
@@ -658,6 +769,7 @@ int32_t arroy_b200_stage_items(arroy_ctx* c, int32_t metric, uint32_t dim, uint6
         }
         CK(cudaStreamSynchronize(c->stream));
         cudaEventDestroy(done[0]); cudaEventDestroy(done[1]);
+        c->h2d_bytes += (uint64_t)n * ld * 4 + 8 * n;
         c->staged = true;
     });
 }
@@ -675,6 +787,7 @@ int32_t arroy_b200_stage_items_flat(arroy_ctx* c, int32_t metric, uint32_t dim, 
             if (hdr1) CK(cudaMemcpyAsync(c->h1.p, hdr1, n * 4, cudaMemcpyHostToDevice, c->stream));
         }
         CK(cudaStreamSynchronize(c->stream));
+        c->h2d_bytes += (uint64_t)n * dim * 4 + (hdr0 ? 4 * n : 0) + (hdr1 ? 4 * n : 0);
         c->staged = true;
     });
 }
@@ -852,6 +965,26 @@ int32_t arroy_b200_time_scan(arroy_ctx* c, const float* normal, float hdr0, floa
     });
 }
 
+int32_t arroy_b200_build_breakdown(arroy_ctx* c, double out[8]) {
+    return guarded(c, [&] { for (int i = 0; i < 8; ++i) out[i] = c->breakdown[i]; });
+}
+
+int32_t arroy_b200_counters(arroy_ctx* c, uint64_t out[4]) {
+    return guarded(c, [&] { out[0] = c->n_launches; out[1] = c->h2d_bytes; out[2] = c->d2h_bytes; out[3] = 0; });
+}
+
+int32_t arroy_b200_timer_start(arroy_ctx* c) {
+    return guarded(c, [&] { set_device(c); CK(cudaStreamSynchronize(c->stream)); CK(cudaEventRecord(c->tev0, c->stream)); });
+}
+int32_t arroy_b200_timer_stop(arroy_ctx* c, float* out_ms) {
+    return guarded(c, [&] {
+        set_device(c);
+        CK(cudaEventRecord(c->tev1, c->stream));
+        CK(cudaEventSynchronize(c->tev1));
+        CK(cudaEventElapsedTime(out_ms, c->tev0, c->tev1));
+    });
+}
+
 int32_t arroy_b200_device_ptrs(arroy_ctx* c, void* out[3], uint32_t* out_ld) {
     return guarded(c, [&] {
         require_staged(c);
@@ -861,3 +994,6 @@ int32_t arroy_b200_device_ptrs(arroy_ctx* c, void* out[3], uint32_t* out_ld) {
 }
 
 }  // extern "C"
+
+// C++ host mirror of the reference's Writer / Reader (client of the C ABI above)
+#include "host.hpp"

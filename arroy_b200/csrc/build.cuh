@@ -260,7 +260,7 @@ __device__ uint32_t cta_exclusive_scan(uint32_t* v, uint32_t n, uint32_t* sm_tmp
 
 enum : int { ACT_NONE = 0, ACT_SPLIT = 1, ACT_PART_INLINE = 2, ACT_RANDOM = 3, ACT_EXIT = 4 };
 
-__global__ void __launch_bounds__(CTRL_THREADS, 1) control_kernel(BuildParams P) {
+__global__ void __launch_bounds__(CTRL_THREADS, 1) control_kernel(BuildParams P, uint32_t tree_base) {
     extern __shared__ __align__(16) unsigned char ctrl_smem[];
     __shared__ TwoMeansShared TM;
     __shared__ uint32_t sm_tmp[CTRL_THREADS + 1];
@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(CTRL_THREADS, 1) control_kernel(BuildParams P)
     __shared__ Frame sm_frames[SMF];
     __shared__ TreeState S;
 
-    const uint32_t t = blockIdx.x;
+    const uint32_t t = blockIdx.x + tree_base;
     Job& job = P.jobs[t];
     if (P.st[t].phase == PH_DONE) return;  // job.kind already JOB_NONE
     if (*P.error != ERR_NONE) return;

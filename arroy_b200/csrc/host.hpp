@@ -1,0 +1,739 @@
+// host.hpp — C++ host mirror of arroy's Writer / ArroyBuilder / Reader / QueryBuilder above the
+// device boundary (include/arroy_b200.h). See include/arroy_b200_host.h for the interface map.
+// It is a *client* of the C ABI exactly as a fork of the Rust crate would be: every O(N*d) loop
+// (item staging, preprocess, side() scans inside the forest build, re-rank) goes through
+// arroy_b200_* calls; what stays here is the reference's host control flow:
+//   key/value byte formats     src/key.rs:56-83, src/node.rs:218-282, src/metadata.rs:21-61, src/version.rs:39-49
+//   Writer::build              src/writer.rs:487-629 (fresh-build path; see DESIGN.md for the incremental path)
+//   target_n_trees             src/writer.rs:1358-1394
+//   seed chain                 src/writer.rs:575, :795
+//   Reader::open / nns_by_leaf src/reader.rs:138-176, :317-401 (the priority-queue tree walk, :338-374)
+#pragma once
+#include <array>
+#include <chrono>
+#include <cmath>
+#include <functional>
+#include <map>
+#include <memory>
+#include <queue>
+
+#include "../../include/arroy_b200_host.h"
+
+namespace arroy_host {
+
+using Key8 = std::array<uint8_t, 8>;
+enum : uint8_t { MODE_METADATA = 0, MODE_UPDATED = 1, MODE_TREE = 2, MODE_ITEM = 3 };  // src/node_id.rs:11-21
+
+inline Key8 make_key(uint16_t index, uint8_t mode, uint32_t item) {  // src/key.rs:56-68
+    return Key8{(uint8_t)(index >> 8), (uint8_t)index, mode, (uint8_t)(item >> 24), (uint8_t)(item >> 16), (uint8_t)(item >> 8), (uint8_t)item, 0};
+}
+inline uint32_t key_item(const Key8& k) { return ((uint32_t)k[3] << 24) | ((uint32_t)k[4] << 16) | ((uint32_t)k[5] << 8) | k[6]; }
+
+inline const char* metric_name(int m) {
+    switch (m) {
+        case 0: return "euclidean";
+        case 1: return "cosine";
+        case 2: return "dot-product";
+        default: return "manhattan";
+    }
+}
+inline int header_floats(int m) { return m == 2 ? 2 : 1; }
+
+struct HostError : std::runtime_error {
+    int code;
+    HostError(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+inline std::string& tls_error() { static thread_local std::string e; return e; }
+
+// ---- exact host arithmetic for the tree walk (one D::margin per popped split node) --------------
+// Same summation orders as the device code (exact.cuh), written as portable scalar C++; compiled
+// with -ffp-contract=off so only the explicit fmaf fuses.
+inline float host_dot(const float* a, const float* b, size_t n) {
+    if (n >= 32) {
+        size_t m = n - (n % 32);
+        float acc[32];
+        for (int l = 0; l < 32; ++l) acc[l] = 0.f;
+        for (size_t i = 0; i < m; i += 32)
+            for (int l = 0; l < 32; ++l) acc[l] = __builtin_fmaf(a[i + l], b[i + l], acc[l]);
+        float h[4];
+        for (int k = 0; k < 4; ++k) {
+            const float* x = acc + 8 * k;
+            float x0 = x[4] + x[0], x1 = x[5] + x[1], x2 = x[6] + x[2], x3 = x[7] + x[3];
+            h[k] = (x0 + x2) + (x1 + x3);
+        }
+        float r = ((h[0] + h[1]) + h[2]) + h[3];
+        for (size_t i = m; i < n; ++i) r += a[i] * b[i];
+        return r;
+    }
+    if (n >= 16) {
+        size_t m = n - (n % 16);
+        float acc[16];
+        for (int l = 0; l < 16; ++l) acc[l] = 0.f;
+        for (size_t i = 0; i < m; i += 16)
+            for (int l = 0; l < 16; ++l) acc[l] = a[i + l] * b[i + l] + acc[l];
+        float h[4];
+        for (int k = 0; k < 4; ++k) { const float* x = acc + 4 * k; h[k] = (x[0] + x[2]) + (x[1] + x[3]); }
+        float r = ((h[0] + h[1]) + h[2]) + h[3];
+        for (size_t i = m; i < n; ++i) r += a[i] * b[i];
+        return r;
+    }
+    float s = 0.0f;
+    for (size_t i = 0; i < n; ++i) s += a[i] * b[i];
+    return s;
+}
+inline float host_margin(int metric, const float* nv, float nh0, const float* qv, float qh0, size_t d) {
+    float dot = host_dot(nv, qv, d);
+    if (metric == 1) return dot;                    // cosine.rs:87-89
+    if (metric == 2) return dot + nh0 * qh0;        // dot_product.rs:115-117
+    return nh0 + dot;                               // euclidean.rs:79-81, manhattan.rs:82-84
+}
+inline float f32_min(float a, float b) { if (a != a) return b; if (b != b) return a; return a < b ? a : b; }
+
+inline uint64_t target_n_trees(int64_t n_trees_opt, uint64_t dimensions, uint64_t n_items, uint64_t n_roots) {  // writer.rs:1358-1394
+    if (n_trees_opt >= 0) return (uint64_t)n_trees_opt;
+    double nb_vec = (double)n_items, nb_trees;
+    if (nb_vec < 10000.0) nb_trees = std::pow(2.0, std::log2(nb_vec) - 6.0);
+    else nb_trees = std::pow(2.0, std::log10(nb_vec) + std::log10((double)dimensions) + std::pow(768.0 / (double)dimensions, 4.0));
+    double c = std::ceil(nb_trees);
+    uint64_t n = (!(c == c) || c <= 0.0) ? 0 : (c >= 18446744073709551615.0 ? UINT64_MAX : (uint64_t)c);
+    if (n_roots > n) {
+        uint64_t rm = n_roots - n;
+        if ((double)rm / (double)n < 0.20) n = n_roots;
+    }
+    return n;
+}
+
+// RoaringBitmap::deserialize_from for the no-run-container portable format
+inline void roaring_deserialize(const uint8_t* b, size_t len, std::vector<uint32_t>& out) {
+    auto r32 = [&](size_t o) { uint32_t v; memcpy(&v, b + o, 4); return v; };
+    auto r16 = [&](size_t o) { uint16_t v; memcpy(&v, b + o, 2); return v; };
+    if (len < 8 || r32(0) != 12346u) throw HostError(ARROY_ERR_PANIC, "unsupported roaring cookie");
+    uint32_t n = r32(4);
+    size_t off = 8 + 8 * (size_t)n;
+    for (uint32_t i = 0; i < n; ++i) {
+        uint32_t key = r16(8 + 4 * i), card = (uint32_t)r16(8 + 4 * i + 2) + 1;
+        if (card > 4096) {
+            for (uint32_t w = 0; w < 8192; ++w) { uint8_t byte = b[off + w]; while (byte) { int bit = __builtin_ctz(byte); out.push_back((key << 16) | (w * 8 + bit)); byte &= byte - 1; } }
+            off += 8192;
+        } else {
+            for (uint32_t k = 0; k < card; ++k) out.push_back((key << 16) | r16(off + 2 * k));
+            off += 2 * (size_t)card;
+        }
+    }
+}
+
+}  // namespace arroy_host
+
+struct arroy_env {
+    std::map<arroy_host::Key8, std::string> kv;
+    std::mutex mu;
+    uint64_t generation = 0;  // bumped on every write; lets a context know its staged items are stale
+};
+struct arroy_rng {
+    ab::Rng r;
+};
+struct arroy_writer {
+    arroy_env* env;
+    uint16_t index;
+    uint32_t dims;
+    int metric;
+    double timings[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+};
+struct arroy_reader {
+    arroy_env* env;
+    arroy_ctx* ctx;
+    uint16_t index;
+    uint32_t dims;
+    int metric;
+    std::vector<uint32_t> roots;
+    std::vector<uint32_t> items;   // ascending ids (metadata.items)
+    // decoded tree nodes, indexed by node id
+    struct Node { uint8_t kind = 0; bool has_normal = false; uint32_t left = 0, right = 0; uint32_t normal_off = 0; float h0 = 0, h1 = 0; uint32_t desc_off = 0, desc_len = 0; };
+    std::vector<Node> nodes;
+    std::vector<float> normals;     // d floats per split node with a normal
+    std::vector<uint32_t> desc;     // concatenated descendant id lists
+    std::vector<float> hdr0, hdr1;  // item headers (query by item)
+    bool staged = false;
+};
+
+namespace arroy_host {
+
+using clk = std::chrono::steady_clock;
+inline double ms_since(clk::time_point t0) { return std::chrono::duration<double, std::milli>(clk::now() - t0).count(); }
+
+template <class F>
+int32_t hguard(F&& f) {
+    try { f(); return 0; }
+    catch (const HostError& e) { tls_error() = e.what(); return e.code; }
+    catch (const std::exception& e) { tls_error() = std::string("Unexpected panic in: ") + e.what(); return ARROY_ERR_PANIC; }
+    catch (...) { tls_error() = "Unexpected panic in: unknown"; return ARROY_ERR_PANIC; }
+}
+inline void dev_ck(arroy_ctx* ctx, int32_t rc) {
+    if (rc == ARROY_B200_OK) return;
+    std::string msg = arroy_b200_last_error(ctx);
+    if (rc == ARROY_B200_ERR_CANCELLED) throw HostError(ARROY_ERR_BUILD_CANCELLED, "The corresponding build process has been cancelled");
+    throw HostError(rc, msg);
+}
+
+inline std::string encode_leaf(int metric, const float* v, uint32_t d, float h0, float h1) {  // src/node.rs:224-228
+    std::string s;
+    s.resize(1 + 4 * header_floats(metric) + 4ull * d);
+    s[0] = 0;
+    memcpy(&s[1], &h0, 4);
+    if (header_floats(metric) == 2) memcpy(&s[5], &h1, 4);
+    memcpy(&s[1 + 4 * header_floats(metric)], v, 4ull * d);
+    return s;
+}
+
+// D::new_header (cosine.rs:39-41: norm; others zero). The cosine norm is left 0 here and filled in
+// by the device at build time? No: the stored header must be right at add_item time, so compute it
+// with the exact host dot.
+inline void new_header(int metric, const float* v, uint32_t d, float& h0, float& h1) {
+    h0 = 0.f; h1 = 0.f;
+    if (metric == 1) h0 = std::sqrt(host_dot(v, v, d));
+}
+
+inline void put_item(arroy_writer* w, uint32_t item, const float* v) {  // Writer::add_item — src/writer.rs:380-395
+    float h0, h1;
+    new_header(w->metric, v, w->dims, h0, h1);
+    w->env->kv[make_key(w->index, MODE_ITEM, item)] = encode_leaf(w->metric, v, w->dims, h0, h1);
+    w->env->kv[make_key(w->index, MODE_UPDATED, item)] = std::string();
+    w->env->generation++;
+}
+
+struct ItemView { std::vector<uint32_t> ids; std::vector<const uint8_t*> ptrs; std::vector<size_t> sizes; };
+inline ItemView collect_items(arroy_env* env, uint16_t index) {
+    ItemView v;
+    auto it = env->kv.lower_bound(make_key(index, MODE_ITEM, 0));
+    for (; it != env->kv.end() && it->first[0] == (uint8_t)(index >> 8) && it->first[1] == (uint8_t)index && it->first[2] == MODE_ITEM; ++it) {
+        v.ids.push_back(key_item(it->first));
+        v.ptrs.push_back(reinterpret_cast<const uint8_t*>(it->second.data()));
+        v.sizes.push_back(it->second.size());
+    }
+    return v;
+}
+inline void erase_mode(arroy_env* env, uint16_t index, uint8_t mode) {
+    auto b = env->kv.lower_bound(make_key(index, mode, 0));
+    auto e = b;
+    while (e != env->kv.end() && e->first[0] == (uint8_t)(index >> 8) && e->first[1] == (uint8_t)index && e->first[2] == mode) ++e;
+    env->kv.erase(b, e);
+}
+inline std::string encode_metadata(int metric, uint32_t dims, const std::vector<uint32_t>& items, const std::vector<uint32_t>& roots) {  // metadata.rs:21-44
+    std::vector<uint8_t> bm;
+    ::roaring_serialize(items.data(), items.size(), bm);
+    std::string out = metric_name(metric);
+    out.push_back('\0');
+    uint8_t be[4] = {(uint8_t)(dims >> 24), (uint8_t)(dims >> 16), (uint8_t)(dims >> 8), (uint8_t)dims};
+    out.append(reinterpret_cast<char*>(be), 4);
+    uint32_t sz = (uint32_t)bm.size();
+    uint8_t bs[4] = {(uint8_t)(sz >> 24), (uint8_t)(sz >> 16), (uint8_t)(sz >> 8), (uint8_t)sz};
+    out.append(reinterpret_cast<char*>(bs), 4);
+    out.append(reinterpret_cast<char*>(bm.data()), bm.size());
+    out.append(reinterpret_cast<const char*>(roots.data()), 4 * roots.size());  // native endian (ItemIds::from_slice)
+    return out;
+}
+struct Metadata { std::string distance; uint32_t dims = 0; std::vector<uint32_t> items, roots; };
+inline bool read_metadata(arroy_env* env, uint16_t index, Metadata& m) {
+    auto it = env->kv.find(make_key(index, MODE_METADATA, 0));
+    if (it == env->kv.end()) return false;
+    const std::string& s = it->second;
+    size_t z = s.find('\0');
+    m.distance = s.substr(0, z);
+    const uint8_t* b = reinterpret_cast<const uint8_t*>(s.data()) + z + 1;
+    m.dims = ((uint32_t)b[0] << 24) | ((uint32_t)b[1] << 16) | ((uint32_t)b[2] << 8) | b[3];
+    uint32_t sz = ((uint32_t)b[4] << 24) | ((uint32_t)b[5] << 16) | ((uint32_t)b[6] << 8) | b[7];
+    roaring_deserialize(b + 8, sz, m.items);
+    size_t rest = s.size() - (z + 1 + 8 + sz);
+    m.roots.resize(rest / 4);
+    memcpy(m.roots.data(), b + 8 + sz, rest);
+    return true;
+}
+inline void write_version(arroy_env* env, uint16_t index) {  // version.rs:39-49, Version::current() = 0.7.0
+    const uint8_t v[12] = {0, 0, 0, 0, 0, 0, 0, 7, 0, 0, 0, 0};
+    env->kv[make_key(index, MODE_METADATA, 1)] = std::string(reinterpret_cast<const char*>(v), 12);
+}
+
+struct SinkArg { arroy_env* env; uint16_t index; uint64_t bytes; };
+inline int32_t tree_sink(void* arg, uint32_t node_id, const uint8_t* bytes, uint64_t len) {
+    auto* a = static_cast<SinkArg*>(arg);
+    a->env->kv[make_key(a->index, MODE_TREE, node_id)] = std::string(reinterpret_cast<const char*>(bytes), len);
+    a->bytes += len;
+    return 0;
+}
+
+inline void writer_build(arroy_writer* w, arroy_ctx* ctx, arroy_rng* rng, int64_t n_trees_opt, uint64_t split_after,
+                         arroy_b200_cancel_fn cancel, void* cancel_arg, arroy_progress_fn progress, void* progress_arg) {
+    arroy_env* env = w->env;
+    std::lock_guard<std::mutex> lk(env->mu);
+    for (auto& t : w->timings) t = 0;
+    auto t_all = clk::now();
+    auto step = [&](const char* name) { if (progress) progress(progress_arg, name); };
+    auto cancelled = [&]() { if (cancel && cancel(cancel_arg)) throw HostError(ARROY_ERR_BUILD_CANCELLED, "The corresponding build process has been cancelled"); };
+    const uint16_t index = w->index;
+    const uint32_t d = w->dims;
+    const int hf = header_floats(w->metric);
+
+    // pre_process_items — writer.rs:964-976 (DotProduct only: needs the items on the device)
+    step("PreProcessingTheItems");
+    cancelled();
+    ItemView items = collect_items(env, index);
+    const uint64_t n = items.ids.size();
+    const size_t leaf_len = 1 + 4 * hf + 4ull * d;
+    for (uint64_t i = 0; i < n; ++i)
+        if (items.sizes[i] != leaf_len) throw HostError(ARROY_ERR_PANIC, "items of different sizes in one index");
+    auto t0 = clk::now();
+    const uint64_t K_early = split_after ? split_after : d;
+    const bool needs_device = n > K_early || (w->metric == ARROY_B200_DOT_PRODUCT && n > 0);
+    if (needs_device) {
+        if (!ctx) throw HostError(ARROY_B200_ERR_CUDA, "no CUDA device context: arroy_b200 has no CPU fallback");
+        dev_ck(ctx, arroy_b200_stage_items(ctx, w->metric, d, n, items.ids.data(), items.ptrs.data()));
+        w->timings[0] = ms_since(t0);
+        w->timings[5] = (double)n * (((d + 31) & ~31u) * 4.0 + 8.0);
+    }
+    if (w->metric == ARROY_B200_DOT_PRODUCT && n > 0) {
+        t0 = clk::now();
+        std::vector<float> extra(n), norm(n);
+        dev_ck(ctx, arroy_b200_dot_preprocess(ctx, extra.data(), norm.data()));
+        for (uint64_t i = 0; i < n; ++i) {  // cursor.put_current — dot_product.rs:154-160
+            std::string& v = env->kv[make_key(index, MODE_ITEM, items.ids[i])];
+            memcpy(&v[1], &extra[i], 4);
+            memcpy(&v[5], &norm[i], 4);
+        }
+        w->timings[1] = ms_since(t0);
+    }
+    step("RetrievingTheItemsIds");
+    cancelled();
+    step("RetrieveTheUpdatedItems");
+    std::vector<uint32_t> updated;
+    {
+        auto b = env->kv.lower_bound(make_key(index, MODE_UPDATED, 0));
+        auto e = b;
+        while (e != env->kv.end() && e->first[0] == (uint8_t)(index >> 8) && e->first[1] == (uint8_t)index && e->first[2] == MODE_UPDATED) { updated.push_back(key_item(e->first)); ++e; }
+        env->kv.erase(b, e);
+    }
+    env->generation++;
+    const uint64_t K = split_after ? split_after : d;
+    if (n <= K) {  // clear_db_and_create_a_single_leaf — writer.rs:916-962
+        step("WritingTheDescendantsAndMetadata");
+        erase_mode(env, index, MODE_TREE);
+        std::vector<uint32_t> roots;
+        if (n > 0) {
+            std::vector<uint8_t> buf;
+            buf.push_back(1);
+            ::roaring_serialize(items.ids.data(), items.ids.size(), buf);
+            env->kv[make_key(index, MODE_TREE, 0)] = std::string(reinterpret_cast<char*>(buf.data()), buf.size());
+            roots.push_back(0);
+        }
+        cancelled();
+        env->kv[make_key(index, MODE_METADATA, 0)] = encode_metadata(w->metric, d, items.ids, roots);
+        write_version(env, index);
+        w->timings[4] = ms_since(t_all);
+        return;
+    }
+    Metadata old;
+    bool had = read_metadata(env, index, old);
+    std::vector<uint32_t> roots = had ? old.roots : std::vector<uint32_t>();
+    const uint64_t target = target_n_trees(n_trees_opt, d, n, roots.size());
+    step("DeletingExtraTrees");
+    if (!roots.empty()) {
+        if (updated.empty() && roots.size() == target) {  // nothing changed: the forest stays as it is
+            step("WriteTheMetadata");
+            env->kv[make_key(index, MODE_METADATA, 0)] = encode_metadata(w->metric, d, items.ids, roots);
+            write_version(env, index);
+            w->timings[4] = ms_since(t_all);
+            return;
+        }
+        // Incremental insert/delete in existing trees (writer.rs:846-889, :978-1114) is row "next #3"
+        // of SURVEY.md §8f: until it lands the forest is rebuilt from scratch, which yields a valid
+        // (but not snapshot-identical) index.
+        erase_mode(env, index, MODE_TREE);
+        roots.clear();
+    }
+    step("RetrievingTheItems");
+    step("RetrieveTheLargeDescendants");
+    if (target > 0xffffffffull) throw HostError(ARROY_ERR_DATABASE_FULL, "Database full. Arroy cannot generate enough internal IDs for your items");
+    for (uint64_t t = 0; t < target; ++t) roots.push_back((uint32_t)t);  // concurrent_node_ids.next() — writer.rs:556-561
+    // seed chain — writer.rs:575 (rng1 = from_seed(rng.gen())), :795 (one from_seed(rng1.gen()) per tree)
+    uint8_t s1[32];
+    rng->r.gen_seed(s1);
+    uint32_t key1[8];
+    for (int i = 0; i < 8; ++i) key1[i] = (uint32_t)s1[4 * i] | ((uint32_t)s1[4 * i + 1] << 8) | ((uint32_t)s1[4 * i + 2] << 16) | ((uint32_t)s1[4 * i + 3] << 24);
+    ab::Rng rng1;
+    rng1.init(key1, 0);
+    std::vector<std::array<uint8_t, 32>> seeds(target);
+    for (uint64_t t = 0; t < target; ++t) rng1.gen_seed(seeds[t].data());
+    step("CreateTreesForItems");
+    t0 = clk::now();
+    SinkArg sa{env, index, 0};
+    uint64_t n_nodes = 0;
+    dev_ck(ctx, arroy_b200_build_trees(ctx, (uint32_t)target, reinterpret_cast<const uint8_t(*)[32]>(seeds.data()), roots.data(), (uint32_t)target,
+                                       (uint32_t)split_after, cancel, cancel_arg, tree_sink, &sa, &n_nodes));
+    w->timings[2] = ms_since(t0);
+    w->timings[6] = (double)sa.bytes;
+    step("WriteTheMetadata");
+    t0 = clk::now();
+    env->kv[make_key(index, MODE_METADATA, 0)] = encode_metadata(w->metric, d, items.ids, roots);
+    write_version(env, index);
+    env->generation++;
+    w->timings[3] = ms_since(t0);
+    w->timings[4] = ms_since(t_all);
+}
+
+// ---- Reader ---------------------------------------------------------------------------------------
+inline void reader_open(arroy_env* env, uint16_t index, int metric, arroy_ctx* ctx, arroy_reader** out) {
+    std::lock_guard<std::mutex> lk(env->mu);
+    Metadata md;
+    if (!read_metadata(env, index, md))
+        throw HostError(ARROY_ERR_MISSING_METADATA, "Metadata are missing on index " + std::to_string(index) + ", You must build your database before attempting to read it");
+    if (md.distance != metric_name(metric))
+        throw HostError(ARROY_ERR_UNMATCHING_DISTANCE, "Invalid distance provided. Got " + std::string(metric_name(metric)) + " but expected " + md.distance);
+    {
+        auto it = env->kv.lower_bound(make_key(index, MODE_UPDATED, 0));
+        if (it != env->kv.end() && it->first[0] == (uint8_t)(index >> 8) && it->first[1] == (uint8_t)index && it->first[2] == MODE_UPDATED)
+            throw HostError(ARROY_ERR_NEED_BUILD, "The trees have not been built after an update on index " + std::to_string(index));
+    }
+    auto r = std::unique_ptr<arroy_reader>(new arroy_reader());
+    r->env = env; r->ctx = ctx; r->index = index; r->metric = metric; r->dims = md.dims;
+    r->roots = md.roots; r->items = md.items;
+    const uint32_t d = md.dims;
+    const int hf = header_floats(metric);
+    // decode the tree nodes once (the reference decodes per access from the LMDB page)
+    auto it = env->kv.lower_bound(make_key(index, MODE_TREE, 0));
+    for (; it != env->kv.end() && it->first[0] == (uint8_t)(index >> 8) && it->first[1] == (uint8_t)index && it->first[2] == MODE_TREE; ++it) {
+        uint32_t id = key_item(it->first);
+        if (r->nodes.size() <= id) r->nodes.resize((size_t)id + 1);
+        arroy_reader::Node& nd = r->nodes[id];
+        const uint8_t* b = reinterpret_cast<const uint8_t*>(it->second.data());
+        size_t len = it->second.size();
+        if (b[0] == 1) {
+            nd.kind = 1;
+            nd.desc_off = (uint32_t)r->desc.size();
+            roaring_deserialize(b + 1, len - 1, r->desc);
+            nd.desc_len = (uint32_t)r->desc.size() - nd.desc_off;
+        } else if (b[0] == 2) {
+            nd.kind = 2;
+            nd.left = ((uint32_t)b[1] << 24) | ((uint32_t)b[2] << 16) | ((uint32_t)b[3] << 8) | b[4];
+            nd.right = ((uint32_t)b[5] << 24) | ((uint32_t)b[6] << 16) | ((uint32_t)b[7] << 8) | b[8];
+            if (len > 9) {
+                nd.has_normal = true;
+                memcpy(&nd.h0, b + 9, 4);
+                if (hf == 2) memcpy(&nd.h1, b + 13, 4);
+                nd.normal_off = (uint32_t)(r->normals.size() / d);
+                size_t o = r->normals.size();
+                r->normals.resize(o + d);
+                memcpy(&r->normals[o], b + 9 + 4 * hf, 4ull * d);
+            }
+        } else throw HostError(ARROY_ERR_PANIC, "Did not recognize node tag type");
+    }
+    // items: keep the headers for by_item; the vectors are staged on the device lazily, at the first
+    // query that has candidates to re-rank
+    ItemView iv = collect_items(env, index);
+    if (iv.ids != r->items) throw HostError(ARROY_ERR_NEED_BUILD, "The trees have not been built after an update on index " + std::to_string(index));
+    r->hdr0.resize(iv.ids.size());
+    r->hdr1.assign(iv.ids.size(), 0.f);
+    for (size_t i = 0; i < iv.ids.size(); ++i) { memcpy(&r->hdr0[i], iv.ptrs[i] + 1, 4); if (hf == 2) memcpy(&r->hdr1[i], iv.ptrs[i] + 5, 4); }
+    *out = r.release();
+}
+
+inline void ensure_staged(arroy_reader* r) {
+    if (r->staged) return;
+    if (!r->ctx) throw HostError(ARROY_B200_ERR_CUDA, "no CUDA device context: arroy_b200 has no CPU fallback");
+    std::lock_guard<std::mutex> lk(r->env->mu);
+    ItemView iv = collect_items(r->env, r->index);
+    if (iv.ids != r->items) throw HostError(ARROY_ERR_NEED_BUILD, "The trees have not been built after an update on index " + std::to_string(r->index));
+    dev_ck(r->ctx, arroy_b200_stage_items(r->ctx, r->metric, r->dims, iv.ids.size(), iv.ids.data(), iv.ptrs.data()));
+    r->staged = true;
+}
+
+inline int64_t row_of(const arroy_reader* r, uint32_t item) {
+    auto it = std::lower_bound(r->items.begin(), r->items.end(), item);
+    if (it == r->items.end() || *it != item) return -1;
+    return it - r->items.begin();
+}
+
+struct QE { float dist; uint32_t node; };
+struct QLess {  // max-heap on (OrderedFloat(dist), NodeId): NaN greatest, -0 == +0 — reader.rs:338-342
+    bool operator()(const QE& a, const QE& b) const {
+        bool an = a.dist != a.dist, bn = b.dist != b.dist;
+        if (an || bn) { if (an && bn) return a.node < b.node; return bn; }
+        if (a.dist < b.dist) return true;
+        if (a.dist > b.dist) return false;
+        return a.node < b.node;
+    }
+};
+
+// the candidate-collecting walk of nns_by_leaf — reader.rs:328-379. Returns sorted unique ROW indices.
+inline void tree_walk(const arroy_reader* r, const float* qv, float qh0, uint64_t count, uint64_t search_k_opt, uint64_t oversampling_opt,
+                      const std::vector<uint32_t>* candidates, std::vector<uint32_t>& out_rows) {
+    out_rows.clear();
+    if (r->items.empty()) return;
+    unsigned __int128 sk = search_k_opt ? (unsigned __int128)search_k_opt : (unsigned __int128)count * r->roots.size();
+    sk *= oversampling_opt ? oversampling_opt : 1;  // D::DEFAULT_OVERSAMPLING = 1
+    const uint64_t search_k = sk > (unsigned __int128)UINT64_MAX ? UINT64_MAX : (uint64_t)sk;
+    std::priority_queue<QE, std::vector<QE>, QLess> queue;
+    for (uint32_t root : r->roots) queue.push(QE{INFINITY, root});
+    std::vector<uint32_t> nns;
+    const size_t d = r->dims;
+    while (nns.size() < search_k) {
+        if (queue.empty()) break;
+        QE top = queue.top();
+        queue.pop();
+        if (top.node >= r->nodes.size() || r->nodes[top.node].kind == 0)
+            throw HostError(ARROY_ERR_MISSING_KEY, "Internal error: Tree(" + std::to_string(top.node) + ") is missing in index `" + std::to_string(r->index) + "`");
+        const arroy_reader::Node& nd = r->nodes[top.node];
+        if (nd.kind == 1) {
+            const uint32_t* ids = r->desc.data() + nd.desc_off;
+            if (candidates) { for (uint32_t i = 0; i < nd.desc_len; ++i) if (std::binary_search(candidates->begin(), candidates->end(), ids[i])) nns.push_back(ids[i]); }
+            else nns.insert(nns.end(), ids, ids + nd.desc_len);
+        } else {
+            float mg = nd.has_normal ? host_margin(r->metric, r->normals.data() + (size_t)nd.normal_off * d, nd.h0, qv, qh0, d) : 0.0f;
+            queue.push(QE{f32_min(-mg, top.dist), nd.left});   // D::pq_distance — mod.rs:63-68
+            queue.push(QE{f32_min(mg, top.dist), nd.right});
+        }
+    }
+    std::sort(nns.begin(), nns.end());
+    nns.erase(std::unique(nns.begin(), nns.end()), nns.end());
+    out_rows.reserve(nns.size());
+    for (uint32_t id : nns) {
+        int64_t row = row_of(r, id);
+        if (row < 0) throw HostError(ARROY_ERR_MISSING_KEY, "Internal error: Item(" + std::to_string(id) + ") is missing in index `" + std::to_string(r->index) + "`");
+        out_rows.push_back((uint32_t)row);
+    }
+}
+
+inline void nns_by_leaf(arroy_reader* r, const float* qv, float qh0, float qh1, uint64_t count, uint64_t search_k, uint64_t oversampling,
+                        const uint32_t* cand, int64_t n_cand, uint32_t* out_ids, float* out_dist, uint64_t* out_len) {
+    std::vector<uint32_t> cv, rows;
+    if (n_cand >= 0) { cv.assign(cand, cand + n_cand); std::sort(cv.begin(), cv.end()); }
+    tree_walk(r, qv, qh0, count, search_k, oversampling, n_cand >= 0 ? &cv : nullptr, rows);
+    *out_len = 0;
+    if (rows.empty() || count == 0) return;
+    const uint32_t k = (uint32_t)std::min<uint64_t>(count, rows.size());
+    ensure_staged(r);
+    std::vector<uint32_t> orow(k);
+    uint32_t olen = 0;
+    dev_ck(r->ctx, arroy_b200_rerank(r->ctx, qv, qh0, qh1, rows.data(), rows.size(), k, orow.data(), out_dist, &olen));
+    for (uint32_t i = 0; i < olen; ++i) out_ids[i] = r->items[orow[i]];
+    *out_len = olen;
+}
+
+}  // namespace arroy_host
+
+// ====================================================================================================
+extern "C" {
+using namespace arroy_host;
+
+const char* arroy_host_last_error(void) { return tls_error().c_str(); }
+
+arroy_env* arroy_env_new(void) { return new arroy_env(); }
+void arroy_env_free(arroy_env* e) { delete e; }
+uint64_t arroy_env_len(arroy_env* e) { std::lock_guard<std::mutex> lk(e->mu); return e->kv.size(); }
+int32_t arroy_env_iter(arroy_env* e, arroy_kv_sink sink, void* arg) {
+    return hguard([&] {
+        std::lock_guard<std::mutex> lk(e->mu);
+        for (auto& kv : e->kv)
+            if (sink(arg, kv.first.data(), 8, reinterpret_cast<const uint8_t*>(kv.second.data()), kv.second.size()) != 0) break;
+    });
+}
+
+arroy_rng* arroy_rng_from_seed(const uint8_t seed[32]) {
+    auto* r = new arroy_rng();
+    uint32_t key[8];
+    for (int i = 0; i < 8; ++i) key[i] = (uint32_t)seed[4 * i] | ((uint32_t)seed[4 * i + 1] << 8) | ((uint32_t)seed[4 * i + 2] << 16) | ((uint32_t)seed[4 * i + 3] << 24);
+    r->r.init(key, 0);
+    return r;
+}
+arroy_rng* arroy_rng_seed_from_u64(uint64_t state) {  // rand_core 0.6 SeedableRng::seed_from_u64 (PCG32 expansion)
+    const uint64_t MUL = 6364136223846793005ull, INC = 11634580027462260723ull;
+    uint8_t seed[32];
+    for (int c = 0; c < 8; ++c) {
+        state = state * MUL + INC;
+        uint32_t xs = (uint32_t)(((state >> 18) ^ state) >> 27), rot = (uint32_t)(state >> 59);
+        uint32_t x = (xs >> rot) | (xs << ((32 - rot) & 31));
+        memcpy(seed + 4 * c, &x, 4);
+    }
+    return arroy_rng_from_seed(seed);
+}
+arroy_rng* arroy_rng_clone(const arroy_rng* r) { return new arroy_rng(*r); }
+void arroy_rng_free(arroy_rng* r) { delete r; }
+uint32_t arroy_rng_next_u32(arroy_rng* r) { return r->r.next_u32(); }
+float arroy_rng_gen_f32(arroy_rng* r) { return (float)(r->r.next_u32() >> 8) * (1.0f / 16777216.0f); }
+void arroy_rng_fill_f32(arroy_rng* r, float* out, uint64_t n) { for (uint64_t i = 0; i < n; ++i) out[i] = arroy_rng_gen_f32(r); }
+
+arroy_writer* arroy_writer_new(arroy_env* env, uint16_t index, uint32_t dimensions, int32_t metric) {
+    auto* w = new arroy_writer();
+    w->env = env; w->index = index; w->dims = dimensions; w->metric = metric;
+    return w;
+}
+void arroy_writer_free(arroy_writer* w) { delete w; }
+
+static void check_dim(arroy_writer* w, uint32_t len) {
+    if (len != w->dims) throw HostError(ARROY_ERR_INVALID_VEC_DIMENSION, "Invalid vector dimensions. Got " + std::to_string(len) + " but expected " + std::to_string(w->dims));
+}
+int32_t arroy_writer_add_item(arroy_writer* w, uint32_t item, const float* vector, uint32_t len) {
+    return hguard([&] { check_dim(w, len); std::lock_guard<std::mutex> lk(w->env->mu); put_item(w, item, vector); });
+}
+int32_t arroy_writer_add_items(arroy_writer* w, uint64_t n, const uint32_t* items, const float* vectors) {
+    return hguard([&] { std::lock_guard<std::mutex> lk(w->env->mu); for (uint64_t i = 0; i < n; ++i) put_item(w, items[i], vectors + i * w->dims); });
+}
+int32_t arroy_writer_append_item(arroy_writer* w, uint32_t item, const float* vector, uint32_t len) {  // writer.rs:403-425
+    return hguard([&] {
+        check_dim(w, len);
+        std::lock_guard<std::mutex> lk(w->env->mu);
+        // PutFlags::APPEND: the key must be greater than every key of the database
+        if (!w->env->kv.empty() && !(w->env->kv.rbegin()->first < make_key(w->index, MODE_ITEM, item)))
+            throw HostError(ARROY_ERR_INVALID_ITEM_APPEND, "Item cannot be appended into the database");
+        put_item(w, item, vector);
+    });
+}
+int32_t arroy_writer_del_item(arroy_writer* w, uint32_t item, int32_t* out_existed) {  // writer.rs:428-441
+    return hguard([&] {
+        std::lock_guard<std::mutex> lk(w->env->mu);
+        bool ex = w->env->kv.erase(make_key(w->index, MODE_ITEM, item)) > 0;
+        if (ex) { w->env->kv[make_key(w->index, MODE_UPDATED, item)] = std::string(); w->env->generation++; }
+        if (out_existed) *out_existed = ex ? 1 : 0;
+    });
+}
+int32_t arroy_writer_clear(arroy_writer* w) {  // writer.rs:444-457
+    return hguard([&] {
+        std::lock_guard<std::mutex> lk(w->env->mu);
+        for (uint8_t m = 0; m < 4; ++m) erase_mode(w->env, w->index, m);
+        w->env->generation++;
+    });
+}
+int32_t arroy_writer_need_build(arroy_writer* w, int32_t* out) {  // writer.rs:343-357
+    return hguard([&] {
+        std::lock_guard<std::mutex> lk(w->env->mu);
+        auto it = w->env->kv.lower_bound(make_key(w->index, MODE_UPDATED, 0));
+        bool upd = it != w->env->kv.end() && it->first[0] == (uint8_t)(w->index >> 8) && it->first[1] == (uint8_t)w->index && it->first[2] == MODE_UPDATED;
+        *out = (upd || w->env->kv.find(make_key(w->index, MODE_METADATA, 0)) == w->env->kv.end()) ? 1 : 0;
+    });
+}
+int32_t arroy_writer_contains_item(arroy_writer* w, uint32_t item, int32_t* out) {
+    return hguard([&] { std::lock_guard<std::mutex> lk(w->env->mu); *out = w->env->kv.count(make_key(w->index, MODE_ITEM, item)) ? 1 : 0; });
+}
+int32_t arroy_writer_is_empty(arroy_writer* w, int32_t* out) {
+    return hguard([&] { std::lock_guard<std::mutex> lk(w->env->mu); *out = collect_items(w->env, w->index).ids.empty() ? 1 : 0; });
+}
+int32_t arroy_writer_item_vector(arroy_writer* w, uint32_t item, float* out, int32_t* out_found) {
+    return hguard([&] {
+        std::lock_guard<std::mutex> lk(w->env->mu);
+        auto it = w->env->kv.find(make_key(w->index, MODE_ITEM, item));
+        *out_found = it != w->env->kv.end();
+        if (*out_found) memcpy(out, it->second.data() + 1 + 4 * header_floats(w->metric), 4ull * w->dims);
+    });
+}
+int32_t arroy_writer_build(arroy_writer* w, arroy_ctx* ctx, arroy_rng* rng, int64_t n_trees, uint64_t split_after, uint64_t /*available_memory*/,
+                           arroy_b200_cancel_fn cancel, void* cancel_arg, arroy_progress_fn progress, void* progress_arg) {
+    return hguard([&] { writer_build(w, ctx, rng, n_trees, split_after, cancel, cancel_arg, progress, progress_arg); });
+}
+int32_t arroy_writer_build_timings(arroy_writer* w, double out[8]) { for (int i = 0; i < 8; ++i) out[i] = w->timings[i]; return 0; }
+
+int32_t arroy_reader_open(arroy_env* env, uint16_t index, int32_t metric, arroy_ctx* ctx, arroy_reader** out) {
+    *out = nullptr;
+    return hguard([&] { reader_open(env, index, metric, ctx, out); });
+}
+void arroy_reader_free(arroy_reader* r) { delete r; }
+uint32_t arroy_reader_dimensions(arroy_reader* r) { return r->dims; }
+uint64_t arroy_reader_n_trees(arroy_reader* r) { return r->roots.size(); }
+uint64_t arroy_reader_n_items(arroy_reader* r) { return r->items.size(); }
+uint64_t arroy_reader_item_ids(arroy_reader* r, uint32_t* out, uint64_t cap) {
+    if (out) memcpy(out, r->items.data(), 4 * std::min<uint64_t>(cap, r->items.size()));
+    return r->items.size();
+}
+int32_t arroy_reader_item_vector(arroy_reader* r, uint32_t item, float* out, int32_t* out_found) {
+    return hguard([&] {
+        std::lock_guard<std::mutex> lk(r->env->mu);
+        auto it = r->env->kv.find(make_key(r->index, MODE_ITEM, item));
+        *out_found = it != r->env->kv.end();
+        if (*out_found) memcpy(out, it->second.data() + 1 + 4 * header_floats(r->metric), 4ull * r->dims);
+    });
+}
+int32_t arroy_reader_stats(arroy_reader* r, uint64_t* out) {  // reader.rs:210-252
+    return hguard([&] {
+        struct TS { uint64_t depth, dummy, split, desc; };
+        std::function<TS(uint32_t)> rec = [&](uint32_t id) -> TS {
+            const arroy_reader::Node& nd = r->nodes.at(id);
+            if (nd.kind == 1) return TS{1, 0, 0, 1};
+            TS l = rec(nd.left), rr = rec(nd.right);
+            return TS{1 + std::max(l.depth, rr.depth), l.dummy + rr.dummy + (nd.has_normal ? 0u : 1u), l.split + rr.split + 1, l.desc + rr.desc};
+        };
+        for (size_t t = 0; t < r->roots.size(); ++t) { TS s = rec(r->roots[t]); out[4 * t] = s.depth; out[4 * t + 1] = s.dummy; out[4 * t + 2] = s.split; out[4 * t + 3] = s.desc; }
+    });
+}
+int32_t arroy_reader_nns_by_item(arroy_reader* r, uint32_t item, uint64_t count, uint64_t search_k, uint64_t oversampling, const uint32_t* cand, int64_t n_cand,
+                                 uint32_t* out_ids, float* out_dist, uint64_t* out_len, int32_t* out_found) {
+    return hguard([&] {
+        *out_len = 0;
+        int64_t row = row_of(r, item);
+        *out_found = row >= 0;
+        if (row < 0) return;  // Ok(None) — reader.rs:46-51
+        std::vector<float> q(r->dims);
+        int32_t found = 0;
+        { std::lock_guard<std::mutex> lk(r->env->mu); auto it = r->env->kv.find(make_key(r->index, MODE_ITEM, item)); found = it != r->env->kv.end(); if (found) memcpy(q.data(), it->second.data() + 1 + 4 * header_floats(r->metric), 4ull * r->dims); }
+        if (!found) { *out_found = 0; return; }
+        nns_by_leaf(r, q.data(), r->hdr0[row], r->hdr1[row], count, search_k, oversampling, cand, n_cand, out_ids, out_dist, out_len);
+    });
+}
+int32_t arroy_reader_nns_by_vector(arroy_reader* r, const float* vector, uint32_t len, uint64_t count, uint64_t search_k, uint64_t oversampling,
+                                   const uint32_t* cand, int64_t n_cand, uint32_t* out_ids, float* out_dist, uint64_t* out_len) {
+    return hguard([&] {
+        *out_len = 0;
+        if (len != r->dims) throw HostError(ARROY_ERR_INVALID_VEC_DIMENSION, "Invalid vector dimensions. Got " + std::to_string(len) + " but expected " + std::to_string(r->dims));
+        float h0, h1;
+        new_header(r->metric, vector, r->dims, h0, h1);  // reader.rs:72-73
+        nns_by_leaf(r, vector, h0, h1, count, search_k, oversampling, cand, n_cand, out_ids, out_dist, out_len);
+    });
+}
+int32_t arroy_reader_nns_batch_by_item(arroy_reader* r, uint32_t nq, const uint32_t* items, uint64_t count, uint64_t search_k, uint64_t oversampling,
+                                       uint32_t* out_ids, float* out_dist, uint32_t* out_len, double* out_ms) {
+    return hguard([&] {
+        const uint32_t d = r->dims;
+        const int hf = header_floats(r->metric);
+        std::vector<float> q((size_t)nq * d), qh0(nq), qh1(nq);
+        std::vector<std::vector<uint32_t>> rows(nq);
+        {
+            std::lock_guard<std::mutex> lk(r->env->mu);
+            for (uint32_t i = 0; i < nq; ++i) {
+                int64_t row = row_of(r, items[i]);
+                if (row < 0) throw HostError(ARROY_ERR_MISSING_KEY, "Internal error: Item(" + std::to_string(items[i]) + ") is missing in index `" + std::to_string(r->index) + "`");
+                const std::string& v = r->env->kv.at(make_key(r->index, MODE_ITEM, items[i]));
+                memcpy(&q[(size_t)i * d], v.data() + 1 + 4 * hf, 4ull * d);
+                qh0[i] = r->hdr0[row]; qh1[i] = r->hdr1[row];
+            }
+        }
+        auto t0 = clk::now();
+        std::atomic<uint32_t> next{0};
+        std::string err; std::mutex emu;
+        auto worker = [&] {
+            try { for (;;) { uint32_t i = next.fetch_add(1); if (i >= nq) return; tree_walk(r, &q[(size_t)i * d], qh0[i], count, search_k, oversampling, nullptr, rows[i]); } }
+            catch (const std::exception& e) { std::lock_guard<std::mutex> lk(emu); err = e.what(); }
+        };
+        unsigned nt = std::max(1u, std::min<unsigned>(nq, std::thread::hardware_concurrency()));
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < nt; ++t) th.emplace_back(worker);
+        for (auto& x : th) x.join();
+        if (!err.empty()) throw HostError(ARROY_ERR_PANIC, err);
+        if (out_ms) out_ms[0] = ms_since(t0);
+        ensure_staged(r);
+        t0 = clk::now();
+        std::vector<uint64_t> offs(nq + 1, 0);
+        for (uint32_t i = 0; i < nq; ++i) offs[i + 1] = offs[i] + rows[i].size();
+        std::vector<uint32_t> flat(offs[nq]);
+        for (uint32_t i = 0; i < nq; ++i) memcpy(flat.data() + offs[i], rows[i].data(), 4 * rows[i].size());
+        const uint32_t k = (uint32_t)count;
+        std::vector<uint32_t> orow((size_t)nq * std::max<uint32_t>(k, 1));
+        for (uint32_t base = 0; base < nq; base += 32768) {
+            uint32_t m = std::min<uint32_t>(32768, nq - base);
+            std::vector<uint64_t> lo(m + 1);
+            for (uint32_t i = 0; i <= m; ++i) lo[i] = offs[base + i] - offs[base];
+            dev_ck(r->ctx, arroy_b200_rerank_batch(r->ctx, m, &q[(size_t)base * d], &qh0[base], &qh1[base], flat.data() + offs[base], lo.data(), k,
+                                                   orow.data() + (size_t)base * k, out_dist + (size_t)base * k, out_len + base));
+        }
+        for (uint32_t i = 0; i < nq; ++i) for (uint32_t j = 0; j < out_len[i]; ++j) out_ids[(size_t)i * k + j] = r->items[orow[(size_t)i * k + j]];
+        if (out_ms) out_ms[1] = ms_since(t0);
+    });
+}
+
+}  // extern "C"

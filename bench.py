@@ -1,0 +1,319 @@
+#!/usr/bin/env python3
+"""bench.py — index-build throughput of arroy's distance / split hot path on B200.
+
+One "step" = one complete forest build (Writer::build of the reference, src/writer.rs:487-629)
+over one synthetic item matrix. Contract: `python bench.py --gpus N --steps K --warmup W`
+prints ONE JSON line (rank 0). `--impl reference` times the reference's CPU path instead (the
+Rust crate cannot be compiled in this image, so it is the C++ restatement in oracle/, kind
+"port": same AVX+FMA kernels, one task per tree on all host cores — see BASELINE.md §3).
+
+Workloads (BASELINE.json configs; SURVEY.md §8d synthetic data: element (i,j) = gen::<f32>()
+number i*d+j of StdRng::from_seed([42;32]) minus 0.5; build rng = fresh StdRng([42;32])):
+  c2 (default)  1 000 000 x 768  Cosine      n_trees = 50    <- BASELINE.json configs[1]
+  c3            10 000 000 x 768 DotProduct  n_trees = 100
+  c1            10 000 x 64      Euclidean   n_trees = 10    (raw [0,1) data)
+  small         100 000 x 768    Cosine      n_trees = 16    (quick check)
+
+Keys beyond the base contract: "roofline" (dominant kernel = the side()/margin scan inside
+work_kernel), "cpu_baseline", "e2e" (through Writer.builder(rng).build() with the items as host
+leaf values: decode + H2D + device build + D2H + NodeCodec encoding + metadata, all timed),
+"clocks", "gpu_launches".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SEED = bytes([42] * 32)
+WORKLOADS = {
+    "c2": dict(n=1_000_000, d=768, metric="cosine", n_trees=50, centre=0.5, name="C2 1Mx768 Cosine n_trees=50"),
+    "c3": dict(n=10_000_000, d=768, metric="dot-product", n_trees=100, centre=0.5, name="C3 10Mx768 DotProduct n_trees=100"),
+    "c1": dict(n=10_000, d=64, metric="euclidean", n_trees=10, centre=0.0, name="C1 10kx64 Euclidean n_trees=10"),
+    "small": dict(n=100_000, d=768, metric="cosine", n_trees=16, centre=0.5, name="small 100kx768 Cosine n_trees=16"),
+}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d.get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def derive_seeds(ab, n_trees):
+    """seed chain of Writer::build (src/writer.rs:575, :795) with the product's own StdRng."""
+    import numpy as np
+    user = ab.StdRng.from_seed(SEED)
+    s1 = bytes(np.array([user.next_u32() & 0xff for _ in range(32)], dtype=np.uint8))
+    r1 = ab.StdRng.from_seed(s1)
+    return [bytes(np.array([r1.next_u32() & 0xff for _ in range(32)], dtype=np.uint8)) for _ in range(n_trees)]
+
+
+def run_reference(args, wl):
+    """The reference's CPU path (oracle port) on all host cores; rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import numpy as np
+    import oracle
+    oracle.build_lib()
+    cores = os.cpu_count() or 1
+    n, d, T = wl["n"], wl["d"], wl["n_trees"]
+    # bounded sample: the same item matrix, as many trees as keep one step within ~tens of seconds
+    t_sample = T if args.ref_trees is None else args.ref_trees
+    if args.ref_trees is None and n * d >= 5e8:
+        t_sample = min(T, max(8, cores // 2))
+    data = oracle.synth_rows(SEED, d, 0, n, wl["centre"], threads=min(cores, 64))
+    ids = np.arange(n, dtype=np.uint32)
+    times = []
+    scanned = 0
+    for step in range(args.warmup + args.steps):
+        db = oracle.Db(wl["metric"], d)
+        db.set_items(ids, data)
+        rng = oracle.StdRng(SEED)
+        t0 = time.perf_counter()
+        db.build(rng, n_trees=t_sample, threads=min(cores, t_sample))
+        dt = time.perf_counter() - t0
+        scanned = db.scanned_rows
+        if step >= args.warmup:
+            times.append(dt)
+        del db
+    sec = sum(times) / len(times)
+    # vectors/s of the FULL forest, extrapolated linearly in the number of trees (trees are independent)
+    value = n / (sec * T / t_sample)
+    line = {
+        "impl": "reference", "metric": "index-build vectors/sec", "value": value, "unit": "vectors/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": {"workload": wl["name"], "n": n, "d": d, "distance": wl["metric"], "n_trees": T},
+        "cpu_baseline": {"value": value, "unit": "vectors/s", "cores": min(cores, t_sample), "kind": "port",
+                         "sample": "%d of %d trees over the full %dx%d matrix, %d threads (one tree per thread), extrapolated x%.2f" % (t_sample, T, n, d, min(cores, t_sample), T / t_sample),
+                         "scan_GBps": scanned * d * 4 / sec / 1e9},
+        "e2e": {"value": value, "unit": "vectors/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("ARROY_BENCH_WORKLOAD", "c2"), choices=sorted(WORKLOADS))
+    ap.add_argument("--ref-trees", type=int, default=None, help="trees built per step by --impl reference / cpu_baseline")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, wl)
+        return
+
+    import numpy as np
+    import torch
+    import __graft_entry__ as ge
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank == 0:
+        ge.build()
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.barrier()
+    import arroy_b200 as ab
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    ctx = ab.Context(local_rank)
+    n, d, T, metric = wl["n"], wl["d"], wl["n_trees"], wl["metric"]
+    ids = np.arange(n, dtype=np.uint32)
+
+    # synthetic items, generated on the device of rank 0 (counter-based ChaCha12 stream)
+    items = torch.empty((n, d), dtype=torch.float32, device=dev)
+    if rank == 0:
+        ctx.synth_device(SEED, d, 0, n, wl["centre"], items.data_ptr())
+    torch.cuda.synchronize()
+    seeds = derive_seeds(ab, T)
+    my_trees = list(range(rank, T, world))  # trees are independent units: tree t -> rank t mod world
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    def one_step():
+        # multi-GPU: ONE NCCL broadcast of the item buffer over NVLink, then no further exchange
+        if dist is not None:
+            dist.broadcast(items, src=0)
+            torch.cuda.synchronize()
+        ctx.stage_items_device(metric, ids, d, items.data_ptr())
+        if metric == "dot-product":
+            ctx.dot_preprocess()
+        return ctx.build_trees([seeds[t] for t in my_trees], my_trees, T, collect=False)
+
+    for _ in range(args.warmup):
+        one_step()
+    c0 = ctx.counters()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    ctx.timer_start()
+    t0 = time.perf_counter()
+    scanned = 0
+    for _ in range(args.steps):
+        one_step()
+        scanned += ctx.build_stats()["scanned_rows"]
+    dev_ms = ctx.timer_stop()   # CUDA events on the library's stream (the launching stream)
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+    c1 = ctx.counters()
+    t_ms = torch.tensor([max(dev_ms, 0.0)], dtype=torch.float64, device=dev)
+    sc = torch.tensor([float(scanned)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(sc, op=dist.ReduceOp.SUM)
+    ms_per_step = float(t_ms.item()) / args.steps
+    value = n / (ms_per_step * 1e-3)
+    launches = c1["launches"] - c0["launches"]
+    last_stats = ctx.build_stats()
+    breakdown = ctx.build_breakdown()
+
+    line = {
+        "metric": "index-build vectors/sec", "value": value, "unit": "vectors/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["name"], "n": n, "d": d, "distance": metric, "n_trees": T, "parallelism": "trees sharded t mod %d" % world,
+                   "l2": "inputs (%.1f GB) larger than L2; no flush needed" % (n * d * 4 / 1e9), "timing": "CUDA events on the library stream, max over ranks",
+                   "wall_ms_per_step": wall * 1e3 / args.steps},
+        "gpu_launches": int(launches),
+        "build": {"scanned_rows_per_step": float(sc.item()) / args.steps, "device_steps": last_stats["steps"], "create_split_calls": last_stats["create_split_calls"],
+                  "random_splits": last_stats["random_splits"], "algorithmic_GB_per_step": float(sc.item()) / args.steps * d * 4 / 1e9,
+                  "whole_build_GBps": float(sc.item()) / args.steps * d * 4 / 1e9 / (ms_per_step * 1e-3),
+                  "schedule": "lockstep" if os.environ.get("ARROY_B200_LOCKSTEP") else "async per-tree graph branches", "breakdown_ms_last_step": breakdown},
+    }
+    if rank == 0:
+        line["clocks"] = clocks
+        hbm, which = peaks()
+        # roofline of the dominant kernel: work_kernel (side()/margin scan). One extra, untimed build
+        # with CUDA events around every work_kernel launch on its launching stream.
+        os.environ["ARROY_B200_PROFILE"] = "1"
+        one_step()
+        os.environ.pop("ARROY_B200_PROFILE")
+        st = ctx.build_stats()
+        scan_ms, steps_dev = st["scan_ms"], st["steps"]
+        alg_bytes = st["scanned_rows"] * d * 4
+        achieved = alg_bytes / (scan_ms * 1e-3) / 1e9 if scan_ms > 0 else 0.0
+        r = np.random.default_rng(0)
+        normal = (r.standard_normal(d) / np.sqrt(d)).astype(np.float32)
+        root_ms, _ = ctx.time_scan(normal, (0.0, 0.0), n, iters=5, flush_l2=True)
+        line["roofline"] = {
+            "bound": "hbm", "kernel": "work_kernel (side()/margin scan + id partition)", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
+            "peak_source": which, "traffic": None,
+            "per_launch": {"launches": steps_dev, "avg_ms": scan_ms / max(steps_dev, 1), "avg_algorithmic_GB": alg_bytes / max(steps_dev, 1) / 1e9},
+            "root_scan": {"rows": n, "ms": root_ms, "GBps": n * d * 4 / (root_ms * 1e-3) / 1e9, "frac": n * d * 4 / (root_ms * 1e-3) / 1e9 / hbm},
+            "share_of_step": scan_ms / (st["build_ms"] if st["build_ms"] else 1.0),
+        }
+    # ---- e2e: the call a user makes, host buffers in, tree nodes out -------------------------------
+    if rank == 0 and not args.no_e2e and world == 1:
+        host = items.cpu().numpy()
+        env = ab.Env(local_rank)
+        env._ctx = ctx
+        w = ab.Writer(env, 0, d, metric)
+        w.add_items(ids, host)  # Writer::add_item x n (untimed: the reference's build timing starts at build())
+        e_times, h2d, d2h = [], 0, 0
+        for step in range(max(1, min(args.warmup, 2)) + args.steps):
+            w.add_item(0, host[0])  # mark the index dirty so build() rebuilds the forest
+            cc0 = ctx.counters()
+            t0 = time.perf_counter()
+            w.builder(ab.StdRng.from_seed(SEED)).n_trees(T).build()
+            dt = time.perf_counter() - t0
+            cc1 = ctx.counters()
+            if step >= max(1, min(args.warmup, 2)):
+                e_times.append(dt)
+                h2d, d2h = cc1["h2d_bytes"] - cc0["h2d_bytes"], cc1["d2h_bytes"] - cc0["d2h_bytes"]
+        e_sec = sum(e_times) / len(e_times)
+        line["e2e"] = {"value": n / e_sec, "unit": "vectors/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e_sec * 1e3,
+                       "api": "Writer.builder(rng).n_trees(T).build() over host leaf values", "breakdown_ms": w.build_timings()}
+        env._ctx = None
+        del w, env, host
+    elif rank == 0:
+        line["e2e"] = None
+    # ---- CPU baseline (oracle port) on a bounded sample, rank 0, N=1 only --------------------------------
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        import oracle
+        cores = os.cpu_count() or 1
+        t_sample = args.ref_trees or (T if n * d < 5e8 else min(T, max(8, cores // 2)))
+        data = oracle.synth_rows(SEED, d, 0, n, wl["centre"], threads=min(cores, 64))
+        db = oracle.Db(metric, d)
+        db.set_items(ids, data)
+        t0 = time.perf_counter()
+        db.build(oracle.StdRng(SEED), n_trees=t_sample, threads=min(cores, t_sample))
+        sec = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": n / (sec * T / t_sample), "unit": "vectors/s", "cores": min(cores, t_sample), "kind": "port",
+                                "sample": "%d of %d trees over the full %dx%d matrix in %.1f s, one tree per thread, extrapolated x%.2f" % (t_sample, T, n, d, sec, T / t_sample)}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -173,6 +173,21 @@ int32_t arroy_b200_time_scan(arroy_ctx* ctx, const float* normal, float hdr0, fl
                              const uint32_t* rows, uint64_t n_rows, int32_t variant, int32_t iters,
                              int32_t flush_l2, float* out_ms_avg, uint64_t* out_left_count);
 
+/* Host-side wall-clock breakdown of the last build (ms): [0] buffer setup + tree init,
+ * [1] CUDA graph capture + instantiate, [2] device step loop, [3] finalize + device->host copies,
+ * [4] NodeCodec encoding + sink calls, [5] graph launches (count), [6..7] reserved. */
+int32_t arroy_b200_build_breakdown(arroy_ctx* ctx, double out[8]);
+
+/* Counters since arroy_b200_create: out[0] = kernel launches issued by this library,
+ * out[1] = bytes copied host->device, out[2] = bytes copied device->host, out[3] reserved. */
+int32_t arroy_b200_counters(arroy_ctx* ctx, uint64_t out[4]);
+
+/* CUDA-event stopwatch on the library's own stream (the stream every kernel above is launched
+ * on): start records an event after draining the stream, stop records a second one, waits for
+ * it and returns the elapsed milliseconds between the two. */
+int32_t arroy_b200_timer_start(arroy_ctx* ctx);
+int32_t arroy_b200_timer_stop(arroy_ctx* ctx, float* out_ms);
+
 /* Raw device pointers of the staged items (for the NCCL broadcast of the multi-GPU path):
  * out[0] = float[n][ld] matrix, out[1] = hdr0[n], out[2] = hdr1[n] (may be 0); *out_ld = ld. */
 int32_t arroy_b200_device_ptrs(arroy_ctx* ctx, void* out[3], uint32_t* out_ld);

@@ -1,0 +1,167 @@
+"""GPU tests through the host mirror (Writer / Reader API of the reference), written after the
+reference's own tests in src/tests/writer.rs and src/tests/reader.rs, plus oracle cross-checks."""
+import numpy as np
+import pytest
+
+import arroy_b200 as ab
+import oracle
+from helpers import check_dump, golden
+
+pytestmark = pytest.mark.gpu
+G = golden()
+SEED = bytes([42] * 32)
+
+
+def rng42():
+    return ab.StdRng.from_seed(SEED)
+
+
+@pytest.fixture(scope="module")
+def env_factory():
+    envs = []
+    shared = {"ctx": None}
+
+    def make():
+        e = ab.Env(0)
+        if shared["ctx"] is None:
+            shared["ctx"] = e.ctx
+        else:
+            e._ctx = shared["ctx"]
+        envs.append(e)
+        return e
+
+    yield make
+    for e in envs:
+        e._ctx = None
+    if shared["ctx"] is not None:
+        shared["ctx"].close()
+
+
+@pytest.mark.parametrize("line,n,dims,gen", [
+    ("280", 4, 3, lambda i: [i, i, i]),     # write_vectors_until_there_is_a_split
+    ("403", 6, 2, lambda i: [i, 0.0]),      # overwrite_one_item_incremental (first build)
+    ("605", 3, 2, lambda i: [i, 0.0]),      # delete_one_leaf_in_a_split (first build)
+])
+def test_reference_inline_snapshots_through_the_writer(env_factory, line, n, dims, gen):
+    gold = G["writer_inline"][line]
+    env = env_factory()
+    w = ab.Writer(env, 0, dims, "euclidean")
+    for i in range(n):
+        w.add_item(i, gen(float(i)))
+    w.builder(rng42()).n_trees(1).build()
+    r = ab.Reader.open(env, 0, "euclidean")
+    check_dump(gold, env.tree_nodes(), r._roots(), oracle.EUCLIDEAN, dims, oracle.decode_node)
+    # items dump: header bias 0.0000 + vector
+    for key, it in gold["items"].items():
+        assert ["%.4f" % v for v in w.item_vector(int(key))] == it["vector"]
+
+
+def test_write_and_update_lot_of_random_points_first_snapshot(env_factory):
+    gold = G["lot_of_random_points"]
+    env = env_factory()
+    w = ab.Writer(env, 0, 30, "euclidean")
+    rng = rng42()
+    for i in range(100):
+        w.add_item(i, rng.fill_f32(30))
+    w.builder(rng).n_trees(10).build()
+    r = ab.Reader.open(env, 0, "euclidean")
+    check_dump(gold, env.tree_nodes(), r._roots(), oracle.EUCLIDEAN, 30, oracle.decode_node)
+    st = r.stats()
+    assert st["leaf"] == 100 and len(st["tree_stats"]) == 10
+    assert all(t["dummy_normals"] == 0 and t["descendants"] == t["split_nodes"] + 1 for t in st["tree_stats"])
+
+
+def _line(env_factory, column=False):
+    env = env_factory()
+    w = ab.Writer(env, 0, 2, "euclidean")
+    for i in range(100):
+        w.add_item(i, [0.0, float(i)] if column else [float(i), 0.0])
+    w.builder(rng42()).n_trees(50).build()
+    return ab.Reader.open(env, 0, "euclidean")
+
+
+def test_two_dimension_on_a_line(env_factory):  # src/tests/reader.rs:101-144
+    r = _line(env_factory)
+    q = G["reader_inline"]
+    assert r.nns(5).search_k(1).by_item(1) == [tuple(x) for x in q["120"]]
+    assert r.nns(5).search_k(2**64 - 1).by_item(0) == [tuple(x) for x in q["128"]]
+    assert r.nns(5).by_item(0) == [tuple(x) for x in q["137"]]
+    assert r.nns(5).by_item(1000) is None
+
+
+def test_two_dimension_on_a_column_and_filtering(env_factory):  # src/tests/reader.rs:146-227
+    r = _line(env_factory, column=True)
+    q = G["reader_inline"]
+    assert r.nns(5).by_item(0) == [tuple(x) for x in q["168"]]
+    assert r.nns(5).candidates(range(0, 2)).by_item(0) == [tuple(x) for x in q["216"]]
+    assert r.nns(5).candidates(range(98, 1000)).by_item(0) == [tuple(x) for x in q["223"]]
+    assert r.item_ids() == list(range(100))
+
+
+def test_search_in_db_with_a_single_vector(env_factory):  # src/tests/reader.rs:81-99
+    env = env_factory()
+    w = ab.Writer(env, 0, 3, "cosine")
+    w.add_item(0, [0.00397, 0.553, 0.0])
+    w.builder(rng42()).build()
+    r = ab.Reader.open(env, 0, "cosine")
+    assert r.nns(1).by_item(0) == [tuple(x) for x in G["reader_inline"]["96"]]
+
+
+@pytest.mark.parametrize("metric,n,d,trees,centre", [
+    ("euclidean", 10000, 64, 10, 0.0),    # config C1 (examples/compare_with_hnsw.rs shape)
+    ("cosine", 6000, 128, 8, 0.5),
+    ("dot-product", 6000, 96, 8, 0.5),
+    ("manhattan", 3000, 48, 4, 0.5),
+])
+def test_forest_and_queries_match_the_oracle_end_to_end(env_factory, metric, n, d, trees, centre):
+    data = oracle.synth_rows(SEED, d, 0, n, centre, threads=4)
+    ids = np.arange(n, dtype=np.uint32)
+    odb = oracle.Db(metric, d)
+    odb.set_items(ids, data)
+    odb.build(oracle.StdRng(SEED), n_trees=trees, threads=8)
+    env = env_factory()
+    w = ab.Writer(env, 0, d, metric)
+    w.add_items(ids, data)
+    w.builder(rng42()).n_trees(trees).build()
+    assert env.tree_nodes() == odb.nodes()
+    r = ab.Reader.open(env, 0, metric)
+    assert r.n_trees() == trees and r.n_items() == n
+    qitems = list(range(0, 200, 7))
+    for k, search_k in ((5, None), (100, None), (10, 2000)):
+        for it in qitems:
+            want = odb.nns_by_item(it, k, search_k=search_k)
+            got = r.nns(k).search_k(search_k).by_item(it) if search_k else r.nns(k).by_item(it)
+            assert [g[0] for g in got] == [x[0] for x in want], (it, k)
+            assert np.array([g[1] for g in got], dtype=np.float32).tobytes() == np.array([x[1] for x in want], dtype=np.float32).tobytes()
+    # by_vector with a vector that is not in the index
+    qv = oracle.synth_rows(SEED, d, n + 3, 1, centre)[0]
+    assert r.nns(20).by_vector(qv) == odb.nns_by_vector(qv, 20)
+    # batched by_item == one at a time
+    out_ids, out_dist, out_len, _ = r.nns_batch_by_item(qitems, 10)
+    for i, it in enumerate(qitems):
+        single = r.nns(10).by_item(it)
+        assert out_ids[i, :out_len[i]].tolist() == [s[0] for s in single]
+        assert out_dist[i, :out_len[i]].tolist() == [s[1] for s in single]
+
+
+def test_rebuild_after_update_gives_a_valid_index(env_factory):
+    # incremental insertion is not restated yet: an update triggers a full rebuild
+    n, d = 3000, 32
+    data = oracle.synth_rows(SEED, d, 0, n, 0.5)
+    env = env_factory()
+    w = ab.Writer(env, 0, d, "cosine")
+    w.add_items(np.arange(n, dtype=np.uint32), data)
+    rng = rng42()
+    w.builder(rng).n_trees(4).build()
+    w.add_item(n, oracle.synth_rows(SEED, d, n, 1, 0.5)[0])
+    w.del_item(5)
+    assert w.need_build()
+    w.builder(rng).n_trees(4).build()
+    r = ab.Reader.open(env, 0, "cosine")
+    assert r.n_items() == n and 5 not in r.item_ids() and n in r.item_ids()
+    st = r.stats()
+    nodes = env.tree_nodes()
+    seen = sorted(i for b in nodes.values() if b[0] == 1 for i in oracle.roaring_deserialize(b[1:]))
+    assert len(seen) == 4 * n and all(t["depth"] > 1 for t in st["tree_stats"])
+    res = r.nns(3).by_item(n)
+    assert res[0] == (n, 0.0)
