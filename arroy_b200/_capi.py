@@ -36,11 +36,19 @@ SIGNATURES = [
     ("arroy_b200_side_batch", C.c_int32, [C.c_void_p, _f32p, C.c_float, C.c_float, _u32p, C.c_uint64, _u8p, _f32p]),
     ("arroy_b200_create_split", C.c_int32, [C.c_void_p, _u32p, _u64p, _u32p, C.c_uint64, _f32p, _f32p]),
     ("arroy_b200_build_trees", C.c_int32, [C.c_void_p, C.c_uint32, C.c_void_p, _u32p, C.c_uint32, C.c_uint32, CANCEL_FN, C.c_void_p, NODE_SINK, C.c_void_p, _u64p]),
+    ("arroy_b200_build_trees_begin", C.c_int32, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, CANCEL_FN, C.c_void_p, _u32p]),
+    ("arroy_b200_build_trees_emit", C.c_int32, [C.c_void_p, _u32p, _u64p, NODE_SINK, C.c_void_p]),
     ("arroy_b200_build_stats", C.c_int32, [C.c_void_p, C.POINTER(C.c_double)]),
     ("arroy_b200_rerank", C.c_int32, [C.c_void_p, _f32p, C.c_float, C.c_float, _u32p, C.c_uint64, C.c_uint32, _u32p, _f32p, _u32p]),
     ("arroy_b200_rerank_batch", C.c_int32, [C.c_void_p, C.c_uint32, _f32p, _f32p, _f32p, _u32p, _u64p, C.c_uint32, _u32p, _f32p, _u32p]),
     ("arroy_b200_synth_device", C.c_int32, [C.c_void_p, _u8p, C.c_uint32, C.c_uint64, C.c_uint64, C.c_float, C.c_void_p]),
     ("arroy_b200_time_scan", C.c_int32, [C.c_void_p, _f32p, C.c_float, C.c_float, _u32p, C.c_uint64, C.c_int32, C.c_int32, C.c_int32, _f32p, _u64p]),
+    ("arroy_b200_arena_new", C.c_void_p, []),
+    ("arroy_b200_arena_free", None, [C.c_void_p]),
+    ("arroy_b200_arena_clear", None, [C.c_void_p]),
+    ("arroy_b200_arena_sink", C.c_int32, [C.c_void_p, C.c_uint32, _u8p, C.c_uint64]),
+    ("arroy_b200_arena_stats", C.c_uint64, [C.c_void_p, _u64p]),
+    ("arroy_b200_arena_get", C.c_int32, [C.c_void_p, C.c_uint32, C.POINTER(_u8p), _u64p]),
     ("arroy_b200_build_breakdown", C.c_int32, [C.c_void_p, C.POINTER(C.c_double)]),
     ("arroy_b200_counters", C.c_int32, [C.c_void_p, _u64p]),
     ("arroy_b200_timer_start", C.c_int32, [C.c_void_p]),
@@ -200,6 +208,55 @@ class Context:
                                                  ccb, None, cb, None, C.byref(n_nodes)))
         return out if collect else n_nodes.value
 
+    def build_trees_begin(self, tree_seeds, split_after=0):
+        """Phase 1 of a sharded build: device work for the given (local) trees; returns node counts."""
+        n_trees = len(tree_seeds)
+        seeds = (C.c_uint8 * (32 * max(n_trees, 1)))()
+        for t, s in enumerate(tree_seeds):
+            seeds[32 * t:32 * t + 32] = list(s)
+        counts = np.zeros(max(n_trees, 1), dtype=np.uint32)
+        self._ck(self.lib.arroy_b200_build_trees_begin(self.h, n_trees, C.cast(seeds, C.c_void_p), split_after, C.cast(None, CANCEL_FN), None, _up(counts)))
+        return counts[:n_trees]
+
+    def build_trees_emit(self, root_ids, base_ids, arena=None):
+        """Phase 2: encode the parked trees. Returns {node id: bytes} unless an Arena is given."""
+        roots = np.ascontiguousarray(root_ids, dtype=np.uint32)
+        bases = np.ascontiguousarray(base_ids, dtype=np.uint64)
+        if arena is not None:
+            sink = C.cast(self.lib.arroy_b200_arena_sink, NODE_SINK)
+            self._ck(self.lib.arroy_b200_build_trees_emit(self.h, _up(roots), bases.ctypes.data_as(_u64p), sink, arena.h))
+            return None
+        out = {}
+
+        def sink(_arg, node_id, ptr, length):
+            out[node_id] = C.string_at(ptr, length)
+            return 0
+
+        cb = NODE_SINK(sink)
+        self._ck(self.lib.arroy_b200_build_trees_emit(self.h, _up(roots), bases.ctypes.data_as(_u64p), cb, None))
+        return out
+
+    def build_trees_into_arena(self, arena, tree_seeds, root_ids, first_free_node_id, split_after=0):
+        """C-level path: the library's own thread-safe arena sink (no Python callback)."""
+        n_trees = len(tree_seeds)
+        seeds = (C.c_uint8 * (32 * max(n_trees, 1)))()
+        for t, s in enumerate(tree_seeds):
+            seeds[32 * t:32 * t + 32] = list(s)
+        roots = np.ascontiguousarray(root_ids, dtype=np.uint32)
+        n_nodes = C.c_uint64(0)
+        sink = C.cast(self.lib.arroy_b200_arena_sink, NODE_SINK)
+        self._ck(self.lib.arroy_b200_build_trees(self.h, n_trees, C.cast(seeds, C.c_void_p), _up(roots), first_free_node_id, split_after,
+                                                 C.cast(None, CANCEL_FN), None, sink, arena.h, C.byref(n_nodes)))
+        return n_nodes.value
+
+    def stage_items_ptrs(self, metric, dim, ids, ptr_array):
+        """ptr_array: numpy uint64 array of host addresses of raw Leaf values (LMDB-style)."""
+        metric = METRICS[metric] if isinstance(metric, str) else metric
+        ids = np.ascontiguousarray(ids, dtype=np.uint32)
+        ptrs = np.ascontiguousarray(ptr_array, dtype=np.uint64)
+        self._ck(self.lib.arroy_b200_stage_items(self.h, metric, dim, ids.size, _up(ids), ptrs.ctypes.data_as(C.POINTER(C.c_void_p))))
+        self.n, self.dim, self.metric = ids.size, dim, metric
+
     def build_stats(self):
         st = (C.c_double * 8)()
         self._ck(self.lib.arroy_b200_build_stats(self.h, st))
@@ -267,3 +324,32 @@ class Context:
         ld = C.c_uint32(0)
         self._ck(self.lib.arroy_b200_device_ptrs(self.h, out, C.byref(ld)))
         return [out[0], out[1], out[2]], ld.value
+
+
+class Arena:
+    """arroy_b200_arena: thread-safe append-only node sink (TmpNodes stand-in)."""
+
+    def __init__(self):
+        self.lib = load()
+        self.h = C.c_void_p(self.lib.arroy_b200_arena_new())
+
+    def clear(self):
+        self.lib.arroy_b200_arena_clear(self.h)
+
+    def stats(self):
+        b = C.c_uint64(0)
+        n = self.lib.arroy_b200_arena_stats(self.h, C.byref(b))
+        return n, b.value
+
+    def get(self, node_id):
+        p = _u8p()
+        ln = C.c_uint64(0)
+        if self.lib.arroy_b200_arena_get(self.h, node_id, C.byref(p), C.byref(ln)) != 0:
+            return None
+        return C.string_at(p, ln.value)
+
+    def __del__(self):
+        try:
+            self.lib.arroy_b200_arena_free(self.h)
+        except Exception:
+            pass

@@ -71,6 +71,17 @@ struct Wave {  // device buffers of one wave of trees; kept across builds
         pool.release(); pool_counter.release(); jobs.release(); scratch.release(); active.release(); error.release(); final_ids.release(); keys.release();
     }
 };
+struct BuiltTreeView {  // views into the pinned HostWave buffers of the context
+    const void* recs = nullptr;
+    uint32_t n_recs = 0;
+    const uint32_t* final_rows = nullptr;  // n entries
+    const float* pool = nullptr;
+};
+struct StageWorker {  // one H2D lane of the staging pipeline: own stream, two pinned bounce buffers
+    cudaStream_t st = nullptr;
+    PinBuf pin[2];
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+};
 struct HostWave {  // pinned host copies of one wave's results; kept across builds
     PinBuf recs, final_rows, pool;
     void release() { recs.release(); final_rows.release(); pool.release(); }
@@ -98,7 +109,15 @@ struct arroy_ctx {
     double stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     uint64_t n_launches = 0, h2d_bytes = 0, d2h_bytes = 0;  // since create (arroy_b200_counters)
     cudaEvent_t tev0 = nullptr, tev1 = nullptr;
+    std::vector<StageWorker> stage_workers;
+    // results of the last build_trees_begin, waiting for build_trees_emit
+    std::vector<std::vector<struct BuiltTreeView>> pending_waves;
+    std::vector<uint32_t> pending_wave_t0;
+    uint32_t pending_pool_stride = 0, pending_n_trees = 0;
     Wave wave;
+    cudaGraph_t cached_graph = nullptr;
+    cudaGraphExec_t cached_exec = nullptr;
+    std::vector<uint8_t> cached_graph_key;  // BuildParams bytes + schedule the cached graph was captured for
     std::vector<HostWave> host_waves;
     double breakdown[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     std::vector<cudaStream_t> tree_streams;   // one per tree of a wave (asynchronous per-tree chains)
@@ -122,7 +141,7 @@ void launch_work(arroy_ctx* c, const Job* jobs, int njobs, int grid) {
         CK(cudaFuncSetAttribute(work_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    work_kernel<<<grid, WORK_THREADS, smem, c->stream>>>(jobs, njobs, c->items.as<float>(), c->h0.as<float>(), c->dim, c->ld, c->metric);
+    work_kernel<<<grid, WORK_THREADS, smem, c->stream>>>(jobs, njobs, c->items.as<float>(), c->h0.as<float>(), c->dim, c->ld, c->metric, 0);
     CK(cudaGetLastError());
     c->n_launches += 1;
 }
@@ -160,6 +179,57 @@ void default_headers(arroy_ctx* c) {
         compute_norms(c, false);
         CK(cudaMemcpyAsync(c->h0.p, c->norms.p, c->n * 4, cudaMemcpyDeviceToDevice, c->stream));
     }
+}
+
+// Staging pipeline: W host threads, each decoding row chunks into its own pinned bounce buffers and
+// issuing its own cudaMemcpyAsync on its own stream, so decode (host memcpy of unaligned values)
+// and PCIe transfers of different chunks overlap. row_src(i) = address of the dim floats of row i.
+template <class RowSrc>
+void stage_rows_pipeline(arroy_ctx* c, uint64_t n, uint32_t dim, uint32_t ld, RowSrc row_src) {
+    if (n == 0) return;
+    unsigned W = 8;   // measured on the B200 box: 8 lanes x 4 MB chunks reach ~48 GB/s (PCIe copy alone: 54 GB/s)
+    if (const char* e = getenv("ARROY_B200_STAGE_THREADS")) W = (unsigned)std::max(1, atoi(e));
+    W = std::max(1u, std::min(W, std::max(1u, std::thread::hardware_concurrency())));
+    size_t chunk_mb = 4;
+    if (const char* e = getenv("ARROY_B200_STAGE_CHUNK_MB")) chunk_mb = (size_t)std::max(1, atoi(e));
+    const uint64_t chunk_rows = std::max<uint64_t>(1, (chunk_mb << 20) / ((size_t)ld * 4));
+    const uint64_t n_chunks = (n + chunk_rows - 1) / chunk_rows;
+    W = (unsigned)std::min<uint64_t>(W, n_chunks);
+    if (c->stage_workers.size() < W) c->stage_workers.resize(W);
+    for (unsigned w = 0; w < W; ++w) {
+        StageWorker& sw = c->stage_workers[w];
+        if (!sw.st) CK(cudaStreamCreateWithFlags(&sw.st, cudaStreamNonBlocking));
+        for (int k = 0; k < 2; ++k) { sw.pin[k].ensure(chunk_rows * ld * 4); if (!sw.ev[k]) CK(cudaEventCreateWithFlags(&sw.ev[k], cudaEventDisableTiming)); }
+    }
+    CK(cudaStreamSynchronize(c->stream));  // the destination buffer must not be in use
+    std::mutex emu;
+    std::string err;
+    float* dst = c->items.as<float>();
+    auto worker = [&](unsigned w) {
+        try {
+            CK(cudaSetDevice(c->device));
+            StageWorker& sw = c->stage_workers[w];
+            bool used[2] = {false, false};
+            int k = 0;
+            for (uint64_t ch = w; ch < n_chunks; ch += W, k ^= 1) {
+                const uint64_t r0 = ch * chunk_rows, rows = std::min<uint64_t>(chunk_rows, n - r0);
+                if (used[k]) CK(cudaEventSynchronize(sw.ev[k]));
+                float* b = sw.pin[k].as<float>();
+                for (uint64_t i = 0; i < rows; ++i) {
+                    memcpy(b + i * ld, row_src(r0 + i), 4ull * dim);
+                    for (uint32_t t = dim; t < ld; ++t) b[i * ld + t] = 0.f;
+                }
+                CK(cudaMemcpyAsync(dst + r0 * ld, b, rows * ld * 4, cudaMemcpyHostToDevice, sw.st));
+                CK(cudaEventRecord(sw.ev[k], sw.st));
+                used[k] = true;
+            }
+            CK(cudaStreamSynchronize(sw.st));
+        } catch (const std::exception& e) { std::lock_guard<std::mutex> lk(emu); if (err.empty()) err = e.what(); }
+    };
+    if (W == 1) worker(0);
+    else { std::vector<std::thread> th; for (unsigned w = 0; w < W; ++w) th.emplace_back(worker, w); for (auto& x : th) x.join(); }
+    if (!err.empty()) throw CudaError(err);
+    c->h2d_bytes += n * (uint64_t)ld * 4;
 }
 
 // ---- RoaringBitmap::serialize_into (roaring 0.10.9, portable format, no run containers) ------
@@ -206,12 +276,7 @@ void roaring_serialize(const uint32_t* ids, size_t n, std::vector<uint8_t>& out)
 // ================================================================================================
 namespace {
 
-struct BuiltTree {  // views into the pinned HostWave buffers of the context
-    const Record* recs = nullptr;
-    uint32_t n_recs = 0;
-    const uint32_t* final_rows = nullptr;  // n entries
-    const float* pool = nullptr;
-};
+using BuiltTree = BuiltTreeView;
 
 void build_wave(arroy_ctx* c, size_t wave_no, uint32_t t0, uint32_t tw, const uint8_t (*seeds)[32], uint32_t K, uint32_t cap_mult,
                 arroy_b200_cancel_fn cancel, void* cancel_arg, std::vector<BuiltTree>& out_trees, uint32_t& out_pool_stride) {
@@ -242,7 +307,7 @@ void build_wave(arroy_ctx* c, size_t wave_no, uint32_t t0, uint32_t tw, const ui
     W.active.ensure(4);
     W.error.ensure(4);
     W.keys.ensure(32ull * tw);
-    size_t ws_bytes = 13ull * ld * 4;
+    size_t ws_bytes = (size_t)WS_VECS * ld * 4;
     int use_smem = ws_bytes <= 200 * 1024 ? 1 : 0;
     if (!use_smem) W.scratch.ensure(ws_bytes * tw);
 
@@ -289,15 +354,16 @@ void build_wave(arroy_ctx* c, size_t wave_no, uint32_t t0, uint32_t tw, const ui
     const bool use_graph = getenv("ARROY_B200_NO_GRAPH") == nullptr && !profile;
     const int steps_per_batch = lockstep ? 32 : (getenv("ARROY_B200_BATCH") ? std::max(1, atoi(getenv("ARROY_B200_BATCH"))) : 64);
     const int tree_grid = c->sm_count;  // work CTAs per tree launch in async mode
+    const int interleave = (getenv("ARROY_B200_INTERLEAVE") != nullptr && atoi(getenv("ARROY_B200_INTERLEAVE")) != 0) ? 1 : 0;
     const size_t wsmem1 = work_smem(ld, 1);
 
     auto launch_step = [&](cudaStream_t s) {  // lockstep: all trees per launch
         control_kernel<<<tw, CTRL_THREADS, ctrl_smem, s>>>(P, 0u);
-        work_kernel<<<work_grid, WORK_THREADS, wsmem, s>>>(P.jobs, (int)tw, P.items, P.ih0, P.d, P.ld, P.metric);
+        work_kernel<<<work_grid, WORK_THREADS, wsmem, s>>>(P.jobs, (int)tw, P.items, P.ih0, P.d, P.ld, P.metric, interleave);
     };
     auto launch_tree_step = [&](uint32_t t, cudaStream_t s) {  // async: one tree per launch
         control_kernel<<<1, CTRL_THREADS, ctrl_smem, s>>>(P, t);
-        work_kernel<<<tree_grid, WORK_THREADS, wsmem1, s>>>(P.jobs + t, 1, P.items, P.ih0, P.d, P.ld, P.metric);
+        work_kernel<<<tree_grid, WORK_THREADS, wsmem1, s>>>(P.jobs + t, 1, P.items, P.ih0, P.d, P.ld, P.metric, 0);
     };
     if (!lockstep) {
         while (c->tree_streams.size() < tw) { cudaStream_t st; CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking)); c->tree_streams.push_back(st); }
@@ -307,25 +373,40 @@ void build_wave(arroy_ctx* c, size_t wave_no, uint32_t t0, uint32_t tw, const ui
     CK(cudaStreamSynchronize(c->stream));
     c->breakdown[0] += ms_since(t_setup);
     auto t_graph = std::chrono::steady_clock::now();
-    cudaGraph_t graph = nullptr;
+    // The captured graph only depends on the kernel arguments (BuildParams: buffer pointers are
+    // stable because the wave buffers live in the context) and the schedule, so it is reused by
+    // later builds with the same shapes.
     cudaGraphExec_t gexec = nullptr;
     if (use_graph) {
-        CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
-        if (lockstep) { for (int i = 0; i < steps_per_batch; ++i) launch_step(c->stream); }
+        std::vector<uint8_t> key(sizeof(BuildParams) + 16);
+        memcpy(key.data(), &P, sizeof(BuildParams));
+        int32_t sched[4] = {(lockstep ? 1 : 0) | (interleave << 1), steps_per_batch, (int32_t)tw, (int32_t)ctrl_smem};
+        memcpy(key.data() + sizeof(BuildParams), sched, 16);
+        if (c->cached_exec && key == c->cached_graph_key) gexec = c->cached_exec;
         else {
-            CK(cudaEventRecord(c->tree_events[0], c->stream));
-            for (uint32_t t = 0; t < tw; ++t) {
-                cudaStream_t st = c->tree_streams[t];
-                CK(cudaStreamWaitEvent(st, c->tree_events[0], 0));
-                for (int i = 0; i < steps_per_batch; ++i) launch_tree_step(t, st);
-                CK(cudaEventRecord(c->tree_events[1 + t], st));
-                CK(cudaStreamWaitEvent(c->stream, c->tree_events[1 + t], 0));
+            if (c->cached_exec) { cudaGraphExecDestroy(c->cached_exec); c->cached_exec = nullptr; }
+            if (c->cached_graph) { cudaGraphDestroy(c->cached_graph); c->cached_graph = nullptr; }
+            c->cached_graph_key.clear();
+            cudaGraph_t graph = nullptr;
+            CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+            if (lockstep) { for (int i = 0; i < steps_per_batch; ++i) launch_step(c->stream); }
+            else {
+                CK(cudaEventRecord(c->tree_events[0], c->stream));
+                for (uint32_t t = 0; t < tw; ++t) {
+                    cudaStream_t st = c->tree_streams[t];
+                    CK(cudaStreamWaitEvent(st, c->tree_events[0], 0));
+                    for (int i = 0; i < steps_per_batch; ++i) launch_tree_step(t, st);
+                    CK(cudaEventRecord(c->tree_events[1 + t], st));
+                    CK(cudaStreamWaitEvent(c->stream, c->tree_events[1 + t], 0));
+                }
             }
+            CK(cudaStreamEndCapture(c->stream, &graph));
+            c->cached_graph = graph;
+            CK(cudaGraphInstantiate(&gexec, graph, 0));
+            c->cached_exec = gexec;
+            c->cached_graph_key = key;
         }
-        CK(cudaStreamEndCapture(c->stream, &graph));
-        CK(cudaGraphInstantiate(&gexec, graph, 0));
     }
-    struct GraphGuard { cudaGraph_t& g; cudaGraphExec_t& e; ~GraphGuard() { if (e) cudaGraphExecDestroy(e); if (g) cudaGraphDestroy(g); } } gg{graph, gexec};
 
     c->breakdown[1] += ms_since(t_graph);
     auto t_loop = std::chrono::steady_clock::now();
@@ -346,11 +427,14 @@ void build_wave(arroy_ctx* c, size_t wave_no, uint32_t t0, uint32_t tw, const ui
             for (int i = 0; i < steps_per_batch; ++i) {
                 control_kernel<<<tw, CTRL_THREADS, ctrl_smem, c->stream>>>(P, 0u);
                 CK(cudaEventRecord(pev[2 * i], c->stream));
-                work_kernel<<<work_grid, WORK_THREADS, wsmem, c->stream>>>(P.jobs, (int)tw, P.items, P.ih0, P.d, P.ld, P.metric);
+                work_kernel<<<work_grid, WORK_THREADS, wsmem, c->stream>>>(P.jobs, (int)tw, P.items, P.ih0, P.d, P.ld, P.metric, interleave);
                 CK(cudaEventRecord(pev[2 * i + 1], c->stream));
             }
             CK(cudaStreamSynchronize(c->stream));
-            for (int i = 0; i < steps_per_batch; ++i) { float ms = 0; CK(cudaEventElapsedTime(&ms, pev[2 * i], pev[2 * i + 1])); c->stats[5] += ms; }
+            for (int i = 0; i < steps_per_batch; ++i) {
+                float ms = 0; CK(cudaEventElapsedTime(&ms, pev[2 * i], pev[2 * i + 1])); c->stats[5] += ms;
+                if (getenv("ARROY_B200_TRACE") && steps + i < 48) fprintf(stderr, "[trace] step %llu work_kernel %.3f ms\n", (unsigned long long)(steps + i), ms);
+            }
         }
         else if (lockstep) { for (int i = 0; i < steps_per_batch; ++i) launch_step(c->stream); CK(cudaGetLastError()); }
         else {  // async without a graph (debugging): fork / join by events
@@ -403,7 +487,7 @@ void build_wave(arroy_ctx* c, size_t wave_no, uint32_t t0, uint32_t tw, const ui
     out_trees.resize(tw);
     uint64_t rec_off = 0;
     for (uint32_t t = 0; t < tw; ++t) {
-        out_trees[t].recs = H.recs.as<Record>() + rec_off;
+        out_trees[t].recs = static_cast<const void*>(H.recs.as<Record>() + rec_off);
         out_trees[t].n_recs = st[t].n_recs;
         out_trees[t].final_rows = H.final_rows.as<uint32_t>() + (size_t)t * n;
         out_trees[t].pool = H.pool.as<float>();
@@ -418,14 +502,15 @@ void build_wave(arroy_ctx* c, size_t wave_no, uint32_t t0, uint32_t tw, const ui
     c->breakdown[3] += ms_since(t_d2h);
 }
 
-void do_build(arroy_ctx* c, uint32_t n_trees, const uint8_t (*seeds)[32], const uint32_t* root_ids, uint32_t first_free, uint32_t split_after,
-              arroy_b200_cancel_fn cancel, void* cancel_arg, arroy_b200_node_sink sink, void* sink_arg, uint64_t* out_n_nodes) {
+// Phase 1: device build of `n_trees` trees; results stay parked in the context.
+void do_build_begin(arroy_ctx* c, uint32_t n_trees, const uint8_t (*seeds)[32], uint32_t split_after, arroy_b200_cancel_fn cancel, void* cancel_arg, uint32_t* out_counts) {
     require_staged(c);
     set_device(c);
     for (auto& s : c->stats) s = 0;
+    c->pending_waves.clear(); c->pending_wave_t0.clear(); c->pending_n_trees = 0;
     const uint32_t K = split_after ? split_after : c->dim;
     if (c->n <= K) throw ArgError("build_trees needs more items than split_after (a single Descendants node is the caller's job, src/writer.rs:499-501)");
-    if (n_trees == 0) { if (out_n_nodes) *out_n_nodes = 0; return; }
+    if (n_trees == 0) return;
     if (cancel && cancel(cancel_arg)) throw Cancelled("The corresponding build process has been cancelled");
 
     // wave size from free memory
@@ -435,25 +520,24 @@ void do_build(arroy_ctx* c, uint32_t n_trees, const uint8_t (*seeds)[32], const 
     const uint64_t leaves_est = n / K + 1;
     const uint64_t per_tree = n * (4 + 4 + 1 + 4) + (n / SCAN_UNIT + 1) * 4 + sizeof(Frame) * (uint64_t)MAX_DEPTH + 16ull * 8 * leaves_est +
                               4ull * (c->ld + NORMAL_HDR) * 4 * leaves_est + 4096;
-    uint64_t max_wave = (uint64_t)(free_b * 0.7) / std::max<uint64_t>(per_tree, 1);
+    uint64_t reusable = c->wave.perm0.cap + c->wave.perm1.cap + c->wave.flags.cap + c->wave.final_ids.cap + c->wave.pool.cap + c->wave.recs.cap;
+    uint64_t max_wave = (uint64_t)((free_b + reusable) * 0.7) / std::max<uint64_t>(per_tree, 1);
     if (const char* e = getenv("ARROY_B200_MAX_WAVE")) max_wave = std::min<uint64_t>(max_wave, (uint64_t)atoi(e));
-    max_wave = std::max<uint64_t>(1, std::min<uint64_t>(max_wave, 256));
+    max_wave = std::max<uint64_t>(1, std::min<uint64_t>(max_wave, 120));  // <= 128 concurrent kernels
 
     for (auto& b : c->breakdown) b = 0;
     CK(cudaEventRecord(c->ev0, c->stream));
-    std::vector<std::vector<BuiltTree>> waves;
-    std::vector<uint32_t> wave_t0;
     uint32_t pool_stride = 0;
     for (uint32_t t0 = 0; t0 < n_trees;) {
         uint32_t tw = (uint32_t)std::min<uint64_t>(max_wave, n_trees - t0);
         std::vector<BuiltTree> trees;
         uint32_t cap_mult = 1;
         for (;;) {
-            try { build_wave(c, waves.size(), t0, tw, seeds, K, cap_mult, cancel, cancel_arg, trees, pool_stride); break; }
+            try { build_wave(c, c->pending_waves.size(), t0, tw, seeds, K, cap_mult, cancel, cancel_arg, trees, pool_stride); break; }
             catch (const CapacityError&) { if (cap_mult >= 64) throw; cap_mult *= 4; }
         }
-        waves.push_back(std::move(trees));
-        wave_t0.push_back(t0);
+        c->pending_waves.push_back(std::move(trees));
+        c->pending_wave_t0.push_back(t0);
         t0 += tw;
     }
     CK(cudaEventRecord(c->ev1, c->stream));
@@ -461,28 +545,30 @@ void do_build(arroy_ctx* c, uint32_t n_trees, const uint8_t (*seeds)[32], const 
     float ms = 0;
     CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
     c->stats[4] = ms;
-
-    // node ids: roots pre-allocated; the rest numbered as a 1-thread rayon pool would (tree tasks
-    // LIFO => last tree first; post-order inside a tree) — SURVEY.md Appendix B.4
-    std::vector<const BuiltTree*> tree_ptr(n_trees);
-    for (size_t w = 0; w < waves.size(); ++w)
-        for (size_t i = 0; i < waves[w].size(); ++i) tree_ptr[wave_t0[w] + i] = &waves[w][i];
-    std::vector<uint64_t> base(n_trees);
-    uint64_t counter = first_free;
-    for (uint32_t k = 0; k < n_trees; ++k) {
-        uint32_t t = n_trees - 1 - k;
-        base[t] = counter;
-        counter += tree_ptr[t]->n_recs - 1;
-    }
-    if (counter > 0xffffffffull) throw CapacityError("node ids exceed u32 (Error::DatabaseFull)");
+    c->pending_pool_stride = pool_stride;
+    c->pending_n_trees = n_trees;
     uint64_t total_nodes = 0;
-    for (uint32_t t = 0; t < n_trees; ++t) total_nodes += tree_ptr[t]->n_recs;
-    if (out_n_nodes) *out_n_nodes = total_nodes;
+    for (size_t w = 0; w < c->pending_waves.size(); ++w)
+        for (size_t i = 0; i < c->pending_waves[w].size(); ++i) {
+            if (out_counts) out_counts[c->pending_wave_t0[w] + i] = c->pending_waves[w][i].n_recs;
+            total_nodes += c->pending_waves[w][i].n_recs;
+        }
     c->stats[6] = (double)total_nodes;
-    if (!sink) return;
+}
+
+// Phase 2: NodeCodec encoding of the parked trees. Non-root node li of tree t gets id base_ids[t] + li.
+void do_build_emit(arroy_ctx* c, const uint32_t* root_ids, const uint64_t* base, arroy_b200_node_sink sink, void* sink_arg) {
+    const uint32_t n_trees = c->pending_n_trees;
+    if (n_trees == 0 || !sink) return;
+    std::vector<const BuiltTree*> tree_ptr(n_trees);
+    for (size_t w = 0; w < c->pending_waves.size(); ++w)
+        for (size_t i = 0; i < c->pending_waves[w].size(); ++i) tree_ptr[c->pending_wave_t0[w] + i] = &c->pending_waves[w][i];
+    for (uint32_t t = 0; t < n_trees; ++t)
+        if (base[t] + tree_ptr[t]->n_recs > 0x100000000ull) throw CapacityError("node ids exceed u32 (Error::DatabaseFull)");
+    const uint32_t pool_stride = c->pending_pool_stride;
     auto t_enc = std::chrono::steady_clock::now();
 
-    // encode NodeCodec bytes (src/node.rs:229-241); trees in parallel, sink calls serialised
+    // encode NodeCodec bytes (src/node.rs:229-241); trees in parallel, the sink is called concurrently
     const int hdrf = metric_header_floats(c->metric);
     const uint32_t d = c->dim;
     std::mutex sink_mu;
@@ -497,11 +583,12 @@ void do_build(arroy_ctx* c, uint32_t n_trees, const uint8_t (*seeds)[32], const 
                 uint32_t t = next_tree.fetch_add(1);
                 if (t >= n_trees || abort_flag.load()) return;
                 const BuiltTree& T = *tree_ptr[t];
+                const Record* recs = static_cast<const Record*>(T.recs);
                 const float* pool = T.pool;
                 const uint32_t root_local = T.n_recs - 1;
                 auto gid = [&](uint32_t li) { return li == root_local ? root_ids[t] : (uint32_t)(base[t] + li); };
                 for (uint32_t li = 0; li < T.n_recs; ++li) {
-                    const Record& r = T.recs[li];
+                    const Record& r = recs[li];
                     buf.clear();
                     if (r.kind == REC_DESC) {
                         buf.push_back(1);
@@ -521,20 +608,34 @@ void do_build(arroy_ctx* c, uint32_t n_trees, const uint8_t (*seeds)[32], const 
                             memcpy(buf.data() + o + 4 * hdrf, s + NORMAL_HDR, 4ull * d);
                         }
                     }
-                    std::lock_guard<std::mutex> lk(sink_mu);
                     if (abort_flag.load()) return;
                     if (sink(sink_arg, gid(li), buf.data(), buf.size()) != 0) { abort_flag = 1; return; }
                 }
             }
         } catch (const std::exception& e) { std::lock_guard<std::mutex> lk(sink_mu); worker_err = e.what(); abort_flag = 2; }
     };
-    int nthreads = (int)std::min<uint32_t>(n_trees, std::max(1u, std::min(16u, std::thread::hardware_concurrency())));
+    int nthreads = (int)std::min<uint32_t>(n_trees, std::max(1u, std::min(32u, std::thread::hardware_concurrency())));
+    if (const char* e = getenv("ARROY_B200_ENCODE_THREADS")) nthreads = std::max(1, atoi(e));
     if (c->n < 100000) nthreads = 1;
     if (nthreads <= 1) worker();
     else { std::vector<std::thread> th; for (int i = 0; i < nthreads; ++i) th.emplace_back(worker); for (auto& x : th) x.join(); }
     c->breakdown[4] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_enc).count();
     if (abort_flag.load() == 1) throw Cancelled("node sink aborted the build");
     if (abort_flag.load() == 2) throw std::runtime_error(worker_err);
+}
+
+void do_build(arroy_ctx* c, uint32_t n_trees, const uint8_t (*seeds)[32], const uint32_t* root_ids, uint32_t first_free, uint32_t split_after,
+              arroy_b200_cancel_fn cancel, void* cancel_arg, arroy_b200_node_sink sink, void* sink_arg, uint64_t* out_n_nodes) {
+    std::vector<uint32_t> counts(n_trees, 0);
+    do_build_begin(c, n_trees, seeds, split_after, cancel, cancel_arg, counts.data());
+    // node ids: roots pre-allocated; the rest numbered as a 1-thread rayon pool would (tree tasks
+    // LIFO => last tree first; post-order inside a tree) — SURVEY.md Appendix B.4
+    std::vector<uint64_t> base(n_trees);
+    uint64_t counter = first_free, total = 0;
+    for (uint32_t k = 0; k < n_trees; ++k) { uint32_t t = n_trees - 1 - k; base[t] = counter; counter += counts[t] - 1; total += counts[t]; }
+    if (counter > 0xffffffffull) throw CapacityError("node ids exceed u32 (Error::DatabaseFull)");
+    if (out_n_nodes) *out_n_nodes = total;
+    do_build_emit(c, root_ids, base.data(), sink, sink_arg);
 }
 
 // ================================================================================================
@@ -705,6 +806,9 @@ void arroy_b200_destroy(arroy_ctx* c) {
     DevBuf* bufs[] = {&c->items, &c->h0, &c->h1, &c->norms, &c->maxbits, &c->s_rows, &c->s_flags, &c->s_margins, &c->s_normal, &c->s_unit, &c->s_job,
                       &c->s_keys, &c->s_dists, &c->s_q, &c->s_qh0, &c->s_off, &c->s_orows, &c->s_odist, &c->s_olen, &c->s_misc};
     for (auto* b : bufs) b->release();
+    if (c->cached_exec) cudaGraphExecDestroy(c->cached_exec);
+    if (c->cached_graph) cudaGraphDestroy(c->cached_graph);
+    for (auto& sw : c->stage_workers) { sw.pin[0].release(); sw.pin[1].release(); if (sw.ev[0]) cudaEventDestroy(sw.ev[0]); if (sw.ev[1]) cudaEventDestroy(sw.ev[1]); if (sw.st) cudaStreamDestroy(sw.st); }
     c->pin.release();
     c->wave.release();
     for (auto& hw : c->host_waves) hw.release();
@@ -728,48 +832,30 @@ int32_t arroy_b200_stage_items(arroy_ctx* c, int32_t metric, uint32_t dim, uint6
         const uint32_t ld = c->ld;
         const int hf = metric_header_floats(metric);
         std::vector<float> h0(n), h1(n, 0.f);
-        // decode the unaligned LMDB values into pinned chunks: [tag][Header][dim x f32]
-        const size_t chunk_rows = std::max<size_t>(1, (32u << 20) / ((size_t)ld * 4));
-        c->pin.ensure(2 * chunk_rows * ld * 4);
-        float* bufs[2] = {c->pin.as<float>(), c->pin.as<float>() + chunk_rows * ld};
-        cudaEvent_t done[2];
-        CK(cudaEventCreate(&done[0])); CK(cudaEventCreate(&done[1]));
-        bool used[2] = {false, false};
-        int which = 0;
-        for (uint64_t r0 = 0; r0 < n; r0 += chunk_rows, which ^= 1) {
-            uint64_t rows = std::min<uint64_t>(chunk_rows, n - r0);
-            if (used[which]) CK(cudaEventSynchronize(done[which]));
-            float* b = bufs[which];
+        // decode the unaligned LMDB values: [tag][Header][dim x f32]
+        {
             std::atomic<int> bad{0};
-            auto decode = [&](uint64_t i0, uint64_t i1) {
+            const unsigned nt = n < 65536 ? 1u : std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+            auto hdrs = [&](uint64_t i0, uint64_t i1) {
                 for (uint64_t i = i0; i < i1; ++i) {
-                    const uint8_t* v = leaf_values[r0 + i];
+                    const uint8_t* v = leaf_values[i];
                     if (!v || v[0] != 0) { bad = 1; return; }
-                    memcpy(&h0[r0 + i], v + 1, 4);
-                    if (hf == 2) memcpy(&h1[r0 + i], v + 5, 4);
-                    memcpy(b + i * ld, v + 1 + 4 * hf, 4ull * dim);
-                    for (uint32_t k = dim; k < ld; ++k) b[i * ld + k] = 0.f;
+                    memcpy(&h0[i], v + 1, 4);
+                    if (hf == 2) memcpy(&h1[i], v + 5, 4);
                 }
             };
-            const unsigned nt = rows * ld * 4 < (4u << 20) ? 1u : std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
-            if (nt <= 1) decode(0, rows);
-            else {
-                std::vector<std::thread> th;
-                for (unsigned t = 0; t < nt; ++t) th.emplace_back(decode, rows * t / nt, rows * (t + 1) / nt);
-                for (auto& x : th) x.join();
-            }
+            if (nt <= 1) hdrs(0, n);
+            else { std::vector<std::thread> th; for (unsigned t = 0; t < nt; ++t) th.emplace_back(hdrs, n * t / nt, n * (t + 1) / nt); for (auto& x : th) x.join(); }
             if (bad.load()) throw ArgError("leaf value does not start with the Leaf tag 0x00");
-            CK(cudaMemcpyAsync(c->items.as<float>() + r0 * ld, b, rows * ld * 4, cudaMemcpyHostToDevice, c->stream));
-            CK(cudaEventRecord(done[which], c->stream));
-            used[which] = true;
         }
+        const size_t voff = 1 + 4 * (size_t)hf;
+        stage_rows_pipeline(c, n, dim, ld, [&](uint64_t i) { return leaf_values[i] + voff; });
         if (n) {
             CK(cudaMemcpyAsync(c->h0.p, h0.data(), n * 4, cudaMemcpyHostToDevice, c->stream));
             CK(cudaMemcpyAsync(c->h1.p, h1.data(), n * 4, cudaMemcpyHostToDevice, c->stream));
         }
         CK(cudaStreamSynchronize(c->stream));
-        cudaEventDestroy(done[0]); cudaEventDestroy(done[1]);
-        c->h2d_bytes += (uint64_t)n * ld * 4 + 8 * n;
+        c->h2d_bytes += 8 * n;
         c->staged = true;
     });
 }
@@ -780,14 +866,15 @@ int32_t arroy_b200_stage_items_flat(arroy_ctx* c, int32_t metric, uint32_t dim, 
         if (n && (!ids || !vectors)) throw ArgError("null ids / vectors");
         alloc_items(c, metric, dim, n, ids);
         if (n) {
-            if (c->ld != dim) CK(cudaMemsetAsync(c->items.p, 0, (size_t)n * c->ld * 4, c->stream));
-            CK(cudaMemcpy2DAsync(c->items.p, (size_t)c->ld * 4, vectors, (size_t)dim * 4, (size_t)dim * 4, n, cudaMemcpyHostToDevice, c->stream));
+            const uint8_t* base = reinterpret_cast<const uint8_t*>(vectors);
+            const size_t stride = 4ull * dim;
+            stage_rows_pipeline(c, n, dim, c->ld, [&](uint64_t i) { return base + i * stride; });
             if (hdr0) CK(cudaMemcpyAsync(c->h0.p, hdr0, n * 4, cudaMemcpyHostToDevice, c->stream));
             else default_headers(c);
             if (hdr1) CK(cudaMemcpyAsync(c->h1.p, hdr1, n * 4, cudaMemcpyHostToDevice, c->stream));
         }
         CK(cudaStreamSynchronize(c->stream));
-        c->h2d_bytes += (uint64_t)n * dim * 4 + (hdr0 ? 4 * n : 0) + (hdr1 ? 4 * n : 0);
+        c->h2d_bytes += (hdr0 ? 4 * n : 0) + (hdr1 ? 4 * n : 0);
         c->staged = true;
     });
 }
@@ -846,13 +933,13 @@ int32_t arroy_b200_create_split(arroy_ctx* c, const uint32_t rng_key[8], uint64_
         const uint32_t ld = c->ld;
         c->s_rows.ensure(n_rows * 4);
         c->s_normal.ensure((size_t)(ld + NORMAL_HDR) * 4);
-        c->s_misc.ensure(64 + 13ull * ld * 4);
+        c->s_misc.ensure(64 + (size_t)WS_VECS * ld * 4);
         CK(cudaMemcpyAsync(c->s_rows.p, rows, n_rows * 4, cudaMemcpyHostToDevice, c->stream));
         CK(cudaMemcpyAsync(c->s_misc.p, rng_key, 32, cudaMemcpyHostToDevice, c->stream));
         BuildParams P{};
         P.items = c->items.as<float>(); P.ih0 = c->h0.as<float>(); P.ih1 = c->h1.as<float>();
         P.n = (uint32_t)c->n; P.d = c->dim; P.ld = ld; P.metric = c->metric;
-        size_t ws_bytes = 13ull * ld * 4;
+        size_t ws_bytes = (size_t)WS_VECS * ld * 4;
         P.use_smem_ws = ws_bytes <= 200 * 1024;
         P.scratch = reinterpret_cast<float*>(c->s_misc.as<uint8_t>() + 64);
         size_t smem = P.use_smem_ws ? ws_bytes : 0;
@@ -876,6 +963,20 @@ int32_t arroy_b200_build_trees(arroy_ctx* c, uint32_t n_trees, const uint8_t (*t
     return guarded(c, [&] {
         if (n_trees && (!tree_seeds || !root_ids)) throw ArgError("null seeds / root ids");
         do_build(c, n_trees, tree_seeds, root_ids, first_free_node_id, split_after, cancel, cancel_arg, sink, sink_arg, out_n_nodes);
+    });
+}
+
+int32_t arroy_b200_build_trees_begin(arroy_ctx* c, uint32_t n_trees, const uint8_t (*tree_seeds)[32], uint32_t split_after,
+                                     arroy_b200_cancel_fn cancel, void* cancel_arg, uint32_t* out_node_counts) {
+    return guarded(c, [&] {
+        if (n_trees && !tree_seeds) throw ArgError("null seeds");
+        do_build_begin(c, n_trees, tree_seeds, split_after, cancel, cancel_arg, out_node_counts);
+    });
+}
+int32_t arroy_b200_build_trees_emit(arroy_ctx* c, const uint32_t* root_ids, const uint64_t* base_ids, arroy_b200_node_sink sink, void* sink_arg) {
+    return guarded(c, [&] {
+        if (c->pending_n_trees && (!root_ids || !base_ids)) throw ArgError("null root / base ids");
+        do_build_emit(c, root_ids, base_ids, sink, sink_arg);
     });
 }
 
@@ -963,6 +1064,36 @@ int32_t arroy_b200_time_scan(arroy_ctx* c, const float* normal, float hdr0, floa
             *out_left_count = s;
         }
     });
+}
+
+struct arroy_b200_arena {
+    static constexpr int SHARDS = 64;
+    std::mutex mu[SHARDS];
+    std::vector<uint8_t> bytes[SHARDS];
+    std::vector<std::pair<uint32_t, std::pair<uint64_t, uint64_t>>> index[SHARDS];  // node id -> (offset, len) in its shard
+};
+arroy_b200_arena* arroy_b200_arena_new(void) { return new arroy_b200_arena(); }
+void arroy_b200_arena_free(arroy_b200_arena* a) { delete a; }
+void arroy_b200_arena_clear(arroy_b200_arena* a) { for (int i = 0; i < arroy_b200_arena::SHARDS; ++i) { a->bytes[i].clear(); a->index[i].clear(); } }
+int32_t arroy_b200_arena_sink(void* arg, uint32_t node_id, const uint8_t* bytes, uint64_t len) {
+    auto* a = static_cast<arroy_b200_arena*>(arg);
+    const int sh = (int)(std::hash<std::thread::id>()(std::this_thread::get_id()) % arroy_b200_arena::SHARDS);
+    std::lock_guard<std::mutex> lk(a->mu[sh]);
+    uint64_t off = a->bytes[sh].size();
+    a->bytes[sh].insert(a->bytes[sh].end(), bytes, bytes + len);
+    a->index[sh].push_back({node_id, {off, len}});
+    return 0;
+}
+uint64_t arroy_b200_arena_stats(arroy_b200_arena* a, uint64_t* out_total_bytes) {
+    uint64_t n = 0, b = 0;
+    for (int i = 0; i < arroy_b200_arena::SHARDS; ++i) { n += a->index[i].size(); b += a->bytes[i].size(); }
+    if (out_total_bytes) *out_total_bytes = b;
+    return n;
+}
+int32_t arroy_b200_arena_get(arroy_b200_arena* a, uint32_t node_id, const uint8_t** out_bytes, uint64_t* out_len) {
+    for (int i = 0; i < arroy_b200_arena::SHARDS; ++i)
+        for (auto& e : a->index[i]) if (e.first == node_id) { *out_bytes = a->bytes[i].data() + e.second.first; *out_len = e.second.second; return 0; }
+    return ARROY_B200_ERR_INVALID;
 }
 
 int32_t arroy_b200_build_breakdown(arroy_ctx* c, double out[8]) {

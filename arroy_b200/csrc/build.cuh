@@ -64,7 +64,7 @@ struct BuildParams {
     uint32_t units_per_tree;
     float* pool; uint32_t pool_stride; uint32_t pool_cap; uint32_t* pool_counter;
     Job* jobs;
-    float* scratch;          // n_trees x 13 x ld (two_means workspace when it does not fit in smem)
+    float* scratch;          // n_trees x WS_VECS x ld (two_means workspace when it does not fit in smem)
     int32_t use_smem_ws;
     uint32_t* active;        // trees not yet done
     int32_t* error;
@@ -78,40 +78,46 @@ __device__ __forceinline__ double split_imbalance_dev(uint32_t l, uint32_t r) { 
 }
 
 // ---- two_means + create_split on one CTA ----------------------------------------------------
-// ws: 13 vectors of ld floats: ws[0]=p, ws[1]=q, ws[2..11]=the ten sampled k, ws[12]=normal/bias terms.
+// ws: WS_VECS vectors of ld floats: ws[0]=p, ws[1]=q, ws[2..11]=the ten sampled k,
+// ws[12], ws[13] = scratch (normal / bias terms / Manhattan terms).
+constexpr int WS_VECS = 14;
 struct TwoMeansShared {
     uint32_t rows[12];
     float h0[12], h1[12];
-    float res[4];
+    float nk[12];           // D::norm of p (0), q (1) and of the ten k (2..11)
+    float res[2][2];        // di, dj, double buffered by iteration parity
     float php[2], phq[2];   // headers of p and q
+    float misc[2];
 };
 
-__device__ __forceinline__ float nbd_warp(int metric, const float* p, float ph0, float ph1, const float* k, float kh0, float kh1, int d) {
-    // D::non_built_distance — mod.rs:54-56 (= built_distance) except dot_product.rs:58-70
-    if (metric == EUCLIDEAN) return exact_warp<true>(p, k, d);
-    if (metric == MANHATTAN) {
-        float s = 0.0f;
-        if ((threadIdx.x & 31) == 0) for (int i = 0; i < d; ++i) s = __fadd_rn(s, fabsf(__fsub_rn(p[i], k[i])));
-        return __shfl_sync(0xffffffffu, s, 0);
-    }
-    float pq = exact_warp<false>(p, k, d);
+// D::non_built_distance on one 8-lane group — mod.rs:54-56 (= built_distance) except dot_product.rs:58-70.
+// Manhattan is handled by the caller (strictly sequential sum).
+__device__ __forceinline__ float nbd_group(int metric, const float* p, float ph0, float ph1, const float* k, float kh0, float kh1, int d) {
+    if (metric == EUCLIDEAN) return exact_group8<true>(p, k, d);
+    float pq = exact_group8<false>(p, k, d);
     if (metric == COSINE) return built_finish(COSINE, pq, ph0, kh0);
-    // DOT_PRODUCT
-    float pp = ph1, qq = kh1;
+    float pp = ph1, qq = kh1;  // DOT_PRODUCT
     pq = __fadd_rn(pq, __fmul_rn(ph0, kh0));
     float ppqq = __fmul_rn(pp, qq);
     if (ppqq >= 1.17549435e-38f) return __fsub_rn(2.0f, __fdiv_rn(__fmul_rn(2.0f, pq), __fsqrt_rn(ppqq)));
     return 2.0f;
 }
-__device__ __forceinline__ float norm_leaf_warp(int metric, const float* v, float h0, int d) {
-    float dot = exact_warp<false>(v, v, d);
+__device__ __forceinline__ float norm_leaf_group(int metric, const float* v, float h0, int d) {
+    float dot = exact_group8<false>(v, v, d);
     if (metric == DOT_PRODUCT) return __fsqrt_rn(__fadd_rn(dot, __fmul_rn(h0, h0)));  // dot_product.rs:72-75
     return __fsqrt_rn(dot);                                                              // mod.rs:70-72
 }
-// D::init — cosine.rs:69-71, dot_product.rs:94-96 (no-op otherwise). Called by one warp.
-__device__ __forceinline__ void init_warp(int metric, const float* v, float* hdr, int d) {
-    if (metric == COSINE) { float x = __fsqrt_rn(exact_warp<false>(v, v, d)); if ((threadIdx.x & 31) == 0) hdr[0] = x; }
-    else if (metric == DOT_PRODUCT) { float x = exact_warp<false>(v, v, d); if ((threadIdx.x & 31) == 0) hdr[1] = x; }
+// D::init of p (group 0) and q (group 1) by warp 0 — cosine.rs:69-71, dot_product.rs:94-96
+__device__ __forceinline__ void init_pq_warp0(int metric, const float* p, const float* q, TwoMeansShared& S, int d, bool do_p, bool do_q) {
+    if (metric != COSINE && metric != DOT_PRODUCT) return;
+    const int lane = threadIdx.x & 31, grp = lane >> 3;
+    const float* v = (grp & 1) ? q : p;
+    float x = exact_group8<false>(v, v, d);
+    if (metric == COSINE) x = __fsqrt_rn(x);
+    const int slot = metric == COSINE ? 0 : 1;
+    if (lane == 0 && do_p) S.php[slot] = x;
+    if (lane == 8 && do_q) S.phq[slot] = x;
+    __syncwarp();
 }
 
 // Draws the RNG exactly like choose_two + 10 x choose (src/parallel.rs:342-367), runs
@@ -120,7 +126,7 @@ __device__ __forceinline__ void init_warp(int metric, const float* v, float* hdr
 __device__ void create_split_cta(const BuildParams& P, Rng& rng /* thread 0 only */, const uint32_t* seg, uint32_t len,
                                  float* ws, TwoMeansShared& S, float* slot_ptr) {
     const int d = (int)P.d, ld = (int)P.ld, metric = P.metric;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, grp = lane >> 3;
     const bool cosine = (metric == COSINE || metric == DOT_PRODUCT);
     if (tid == 0) {  // all RNG draws of the attempt first: they do not depend on the data
         uint32_t a, b;
@@ -132,7 +138,7 @@ __device__ void create_split_cta(const BuildParams& P, Rng& rng /* thread 0 only
     uint32_t my_row = 0;
     if (tid < 12) my_row = seg[S.rows[tid]];  // RoaringBitmap::select(rank) on the ascending id list
     __syncthreads();
-    if (tid < 12) S.rows[tid] = my_row;
+    if (tid < 12) { S.rows[tid] = my_row; S.h0[tid] = P.ih0 ? P.ih0[my_row] : 0.f; S.h1[tid] = P.ih1 ? P.ih1[my_row] : 0.f; }
     __syncthreads();
     {   // gather the 12 rows (float4, all loads independent)
         const int l4 = ld >> 2;
@@ -140,76 +146,99 @@ __device__ void create_split_cta(const BuildParams& P, Rng& rng /* thread 0 only
             int j = i / l4, c = i - j * l4;
             reinterpret_cast<float4*>(ws + (size_t)j * ld)[c] = __ldg(reinterpret_cast<const float4*>(P.items + (size_t)S.rows[j] * ld) + c);
         }
-        if (tid < 12) { S.h0[tid] = P.ih0 ? P.ih0[S.rows[tid]] : 0.f; S.h1[tid] = P.ih1 ? P.ih1[S.rows[tid]] : 0.f; }
+        if (tid == 0) { S.php[0] = S.h0[0]; S.php[1] = S.h1[0]; S.phq[0] = S.h0[1]; S.phq[1] = S.h1[1]; }
     }
     __syncthreads();
     float* p = ws; float* q = ws + ld;
-    if (tid == 0) { S.php[0] = S.h0[0]; S.php[1] = S.h1[0]; S.phq[0] = S.h0[1]; S.phq[1] = S.h1[1]; }
-    __syncthreads();
-    if (cosine) {  // D::normalize(p), D::normalize(q) — mod.rs:76-82, dot_product.rs:85-92
-        if (warp == 0) { float x = norm_leaf_warp(metric, p, S.php[0], d); if (lane == 0) S.res[0] = x; }
-        if (warp == 1) { float x = norm_leaf_warp(metric, q, S.phq[0], d); if (lane == 0) S.res[1] = x; }
+    float* sc0 = ws + (size_t)12 * ld; float* sc1 = ws + (size_t)13 * ld;
+    if (cosine) {
+        // D::norm of all 12 gathered leaves in one pass: 8 warps x 4 groups. For p and q it feeds
+        // D::normalize (mod.rs:76-82, dot_product.rs:85-92); for the ten k it is the `norm` of
+        // two_means' loop (mod.rs:152) — it does not depend on the centroids.
+        const int gi = warp * 4 + grp;
+        const int j = gi < 12 ? gi : 0;
+        float x = norm_leaf_group(metric, ws + (size_t)j * ld, S.h0[j], d);
+        if (gi < 12 && (lane & 7) == 0) S.nk[gi] = x;
         __syncthreads();
-        float np = S.res[0], nq = S.res[1];
+        const float np = S.nk[0], nq = S.nk[1];
         if (np > 0.0f) for (int i = tid; i < d; i += blockDim.x) p[i] = __fdiv_rn(p[i], np);
         if (nq > 0.0f) for (int i = tid; i < d; i += blockDim.x) q[i] = __fdiv_rn(q[i], nq);
-        __syncthreads();
         if (tid == 0 && metric == DOT_PRODUCT) {
             if (np > 0.0f) S.php[0] = __fdiv_rn(S.php[0], np);
             if (nq > 0.0f) S.phq[0] = __fdiv_rn(S.phq[0], nq);
         }
+        __syncthreads();
     }
-    if (warp == 0) init_warp(metric, p, S.php, d);
-    if (warp == 1) init_warp(metric, q, S.phq, d);
-    __syncthreads();
+    if (warp == 0) init_pq_warp0(metric, p, q, S, d, true, true);
     float ic = 1.0f, jc = 1.0f;
     for (int it = 0; it < 10; ++it) {
         const float* k = ws + (size_t)(2 + it) * ld;
         const float kh0 = S.h0[2 + it], kh1 = S.h1[2 + it];
-        if (warp == 0) { float x = nbd_warp(metric, p, S.php[0], S.php[1], k, kh0, kh1, d); if (lane == 0) S.res[0] = x; }
-        if (warp == 1) { float x = nbd_warp(metric, q, S.phq[0], S.phq[1], k, kh0, kh1, d); if (lane == 0) S.res[1] = x; }
-        if (warp == 2) { float x = cosine ? norm_leaf_warp(metric, k, kh0, d) : 1.0f; if (lane == 0) S.res[2] = x; }
+        if (metric == MANHATTAN) {  // manhattan.rs:44-46: strictly sequential sum of |p - k|
+            for (int i = tid; i < d; i += blockDim.x) { sc0[i] = fabsf(__fsub_rn(p[i], k[i])); sc1[i] = fabsf(__fsub_rn(q[i], k[i])); }
+            __syncthreads();
+            if (tid < 2) {
+                const float* t = tid ? sc1 : sc0;
+                float s = 0.0f;
+                int i = 0;
+                for (; i + 8 <= d; i += 8) {
+                    float t0 = t[i], t1 = t[i + 1], t2 = t[i + 2], t3 = t[i + 3], t4 = t[i + 4], t5 = t[i + 5], t6 = t[i + 6], t7 = t[i + 7];
+                    s = __fadd_rn(s, t0); s = __fadd_rn(s, t1); s = __fadd_rn(s, t2); s = __fadd_rn(s, t3);
+                    s = __fadd_rn(s, t4); s = __fadd_rn(s, t5); s = __fadd_rn(s, t6); s = __fadd_rn(s, t7);
+                }
+                for (; i < d; ++i) s = __fadd_rn(s, t[i]);
+                S.res[it & 1][tid] = __fmul_rn(tid ? jc : ic, s);
+            }
+        } else if (warp == 0) {  // di on group 0, dj on group 1 (groups 2, 3 mirror them)
+            const bool second = (grp & 1) != 0;
+            float x = nbd_group(metric, second ? q : p, second ? S.phq[0] : S.php[0], second ? S.phq[1] : S.php[1], k, kh0, kh1, d);
+            if (lane == 0) S.res[it & 1][0] = __fmul_rn(ic, x);
+            if (lane == 8) S.res[it & 1][1] = __fmul_rn(jc, x);
+        }
         __syncthreads();
-        const float di = __fmul_rn(ic, S.res[0]), dj = __fmul_rn(jc, S.res[1]), norm = S.res[2];
-        __syncthreads();  // everyone has read res before the next iteration overwrites it
+        const float di = S.res[it & 1][0], dj = S.res[it & 1][1];
+        const float norm = cosine ? S.nk[2 + it] : 1.0f;
         if (norm != norm || norm <= 0.0f) continue;
         if (di < dj) {        // update_mean(p, k, norm, ic) — mod.rs:86-94
             const float c1 = __fadd_rn(ic, 1.0f);
             for (int i = tid; i < d; i += blockDim.x) p[i] = __fdiv_rn(__fadd_rn(__fmul_rn(p[i], ic), __fdiv_rn(k[i], norm)), c1);
-            __syncthreads();
-            if (warp == 0) init_warp(metric, p, S.php, d);
             ic = c1;
             __syncthreads();
+            if (warp == 0) init_pq_warp0(metric, p, q, S, d, true, false);
         } else if (dj < di) {
             const float c1 = __fadd_rn(jc, 1.0f);
             for (int i = tid; i < d; i += blockDim.x) q[i] = __fdiv_rn(__fadd_rn(__fmul_rn(q[i], jc), __fdiv_rn(k[i], norm)), c1);
-            __syncthreads();
-            if (warp == 0) init_warp(metric, q, S.phq, d);
             jc = c1;
             __syncthreads();
+            if (warp == 0) init_pq_warp0(metric, p, q, S, d, false, true);
         }
     }
+    __syncthreads();
     // normal = normalize(p - q) (+ bias / extra_dim) — euclidean.rs:59-75, manhattan.rs:62-78,
     // cosine.rs:77-83, dot_product.rs:102-111
-    float* nv = ws + (size_t)12 * ld;
+    float* nv = sc0;
     for (int i = tid; i < ld; i += blockDim.x) nv[i] = i < d ? __fsub_rn(p[i], q[i]) : 0.f;
     float extra = (metric == DOT_PRODUCT) ? __fsub_rn(S.php[0], S.phq[0]) : 0.f;
     __syncthreads();
-    if (warp == 0) { float x = norm_leaf_warp(metric, nv, extra, d); if (lane == 0) S.res[0] = x; }
+    if (warp == 0) { float x = norm_leaf_group(metric, nv, extra, d); if (lane == 0) S.misc[0] = x; }
     __syncthreads();
-    const float nn = S.res[0];
+    const float nn = S.misc[0];
     float* out = slot_ptr + NORMAL_HDR;
     if (nn > 0.0f) { for (int i = tid; i < d; i += blockDim.x) nv[i] = __fdiv_rn(nv[i], nn); extra = (metric == DOT_PRODUCT) ? __fdiv_rn(extra, nn) : extra; }
-    __syncthreads();
-    for (int i = tid; i < ld; i += blockDim.x) out[i] = nv[i];
+    for (int i = tid; i < ld; i += blockDim.x) out[i] = nv[i];  // each thread re-reads only what it wrote
     if (metric == EUCLIDEAN || metric == MANHATTAN) {
         // bias = sum over i of ((-n_i) * (p_i + q_i)) / 2, folded left to right from +0.0
-        __syncthreads();
-        for (int i = tid; i < d; i += blockDim.x) nv[i] = __fdiv_rn(__fmul_rn(-nv[i], __fadd_rn(p[i], q[i])), 2.0f);
+        for (int i = tid; i < d; i += blockDim.x) sc1[i] = __fdiv_rn(__fmul_rn(-nv[i], __fadd_rn(p[i], q[i])), 2.0f);
         __syncthreads();
         if (tid == 0) {
             float bias = 0.0f;
-            for (int i = 0; i < d; ++i) bias = __fadd_rn(bias, nv[i]);
+            int i = 0;
+            for (; i + 8 <= d; i += 8) {
+                float t0 = sc1[i], t1 = sc1[i + 1], t2 = sc1[i + 2], t3 = sc1[i + 3], t4 = sc1[i + 4], t5 = sc1[i + 5], t6 = sc1[i + 6], t7 = sc1[i + 7];
+                bias = __fadd_rn(bias, t0); bias = __fadd_rn(bias, t1); bias = __fadd_rn(bias, t2); bias = __fadd_rn(bias, t3);
+                bias = __fadd_rn(bias, t4); bias = __fadd_rn(bias, t5); bias = __fadd_rn(bias, t6); bias = __fadd_rn(bias, t7);
+            }
+            for (; i < d; ++i) bias = __fadd_rn(bias, sc1[i]);
             slot_ptr[0] = bias; slot_ptr[1] = 0.f; slot_ptr[2] = 0.f; slot_ptr[3] = 0.f;
         }
     } else if (tid == 0) {
@@ -219,14 +248,50 @@ __device__ void create_split_cta(const BuildParams& P, Rng& rng /* thread 0 only
     __syncthreads();
 }
 
-// CTA-wide stable partition of a whole node (any size) by its flags.
-__device__ void partition_inline(const uint32_t* src, const uint8_t* flags, uint32_t* dst, uint32_t len, uint32_t total_left, uint32_t* sm_w) {
+// CTA-wide stable partition of a whole node (any size) by its flags. Each round handles
+// PART_BATCH sub-blocks of blockDim ids: all loads of the round are issued before any is used, one
+// barrier per round. sm_pw: 2 * PART_BATCH * 8 + 2 uint32.
+constexpr int PART_BATCH = 8;
+__device__ void partition_inline(const uint32_t* __restrict__ src, const uint8_t* __restrict__ flags, uint32_t* __restrict__ dst, uint32_t len, uint32_t total_left, uint32_t* sm_pw) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t left_before = 0;
-    for (uint32_t base = 0; base < len; base += PART_UNIT) {
-        partition_block(src, flags, dst, base, len, left_before, total_left, sm_w);
-        uint32_t add = 0;
-        for (int w = 0; w < 8; ++w) add += sm_w[w];
-        left_before += add;
+    for (uint32_t base = 0; base < len; base += PART_BATCH * CTRL_THREADS) {
+        uint32_t id[PART_BATCH];
+        int fl[PART_BATCH];
+#pragma unroll
+        for (int j = 0; j < PART_BATCH; ++j) {
+            uint32_t p = base + j * CTRL_THREADS + threadIdx.x;
+            bool v = p < len;
+            fl[j] = v ? (int)flags[p] : 2;   // 2 = out of range
+            id[j] = v ? src[p] : 0u;
+        }
+        unsigned lm[PART_BATCH], rm[PART_BATCH];
+#pragma unroll
+        for (int j = 0; j < PART_BATCH; ++j) {
+            lm[j] = __ballot_sync(0xffffffffu, fl[j] == 0);
+            rm[j] = __ballot_sync(0xffffffffu, fl[j] == 1);
+            if (lane == 0) { sm_pw[j * 8 + warp] = __popc(lm[j]); sm_pw[PART_BATCH * 8 + j * 8 + warp] = __popc(rm[j]); }
+        }
+        __syncthreads();
+        // offsets in source order: sub-blocks in order, warps in order inside a sub-block
+        const unsigned below = (1u << lane) - 1u;
+        const uint32_t right_before = base - left_before;
+        uint32_t run_l = 0, run_r = 0;
+#pragma unroll
+        for (int j = 0; j < PART_BATCH; ++j) {
+            uint32_t wl = 0, wr = 0, jl = 0, jr = 0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) {
+                const uint32_t a = sm_pw[j * 8 + w], b = sm_pw[PART_BATCH * 8 + j * 8 + w];
+                jl += a; jr += b;
+                if (w < warp) { wl += a; wr += b; }
+            }
+            if (fl[j] == 0) dst[left_before + run_l + wl + __popc(lm[j] & below)] = id[j];
+            else if (fl[j] == 1) dst[total_left + right_before + run_r + wr + __popc(rm[j] & below)] = id[j];
+            run_l += jl; run_r += jr;
+        }
+        const uint32_t ltot = run_l;
+        left_before += ltot;
         __syncthreads();
     }
 }
@@ -264,7 +329,7 @@ __global__ void __launch_bounds__(CTRL_THREADS, 1) control_kernel(BuildParams P,
     extern __shared__ __align__(16) unsigned char ctrl_smem[];
     __shared__ TwoMeansShared TM;
     __shared__ uint32_t sm_tmp[CTRL_THREADS + 1];
-    __shared__ uint32_t sm_w[16];
+    __shared__ uint32_t sm_w[2 * PART_BATCH * 8 + 2];
     __shared__ int s_action;
     __shared__ uint32_t s_total_left;
     __shared__ Rng s_rng;  // thread 0 only
@@ -288,7 +353,7 @@ __global__ void __launch_bounds__(CTRL_THREADS, 1) control_kernel(BuildParams P,
     uint32_t* perm1 = P.perm[1] + (size_t)t * P.n;
     uint8_t* flags = P.flags + (size_t)t * P.n;
     uint32_t* unit_left = P.unit_left + (size_t)t * P.units_per_tree;
-    float* ws = P.use_smem_ws ? reinterpret_cast<float*>(ctrl_smem) : P.scratch + (size_t)t * 13 * P.ld;
+    float* ws = P.use_smem_ws ? reinterpret_cast<float*>(ctrl_smem) : P.scratch + (size_t)t * WS_VECS * P.ld;
     const int tid = threadIdx.x;
 
     if (tid == 0) { s_rng.init(S.key, S.pos); job.kind = JOB_NONE; }

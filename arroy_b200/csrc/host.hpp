@@ -254,10 +254,20 @@ inline void write_version(arroy_env* env, uint16_t index) {  // version.rs:39-49
     env->kv[make_key(index, MODE_METADATA, 1)] = std::string(reinterpret_cast<const char*>(v), 12);
 }
 
-struct SinkArg { arroy_env* env; uint16_t index; uint64_t bytes; };
+// The library calls the sink concurrently from its encoder threads; nodes are parked in shards and
+// moved into the ordered table once the build is over (TmpNodes files -> LMDB, writer.rs:597-607).
+struct SinkArg {
+    static constexpr int SHARDS = 64;
+    std::mutex mu[SHARDS];
+    std::vector<std::pair<uint32_t, std::string>> nodes[SHARDS];
+    std::atomic<uint64_t> bytes{0};
+};
 inline int32_t tree_sink(void* arg, uint32_t node_id, const uint8_t* bytes, uint64_t len) {
     auto* a = static_cast<SinkArg*>(arg);
-    a->env->kv[make_key(a->index, MODE_TREE, node_id)] = std::string(reinterpret_cast<const char*>(bytes), len);
+    const int sh = (int)(std::hash<std::thread::id>()(std::this_thread::get_id()) % SinkArg::SHARDS);
+    std::string v(reinterpret_cast<const char*>(bytes), len);
+    std::lock_guard<std::mutex> lk(a->mu[sh]);
+    a->nodes[sh].emplace_back(node_id, std::move(v));
     a->bytes += len;
     return 0;
 }
@@ -365,12 +375,19 @@ inline void writer_build(arroy_writer* w, arroy_ctx* ctx, arroy_rng* rng, int64_
     for (uint64_t t = 0; t < target; ++t) rng1.gen_seed(seeds[t].data());
     step("CreateTreesForItems");
     t0 = clk::now();
-    SinkArg sa{env, index, 0};
+    SinkArg sa;
     uint64_t n_nodes = 0;
     dev_ck(ctx, arroy_b200_build_trees(ctx, (uint32_t)target, reinterpret_cast<const uint8_t(*)[32]>(seeds.data()), roots.data(), (uint32_t)target,
                                        (uint32_t)split_after, cancel, cancel_arg, tree_sink, &sa, &n_nodes));
+    {   // move the parked nodes into the ordered table, ascending by id
+        std::vector<std::pair<uint32_t, std::string>> all;
+        for (int sh = 0; sh < SinkArg::SHARDS; ++sh) { for (auto& e : sa.nodes[sh]) all.emplace_back(std::move(e)); sa.nodes[sh].clear(); }
+        std::sort(all.begin(), all.end(), [](const std::pair<uint32_t, std::string>& a, const std::pair<uint32_t, std::string>& b) { return a.first < b.first; });
+        auto hint = env->kv.lower_bound(make_key(index, MODE_TREE, 0));
+        for (auto& e : all) hint = std::next(env->kv.insert_or_assign(hint, make_key(index, MODE_TREE, e.first), std::move(e.second)));
+    }
     w->timings[2] = ms_since(t0);
-    w->timings[6] = (double)sa.bytes;
+    w->timings[6] = (double)sa.bytes.load();
     step("WriteTheMetadata");
     t0 = clk::now();
     env->kv[make_key(index, MODE_METADATA, 0)] = encode_metadata(w->metric, d, items.ids, roots);

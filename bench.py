@@ -157,6 +157,7 @@ def main():
     ap.add_argument("--ref-trees", type=int, default=None, help="trees built per step by --impl reference / cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-writer-e2e", action="store_true")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
@@ -197,15 +198,20 @@ def main():
         if dist is not None:
             dist.barrier()
 
+    from arroy_b200 import parallel
+
     def one_step():
-        # multi-GPU: ONE NCCL broadcast of the item buffer over NVLink, then no further exchange
+        # multi-GPU: ONE NCCL broadcast of the item buffer over NVLink, then no further data exchange
         if dist is not None:
-            dist.broadcast(items, src=0)
+            parallel.broadcast_items(dist, items, src=0)
             torch.cuda.synchronize()
         ctx.stage_items_device(metric, ids, d, items.data_ptr())
         if metric == "dot-product":
             ctx.dot_preprocess()
-        return ctx.build_trees([seeds[t] for t in my_trees], my_trees, T, collect=False)
+        counts = ctx.build_trees_begin([seeds[t] for t in my_trees])
+        # tiny all-gather of node counts so every rank can number its nodes like a single-GPU build
+        parallel.gather_counts(dist, counts, T, rank, world, device=dev if dist is not None else None)
+        return counts
 
     for _ in range(args.warmup):
         one_step()
@@ -254,7 +260,7 @@ def main():
         # roofline of the dominant kernel: work_kernel (side()/margin scan). One extra, untimed build
         # with CUDA events around every work_kernel launch on its launching stream.
         os.environ["ARROY_B200_PROFILE"] = "1"
-        one_step()
+        ctx.build_trees_begin([seeds[t] for t in my_trees])   # rank-local: no collective in here
         os.environ.pop("ARROY_B200_PROFILE")
         st = ctx.build_stats()
         scan_ms, steps_dev = st["scan_ms"], st["steps"]
@@ -270,29 +276,64 @@ def main():
             "root_scan": {"rows": n, "ms": root_ms, "GBps": n * d * 4 / (root_ms * 1e-3) / 1e9, "frac": n * d * 4 / (root_ms * 1e-3) / 1e9 / hbm},
             "share_of_step": scan_ms / (st["build_ms"] if st["build_ms"] else 1.0),
         }
-    # ---- e2e: the call a user makes, host buffers in, tree nodes out -------------------------------
+    # ---- e2e: through the C ABI with HOST buffers (what a fork of the Rust crate would call) -----------
+    # items = raw stored Leaf values [0x00][header][d x f32] at unaligned host addresses, exactly
+    # what LMDB hands to ImmutableLeafs::new; nodes come back through the thread-safe arena sink
+    # (the TmpNodes stand-in). Timed: decode + H2D + device build + D2H + NodeCodec encoding.
     if rank == 0 and not args.no_e2e and world == 1:
         host = items.cpu().numpy()
-        env = ab.Env(local_rank)
-        env._ctx = ctx
-        w = ab.Writer(env, 0, d, metric)
-        w.add_items(ids, host)  # Writer::add_item x n (untimed: the reference's build timing starts at build())
-        e_times, h2d, d2h = [], 0, 0
-        for step in range(max(1, min(args.warmup, 2)) + args.steps):
-            w.add_item(0, host[0])  # mark the index dirty so build() rebuilds the forest
+        ctx.stage_items_device(metric, ids, d, items.data_ptr())
+        if metric == "dot-product":
+            ctx.dot_preprocess()
+        h0, h1 = ctx.item_headers()          # D::new_header / preprocess result, as stored by the writer
+        hf = 2 if metric == "dot-product" else 1
+        stride = 1 + 4 * hf + 4 * d           # odd => every value is byte aligned only
+        blob = np.zeros(n * stride, dtype=np.uint8)
+        b2 = blob.reshape(n, stride)
+        b2[:, 1:5] = h0.view(np.uint8).reshape(n, 4)
+        if hf == 2:
+            b2[:, 5:9] = h1.view(np.uint8).reshape(n, 4)
+        b2[:, 1 + 4 * hf:] = host.view(np.uint8).reshape(n, 4 * d)
+        ptrs = (blob.ctypes.data + np.arange(n, dtype=np.uint64) * np.uint64(stride)).astype(np.uint64)
+        arena = ab.Arena()
+        e_times, h2d, d2h, bd = [], 0, 0, None
+        n_warm = max(1, min(args.warmup, 2))
+        for step in range(n_warm + args.steps):
+            arena.clear()
             cc0 = ctx.counters()
             t0 = time.perf_counter()
-            w.builder(ab.StdRng.from_seed(SEED)).n_trees(T).build()
+            ctx.stage_items_ptrs(metric, d, ids, ptrs)
+            ctx.build_trees_into_arena(arena, seeds, list(range(T)), T)
             dt = time.perf_counter() - t0
             cc1 = ctx.counters()
-            if step >= max(1, min(args.warmup, 2)):
+            if step >= n_warm:
                 e_times.append(dt)
                 h2d, d2h = cc1["h2d_bytes"] - cc0["h2d_bytes"], cc1["d2h_bytes"] - cc0["d2h_bytes"]
+                bd = ctx.build_breakdown()
         e_sec = sum(e_times) / len(e_times)
+        n_nodes, node_bytes = arena.stats()
         line["e2e"] = {"value": n / e_sec, "unit": "vectors/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e_sec * 1e3,
-                       "api": "Writer.builder(rng).n_trees(T).build() over host leaf values", "breakdown_ms": w.build_timings()}
-        env._ctx = None
-        del w, env, host
+                       "api": "arroy_b200_stage_items(leaf value pointers) + arroy_b200_build_trees(arena sink)", "nodes": int(n_nodes), "node_bytes": int(node_bytes),
+                       "build_breakdown_ms": bd}
+        del arena, blob, b2, ptrs
+        # the same through the host mirror's Writer (adds the in-memory key/value table standing in for LMDB)
+        if not args.no_writer_e2e:
+            env = ab.Env(local_rank)
+            env._ctx = ctx
+            w = ab.Writer(env, 0, d, metric)
+            w.add_items(ids, host)
+            w_times = []
+            for step in range(1 + max(1, args.steps - 1)):
+                w.add_item(0, host[0])  # mark the index dirty so build() rebuilds the forest
+                t0 = time.perf_counter()
+                w.builder(ab.StdRng.from_seed(SEED)).n_trees(T).build()
+                if step >= 1:
+                    w_times.append(time.perf_counter() - t0)
+            ws = sum(w_times) / len(w_times)
+            line["e2e_writer"] = {"value": n / ws, "unit": "vectors/s", "ms_per_step": ws * 1e3, "api": "Writer.builder(rng).n_trees(T).build()", "breakdown_ms": w.build_timings()}
+            env._ctx = None
+            del w, env
+        del host
     elif rank == 0:
         line["e2e"] = None
     # ---- CPU baseline (oracle port) on a bounded sample, rank 0, N=1 only --------------------------------

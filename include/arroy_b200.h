@@ -115,7 +115,10 @@ int32_t arroy_b200_create_split(arroy_ctx* ctx, const uint32_t rng_key[8], uint6
 
 /* Called once per produced tree node, in no particular order, with the exact bytes
  * NodeCodec::bytes_encode would produce (src/node.rs:229-241) — what TmpNodes::put
- * receives in the reference (src/parallel.rs:130-147). Return non-zero to abort. */
+ * receives in the reference (src/parallel.rs:130-147). Like TmpNodes::put, which every rayon
+ * worker calls on its own thread-local file, the sink may be called CONCURRENTLY from several
+ * host threads (never twice for the same node id); it must be thread-safe. Return non-zero to
+ * abort the build. */
 typedef int32_t (*arroy_b200_node_sink)(void* arg, uint32_t node_id, const uint8_t* bytes, uint64_t len);
 /* Polled between device steps; non-zero cancels (BuildOption::cancel, src/writer.rs:116-124). */
 typedef int32_t (*arroy_b200_cancel_fn)(void* arg);
@@ -133,6 +136,19 @@ int32_t arroy_b200_build_trees(arroy_ctx* ctx, uint32_t n_trees, const uint8_t (
                                arroy_b200_cancel_fn cancel, void* cancel_arg,
                                arroy_b200_node_sink sink, void* sink_arg,
                                uint64_t* out_n_nodes);
+
+/* The same build in two phases, for forests sharded over several GPUs / processes (trees are
+ * independent given the item matrix and their seed, src/writer.rs:795): every rank calls _begin
+ * for ITS trees (the device work; out_node_counts[t] = number of nodes of local tree t, root
+ * included), the ranks exchange the counts and derive the id bases, then _emit encodes the nodes:
+ * non-root node number li (post-order) of local tree t gets id base_ids[t] + li, its root gets
+ * root_ids[t]. With base_ids following the last-tree-first rule the union of all ranks' nodes is
+ * byte-identical to a single arroy_b200_build_trees call over all trees. */
+int32_t arroy_b200_build_trees_begin(arroy_ctx* ctx, uint32_t n_trees, const uint8_t (*tree_seeds)[32],
+                                     uint32_t split_after, arroy_b200_cancel_fn cancel, void* cancel_arg,
+                                     uint32_t* out_node_counts /* n_trees */);
+int32_t arroy_b200_build_trees_emit(arroy_ctx* ctx, const uint32_t* root_ids, const uint64_t* base_ids,
+                                    arroy_b200_node_sink sink, void* sink_arg);
 
 /* Statistics of the last build on this context (for roofline accounting):
  * stats[0] = rows that went through side() (sum over scans, retries included)
@@ -172,6 +188,18 @@ int32_t arroy_b200_synth_device(arroy_ctx* ctx, const uint8_t seed[32], uint32_t
 int32_t arroy_b200_time_scan(arroy_ctx* ctx, const float* normal, float hdr0, float hdr1,
                              const uint32_t* rows, uint64_t n_rows, int32_t variant, int32_t iters,
                              int32_t flush_l2, float* out_ms_avg, uint64_t* out_left_count);
+
+/* A ready-made thread-safe node sink: an append-only arena, the in-memory counterpart of the
+ * reference's per-thread TmpNodes files (src/parallel.rs:22-147). Pass arroy_b200_arena_sink
+ * as `sink` and the arena as `sink_arg`. */
+typedef struct arroy_b200_arena arroy_b200_arena;
+arroy_b200_arena* arroy_b200_arena_new(void);
+void arroy_b200_arena_free(arroy_b200_arena* arena);
+void arroy_b200_arena_clear(arroy_b200_arena* arena);
+int32_t arroy_b200_arena_sink(void* arena, uint32_t node_id, const uint8_t* bytes, uint64_t len);
+/* returns the number of nodes held; *out_total_bytes = sum of their lengths */
+uint64_t arroy_b200_arena_stats(arroy_b200_arena* arena, uint64_t* out_total_bytes);
+int32_t arroy_b200_arena_get(arroy_b200_arena* arena, uint32_t node_id, const uint8_t** out_bytes, uint64_t* out_len);
 
 /* Host-side wall-clock breakdown of the last build (ms): [0] buffer setup + tree init,
  * [1] CUDA graph capture + instantiate, [2] device step loop, [3] finalize + device->host copies,
