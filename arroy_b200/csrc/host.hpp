@@ -741,6 +741,8 @@ int32_t arroy_reader_nns_batch_by_item(arroy_reader* r, uint32_t nq, const uint3
         for (uint32_t i = 0; i < nq; ++i) memcpy(flat.data() + offs[i], rows[i].data(), 4 * rows[i].size());
         const uint32_t k = (uint32_t)count;
         std::vector<uint32_t> orow((size_t)nq * std::max<uint32_t>(k, 1));
+        const bool trace = getenv("ARROY_B200_TRACE") != nullptr;
+        if (trace) fprintf(stderr, "[trace] nns_batch: %u queries, %llu candidates, flatten %.2f ms\n", nq, (unsigned long long)offs[nq], ms_since(t0));
         for (uint32_t base = 0; base < nq; base += 32768) {
             uint32_t m = std::min<uint32_t>(32768, nq - base);
             std::vector<uint64_t> lo(m + 1);
@@ -748,6 +750,7 @@ int32_t arroy_reader_nns_batch_by_item(arroy_reader* r, uint32_t nq, const uint3
             dev_ck(r->ctx, arroy_b200_rerank_batch(r->ctx, m, &q[(size_t)base * d], &qh0[base], &qh1[base], flat.data() + offs[base], lo.data(), k,
                                                    orow.data() + (size_t)base * k, out_dist + (size_t)base * k, out_len + base));
         }
+        if (trace) fprintf(stderr, "[trace] nns_batch: device re-rank done at %.2f ms\n", ms_since(t0));
         for (uint32_t i = 0; i < nq; ++i) for (uint32_t j = 0; j < out_len[i]; ++j) out_ids[(size_t)i * k + j] = r->items[orow[(size_t)i * k + j]];
         if (out_ms) out_ms[1] = ms_since(t0);
     });

@@ -158,6 +158,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-writer-e2e", action="store_true")
+    ap.add_argument("--no-query", action="store_true")
+    ap.add_argument("--queries", type=int, default=1000)
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
@@ -266,12 +268,21 @@ def main():
         scan_ms, steps_dev = st["scan_ms"], st["steps"]
         alg_bytes = st["scanned_rows"] * d * 4
         achieved = alg_bytes / (scan_ms * 1e-3) / 1e9 if scan_ms > 0 else 0.0
+        # DRAM traffic per launch: ratio dram/algorithmic of the committed ncu --set full capture of this
+        # kernel, applied to this run's average algorithmic bytes per launch
+        traffic, traffic_note = None, "no ncu capture committed"
+        tp = os.path.join(ROOT, "profiles", "r01_work_kernel_traffic.json")
+        if os.path.exists(tp):
+            tj = json.load(open(tp))
+            ratio = (tj["dram_bytes_read"] + tj["dram_bytes_write"]) / tj["algorithmic_bytes"]
+            traffic = ratio * alg_bytes / max(steps_dev, 1)
+            traffic_note = "avg algorithmic bytes/launch x %.4f (dram/algorithmic of %s)" % (ratio, tj["source"])
         r = np.random.default_rng(0)
         normal = (r.standard_normal(d) / np.sqrt(d)).astype(np.float32)
         root_ms, _ = ctx.time_scan(normal, (0.0, 0.0), n, iters=5, flush_l2=True)
         line["roofline"] = {
             "bound": "hbm", "kernel": "work_kernel (side()/margin scan + id partition)", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-            "peak_source": which, "traffic": None,
+            "peak_source": which, "traffic": traffic, "traffic_note": traffic_note,
             "per_launch": {"launches": steps_dev, "avg_ms": scan_ms / max(steps_dev, 1), "avg_algorithmic_GB": alg_bytes / max(steps_dev, 1) / 1e9},
             "root_scan": {"rows": n, "ms": root_ms, "GBps": n * d * 4 / (root_ms * 1e-3) / 1e9, "frac": n * d * 4 / (root_ms * 1e-3) / 1e9 / hbm},
             "share_of_step": scan_ms / (st["build_ms"] if st["build_ms"] else 1.0),
@@ -331,6 +342,35 @@ def main():
                     w_times.append(time.perf_counter() - t0)
             ws = sum(w_times) / len(w_times)
             line["e2e_writer"] = {"value": n / ws, "unit": "vectors/s", "ms_per_step": ws * 1e3, "api": "Writer.builder(rng).n_trees(T).build()", "breakdown_ms": w.build_timings()}
+            if not args.no_query:
+                # QPS @ recall: by_item queries for items 0..Q-1, top-100, default search_k
+                Q, k = args.queries, 100
+                reader = ab.Reader.open(env, 0, metric)
+                qitems = np.arange(Q, dtype=np.uint32)
+                reader.nns_batch_by_item(qitems, k)  # warm-up (stages the items, sizes the scratch buffers)
+                q_times = []
+                for _ in range(3):
+                    t0 = time.perf_counter()
+                    out_ids, out_dist, out_len, qms = reader.nns_batch_by_item(qitems, k)
+                    q_times.append(time.perf_counter() - t0)
+                q_sec = min(q_times)
+                t0 = time.perf_counter()
+                single = [reader.nns(k).by_item(int(i)) for i in qitems[:50]]
+                one_sec = (time.perf_counter() - t0) / 50
+                assert all([s[0] for s in single[i]] == out_ids[i, :out_len[i]].tolist() for i in range(50))
+                # exact ground truth: the same distance over ALL rows (brute force on the device)
+                allrows = np.arange(n, dtype=np.uint32)
+                hits = 0
+                QG = min(Q, 100)
+                h0q, _ = ctx.item_headers()
+                offs = (np.arange(QG + 1, dtype=np.uint64) * np.uint64(n))
+                g_rows, _, g_len = ctx.rerank_batch(host[:QG], h0q[:QG], np.tile(allrows, QG), offs, k)
+                for i in range(QG):
+                    hits += len(set(g_rows[i, :g_len[i]].tolist()) & set(out_ids[i, :out_len[i]].tolist()))
+                line["query"] = {"qps_batched": Q / q_sec, "queries": Q, "k": k, "search_k": k * T, "recall_at_100": hits / (QG * k), "recall_queries": QG,
+                                 "tree_walk_ms": qms["tree_walk_ms"], "rerank_ms": qms["rerank_ms"], "qps_one_at_a_time": 1.0 / one_sec,
+                                 "api": "Reader.nns(100).by_item / nns_batch_by_item (host tree walk on %d threads + device re-rank)" % (os.cpu_count() or 1)}
+                del reader
             env._ctx = None
             del w, env
         del host

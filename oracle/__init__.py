@@ -76,6 +76,7 @@ def lib():
     sig("oracle_db_del_item", i32, vp, u32)
     sig("oracle_db_set_items", None, vp, u64, _u32p, _f32p)
     sig("oracle_db_build", i32, vp, vp, i64, u64, i32)
+    sig("oracle_db_build_memory_limited", i32, vp, vp, i64, u64, u64)
     sig("oracle_db_n_nodes", u64, vp)
     sig("oracle_db_n_roots", u64, vp)
     sig("oracle_db_roots", None, vp, _u32p)
@@ -270,6 +271,12 @@ class Db:
 
     def build(self, rng, n_trees=None, split_after=None, threads=1):
         rc = lib().oracle_db_build(self.h, rng.h, -1 if n_trees is None else n_trees, split_after or 0, threads)
+        if rc != 0:
+            raise RuntimeError("oracle build failed")
+
+    def build_memory_limited(self, rng, n_trees=None, split_after=None, available_memory=0):
+        """Writer::build with available_memory set, on a 1-thread rayon pool (golden pinning only)."""
+        rc = lib().oracle_db_build_memory_limited(self.h, rng.h, -1 if n_trees is None else n_trees, split_after or 0, available_memory)
         if rc != 0:
             raise RuntimeError("oracle build failed")
 

@@ -272,6 +272,173 @@ struct Db {
         built = true;
     }
 
+    // ---------------------------------------------------------------------------------------------
+    // Memory-limited build (available_memory set) on a 1-thread rayon pool — restated only to pin the
+    // oracle against the reference's `..._with_little_memory.snap` (src/tests/writer.rs:1377-1391),
+    // the one golden that exercises Cosine two_means / create_split / margin:
+    //   src/writer.rs:660-739    incremental_index_large_descendant
+    //   src/writer.rs:744-844    insert_descendants_in_file_and_spawn_tasks
+    //   src/writer.rs:1463-1531  insert_items_in_descendants_from_tmpfile
+    //   src/writer.rs:1536-1584  fit_in_memory
+    // plus the third-party behaviour the node ids depend on: hashbrown (via
+    // nohash::IntMap) insertion / growth / iteration order, rayon's LIFO order of scope.spawn.
+    struct IntMapEmu {  // std HashMap<u32, _, BuildNoHashHasher>: identity hash, SwissTable slots
+        std::vector<int64_t> keys;               // -1 = empty
+        std::vector<std::vector<uint32_t>> vals;
+        size_t items = 0;
+        static size_t capacity_of(size_t buckets) { return buckets < 8 ? buckets - 1 : buckets / 8 * 7; }
+        size_t find(uint32_t k) const {
+            if (keys.empty()) return SIZE_MAX;
+            size_t mask = keys.size() - 1, pos = k & mask;
+            for (size_t i = 0; i < keys.size(); ++i) { size_t b = (pos + i) & mask; if (keys[b] == (int64_t)k) return b; if (keys[b] < 0) return SIZE_MAX; }
+            return SIZE_MAX;
+        }
+        void raw_insert(uint32_t k, std::vector<uint32_t>&& v) {
+            size_t mask = keys.size() - 1, pos = k & mask;
+            for (size_t i = 0;; ++i) { size_t b = (pos + i) & mask; if (keys[b] < 0) { keys[b] = k; vals[b] = std::move(v); return; } }
+        }
+        std::vector<uint32_t>& entry(uint32_t k) {  // insert-or-get
+            size_t f = find(k);
+            if (f != SIZE_MAX) return vals[f];
+            if (keys.empty() || items == capacity_of(keys.size())) {  // reserve_rehash(1)
+                size_t cap = std::max(items + 1, keys.empty() ? (size_t)0 : capacity_of(keys.size()) + 1);
+                size_t nb = cap < 4 ? 4 : (cap < 8 ? 8 : 1);
+                if (nb == 1) { size_t adj = cap * 8 / 7; nb = 1; while (nb < adj) nb <<= 1; }
+                std::vector<int64_t> ok = std::move(keys);
+                std::vector<std::vector<uint32_t>> ov = std::move(vals);
+                keys.assign(nb, -1); vals.assign(nb, {});
+                for (size_t b = 0; b < ok.size(); ++b) if (ok[b] >= 0) raw_insert((uint32_t)ok[b], std::move(ov[b]));
+            }
+            raw_insert(k, {});
+            ++items;
+            return vals[find(k)];
+        }
+    };
+
+    struct LmTask { StdRng rng; uint32_t id; std::vector<uint32_t> rows; };
+    struct LmState {
+        size_t K = 0, memory = 0;
+        uint32_t counter = 0;
+        std::map<uint32_t, TreeNode> out;                 // final nodes (by id), rows still as row indices
+        std::map<uint32_t, LocalNode> tmp_splits;         // the (single) thread's TmpNodes file: split nodes
+        std::vector<LmTask> stack;                         // rayon local deque, popped LIFO
+    };
+
+    // fit_in_memory — writer.rs:1536-1584 (page_size = 4096)
+    bool lm_fit_in_memory(LmState& S, std::vector<uint32_t>& to_insert, StdRng& rng, std::vector<uint32_t>& out) {
+        out.clear();
+        if (to_insert.empty()) return false;
+        if (to_insert.size() <= d) { out.swap(to_insert); return true; }
+        const size_t page_size = 4096;
+        size_t nb_page_allowed = (size_t)std::floor((double)S.memory / (double)page_size);
+        size_t largest_item_size = 4 * (size_t)header_floats(metric) + 4 * d;   // D::size_of_item
+        size_t nb_items_per_page = page_size / largest_item_size;
+        size_t nb_page_per_item = (size_t)std::ceil((double)largest_item_size / (double)page_size);
+        size_t nb_items = nb_items_per_page > 1 ? nb_page_allowed * nb_items_per_page : (nb_page_per_item > 1 ? nb_page_allowed / nb_page_per_item : nb_page_allowed);
+        if (nb_items <= d) nb_items = d + 1;
+        if (nb_items >= to_insert.size()) { out.swap(to_insert); return true; }
+        for (size_t i = 0; i < nb_items; ++i) {
+            uint64_t idx = rng.gen_range_u64(0, to_insert.size());
+            uint32_t item = to_insert[idx];                  // RoaringBitmap::select(idx)
+            out.insert(std::lower_bound(out.begin(), out.end(), item), item);
+            to_insert.erase(to_insert.begin() + idx);
+        }
+        return true;
+    }
+
+    uint32_t lm_make_tree(LmState& S, StdRng& rng, const std::vector<uint32_t>& rows, IntMapEmu& descendants, int64_t next_id) {
+        if (rows.size() <= S.K) {
+            uint32_t id = next_id >= 0 ? (uint32_t)next_id : S.counter++;
+            descendants.entry(id) = rows;   // descendants.insert(item_id, item_indices.clone())
+            return id;
+        }
+        SubsetView children{rows.data(), (uint32_t)rows.size(), vec, h0_own.data(), h1_own.empty() ? nullptr : h1_own.data(), d};
+        std::vector<uint32_t> left, right;
+        int remaining_attempts = 3;
+        OwnedLeaf normal;
+        for (;;) {
+            left.clear(); right.clear();
+            create_split(metric, rng, children, normal);
+            Leaf nl = normal.view();
+            for (uint32_t r : rows) { if (side_is_right(margin(metric, nl, leaf(r), d))) right.push_back(r); else left.push_back(r); }
+            if (split_imbalance(left.size(), right.size()) < 0.95 || remaining_attempts == 0) break;
+            --remaining_attempts;
+        }
+        bool has_normal = true;
+        if (split_imbalance(left.size(), right.size()) > 0.99) {
+            left.clear(); right.clear();
+            for (uint32_t r : rows) { if (rng.gen_bool()) left.push_back(r); else right.push_back(r); }
+            has_normal = false;
+        }
+        uint32_t l = lm_make_tree(S, rng, left, descendants, -1);
+        uint32_t r = lm_make_tree(S, rng, right, descendants, -1);
+        uint32_t id = next_id >= 0 ? (uint32_t)next_id : S.counter++;
+        S.tmp_splits[id] = LocalNode{2, l, r, has_normal, has_normal ? normal : OwnedLeaf{}, {}};
+        return id;
+    }
+
+    // insert_items_in_descendants_from_tmpfile — writer.rs:1463-1531
+    void lm_route(LmState& S, StdRng& rng, uint32_t node, const std::vector<uint32_t>& to_insert, IntMapEmu& descendants) {
+        auto it = S.tmp_splits.find(node);
+        if (it == S.tmp_splits.end()) {   // tmp_nodes.get(..) == None: a pending descendants entry
+            std::vector<uint32_t>& dst = descendants.vals[descendants.find(node)];
+            std::vector<uint32_t> merged;
+            std::set_union(dst.begin(), dst.end(), to_insert.begin(), to_insert.end(), std::back_inserter(merged));
+            dst.swap(merged);
+            return;
+        }
+        const LocalNode& sp = it->second;
+        std::vector<uint32_t> left, right;
+        if (!sp.has_normal) { for (uint32_t r : to_insert) { if (rng.gen_bool()) left.push_back(r); else right.push_back(r); } }
+        else { Leaf nl = sp.normal.view(); for (uint32_t r : to_insert) { if (side_is_right(margin(metric, nl, leaf(r), d))) right.push_back(r); else left.push_back(r); } }
+        const uint32_t lid = sp.left, rid = sp.right;
+        if (!left.empty()) lm_route(S, rng, lid, left, descendants);
+        if (!right.empty()) lm_route(S, rng, rid, right, descendants);
+    }
+
+    // insert_descendants_in_file_and_spawn_tasks — writer.rs:744-844
+    void lm_process_descendants(LmState& S, StdRng& rng, IntMapEmu& descendants) {
+        for (size_t b = 0; b < descendants.keys.size(); ++b) {   // hashbrown iteration: ascending bucket
+            if (descendants.keys[b] < 0) continue;
+            uint32_t id = (uint32_t)descendants.keys[b];
+            std::vector<uint32_t>& rows = descendants.vals[b];
+            if (rows.size() <= S.K) { TreeNode t; t.kind = 1; t.descendants = rows; S.out[id] = std::move(t); }
+            else { LmTask task{rng.fork(), id, rows}; S.stack.push_back(std::move(task)); }
+        }
+    }
+
+    // incremental_index_large_descendant — writer.rs:660-739
+    void lm_run_task(LmState& S, LmTask& task) {
+        IntMapEmu descendants;
+        std::vector<uint32_t> to_insert = task.rows, chunk;
+        lm_fit_in_memory(S, to_insert, task.rng, chunk);
+        lm_make_tree(S, task.rng, chunk, descendants, (int64_t)task.id);
+        while (lm_fit_in_memory(S, to_insert, task.rng, chunk)) lm_route(S, task.rng, task.id, chunk, descendants);
+        lm_process_descendants(S, task.rng, descendants);
+    }
+
+    void build_memory_limited(StdRng& user_rng, int64_t n_trees_opt, size_t split_after, size_t available_memory) {
+        freeze();
+        preprocess();
+        nodes.clear(); roots.clear(); scanned_rows = 0;
+        LmState S;
+        S.K = split_after ? split_after : d;
+        S.memory = available_memory;   // / current_num_threads() == 1
+        if (n <= S.K) throw std::runtime_error("single-leaf case: use build()");
+        uint64_t T = target_n_trees(n_trees_opt, d, n, 0);
+        IntMapEmu top;
+        std::vector<uint32_t> all(n);
+        for (size_t r = 0; r < n; ++r) all[r] = (uint32_t)r;
+        for (uint64_t t = 0; t < T; ++t) { roots.push_back(S.counter); top.entry(S.counter++) = all; }   // writer.rs:556-561
+        StdRng rng1 = user_rng.fork();                                                                        // writer.rs:575
+        lm_process_descendants(S, rng1, top);
+        while (!S.stack.empty()) { LmTask t = std::move(S.stack.back()); S.stack.pop_back(); lm_run_task(S, t); }
+        nodes.resize(S.counter);
+        for (auto& kv : S.out) { TreeNode& o = nodes[kv.first]; o.kind = 1; o.descendants.resize(kv.second.descendants.size()); for (size_t i = 0; i < o.descendants.size(); ++i) o.descendants[i] = ids[kv.second.descendants[i]]; }
+        for (auto& kv : S.tmp_splits) { TreeNode& o = nodes[kv.first]; o.kind = 2; o.left = kv.second.left; o.right = kv.second.right; o.has_normal = kv.second.has_normal; o.normal = kv.second.normal; }
+        built = true;
+    }
+
     // Total order of (OrderedFloat<f32>, u32): NaN greatest & all NaN equal, -0 == +0.
     static bool less_key(float a, uint32_t ia, float b, uint32_t ib) {
         bool an = a != a, bn = b != b;

@@ -117,6 +117,9 @@ void oracle_db_set_items(void* db, uint64_t n, const uint32_t* ids, const float*
 int oracle_db_build(void* db, void* rng, int64_t n_trees_opt, uint64_t split_after, int n_threads) {
     try { static_cast<Db*>(db)->build(*static_cast<StdRng*>(rng), n_trees_opt, split_after, n_threads); return 0; } catch (...) { return -1; }
 }
+int oracle_db_build_memory_limited(void* db, void* rng, int64_t n_trees_opt, uint64_t split_after, uint64_t available_memory) {
+    try { static_cast<Db*>(db)->build_memory_limited(*static_cast<StdRng*>(rng), n_trees_opt, split_after, available_memory); return 0; } catch (...) { return -1; }
+}
 uint64_t oracle_db_n_nodes(void* db) { return static_cast<Db*>(db)->nodes.size(); }
 uint64_t oracle_db_n_roots(void* db) { return static_cast<Db*>(db)->roots.size(); }
 void oracle_db_roots(void* db, uint32_t* out) { auto* D = static_cast<Db*>(db); memcpy(out, D->roots.data(), 4 * D->roots.size()); }

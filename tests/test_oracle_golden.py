@@ -83,6 +83,23 @@ def test_lot_of_random_points_all_92_nodes():
     check_dump(gold, db.nodes(), db.roots, oracle.EUCLIDEAN, 30, oracle.decode_node)
 
 
+def test_little_memory_cosine_all_188_nodes():
+    # golden 6: 100 x 3 Cosine, available_memory(0), 2 trees (src/tests/writer.rs:1377-1391). Pins
+    # Cosine two_means / create_split / margin, fit_in_memory's u64 gen_range, the tmp-file routing
+    # scan, hashbrown iteration order and rayon's LIFO task order.
+    gold = G["little_memory"]
+    assert gold["distance"] == "cosine" and len(gold["tree"]) == 188
+    rng = rng42()
+    data = rng.fill_f32(100 * 3).reshape(100, 3)
+    db = oracle.Db("cosine", 3)
+    for i in range(100):
+        db.add_item(i, data[i])
+    db.build_memory_limited(rng, n_trees=2, available_memory=0)
+    check_dump(gold, db.nodes(), db.roots, oracle.COSINE, 3, oracle.decode_node)
+    for key, it in gold["items"].items():   # stored Cosine headers (norm) as printed by the snapshot
+        assert fmt4(db.item_header(int(key))[0]) == it["header"]["norm"]
+
+
 def test_target_n_trees_table():
     for n_items, dims, want in G["target_n_trees"]:
         assert oracle.target_n_trees(None, dims, n_items) == want, (n_items, dims)
