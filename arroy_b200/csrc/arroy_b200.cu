@@ -17,6 +17,7 @@
 
 #include "../../include/arroy_b200.h"
 #include "build.cuh"
+#include "search.cuh"
 
 using namespace ab;
 
@@ -110,6 +111,12 @@ struct arroy_ctx {
     uint64_t n_launches = 0, h2d_bytes = 0, d2h_bytes = 0;  // since create (arroy_b200_counters)
     cudaEvent_t tev0 = nullptr, tev1 = nullptr;
     std::vector<StageWorker> stage_workers;
+    // device-resident forest for the batched query path (arroy_b200_load_forest)
+    DevBuf f_kind, f_left, f_right, f_nidx, f_nh0, f_doff, f_dlen, f_normals, f_desc, f_roots;
+    DevForest forest{};
+    bool forest_loaded = false;
+    uint32_t forest_max_desc = 0;
+    DevBuf w_heaps, w_cand, w_cand2, w_count, w_bitmap, w_status, w_beg, w_end, w_qrows, w_tmp;
     // results of the last build_trees_begin, waiting for build_trees_emit
     std::vector<std::vector<struct BuiltTreeView>> pending_waves;
     std::vector<uint32_t> pending_wave_t0;
@@ -716,11 +723,11 @@ void do_rerank_batch(arroy_ctx* c, uint32_t nq, const float* queries, const floa
         uint64_t warps = (max_c + per - 1) / per;
         uint32_t gx = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((warps + 7) / 8, std::max<uint64_t>(1, ((uint64_t)c->sm_count * 8) / std::min<uint32_t>(nq, c->sm_count * 8u))));
         dim3 grid(gx, nq);
-        distance_kernel<<<grid, 256, 0, c->stream>>>(c->items.as<float>(), c->h0.as<float>(), c->dim, ld, c->metric, c->s_q.as<float>(), c->s_qh0.as<float>(), nq,
-                                                     c->s_rows.as<uint32_t>(), c->s_off.as<uint64_t>(), c->s_dists.as<float>(), c->s_keys.as<unsigned long long>());
+        distance_kernel<<<grid, 256, 0, c->stream>>>(c->items.as<float>(), c->h0.as<float>(), c->dim, ld, c->metric, c->s_q.as<float>(), nullptr, c->s_qh0.as<float>(), nq,
+                                                     c->s_rows.as<uint32_t>(), c->s_off.as<uint64_t>(), c->s_off.as<uint64_t>() + 1, c->s_dists.as<float>(), c->s_keys.as<unsigned long long>());
         CK(cudaGetLastError());
     }
-    topk_kernel<<<nq, TOPK_THREADS, 0, c->stream>>>(c->s_keys.as<unsigned long long>(), c->s_dists.as<float>(), c->s_rows.as<uint32_t>(), c->s_off.as<uint64_t>(), k, c->metric,
+    topk_kernel<<<nq, TOPK_THREADS, 0, c->stream>>>(c->s_keys.as<unsigned long long>(), c->s_dists.as<float>(), c->s_rows.as<uint32_t>(), c->s_off.as<uint64_t>(), c->s_off.as<uint64_t>() + 1, k, c->metric,
                                                     c->s_orows.as<uint32_t>(), c->s_odist.as<float>(), c->s_olen.as<uint32_t>());
     CK(cudaGetLastError());
     c->n_launches += total ? 2 : 1;
@@ -809,6 +816,9 @@ void arroy_b200_destroy(arroy_ctx* c) {
     if (c->cached_exec) cudaGraphExecDestroy(c->cached_exec);
     if (c->cached_graph) cudaGraphDestroy(c->cached_graph);
     for (auto& sw : c->stage_workers) { sw.pin[0].release(); sw.pin[1].release(); if (sw.ev[0]) cudaEventDestroy(sw.ev[0]); if (sw.ev[1]) cudaEventDestroy(sw.ev[1]); if (sw.st) cudaStreamDestroy(sw.st); }
+    { DevBuf* fb[] = {&c->f_kind, &c->f_left, &c->f_right, &c->f_nidx, &c->f_nh0, &c->f_doff, &c->f_dlen, &c->f_normals, &c->f_desc, &c->f_roots,
+                      &c->w_heaps, &c->w_cand, &c->w_cand2, &c->w_count, &c->w_bitmap, &c->w_status, &c->w_beg, &c->w_end, &c->w_qrows, &c->w_tmp};
+      for (auto* b : fb) b->release(); }
     c->pin.release();
     c->wave.release();
     for (auto& hw : c->host_waves) hw.release();
@@ -998,6 +1008,120 @@ int32_t arroy_b200_rerank_batch(arroy_ctx* c, uint32_t nq, const float* queries,
     return guarded(c, [&] {
         if (nq && (!queries || !row_offsets || !out_len)) throw ArgError("null argument");
         do_rerank_batch(c, nq, queries, qhdr0, qhdr1, rows, row_offsets, k, out_rows, out_dist, out_len);
+    });
+}
+
+int32_t arroy_b200_load_forest(arroy_ctx* c, uint32_t n_nodes, const uint8_t* kind, const uint32_t* left, const uint32_t* right,
+                               const uint32_t* normal_idx, const float* normal_hdr0, const uint32_t* desc_off, const uint32_t* desc_len,
+                               uint32_t n_normals, const float* normals, uint64_t n_desc, const uint32_t* desc_rows,
+                               uint32_t n_roots, const uint32_t* roots) {
+    return guarded(c, [&] {
+        require_staged(c); set_device(c);
+        c->forest_loaded = false;
+        if (n_nodes && (!kind || !left || !right || !normal_idx || !normal_hdr0 || !desc_off || !desc_len)) throw ArgError("null node arrays");
+        if (n_roots && !roots) throw ArgError("null roots");
+        uint32_t max_desc = 0;
+        for (uint32_t i = 0; i < n_nodes; ++i) {
+            if (kind[i] == 1) { if ((uint64_t)desc_off[i] + desc_len[i] > n_desc) throw ArgError("descendants out of range"); max_desc = std::max(max_desc, desc_len[i]); }
+            else if (kind[i] == 2) { if (left[i] >= n_nodes || right[i] >= n_nodes) throw ArgError("child id out of range"); if (normal_idx[i] != 0xffffffffu && normal_idx[i] >= n_normals) throw ArgError("normal index out of range"); }
+        }
+        for (uint64_t i = 0; i < n_desc; ++i) if (desc_rows[i] >= c->n) throw ArgError("descendant row out of range");
+        for (uint32_t i = 0; i < n_roots; ++i) if (roots[i] >= n_nodes) throw ArgError("root id out of range");
+        const uint32_t ld = c->ld;
+        auto up = [&](DevBuf& b, const void* src, size_t bytes) { b.ensure(std::max<size_t>(16, bytes)); if (bytes) CK(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, c->stream)); };
+        up(c->f_kind, kind, n_nodes); up(c->f_left, left, 4ull * n_nodes); up(c->f_right, right, 4ull * n_nodes); up(c->f_nidx, normal_idx, 4ull * n_nodes);
+        up(c->f_nh0, normal_hdr0, 4ull * n_nodes); up(c->f_doff, desc_off, 4ull * n_nodes); up(c->f_dlen, desc_len, 4ull * n_nodes);
+        up(c->f_desc, desc_rows, 4ull * n_desc); up(c->f_roots, roots, 4ull * n_roots);
+        c->f_normals.ensure(std::max<size_t>(16, (size_t)n_normals * ld * 4));
+        if (n_normals) {
+            if (ld != c->dim) CK(cudaMemsetAsync(c->f_normals.p, 0, (size_t)n_normals * ld * 4, c->stream));
+            CK(cudaMemcpy2DAsync(c->f_normals.p, (size_t)ld * 4, normals, (size_t)c->dim * 4, (size_t)c->dim * 4, n_normals, cudaMemcpyHostToDevice, c->stream));
+        }
+        CK(cudaStreamSynchronize(c->stream));
+        c->h2d_bytes += 25ull * n_nodes + 4ull * n_desc + (uint64_t)n_normals * c->dim * 4;
+        DevForest F{};
+        F.kind = c->f_kind.as<uint8_t>(); F.left = c->f_left.as<uint32_t>(); F.right = c->f_right.as<uint32_t>(); F.normal_idx = c->f_nidx.as<uint32_t>();
+        F.nh0 = c->f_nh0.as<float>(); F.desc_off = c->f_doff.as<uint32_t>(); F.desc_len = c->f_dlen.as<uint32_t>(); F.normals = c->f_normals.as<float>();
+        F.desc_rows = c->f_desc.as<uint32_t>(); F.roots = c->f_roots.as<uint32_t>(); F.n_roots = n_roots; F.n_nodes = n_nodes;
+        c->forest = F; c->forest_max_desc = max_desc; c->forest_loaded = true;
+    });
+}
+
+int32_t arroy_b200_search_batch(arroy_ctx* c, uint32_t nq, const uint32_t* query_rows, const float* queries, const float* qhdr0,
+                                uint64_t count, uint64_t search_k, uint32_t* out_rows, float* out_dist, uint32_t* out_len, int32_t* out_status) {
+    return guarded(c, [&] {
+        require_staged(c); set_device(c);
+        if (!c->forest_loaded) throw NotStaged("no forest loaded on this context (arroy_b200_load_forest)");
+        if (nq == 0) return;
+        if ((!query_rows && !queries) || !out_rows || !out_dist || !out_len) throw ArgError("null argument");
+        if (count == 0) { for (uint32_t q = 0; q < nq; ++q) { out_len[q] = 0; if (out_status) out_status[q] = 0; } return; }
+        if (count > TOPK_CAP / 2) throw ArgError("count larger than the top-k buffer (TOPK_CAP/2 = 2048)");
+        if (query_rows) for (uint32_t q = 0; q < nq; ++q) if (query_rows[q] >= c->n) throw ArgError("query row out of range");
+        const uint32_t ld = c->ld, k = (uint32_t)count;
+        const DevForest& F = c->forest;
+        if (search_k == 0) search_k = count * F.n_roots;  // reader.rs:330
+        const uint64_t cand_cap64 = std::min<uint64_t>(c->n, search_k + c->forest_max_desc);
+        const uint64_t heap_cap64 = (uint64_t)F.n_roots + std::min<uint64_t>(F.n_nodes, 2 * std::min<uint64_t>(search_k, c->n) + 1024);
+        if (cand_cap64 > 0x7fffffffull || heap_cap64 > 0x7fffffffull) throw ArgError("search_k too large for the device walk");
+        const uint32_t cand_cap = (uint32_t)std::max<uint64_t>(cand_cap64, 1), heap_cap = (uint32_t)heap_cap64;
+        const uint32_t bm_words = (uint32_t)((c->n + 31) / 32);
+        // process the queries in chunks that keep the scratch memory bounded (~1 GiB)
+        const uint64_t per_q = 8ull * heap_cap + 8ull * cand_cap + 4ull * bm_words + 12ull * cand_cap + 64;
+        uint32_t chunk = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>({(uint64_t)nq, (1ull << 30) / per_q, 65535ull}));
+        for (uint32_t q0 = 0; q0 < nq; q0 += chunk) {
+            const uint32_t m = std::min(chunk, nq - q0);
+            c->w_heaps.ensure(8ull * heap_cap * m); c->w_cand.ensure(4ull * cand_cap * m); c->w_cand2.ensure(4ull * cand_cap * m);
+            c->w_count.ensure(4ull * m); c->w_bitmap.ensure(4ull * bm_words * m); c->w_status.ensure(4ull * m);
+            c->w_beg.ensure(8ull * (m + 1)); c->w_end.ensure(8ull * (m + 1));
+            c->s_keys.ensure(8ull * cand_cap * m); c->s_dists.ensure(4ull * cand_cap * m);
+            c->s_orows.ensure(4ull * m * k); c->s_odist.ensure(4ull * m * k); c->s_olen.ensure(4ull * m); c->s_qh0.ensure(4ull * m);
+            const uint32_t* d_qrows = nullptr;
+            const float* d_q = nullptr;
+            if (query_rows) {
+                c->w_qrows.ensure(4ull * m);
+                CK(cudaMemcpyAsync(c->w_qrows.p, query_rows + q0, 4ull * m, cudaMemcpyHostToDevice, c->stream));
+                d_qrows = c->w_qrows.as<uint32_t>();
+            } else {
+                c->s_q.ensure((size_t)m * ld * 4);
+                CK(cudaMemsetAsync(c->s_q.p, 0, (size_t)m * ld * 4, c->stream));
+                CK(cudaMemcpy2DAsync(c->s_q.p, (size_t)ld * 4, queries + (size_t)q0 * c->dim, (size_t)c->dim * 4, (size_t)c->dim * 4, m, cudaMemcpyHostToDevice, c->stream));
+                d_q = c->s_q.as<float>();
+            }
+            if (qhdr0) CK(cudaMemcpyAsync(c->s_qh0.p, qhdr0 + q0, 4ull * m, cudaMemcpyHostToDevice, c->stream));
+            else if (query_rows) {  // by_item: the stored header of the item
+                gather_f32_kernel<<<(m + 255) / 256, 256, 0, c->stream>>>(c->s_qh0.as<float>(), c->h0.as<float>(), d_qrows, m);
+                CK(cudaGetLastError());
+            } else CK(cudaMemsetAsync(c->s_qh0.p, 0, 4ull * m, c->stream));
+            CK(cudaMemsetAsync(c->w_bitmap.p, 0, 4ull * bm_words * m, c->stream));
+            walk_kernel<<<(m + WALK_WARPS - 1) / WALK_WARPS, WALK_WARPS * 32, 0, c->stream>>>(F, c->items.as<float>(), c->dim, ld, c->metric, m, d_qrows, d_q, c->s_qh0.as<float>(),
+                                                                                       search_k, c->w_heaps.as<unsigned long long>(), heap_cap, c->w_cand.as<uint32_t>(), cand_cap,
+                                                                                       c->w_count.as<uint32_t>(), c->w_bitmap.as<uint32_t>(), bm_words, c->w_status.as<int32_t>());
+            CK(cudaGetLastError());
+            walk_segments_kernel<<<(m + 256) / 256, 256, 0, c->stream>>>(c->w_count.as<uint32_t>(), m, cand_cap, c->w_beg.as<uint64_t>(), c->w_end.as<uint64_t>());
+            CK(cudaGetLastError());
+            // sort every query's unique candidates ascending (= ascending item ids): reader.rs:378
+            size_t tmp_bytes = 0;
+            CK(cub::DeviceSegmentedSort::SortKeys(nullptr, tmp_bytes, c->w_cand.as<uint32_t>(), c->w_cand2.as<uint32_t>(), (int64_t)cand_cap * m, (int64_t)m,
+                                                  c->w_beg.as<uint64_t>(), c->w_end.as<uint64_t>(), c->stream));
+            c->w_tmp.ensure(std::max<size_t>(tmp_bytes, 16));
+            CK(cub::DeviceSegmentedSort::SortKeys(c->w_tmp.p, tmp_bytes, c->w_cand.as<uint32_t>(), c->w_cand2.as<uint32_t>(), (int64_t)cand_cap * m, (int64_t)m,
+                                                  c->w_beg.as<uint64_t>(), c->w_end.as<uint64_t>(), c->stream));
+            uint64_t warps = ((uint64_t)cand_cap + 3) / 4;
+            uint32_t gx = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((warps + 7) / 8, std::max<uint64_t>(1, ((uint64_t)c->sm_count * 8) / std::min<uint32_t>(m, c->sm_count * 8u))));
+            distance_kernel<<<dim3(gx, m), 256, 0, c->stream>>>(c->items.as<float>(), c->h0.as<float>(), c->dim, ld, c->metric, d_q, d_qrows, c->s_qh0.as<float>(), m,
+                                                               c->w_cand2.as<uint32_t>(), c->w_beg.as<uint64_t>(), c->w_end.as<uint64_t>(), c->s_dists.as<float>(), c->s_keys.as<unsigned long long>());
+            CK(cudaGetLastError());
+            topk_kernel<<<m, TOPK_THREADS, 0, c->stream>>>(c->s_keys.as<unsigned long long>(), c->s_dists.as<float>(), c->w_cand2.as<uint32_t>(), c->w_beg.as<uint64_t>(), c->w_end.as<uint64_t>(), k, c->metric,
+                                                           c->s_orows.as<uint32_t>(), c->s_odist.as<float>(), c->s_olen.as<uint32_t>());
+            CK(cudaGetLastError());
+            c->n_launches += 5;
+            CK(cudaMemcpyAsync(out_rows + (size_t)q0 * k, c->s_orows.p, 4ull * m * k, cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaMemcpyAsync(out_dist + (size_t)q0 * k, c->s_odist.p, 4ull * m * k, cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaMemcpyAsync(out_len + q0, c->s_olen.p, 4ull * m, cudaMemcpyDeviceToHost, c->stream));
+            if (out_status) CK(cudaMemcpyAsync(out_status + q0, c->w_status.p, 4ull * m, cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaStreamSynchronize(c->stream));
+            c->d2h_bytes += 8ull * m * k + 8ull * m;
+        }
     });
 }
 

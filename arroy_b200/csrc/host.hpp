@@ -155,6 +155,7 @@ struct arroy_reader {
     std::vector<uint32_t> desc;     // concatenated descendant id lists
     std::vector<float> hdr0, hdr1;  // item headers (query by item)
     bool staged = false;
+    bool forest_on_device = false;
 };
 
 namespace arroy_host {
@@ -463,6 +464,38 @@ inline void ensure_staged(arroy_reader* r) {
     r->staged = true;
 }
 
+inline int64_t row_of(const arroy_reader* r, uint32_t item);
+
+// Upload the decoded forest for the batched device search (arroy_b200_load_forest); descendants
+// are converted from item ids to rows once.
+inline void ensure_forest(arroy_reader* r) {
+    if (r->forest_on_device) return;
+    ensure_staged(r);
+    const size_t nn = r->nodes.size();
+    std::vector<uint8_t> kind(nn);
+    std::vector<uint32_t> left(nn), right(nn), nidx(nn), doff(nn), dlen(nn);
+    std::vector<float> nh0(nn);
+    for (size_t i = 0; i < nn; ++i) {
+        const arroy_reader::Node& nd = r->nodes[i];
+        kind[i] = nd.kind; left[i] = nd.left; right[i] = nd.right; nidx[i] = nd.has_normal ? nd.normal_off : 0xffffffffu;
+        nh0[i] = nd.h0; doff[i] = nd.desc_off; dlen[i] = nd.desc_len;
+    }
+    std::vector<uint32_t> rows(r->desc.size());
+    const bool dense = !r->items.empty() && r->items.front() == 0 && r->items.back() == r->items.size() - 1;
+    if (dense) rows = r->desc;
+    else {
+        unsigned nt = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+        if (rows.size() < 100000) nt = 1;
+        auto conv = [&](size_t a, size_t b) { for (size_t i = a; i < b; ++i) rows[i] = (uint32_t)(std::lower_bound(r->items.begin(), r->items.end(), r->desc[i]) - r->items.begin()); };
+        if (nt == 1) conv(0, rows.size());
+        else { std::vector<std::thread> th; for (unsigned t = 0; t < nt; ++t) th.emplace_back(conv, rows.size() * t / nt, rows.size() * (t + 1) / nt); for (auto& x : th) x.join(); }
+    }
+    dev_ck(r->ctx, arroy_b200_load_forest(r->ctx, (uint32_t)nn, kind.data(), left.data(), right.data(), nidx.data(), nh0.data(), doff.data(), dlen.data(),
+                                          (uint32_t)(r->normals.size() / std::max<uint32_t>(r->dims, 1)), r->normals.data(), rows.size(), rows.data(),
+                                          (uint32_t)r->roots.size(), r->roots.data()));
+    r->forest_on_device = true;
+}
+
 inline int64_t row_of(const arroy_reader* r, uint32_t item) {
     auto it = std::lower_bound(r->items.begin(), r->items.end(), item);
     if (it == r->items.end() || *it != item) return -1;
@@ -720,11 +753,37 @@ int32_t arroy_reader_nns_batch_by_item(arroy_reader* r, uint32_t nq, const uint3
                 qh0[i] = r->hdr0[row]; qh1[i] = r->hdr1[row];
             }
         }
+        const uint32_t k_dev = (uint32_t)count;
+        std::vector<int32_t> status(nq, 0);
+        std::vector<uint32_t> orow_dev;
+        const bool host_walk = getenv("ARROY_B200_HOST_WALK") != nullptr || count > 2048 || r->items.empty();
+        if (!host_walk) {
+            // whole search on the device: walk + dedup/sort + re-rank in one call
+            ensure_forest(r);
+            auto t0d = clk::now();
+            std::vector<uint32_t> qrows(nq);
+            for (uint32_t i = 0; i < nq; ++i) qrows[i] = (uint32_t)row_of(r, items[i]);
+            orow_dev.resize((size_t)nq * std::max<uint32_t>(k_dev, 1));
+            unsigned __int128 sk = search_k ? (unsigned __int128)search_k : (unsigned __int128)count * r->roots.size();   // reader.rs:330-335
+            sk *= oversampling ? oversampling : 1;
+            const uint64_t eff_search_k = sk > (unsigned __int128)UINT64_MAX ? UINT64_MAX : std::max<uint64_t>((uint64_t)sk, 1);
+            dev_ck(r->ctx, arroy_b200_search_batch(r->ctx, nq, qrows.data(), nullptr, nullptr, count, eff_search_k,
+                                                   orow_dev.data(), out_dist, out_len, status.data()));
+            bool all_ok = true;
+            for (uint32_t i = 0; i < nq; ++i) {
+                if (status[i] != 0) { all_ok = false; continue; }
+                for (uint32_t j = 0; j < out_len[i]; ++j) out_ids[(size_t)i * k_dev + j] = r->items[orow_dev[(size_t)i * k_dev + j]];
+            }
+            if (out_ms) { out_ms[0] = 0.0; out_ms[1] = ms_since(t0d); }
+            if (all_ok) return;
+        }
+        // host walk (all queries, or only the ones the device walk gave up on)
         auto t0 = clk::now();
         std::atomic<uint32_t> next{0};
         std::string err; std::mutex emu;
+        const bool only_failed = !host_walk;
         auto worker = [&] {
-            try { for (;;) { uint32_t i = next.fetch_add(1); if (i >= nq) return; tree_walk(r, &q[(size_t)i * d], qh0[i], count, search_k, oversampling, nullptr, rows[i]); } }
+            try { for (;;) { uint32_t i = next.fetch_add(1); if (i >= nq) return; if (only_failed && status[i] == 0) continue; tree_walk(r, &q[(size_t)i * d], qh0[i], count, search_k, oversampling, nullptr, rows[i]); } }
             catch (const std::exception& e) { std::lock_guard<std::mutex> lk(emu); err = e.what(); }
         };
         unsigned nt = std::max(1u, std::min<unsigned>(nq, std::thread::hardware_concurrency()));
@@ -735,6 +794,10 @@ int32_t arroy_reader_nns_batch_by_item(arroy_reader* r, uint32_t nq, const uint3
         if (out_ms) out_ms[0] = ms_since(t0);
         ensure_staged(r);
         t0 = clk::now();
+        std::vector<uint32_t> keep_len(out_len, out_len + nq);
+        std::vector<float> keep_dist;
+        std::vector<uint32_t> keep_ids;
+        if (only_failed) { keep_dist.assign(out_dist, out_dist + (size_t)nq * k_dev); keep_ids.assign(out_ids, out_ids + (size_t)nq * k_dev); }
         std::vector<uint64_t> offs(nq + 1, 0);
         for (uint32_t i = 0; i < nq; ++i) offs[i + 1] = offs[i] + rows[i].size();
         std::vector<uint32_t> flat(offs[nq]);
@@ -752,7 +815,13 @@ int32_t arroy_reader_nns_batch_by_item(arroy_reader* r, uint32_t nq, const uint3
         }
         if (trace) fprintf(stderr, "[trace] nns_batch: device re-rank done at %.2f ms\n", ms_since(t0));
         for (uint32_t i = 0; i < nq; ++i) for (uint32_t j = 0; j < out_len[i]; ++j) out_ids[(size_t)i * k + j] = r->items[orow[(size_t)i * k + j]];
-        if (out_ms) out_ms[1] = ms_since(t0);
+        if (only_failed)
+            for (uint32_t i = 0; i < nq; ++i) if (status[i] == 0) {
+                out_len[i] = keep_len[i];
+                memcpy(out_dist + (size_t)i * k, keep_dist.data() + (size_t)i * k, 4ull * k);
+                memcpy(out_ids + (size_t)i * k, keep_ids.data() + (size_t)i * k, 4ull * k);
+            }
+        if (out_ms) out_ms[1] += ms_since(t0);
     });
 }
 

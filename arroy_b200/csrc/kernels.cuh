@@ -297,12 +297,12 @@ __device__ __forceinline__ float built_finish(int metric, float acc, float qh0, 
 
 __global__ void __launch_bounds__(256)
 distance_kernel(const float* __restrict__ items, const float* __restrict__ ih0, uint32_t d, uint32_t ld, int metric,
-                const float* __restrict__ queries, const float* __restrict__ qh0, uint32_t nq,
-                const uint32_t* __restrict__ rows, const uint64_t* __restrict__ offsets,
+                const float* __restrict__ queries, const uint32_t* __restrict__ qrows, const float* __restrict__ qh0, uint32_t nq,
+                const uint32_t* __restrict__ rows, const uint64_t* __restrict__ seg_beg, const uint64_t* __restrict__ seg_end,
                 float* __restrict__ dists, unsigned long long* __restrict__ keys) {
     const uint32_t q = blockIdx.y;
-    const uint64_t beg = offsets[q], end = offsets[q + 1];
-    const float* qv = queries + (size_t)q * ld;
+    const uint64_t beg = seg_beg[q], end = seg_end[q];
+    const float* qv = qrows ? items + (size_t)qrows[q] * ld : queries + (size_t)q * ld;
     const float qhdr = qh0 ? qh0[q] : 0.f;
     const int lane = threadIdx.x & 31;
     const uint64_t warp_global = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -410,12 +410,12 @@ __device__ __forceinline__ float normalized_distance_dev(int metric, float dist)
 
 __global__ void __launch_bounds__(TOPK_THREADS)
 topk_kernel(const unsigned long long* __restrict__ keys, const float* __restrict__ dists, const uint32_t* __restrict__ rows,
-            const uint64_t* __restrict__ offsets, uint32_t k, int metric,
+            const uint64_t* __restrict__ seg_beg, const uint64_t* __restrict__ seg_end, uint32_t k, int metric,
             uint32_t* __restrict__ out_rows, float* __restrict__ out_dist, uint32_t* __restrict__ out_len) {
     __shared__ unsigned long long buf[TOPK_CAP];
     __shared__ uint32_t fill;
     const uint32_t q = blockIdx.x;
-    const uint64_t beg = offsets[q], end = offsets[q + 1];
+    const uint64_t beg = seg_beg[q], end = seg_end[q];
     const uint64_t n = end - beg;
     const uint32_t kk = (uint32_t)(n < (uint64_t)k ? n : (uint64_t)k);
     for (int i = threadIdx.x; i < TOPK_CAP; i += blockDim.x) buf[i] = ~0ull;

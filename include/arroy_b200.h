@@ -174,6 +174,29 @@ int32_t arroy_b200_rerank_batch(arroy_ctx* ctx, uint32_t nq, const float* querie
                                 const uint32_t* rows, const uint64_t* row_offsets /* nq+1 */, uint32_t k,
                                 uint32_t* out_rows, float* out_dist, uint32_t* out_len);
 
+/* ---- batched search on the device: candidate walk + re-rank (src/reader.rs:317-401) --------- */
+
+/* Upload a built forest once (after a build / when a reader opens): node arrays indexed by
+ * tree node id — kind 0 = missing, 1 = Descendants (desc_rows[desc_off .. +desc_len], ROW indices,
+ * ascending), 2 = SplitPlaneNormal (left / right child ids, normal_idx into `normals`
+ * (n_normals x dim, row-major) or 0xffffffff for "normal: none", normal_hdr0 = bias / extra_dim). */
+int32_t arroy_b200_load_forest(arroy_ctx* ctx, uint32_t n_nodes, const uint8_t* kind, const uint32_t* left,
+                               const uint32_t* right, const uint32_t* normal_idx, const float* normal_hdr0,
+                               const uint32_t* desc_off, const uint32_t* desc_len,
+                               uint32_t n_normals, const float* normals, uint64_t n_desc, const uint32_t* desc_rows,
+                               uint32_t n_roots, const uint32_t* roots);
+
+/* nq complete searches in one call: the priority-queue walk of Reader::nns_by_leaf
+ * (reader.rs:338-374, one warp per query, identical pop order and margins), dedup + sort of the
+ * candidates (reader.rs:378-379), then the re-rank + top-k above. Queries are either stored items
+ * (query_rows != NULL: QueryBuilder::by_item) or vectors (queries: nq x dim, qhdr0 = their header:
+ * Cosine norm; 0 for the other metrics: QueryBuilder::by_vector). search_k = 0 means
+ * count * n_trees (reader.rs:330). out_status[q] (optional): 0 ok, 1 candidate buffer overflow,
+ * 2 heap overflow, 3 missing node — the caller falls back to its own walk for those queries. */
+int32_t arroy_b200_search_batch(arroy_ctx* ctx, uint32_t nq, const uint32_t* query_rows, const float* queries,
+                                const float* qhdr0, uint64_t count, uint64_t search_k,
+                                uint32_t* out_rows, float* out_dist, uint32_t* out_len, int32_t* out_status);
+
 /* ---- synthetic data + timing helpers (bench / tests; not part of the reference seam) ---- */
 
 /* Fill a device matrix (rows x dim f32, dense) with element (i,j) = n-th gen::<f32>() of

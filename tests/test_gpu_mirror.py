@@ -136,12 +136,22 @@ def test_forest_and_queries_match_the_oracle_end_to_end(env_factory, metric, n, 
     # by_vector with a vector that is not in the index
     qv = oracle.synth_rows(SEED, d, n + 3, 1, centre)[0]
     assert r.nns(20).by_vector(qv) == odb.nns_by_vector(qv, 20)
-    # batched by_item == one at a time
-    out_ids, out_dist, out_len, _ = r.nns_batch_by_item(qitems, 10)
-    for i, it in enumerate(qitems):
-        single = r.nns(10).by_item(it)
-        assert out_ids[i, :out_len[i]].tolist() == [s[0] for s in single]
-        assert out_dist[i, :out_len[i]].tolist() == [s[1] for s in single]
+    # batched by_item (device tree walk + re-rank) == one at a time (host walk + device re-rank)
+    for k, sk in ((10, None), (100, None), (7, 3000)):
+        out_ids, out_dist, out_len, _ = r.nns_batch_by_item(qitems, k, search_k=sk)
+        for i, it in enumerate(qitems):
+            single = r.nns(k).search_k(sk).by_item(it) if sk else r.nns(k).by_item(it)
+            assert out_ids[i, :out_len[i]].tolist() == [s[0] for s in single], (k, sk, it)
+            assert out_dist[i, :out_len[i]].tolist() == [s[1] for s in single]
+    # and the host-walk batch path gives the same
+    import os
+    os.environ["ARROY_B200_HOST_WALK"] = "1"
+    try:
+        h_ids, h_dist, h_len, _ = r.nns_batch_by_item(qitems, 10)
+    finally:
+        os.environ.pop("ARROY_B200_HOST_WALK")
+    d_ids, d_dist, d_len, _ = r.nns_batch_by_item(qitems, 10)
+    assert h_len.tolist() == d_len.tolist() and h_ids.tolist() == d_ids.tolist() and h_dist.tobytes() == d_dist.tobytes()
 
 
 def test_rebuild_after_update_gives_a_valid_index(env_factory):

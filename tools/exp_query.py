@@ -19,4 +19,9 @@ for rep in range(3):
     t0 = time.perf_counter()
     out = r.nns_batch_by_item(q, 100)
     print("batch 1000: %.1f ms" % ((time.perf_counter() - t0) * 1e3), out[3], flush=True)
+os.environ["ARROY_B200_HOST_WALK"] = "1"
+for rep in range(2):
+    t0 = time.perf_counter()
+    out = r.nns_batch_by_item(q, 100)
+    print("host-walk batch 1000: %.1f ms" % ((time.perf_counter() - t0) * 1e3), out[3], flush=True)
 env._ctx = None
