@@ -41,6 +41,7 @@ SIGNATURES = [
     ("arroy_b200_build_stats", C.c_int32, [C.c_void_p, C.POINTER(C.c_double)]),
     ("arroy_b200_rerank", C.c_int32, [C.c_void_p, _f32p, C.c_float, C.c_float, _u32p, C.c_uint64, C.c_uint32, _u32p, _f32p, _u32p]),
     ("arroy_b200_rerank_batch", C.c_int32, [C.c_void_p, C.c_uint32, _f32p, _f32p, _f32p, _u32p, _u64p, C.c_uint32, _u32p, _f32p, _u32p]),
+    ("arroy_b200_rerank_shared", C.c_int32, [C.c_void_p, C.c_uint32, _f32p, _f32p, _u32p, C.c_uint64, C.c_uint32, _u32p, _f32p, _u32p]),
     ("arroy_b200_load_forest", C.c_int32, [C.c_void_p, C.c_uint32, _u8p, _u32p, _u32p, _u32p, _f32p, _u32p, _u32p, C.c_uint32, _f32p, C.c_uint64, _u32p, C.c_uint32, _u32p]),
     ("arroy_b200_search_batch", C.c_int32, [C.c_void_p, C.c_uint32, _u32p, _f32p, _f32p, C.c_uint64, C.c_uint64, _u32p, _f32p, _u32p, C.POINTER(C.c_int32)]),
     ("arroy_b200_synth_device", C.c_int32, [C.c_void_p, _u8p, C.c_uint32, C.c_uint64, C.c_uint64, C.c_float, C.c_void_p]),
@@ -286,6 +287,17 @@ class Context:
         out_len = np.zeros(nq, dtype=np.uint32)
         self._ck(self.lib.arroy_b200_rerank_batch(self.h, nq, _fp(queries), _fp(h0), None, _up(rows), offsets.ctypes.data_as(_u64p), k,
                                                   _up(out_rows), _fp(out_dist), _up(out_len)))
+        return out_rows, out_dist, out_len
+
+    def rerank_shared(self, queries, qhdr0, rows, k):
+        queries = np.ascontiguousarray(queries, dtype=np.float32)
+        nq = queries.shape[0]
+        rows = np.ascontiguousarray(rows, dtype=np.uint32)
+        h0 = None if qhdr0 is None else np.ascontiguousarray(qhdr0, dtype=np.float32)
+        out_rows = np.empty((nq, max(k, 1)), dtype=np.uint32)
+        out_dist = np.empty((nq, max(k, 1)), dtype=np.float32)
+        out_len = np.zeros(nq, dtype=np.uint32)
+        self._ck(self.lib.arroy_b200_rerank_shared(self.h, nq, _fp(queries), _fp(h0), _up(rows), rows.size, k, _up(out_rows), _fp(out_dist), _up(out_len)))
         return out_rows, out_dist, out_len
 
     # -- helpers ---------------------------------------------------------------------------------

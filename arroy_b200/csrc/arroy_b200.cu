@@ -18,6 +18,7 @@
 #include "../../include/arroy_b200.h"
 #include "build.cuh"
 #include "search.cuh"
+#include "xrerank.cuh"
 
 using namespace ab;
 
@@ -1008,6 +1009,61 @@ int32_t arroy_b200_rerank_batch(arroy_ctx* c, uint32_t nq, const float* queries,
     return guarded(c, [&] {
         if (nq && (!queries || !row_offsets || !out_len)) throw ArgError("null argument");
         do_rerank_batch(c, nq, queries, qhdr0, qhdr1, rows, row_offsets, k, out_rows, out_dist, out_len);
+    });
+}
+
+int32_t arroy_b200_rerank_shared(arroy_ctx* c, uint32_t nq, const float* queries, const float* qhdr0, const uint32_t* rows, uint64_t n_rows,
+                                 uint32_t k, uint32_t* out_rows, float* out_dist, uint32_t* out_len) {
+    return guarded(c, [&] {
+        require_staged(c); set_device(c);
+        if (nq == 0) return;
+        if (!queries || (n_rows && !rows) || !out_len) throw ArgError("null argument");
+        if (k == 0 || n_rows == 0) { for (uint32_t q = 0; q < nq; ++q) out_len[q] = 0; return; }
+        if (k > TOPK_CAP / 2) throw ArgError("k larger than the top-k buffer (TOPK_CAP/2 = 2048)");
+        if (n_rows > 0x7fffffffull) throw ArgError("too many candidates");
+        for (uint64_t i = 0; i < n_rows; ++i) { if (rows[i] >= c->n) throw ArgError("row index out of range"); if (i && rows[i] <= rows[i - 1]) throw ArgError("rows must be ascending and unique"); }
+        if (c->metric == MANHATTAN || c->dim < 32) {
+            // sequential-sum metric / SSE + scalar paths: generic per-pair kernels over replicated row lists
+            if ((uint64_t)nq * n_rows > (1ull << 28)) throw ArgError("rerank_shared: this metric / dimension only supports nq * n_rows <= 2^28");
+            std::vector<uint32_t> rep((size_t)nq * n_rows);
+            std::vector<uint64_t> offs(nq + 1);
+            for (uint32_t q = 0; q <= nq; ++q) offs[q] = (uint64_t)q * n_rows;
+            for (uint32_t q = 0; q < nq; ++q) memcpy(rep.data() + (size_t)q * n_rows, rows, 4 * n_rows);
+            do_rerank_batch(c, nq, queries, qhdr0, nullptr, rep.data(), offs.data(), k, out_rows, out_dist, out_len);
+            return;
+        }
+        const uint32_t ld = c->ld, nc = (uint32_t)n_rows;
+        c->s_rows.ensure(4ull * nc);
+        CK(cudaMemcpyAsync(c->s_rows.p, rows, 4ull * nc, cudaMemcpyHostToDevice, c->stream));
+        // queries in chunks so the dense distance matrix stays <= 2 GiB
+        const uint32_t chunk = (uint32_t)std::max<uint64_t>(XQB, std::min<uint64_t>(nq, ((2ull << 30) / (4ull * nc)) / XQB * XQB));
+        for (uint32_t q0 = 0; q0 < nq; q0 += chunk) {
+            const uint32_t m = std::min(chunk, nq - q0);
+            c->s_q.ensure((size_t)m * ld * 4); c->s_qh0.ensure(4ull * m); c->s_dists.ensure(4ull * m * nc);
+            c->s_orows.ensure(4ull * m * k); c->s_odist.ensure(4ull * m * k); c->s_olen.ensure(4ull * m);
+            if (ld != c->dim) CK(cudaMemsetAsync(c->s_q.p, 0, (size_t)m * ld * 4, c->stream));
+            CK(cudaMemcpy2DAsync(c->s_q.p, (size_t)ld * 4, queries + (size_t)q0 * c->dim, (size_t)c->dim * 4, (size_t)c->dim * 4, m, cudaMemcpyHostToDevice, c->stream));
+            if (qhdr0) CK(cudaMemcpyAsync(c->s_qh0.p, qhdr0 + q0, 4ull * m, cudaMemcpyHostToDevice, c->stream));
+            else CK(cudaMemsetAsync(c->s_qh0.p, 0, 4ull * m, c->stream));
+            dim3 grid((nc + XCB - 1) / XCB, (m + XQB - 1) / XQB);
+            if (c->metric == EUCLIDEAN)
+                xrerank_kernel<true><<<grid, XTHREADS, 0, c->stream>>>(c->items.as<float>(), c->h0.as<float>(), c->dim, ld, c->metric, c->s_q.as<float>(), c->s_qh0.as<float>(), m,
+                                                                      c->s_rows.as<uint32_t>(), nc, c->s_dists.as<float>());
+            else
+                xrerank_kernel<false><<<grid, XTHREADS, 0, c->stream>>>(c->items.as<float>(), c->h0.as<float>(), c->dim, ld, c->metric, c->s_q.as<float>(), c->s_qh0.as<float>(), m,
+                                                                       c->s_rows.as<uint32_t>(), nc, c->s_dists.as<float>());
+            CK(cudaGetLastError());
+            topk_dense_kernel<<<m, TOPK_THREADS, 0, c->stream>>>(c->s_dists.as<float>(), c->s_rows.as<uint32_t>(), nc, k, c->metric,
+                                                                 c->s_orows.as<uint32_t>(), c->s_odist.as<float>(), c->s_olen.as<uint32_t>());
+            CK(cudaGetLastError());
+            c->n_launches += 2;
+            CK(cudaMemcpyAsync(out_rows + (size_t)q0 * k, c->s_orows.p, 4ull * m * k, cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaMemcpyAsync(out_dist + (size_t)q0 * k, c->s_odist.p, 4ull * m * k, cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaMemcpyAsync(out_len + q0, c->s_olen.p, 4ull * m, cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaStreamSynchronize(c->stream));
+        }
+        c->h2d_bytes += (uint64_t)nq * c->dim * 4 + 4ull * nc;
+        c->d2h_bytes += 8ull * nq * k + 4ull * nq;
     });
 }
 

@@ -174,6 +174,14 @@ int32_t arroy_b200_rerank_batch(arroy_ctx* ctx, uint32_t nq, const float* querie
                                 const uint32_t* rows, const uint64_t* row_offsets /* nq+1 */, uint32_t k,
                                 uint32_t* out_rows, float* out_dist, uint32_t* out_len);
 
+/* nq queries against ONE shared candidate list (BASELINE config 5: 4096 x 100k, d = 768): a dense
+ * query x candidate contraction on a register-tiled kernel that keeps the reference's summation
+ * order per pair, so ids and distances are identical to nq calls of arroy_b200_rerank. `rows`
+ * ascending and unique. */
+int32_t arroy_b200_rerank_shared(arroy_ctx* ctx, uint32_t nq, const float* queries /* nq x dim */,
+                                 const float* qhdr0 /* nq or NULL */, const uint32_t* rows, uint64_t n_rows, uint32_t k,
+                                 uint32_t* out_rows, float* out_dist, uint32_t* out_len);
+
 /* ---- batched search on the device: candidate walk + re-rank (src/reader.rs:317-401) --------- */
 
 /* Upload a built forest once (after a build / when a reader opens): node arrays indexed by

@@ -240,6 +240,27 @@ def test_rerank_batch_ragged_and_empty(ctx):
         assert out_dist[i, :len(wr)].tobytes() == wd.tobytes()
 
 
+@pytest.mark.parametrize("metric", MET)
+@pytest.mark.parametrize("d,nq,nc,k", [(768, 37, 1500, 100), (100, 16, 333, 10), (64, 5, 40, 50), (30, 9, 200, 7), (1536, 20, 700, 64)])
+def test_rerank_shared_matches_per_query_rerank_and_oracle(ctx, metric, d, nq, nc, k):
+    # config 5 shape (many queries x one candidate list) on the exact register-tiled kernel
+    n = 4000
+    data = synth(n, d)
+    h0, h1 = headers_for(metric, data)
+    ctx.stage_items_flat(metric, np.arange(n, dtype=np.uint32), data, h0, h1)
+    m = oracle.METRICS[metric]
+    r = np.random.default_rng(nq * 1000 + nc)
+    rows = np.sort(r.choice(n, size=nc, replace=False)).astype(np.uint32)
+    qs = synth(nq, d, row0=n + 11)
+    qh = np.array([oracle.new_header(m, q)[0] for q in qs], dtype=np.float32)
+    out_rows, out_dist, out_len = ctx.rerank_shared(qs, qh, rows, k)
+    for i in range(nq):
+        wr, wd = oracle.rerank(m, qs[i], (qh[i], 0.0), data, h0, h1, rows, k)
+        assert out_len[i] == len(wr)
+        assert out_rows[i, :len(wr)].tolist() == wr.tolist(), (i,)
+        assert out_dist[i, :len(wr)].tobytes() == wd.tobytes()
+
+
 def test_stage_from_unaligned_leaf_values(ctx):
     # the raw LMDB value layout: [0x00][header][dim x f32], byte aligned only (src/node.rs:224-228)
     n, d = 300, 40
