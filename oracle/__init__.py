@@ -77,6 +77,7 @@ def lib():
     sig("oracle_db_set_items", None, vp, u64, _u32p, _f32p)
     sig("oracle_db_build", i32, vp, vp, i64, u64, i32)
     sig("oracle_db_build_memory_limited", i32, vp, vp, i64, u64, u64)
+    sig("oracle_db_build_incremental", i32, vp, vp, i64, u64)
     sig("oracle_db_n_nodes", u64, vp)
     sig("oracle_db_n_roots", u64, vp)
     sig("oracle_db_roots", None, vp, _u32p)
@@ -271,6 +272,12 @@ class Db:
 
     def build(self, rng, n_trees=None, split_after=None, threads=1):
         rc = lib().oracle_db_build(self.h, rng.h, -1 if n_trees is None else n_trees, split_after or 0, threads)
+        if rc != 0:
+            raise RuntimeError("oracle build failed")
+
+    def build_incremental(self, rng, n_trees=None, split_after=None):
+        """Writer::build in general (fresh or on top of existing trees), 1-thread execution order."""
+        rc = lib().oracle_db_build_incremental(self.h, rng.h, -1 if n_trees is None else n_trees, split_after or 0)
         if rc != 0:
             raise RuntimeError("oracle build failed")
 

@@ -23,6 +23,7 @@
 #include <functional>
 #include <map>
 #include <queue>
+#include <set>
 #include <stdexcept>
 #include <string>
 #include <thread>
@@ -126,6 +127,7 @@ struct Db {
     std::vector<float> vec_own, h0_own, h1_own;
     const uint32_t* ids = nullptr;
     const float* vec = nullptr;
+    bool borrowed = false;   // set_items(): caller-owned arrays instead of the add_item staging area
     size_t n = 0;
     // forest
     std::vector<TreeNode> nodes;  // index = tree node id
@@ -143,7 +145,7 @@ struct Db {
     Leaf leaf(size_t row) const { return Leaf{h0_own[row], h1_own.empty() ? 0.f : h1_own[row], vec + row * d}; }
 
     void freeze() {
-        if (!staged.empty() || ids == nullptr) {
+        if (!borrowed) {
             ids_own.clear(); vec_own.clear();
             for (auto& kv : staged) { ids_own.push_back(kv.first); vec_own.insert(vec_own.end(), kv.second.begin(), kv.second.end()); }
             ids = ids_own.data(); vec = vec_own.data(); n = ids_own.size();
@@ -224,7 +226,7 @@ struct Db {
                 nodes.push_back(std::move(t));
                 roots.push_back(0);
             }
-            built = true;
+            built = true; has_metadata = true; updated.clear();
             return;
         }
         uint64_t T = target_n_trees(n_trees_opt, d, n, 0);
@@ -269,7 +271,7 @@ struct Db {
             }
             L.clear(); L.shrink_to_fit();
         }
-        built = true;
+        built = true; has_metadata = true; updated.clear();
     }
 
     // ---------------------------------------------------------------------------------------------
@@ -319,6 +321,17 @@ struct Db {
     struct LmState {
         size_t K = 0, memory = 0;
         uint32_t counter = 0;
+        // ConcurrentNodeIds::next — src/parallel.rs:238-254: exhaust the free list first, then count up
+        std::vector<uint32_t> available;
+        size_t select_in_bitmap = 0;
+        bool look_into_bitmap = false;
+        uint32_t next_id() {
+            if (look_into_bitmap) {
+                if (select_in_bitmap < available.size()) return available[select_in_bitmap++];
+                look_into_bitmap = false;
+            }
+            return counter++;
+        }
         std::map<uint32_t, TreeNode> out;                 // final nodes (by id), rows still as row indices
         std::map<uint32_t, LocalNode> tmp_splits;         // the (single) thread's TmpNodes file: split nodes
         std::vector<LmTask> stack;                         // rayon local deque, popped LIFO
@@ -348,7 +361,7 @@ struct Db {
 
     uint32_t lm_make_tree(LmState& S, StdRng& rng, const std::vector<uint32_t>& rows, IntMapEmu& descendants, int64_t next_id) {
         if (rows.size() <= S.K) {
-            uint32_t id = next_id >= 0 ? (uint32_t)next_id : S.counter++;
+            uint32_t id = next_id >= 0 ? (uint32_t)next_id : S.next_id();
             descendants.entry(id) = rows;   // descendants.insert(item_id, item_indices.clone())
             return id;
         }
@@ -372,7 +385,7 @@ struct Db {
         }
         uint32_t l = lm_make_tree(S, rng, left, descendants, -1);
         uint32_t r = lm_make_tree(S, rng, right, descendants, -1);
-        uint32_t id = next_id >= 0 ? (uint32_t)next_id : S.counter++;
+        uint32_t id = next_id >= 0 ? (uint32_t)next_id : S.next_id();
         S.tmp_splits[id] = LocalNode{2, l, r, has_normal, has_normal ? normal : OwnedLeaf{}, {}};
         return id;
     }
@@ -429,7 +442,7 @@ struct Db {
         IntMapEmu top;
         std::vector<uint32_t> all(n);
         for (size_t r = 0; r < n; ++r) all[r] = (uint32_t)r;
-        for (uint64_t t = 0; t < T; ++t) { roots.push_back(S.counter); top.entry(S.counter++) = all; }   // writer.rs:556-561
+        for (uint64_t t = 0; t < T; ++t) { uint32_t nid = S.next_id(); roots.push_back(nid); top.entry(nid) = all; }   // writer.rs:556-561
         StdRng rng1 = user_rng.fork();                                                                        // writer.rs:575
         lm_process_descendants(S, rng1, top);
         while (!S.stack.empty()) { LmTask t = std::move(S.stack.back()); S.stack.pop_back(); lm_run_task(S, t); }
@@ -437,6 +450,167 @@ struct Db {
         for (auto& kv : S.out) { TreeNode& o = nodes[kv.first]; o.kind = 1; o.descendants.resize(kv.second.descendants.size()); for (size_t i = 0; i < o.descendants.size(); ++i) o.descendants[i] = ids[kv.second.descendants[i]]; }
         for (auto& kv : S.tmp_splits) { TreeNode& o = nodes[kv.first]; o.kind = 2; o.left = kv.second.left; o.right = kv.second.right; o.has_normal = kv.second.has_normal; o.normal = kv.second.normal; }
         built = true;
+    }
+
+    // ---------------------------------------------------------------------------------------------
+    // Writer::build on an index that already has trees (src/writer.rs:487-629), in the order a
+    // 1-thread rayon pool executes it:
+    //   delete_extra_trees :632-653, delete_tree :1263-1277
+    //   delete_items_from_trees :978-1015, delete_items_in_file :1021-1114
+    //   insert_items_in_current_trees :846-889, insert_items_in_tree :1119-1160,
+    //   insert_items_in_descendants_from_frozen_reader :1398-1459
+    //   ConcurrentNodeIds (free list first) src/parallel.rs:207-255
+    // Pinned by the reference's incremental inline snapshots (tests/test_oracle_golden.py). With
+    // several roots the reference merges the per-root results through rayon's `reduce`
+    // (writer.rs:1148-1159); this restatement merges in ascending root order.
+    std::set<uint32_t> updated;      // the `Updated` keys (src/node_id.rs:14-16)
+    bool has_metadata = false;
+
+    void mark_updated(uint32_t id) { updated.insert(id); }
+
+    void inc_delete_tree(uint32_t node) {
+        if (node >= nodes.size() || nodes[node].kind == 0) return;
+        if (nodes[node].kind == 2) { inc_delete_tree(nodes[node].left); inc_delete_tree(nodes[node].right); }
+        nodes[node] = TreeNode{};
+    }
+
+    struct TmpOps { std::vector<std::pair<uint32_t, TreeNode>> puts; std::set<uint32_t> deleted; };
+
+    // returns (new id, Some(items) / None)
+    std::pair<uint32_t, std::pair<bool, std::vector<uint32_t>>> inc_delete_items(uint32_t current, TmpOps& tmp, const std::set<uint32_t>& to_delete, size_t K) {
+        const TreeNode& nd = nodes[current];
+        if (nd.kind == 1) {
+            std::vector<uint32_t> nw;
+            for (uint32_t id : nd.descendants) if (!to_delete.count(id)) nw.push_back(id);
+            if (nw.size() != nd.descendants.size()) { TreeNode t; t.kind = 1; t.descendants = nw; tmp.puts.push_back({current, std::move(t)}); }
+            return {current, {true, nw}};
+        }
+        const uint32_t left = nd.left, right = nd.right;
+        auto L = inc_delete_items(left, tmp, to_delete, K);
+        auto R = inc_delete_items(right, tmp, to_delete, K);
+        const uint32_t new_left = L.first, new_right = R.first;
+        const bool ls = L.second.first, rs = R.second.first;
+        auto put_split = [&]() {
+            if (new_left != left || new_right != right) { TreeNode t = nodes[current]; t.left = new_left; t.right = new_right; tmp.puts.push_back({current, std::move(t)}); }
+        };
+        if (ls && L.second.second.empty()) { tmp.deleted.insert(new_left); tmp.deleted.insert(current); return {new_right, R.second}; }
+        if (rs && R.second.second.empty()) { tmp.deleted.insert(new_right); tmp.deleted.insert(current); return {new_left, L.second}; }
+        if (ls && rs) {
+            size_t total = L.second.second.size() + R.second.second.size();
+            if (total <= K) {
+                std::vector<uint32_t> all;
+                std::set_union(L.second.second.begin(), L.second.second.end(), R.second.second.begin(), R.second.second.end(), std::back_inserter(all));
+                tmp.deleted.insert(new_left); tmp.deleted.insert(new_right);
+                TreeNode t; t.kind = 1; t.descendants = all;
+                tmp.puts.push_back({current, std::move(t)});
+                return {current, {true, all}};
+            }
+            put_split();
+            return {current, {false, {}}};
+        }
+        put_split();
+        return {current, {false, {}}};
+    }
+
+    void inc_route(StdRng& rng, uint32_t node, const std::vector<uint32_t>& to_insert /* item ids */, IntMapEmu& out) {
+        const TreeNode& nd = nodes[node];
+        if (nd.kind == 1) {
+            std::vector<uint32_t> merged;
+            std::set_union(nd.descendants.begin(), nd.descendants.end(), to_insert.begin(), to_insert.end(), std::back_inserter(merged));
+            out.entry(node) = merged;   // descendants_to_update.insert(current_node, descendants | to_insert)
+            return;
+        }
+        std::vector<uint32_t> left, right;
+        if (!nd.has_normal) { for (uint32_t id : to_insert) { if (rng.gen_bool()) left.push_back(id); else right.push_back(id); } }
+        else { Leaf nl = nd.normal.view(); for (uint32_t id : to_insert) { if (side_is_right(margin(metric, nl, leaf((size_t)row_of(id)), d))) right.push_back(id); else left.push_back(id); } }
+        const uint32_t l = nd.left, r = nd.right;
+        if (!left.empty()) inc_route(rng, l, left, out);
+        if (!right.empty()) inc_route(rng, r, right, out);
+    }
+
+    void build_incremental(StdRng& user_rng, int64_t n_trees_opt, size_t split_after) {
+        freeze();
+        preprocess();
+        const size_t K = split_after ? split_after : d;
+        std::set<uint32_t> updated_items;
+        updated_items.swap(updated);                       // reset_and_retrieve_updated_items
+        if (n <= K) {                                      // clear_db_and_create_a_single_leaf
+            nodes.clear(); roots.clear();
+            if (n > 0) { TreeNode t; t.kind = 1; t.descendants.assign(ids, ids + n); nodes.push_back(std::move(t)); roots.push_back(0); }
+            has_metadata = true; built = true;
+            return;
+        }
+        const std::set<uint32_t>& to_delete = updated_items;
+        std::vector<uint32_t> to_insert;
+        for (uint32_t id : updated_items) if (row_of(id) >= 0) to_insert.push_back(id);
+        if (!has_metadata) roots.clear();
+        LmState S;
+        S.K = K; S.memory = SIZE_MAX;
+        {   // ConcurrentNodeIds::new(used_tree_node) — before anything is deleted
+            uint32_t last = 0; bool any = false;
+            for (uint32_t i = 0; i < nodes.size(); ++i) if (nodes[i].kind) { last = i; any = true; }
+            uint32_t last_id = any ? last + 1 : 0;
+            for (uint32_t i = 0; i < last_id; ++i) if (!nodes[i].kind) S.available.push_back(i);
+            S.counter = last_id;
+            S.look_into_bitmap = !S.available.empty();
+        }
+        uint64_t target = target_n_trees(n_trees_opt, d, n, roots.size());
+        {   // delete_extra_trees
+            size_t extraneous = roots.size() > target ? roots.size() - (size_t)target : 0;
+            for (size_t i = 0; i < extraneous && !roots.empty(); ++i) { uint32_t r0 = roots[0]; roots[0] = roots.back(); roots.pop_back(); inc_delete_tree(r0); }
+        }
+        {   // delete_items_from_trees
+            TmpOps tmp;
+            for (uint32_t& root : roots) { auto res = inc_delete_items(root, tmp, to_delete, K); root = res.first; }
+            std::sort(roots.begin(), roots.end());
+            for (uint32_t id : tmp.deleted) nodes[id] = TreeNode{};
+            for (auto& pr : tmp.puts) if (!tmp.deleted.count(pr.first)) nodes[pr.first] = pr.second;
+        }
+        // insert_items_in_current_trees. The per-root results are combined by rayon's
+        // `repeat_n(..).zip(roots).map(..).reduce(..)` (writer.rs:1128-1159); on a 1-thread pool the
+        // length splitter splits the roots exactly once, at len / 2: each half is folded left to
+        // right into its own map, then the right map is merged into the left one, and the result is
+        // re-inserted into a fresh map (writer.rs:879-887) — every step in hashbrown iteration order.
+        IntMapEmu top_ids;
+        if (!roots.empty() && !to_insert.empty()) {
+            uint64_t seed = user_rng.next_u64();                       // repeat_n(rng.next_u64(), roots.len())
+            auto merge_into = [](IntMapEmu& dst, IntMapEmu& src) {
+                for (size_t b = 0; b < src.keys.size(); ++b) {
+                    if (src.keys[b] < 0) continue;
+                    std::vector<uint32_t>& dv = dst.entry((uint32_t)src.keys[b]);
+                    std::vector<uint32_t> merged;
+                    std::set_union(dv.begin(), dv.end(), src.vals[b].begin(), src.vals[b].end(), std::back_inserter(merged));
+                    dv.swap(merged);
+                }
+            };
+            auto fold = [&](size_t a, size_t b) {
+                IntMapEmu acc;
+                for (size_t i = a; i < b; ++i) {
+                    StdRng rr = StdRng::seed_from_u64(seed + (uint64_t)roots[i]);
+                    IntMapEmu per_root;
+                    inc_route(rr, roots[i], to_insert, per_root);
+                    merge_into(acc, per_root);
+                }
+                return acc;
+            };
+            IntMapEmu reduced;
+            if (roots.size() >= 2) { size_t mid = roots.size() / 2; reduced = fold(0, mid); IntMapEmu right = fold(mid, roots.size()); merge_into(reduced, right); }
+            else reduced = fold(0, roots.size());
+            merge_into(top_ids, reduced);
+        }
+        uint64_t nb_missing = target > roots.size() ? target - roots.size() : 0;
+        std::vector<uint32_t> all_ids(ids, ids + n);
+        for (uint64_t i = 0; i < nb_missing; ++i) { uint32_t nid = S.next_id(); roots.push_back(nid); top_ids.entry(nid) = all_ids; }
+        // ids -> rows for the tree builder
+        IntMapEmu top = top_ids;
+        for (auto& v : top.vals) for (auto& x : v) x = (uint32_t)row_of(x);
+        StdRng rng1 = user_rng.fork();                                  // writer.rs:575
+        lm_process_descendants(S, rng1, top);
+        while (!S.stack.empty()) { LmTask t = std::move(S.stack.back()); S.stack.pop_back(); lm_run_task(S, t); }
+        if (nodes.size() < S.counter) nodes.resize(S.counter);
+        for (auto& kv : S.out) { TreeNode& o = nodes[kv.first]; o = TreeNode{}; o.kind = 1; o.descendants.resize(kv.second.descendants.size()); for (size_t i = 0; i < o.descendants.size(); ++i) o.descendants[i] = ids[kv.second.descendants[i]]; }
+        for (auto& kv : S.tmp_splits) { TreeNode& o = nodes[kv.first]; o = TreeNode{}; o.kind = 2; o.left = kv.second.left; o.right = kv.second.right; o.has_normal = kv.second.has_normal; o.normal = kv.second.normal; }
+        has_metadata = true; built = true;
     }
 
     // Total order of (OrderedFloat<f32>, u32): NaN greatest & all NaN equal, -0 == +0.

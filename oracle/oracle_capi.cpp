@@ -97,7 +97,7 @@ void oracle_dot_preprocess(const float* vectors, uint64_t n, uint64_t d, float* 
     Db db(DOT_PRODUCT, d);
     std::vector<uint32_t> ids(n);
     for (uint64_t i = 0; i < n; ++i) ids[i] = (uint32_t)i;
-    db.ids = ids.data(); db.vec = vectors; db.n = n;
+    db.ids = ids.data(); db.vec = vectors; db.n = n; db.borrowed = true;
     db.freeze(); db.preprocess();
     for (uint64_t i = 0; i < n; ++i) { out_extra_dim[i] = db.h0_own[i]; out_norm[i] = db.h1_own[i]; }
 }
@@ -108,11 +108,14 @@ double oracle_split_imbalance(uint64_t l, uint64_t r) { return split_imbalance(l
 // ---- database --------------------------------------------------------------------------
 void* oracle_db_new(int metric, uint64_t d) { return new Db(metric, d); }
 void oracle_db_free(void* db) { delete static_cast<Db*>(db); }
-void oracle_db_add_item(void* db, uint32_t id, const float* v) { auto* D = static_cast<Db*>(db); D->staged[id] = std::vector<float>(v, v + D->d); }
-int oracle_db_del_item(void* db, uint32_t id) { return (int)static_cast<Db*>(db)->staged.erase(id); }
+void oracle_db_add_item(void* db, uint32_t id, const float* v) { auto* D = static_cast<Db*>(db); D->staged[id] = std::vector<float>(v, v + D->d); D->mark_updated(id); }
+int oracle_db_del_item(void* db, uint32_t id) { auto* D = static_cast<Db*>(db); int ex = (int)D->staged.erase(id); if (ex) D->mark_updated(id); return ex; }
+int oracle_db_build_incremental(void* db, void* rng, int64_t n_trees_opt, uint64_t split_after) {
+    try { static_cast<Db*>(db)->build_incremental(*static_cast<StdRng*>(rng), n_trees_opt, split_after); return 0; } catch (...) { return -1; }
+}
 // borrow caller-owned arrays (ids ascending); they must outlive the db
 void oracle_db_set_items(void* db, uint64_t n, const uint32_t* ids, const float* vectors) {
-    auto* D = static_cast<Db*>(db); D->staged.clear(); D->ids = ids; D->vec = vectors; D->n = n;
+    auto* D = static_cast<Db*>(db); D->staged.clear(); D->ids = ids; D->vec = vectors; D->n = n; D->borrowed = true;
 }
 int oracle_db_build(void* db, void* rng, int64_t n_trees_opt, uint64_t split_after, int n_threads) {
     try { static_cast<Db*>(db)->build(*static_cast<StdRng*>(rng), n_trees_opt, split_after, n_threads); return 0; } catch (...) { return -1; }
@@ -132,7 +135,7 @@ typedef void (*oracle_node_sink)(void* arg, uint32_t node_id, const uint8_t* byt
 void oracle_db_emit_nodes(void* db, oracle_node_sink sink, void* arg) {
     auto* D = static_cast<Db*>(db);
     std::vector<uint8_t> buf;
-    for (size_t id = 0; id < D->nodes.size(); ++id) { encode_tree_node(D->metric, D->d, D->nodes[id], buf); sink(arg, (uint32_t)id, buf.data(), buf.size()); }
+    for (size_t id = 0; id < D->nodes.size(); ++id) { if (D->nodes[id].kind == 0) continue; encode_tree_node(D->metric, D->d, D->nodes[id], buf); sink(arg, (uint32_t)id, buf.data(), buf.size()); }
 }
 // returns number of results, -1 if the item does not exist. out_cand (optional, cap
 // cand_cap) receives the deduplicated candidate ids that entered the re-rank loop.

@@ -102,7 +102,9 @@ def main():
     g["lot_of_random_points"] = snap_file("arroy__tests__writer__write_and_update_lot_of_random_points.snap")
     # second snapshot of the same test: only its *items* are used (even ids redrawn after the
     # first build), which pins how many words Writer::build takes from the user rng
-    g["lot_of_random_points_2_items"] = snap_file("arroy__tests__writer__write_and_update_lot_of_random_points-2.snap")["items"]
+    second = snap_file("arroy__tests__writer__write_and_update_lot_of_random_points-2.snap")
+    g["lot_of_random_points_2_items"] = second["items"]
+    g["lot_of_random_points_2"] = {k: v for k, v in second.items() if k != "items"}   # forest after the incremental update (10 roots)
     g["little_memory"] = snap_file("arroy__tests__writer__write_and_update_lot_of_random_points_with_little_memory.snap")
     # inline snapshots of src/tests/writer.rs, keyed by the line they start on
     inl = {}

@@ -172,3 +172,83 @@ def test_simd_paths_agree_with_scalar_on_integers():
         a, b = v1[:n], v2[:n]
         assert oracle.dot(a, b) == float(np.sum(a.astype(np.float64) * b.astype(np.float64)))
         assert oracle.euclid(a, b) == float(np.sum((a.astype(np.float64) - b.astype(np.float64)) ** 2))
+
+
+# ---- incremental builds: the reference's own add / delete / rebuild scenarios (src/tests/writer.rs) ----
+# each scenario: dims, then a list of steps; ("add", id, vec) / ("del", id) / ("build", n_trees, golden line, split_after)
+LINE6 = [("add", i, [float(i), 0.0]) for i in range(6)]
+SCENARIOS = {
+    "overwrite_one_item_incremental": (2, LINE6 + [("build", 1, "403"), ("add", 3, [6.0, 0.0]), ("build", 1, "432")]),
+    "delete_one_item_in_a_one_item_db": (2, [("add", 0, [0.0, 0.0]), ("build", 1, "464"), ("del", 0), ("build", 1, "481")]),
+    "delete_one_item_in_a_descendant": (2, [("add", 0, [0.0, 0.0]), ("add", 1, [1.0, 0.0]), ("build", 1, "563"), ("del", 0), ("build", 1, "581")]),
+    "delete_one_leaf_in_a_split": (2, [("add", i, [float(i), 0.0]) for i in range(3)] + [("build", 1, "605"), ("del", 1), ("build", 1, "627")]),
+    "delete_one_item_in_a_single_document_database": (2, [("add", 0, [0.0, 0.0]), ("build", None, "650"), ("del", 0), ("build", None, "667")]),
+    "delete_one_item": (2, LINE6 + [("build", 1, "689"), ("del", 3), ("build", 1, "717"), ("del", 1), ("build", 1, "743")]),
+    "add_one_item_incrementally_in_an_empty_db": (2, [("build", 1, "767"), ("add", 0, [0.0, 0.0]), ("build", 1, "780")]),
+    "add_one_item_incrementally_in_a_one_item_db": (2, [("add", 0, [0.0, 0.0]), ("build", 1, "800"), ("add", 1, [1.0, 0.0]), ("build", 1, "815")]),
+    "add_one_item_incrementally_to_create_a_split_node": (2, [("add", 0, [0.0, 0.0]), ("add", 1, [1.0, 0.0]), ("build", 1, "837"), ("add", 2, [2.0, 0.0]), ("build", 1, "853")]),
+    "add_one_item_incrementally": (2, LINE6 + [("build", 1, "880"), ("add", 25, [25.0, 0.0]), ("build", 1, "908"), ("add", 8, [8.0, 0.0]), ("build", 1, "939")]),
+    "create_root_split_node_with_empty_child": (2, LINE6 + [("build", 1, "1057"), ("del", 1), ("del", 5), ("build", 1, "1086"), ("del", 0), ("build", 1, "1108")]),
+    "reuse_node_id": (2, LINE6 + [("build", 1, "1135"), ("del", 4), ("build", 1, "1163"), ("add", 4, [4.0, 0.0]), ("build", 1, "1188"), ("build", 2, "1215")]),
+    # a Writer opened with dimensions = 2 over 4-dimensional items (the test does that): only
+    # fit_in_descendant sees the 2, which is what split_after = 2 expresses
+    "delete_extraneous_tree": (4, [("add", i, [float(i), 0.0, 0.0, 0.0]) for i in range(5)] + [("build", None, "980"), ("build", 2, "1000", 2), ("build", 1, "1025", 2)]),
+}
+
+
+def run_scenario(make_db, steps, check):
+    """Drive a db object exposing add_item / del_item / build(rng, n_trees, split_after)."""
+    db = make_db()
+    rng = rng42()
+    for st in steps:
+        if st[0] == "add":
+            db.add_item(st[1], st[2])
+        elif st[0] == "del":
+            db.del_item(st[1])
+        else:
+            split_after = st[3] if len(st) > 3 else None
+            db.build_incremental(rng, n_trees=st[1], split_after=split_after)
+            check(db, st[2])
+    return db
+
+
+@pytest.mark.parametrize("name", sorted(SCENARIOS))
+def test_incremental_scenarios_match_reference_snapshots(name):
+    dims, steps = SCENARIOS[name]
+
+    def check(db, line):
+        gold = G["writer_inline"][line]
+        check_dump(gold, db.nodes(), db.roots, oracle.EUCLIDEAN, dims, oracle.decode_node)
+
+    run_scenario(lambda: oracle.Db("euclidean", dims), steps, check)
+
+
+def test_incremental_equals_fresh_build_for_a_fresh_index():
+    rng_a, rng_b = rng42(), rng42()
+    data = rng_a.fill_f32(300 * 24).reshape(300, 24)
+    rng_b.fill_f32(300 * 24)
+    a, b = oracle.Db("cosine", 24), oracle.Db("cosine", 24)
+    for i in range(300):
+        a.add_item(i, data[i])
+        b.add_item(i, data[i])
+    a.build(rng_a, n_trees=5)
+    b.build_incremental(rng_b, n_trees=5)
+    assert a.nodes() == b.nodes() and a.roots == b.roots
+
+
+def test_lot_of_random_points_second_snapshot_after_update():
+    # write_and_update_lot_of_random_points, second half (tests/writer.rs:310-319): 50 items
+    # overwritten, then an incremental build over 10 existing roots. Node ids depend on the order in
+    # which the per-root results are merged (rayon `reduce`, writer.rs:1148-1159).
+    gold = G["lot_of_random_points_2"]
+    rng = rng42()
+    data = rng.fill_f32(100 * 30).reshape(100, 30)
+    db = oracle.Db("euclidean", 30)
+    for i in range(100):
+        db.add_item(i, data[i])
+    db.build_incremental(rng, n_trees=10)
+    check_dump(G["lot_of_random_points"], db.nodes(), db.roots, oracle.EUCLIDEAN, 30, oracle.decode_node)
+    for i in range(0, 100, 2):
+        db.add_item(i, rng.fill_f32(30))
+    db.build_incremental(rng, n_trees=10)
+    check_dump(gold, db.nodes(), db.roots, oracle.EUCLIDEAN, 30, oracle.decode_node)
