@@ -67,8 +67,9 @@ struct PinBuf {
 };
 
 struct Wave {  // device buffers of one wave of trees; kept across builds
-    DevBuf st, frames, recs, perm0, perm1, flags, unit_left, pool, pool_counter, jobs, scratch, active, error, final_ids, keys;
+    DevBuf st, frames, recs, perm0, perm1, flags, unit_left, pool, pool_counter, jobs, scratch, active, error, final_ids, keys, sub_rows, sub_off;
     void release() {
+        sub_rows.release(); sub_off.release();
         st.release(); frames.release(); recs.release(); perm0.release(); perm1.release(); flags.release(); unit_left.release();
         pool.release(); pool_counter.release(); jobs.release(); scratch.release(); active.release(); error.release(); final_ids.release(); keys.release();
     }
@@ -286,8 +287,10 @@ namespace {
 
 using BuiltTree = BuiltTreeView;
 
+struct Subsets { const uint32_t* rows = nullptr; const uint64_t* off = nullptr; };   // host arrays, indexed by global tree
+
 void build_wave(arroy_ctx* c, size_t wave_no, uint32_t t0, uint32_t tw, const uint8_t (*seeds)[32], uint32_t K, uint32_t cap_mult,
-                arroy_b200_cancel_fn cancel, void* cancel_arg, std::vector<BuiltTree>& out_trees, uint32_t& out_pool_stride) {
+                arroy_b200_cancel_fn cancel, void* cancel_arg, std::vector<BuiltTree>& out_trees, uint32_t& out_pool_stride, Subsets sub = Subsets{}) {
     const uint64_t n = c->n;
     const uint32_t ld = c->ld;
     Wave& W = c->wave;
@@ -328,6 +331,17 @@ void build_wave(arroy_ctx* c, size_t wave_no, uint32_t t0, uint32_t tw, const ui
     P.pool = W.pool.as<float>(); P.pool_stride = pool_stride; P.pool_cap = pool_cap; P.pool_counter = W.pool_counter.as<uint32_t>();
     P.jobs = W.jobs.as<Job>(); P.scratch = W.scratch.as<float>(); P.use_smem_ws = use_smem;
     P.active = W.active.as<uint32_t>(); P.error = W.error.as<int32_t>();
+    P.sub_rows = nullptr; P.sub_off = nullptr;
+    if (sub.rows) {   // this wave's subsets, offsets rebased to the wave
+        const uint64_t b = sub.off[t0], e = sub.off[t0 + tw];
+        std::vector<uint64_t> off(tw + 1);
+        for (uint32_t t = 0; t <= tw; ++t) off[t] = sub.off[t0 + t] - b;
+        W.sub_rows.ensure(std::max<size_t>(16, 4ull * (e - b)));
+        W.sub_off.ensure(8ull * (tw + 1));
+        if (e > b) CK(cudaMemcpyAsync(W.sub_rows.p, sub.rows + b, 4ull * (e - b), cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpy(W.sub_off.p, off.data(), 8ull * (tw + 1), cudaMemcpyHostToDevice));
+        P.sub_rows = W.sub_rows.as<uint32_t>(); P.sub_off = W.sub_off.as<uint64_t>();
+    }
 
     // tree keys = the 8 little-endian words of each 32-byte seed (StdRng::from_seed)
     std::vector<uint32_t> keys((size_t)tw * 8);
@@ -511,13 +525,19 @@ void build_wave(arroy_ctx* c, size_t wave_no, uint32_t t0, uint32_t tw, const ui
 }
 
 // Phase 1: device build of `n_trees` trees; results stay parked in the context.
-void do_build_begin(arroy_ctx* c, uint32_t n_trees, const uint8_t (*seeds)[32], uint32_t split_after, arroy_b200_cancel_fn cancel, void* cancel_arg, uint32_t* out_counts) {
+void do_build_begin(arroy_ctx* c, uint32_t n_trees, const uint8_t (*seeds)[32], uint32_t split_after, arroy_b200_cancel_fn cancel, void* cancel_arg, uint32_t* out_counts,
+                    Subsets sub = Subsets{}) {
     require_staged(c);
     set_device(c);
     for (auto& s : c->stats) s = 0;
     c->pending_waves.clear(); c->pending_wave_t0.clear(); c->pending_n_trees = 0;
     const uint32_t K = split_after ? split_after : c->dim;
-    if (c->n <= K) throw ArgError("build_trees needs more items than split_after (a single Descendants node is the caller's job, src/writer.rs:499-501)");
+    if (!sub.rows && c->n <= K) throw ArgError("build_trees needs more items than split_after (a single Descendants node is the caller's job, src/writer.rs:499-501)");
+    if (sub.rows)
+        for (uint32_t t = 0; t < n_trees; ++t) {
+            if (sub.off[t + 1] - sub.off[t] <= K) throw ArgError("build_subtrees: every subset must hold more rows than split_after");
+            for (uint64_t i = sub.off[t]; i < sub.off[t + 1]; ++i) { if (sub.rows[i] >= c->n) throw ArgError("row index out of range"); if (i > sub.off[t] && sub.rows[i] <= sub.rows[i - 1]) throw ArgError("subset rows must be ascending"); }
+        }
     if (n_trees == 0) return;
     if (cancel && cancel(cancel_arg)) throw Cancelled("The corresponding build process has been cancelled");
 
@@ -541,7 +561,7 @@ void do_build_begin(arroy_ctx* c, uint32_t n_trees, const uint8_t (*seeds)[32], 
         std::vector<BuiltTree> trees;
         uint32_t cap_mult = 1;
         for (;;) {
-            try { build_wave(c, c->pending_waves.size(), t0, tw, seeds, K, cap_mult, cancel, cancel_arg, trees, pool_stride); break; }
+            try { build_wave(c, c->pending_waves.size(), t0, tw, seeds, K, cap_mult, cancel, cancel_arg, trees, pool_stride, sub); break; }
             catch (const CapacityError&) { if (cap_mult >= 64) throw; cap_mult *= 4; }
         }
         c->pending_waves.push_back(std::move(trees));
@@ -565,14 +585,19 @@ void do_build_begin(arroy_ctx* c, uint32_t n_trees, const uint8_t (*seeds)[32], 
 }
 
 // Phase 2: NodeCodec encoding of the parked trees. Non-root node li of tree t gets id base_ids[t] + li.
-void do_build_emit(arroy_ctx* c, const uint32_t* root_ids, const uint64_t* base, arroy_b200_node_sink sink, void* sink_arg) {
+// node_ids (optional): explicit ids of the non-root nodes, concatenated per tree in post-order
+// (tree t contributes n_recs[t] - 1 entries); otherwise node li of tree t gets base[t] + li.
+void do_build_emit(arroy_ctx* c, const uint32_t* root_ids, const uint64_t* base, arroy_b200_node_sink sink, void* sink_arg, const uint32_t* node_ids = nullptr) {
     const uint32_t n_trees = c->pending_n_trees;
     if (n_trees == 0 || !sink) return;
     std::vector<const BuiltTree*> tree_ptr(n_trees);
     for (size_t w = 0; w < c->pending_waves.size(); ++w)
         for (size_t i = 0; i < c->pending_waves[w].size(); ++i) tree_ptr[c->pending_wave_t0[w] + i] = &c->pending_waves[w][i];
-    for (uint32_t t = 0; t < n_trees; ++t)
-        if (base[t] + tree_ptr[t]->n_recs > 0x100000000ull) throw CapacityError("node ids exceed u32 (Error::DatabaseFull)");
+    std::vector<uint64_t> id_off(n_trees + 1, 0);
+    for (uint32_t t = 0; t < n_trees; ++t) id_off[t + 1] = id_off[t] + tree_ptr[t]->n_recs - 1;
+    if (!node_ids)
+        for (uint32_t t = 0; t < n_trees; ++t)
+            if (base[t] + tree_ptr[t]->n_recs > 0x100000000ull) throw CapacityError("node ids exceed u32 (Error::DatabaseFull)");
     const uint32_t pool_stride = c->pending_pool_stride;
     auto t_enc = std::chrono::steady_clock::now();
 
@@ -594,7 +619,7 @@ void do_build_emit(arroy_ctx* c, const uint32_t* root_ids, const uint64_t* base,
                 const Record* recs = static_cast<const Record*>(T.recs);
                 const float* pool = T.pool;
                 const uint32_t root_local = T.n_recs - 1;
-                auto gid = [&](uint32_t li) { return li == root_local ? root_ids[t] : (uint32_t)(base[t] + li); };
+                auto gid = [&](uint32_t li) { return li == root_local ? root_ids[t] : (node_ids ? node_ids[id_off[t] + li] : (uint32_t)(base[t] + li)); };
                 for (uint32_t li = 0; li < T.n_recs; ++li) {
                     const Record& r = recs[li];
                     buf.clear();
@@ -988,6 +1013,21 @@ int32_t arroy_b200_build_trees_emit(arroy_ctx* c, const uint32_t* root_ids, cons
     return guarded(c, [&] {
         if (c->pending_n_trees && (!root_ids || !base_ids)) throw ArgError("null root / base ids");
         do_build_emit(c, root_ids, base_ids, sink, sink_arg);
+    });
+}
+
+int32_t arroy_b200_build_subtrees_begin(arroy_ctx* c, uint32_t n_subtrees, const uint8_t (*seeds)[32], const uint32_t* rows, const uint64_t* row_offsets,
+                                        uint32_t split_after, arroy_b200_cancel_fn cancel, void* cancel_arg, uint32_t* out_node_counts) {
+    return guarded(c, [&] {
+        if (n_subtrees && (!seeds || !rows || !row_offsets)) throw ArgError("null argument");
+        Subsets sub; sub.rows = rows; sub.off = row_offsets;
+        do_build_begin(c, n_subtrees, seeds, split_after, cancel, cancel_arg, out_node_counts, sub);
+    });
+}
+int32_t arroy_b200_build_trees_emit_mapped(arroy_ctx* c, const uint32_t* root_ids, const uint32_t* node_ids, arroy_b200_node_sink sink, void* sink_arg) {
+    return guarded(c, [&] {
+        if (c->pending_n_trees && (!root_ids || !node_ids)) throw ArgError("null root / node ids");
+        do_build_emit(c, root_ids, nullptr, sink, sink_arg, node_ids);
     });
 }
 

@@ -68,6 +68,10 @@ struct BuildParams {
     int32_t use_smem_ws;
     uint32_t* active;        // trees not yet done
     int32_t* error;
+    // optional: tree t is built over the ascending row subset sub_rows[sub_off[t] .. sub_off[t+1])
+    // instead of all n rows (incremental builds: one subtree per over-full descendant)
+    const uint32_t* sub_rows;
+    const uint64_t* sub_off;
 };
 
 __device__ __forceinline__ double split_imbalance_dev(uint32_t l, uint32_t r) {  // src/writer.rs:1348-1353
@@ -369,7 +373,7 @@ __global__ void __launch_bounds__(CTRL_THREADS, 1) control_kernel(BuildParams P,
         if (tid == 0) {
             int action = ACT_NONE;
             if (S.phase == PH_START) {
-                Frame r; r.start = 0; r.len = P.n; r.left_len = 0; r.left_id = 0; r.slot = NO_SLOT; r.parity = 0; r.stage = 0; r.pad = 0;
+                Frame r; r.start = 0; r.len = P.sub_off ? (uint32_t)(P.sub_off[t + 1] - P.sub_off[t]) : P.n; r.left_len = 0; r.left_id = 0; r.slot = NO_SLOT; r.parity = 0; r.stage = 0; r.pad = 0;
                 FR(0) = r; S.sp = 0; S.phase = PH_AWAIT_PART;  // falls into the descend loop below
             } else if (S.phase == PH_AWAIT_SCAN) {
                 Frame& f = FR(S.sp);
@@ -523,7 +527,12 @@ __global__ void init_trees_kernel(BuildParams P, const uint32_t* __restrict__ ke
         P.jobs[t].kind = JOB_NONE;
     }
     uint32_t* perm0 = P.perm[0] + (size_t)t * P.n;
-    for (uint32_t i = threadIdx.x; i < P.n; i += blockDim.x) perm0[i] = i;
+    if (P.sub_off) {
+        const uint64_t b = P.sub_off[t], len = P.sub_off[t + 1] - b;
+        for (uint64_t i = threadIdx.x; i < len; i += blockDim.x) perm0[i] = P.sub_rows[b + i];
+    } else {
+        for (uint32_t i = threadIdx.x; i < P.n; i += blockDim.x) perm0[i] = i;
+    }
 }
 
 }  // namespace ab

@@ -16,6 +16,7 @@
 #include <map>
 #include <memory>
 #include <queue>
+#include <set>
 
 #include "../../include/arroy_b200_host.h"
 
@@ -255,6 +256,201 @@ inline void write_version(arroy_env* env, uint16_t index) {  // version.rs:39-49
     env->kv[make_key(index, MODE_METADATA, 1)] = std::string(reinterpret_cast<const char*>(v), 12);
 }
 
+
+// ---- pieces of the incremental build (src/writer.rs:632-653, :846-889, :978-1160, :1398-1459) ----------
+
+// std HashMap<u32, _, BuildNoHashHasher> as nohash::IntMap gives it to the reference: the order in
+// which `descendants` is iterated decides which seed and which node ids every rebuilt subtree gets
+// (writer.rs:778-795), so the insertion / growth / iteration order of hashbrown's SwissTable is
+// restated here (identity hash: slot = first free bucket at or after id & mask; capacity 3, 7, then
+// buckets / 8 * 7; growth re-inserts in iteration order; iteration = ascending bucket).
+struct IntMapOrder {
+    std::vector<int64_t> keys;
+    std::vector<std::vector<uint32_t>> vals;
+    size_t items = 0;
+    static size_t capacity_of(size_t buckets) { return buckets < 8 ? buckets - 1 : buckets / 8 * 7; }
+    size_t find(uint32_t k) const {
+        if (keys.empty()) return SIZE_MAX;
+        size_t mask = keys.size() - 1, pos = k & mask;
+        for (size_t i = 0; i < keys.size(); ++i) { size_t b = (pos + i) & mask; if (keys[b] == (int64_t)k) return b; if (keys[b] < 0) return SIZE_MAX; }
+        return SIZE_MAX;
+    }
+    void raw_insert(uint32_t k, std::vector<uint32_t>&& v) {
+        size_t mask = keys.size() - 1, pos = k & mask;
+        for (size_t i = 0;; ++i) { size_t b = (pos + i) & mask; if (keys[b] < 0) { keys[b] = k; vals[b] = std::move(v); return; } }
+    }
+    std::vector<uint32_t>& entry(uint32_t k) {
+        size_t f = find(k);
+        if (f != SIZE_MAX) return vals[f];
+        if (keys.empty() || items == capacity_of(keys.size())) {
+            size_t cap = std::max(items + 1, keys.empty() ? (size_t)0 : capacity_of(keys.size()) + 1);
+            size_t nb = cap < 4 ? 4 : (cap < 8 ? 8 : 1);
+            if (nb == 1) { size_t adj = cap * 8 / 7; while (nb < adj) nb <<= 1; }
+            std::vector<int64_t> ok = std::move(keys);
+            std::vector<std::vector<uint32_t>> ov = std::move(vals);
+            keys.assign(nb, -1); vals.assign(nb, {});
+            for (size_t b = 0; b < ok.size(); ++b) if (ok[b] >= 0) raw_insert((uint32_t)ok[b], std::move(ov[b]));
+        }
+        raw_insert(k, {});
+        ++items;
+        return vals[find(k)];
+    }
+    void merge_from(const IntMapOrder& src) {   // for (k, v) in src { self.entry(k).or_default().extend(v) }
+        for (size_t b = 0; b < src.keys.size(); ++b) {
+            if (src.keys[b] < 0) continue;
+            std::vector<uint32_t>& dv = entry((uint32_t)src.keys[b]);
+            std::vector<uint32_t> merged;
+            std::set_union(dv.begin(), dv.end(), src.vals[b].begin(), src.vals[b].end(), std::back_inserter(merged));
+            dv.swap(merged);
+        }
+    }
+};
+
+struct HNode {  // a decoded tree node (src/node.rs:246-282); the normal stays as raw bytes [header | vector]
+    uint8_t kind = 0;
+    uint32_t left = 0, right = 0;
+    std::string normal;             // empty = "normal: none"
+    std::vector<uint32_t> desc;
+};
+inline HNode decode_tree_node(const std::string& v) {
+    HNode n;
+    const uint8_t* b = reinterpret_cast<const uint8_t*>(v.data());
+    if (b[0] == 1) { n.kind = 1; roaring_deserialize(b + 1, v.size() - 1, n.desc); }
+    else if (b[0] == 2) {
+        n.kind = 2;
+        n.left = ((uint32_t)b[1] << 24) | ((uint32_t)b[2] << 16) | ((uint32_t)b[3] << 8) | b[4];
+        n.right = ((uint32_t)b[5] << 24) | ((uint32_t)b[6] << 16) | ((uint32_t)b[7] << 8) | b[8];
+        n.normal.assign(v.data() + 9, v.size() - 9);
+    } else throw HostError(ARROY_ERR_PANIC, "Did not recognize node tag type");
+    return n;
+}
+inline std::string encode_tree_node(const HNode& n) {   // NodeCodec::bytes_encode — src/node.rs:229-241
+    std::string out;
+    if (n.kind == 1) {
+        std::vector<uint8_t> buf;
+        buf.push_back(1);
+        ::roaring_serialize(n.desc.data(), n.desc.size(), buf);
+        out.assign(reinterpret_cast<char*>(buf.data()), buf.size());
+    } else {
+        out.push_back(2);
+        for (int k = 3; k >= 0; --k) out.push_back((char)(n.left >> (8 * k)));
+        for (int k = 3; k >= 0; --k) out.push_back((char)(n.right >> (8 * k)));
+        out += n.normal;
+    }
+    return out;
+}
+
+struct NodeIdAlloc {  // ConcurrentNodeIds — src/parallel.rs:207-255
+    std::vector<uint32_t> available;
+    size_t select = 0;
+    bool look = false;
+    uint64_t current = 0;
+    explicit NodeIdAlloc(const std::map<uint32_t, HNode>& used) {
+        uint32_t last_id = used.empty() ? 0 : used.rbegin()->first + 1;
+        for (uint32_t i = 0; i < last_id; ++i) if (!used.count(i)) available.push_back(i);
+        current = last_id;
+        look = !available.empty();
+    }
+    uint32_t next() {
+        if (look) { if (select < available.size()) return available[select++]; look = false; }
+        if (current > 0xffffffffull) throw HostError(ARROY_ERR_DATABASE_FULL, "Database full. Arroy cannot generate enough internal IDs for your items");
+        return (uint32_t)current++;
+    }
+};
+
+struct IncCtx {
+    arroy_env* env; arroy_ctx* ctx; uint16_t index; int metric; uint32_t d; size_t K;
+    std::map<uint32_t, HNode> tree;                 // the index' tree nodes, kept in sync with env->kv
+    const std::vector<uint32_t>* item_ids;          // ascending ids of the staged items (row = rank)
+    void put(uint32_t id, HNode&& n) { env->kv[make_key(index, MODE_TREE, id)] = encode_tree_node(n); tree[id] = std::move(n); }
+    void erase(uint32_t id) { env->kv.erase(make_key(index, MODE_TREE, id)); tree.erase(id); }
+    uint32_t row_of(uint32_t id) const { return (uint32_t)(std::lower_bound(item_ids->begin(), item_ids->end(), id) - item_ids->begin()); }
+};
+
+inline void inc_delete_tree(IncCtx& C, uint32_t node) {   // writer.rs:1263-1277
+    auto it = C.tree.find(node);
+    if (it == C.tree.end()) return;
+    if (it->second.kind == 2) { uint32_t l = it->second.left, r = it->second.right; inc_delete_tree(C, l); inc_delete_tree(C, r); }
+    C.erase(node);
+}
+
+struct TmpOps { std::vector<std::pair<uint32_t, HNode>> puts; std::set<uint32_t> deleted; };   // TmpNodes put / remove
+
+// delete_items_in_file — writer.rs:1021-1114. second.first = "Some(items)"
+inline std::pair<uint32_t, std::pair<bool, std::vector<uint32_t>>> inc_delete_items(IncCtx& C, uint32_t current, TmpOps& tmp, const std::set<uint32_t>& to_delete) {
+    const HNode& nd = C.tree.at(current);
+    if (nd.kind == 1) {
+        std::vector<uint32_t> nw;
+        for (uint32_t id : nd.desc) if (!to_delete.count(id)) nw.push_back(id);
+        if (nw.size() != nd.desc.size()) { HNode t; t.kind = 1; t.desc = nw; tmp.puts.push_back({current, std::move(t)}); }
+        return {current, {true, nw}};
+    }
+    const uint32_t left = nd.left, right = nd.right;
+    auto L = inc_delete_items(C, left, tmp, to_delete);
+    auto R = inc_delete_items(C, right, tmp, to_delete);
+    const uint32_t nl = L.first, nr = R.first;
+    auto put_split = [&]() { if (nl != left || nr != right) { HNode t = C.tree.at(current); t.left = nl; t.right = nr; tmp.puts.push_back({current, std::move(t)}); } };
+    if (L.second.first && L.second.second.empty()) { tmp.deleted.insert(nl); tmp.deleted.insert(current); return {nr, R.second}; }
+    if (R.second.first && R.second.second.empty()) { tmp.deleted.insert(nr); tmp.deleted.insert(current); return {nl, L.second}; }
+    if (L.second.first && R.second.first) {
+        if (L.second.second.size() + R.second.second.size() <= C.K) {
+            std::vector<uint32_t> all;
+            std::set_union(L.second.second.begin(), L.second.second.end(), R.second.second.begin(), R.second.second.end(), std::back_inserter(all));
+            tmp.deleted.insert(nl); tmp.deleted.insert(nr);
+            HNode t; t.kind = 1; t.desc = all;
+            tmp.puts.push_back({current, std::move(t)});
+            return {current, {true, all}};
+        }
+        put_split();
+        return {current, {false, {}}};
+    }
+    put_split();
+    return {current, {false, {}}};
+}
+
+// insert_items_in_descendants_from_frozen_reader — writer.rs:1398-1459; the side() loop runs on the device
+inline void inc_route(IncCtx& C, ab::Rng& rng, uint32_t node, const std::vector<uint32_t>& to_insert, IntMapOrder& out) {
+    const HNode& nd = C.tree.at(node);
+    if (nd.kind == 1) {
+        std::vector<uint32_t> merged;
+        std::set_union(nd.desc.begin(), nd.desc.end(), to_insert.begin(), to_insert.end(), std::back_inserter(merged));
+        out.entry(node) = merged;
+        return;
+    }
+    std::vector<uint32_t> left, right;
+    if (nd.normal.empty()) {   // randomly_split_children: Side::random = rng.gen::<bool>() ? Left : Right
+        for (uint32_t id : to_insert) { if ((int32_t)rng.next_u32() < 0) left.push_back(id); else right.push_back(id); }
+    } else {
+        const int hf = header_floats(C.metric);
+        float h0 = 0.f, h1 = 0.f;
+        memcpy(&h0, nd.normal.data(), 4);
+        if (hf == 2) memcpy(&h1, nd.normal.data() + 4, 4);
+        std::vector<float> nv(C.d);
+        memcpy(nv.data(), nd.normal.data() + 4 * hf, 4ull * C.d);
+        std::vector<uint32_t> rows(to_insert.size());
+        for (size_t i = 0; i < rows.size(); ++i) rows[i] = C.row_of(to_insert[i]);
+        std::vector<uint8_t> side(rows.size());
+        dev_ck(C.ctx, arroy_b200_side_batch(C.ctx, nv.data(), h0, h1, rows.data(), rows.size(), side.data(), nullptr));
+        for (size_t i = 0; i < rows.size(); ++i) { if (side[i]) right.push_back(to_insert[i]); else left.push_back(to_insert[i]); }
+    }
+    const uint32_t l = nd.left, r = nd.right;
+    if (!left.empty()) inc_route(C, rng, l, left, out);
+    if (!right.empty()) inc_route(C, rng, r, right, out);
+}
+
+inline ab::Rng rng_seed_from_u64(uint64_t state) {   // rand_core 0.6 SeedableRng::seed_from_u64
+    const uint64_t MUL = 6364136223846793005ull, INC = 11634580027462260723ull;
+    uint32_t key[8];
+    for (int c = 0; c < 8; ++c) {
+        state = state * MUL + INC;
+        uint32_t xs = (uint32_t)(((state >> 18) ^ state) >> 27), rot = (uint32_t)(state >> 59);
+        key[c] = (xs >> rot) | (xs << ((32 - rot) & 31));
+    }
+    ab::Rng r;
+    r.init(key, 0);
+    return r;
+}
+
 // The library calls the sink concurrently from its encoder threads; nodes are parked in shards and
 // moved into the ordered table once the build is over (TmpNodes files -> LMDB, writer.rs:597-607).
 struct SinkArg {
@@ -346,20 +542,105 @@ inline void writer_build(arroy_writer* w, arroy_ctx* ctx, arroy_rng* rng, int64_
     bool had = read_metadata(env, index, old);
     std::vector<uint32_t> roots = had ? old.roots : std::vector<uint32_t>();
     const uint64_t target = target_n_trees(n_trees_opt, d, n, roots.size());
-    step("DeletingExtraTrees");
     if (!roots.empty()) {
-        if (updated.empty() && roots.size() == target) {  // nothing changed: the forest stays as it is
-            step("WriteTheMetadata");
-            env->kv[make_key(index, MODE_METADATA, 0)] = encode_metadata(w->metric, d, items.ids, roots);
-            write_version(env, index);
-            w->timings[4] = ms_since(t_all);
-            return;
+        // ---- an index that already has trees: update it in place --------------------------------------
+        IncCtx C{env, ctx, index, w->metric, d, (size_t)K, {}, &items.ids};
+        {
+            auto it = env->kv.lower_bound(make_key(index, MODE_TREE, 0));
+            for (; it != env->kv.end() && it->first[0] == (uint8_t)(index >> 8) && it->first[1] == (uint8_t)index && it->first[2] == MODE_TREE; ++it)
+                C.tree[key_item(it->first)] = decode_tree_node(it->second);
         }
-        // Incremental insert/delete in existing trees (writer.rs:846-889, :978-1114) is row "next #3"
-        // of SURVEY.md §8f: until it lands the forest is rebuilt from scratch, which yields a valid
-        // (but not snapshot-identical) index.
-        erase_mode(env, index, MODE_TREE);
-        roots.clear();
+        step("RetrievingTheUsedTreeNodes");
+        NodeIdAlloc alloc(C.tree);
+        step("DeletingExtraTrees");
+        {   // writer.rs:632-653
+            size_t extraneous = roots.size() > target ? roots.size() - (size_t)target : 0;
+            for (size_t i = 0; i < extraneous && !roots.empty(); ++i) { cancelled(); uint32_t r0 = roots[0]; roots[0] = roots.back(); roots.pop_back(); inc_delete_tree(C, r0); }
+        }
+        step("RemoveItemsFromExistingTrees");
+        const std::set<uint32_t> to_delete(updated.begin(), updated.end());
+        {   // writer.rs:978-1015
+            TmpOps tmp;
+            for (uint32_t& root : roots) { cancelled(); root = inc_delete_items(C, root, tmp, to_delete).first; }
+            std::sort(roots.begin(), roots.end());
+            for (uint32_t id : tmp.deleted) C.erase(id);
+            for (auto& pr : tmp.puts) if (!tmp.deleted.count(pr.first)) C.put(pr.first, HNode(pr.second));
+        }
+        step("InsertItemsInCurrentTrees");
+        std::vector<uint32_t> to_insert;
+        for (uint32_t id : updated) if (std::binary_search(items.ids.begin(), items.ids.end(), id)) to_insert.push_back(id);
+        IntMapOrder top;
+        if (!roots.empty() && !to_insert.empty()) {   // writer.rs:846-889, :1119-1160 (rayon reduce on a 1-thread pool: one split at len / 2)
+            const uint64_t seed = rng->r.next_u64();
+            auto fold = [&](size_t a, size_t b) {
+                IntMapOrder acc;
+                for (size_t i = a; i < b; ++i) {
+                    cancelled();
+                    ab::Rng rr = rng_seed_from_u64(seed + (uint64_t)roots[i]);
+                    IntMapOrder per_root;
+                    inc_route(C, rr, roots[i], to_insert, per_root);
+                    acc.merge_from(per_root);
+                }
+                return acc;
+            };
+            IntMapOrder reduced;
+            if (roots.size() >= 2) { size_t mid = roots.size() / 2; reduced = fold(0, mid); IntMapOrder right = fold(mid, roots.size()); reduced.merge_from(right); }
+            else reduced = fold(0, roots.size());
+            top.merge_from(reduced);
+        }
+        step("RetrieveTheLargeDescendants");
+        const uint64_t nb_missing = target > roots.size() ? target - roots.size() : 0;
+        for (uint64_t i = 0; i < nb_missing; ++i) { uint32_t nid = alloc.next(); roots.push_back(nid); top.entry(nid) = items.ids; }
+        // writer.rs:575 + insert_descendants_in_file_and_spawn_tasks (:744-844) in hashbrown order
+        uint8_t s1[32];
+        rng->r.gen_seed(s1);
+        uint32_t key1[8];
+        for (int i = 0; i < 8; ++i) key1[i] = (uint32_t)s1[4 * i] | ((uint32_t)s1[4 * i + 1] << 8) | ((uint32_t)s1[4 * i + 2] << 16) | ((uint32_t)s1[4 * i + 3] << 24);
+        ab::Rng rng1;
+        rng1.init(key1, 0);
+        std::vector<std::array<uint8_t, 32>> task_seeds;
+        std::vector<uint32_t> task_ids, sub_rows;
+        std::vector<uint64_t> sub_off(1, 0);
+        for (size_t b = 0; b < top.keys.size(); ++b) {
+            if (top.keys[b] < 0) continue;
+            cancelled();
+            const uint32_t id = (uint32_t)top.keys[b];
+            std::vector<uint32_t>& ids_v = top.vals[b];
+            if (ids_v.size() <= K) { HNode t; t.kind = 1; t.desc = ids_v; C.put(id, std::move(t)); }
+            else {
+                task_seeds.emplace_back();
+                rng1.gen_seed(task_seeds.back().data());
+                task_ids.push_back(id);
+                for (uint32_t iid : ids_v) sub_rows.push_back(C.row_of(iid));
+                sub_off.push_back(sub_rows.size());
+            }
+        }
+        step("CreateTreesForItems");
+        t0 = clk::now();
+        SinkArg sa;
+        if (!task_ids.empty()) {
+            const uint32_t ns = (uint32_t)task_ids.size();
+            std::vector<uint32_t> counts(ns, 0);
+            dev_ck(ctx, arroy_b200_build_subtrees_begin(ctx, ns, reinterpret_cast<const uint8_t(*)[32]>(task_seeds.data()), sub_rows.data(), sub_off.data(),
+                                                       (uint32_t)split_after, cancel, cancel_arg, counts.data()));
+            // the spawned tasks run LIFO on a 1-thread pool; each takes its ids from the allocator in post-order
+            std::vector<uint64_t> id_off(ns + 1, 0);
+            for (uint32_t sidx = 0; sidx < ns; ++sidx) id_off[sidx + 1] = id_off[sidx] + counts[sidx] - 1;
+            std::vector<uint32_t> node_ids(id_off[ns]);
+            for (uint32_t k2 = 0; k2 < ns; ++k2) { uint32_t sidx = ns - 1 - k2; for (uint64_t j = 0; j + 1 < counts[sidx]; ++j) node_ids[id_off[sidx] + j] = alloc.next(); }
+            dev_ck(ctx, arroy_b200_build_trees_emit_mapped(ctx, task_ids.data(), node_ids.data(), tree_sink, &sa));
+            std::vector<std::pair<uint32_t, std::string>> all;
+            for (int sh = 0; sh < SinkArg::SHARDS; ++sh) { for (auto& e : sa.nodes[sh]) all.emplace_back(std::move(e)); sa.nodes[sh].clear(); }
+            for (auto& e : all) env->kv[make_key(index, MODE_TREE, e.first)] = std::move(e.second);
+        }
+        w->timings[2] = ms_since(t0);
+        w->timings[6] = (double)sa.bytes.load();
+        step("WriteTheMetadata");
+        env->kv[make_key(index, MODE_METADATA, 0)] = encode_metadata(w->metric, d, items.ids, roots);
+        write_version(env, index);
+        env->generation++;
+        w->timings[4] = ms_since(t_all);
+        return;
     }
     step("RetrievingTheItems");
     step("RetrieveTheLargeDescendants");

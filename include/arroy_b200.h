@@ -150,6 +150,20 @@ int32_t arroy_b200_build_trees_begin(arroy_ctx* ctx, uint32_t n_trees, const uin
 int32_t arroy_b200_build_trees_emit(arroy_ctx* ctx, const uint32_t* root_ids, const uint64_t* base_ids,
                                     arroy_b200_node_sink sink, void* sink_arg);
 
+/* Incremental builds (src/writer.rs:778-829): after new items were routed down the existing trees,
+ * every Descendants node that outgrew split_after is rebuilt as a subtree over ITS items only.
+ * subtree s is built over the ascending rows rows[row_offsets[s] .. row_offsets[s+1]) (more than
+ * split_after of them) with its own seed; counts as for arroy_b200_build_trees_begin. The nodes are
+ * then emitted with caller-chosen ids (the reference takes them from ConcurrentNodeIds, which
+ * re-uses freed ids first, src/parallel.rs:238-254): the subtree's root gets root_ids[s] (the id of
+ * the descendant it replaces), its other nodes node_ids[...] in post-order, all subtrees
+ * concatenated (subtree s contributes counts[s] - 1 ids). */
+int32_t arroy_b200_build_subtrees_begin(arroy_ctx* ctx, uint32_t n_subtrees, const uint8_t (*seeds)[32],
+                                        const uint32_t* rows, const uint64_t* row_offsets, uint32_t split_after,
+                                        arroy_b200_cancel_fn cancel, void* cancel_arg, uint32_t* out_node_counts);
+int32_t arroy_b200_build_trees_emit_mapped(arroy_ctx* ctx, const uint32_t* root_ids, const uint32_t* node_ids,
+                                           arroy_b200_node_sink sink, void* sink_arg);
+
 /* Statistics of the last build on this context (for roofline accounting):
  * stats[0] = rows that went through side() (sum over scans, retries included)
  * stats[1] = device steps, stats[2] = create_split calls, stats[3] = random-fallback splits,

@@ -152,26 +152,3 @@ def test_forest_and_queries_match_the_oracle_end_to_end(env_factory, metric, n, 
         os.environ.pop("ARROY_B200_HOST_WALK")
     d_ids, d_dist, d_len, _ = r.nns_batch_by_item(qitems, 10)
     assert h_len.tolist() == d_len.tolist() and h_ids.tolist() == d_ids.tolist() and h_dist.tobytes() == d_dist.tobytes()
-
-
-def test_rebuild_after_update_gives_a_valid_index(env_factory):
-    # incremental insertion is not restated yet: an update triggers a full rebuild
-    n, d = 3000, 32
-    data = oracle.synth_rows(SEED, d, 0, n, 0.5)
-    env = env_factory()
-    w = ab.Writer(env, 0, d, "cosine")
-    w.add_items(np.arange(n, dtype=np.uint32), data)
-    rng = rng42()
-    w.builder(rng).n_trees(4).build()
-    w.add_item(n, oracle.synth_rows(SEED, d, n, 1, 0.5)[0])
-    w.del_item(5)
-    assert w.need_build()
-    w.builder(rng).n_trees(4).build()
-    r = ab.Reader.open(env, 0, "cosine")
-    assert r.n_items() == n and 5 not in r.item_ids() and n in r.item_ids()
-    st = r.stats()
-    nodes = env.tree_nodes()
-    seen = sorted(i for b in nodes.values() if b[0] == 1 for i in oracle.roaring_deserialize(b[1:]))
-    assert len(seen) == 4 * n and all(t["depth"] > 1 for t in st["tree_stats"])
-    res = r.nns(3).by_item(n)
-    assert res[0] == (n, 0.0)
