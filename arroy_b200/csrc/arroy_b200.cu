@@ -359,7 +359,7 @@ void build_wave(arroy_ctx* c, size_t wave_no, uint32_t t0, uint32_t tw, const ui
     c->n_launches += 2;  // + finalize_kernel below
 
     const size_t ctrl_smem = use_smem ? ws_bytes : 0;
-    if (ctrl_smem > 48 * 1024) CK(cudaFuncSetAttribute(control_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctrl_smem));
+    if (ctrl_smem > 48 * 1024) CK(cudaFuncSetAttribute(control_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctrl_smem));
     const size_t wsmem = work_smem(ld, (int)tw);
     if (wsmem > 48 * 1024) CK(cudaFuncSetAttribute(work_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
     const int work_grid = c->sm_count * 3;
@@ -380,11 +380,11 @@ void build_wave(arroy_ctx* c, size_t wave_no, uint32_t t0, uint32_t tw, const ui
     const size_t wsmem1 = work_smem(ld, 1);
 
     auto launch_step = [&](cudaStream_t s) {  // lockstep: all trees per launch
-        control_kernel<<<tw, CTRL_THREADS, ctrl_smem, s>>>(P, 0u);
+        if (use_smem) control_kernel<true><<<tw, CTRL_THREADS, ctrl_smem, s>>>(P, 0u); else control_kernel<false><<<tw, CTRL_THREADS, 0, s>>>(P, 0u);
         work_kernel<<<work_grid, WORK_THREADS, wsmem, s>>>(P.jobs, (int)tw, P.items, P.ih0, P.d, P.ld, P.metric, interleave);
     };
     auto launch_tree_step = [&](uint32_t t, cudaStream_t s) {  // async: one tree per launch
-        control_kernel<<<1, CTRL_THREADS, ctrl_smem, s>>>(P, t);
+        if (use_smem) control_kernel<true><<<1, CTRL_THREADS, ctrl_smem, s>>>(P, t); else control_kernel<false><<<1, CTRL_THREADS, 0, s>>>(P, t);
         work_kernel<<<tree_grid, WORK_THREADS, wsmem1, s>>>(P.jobs + t, 1, P.items, P.ih0, P.d, P.ld, P.metric, 0);
     };
     if (!lockstep) {
@@ -447,7 +447,7 @@ void build_wave(arroy_ctx* c, size_t wave_no, uint32_t t0, uint32_t tw, const ui
         if (use_graph) CK(cudaGraphLaunch(gexec, c->stream));
         else if (profile) {
             for (int i = 0; i < steps_per_batch; ++i) {
-                control_kernel<<<tw, CTRL_THREADS, ctrl_smem, c->stream>>>(P, 0u);
+                if (use_smem) control_kernel<true><<<tw, CTRL_THREADS, ctrl_smem, c->stream>>>(P, 0u); else control_kernel<false><<<tw, CTRL_THREADS, 0, c->stream>>>(P, 0u);
                 CK(cudaEventRecord(pev[2 * i], c->stream));
                 work_kernel<<<work_grid, WORK_THREADS, wsmem, c->stream>>>(P.jobs, (int)tw, P.items, P.ih0, P.d, P.ld, P.metric, interleave);
                 CK(cudaEventRecord(pev[2 * i + 1], c->stream));
@@ -767,14 +767,15 @@ void do_rerank_batch(arroy_ctx* c, uint32_t nq, const float* queries, const floa
 
 // single-CTA create_split over a host row list (exposes D::create_split for parity tests and for
 // hosts that keep the DFS on their side)
+template <bool SMEM_WS>
 __global__ void __launch_bounds__(CTRL_THREADS, 1) create_split_kernel(BuildParams P, const uint32_t* rows, uint32_t len, const uint32_t* key8, uint64_t pos, float* slot, uint64_t* out_pos) {
     extern __shared__ __align__(16) unsigned char cs_smem[];
     __shared__ TwoMeansShared TM;
     __shared__ Rng rng;
-    float* ws = P.use_smem_ws ? reinterpret_cast<float*>(cs_smem) : P.scratch;
     if (threadIdx.x == 0) rng.init(key8, pos);
     __syncthreads();
-    create_split_cta(P, rng, rows, len, ws, TM, slot);
+    if (SMEM_WS) create_split_cta(P, rng, rows, len, reinterpret_cast<float*>(cs_smem), TM, slot);
+    else create_split_cta(P, rng, rows, len, P.scratch, TM, slot);
     if (threadIdx.x == 0) *out_pos = rng.pos;
 }
 
@@ -979,9 +980,13 @@ int32_t arroy_b200_create_split(arroy_ctx* c, const uint32_t rng_key[8], uint64_
         P.use_smem_ws = ws_bytes <= 200 * 1024;
         P.scratch = reinterpret_cast<float*>(c->s_misc.as<uint8_t>() + 64);
         size_t smem = P.use_smem_ws ? ws_bytes : 0;
-        if (smem > 48 * 1024) CK(cudaFuncSetAttribute(create_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        create_split_kernel<<<1, CTRL_THREADS, smem, c->stream>>>(P, c->s_rows.as<uint32_t>(), (uint32_t)n_rows, c->s_misc.as<uint32_t>(), *rng_word_pos,
-                                                                  c->s_normal.as<float>(), reinterpret_cast<uint64_t*>(c->s_misc.as<uint8_t>() + 32));
+        if (smem > 48 * 1024) CK(cudaFuncSetAttribute(create_split_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (P.use_smem_ws)
+            create_split_kernel<true><<<1, CTRL_THREADS, smem, c->stream>>>(P, c->s_rows.as<uint32_t>(), (uint32_t)n_rows, c->s_misc.as<uint32_t>(), *rng_word_pos,
+                                                                            c->s_normal.as<float>(), reinterpret_cast<uint64_t*>(c->s_misc.as<uint8_t>() + 32));
+        else
+            create_split_kernel<false><<<1, CTRL_THREADS, 0, c->stream>>>(P, c->s_rows.as<uint32_t>(), (uint32_t)n_rows, c->s_misc.as<uint32_t>(), *rng_word_pos,
+                                                                          c->s_normal.as<float>(), reinterpret_cast<uint64_t*>(c->s_misc.as<uint8_t>() + 32));
         CK(cudaGetLastError());
         std::vector<float> slot(ld + NORMAL_HDR);
         uint64_t new_pos = 0;

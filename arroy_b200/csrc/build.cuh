@@ -94,41 +94,22 @@ struct TwoMeansShared {
     float misc[2];
 };
 
-// D::non_built_distance on one 8-lane group — mod.rs:54-56 (= built_distance) except dot_product.rs:58-70.
-// Manhattan is handled by the caller (strictly sequential sum).
-__device__ __forceinline__ float nbd_group(int metric, const float* p, float ph0, float ph1, const float* k, float kh0, float kh1, int d) {
-    if (metric == EUCLIDEAN) return exact_group8<true>(p, k, d);
-    float pq = exact_group8<false>(p, k, d);
-    if (metric == COSINE) return built_finish(COSINE, pq, ph0, kh0);
-    float pp = ph1, qq = kh1;  // DOT_PRODUCT
-    pq = __fadd_rn(pq, __fmul_rn(ph0, kh0));
-    float ppqq = __fmul_rn(pp, qq);
-    if (ppqq >= 1.17549435e-38f) return __fsub_rn(2.0f, __fdiv_rn(__fmul_rn(2.0f, pq), __fsqrt_rn(ppqq)));
-    return 2.0f;
-}
 __device__ __forceinline__ float norm_leaf_group(int metric, const float* v, float h0, int d) {
     float dot = exact_group8<false>(v, v, d);
     if (metric == DOT_PRODUCT) return __fsqrt_rn(__fadd_rn(dot, __fmul_rn(h0, h0)));  // dot_product.rs:72-75
     return __fsqrt_rn(dot);                                                              // mod.rs:70-72
 }
-// D::init of p (group 0) and q (group 1) by warp 0 — cosine.rs:69-71, dot_product.rs:94-96
-__device__ __forceinline__ void init_pq_warp0(int metric, const float* p, const float* q, TwoMeansShared& S, int d, bool do_p, bool do_q) {
-    if (metric != COSINE && metric != DOT_PRODUCT) return;
-    const int lane = threadIdx.x & 31, grp = lane >> 3;
-    const float* v = (grp & 1) ? q : p;
-    float x = exact_group8<false>(v, v, d);
-    if (metric == COSINE) x = __fsqrt_rn(x);
-    const int slot = metric == COSINE ? 0 : 1;
-    if (lane == 0 && do_p) S.php[slot] = x;
-    if (lane == 8 && do_q) S.phq[slot] = x;
-    __syncwarp();
-}
-
 // Draws the RNG exactly like choose_two + 10 x choose (src/parallel.rs:342-367), runs
 // two_means and the metric's create_split, writes the normal into `slot_ptr`
-// ([h0,h1,0,0,v[ld]]). seg = the node's ascending id list.
-__device__ void create_split_cta(const BuildParams& P, Rng& rng /* thread 0 only */, const uint32_t* seg, uint32_t len,
-                                 float* ws, TwoMeansShared& S, float* slot_ptr) {
+// ([h0,h1,0,0,v[ld]]). seg = the node's ascending id list. `ws` is the 14-vector workspace
+// (shared memory in practice: the function is force-inlined so the loads become LDS).
+//
+// Latency matters here (this is the serial part of every tree's chain), so each two_means iteration
+// is ONE dot phase: warp 0 computes p.k, q.k and — for a centroid that was just moved — its D::init
+// dot (p.p / q.q) on four 8-lane groups at the same time, then one barrier, the element-wise
+// update_mean on all threads, one barrier.
+__device__ __forceinline__ void create_split_cta(const BuildParams& P, Rng& rng /* thread 0 only */, const uint32_t* seg, uint32_t len,
+                                                 float* ws, TwoMeansShared& S, float* slot_ptr) {
     const int d = (int)P.d, ld = (int)P.ld, metric = P.metric;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, grp = lane >> 3;
     const bool cosine = (metric == COSINE || metric == DOT_PRODUCT);
@@ -142,17 +123,25 @@ __device__ void create_split_cta(const BuildParams& P, Rng& rng /* thread 0 only
     uint32_t my_row = 0;
     if (tid < 12) my_row = seg[S.rows[tid]];  // RoaringBitmap::select(rank) on the ascending id list
     __syncthreads();
-    if (tid < 12) { S.rows[tid] = my_row; S.h0[tid] = P.ih0 ? P.ih0[my_row] : 0.f; S.h1[tid] = P.ih1 ? P.ih1[my_row] : 0.f; }
+    if (tid < 12) S.rows[tid] = my_row;
     __syncthreads();
-    {   // gather the 12 rows (float4, all loads independent)
+    {   // gather: warp w copies rows w and w + 8; all loads of a thread are issued before any store
+        if (tid < 12) { S.h0[tid] = P.ih0 ? P.ih0[my_row] : 0.f; S.h1[tid] = P.ih1 ? P.ih1[my_row] : 0.f; }
         const int l4 = ld >> 2;
-        for (int i = tid; i < 12 * l4; i += blockDim.x) {
-            int j = i / l4, c = i - j * l4;
-            reinterpret_cast<float4*>(ws + (size_t)j * ld)[c] = __ldg(reinterpret_cast<const float4*>(P.items + (size_t)S.rows[j] * ld) + c);
+        for (int j = warp; j < 12; j += 8) {
+            const float4* src = reinterpret_cast<const float4*>(P.items + (size_t)S.rows[j] * ld);
+            float4* dst = reinterpret_cast<float4*>(ws + (size_t)j * ld);
+            for (int c0 = lane; c0 < l4; c0 += 32 * 8) {
+                float4 v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) { int c = c0 + 32 * u; if (c < l4) v[u] = __ldg(src + c); }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) { int c = c0 + 32 * u; if (c < l4) dst[c] = v[u]; }
+            }
         }
-        if (tid == 0) { S.php[0] = S.h0[0]; S.php[1] = S.h1[0]; S.phq[0] = S.h0[1]; S.phq[1] = S.h1[1]; }
     }
     __syncthreads();
+    if (tid == 0) { S.php[0] = S.h0[0]; S.php[1] = S.h1[0]; S.phq[0] = S.h0[1]; S.phq[1] = S.h1[1]; }
     float* p = ws; float* q = ws + ld;
     float* sc0 = ws + (size_t)12 * ld; float* sc1 = ws + (size_t)13 * ld;
     if (cosine) {
@@ -171,10 +160,10 @@ __device__ void create_split_cta(const BuildParams& P, Rng& rng /* thread 0 only
             if (np > 0.0f) S.php[0] = __fdiv_rn(S.php[0], np);
             if (nq > 0.0f) S.phq[0] = __fdiv_rn(S.phq[0], nq);
         }
-        __syncthreads();
     }
-    if (warp == 0) init_pq_warp0(metric, p, q, S, d, true, true);
+    __syncthreads();
     float ic = 1.0f, jc = 1.0f;
+    bool p_dirty = cosine, q_dirty = cosine;   // D::init pending (cosine.rs:69-71, dot_product.rs:94-96)
     for (int it = 0; it < 10; ++it) {
         const float* k = ws + (size_t)(2 + it) * ld;
         const float kh0 = S.h0[2 + it], kh1 = S.h1[2 + it];
@@ -193,33 +182,51 @@ __device__ void create_split_cta(const BuildParams& P, Rng& rng /* thread 0 only
                 for (; i < d; ++i) s = __fadd_rn(s, t[i]);
                 S.res[it & 1][tid] = __fmul_rn(tid ? jc : ic, s);
             }
-        } else if (warp == 0) {  // di on group 0, dj on group 1 (groups 2, 3 mirror them)
-            const bool second = (grp & 1) != 0;
-            float x = nbd_group(metric, second ? q : p, second ? S.phq[0] : S.php[0], second ? S.phq[1] : S.php[1], k, kh0, kh1, d);
-            if (lane == 0) S.res[it & 1][0] = __fmul_rn(ic, x);
-            if (lane == 8) S.res[it & 1][1] = __fmul_rn(jc, x);
+        } else if (warp == 0) {
+            // group 0: p.k   group 1: q.k   group 2: p.p   group 3: q.q  (Euclidean: (p-k)^2, (q-k)^2 only)
+            const float* a = (grp & 1) ? q : p;
+            const float* b = (grp < 2) ? k : a;
+            float x = (metric == EUCLIDEAN) ? exact_group8<true>((grp & 1) ? q : p, k, d) : exact_group8<false>(a, b, d);
+            const float pk = __shfl_sync(0xffffffffu, x, 0), qk = __shfl_sync(0xffffffffu, x, 8);
+            const float pp = __shfl_sync(0xffffffffu, x, 16), qq = __shfl_sync(0xffffffffu, x, 24);
+            if (lane == 0) {
+                float ph0 = S.php[0], ph1 = S.php[1], qh0 = S.phq[0], qh1 = S.phq[1];
+                if (p_dirty) { if (metric == COSINE) ph0 = __fsqrt_rn(pp); else ph1 = pp; S.php[0] = ph0; S.php[1] = ph1; }
+                if (q_dirty) { if (metric == COSINE) qh0 = __fsqrt_rn(qq); else qh1 = qq; S.phq[0] = qh0; S.phq[1] = qh1; }
+                float di, dj;   // D::non_built_distance — mod.rs:54-56 (= built_distance) except dot_product.rs:58-70
+                if (metric == EUCLIDEAN) { di = pk; dj = qk; }
+                else if (metric == COSINE) { di = built_finish(COSINE, pk, ph0, kh0); dj = built_finish(COSINE, qk, qh0, kh0); }
+                else {
+                    float a1 = __fadd_rn(pk, __fmul_rn(ph0, kh0)), a2 = __fadd_rn(qk, __fmul_rn(qh0, kh0));
+                    float m1 = __fmul_rn(ph1, kh1), m2 = __fmul_rn(qh1, kh1);
+                    di = (m1 >= 1.17549435e-38f) ? __fsub_rn(2.0f, __fdiv_rn(__fmul_rn(2.0f, a1), __fsqrt_rn(m1))) : 2.0f;
+                    dj = (m2 >= 1.17549435e-38f) ? __fsub_rn(2.0f, __fdiv_rn(__fmul_rn(2.0f, a2), __fsqrt_rn(m2))) : 2.0f;
+                }
+                S.res[it & 1][0] = __fmul_rn(ic, di);
+                S.res[it & 1][1] = __fmul_rn(jc, dj);
+            }
         }
+        p_dirty = false; q_dirty = false;
         __syncthreads();
         const float di = S.res[it & 1][0], dj = S.res[it & 1][1];
         const float norm = cosine ? S.nk[2 + it] : 1.0f;
         if (norm != norm || norm <= 0.0f) continue;
-        if (di < dj) {        // update_mean(p, k, norm, ic) — mod.rs:86-94
+        if (di < dj) {        // update_mean(p, k, norm, ic) — mod.rs:86-94; D::init follows in the next dot phase
             const float c1 = __fadd_rn(ic, 1.0f);
             for (int i = tid; i < d; i += blockDim.x) p[i] = __fdiv_rn(__fadd_rn(__fmul_rn(p[i], ic), __fdiv_rn(k[i], norm)), c1);
-            ic = c1;
+            ic = c1; p_dirty = cosine;
             __syncthreads();
-            if (warp == 0) init_pq_warp0(metric, p, q, S, d, true, false);
         } else if (dj < di) {
             const float c1 = __fadd_rn(jc, 1.0f);
             for (int i = tid; i < d; i += blockDim.x) q[i] = __fdiv_rn(__fadd_rn(__fmul_rn(q[i], jc), __fdiv_rn(k[i], norm)), c1);
-            jc = c1;
+            jc = c1; q_dirty = cosine;
             __syncthreads();
-            if (warp == 0) init_pq_warp0(metric, p, q, S, d, false, true);
         }
     }
     __syncthreads();
     // normal = normalize(p - q) (+ bias / extra_dim) — euclidean.rs:59-75, manhattan.rs:62-78,
-    // cosine.rs:77-83, dot_product.rs:102-111
+    // cosine.rs:77-83, dot_product.rs:102-111. (A D::init still pending after the last update only
+    // touches the centroid's norm header, which create_split does not read.)
     float* nv = sc0;
     for (int i = tid; i < ld; i += blockDim.x) nv[i] = i < d ? __fsub_rn(p[i], q[i]) : 0.f;
     float extra = (metric == DOT_PRODUCT) ? __fsub_rn(S.php[0], S.phq[0]) : 0.f;
@@ -329,6 +336,7 @@ __device__ uint32_t cta_exclusive_scan(uint32_t* v, uint32_t n, uint32_t* sm_tmp
 
 enum : int { ACT_NONE = 0, ACT_SPLIT = 1, ACT_PART_INLINE = 2, ACT_RANDOM = 3, ACT_EXIT = 4 };
 
+template <bool SMEM_WS>
 __global__ void __launch_bounds__(CTRL_THREADS, 1) control_kernel(BuildParams P, uint32_t tree_base) {
     extern __shared__ __align__(16) unsigned char ctrl_smem[];
     __shared__ TwoMeansShared TM;
@@ -357,7 +365,6 @@ __global__ void __launch_bounds__(CTRL_THREADS, 1) control_kernel(BuildParams P,
     uint32_t* perm1 = P.perm[1] + (size_t)t * P.n;
     uint8_t* flags = P.flags + (size_t)t * P.n;
     uint32_t* unit_left = P.unit_left + (size_t)t * P.units_per_tree;
-    float* ws = P.use_smem_ws ? reinterpret_cast<float*>(ctrl_smem) : P.scratch + (size_t)t * WS_VECS * P.ld;
     const int tid = threadIdx.x;
 
     if (tid == 0) { s_rng.init(S.key, S.pos); job.kind = JOB_NONE; }
@@ -450,7 +457,8 @@ __global__ void __launch_bounds__(CTRL_THREADS, 1) control_kernel(BuildParams P,
         uint32_t* dst = (f.parity ? perm0 : perm1) + f.start;
         if (action == ACT_SPLIT) {
             float* slot_ptr = P.pool + (size_t)S.cur_slot * P.pool_stride;
-            create_split_cta(P, s_rng, src, f.len, ws, TM, slot_ptr);
+            if (SMEM_WS) create_split_cta(P, s_rng, src, f.len, reinterpret_cast<float*>(ctrl_smem), TM, slot_ptr);
+            else create_split_cta(P, s_rng, src, f.len, P.scratch + (size_t)t * WS_VECS * P.ld, TM, slot_ptr);
             if (tid == 0) {
                 S.n_splits_tried += 1;
                 job.kind = JOB_SCAN; job.len = f.len; job.rows = src; job.normal = slot_ptr;

@@ -11,6 +11,7 @@ Workloads (BASELINE.json configs; SURVEY.md §8d synthetic data: element (i,j) =
 number i*d+j of StdRng::from_seed([42;32]) minus 0.5; build rng = fresh StdRng([42;32])):
   c2 (default)  1 000 000 x 768  Cosine      n_trees = 50    <- BASELINE.json configs[1]
   c3            10 000 000 x 768 DotProduct  n_trees = 100
+  c4            10 000 000 x 1536 Cosine     n_trees = 100   (meant for 8 GPUs)
   c1            10 000 x 64      Euclidean   n_trees = 10    (raw [0,1) data)
   small         100 000 x 768    Cosine      n_trees = 16    (quick check)
 
@@ -34,6 +35,7 @@ SEED = bytes([42] * 32)
 WORKLOADS = {
     "c2": dict(n=1_000_000, d=768, metric="cosine", n_trees=50, centre=0.5, name="C2 1Mx768 Cosine n_trees=50"),
     "c3": dict(n=10_000_000, d=768, metric="dot-product", n_trees=100, centre=0.5, name="C3 10Mx768 DotProduct n_trees=100"),
+    "c4": dict(n=10_000_000, d=1536, metric="cosine", n_trees=100, centre=0.5, name="C4 10Mx1536 Cosine n_trees=100"),
     "c1": dict(n=10_000, d=64, metric="euclidean", n_trees=10, centre=0.0, name="C1 10kx64 Euclidean n_trees=10"),
     "small": dict(n=100_000, d=768, metric="cosine", n_trees=16, centre=0.5, name="small 100kx768 Cosine n_trees=16"),
 }
