@@ -34,6 +34,7 @@ SIGNATURES = [
     ("arroy_b200_item_headers", C.c_int32, [C.c_void_p, _f32p, _f32p]),
     ("arroy_b200_dot_preprocess", C.c_int32, [C.c_void_p, _f32p, _f32p]),
     ("arroy_b200_side_batch", C.c_int32, [C.c_void_p, _f32p, C.c_float, C.c_float, _u32p, C.c_uint64, _u8p, _f32p]),
+    ("arroy_b200_side_multi", C.c_int32, [C.c_void_p, C.c_uint32, _f32p, _f32p, _f32p, _u32p, _u64p, _u8p]),
     ("arroy_b200_create_split", C.c_int32, [C.c_void_p, _u32p, _u64p, _u32p, C.c_uint64, _f32p, _f32p]),
     ("arroy_b200_build_trees", C.c_int32, [C.c_void_p, C.c_uint32, C.c_void_p, _u32p, C.c_uint32, C.c_uint32, CANCEL_FN, C.c_void_p, NODE_SINK, C.c_void_p, _u64p]),
     ("arroy_b200_build_trees_begin", C.c_int32, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, CANCEL_FN, C.c_void_p, _u32p]),

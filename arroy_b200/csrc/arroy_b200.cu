@@ -961,6 +961,56 @@ int32_t arroy_b200_side_batch(arroy_ctx* c, const float* normal, float hdr0, flo
     });
 }
 
+int32_t arroy_b200_side_multi(arroy_ctx* c, uint32_t n_jobs, const float* normals, const float* hdr0, const float* hdr1,
+                              const uint32_t* rows, const uint64_t* row_offsets, uint8_t* out_side) {
+    return guarded(c, [&] {
+        (void)hdr1;
+        require_staged(c); set_device(c);
+        if (n_jobs == 0) return;
+        if (!normals || !hdr0 || !rows || !row_offsets || !out_side) throw ArgError("null argument");
+        const uint64_t total = row_offsets[n_jobs];
+        for (uint32_t j = 0; j < n_jobs; ++j) if (row_offsets[j + 1] < row_offsets[j] || row_offsets[j + 1] - row_offsets[j] > 0xffffffffull) throw ArgError("bad row_offsets");
+        for (uint64_t i = 0; i < total; ++i) if (rows[i] >= c->n) throw ArgError("row index out of range");
+        if (total == 0) return;
+        const uint32_t ld = c->ld, slot = ld + NORMAL_HDR;
+        // jobs per launch bounded by the shared-memory unit-prefix table of work_kernel
+        const uint32_t max_jobs = 40000;
+        c->s_rows.ensure(4ull * total);
+        c->s_flags.ensure(total);
+        CK(cudaMemcpyAsync(c->s_rows.p, rows, 4ull * total, cudaMemcpyHostToDevice, c->stream));
+        std::vector<float> slots;
+        std::vector<Job> jobs;
+        for (uint32_t j0 = 0; j0 < n_jobs; j0 += max_jobs) {
+            const uint32_t m = std::min(max_jobs, n_jobs - j0);
+            slots.assign((size_t)m * slot, 0.f);
+            jobs.assign(m, Job{});
+            c->s_normal.ensure((size_t)m * slot * 4);
+            c->s_job.ensure(sizeof(Job) * m);
+            uint64_t units = 0;
+            for (uint32_t j = 0; j < m; ++j) {
+                float* sp = slots.data() + (size_t)j * slot;
+                sp[0] = hdr0[j0 + j];
+                memcpy(sp + NORMAL_HDR, normals + (size_t)(j0 + j) * c->dim, 4ull * c->dim);
+                Job& jb = jobs[j];
+                const uint64_t b = row_offsets[j0 + j], len = row_offsets[j0 + j + 1] - b;
+                jb.kind = len ? JOB_SCAN : JOB_NONE; jb.len = (uint32_t)len;
+                jb.rows = c->s_rows.as<uint32_t>() + b; jb.normal = c->s_normal.as<float>() + (size_t)j * slot;
+                jb.flags = c->s_flags.as<uint8_t>() + b; jb.margins = nullptr; jb.unit_left = nullptr;
+                units += (len + SCAN_UNIT - 1) / SCAN_UNIT;
+            }
+            CK(cudaMemcpyAsync(c->s_normal.p, slots.data(), slots.size() * 4, cudaMemcpyHostToDevice, c->stream));
+            CK(cudaMemcpyAsync(c->s_job.p, jobs.data(), sizeof(Job) * m, cudaMemcpyHostToDevice, c->stream));
+            int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(units, (uint64_t)c->sm_count * 3));
+            launch_work(c, c->s_job.as<Job>(), (int)m, grid);
+            CK(cudaStreamSynchronize(c->stream));   // slots / jobs host vectors are reused by the next chunk
+        }
+        CK(cudaMemcpyAsync(out_side, c->s_flags.p, total, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        c->h2d_bytes += 4ull * total + (uint64_t)n_jobs * slot * 4;
+        c->d2h_bytes += total;
+    });
+}
+
 int32_t arroy_b200_create_split(arroy_ctx* c, const uint32_t rng_key[8], uint64_t* rng_word_pos, const uint32_t* rows, uint64_t n_rows, float* out_normal, float* out_hdr) {
     return guarded(c, [&] {
         require_staged(c); set_device(c);

@@ -17,6 +17,7 @@
 #include <memory>
 #include <queue>
 #include <set>
+#include <unordered_map>
 
 #include "../../include/arroy_b200_host.h"
 
@@ -376,8 +377,21 @@ inline void inc_delete_tree(IncCtx& C, uint32_t node) {   // writer.rs:1263-1277
 
 struct TmpOps { std::vector<std::pair<uint32_t, HNode>> puts; std::set<uint32_t> deleted; };   // TmpNodes put / remove
 
+struct IdSet {  // membership test for the updated item ids: dense marker table when ids are small, else a set
+    std::vector<uint8_t> mark;
+    std::set<uint32_t> sparse;
+    bool dense = false;
+    explicit IdSet(const std::vector<uint32_t>& ids) {
+        uint32_t mx = 0;
+        for (uint32_t i : ids) mx = std::max(mx, i);
+        if (!ids.empty() && mx < (1u << 28)) { dense = true; mark.assign((size_t)mx + 1, 0); for (uint32_t i : ids) mark[i] = 1; }
+        else sparse.insert(ids.begin(), ids.end());
+    }
+    bool count(uint32_t id) const { return dense ? (id < mark.size() && mark[id]) : sparse.count(id) > 0; }
+};
+
 // delete_items_in_file — writer.rs:1021-1114. second.first = "Some(items)"
-inline std::pair<uint32_t, std::pair<bool, std::vector<uint32_t>>> inc_delete_items(IncCtx& C, uint32_t current, TmpOps& tmp, const std::set<uint32_t>& to_delete) {
+inline std::pair<uint32_t, std::pair<bool, std::vector<uint32_t>>> inc_delete_items(IncCtx& C, uint32_t current, TmpOps& tmp, const IdSet& to_delete) {
     const HNode& nd = C.tree.at(current);
     if (nd.kind == 1) {
         std::vector<uint32_t> nw;
@@ -436,6 +450,72 @@ inline void inc_route(IncCtx& C, ab::Rng& rng, uint32_t node, const std::vector<
     const uint32_t l = nd.left, r = nd.right;
     if (!left.empty()) inc_route(C, rng, l, left, out);
     if (!right.empty()) inc_route(C, rng, r, right, out);
+}
+
+// Level-batched version of the same routing for many roots at once: one arroy_b200_side_multi launch
+// per tree depth. The per-root results are then replayed depth-first so that the insertion order
+// into the IntMap (which the node ids depend on) is the reference's. Roots whose paths meet a
+// "normal: none" node keep the depth-first routine above (its random sides consume the root's rng
+// in depth-first order). Returns, per root, whether it was handled here.
+struct Routed { std::vector<uint32_t> left, right; };
+inline std::vector<char> inc_route_batched(IncCtx& C, const std::vector<uint32_t>& roots, const std::vector<uint32_t>& to_insert,
+                                          std::unordered_map<uint32_t, Routed>& routed, std::unordered_map<uint32_t, std::vector<uint32_t>>& leaf_ins) {
+    struct Front { uint32_t root_idx, node; std::vector<uint32_t> ids; };
+    std::vector<char> ok(roots.size(), 1);
+    std::vector<Front> front;
+    for (uint32_t r = 0; r < roots.size(); ++r) front.push_back({r, roots[r], to_insert});
+    const int hf = header_floats(C.metric);
+    while (!front.empty()) {
+        std::vector<float> normals, h0;
+        std::vector<uint32_t> rows;
+        std::vector<uint64_t> off(1, 0);
+        std::vector<size_t> job_front;
+        for (size_t i = 0; i < front.size(); ++i) {
+            Front& f = front[i];
+            if (!ok[f.root_idx]) continue;
+            const HNode& nd = C.tree.at(f.node);
+            if (nd.kind == 1) { leaf_ins[f.node] = std::move(f.ids); continue; }
+            if (nd.normal.empty()) { ok[f.root_idx] = 0; continue; }
+            float hh = 0.f;
+            memcpy(&hh, nd.normal.data(), 4);
+            h0.push_back(hh);
+            size_t o = normals.size();
+            normals.resize(o + C.d);
+            memcpy(normals.data() + o, nd.normal.data() + 4 * hf, 4ull * C.d);
+            for (uint32_t id : f.ids) rows.push_back(C.row_of(id));
+            off.push_back(rows.size());
+            job_front.push_back(i);
+        }
+        std::vector<Front> next;
+        if (!job_front.empty()) {
+            std::vector<uint8_t> side(rows.size());
+            dev_ck(C.ctx, arroy_b200_side_multi(C.ctx, (uint32_t)job_front.size(), normals.data(), h0.data(), nullptr, rows.data(), off.data(), side.data()));
+            for (size_t j = 0; j < job_front.size(); ++j) {
+                Front& f = front[job_front[j]];
+                const HNode& nd = C.tree.at(f.node);
+                Routed rt;
+                for (size_t i = 0; i < f.ids.size(); ++i) { if (side[off[j] + i]) rt.right.push_back(f.ids[i]); else rt.left.push_back(f.ids[i]); }
+                if (!rt.left.empty()) next.push_back({f.root_idx, nd.left, rt.left});
+                if (!rt.right.empty()) next.push_back({f.root_idx, nd.right, rt.right});
+                routed[f.node] = std::move(rt);
+            }
+        }
+        front.swap(next);
+    }
+    return ok;
+}
+inline void inc_replay(IncCtx& C, uint32_t node, const std::unordered_map<uint32_t, Routed>& routed, std::unordered_map<uint32_t, std::vector<uint32_t>>& leaf_ins, IntMapOrder& out) {
+    const HNode& nd = C.tree.at(node);
+    if (nd.kind == 1) {
+        const std::vector<uint32_t>& ins = leaf_ins.at(node);
+        std::vector<uint32_t> merged;
+        std::set_union(nd.desc.begin(), nd.desc.end(), ins.begin(), ins.end(), std::back_inserter(merged));
+        out.entry(node) = merged;
+        return;
+    }
+    const Routed& rt = routed.at(node);
+    if (!rt.left.empty()) inc_replay(C, nd.left, routed, leaf_ins, out);
+    if (!rt.right.empty()) inc_replay(C, nd.right, routed, leaf_ins, out);
 }
 
 inline ab::Rng rng_seed_from_u64(uint64_t state) {   // rand_core 0.6 SeedableRng::seed_from_u64
@@ -558,7 +638,7 @@ inline void writer_build(arroy_writer* w, arroy_ctx* ctx, arroy_rng* rng, int64_
             for (size_t i = 0; i < extraneous && !roots.empty(); ++i) { cancelled(); uint32_t r0 = roots[0]; roots[0] = roots.back(); roots.pop_back(); inc_delete_tree(C, r0); }
         }
         step("RemoveItemsFromExistingTrees");
-        const std::set<uint32_t> to_delete(updated.begin(), updated.end());
+        const IdSet to_delete(updated);
         {   // writer.rs:978-1015
             TmpOps tmp;
             for (uint32_t& root : roots) { cancelled(); root = inc_delete_items(C, root, tmp, to_delete).first; }
@@ -572,13 +652,16 @@ inline void writer_build(arroy_writer* w, arroy_ctx* ctx, arroy_rng* rng, int64_
         IntMapOrder top;
         if (!roots.empty() && !to_insert.empty()) {   // writer.rs:846-889, :1119-1160 (rayon reduce on a 1-thread pool: one split at len / 2)
             const uint64_t seed = rng->r.next_u64();
+            std::unordered_map<uint32_t, Routed> routed;
+            std::unordered_map<uint32_t, std::vector<uint32_t>> leaf_ins;
+            const std::vector<char> batched = inc_route_batched(C, roots, to_insert, routed, leaf_ins);   // all side() loops, one launch per depth
             auto fold = [&](size_t a, size_t b) {
                 IntMapOrder acc;
                 for (size_t i = a; i < b; ++i) {
                     cancelled();
-                    ab::Rng rr = rng_seed_from_u64(seed + (uint64_t)roots[i]);
                     IntMapOrder per_root;
-                    inc_route(C, rr, roots[i], to_insert, per_root);
+                    if (batched[i]) inc_replay(C, roots[i], routed, leaf_ins, per_root);
+                    else { ab::Rng rr = rng_seed_from_u64(seed + (uint64_t)roots[i]); inc_route(C, rr, roots[i], to_insert, per_root); }
                     acc.merge_from(per_root);
                 }
                 return acc;

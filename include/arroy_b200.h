@@ -102,6 +102,12 @@ int32_t arroy_b200_side_batch(arroy_ctx* ctx, const float* normal, float hdr0, f
                               const uint32_t* rows, uint64_t n_rows,
                               uint8_t* out_side, float* out_margin);
 
+/* Many side() loops in one launch (level-batched routing of new items down existing trees,
+ * src/writer.rs:1398-1459): job j tests rows[row_offsets[j] .. row_offsets[j+1]) against
+ * normals[j] (dim floats) with header hdr0[j] (bias / extra_dim). out_side has the layout of rows. */
+int32_t arroy_b200_side_multi(arroy_ctx* ctx, uint32_t n_jobs, const float* normals, const float* hdr0, const float* hdr1,
+                              const uint32_t* rows, const uint64_t* row_offsets, uint8_t* out_side);
+
 /* ---- D::create_split (two_means + normal) on a row subset — src/distance/mod.rs:126-171
  *      and the four create_split impls. `rng_key` (8 LE words of the 32-byte StdRng seed)
  *      and `*rng_word_pos` (how many u32 words of the ChaCha12 stream have been consumed)

@@ -103,3 +103,26 @@ def test_random_update_sequences_match_the_oracle(shared_ctx, metric, d, n_trees
         got = rd.nns(10).by_item(it)
         assert [g[0] for g in got] == [x[0] for x in want]
     env._ctx = None
+
+
+def test_incremental_on_degenerate_data_uses_random_sides_like_the_oracle(shared_ctx):
+    # identical vectors => "normal: none" nodes; routing new items through them draws Side::random
+    # from R::seed_from_u64(seed + root) in depth-first order (writer.rs:1128-1133, :1419-1421)
+    n, d = 400, 32
+    env = make_env(shared_ctx)
+    w = ab.Writer(env, 0, d, "euclidean")
+    odb = oracle.Db("euclidean", d)
+    prng, orng = ab.StdRng.from_seed(SEED), oracle.StdRng(SEED)
+    one = np.ones(d, dtype=np.float32)
+    for i in range(n):
+        w.add_item(i, one); odb.add_item(i, one)
+    w.builder(prng).n_trees(3).split_after(40).build()
+    odb.build_incremental(orng, n_trees=3, split_after=40)
+    assert env.tree_nodes() == odb.nodes()
+    for i in range(n, n + 120):
+        w.add_item(i, one); odb.add_item(i, one)
+    w.del_item(7); odb.del_item(7)
+    w.builder(prng).n_trees(3).split_after(40).build()
+    odb.build_incremental(orng, n_trees=3, split_after=40)
+    assert env.tree_nodes() == odb.nodes()
+    env._ctx = None
