@@ -1,0 +1,92 @@
+"""Edge cases of the C-ABI entry points (empty / ragged / limit inputs), checked against the oracle."""
+import numpy as np
+import pytest
+
+import arroy_b200 as ab
+import oracle
+
+pytestmark = pytest.mark.gpu
+SEED = bytes([42] * 32)
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = ab.Context(0)
+    yield c
+    c.close()
+
+
+def test_empty_and_tiny_inputs(ctx):
+    d = 40
+    data = oracle.synth_rows(SEED, d, 0, 50, 0.5)
+    ctx.stage_items_flat("euclidean", np.arange(50, dtype=np.uint32), data)
+    side, mg = ctx.side_batch(np.ones(d, np.float32), (0.0, 0.0), np.zeros(0, dtype=np.uint32))
+    assert side.size == 0 and mg.size == 0
+    r, dist = ctx.rerank(data[0], (0.0, 0.0), np.zeros(0, dtype=np.uint32), 5)
+    assert r.size == 0
+    r, dist = ctx.rerank(data[0], (0.0, 0.0), np.arange(3, dtype=np.uint32), 10)     # k > candidates
+    wr, wd = oracle.rerank(oracle.EUCLIDEAN, data[0], (0, 0), data, np.zeros(50, np.float32), None, np.arange(3, dtype=np.uint32), 10)
+    assert r.tolist() == wr.tolist() and dist.tobytes() == wd.tobytes()
+    r, dist = ctx.rerank(data[0], (0.0, 0.0), np.arange(50, dtype=np.uint32), 0)      # k == 0
+    assert r.size == 0
+    out_rows, out_dist, out_len = ctx.rerank_shared(data[:3], None, np.arange(50, dtype=np.uint32), 50)
+    for i in range(3):
+        wr, wd = oracle.rerank(oracle.EUCLIDEAN, data[i], (0, 0), data, np.zeros(50, np.float32), None, np.arange(50, dtype=np.uint32), 50)
+        assert out_rows[i, :out_len[i]].tolist() == wr.tolist() and out_dist[i, :out_len[i]].tobytes() == wd.tobytes()
+    # staging zero items is allowed; building on it is not
+    ctx.stage_items_flat("euclidean", np.zeros(0, dtype=np.uint32), np.zeros((0, d), dtype=np.float32))
+    with pytest.raises(ab.ArroyB200Error):
+        ctx.build_trees([SEED], [0], 1)
+
+
+def test_two_item_nodes_and_split_after_one(ctx):
+    # the smallest possible splits: K = 1 forces every node down to single items
+    n, d = 64, 32
+    data = oracle.synth_rows(SEED, d, 0, n, 0.5)
+    ids = np.arange(n, dtype=np.uint32)
+    odb = oracle.Db("cosine", d)
+    odb.set_items(ids, data)
+    rng = oracle.StdRng(SEED)
+    user = rng.clone()
+    odb.build(rng, n_trees=3, split_after=1)
+    ctx.stage_items_flat("cosine", ids, data)
+    r1 = oracle.StdRng(user.gen_seed())
+    seeds = [r1.gen_seed() for _ in range(3)]
+    got = ctx.build_trees(seeds, [0, 1, 2], 3, split_after=1)
+    assert got == odb.nodes()
+
+
+def test_many_trees_run_in_several_waves(ctx, monkeypatch):
+    # more trees than one wave holds: results must not depend on the wave size
+    n, d, T = 1500, 48, 9
+    data = oracle.synth_rows(SEED, d, 0, n, 0.5)
+    ids = np.arange(n, dtype=np.uint32)
+    ctx.stage_items_flat("euclidean", ids, data)
+    user = oracle.StdRng(SEED)
+    r1 = oracle.StdRng(user.gen_seed())
+    seeds = [r1.gen_seed() for _ in range(T)]
+    one_wave = ctx.build_trees(seeds, list(range(T)), T)
+    monkeypatch.setenv("ARROY_B200_MAX_WAVE", "4")
+    three_waves = ctx.build_trees(seeds, list(range(T)), T)
+    monkeypatch.setenv("ARROY_B200_LOCKSTEP", "1")
+    lockstep = ctx.build_trees(seeds, list(range(T)), T)
+    assert one_wave == three_waves == lockstep
+
+
+def test_search_batch_by_vector_and_status(ctx):
+    n, d, T = 4000, 64, 5
+    data = oracle.synth_rows(SEED, d, 0, n, 0.5)
+    env = ab.Env(0)
+    env._ctx = ctx
+    w = ab.Writer(env, 0, d, "cosine")
+    w.add_items(np.arange(n, dtype=np.uint32), data)
+    w.builder(ab.StdRng.from_seed(SEED)).n_trees(T).build()
+    r = ab.Reader.open(env, 0, "cosine")
+    out_ids, out_dist, out_len, _ = r.nns_batch_by_item(np.arange(30, dtype=np.uint32), 2000)   # large k, still <= 2048
+    odb = oracle.Db("cosine", d)
+    odb.set_items(np.arange(n, dtype=np.uint32), data)
+    odb.build(oracle.StdRng(SEED), n_trees=T, threads=4)
+    for i in range(30):
+        want = odb.nns_by_item(i, 2000)
+        assert out_ids[i, :out_len[i]].tolist() == [x[0] for x in want]
+    env._ctx = None
