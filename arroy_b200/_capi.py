@@ -57,6 +57,8 @@ SIGNATURES = [
     ("arroy_b200_arena_get", C.c_int32, [C.c_void_p, C.c_uint32, C.POINTER(_u8p), _u64p]),
     ("arroy_b200_build_breakdown", C.c_int32, [C.c_void_p, C.POINTER(C.c_double)]),
     ("arroy_b200_counters", C.c_int32, [C.c_void_p, _u64p]),
+    ("arroy_b200_rerank_stats", C.c_int32, [C.c_void_p, _u64p]),
+    ("arroy_b200_prefilter_scores", C.c_int32, [C.c_void_p, C.c_uint32, _f32p, _u32p, C.c_uint64, C.c_int32, _f32p]),
     ("arroy_b200_timer_start", C.c_int32, [C.c_void_p]),
     ("arroy_b200_timer_stop", C.c_int32, [C.c_void_p, _f32p]),
     ("arroy_b200_device_ptrs", C.c_int32, [C.c_void_p, C.POINTER(C.c_void_p), _u32p]),
@@ -327,6 +329,18 @@ class Context:
         out = (C.c_uint64 * 4)()
         self._ck(self.lib.arroy_b200_counters(self.h, out))
         return {"launches": out[0], "h2d_bytes": out[1], "d2h_bytes": out[2]}
+
+    def prefilter_scores(self, queries, rows, engine=0):
+        queries = np.ascontiguousarray(queries, dtype=np.float32)
+        rows = np.ascontiguousarray(rows, dtype=np.uint32)
+        out = np.empty((queries.shape[0], rows.size), dtype=np.float32)
+        self._ck(self.lib.arroy_b200_prefilter_scores(self.h, queries.shape[0], _fp(queries), _up(rows), rows.size, engine, _fp(out)))
+        return out
+
+    def rerank_stats(self):
+        out = (C.c_uint64 * 4)()
+        self._ck(self.lib.arroy_b200_rerank_stats(self.h, out))
+        return {"prefilter_chunks": out[0], "fallback_chunks": out[1], "survivors": out[2], "queries": out[3]}
 
     def timer_start(self):
         self._ck(self.lib.arroy_b200_timer_start(self.h))

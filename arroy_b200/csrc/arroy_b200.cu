@@ -18,7 +18,10 @@
 #include "../../include/arroy_b200.h"
 #include "build.cuh"
 #include "search.cuh"
+#include <cublas_v2.h>
+
 #include "xrerank.cuh"
+#include "tcgemm.cuh"
 
 using namespace ab;
 
@@ -131,6 +134,10 @@ struct arroy_ctx {
     double breakdown[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     std::vector<cudaStream_t> tree_streams;   // one per tree of a wave (asynchronous per-tree chains)
     std::vector<cudaEvent_t> tree_events;     // join events, [0] = fork
+    // tensor-core pre-filter of rerank_shared
+    cublasHandle_t blas = nullptr;
+    DevBuf x_gather, x_cnorm, x_ca, x_cb, x_gmax, x_qa, x_qb, x_twoe, x_qnorm, x_S, x_sel, x_beg, x_end, x_flag;
+    uint64_t xf_calls = 0, xf_fallbacks = 0, xf_selected = 0, xf_queries = 0;
 };
 
 namespace {
@@ -712,6 +719,40 @@ void do_side_batch(arroy_ctx* c, const float* normal, float h0, float h1, const 
     CK(cudaStreamSynchronize(c->stream));
 }
 
+// ---- tensor-core pre-filter helpers (rerank_shared) ---------------------------------------------
+// candidate matrix for the score GEMM: the item matrix in place when `rows` is a contiguous range,
+// else a gathered copy
+const float* xf_candidates(arroy_ctx* c, const uint32_t* rows, uint32_t nc) {
+    bool contiguous = true;
+    for (uint64_t i = 1; i < nc && contiguous; ++i) contiguous = rows[i] == rows[0] + i;
+    if (contiguous) return c->items.as<float>() + (size_t)rows[0] * c->ld;
+    c->x_gather.ensure(4ull * nc * c->ld);
+    xf_gather_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->x_gather.as<float4>(), c->items.as<float4>(), c->s_rows.as<uint32_t>(), nc, c->ld / 4);
+    CK(cudaGetLastError());
+    c->n_launches += 1;
+    return c->x_gather.as<float>();
+}
+
+// S (m x nc, pitch lds) = Q . cand^T with TF32 inputs and FP32 accumulation. engine 0: the tcgen05
+// kernel of tcgemm.cuh; engine 1: cuBLAS (kept as the cross-check of the hand-written kernel)
+void xf_scores(arroy_ctx* c, const float* q, uint32_t m, const float* cand, uint32_t nc, float* S, uint32_t lds, TgEpilogue ep, int engine) {
+    if (engine == 0) {
+        if (!tcgemm_tf32(q, m, cand, nc, c->ld, S, lds, ep, c->sm_count, c->stream)) throw CudaError(std::string("tcgemm_tf32 launch failed: ") + cudaGetErrorString(cudaGetLastError()));
+        c->n_launches += 1;
+        return;
+    }
+    if (!c->blas) { if (cublasCreate(&c->blas) != CUBLAS_STATUS_SUCCESS) throw CudaError("cublasCreate failed"); }
+    if (cublasSetStream(c->blas, c->stream) != CUBLAS_STATUS_SUCCESS) throw CudaError("cublasSetStream failed");
+    const float one = 1.0f, zero = 0.0f;
+    cublasStatus_t st = cublasGemmEx(c->blas, CUBLAS_OP_T, CUBLAS_OP_N, (int)nc, (int)m, (int)c->ld, &one, cand, CUDA_R_32F, (int)c->ld,
+                                     q, CUDA_R_32F, (int)c->ld, &zero, S, CUDA_R_32F, (int)lds, CUBLAS_COMPUTE_32F_FAST_TF32, CUBLAS_GEMM_DEFAULT);
+    if (st != CUBLAS_STATUS_SUCCESS) throw CudaError("cublasGemmEx failed with status " + std::to_string((int)st));
+    if (ep.mode != TG_RAW) { tg_finish_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(S, m, nc, lds, ep); CK(cudaGetLastError()); }
+    c->n_launches += 2;
+}
+
+int xf_engine() { const char* e = getenv("ARROY_B200_XGEMM"); return (e && strcmp(e, "cublas") == 0) ? 1 : 0; }
+
 void do_rerank_batch(arroy_ctx* c, uint32_t nq, const float* queries, const float* qh0, const float* /*qh1*/, const uint32_t* rows,
                      const uint64_t* offsets, uint32_t k, uint32_t* out_rows, float* out_dist, uint32_t* out_len) {
     require_staged(c);
@@ -840,6 +881,8 @@ void arroy_b200_destroy(arroy_ctx* c) {
     DevBuf* bufs[] = {&c->items, &c->h0, &c->h1, &c->norms, &c->maxbits, &c->s_rows, &c->s_flags, &c->s_margins, &c->s_normal, &c->s_unit, &c->s_job,
                       &c->s_keys, &c->s_dists, &c->s_q, &c->s_qh0, &c->s_off, &c->s_orows, &c->s_odist, &c->s_olen, &c->s_misc};
     for (auto* b : bufs) b->release();
+    { DevBuf* xb[] = {&c->x_gather, &c->x_cnorm, &c->x_ca, &c->x_cb, &c->x_gmax, &c->x_qa, &c->x_qb, &c->x_twoe, &c->x_qnorm, &c->x_S, &c->x_sel, &c->x_beg, &c->x_end, &c->x_flag}; for (auto* b : xb) b->release(); }
+    if (c->blas) cublasDestroy(c->blas);
     if (c->cached_exec) cudaGraphExecDestroy(c->cached_exec);
     if (c->cached_graph) cudaGraphDestroy(c->cached_graph);
     for (auto& sw : c->stage_workers) { sw.pin[0].release(); sw.pin[1].release(); if (sw.ev[0]) cudaEventDestroy(sw.ev[0]); if (sw.ev[1]) cudaEventDestroy(sw.ev[1]); if (sw.st) cudaStreamDestroy(sw.st); }
@@ -1130,28 +1173,100 @@ int32_t arroy_b200_rerank_shared(arroy_ctx* c, uint32_t nq, const float* queries
         const uint32_t ld = c->ld, nc = (uint32_t)n_rows;
         c->s_rows.ensure(4ull * nc);
         CK(cudaMemcpyAsync(c->s_rows.p, rows, 4ull * nc, cudaMemcpyHostToDevice, c->stream));
-        // queries in chunks so the dense distance matrix stays <= 2 GiB
-        const uint32_t chunk = (uint32_t)std::max<uint64_t>(XQB, std::min<uint64_t>(nq, ((2ull << 30) / (4ull * nc)) / XQB * XQB));
+        // ARROY_B200_XRERANK = exact | filter; default: the tensor-core pre-filter once the problem is big enough to pay for it
+        const char* mode = getenv("ARROY_B200_XRERANK");
+        bool filter = mode ? strcmp(mode, "filter") == 0 : ((uint64_t)nq * nc >= (1ull << 22) && nc >= 4u * k);
+        const uint32_t cap = std::max<uint32_t>(1024u, 4u * k);
+        const uint32_t lds = (nc + 3u) & ~3u;   // pitch of the score matrix
+        const float* cand = nullptr;   // nc x ld candidate matrix for the GEMM
+        if (filter) {
+            cand = xf_candidates(c, rows, nc);
+            c->x_cnorm.ensure(4ull * nc);
+            { uint64_t warps = ((uint64_t)nc + 3) / 4; int g = (int)std::max<uint64_t>(1, std::min<uint64_t>((warps + 7) / 8, (uint64_t)c->sm_count * 16));
+              norms_kernel<<<g, 256, 0, c->stream>>>(cand, nc, c->dim, ld, c->x_cnorm.as<float>(), nullptr); CK(cudaGetLastError()); }
+            c->x_ca.ensure(4ull * nc); c->x_cb.ensure(4ull * nc); c->x_gmax.ensure(4);
+            CK(cudaMemsetAsync(c->x_gmax.p, 0, 4, c->stream));
+            xf_cand_prep_kernel<<<(nc + 255) / 256, 256, 0, c->stream>>>(c->x_cnorm.as<float>(), c->h0.as<float>(), c->s_rows.as<uint32_t>(), nc, c->metric,
+                                                                         c->x_ca.as<float>(), c->x_cb.as<float>(), c->x_gmax.as<uint32_t>());
+            CK(cudaGetLastError());
+            c->n_launches += 2;
+            c->x_flag.ensure(4);
+        }
+        // queries in chunks so the dense score / distance matrix stays <= 2 GiB
+        const uint32_t chunk = (uint32_t)std::max<uint64_t>(XQB, std::min<uint64_t>(nq, ((2ull << 30) / (4ull * lds)) / XQB * XQB));
         for (uint32_t q0 = 0; q0 < nq; q0 += chunk) {
             const uint32_t m = std::min(chunk, nq - q0);
-            c->s_q.ensure((size_t)m * ld * 4); c->s_qh0.ensure(4ull * m); c->s_dists.ensure(4ull * m * nc);
+            c->s_q.ensure((size_t)m * ld * 4); c->s_qh0.ensure(4ull * m);
             c->s_orows.ensure(4ull * m * k); c->s_odist.ensure(4ull * m * k); c->s_olen.ensure(4ull * m);
             if (ld != c->dim) CK(cudaMemsetAsync(c->s_q.p, 0, (size_t)m * ld * 4, c->stream));
             CK(cudaMemcpy2DAsync(c->s_q.p, (size_t)ld * 4, queries + (size_t)q0 * c->dim, (size_t)c->dim * 4, (size_t)c->dim * 4, m, cudaMemcpyHostToDevice, c->stream));
             if (qhdr0) CK(cudaMemcpyAsync(c->s_qh0.p, qhdr0 + q0, 4ull * m, cudaMemcpyHostToDevice, c->stream));
             else CK(cudaMemsetAsync(c->s_qh0.p, 0, 4ull * m, c->stream));
-            dim3 grid((nc + XCB - 1) / XCB, (m + XQB - 1) / XQB);
-            if (c->metric == EUCLIDEAN)
-                xrerank_kernel<true><<<grid, XTHREADS, 0, c->stream>>>(c->items.as<float>(), c->h0.as<float>(), c->dim, ld, c->metric, c->s_q.as<float>(), c->s_qh0.as<float>(), m,
-                                                                      c->s_rows.as<uint32_t>(), nc, c->s_dists.as<float>());
-            else
-                xrerank_kernel<false><<<grid, XTHREADS, 0, c->stream>>>(c->items.as<float>(), c->h0.as<float>(), c->dim, ld, c->metric, c->s_q.as<float>(), c->s_qh0.as<float>(), m,
-                                                                       c->s_rows.as<uint32_t>(), nc, c->s_dists.as<float>());
-            CK(cudaGetLastError());
-            topk_dense_kernel<<<m, TOPK_THREADS, 0, c->stream>>>(c->s_dists.as<float>(), c->s_rows.as<uint32_t>(), nc, k, c->metric,
-                                                                 c->s_orows.as<uint32_t>(), c->s_odist.as<float>(), c->s_olen.as<uint32_t>());
-            CK(cudaGetLastError());
-            c->n_launches += 2;
+            bool done = false;
+            static const bool xf_trace = getenv("ARROY_B200_XF_TRACE") != nullptr;
+            cudaEvent_t te[8]; int nte = 0;
+            auto mark = [&]() { if (xf_trace && nte < 8) { CK(cudaEventCreate(&te[nte])); CK(cudaEventRecord(te[nte], c->stream)); ++nte; } };
+            if (filter) {
+                c->xf_calls += 1;
+                mark();
+                c->x_S.ensure(4ull * m * lds); c->x_qnorm.ensure(4ull * m); c->x_qa.ensure(4ull * m); c->x_qb.ensure(4ull * m); c->x_twoe.ensure(4ull * m);
+                c->x_sel.ensure(4ull * m * cap); c->x_beg.ensure(8ull * m); c->x_end.ensure(8ull * m);
+                c->s_dists.ensure(4ull * m * cap); c->s_keys.ensure(8ull * m * cap);
+                { uint64_t warps = ((uint64_t)m + 3) / 4; int g = (int)std::max<uint64_t>(1, std::min<uint64_t>((warps + 7) / 8, (uint64_t)c->sm_count * 16));
+                  norms_kernel<<<g, 256, 0, c->stream>>>(c->s_q.as<float>(), m, c->dim, ld, c->x_qnorm.as<float>(), nullptr); CK(cudaGetLastError()); }
+                xf_query_prep_kernel<<<(m + 255) / 256, 256, 0, c->stream>>>(c->x_qnorm.as<float>(), c->s_qh0.as<float>(), m, c->metric, xf_rel(c->dim), c->dim, c->x_gmax.as<uint32_t>(),
+                                                                             c->x_qa.as<float>(), c->x_qb.as<float>(), c->x_twoe.as<float>());
+                CK(cudaGetLastError());
+                // A (m x nc, row-major) = distance estimates: Q . cand^T on the tensor cores (TF32 inputs, FP32 accumulate) + fused epilogue
+                TgEpilogue ep{c->metric == EUCLIDEAN ? TG_EUCLID : (c->metric == COSINE ? TG_COSINE : TG_NEG), c->x_qa.as<float>(), c->x_qb.as<float>(), c->x_ca.as<float>(), c->x_cb.as<float>()};
+                xf_scores(c, c->s_q.as<float>(), m, cand, nc, c->x_S.as<float>(), lds, ep, xf_engine());
+                mark();
+                CK(cudaMemsetAsync(c->x_flag.p, 0, 4, c->stream));
+                xf_select_kernel<<<m, XF_THREADS, 0, c->stream>>>(c->x_S.as<float>(), lds, nc, k, c->x_twoe.as<float>(), c->s_rows.as<uint32_t>(), cap,
+                                                                  c->x_sel.as<uint32_t>(), c->x_beg.as<uint64_t>(), c->x_end.as<uint64_t>(), c->x_flag.as<int>());
+                CK(cudaGetLastError());
+                mark();
+                // exact re-score of the survivors, in the reference's summation order
+                { uint64_t warps = ((uint64_t)cap + 3) / 4;
+                  uint32_t gx = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((warps + 7) / 8, std::max<uint64_t>(1, ((uint64_t)c->sm_count * 8) / std::min<uint32_t>(m, c->sm_count * 8u))));
+                  dim3 grid(gx, m);
+                  distance_kernel<<<grid, 256, 0, c->stream>>>(c->items.as<float>(), c->h0.as<float>(), c->dim, ld, c->metric, c->s_q.as<float>(), nullptr, c->s_qh0.as<float>(), m,
+                                                               c->x_sel.as<uint32_t>(), c->x_beg.as<uint64_t>(), c->x_end.as<uint64_t>(), c->s_dists.as<float>(), c->s_keys.as<unsigned long long>());
+                  CK(cudaGetLastError()); }
+                mark();
+                topk_kernel<<<m, TOPK_THREADS, 0, c->stream>>>(c->s_keys.as<unsigned long long>(), c->s_dists.as<float>(), c->x_sel.as<uint32_t>(), c->x_beg.as<uint64_t>(), c->x_end.as<uint64_t>(), k, c->metric,
+                                                                c->s_orows.as<uint32_t>(), c->s_odist.as<float>(), c->s_olen.as<uint32_t>());
+                CK(cudaGetLastError());
+                c->n_launches += 6;
+                mark();
+                int flag = 0;
+                CK(cudaMemcpyAsync(&flag, c->x_flag.p, 4, cudaMemcpyDeviceToHost, c->stream));
+                CK(cudaStreamSynchronize(c->stream));
+                if (xf_trace) {
+                    const char* names[] = {"norms+gemm", "select", "rescore", "topk"};
+                    for (int i = 0; i + 1 < nte; ++i) { float ms = 0; cudaEventElapsedTime(&ms, te[i], te[i + 1]); fprintf(stderr, "[xf] %s %.3f ms\n", names[i], ms); }
+                    for (int i = 0; i < nte; ++i) cudaEventDestroy(te[i]);
+                }
+                done = flag == 0;
+                { std::vector<uint64_t> ends(m); CK(cudaMemcpy(ends.data(), c->x_end.p, 8ull * m, cudaMemcpyDeviceToHost));
+                  for (uint32_t q = 0; q < m; ++q) c->xf_selected += ends[q] - (uint64_t)q * cap; c->xf_queries += m; }
+                if (!done) c->xf_fallbacks += 1;   // more survivors than `cap` for some query: take the exact path for this chunk
+            }
+            if (!done) {
+                c->s_dists.ensure(4ull * m * nc);
+                dim3 grid((nc + XCB - 1) / XCB, (m + XQB - 1) / XQB);
+                if (c->metric == EUCLIDEAN)
+                    xrerank_kernel<true><<<grid, XTHREADS, 0, c->stream>>>(c->items.as<float>(), c->h0.as<float>(), c->dim, ld, c->metric, c->s_q.as<float>(), c->s_qh0.as<float>(), m,
+                                                                          c->s_rows.as<uint32_t>(), nc, c->s_dists.as<float>());
+                else
+                    xrerank_kernel<false><<<grid, XTHREADS, 0, c->stream>>>(c->items.as<float>(), c->h0.as<float>(), c->dim, ld, c->metric, c->s_q.as<float>(), c->s_qh0.as<float>(), m,
+                                                                           c->s_rows.as<uint32_t>(), nc, c->s_dists.as<float>());
+                CK(cudaGetLastError());
+                topk_dense_kernel<<<m, TOPK_THREADS, 0, c->stream>>>(c->s_dists.as<float>(), c->s_rows.as<uint32_t>(), nc, k, c->metric,
+                                                                     c->s_orows.as<uint32_t>(), c->s_odist.as<float>(), c->s_olen.as<uint32_t>());
+                CK(cudaGetLastError());
+                c->n_launches += 2;
+            }
             CK(cudaMemcpyAsync(out_rows + (size_t)q0 * k, c->s_orows.p, 4ull * m * k, cudaMemcpyDeviceToHost, c->stream));
             CK(cudaMemcpyAsync(out_dist + (size_t)q0 * k, c->s_odist.p, 4ull * m * k, cudaMemcpyDeviceToHost, c->stream));
             CK(cudaMemcpyAsync(out_len + q0, c->s_olen.p, 4ull * m, cudaMemcpyDeviceToHost, c->stream));
@@ -1377,6 +1492,31 @@ int32_t arroy_b200_build_breakdown(arroy_ctx* c, double out[8]) {
 
 int32_t arroy_b200_counters(arroy_ctx* c, uint64_t out[4]) {
     return guarded(c, [&] { out[0] = c->n_launches; out[1] = c->h2d_bytes; out[2] = c->d2h_bytes; out[3] = 0; });
+}
+
+int32_t arroy_b200_prefilter_scores(arroy_ctx* c, uint32_t nq, const float* queries, const uint32_t* rows, uint64_t n_rows, int32_t engine, float* out_scores) {
+    return guarded(c, [&] {
+        require_staged(c); set_device(c);
+        if (nq == 0 || n_rows == 0) return;
+        if (!queries || !rows || !out_scores) throw ArgError("null argument");
+        if (c->dim < 32) throw ArgError("prefilter_scores needs dim >= 32");
+        if (n_rows > 0x7fffffffull || (uint64_t)nq * n_rows > (1ull << 29)) throw ArgError("prefilter_scores: problem too large");
+        for (uint64_t i = 0; i < n_rows; ++i) if (rows[i] >= c->n) throw ArgError("row index out of range");
+        const uint32_t ld = c->ld, nc = (uint32_t)n_rows, lds = (nc + 3u) & ~3u;
+        c->s_rows.ensure(4ull * nc);
+        CK(cudaMemcpyAsync(c->s_rows.p, rows, 4ull * nc, cudaMemcpyHostToDevice, c->stream));
+        const float* cand = xf_candidates(c, rows, nc);
+        c->s_q.ensure((size_t)nq * ld * 4); c->x_S.ensure(4ull * nq * lds);
+        CK(cudaMemsetAsync(c->s_q.p, 0, (size_t)nq * ld * 4, c->stream));
+        CK(cudaMemcpy2DAsync(c->s_q.p, (size_t)ld * 4, queries, (size_t)c->dim * 4, (size_t)c->dim * 4, nq, cudaMemcpyHostToDevice, c->stream));
+        xf_scores(c, c->s_q.as<float>(), nq, cand, nc, c->x_S.as<float>(), lds, TgEpilogue{TG_RAW, nullptr, nullptr, nullptr, nullptr}, engine);
+        CK(cudaMemcpy2DAsync(out_scores, 4ull * nc, c->x_S.p, 4ull * lds, 4ull * nc, nq, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    });
+}
+
+int32_t arroy_b200_rerank_stats(arroy_ctx* c, uint64_t out[4]) {
+    return guarded(c, [&] { out[0] = c->xf_calls; out[1] = c->xf_fallbacks; out[2] = c->xf_selected; out[3] = c->xf_queries; });
 }
 
 int32_t arroy_b200_timer_start(arroy_ctx* c) {

@@ -201,4 +201,270 @@ topk_dense_kernel(const float* __restrict__ dist, const uint32_t* __restrict__ r
     }
 }
 
+// =================================================================================================
+// Tensor-core pre-filter for the shared-candidate re-rank ("tensor-core
+// pre-filter + exact AVX-order re-score of the top-(k + margin)").
+//
+// The tensor cores cannot produce the reference's value of a pair, but they can bound it. With both
+// operands truncated to TF32 (10-bit mantissa) and FP32 accumulation the contraction s satisfies
+//     | s - dot_ref(q, c) |  <=  rel * |q| * |c|,      rel = 2^-8 + d * 2^-22
+// (Cauchy-Schwarz over the per-element relative errors 2 * 2^-10, the accumulation error, and the
+// reference's own FP32 rounding of dot_ref; about 2x slack). tcgemm.cuh turns s into an estimate
+// a(q, c) of built_distance in its epilogue; for a query q every pair then satisfies
+//     | a(q, c) - built_distance_ref(q, c) |  <=  E(q)
+// where E(q) uses the largest candidate norm (xf_query_prep_kernel). Let a_(k) be the k-th smallest
+// estimate of the query. At least k candidates have a distance <= a_(k) + E, so a candidate of the
+// true top-k has a <= a_(k) + 2 E: everything above that is discarded, the survivors (a few hundred
+// of 100 000 for BASELINE config 5) are re-scored by distance_kernel in the reference's exact
+// summation order and ranked by topk_kernel. Ids and distances are therefore bit-identical to the
+// exact path. Survivors are kept in candidate order, which keeps the (distance, id) tie-break of
+// reader.rs:390. Estimates that are NaN / infinite count as "unknown" and always survive.
+// =================================================================================================
+constexpr int XF_THREADS = 512;
+constexpr int XF_BINS = 4096;
+constexpr int XF_STAGE = 2048;
+constexpr uint32_t XF_SAMPLE = 4;
+
+inline float xf_rel(uint32_t d) { return 0.00390625f + (float)d * 2.384185791015625e-07f; }   // 2^-8 + d 2^-22
+
+// dst[c] = items[rows[c]] (ld floats per row), float4 granularity
+__global__ void xf_gather_kernel(float4* __restrict__ dst, const float4* __restrict__ items, const uint32_t* __restrict__ rows, uint32_t nc, uint32_t ld4) {
+    const uint64_t total = (uint64_t)nc * ld4;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t c = (uint32_t)(i / ld4), k = (uint32_t)(i - (uint64_t)c * ld4);
+        dst[i] = items[(uint64_t)rows[c] * ld4 + k];
+    }
+}
+
+// per-candidate epilogue constants (see TgEpilogue) and gmax = max over candidates of the factor
+// the error bound grows with: |c| (Euclidean, DotProduct) or |c| / header norm (Cosine, normally 1)
+__global__ void xf_cand_prep_kernel(const float* __restrict__ cnorm, const float* __restrict__ ih0, const uint32_t* __restrict__ rows, uint32_t nc, int metric,
+                                    float* __restrict__ ca, float* __restrict__ cb, uint32_t* __restrict__ gmax_bits) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    float g = 0.f;
+    if (i < nc) {
+        const float cn = cnorm[i];
+        g = cn;
+        float a = 0.f, b = 0.f;
+        if (metric == EUCLIDEAN) a = __fmul_rn(cn, cn);
+        else if (metric == COSINE) {
+            b = ih0[rows[i]];
+            if (b >= 1e-30f) { a = __fdiv_rn(1.0f, b); g = __fmul_rn(cn, a); }
+            else { a = __uint_as_float(0x7fc00000u); g = 0.f; }   // only reachable when pnqn <= EPSILON (estimate exactly 0) or the pair is unknown
+        }
+        ca[i] = a; cb[i] = b;
+        if (!(g == g)) g = __uint_as_float(0x7f800000u);
+    }
+    g = fabsf(g);
+    uint32_t bits = __reduce_max_sync(0xffffffffu, __float_as_uint(g));
+    if ((threadIdx.x & 31) == 0 && bits) atomicMax(gmax_bits, bits);
+}
+
+// per-query epilogue constants and E(q) (stored as 2 E, slightly inflated)
+__global__ void xf_query_prep_kernel(const float* __restrict__ qnorm, const float* __restrict__ qh0, uint32_t m, int metric, float rel, uint32_t d,
+                                     const uint32_t* __restrict__ gmax_bits, float* __restrict__ qa, float* __restrict__ qb, float* __restrict__ two_e) {
+    uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= m) return;
+    const float qn = qnorm[q], gmax = __uint_as_float(*gmax_bits);
+    const float eps = __fmaf_rn(rel, __fmul_rn(qn, gmax), 1e-30f);
+    float a = 0.f, b = 0.f, e;
+    if (metric == DOT_PRODUCT) e = eps;
+    else if (metric == EUCLIDEAN) {
+        a = __fmul_rn(qn, qn);
+        const float slack = ((float)(d / 32u) + 16.0f) * 2.384185791015625e-07f;   // reference + estimate rounding, relative to |q|^2 + |c|^2
+        e = __fmaf_rn(slack, __fadd_rn(a, __fmul_rn(gmax, gmax)), __fmul_rn(2.0f, eps));
+    } else {
+        b = qh0[q];
+        if (b >= 1e-30f) { a = __fdiv_rn(1.0f, b); e = __fmaf_rn(__fmul_rn(0.5f, eps), a, 1.9073486328125e-06f /* 2^-19 */); }
+        else { a = __uint_as_float(0x7fc00000u); e = 1.9073486328125e-06f; }
+    }
+    qa[q] = a; qb[q] = b;
+    two_e[q] = __fmul_rn(__fmul_rn(2.0f, e), 1.0009765625f);
+}
+
+__device__ __forceinline__ uint32_t xf_key(float a) { return fabsf(a) <= 3.0e38f ? ordered_key(a) : 0xffffffffu; }   // unknown -> max
+__device__ __forceinline__ float xf_unkey(uint32_t k) {   // inverse of ordered_key for finite values
+    uint32_t b = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+    return __uint_as_float(b);
+}
+__device__ __forceinline__ uint32_t xf_widen(uint32_t key, float two_e) {   // key of (value + 2E), max if not finite
+    if (key == 0xffffffffu) return key;
+    return xf_key(__fadd_rn(xf_unkey(key), two_e));
+}
+
+// exclusive scan of one value per thread over the CTA (XF_THREADS threads); returns the exclusive
+// prefix, *total = sum. sm: 17 uint32.
+__device__ __forceinline__ uint32_t xf_block_scan(uint32_t v, uint32_t* sm, uint32_t* total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    __syncthreads();
+    if (lane == 31) sm[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = lane < (XF_THREADS / 32) ? sm[lane] : 0u, winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc += t; }
+        if (lane < (XF_THREADS / 32)) sm[lane] = winc - w;
+        if (lane == 31) sm[16] = winc;
+    }
+    __syncthreads();
+    const uint32_t res = sm[warp] + inc - v;
+    *total = sm[16];
+    return res;
+}
+
+// smallest bin b with (number of entries in bins <= b) >= want; *before = entries in bins < b
+__device__ __forceinline__ uint32_t xf_find_bin(const uint32_t* hist, uint32_t want, uint32_t* sm, uint32_t* sh_out /* 2 uint32 */, uint32_t* before) {
+    constexpr int PER = XF_BINS / XF_THREADS;
+    uint32_t local = 0;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) local += hist[threadIdx.x * PER + i];
+    uint32_t total;
+    uint32_t ex = xf_block_scan(local, sm, &total);
+    if (threadIdx.x == 0) { sh_out[0] = XF_BINS - 1; sh_out[1] = total; }   // fewer than `want` entries: last bin
+    __syncthreads();
+    if (ex < want && ex + local >= want) {
+        uint32_t cum = ex;
+        for (int i = 0; i < PER; ++i) {
+            uint32_t h = hist[threadIdx.x * PER + i];
+            if (cum + h >= want) { sh_out[0] = threadIdx.x * PER + i; sh_out[1] = cum; break; }
+            cum += h;
+        }
+    }
+    __syncthreads();
+    *before = sh_out[1];
+    return sh_out[0];
+}
+
+__device__ __forceinline__ void xf_bitonic_u32(uint32_t* buf, int n /* power of two */) {
+    for (int size = 2; size <= n; size <<= 1)
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            __syncthreads();
+            for (int t = threadIdx.x; t < (n >> 1); t += XF_THREADS) {
+                int i = 2 * t - (t & (stride - 1)), j = i + stride;
+                bool up = ((i & size) == 0);
+                uint32_t a = buf[i], b = buf[j];
+                if ((a > b) == up) { buf[i] = b; buf[j] = a; }
+            }
+        }
+    __syncthreads();
+}
+
+// One CTA per query, over the query's row of estimates A[q][0..nc).
+//  1. t0: a loose upper bound of the k-th smallest estimate, from a sample (every 4th group of 32
+//     candidates): the r-th smallest sample key, r = k p + 4 sqrt(k p) + 4 (p = sample fraction),
+//     located with linear-range histograms (the keys of the range spread over the bins).
+//  2. One pass over all candidates: count a <= t0 (t0 is valid iff that reaches k) and stage every
+//     candidate with a <= t0 + 2E (or unknown) in shared memory.
+//  3. t1 = the exact k-th smallest estimate (it is staged); survivors = staged with a <= t1 + 2E,
+//     written in candidate order.
+// Anything unusual (t0 not valid, more than XF_STAGE staged, more than `cap` survivors, E not
+// finite) raises *overflow and the caller takes the exact dense kernel for the chunk.
+__global__ void __launch_bounds__(XF_THREADS)
+xf_select_kernel(const float* __restrict__ A, uint32_t lds, uint32_t nc, uint32_t k, const float* __restrict__ two_e_q, const uint32_t* __restrict__ rows, uint32_t cap,
+                 uint32_t* __restrict__ sel_rows, uint64_t* __restrict__ seg_beg, uint64_t* __restrict__ seg_end, int* __restrict__ overflow) {
+    __shared__ uint32_t u_mem[XF_BINS];               // histogram, later sort buffers
+    __shared__ uint32_t st_key[XF_STAGE], st_pos[XF_STAGE];
+    __shared__ uint32_t sm_scan[17];
+    __shared__ uint32_t sh_out[2];
+    __shared__ uint32_t sh_min, sh_max, sh_ns, sh_cnt, sh_nlow, sh_cnt2;
+    const uint32_t q = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float* a = A + (size_t)q * lds;
+    const float two_e = two_e_q[q];
+    if (threadIdx.x == 0) { sh_min = 0xffffffffu; sh_max = 0u; sh_ns = 0u; sh_cnt = 0u; sh_nlow = 0u; sh_cnt2 = 0u; seg_beg[q] = (uint64_t)q * cap; seg_end[q] = (uint64_t)q * cap; }
+    __syncthreads();
+    if (!(two_e >= 0.0f && two_e <= 3.0e38f)) { if (threadIdx.x == 0) atomicExch(overflow, 1); return; }
+
+    uint32_t t0 = 0xffffffffu;
+    if (nc > k) {
+        const uint32_t sf = (nc >= 16384u && nc >= 64u * k) ? XF_SAMPLE : 1u;
+        const uint32_t groups = (nc + 31u) / 32u, sgroups = (groups + sf - 1u) / sf;
+        uint32_t mn = 0xffffffffu, mx = 0u, cnt = 0u;
+        for (uint32_t j = warp; j < sgroups; j += XF_THREADS / 32) {
+            const uint32_t c = j * sf * 32u + lane;
+            if (c < nc) { const uint32_t key = xf_key(a[c]); mn = min(mn, key); mx = max(mx, key); ++cnt; }
+        }
+        mn = __reduce_min_sync(0xffffffffu, mn); mx = __reduce_max_sync(0xffffffffu, mx); cnt = __reduce_add_sync(0xffffffffu, cnt);
+        if (lane == 0) { atomicMin(&sh_min, mn); atomicMax(&sh_max, mx); atomicAdd(&sh_ns, cnt); }
+        __syncthreads();
+        const uint32_t ns = sh_ns;
+        uint32_t rlo = sh_min, rhi = sh_max;
+        uint32_t want;
+        if (sf == 1u) want = k;
+        else {
+            const float mean = (float)k * (float)ns / (float)nc;
+            want = (uint32_t)(mean + 4.0f * sqrtf(mean) + 4.0f) + 1u;
+        }
+        if (want > ns) want = ns;
+        for (int level = 0; level < 3 && rhi > rlo; ++level) {
+            for (int i = threadIdx.x; i < XF_BINS; i += XF_THREADS) u_mem[i] = 0;
+            __syncthreads();
+            const unsigned long long width = (unsigned long long)(rhi - rlo) + 1ull;
+            for (uint32_t j = warp; j < sgroups; j += XF_THREADS / 32) {
+                const uint32_t c = j * sf * 32u + lane;
+                if (c < nc) {
+                    const uint32_t key = xf_key(a[c]);
+                    if (key >= rlo && key <= rhi) atomicAdd(&u_mem[(uint32_t)(((unsigned long long)(key - rlo) * XF_BINS) / width)], 1u);
+                }
+            }
+            __syncthreads();
+            uint32_t before;
+            const uint32_t b = xf_find_bin(u_mem, want, sm_scan, sh_out, &before);
+            const uint32_t in_bin = u_mem[b];
+            __syncthreads();
+            // keys of bin b: (key - rlo) in [ceil(b * width / BINS), ceil((b + 1) * width / BINS) - 1]
+            const uint32_t nlo = rlo + (uint32_t)(((unsigned long long)b * width + XF_BINS - 1) / XF_BINS);
+            const uint32_t nhi = rlo + (uint32_t)(((unsigned long long)(b + 1) * width + XF_BINS - 1) / XF_BINS) - 1u;
+            want -= before; rlo = nlo; rhi = nhi;
+            if (in_bin <= 32u) break;
+        }
+        t0 = rhi;
+    }
+    const uint32_t T0 = xf_widen(t0, two_e);
+
+    // full pass: stage a <= t0 + 2E, count a <= t0
+    uint32_t nlow = 0;
+    for (uint32_t c = threadIdx.x; c < nc; c += XF_THREADS) {
+        const uint32_t key = xf_key(a[c]);
+        nlow += (key <= t0 && key != 0xffffffffu) ? 1u : 0u;
+        if (key <= T0 || key == 0xffffffffu) {
+            const uint32_t i = atomicAdd(&sh_cnt, 1u);
+            if (i < XF_STAGE) { st_key[i] = key; st_pos[i] = c; }
+        }
+    }
+    nlow = __reduce_add_sync(0xffffffffu, nlow);
+    if (lane == 0 && nlow) atomicAdd(&sh_nlow, nlow);
+    __syncthreads();
+    const uint32_t staged = sh_cnt;
+    if (staged > XF_STAGE || (nc > k && sh_nlow < k)) { if (threadIdx.x == 0) atomicExch(overflow, 1); return; }
+
+    // t1 = exact k-th smallest estimate
+    uint32_t T1 = 0xffffffffu;
+    if (nc > k) {
+        int np2 = 2;
+        while ((uint32_t)np2 < staged) np2 <<= 1;
+        for (int i = threadIdx.x; i < np2; i += XF_THREADS) u_mem[i] = (uint32_t)i < staged ? st_key[i] : 0xffffffffu;
+        xf_bitonic_u32(u_mem, np2);
+        T1 = xf_widen(u_mem[k - 1], two_e);
+        __syncthreads();
+    }
+    for (uint32_t i = threadIdx.x; i < staged; i += XF_THREADS)
+        if (st_key[i] <= T1 || st_key[i] == 0xffffffffu) u_mem[atomicAdd(&sh_cnt2, 1u)] = st_pos[i];
+    __syncthreads();
+    const uint32_t keep = sh_cnt2;
+    int kp2 = 2;
+    while ((uint32_t)kp2 < keep) kp2 <<= 1;
+    for (int i = keep + threadIdx.x; i < kp2; i += XF_THREADS) u_mem[i] = 0xffffffffu;
+    xf_bitonic_u32(u_mem, kp2);                       // back to candidate order (ties are broken by id)
+    uint32_t* out = sel_rows + (size_t)q * cap;
+    for (uint32_t i = threadIdx.x; i < keep && i < cap; i += XF_THREADS) out[i] = rows[u_mem[i]];
+    if (threadIdx.x == 0) {
+        seg_end[q] = (uint64_t)q * cap + (keep < cap ? keep : cap);
+        if (keep > cap) atomicExch(overflow, 1);
+    }
+}
+
 }  // namespace ab

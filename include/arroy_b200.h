@@ -194,10 +194,13 @@ int32_t arroy_b200_rerank_batch(arroy_ctx* ctx, uint32_t nq, const float* querie
                                 const uint32_t* rows, const uint64_t* row_offsets /* nq+1 */, uint32_t k,
                                 uint32_t* out_rows, float* out_dist, uint32_t* out_len);
 
-/* nq queries against ONE shared candidate list (BASELINE config 5: 4096 x 100k, d = 768): a dense
- * query x candidate contraction on a register-tiled kernel that keeps the reference's summation
- * order per pair, so ids and distances are identical to nq calls of arroy_b200_rerank. `rows`
- * ascending and unique. */
+/* nq queries against ONE shared candidate list (BASELINE config 5: 4096 x 100k, d = 768).
+ * Large problems (nq * n_rows >= 2^22, d >= 32, not Manhattan) run in two stages: a TF32
+ * tensor-core contraction bounds every pair's distance, which discards all candidates that
+ * provably cannot reach a query's top-k; the survivors are then re-scored in the reference's exact
+ * summation order. Small problems (or ARROY_B200_XRERANK=exact) use a register-tiled exact FP32
+ * kernel for every pair. Either way ids and distances are identical to nq calls of
+ * arroy_b200_rerank. `rows` ascending and unique. */
 int32_t arroy_b200_rerank_shared(arroy_ctx* ctx, uint32_t nq, const float* queries /* nq x dim */,
                                  const float* qhdr0 /* nq or NULL */, const uint32_t* rows, uint64_t n_rows, uint32_t k,
                                  uint32_t* out_rows, float* out_dist, uint32_t* out_len);
@@ -260,6 +263,19 @@ int32_t arroy_b200_build_breakdown(arroy_ctx* ctx, double out[8]);
 /* Counters since arroy_b200_create: out[0] = kernel launches issued by this library,
  * out[1] = bytes copied host->device, out[2] = bytes copied device->host, out[3] reserved. */
 int32_t arroy_b200_counters(arroy_ctx* ctx, uint64_t out[4]);
+
+/* The score matrix of the pre-filter, for tests and profiling: out_scores[q * n_rows + i] ~ dot(query q,
+ * item rows[i]) computed with TF32 inputs and FP32 accumulation on the tensor cores; guaranteed within
+ * 2^-8 * |q| * |item| of the exact dot product. engine 0 = the library's tcgen05 kernel, 1 = cuBLAS.
+ * Needs dim >= 32. */
+int32_t arroy_b200_prefilter_scores(arroy_ctx* ctx, uint32_t nq, const float* queries /* nq x dim */,
+                                    const uint32_t* rows, uint64_t n_rows, int32_t engine, float* out_scores);
+
+/* Pre-filter statistics of arroy_b200_rerank_shared since create: out[0] = query chunks that went
+ * through the tensor-core pre-filter, out[1] = chunks that fell back to the exact dense kernel
+ * (more survivors than the per-query cap), out[2] = survivors re-scored exactly (sum over
+ * queries), out[3] = queries pre-filtered. */
+int32_t arroy_b200_rerank_stats(arroy_ctx* ctx, uint64_t out[4]);
 
 /* CUDA-event stopwatch on the library's own stream (the stream every kernel above is launched
  * on): start records an event after draining the stream, stop records a second one, waits for

@@ -12,11 +12,13 @@ h0, _ = ctx.item_headers()
 q = items[n - nq:].cpu().numpy()            # queries = fresh rows after the candidates
 qh = h0[n - nq:]
 rows = np.arange(nc, dtype=np.uint32)
-for rep in range(3):
+for rep in range(6):
+    os.environ["ARROY_B200_XRERANK"] = "exact" if rep < 2 else "filter"
     ctx.timer_start(); t0 = time.perf_counter()
     out = ctx.rerank_shared(q, qh, rows, k)
     ms = ctx.timer_stop()
     flop = 2.0 * nq * nc * d
+    print(os.environ["ARROY_B200_XRERANK"], ctx.rerank_stats(), end=" ")
     print("rerank_shared %dx%d: wall %.1f ms, stream %.1f ms, %.1f TFLOP/s fp32 (%.1f TFMA/s)" % (nq, nc, (time.perf_counter() - t0) * 1e3, ms, flop / ms / 1e9, flop / 2 / ms / 1e9), flush=True)
 m = 128
 offs = (np.arange(m + 1, dtype=np.uint64) * np.uint64(nc))
