@@ -282,11 +282,15 @@ __global__ void xf_query_prep_kernel(const float* __restrict__ qnorm, const floa
     two_e[q] = __fmul_rn(__fmul_rn(2.0f, e), 1.0009765625f);
 }
 
-__device__ __forceinline__ uint32_t xf_key(float a) { return fabsf(a) <= 3.0e38f ? ordered_key(a) : 0xffffffffu; }   // unknown -> max
-__device__ __forceinline__ float xf_unkey(uint32_t k) {   // inverse of ordered_key for finite values
-    uint32_t b = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
-    return __uint_as_float(b);
+// monotone float -> uint32 key for finite estimates; NaN / infinite estimates are "unknown" = max
+__device__ __forceinline__ uint32_t xf_key(float a) {
+    const uint32_t b = __float_as_uint(a);
+    return fabsf(a) <= 3.0e38f ? (b ^ ((b & 0x80000000u) ? 0xffffffffu : 0x80000000u)) : 0xffffffffu;
 }
+__device__ __forceinline__ float xf_unkey(uint32_t k) {   // inverse of xf_key for finite values
+    return __uint_as_float(k ^ ((k & 0x80000000u) ? 0x80000000u : 0xffffffffu));
+}
+__device__ __forceinline__ bool xf_unknown(float a) { return !(fabsf(a) <= 3.0e38f); }
 __device__ __forceinline__ uint32_t xf_widen(uint32_t key, float two_e) {   // key of (value + 2E), max if not finite
     if (key == 0xffffffffu) return key;
     return xf_key(__fadd_rn(xf_unkey(key), two_e));
@@ -378,6 +382,7 @@ xf_select_kernel(const float* __restrict__ A, uint32_t lds, uint32_t nc, uint32_
     __syncthreads();
     if (!(two_e >= 0.0f && two_e <= 3.0e38f)) { if (threadIdx.x == 0) atomicExch(overflow, 1); return; }
 
+    // t0 (key) / t0f (float): loose upper bound of the k-th smallest estimate; T0f = t0f + 2E
     uint32_t t0 = 0xffffffffu;
     if (nc > k) {
         const uint32_t sf = (nc >= 16384u && nc >= 64u * k) ? XF_SAMPLE : 1u;
@@ -402,12 +407,14 @@ xf_select_kernel(const float* __restrict__ A, uint32_t lds, uint32_t nc, uint32_
         for (int level = 0; level < 3 && rhi > rlo; ++level) {
             for (int i = threadIdx.x; i < XF_BINS; i += XF_THREADS) u_mem[i] = 0;
             __syncthreads();
-            const unsigned long long width = (unsigned long long)(rhi - rlo) + 1ull;
+            // bin = (key - rlo) >> shift with the smallest shift that keeps every key of the range below XF_BINS
+            const uint32_t span = rhi - rlo;
+            const int shift = span < XF_BINS ? 0 : (32 - __clz(span)) - 12;
             for (uint32_t j = warp; j < sgroups; j += XF_THREADS / 32) {
                 const uint32_t c = j * sf * 32u + lane;
                 if (c < nc) {
                     const uint32_t key = xf_key(a[c]);
-                    if (key >= rlo && key <= rhi) atomicAdd(&u_mem[(uint32_t)(((unsigned long long)(key - rlo) * XF_BINS) / width)], 1u);
+                    if (key >= rlo && key <= rhi) atomicAdd(&u_mem[(key - rlo) >> shift], 1u);
                 }
             }
             __syncthreads();
@@ -415,31 +422,39 @@ xf_select_kernel(const float* __restrict__ A, uint32_t lds, uint32_t nc, uint32_
             const uint32_t b = xf_find_bin(u_mem, want, sm_scan, sh_out, &before);
             const uint32_t in_bin = u_mem[b];
             __syncthreads();
-            // keys of bin b: (key - rlo) in [ceil(b * width / BINS), ceil((b + 1) * width / BINS) - 1]
-            const uint32_t nlo = rlo + (uint32_t)(((unsigned long long)b * width + XF_BINS - 1) / XF_BINS);
-            const uint32_t nhi = rlo + (uint32_t)(((unsigned long long)(b + 1) * width + XF_BINS - 1) / XF_BINS) - 1u;
-            want -= before; rlo = nlo; rhi = nhi;
-            if (in_bin <= 32u) break;
+            const uint32_t nlo = rlo + (b << shift);
+            const uint32_t top = (uint32_t)min((unsigned long long)rhi, (unsigned long long)rlo + (((unsigned long long)b + 1ull) << shift) - 1ull);
+            want -= before; rlo = nlo; rhi = top;
+            if (in_bin <= 32u || shift == 0) break;
         }
         t0 = rhi;
     }
-    const uint32_t T0 = xf_widen(t0, two_e);
+    const bool all = t0 == 0xffffffffu;
+    const float t0f = all ? 0.f : xf_unkey(t0);
+    const float T0f = all ? 0.f : __fadd_rn(t0f, two_e);
+    const bool wide = all || xf_unknown(T0f);          // threshold not finite: everything is staged (and overflows)
 
-    // full pass: stage a <= t0 + 2E, count a <= t0
+    // full pass: stage a <= t0 + 2E (or unknown), count known a <= t0
     uint32_t nlow = 0;
-    for (uint32_t c = threadIdx.x; c < nc; c += XF_THREADS) {
-        const uint32_t key = xf_key(a[c]);
-        nlow += (key <= t0 && key != 0xffffffffu) ? 1u : 0u;
-        if (key <= T0 || key == 0xffffffffu) {
+    auto visit = [&](float v, uint32_t c) {
+        nlow += (v <= t0f && v >= -3.0e38f) ? 1u : 0u;
+        if (wide || !(v > T0f && v <= 3.0e38f)) {
             const uint32_t i = atomicAdd(&sh_cnt, 1u);
-            if (i < XF_STAGE) { st_key[i] = key; st_pos[i] = c; }
+            if (i < XF_STAGE) { st_key[i] = xf_key(v); st_pos[i] = c; }
         }
+    };
+    const uint32_t nc4 = nc & ~3u;
+    const float4* a4 = reinterpret_cast<const float4*>(a);           // lds % 4 == 0 and A is 16-byte aligned
+    for (uint32_t c = threadIdx.x * 4u; c < nc4; c += XF_THREADS * 4u) {
+        const float4 v = __ldg(a4 + (c >> 2));
+        visit(v.x, c); visit(v.y, c + 1u); visit(v.z, c + 2u); visit(v.w, c + 3u);
     }
+    if (threadIdx.x < nc - nc4) visit(a[nc4 + threadIdx.x], nc4 + threadIdx.x);
     nlow = __reduce_add_sync(0xffffffffu, nlow);
     if (lane == 0 && nlow) atomicAdd(&sh_nlow, nlow);
     __syncthreads();
     const uint32_t staged = sh_cnt;
-    if (staged > XF_STAGE || (nc > k && sh_nlow < k)) { if (threadIdx.x == 0) atomicExch(overflow, 1); return; }
+    if (staged > XF_STAGE || (nc > k && (all || sh_nlow < k))) { if (threadIdx.x == 0) atomicExch(overflow, 1); return; }
 
     // t1 = exact k-th smallest estimate
     uint32_t T1 = 0xffffffffu;
