@@ -58,6 +58,7 @@ SIGNATURES = [
     ("arroy_b200_build_breakdown", C.c_int32, [C.c_void_p, C.POINTER(C.c_double)]),
     ("arroy_b200_counters", C.c_int32, [C.c_void_p, _u64p]),
     ("arroy_b200_rerank_stats", C.c_int32, [C.c_void_p, _u64p]),
+    ("arroy_b200_rerank_breakdown", C.c_int32, [C.c_void_p, C.POINTER(C.c_double)]),
     ("arroy_b200_prefilter_scores", C.c_int32, [C.c_void_p, C.c_uint32, _f32p, _u32p, C.c_uint64, C.c_int32, _f32p]),
     ("arroy_b200_timer_start", C.c_int32, [C.c_void_p]),
     ("arroy_b200_timer_stop", C.c_int32, [C.c_void_p, _f32p]),
@@ -336,6 +337,11 @@ class Context:
         out = np.empty((queries.shape[0], rows.size), dtype=np.float32)
         self._ck(self.lib.arroy_b200_prefilter_scores(self.h, queries.shape[0], _fp(queries), _up(rows), rows.size, engine, _fp(out)))
         return out
+
+    def rerank_breakdown(self):
+        out = (C.c_double * 8)()
+        self._ck(self.lib.arroy_b200_rerank_breakdown(self.h, out))
+        return dict(zip(["prep_ms", "score_gemm_ms", "select_ms", "rescore_ms", "topk_ms", "exact_dense_ms"], list(out)[:6]))
 
     def rerank_stats(self):
         out = (C.c_uint64 * 4)()

@@ -138,6 +138,8 @@ struct arroy_ctx {
     cublasHandle_t blas = nullptr;
     DevBuf x_gather, x_cnorm, x_ca, x_cb, x_gmax, x_qa, x_qb, x_twoe, x_qnorm, x_S, x_sel, x_beg, x_end, x_flag;
     uint64_t xf_calls = 0, xf_fallbacks = 0, xf_selected = 0, xf_queries = 0;
+    cudaEvent_t xev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    double xbreak[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // last rerank_shared call, ms: prep, score GEMM, select, re-score, top-k, exact dense path
 };
 
 namespace {
@@ -883,6 +885,7 @@ void arroy_b200_destroy(arroy_ctx* c) {
     for (auto* b : bufs) b->release();
     { DevBuf* xb[] = {&c->x_gather, &c->x_cnorm, &c->x_ca, &c->x_cb, &c->x_gmax, &c->x_qa, &c->x_qb, &c->x_twoe, &c->x_qnorm, &c->x_S, &c->x_sel, &c->x_beg, &c->x_end, &c->x_flag}; for (auto* b : xb) b->release(); }
     if (c->blas) cublasDestroy(c->blas);
+    for (auto& e : c->xev) if (e) cudaEventDestroy(e);
     if (c->cached_exec) cudaGraphExecDestroy(c->cached_exec);
     if (c->cached_graph) cudaGraphDestroy(c->cached_graph);
     for (auto& sw : c->stage_workers) { sw.pin[0].release(); sw.pin[1].release(); if (sw.ev[0]) cudaEventDestroy(sw.ev[0]); if (sw.ev[1]) cudaEventDestroy(sw.ev[1]); if (sw.st) cudaStreamDestroy(sw.st); }
@@ -1171,6 +1174,7 @@ int32_t arroy_b200_rerank_shared(arroy_ctx* c, uint32_t nq, const float* queries
             return;
         }
         const uint32_t ld = c->ld, nc = (uint32_t)n_rows;
+        for (double& x : c->xbreak) x = 0;
         c->s_rows.ensure(4ull * nc);
         CK(cudaMemcpyAsync(c->s_rows.p, rows, 4ull * nc, cudaMemcpyHostToDevice, c->stream));
         // ARROY_B200_XRERANK = exact | filter; default: the tensor-core pre-filter once the problem is big enough to pay for it
@@ -1203,9 +1207,8 @@ int32_t arroy_b200_rerank_shared(arroy_ctx* c, uint32_t nq, const float* queries
             if (qhdr0) CK(cudaMemcpyAsync(c->s_qh0.p, qhdr0 + q0, 4ull * m, cudaMemcpyHostToDevice, c->stream));
             else CK(cudaMemsetAsync(c->s_qh0.p, 0, 4ull * m, c->stream));
             bool done = false;
-            static const bool xf_trace = getenv("ARROY_B200_XF_TRACE") != nullptr;
-            cudaEvent_t te[8]; int nte = 0;
-            auto mark = [&]() { if (xf_trace && nte < 8) { CK(cudaEventCreate(&te[nte])); CK(cudaEventRecord(te[nte], c->stream)); ++nte; } };
+            int nte = 0;
+            auto mark = [&]() { if (!c->xev[nte]) CK(cudaEventCreate(&c->xev[nte])); CK(cudaEventRecord(c->xev[nte], c->stream)); ++nte; };
             if (filter) {
                 c->xf_calls += 1;
                 mark();
@@ -1217,6 +1220,7 @@ int32_t arroy_b200_rerank_shared(arroy_ctx* c, uint32_t nq, const float* queries
                 xf_query_prep_kernel<<<(m + 255) / 256, 256, 0, c->stream>>>(c->x_qnorm.as<float>(), c->s_qh0.as<float>(), m, c->metric, xf_rel(c->dim), c->dim, c->x_gmax.as<uint32_t>(),
                                                                              c->x_qa.as<float>(), c->x_qb.as<float>(), c->x_twoe.as<float>());
                 CK(cudaGetLastError());
+                mark();
                 // A (m x nc, row-major) = distance estimates: Q . cand^T on the tensor cores (TF32 inputs, FP32 accumulate) + fused epilogue
                 TgEpilogue ep{c->metric == EUCLIDEAN ? TG_EUCLID : (c->metric == COSINE ? TG_COSINE : TG_NEG), c->x_qa.as<float>(), c->x_qb.as<float>(), c->x_ca.as<float>(), c->x_cb.as<float>()};
                 xf_scores(c, c->s_q.as<float>(), m, cand, nc, c->x_S.as<float>(), lds, ep, xf_engine());
@@ -1242,11 +1246,7 @@ int32_t arroy_b200_rerank_shared(arroy_ctx* c, uint32_t nq, const float* queries
                 int flag = 0;
                 CK(cudaMemcpyAsync(&flag, c->x_flag.p, 4, cudaMemcpyDeviceToHost, c->stream));
                 CK(cudaStreamSynchronize(c->stream));
-                if (xf_trace) {
-                    const char* names[] = {"norms+gemm", "select", "rescore", "topk"};
-                    for (int i = 0; i + 1 < nte; ++i) { float ms = 0; cudaEventElapsedTime(&ms, te[i], te[i + 1]); fprintf(stderr, "[xf] %s %.3f ms\n", names[i], ms); }
-                    for (int i = 0; i < nte; ++i) cudaEventDestroy(te[i]);
-                }
+                for (int i = 0; i + 1 < nte; ++i) { float ms = 0; CK(cudaEventElapsedTime(&ms, c->xev[i], c->xev[i + 1])); c->xbreak[i] += ms; }
                 done = flag == 0;
                 { std::vector<uint64_t> ends(m); CK(cudaMemcpy(ends.data(), c->x_end.p, 8ull * m, cudaMemcpyDeviceToHost));
                   for (uint32_t q = 0; q < m; ++q) c->xf_selected += ends[q] - (uint64_t)q * cap; c->xf_queries += m; }
@@ -1254,6 +1254,7 @@ int32_t arroy_b200_rerank_shared(arroy_ctx* c, uint32_t nq, const float* queries
             }
             if (!done) {
                 c->s_dists.ensure(4ull * m * nc);
+                nte = 0; mark();
                 dim3 grid((nc + XCB - 1) / XCB, (m + XQB - 1) / XQB);
                 if (c->metric == EUCLIDEAN)
                     xrerank_kernel<true><<<grid, XTHREADS, 0, c->stream>>>(c->items.as<float>(), c->h0.as<float>(), c->dim, ld, c->metric, c->s_q.as<float>(), c->s_qh0.as<float>(), m,
@@ -1266,6 +1267,9 @@ int32_t arroy_b200_rerank_shared(arroy_ctx* c, uint32_t nq, const float* queries
                                                                      c->s_orows.as<uint32_t>(), c->s_odist.as<float>(), c->s_olen.as<uint32_t>());
                 CK(cudaGetLastError());
                 c->n_launches += 2;
+                mark();
+                CK(cudaStreamSynchronize(c->stream));
+                { float ms = 0; CK(cudaEventElapsedTime(&ms, c->xev[0], c->xev[1])); c->xbreak[5] += ms; }
             }
             CK(cudaMemcpyAsync(out_rows + (size_t)q0 * k, c->s_orows.p, 4ull * m * k, cudaMemcpyDeviceToHost, c->stream));
             CK(cudaMemcpyAsync(out_dist + (size_t)q0 * k, c->s_odist.p, 4ull * m * k, cudaMemcpyDeviceToHost, c->stream));
@@ -1513,6 +1517,10 @@ int32_t arroy_b200_prefilter_scores(arroy_ctx* c, uint32_t nq, const float* quer
         CK(cudaMemcpy2DAsync(out_scores, 4ull * nc, c->x_S.p, 4ull * lds, 4ull * nc, nq, cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
     });
+}
+
+int32_t arroy_b200_rerank_breakdown(arroy_ctx* c, double out[8]) {
+    return guarded(c, [&] { for (int i = 0; i < 8; ++i) out[i] = c->xbreak[i]; });
 }
 
 int32_t arroy_b200_rerank_stats(arroy_ctx* c, uint64_t out[4]) {

@@ -14,6 +14,9 @@ number i*d+j of StdRng::from_seed([42;32]) minus 0.5; build rng = fresh StdRng([
   c4            10 000 000 x 1536 Cosine     n_trees = 100   (meant for 8 GPUs)
   c1            10 000 x 64      Euclidean   n_trees = 10    (raw [0,1) data)
   small         100 000 x 768    Cosine      n_trees = 16    (quick check)
+  c5            4096 queries x 100 000 shared candidates, d = 768, Cosine, top-100: the batched
+                re-rank (reader.rs:381-399) as a tcgen05 TF32 pre-filter + exact re-score; its own
+                metric (queries/s) and a "tensor" roofline for the score contraction
 
 Keys beyond the base contract: "roofline" (dominant kernel = the side()/margin scan inside
 work_kernel), "cpu_baseline", "e2e" (through Writer.builder(rng).build() with the items as host
@@ -38,6 +41,7 @@ WORKLOADS = {
     "c4": dict(n=10_000_000, d=1536, metric="cosine", n_trees=100, centre=0.5, name="C4 10Mx1536 Cosine n_trees=100"),
     "c1": dict(n=10_000, d=64, metric="euclidean", n_trees=10, centre=0.0, name="C1 10kx64 Euclidean n_trees=10"),
     "small": dict(n=100_000, d=768, metric="cosine", n_trees=16, centre=0.5, name="small 100kx768 Cosine n_trees=16"),
+    "c5": dict(n=100_000, d=768, metric="cosine", n_trees=0, centre=0.5, nq=4096, k=100, name="C5 4096 queries x 100k candidates re-rank, d=768 Cosine top-100"),
 }
 
 
@@ -149,6 +153,154 @@ def run_reference(args, wl):
     print(json.dumps(line), flush=True)
 
 
+
+def tensor_peak():
+    """TF32 dense peak: half the measured dense bf16 rate (tcgen05 kind::tf32 runs at half the kind::f16 rate)."""
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        if "bf16_tflops_sustained" in d:
+            return d["bf16_tflops_sustained"] / 2.0, "measured bf16 sustained %.1f TFLOP/s / 2 (TF32 rate; MEASURED_PEAKS.json)" % d["bf16_tflops_sustained"]
+    return 1100.0, "fallback: nominal dense TF32 (B200_PROFILING.md)"
+
+
+def c5_cpu(wl, data_host, qh, n_queries, threads):
+    """The reference's re-rank loop (oracle port) for a few queries, one query per thread."""
+    import numpy as np
+    import oracle
+    from concurrent.futures import ThreadPoolExecutor
+    n, nq, k = wl["n"], wl["nq"], wl["k"]
+    rows = np.arange(n, dtype=np.uint32)
+    hdr = qh
+    m = oracle.METRICS[wl["metric"]]
+
+    def one(i):
+        return oracle.rerank(m, data_host[n + i], (float(hdr[n + i]), 0.0), data_host, hdr, None, rows, k)
+    one(0)
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        res = list(ex.map(one, range(n_queries)))
+    return n_queries / (time.perf_counter() - t0), res
+
+
+def run_c5(args, wl):
+    """BASELINE.json configs[4]: batched 4096-query x 100k-candidate re-rank, d = 768, 1 GPU (replicas for N > 1)."""
+    import numpy as np
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    n, d, nq, k, metric = wl["n"], wl["d"], wl["nq"], wl["k"], wl["metric"]
+    cores = os.cpu_count() or 1
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        import oracle
+        oracle.build_lib()
+        data = oracle.synth_rows(SEED, d, 0, n + nq, wl["centre"], threads=min(cores, 64))
+        hdr = np.sqrt((data.astype(np.float64) ** 2).sum(1)).astype(np.float32)   # only the timing matters here
+        sample = min(nq, max(2 * cores, 64))
+        qps = []
+        for step in range(args.warmup + args.steps):
+            v, _ = c5_cpu(wl, data, hdr, sample, cores)
+            if step >= args.warmup:
+                qps.append(v)
+        value = sum(qps) / len(qps)
+        print(json.dumps({"impl": "reference", "metric": "batched re-rank queries/sec", "value": value, "unit": "queries/s", "n_gpus": args.gpus, "steps": args.steps,
+                          "warmup": args.warmup, "ms_per_step": sample / value * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                          "data": "synthetic", "config": {"workload": wl["name"], "n_candidates": n, "n_queries": nq, "d": d, "distance": metric, "k": k},
+                          "cpu_baseline": {"value": value, "unit": "queries/s", "cores": cores, "kind": "port", "sample": "%d of %d queries per step, one query per thread" % (sample, nq)},
+                          "e2e": {"value": value, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}), flush=True)
+        return
+    import torch
+    import __graft_entry__ as ge
+    if rank == 0:
+        ge.build()
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.barrier()
+    import arroy_b200 as ab
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    ctx = ab.Context(local_rank)
+    items = torch.empty((n + nq, d), dtype=torch.float32, device=dev)
+    ctx.synth_device(SEED, d, 0, n + nq, wl["centre"], items.data_ptr())
+    ctx.stage_items_device(metric, np.arange(n + nq, dtype=np.uint32), d, items.data_ptr())
+    h0, _ = ctx.item_headers()
+    q_host = items[n:].cpu().numpy()          # queries = the rows that continue the stream after the candidates (SURVEY.md §8d)
+    qh = np.ascontiguousarray(h0[n:])
+    rows = np.arange(n, dtype=np.uint32)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    out = None
+    for _ in range(max(args.warmup, 1)):
+        out = ctx.rerank_shared(q_host, qh, rows, k)
+    c0 = ctx.counters()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    ctx.timer_start()
+    t0 = time.perf_counter()
+    gemm_ms = []
+    for _ in range(args.steps):
+        out = ctx.rerank_shared(q_host, qh, rows, k)
+        gemm_ms.append(ctx.rerank_breakdown())
+    dev_ms = ctx.timer_stop()
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+    c1 = ctx.counters()
+    t_ms = torch.tensor([max(dev_ms, 0.0)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t_ms.item()) / args.steps
+    value = world * nq / (ms_per_step * 1e-3)
+    bd = {kk: sum(b[kk] for b in gemm_ms) / len(gemm_ms) for kk in gemm_ms[0]}
+    stats = ctx.rerank_stats()
+    peak, peak_src = tensor_peak()
+    flop = 2.0 * nq * n * d
+    line = {
+        "metric": "batched re-rank queries/sec", "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (tf32 tensor-core pre-filter, exact f32 re-score)", "data": "synthetic",
+        "config": {"workload": wl["name"], "n_candidates": n, "n_queries": nq, "d": d, "distance": metric, "k": k, "parallelism": "replicas only (re-rank is single-GPU)",
+                   "l2": "score matrix (1.6 GB) and candidates (307 MB) larger than L2; no flush needed",
+                   "timing": "CUDA events on the library stream around the C-ABI call (host query / result buffers, copies included), max over ranks"},
+        "gpu_launches": int(c1["launches"] - c0["launches"]),
+        "rerank": {"breakdown_ms": bd, "survivors_per_query": stats["survivors"] / max(stats["queries"], 1), "fallback_chunks": stats["fallback_chunks"],
+                   "exact_pairs_per_s": nq * n / (ms_per_step * 1e-3)},
+        "roofline": {"bound": "tensor", "kernel": "tcgemm_tf32_kernel (tcgen05.mma kind::tf32 + TMA + TMEM, fused distance-estimate epilogue)",
+                     "achieved": flop / (bd["score_gemm_ms"] * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s", "frac": flop / (bd["score_gemm_ms"] * 1e-3) / 1e12 / peak,
+                     "peak_source": peak_src, "traffic": 1.919e9,
+                     "traffic_note": "dram read 0.330 GB + write 1.589 GB per launch (profiles/r01_c5_prefilter_ncu_raw.csv); operand traffic L2->SM is 14.7 GB per launch, the actual limiter"},
+        "e2e": {"value": world * nq / (wall / args.steps), "unit": "queries/s", "h2d_bytes_per_step": int((c1["h2d_bytes"] - c0["h2d_bytes"]) / args.steps),
+                "d2h_bytes_per_step": int((c1["d2h_bytes"] - c0["d2h_bytes"]) / args.steps), "note": "wall clock around arroy_b200_rerank_shared with pageable host buffers"},
+        "clocks": clocks,
+    }
+    if rank == 0:
+        if not args.no_cpu_baseline:
+            import oracle
+            oracle.build_lib()
+            data_host = items.cpu().numpy()
+            sample = min(nq, max(cores, 32))
+            v, res = c5_cpu(wl, data_host, h0, sample, cores)
+            same = all(out[0][i, :out[2][i]].tolist() == res[i][0].tolist() and out[1][i, :out[2][i]].tobytes() == res[i][1].tobytes() for i in range(sample))
+            line["cpu_baseline"] = {"value": v, "unit": "queries/s", "cores": cores, "kind": "port", "sample": "%d of %d queries, one query per thread" % (sample, nq),
+                                    "results_identical_on_sample": bool(same)}
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -164,6 +316,9 @@ def main():
     ap.add_argument("--queries", type=int, default=1000)
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
+    if args.workload == "c5":
+        run_c5(args, wl)
+        return
     if args.impl == "reference":
         run_reference(args, wl)
         return

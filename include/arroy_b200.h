@@ -277,6 +277,12 @@ int32_t arroy_b200_prefilter_scores(arroy_ctx* ctx, uint32_t nq, const float* qu
  * queries), out[3] = queries pre-filtered. */
 int32_t arroy_b200_rerank_stats(arroy_ctx* ctx, uint64_t out[4]);
 
+/* CUDA-event breakdown of the last arroy_b200_rerank_shared call (ms, summed over its query chunks):
+ * [0] norms + bound constants, [1] score contraction on the tensor cores (tcgemm_tf32_kernel),
+ * [2] threshold selection, [3] exact re-score of the survivors, [4] top-k, [5] exact dense kernel +
+ * top-k (chunks that did not go through the pre-filter), [6..7] reserved. */
+int32_t arroy_b200_rerank_breakdown(arroy_ctx* ctx, double out[8]);
+
 /* CUDA-event stopwatch on the library's own stream (the stream every kernel above is launched
  * on): start records an event after draining the stream, stop records a second one, waits for
  * it and returns the elapsed milliseconds between the two. */
