@@ -70,9 +70,9 @@ struct PinBuf {
 };
 
 struct Wave {  // device buffers of one wave of trees; kept across builds
-    DevBuf st, frames, recs, perm0, perm1, flags, unit_left, pool, pool_counter, jobs, scratch, active, error, final_ids, keys, sub_rows, sub_off;
+    DevBuf st, frames, recs, perm0, perm1, flags, unit_left, pool, pool_counter, jobs, scratch, active, error, final_ids, keys, sub_rows, sub_off, timing;
     void release() {
-        sub_rows.release(); sub_off.release();
+        sub_rows.release(); sub_off.release(); timing.release();
         st.release(); frames.release(); recs.release(); perm0.release(); perm1.release(); flags.release(); unit_left.release();
         pool.release(); pool_counter.release(); jobs.release(); scratch.release(); active.release(); error.release(); final_ids.release(); keys.release();
     }
@@ -309,7 +309,8 @@ void build_wave(arroy_ctx* c, size_t wave_no, uint32_t t0, uint32_t tw, const ui
     const uint64_t leaves_est = n / std::max<uint32_t>(K, 1) + 1;
     const uint64_t rec_cap64 = std::min<uint64_t>(2 * n + 2, std::max<uint64_t>(64, 8 * leaves_est * cap_mult));
     const uint32_t rec_cap = (uint32_t)rec_cap64;
-    const uint64_t pool_cap64 = std::min<uint64_t>((uint64_t)tw * (n + 1), (uint64_t)tw * (4 * leaves_est * cap_mult + 2));
+    // (+ 8 per tree: slots are handed out eight at a time)
+    const uint64_t pool_cap64 = std::min<uint64_t>((uint64_t)tw * (n + 1), (uint64_t)tw * (4 * leaves_est * cap_mult + 2)) + 8ull * tw;
     if (pool_cap64 > 0xfffffff0ull) throw CapacityError("normal pool too large");
     const uint32_t pool_cap = (uint32_t)pool_cap64;
     const uint32_t pool_stride = ld + NORMAL_HDR;
@@ -341,6 +342,10 @@ void build_wave(arroy_ctx* c, size_t wave_no, uint32_t t0, uint32_t tw, const ui
     P.jobs = W.jobs.as<Job>(); P.scratch = W.scratch.as<float>(); P.use_smem_ws = use_smem;
     P.active = W.active.as<uint32_t>(); P.error = W.error.as<int32_t>();
     P.sub_rows = nullptr; P.sub_off = nullptr;
+    P.small_max = getenv("ARROY_B200_SMALL_MAX") ? (uint32_t)atoi(getenv("ARROY_B200_SMALL_MAX")) : 2048u;
+    P.max_inner = 48u;
+    P.timing = nullptr;
+    if (getenv("ARROY_B200_CTRL_TIMING")) { W.timing.ensure(16 * 8); CK(cudaMemsetAsync(W.timing.p, 0, 16 * 8, c->stream)); P.timing = W.timing.as<unsigned long long>(); }
     if (sub.rows) {   // this wave's subsets, offsets rebased to the wave
         const uint64_t b = sub.off[t0], e = sub.off[t0 + tw];
         std::vector<uint64_t> off(tw + 1);
@@ -368,7 +373,7 @@ void build_wave(arroy_ctx* c, size_t wave_no, uint32_t t0, uint32_t tw, const ui
     c->n_launches += 2;  // + finalize_kernel below
 
     const size_t ctrl_smem = use_smem ? ws_bytes : 0;
-    if (ctrl_smem > 48 * 1024) CK(cudaFuncSetAttribute(control_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctrl_smem));
+    if (ctrl_smem > 48 * 1024) CK(cudaFuncSetAttribute(control_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctrl_smem));
     const size_t wsmem = work_smem(ld, (int)tw);
     if (wsmem > 48 * 1024) CK(cudaFuncSetAttribute(work_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
     const int work_grid = c->sm_count * 3;
@@ -387,13 +392,36 @@ void build_wave(arroy_ctx* c, size_t wave_no, uint32_t t0, uint32_t tw, const ui
     const int tree_grid = c->sm_count;  // work CTAs per tree launch in async mode
     const int interleave = (getenv("ARROY_B200_INTERLEAVE") != nullptr && atoi(getenv("ARROY_B200_INTERLEAVE")) != 0) ? 1 : 0;
     const size_t wsmem1 = work_smem(ld, 1);
+    // Few trees on this GPU = the chain of attempts of each tree is the critical path: run the control
+    // kernel as a thread-block cluster that scans small nodes itself (build.cuh). ARROY_B200_CLUSTER = 0 | 8 | 16.
+    int cluster = 1;
+    if (!lockstep && use_smem) {
+        const char* e = getenv("ARROY_B200_CLUSTER");
+        if (e) { int v = atoi(e); cluster = (v == 8 || v == 16) ? v : 1; }
+        // measured: d = 64, 1-10 trees: 24 -> 20 us per attempt; d = 768: 38 -> 37 us for one tree but slower from ~6 trees on
+        else if (c->dim <= 256) cluster = tw <= 8 ? 16 : (tw <= 16 ? 8 : 1);
+    }
+    if (cluster > 1) {
+        if (cluster == 8) CK(cudaFuncSetAttribute(control_kernel<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctrl_smem));
+        else {
+            CK(cudaFuncSetAttribute(control_kernel<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctrl_smem));
+            CK(cudaFuncSetAttribute(control_kernel<true, 16>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        }
+    }
 
     auto launch_step = [&](cudaStream_t s) {  // lockstep: all trees per launch
-        if (use_smem) control_kernel<true><<<tw, CTRL_THREADS, ctrl_smem, s>>>(P, 0u); else control_kernel<false><<<tw, CTRL_THREADS, 0, s>>>(P, 0u);
+        if (use_smem) control_kernel<true, 1><<<tw, CTRL_THREADS, ctrl_smem, s>>>(P, 0u); else control_kernel<false, 1><<<tw, CTRL_THREADS, 0, s>>>(P, 0u);
         work_kernel<<<work_grid, WORK_THREADS, wsmem, s>>>(P.jobs, (int)tw, P.items, P.ih0, P.d, P.ld, P.metric, interleave);
     };
     auto launch_tree_step = [&](uint32_t t, cudaStream_t s) {  // async: one tree per launch
-        if (use_smem) control_kernel<true><<<1, CTRL_THREADS, ctrl_smem, s>>>(P, t); else control_kernel<false><<<1, CTRL_THREADS, 0, s>>>(P, t);
+        if (cluster > 1) {
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3((unsigned)cluster); cfg.blockDim = dim3(CTRL_THREADS); cfg.dynamicSmemBytes = ctrl_smem; cfg.stream = s;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = (unsigned)cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            if (cluster == 8) CK(cudaLaunchKernelEx(&cfg, control_kernel<true, 8>, P, t)); else CK(cudaLaunchKernelEx(&cfg, control_kernel<true, 16>, P, t));
+        } else if (use_smem) control_kernel<true, 1><<<1, CTRL_THREADS, ctrl_smem, s>>>(P, t); else control_kernel<false, 1><<<1, CTRL_THREADS, 0, s>>>(P, t);
         work_kernel<<<tree_grid, WORK_THREADS, wsmem1, s>>>(P.jobs + t, 1, P.items, P.ih0, P.d, P.ld, P.metric, 0);
     };
     if (!lockstep) {
@@ -411,7 +439,7 @@ void build_wave(arroy_ctx* c, size_t wave_no, uint32_t t0, uint32_t tw, const ui
     if (use_graph) {
         std::vector<uint8_t> key(sizeof(BuildParams) + 16);
         memcpy(key.data(), &P, sizeof(BuildParams));
-        int32_t sched[4] = {(lockstep ? 1 : 0) | (interleave << 1), steps_per_batch, (int32_t)tw, (int32_t)ctrl_smem};
+        int32_t sched[4] = {(lockstep ? 1 : 0) | (interleave << 1) | (cluster << 8), steps_per_batch, (int32_t)tw, (int32_t)ctrl_smem};
         memcpy(key.data() + sizeof(BuildParams), sched, 16);
         if (c->cached_exec && key == c->cached_graph_key) gexec = c->cached_exec;
         else {
@@ -456,7 +484,7 @@ void build_wave(arroy_ctx* c, size_t wave_no, uint32_t t0, uint32_t tw, const ui
         if (use_graph) CK(cudaGraphLaunch(gexec, c->stream));
         else if (profile) {
             for (int i = 0; i < steps_per_batch; ++i) {
-                if (use_smem) control_kernel<true><<<tw, CTRL_THREADS, ctrl_smem, c->stream>>>(P, 0u); else control_kernel<false><<<tw, CTRL_THREADS, 0, c->stream>>>(P, 0u);
+                if (use_smem) control_kernel<true, 1><<<tw, CTRL_THREADS, ctrl_smem, c->stream>>>(P, 0u); else control_kernel<false, 1><<<tw, CTRL_THREADS, 0, c->stream>>>(P, 0u);
                 CK(cudaEventRecord(pev[2 * i], c->stream));
                 work_kernel<<<work_grid, WORK_THREADS, wsmem, c->stream>>>(P.jobs, (int)tw, P.items, P.ih0, P.d, P.ld, P.metric, interleave);
                 CK(cudaEventRecord(pev[2 * i + 1], c->stream));
@@ -493,6 +521,14 @@ void build_wave(arroy_ctx* c, size_t wave_no, uint32_t t0, uint32_t tw, const ui
     }
     c->stats[1] += (double)steps;
     c->breakdown[2] += ms_since(t_loop);
+    if (P.timing) {
+        unsigned long long tv[16]; CK(cudaMemcpy(tv, P.timing, sizeof(tv), cudaMemcpyDeviceToHost));
+        const char* nm[16] = {"decide", "rng", "gather", "norms", "two_means_rest", "finish_split", "cluster_scan", "prefix", "partition", "attempts", "inner", "total", "tm_dot_rest", "tm_update", "tm_dots", "tm_finish"};
+        const double att = (double)std::max<unsigned long long>(tv[9], 1);
+        fprintf(stderr, "[ctrl timing] attempts %llu, in-cluster %llu; cycles per attempt:", tv[9], tv[10]);
+        for (int i = 0; i < 16; ++i) if (i != 9 && i != 10) fprintf(stderr, " %s %.0f", nm[i], (double)tv[i] / att);
+        fprintf(stderr, "\n");
+    }
     c->breakdown[5] += (double)(steps / steps_per_batch);
     auto t_d2h = std::chrono::steady_clock::now();
 

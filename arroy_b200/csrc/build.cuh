@@ -12,6 +12,7 @@
 //     work_kernel      all SMs: the side() scans (and wide partitions) of all trees.
 // Node records come out tree-local and post-order; the host turns them into NodeCodec bytes.
 #pragma once
+#include <cooperative_groups.h>
 #include "kernels.cuh"
 
 namespace ab {
@@ -49,8 +50,10 @@ struct TreeState {
     uint32_t cur_slot;       // pool slot holding the current attempt's normal (NO_SLOT = none reserved)
     uint32_t n_recs;
     uint32_t n_splits_tried, n_random;
-    uint32_t pad;
+    uint32_t slot_next;      // pool slots are taken from the shared counter eight at a time: [slot_next, slot_end)
     uint64_t scanned;        // rows that went through side()
+    uint32_t slot_end;
+    uint32_t pad;
 };
 
 struct BuildParams {
@@ -72,6 +75,10 @@ struct BuildParams {
     // instead of all n rows (incremental builds: one subtree per over-full descendant)
     const uint32_t* sub_rows;
     const uint64_t* sub_off;
+    // cluster-resident small nodes (control_kernel<.., CS > 1>): nodes of at most small_max rows are
+    // scanned by the control kernel's own cluster, at most max_inner attempts per launch
+    uint32_t small_max, max_inner;
+    unsigned long long* timing;   // optional: 16 cycle counters summed over all control launches (ARROY_B200_CTRL_TIMING)
 };
 
 __device__ __forceinline__ double split_imbalance_dev(uint32_t l, uint32_t r) {  // src/writer.rs:1348-1353
@@ -83,7 +90,7 @@ __device__ __forceinline__ double split_imbalance_dev(uint32_t l, uint32_t r) { 
 
 // ---- two_means + create_split on one CTA ----------------------------------------------------
 // ws: WS_VECS vectors of ld floats: ws[0]=p, ws[1]=q, ws[2..11]=the ten sampled k,
-// ws[12], ws[13] = scratch (normal / bias terms / Manhattan terms).
+// ws[12], ws[13] = scratch (normal / bias terms / Manhattan terms / k / norm of the current iteration).
 constexpr int WS_VECS = 14;
 struct TwoMeansShared {
     uint32_t rows[12];
@@ -92,7 +99,49 @@ struct TwoMeansShared {
     float res[2][2];        // di, dj, double buffered by iteration parity
     float php[2], phq[2];   // headers of p and q
     float misc[2];
+    long long tacc[16];     // cycle accumulators of the phases (thread 0; flushed to BuildParams::timing when set)
+    long long tlast;
 };
+// phase ids of BuildParams::timing
+enum { TP_DECIDE = 0, TP_RNG = 1, TP_GATHER = 2, TP_NORMS = 3, TP_TWOMEANS = 4, TP_FINISH_SPLIT = 5, TP_CLUSTER_SCAN = 6, TP_PREFIX = 7, TP_PARTITION = 8, TP_ATTEMPTS = 9, TP_INNER = 10, TP_TOTAL = 11, TP_TM_DOT = 12, TP_TM_UPD = 13 };
+#define TP_MARK(S_, id_) do { if (P.timing != nullptr && threadIdx.x == 0) { long long now_ = clock64(); (S_).tacc[id_] += now_ - (S_).tlast; (S_).tlast = now_; } } while (0)
+
+// hsum256 of the four accumulators + ((h1+h2)+h3)+h4 when lane l holds accumulator lane l (simple_avx.rs:6-13)
+__device__ __forceinline__ float warp_hsum_exact(float acc) {
+    const unsigned full = 0xffffffffu;
+    acc = __fadd_rn(acc, __shfl_xor_sync(full, acc, 4));
+    acc = __fadd_rn(acc, __shfl_xor_sync(full, acc, 2));
+    acc = __fadd_rn(acc, __shfl_xor_sync(full, acc, 1));
+    const float h1 = __shfl_sync(full, acc, 0), h2 = __shfl_sync(full, acc, 8), h3 = __shfl_sync(full, acc, 16), h4 = __shfl_sync(full, acc, 24);
+    return __fadd_rn(__fadd_rn(__fadd_rn(h1, h2), h3), h4);
+}
+
+// dot(a, b) [Euclidean: sum (a-b)^2] and dot(a, a) of one vector pair on one warp, lane l = accumulator lane l
+// (scalar loads, conflict-free; two independent FMA chains per lane). All 32 lanes must call.
+template <bool EUCLID>
+__device__ __forceinline__ void exact_warp_ab_aa(const float* a, const float* b, int n, float& ab, float& aa) {
+    const int lane = threadIdx.x & 31;
+    if (n >= 32) {
+        const int m = n & ~31;
+        float acc = 0.f, acc2 = 0.f;
+#pragma unroll 8
+        for (int i = lane; i < m; i += 32) {
+            const float x = a[i], y = b[i];
+            if (EUCLID) { const float t = __fsub_rn(x, y); acc = fmaf(t, t, acc); }
+            else { acc = fmaf(x, y, acc); acc2 = fmaf(x, x, acc2); }
+        }
+        float r = warp_hsum_exact(acc), r2 = EUCLID ? 0.f : warp_hsum_exact(acc2);
+        for (int i = m; i < n; ++i) {
+            if (EUCLID) { const float t = __fsub_rn(a[i], b[i]); r = __fadd_rn(r, __fmul_rn(t, t)); }
+            else { r = __fadd_rn(r, __fmul_rn(a[i], b[i])); r2 = __fadd_rn(r2, __fmul_rn(a[i], a[i])); }
+        }
+        ab = r; aa = r2;
+    } else {
+        float r = 0.f, r2 = 0.f;
+        if (lane == 0) { r = exact_thread<EUCLID>(a, b, n); if (!EUCLID) r2 = exact_thread<false>(a, a, n); }
+        ab = __shfl_sync(0xffffffffu, r, 0); aa = __shfl_sync(0xffffffffu, r2, 0);
+    }
+}
 
 __device__ __forceinline__ float norm_leaf_group(int metric, const float* v, float h0, int d) {
     float dot = exact_group8<false>(v, v, d);
@@ -113,12 +162,37 @@ __device__ __forceinline__ void create_split_cta(const BuildParams& P, Rng& rng 
     const int d = (int)P.d, ld = (int)P.ld, metric = P.metric;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, grp = lane >> 3;
     const bool cosine = (metric == COSINE || metric == DOT_PRODUCT);
-    if (tid == 0) {  // all RNG draws of the attempt first: they do not depend on the data
-        uint32_t a, b;
-        rng.sample2(len, a, b);
-        S.rows[0] = a; S.rows[1] = b;
-        for (int it = 0; it < 10; ++it) S.rows[2 + it] = rng.gen_range_incl(0, len - 1);
+    // All RNG draws of the attempt first: they do not depend on the data. choose_two = index::sample(len, 2)
+    // = gen_range(0..=len-2), gen_range(0..=len-1); then ten gen_range(0..=len-1). A draw is rejected with
+    // probability ~ len / 2^32, so lanes 0..11 of warp 0 each take one word of the stream (the blocks
+    // were computed ahead, rng.pref) and the serial loop only runs if some lane saw a rejection.
+    if (warp == 0) {
+        bool done = false;
+        const uint64_t pos = rng.pos;
+        if (rng.pref && (pos >> 4) == rng.pref_base && rng.pref_n >= 2) {
+            const uint32_t range = lane == 0 ? len - 1u : len;
+            const uint32_t zone = (range << __clz((int)range)) - 1u;
+            const uint64_t w = pos + (uint64_t)lane;
+            const uint32_t v = lane < 12 ? rng.pref[(w - (rng.pref_base << 4)) & 31u] : 0u;
+            const unsigned long long m = (unsigned long long)v * (unsigned long long)range;
+            const bool ok = lane >= 12 || (uint32_t)m <= zone;
+            if (__all_sync(0xffffffffu, ok)) {
+                const uint32_t r = (uint32_t)(m >> 32);
+                const uint32_t t0 = __shfl_sync(0xffffffffu, r, 0), t1 = __shfl_sync(0xffffffffu, r, 1);
+                if (lane == 0) { if (t1 == t0) { S.rows[0] = len - 1u; S.rows[1] = t0; } else { S.rows[0] = t0; S.rows[1] = t1; } rng.pos = pos + 12u; }
+                if (lane >= 2 && lane < 12) S.rows[lane] = r;
+                done = true;
+            }
+        }
+        if (!done && lane == 0) {
+            uint32_t a, b;
+            rng.sample2(len, a, b);
+            S.rows[0] = a; S.rows[1] = b;
+#pragma unroll 1
+            for (int it = 0; it < 10; ++it) S.rows[2 + it] = rng.gen_range_incl(0, len - 1);
+        }
     }
+    TP_MARK(S, TP_RNG);
     __syncthreads();
     uint32_t my_row = 0;
     if (tid < 12) my_row = seg[S.rows[tid]];  // RoaringBitmap::select(rank) on the ascending id list
@@ -141,6 +215,7 @@ __device__ __forceinline__ void create_split_cta(const BuildParams& P, Rng& rng 
         }
     }
     __syncthreads();
+    TP_MARK(S, TP_GATHER);
     if (tid == 0) { S.php[0] = S.h0[0]; S.php[1] = S.h1[0]; S.phq[0] = S.h0[1]; S.phq[1] = S.h1[1]; }
     float* p = ws; float* q = ws + ld;
     float* sc0 = ws + (size_t)12 * ld; float* sc1 = ws + (size_t)13 * ld;
@@ -162,8 +237,13 @@ __device__ __forceinline__ void create_split_cta(const BuildParams& P, Rng& rng 
         }
     }
     __syncthreads();
+    TP_MARK(S, TP_NORMS);
+    {
     float ic = 1.0f, jc = 1.0f;
     bool p_dirty = cosine, q_dirty = cosine;   // D::init pending (cosine.rs:69-71, dot_product.rs:94-96)
+    // (kept rolled: the serial path runs on one or two warps, whose speed is set by instruction fetch —
+    // ten unrolled copies of this body never hit the instruction cache)
+#pragma unroll 1
     for (int it = 0; it < 10; ++it) {
         const float* k = ws + (size_t)(2 + it) * ld;
         const float kh0 = S.h0[2 + it], kh1 = S.h1[2 + it];
@@ -182,48 +262,61 @@ __device__ __forceinline__ void create_split_cta(const BuildParams& P, Rng& rng 
                 for (; i < d; ++i) s = __fadd_rn(s, t[i]);
                 S.res[it & 1][tid] = __fmul_rn(tid ? jc : ic, s);
             }
-        } else if (warp == 0) {
-            // group 0: p.k   group 1: q.k   group 2: p.p   group 3: q.q  (Euclidean: (p-k)^2, (q-k)^2 only)
-            const float* a = (grp & 1) ? q : p;
-            const float* b = (grp < 2) ? k : a;
-            float x = (metric == EUCLIDEAN) ? exact_group8<true>((grp & 1) ? q : p, k, d) : exact_group8<false>(a, b, d);
-            const float pk = __shfl_sync(0xffffffffu, x, 0), qk = __shfl_sync(0xffffffffu, x, 8);
-            const float pp = __shfl_sync(0xffffffffu, x, 16), qq = __shfl_sync(0xffffffffu, x, 24);
+        } else if (warp < 2) {
+            // warp 0: p.k and (after a move of p) p.p; warp 1: q.k and q.q — lane l = accumulator lane l, so both
+            // sides run at the same time on two schedulers; lane 0 of each warp finishes its side.
+            const bool qs = warp == 1;
+            const float* a = qs ? q : p;
+            float xk, xx;
+            if (metric == EUCLIDEAN) exact_warp_ab_aa<true>(a, k, d, xk, xx); else exact_warp_ab_aa<false>(a, k, d, xk, xx);
+            TP_MARK(S, 14);
             if (lane == 0) {
-                float ph0 = S.php[0], ph1 = S.php[1], qh0 = S.phq[0], qh1 = S.phq[1];
-                if (p_dirty) { if (metric == COSINE) ph0 = __fsqrt_rn(pp); else ph1 = pp; S.php[0] = ph0; S.php[1] = ph1; }
-                if (q_dirty) { if (metric == COSINE) qh0 = __fsqrt_rn(qq); else qh1 = qq; S.phq[0] = qh0; S.phq[1] = qh1; }
-                float di, dj;   // D::non_built_distance — mod.rs:54-56 (= built_distance) except dot_product.rs:58-70
-                if (metric == EUCLIDEAN) { di = pk; dj = qk; }
-                else if (metric == COSINE) { di = built_finish(COSINE, pk, ph0, kh0); dj = built_finish(COSINE, qk, qh0, kh0); }
+                float* hdr = qs ? S.phq : S.php;
+                float h0v = hdr[0], h1v = hdr[1];
+                if (qs ? q_dirty : p_dirty) { if (metric == COSINE) h0v = __fsqrt_rn(xx); else h1v = xx; hdr[0] = h0v; hdr[1] = h1v; }
+                float dv;   // D::non_built_distance — mod.rs:54-56 (= built_distance) except dot_product.rs:58-70
+                if (metric == EUCLIDEAN) dv = xk;
+                else if (metric == COSINE) dv = built_finish(COSINE, xk, h0v, kh0);
                 else {
-                    float a1 = __fadd_rn(pk, __fmul_rn(ph0, kh0)), a2 = __fadd_rn(qk, __fmul_rn(qh0, kh0));
-                    float m1 = __fmul_rn(ph1, kh1), m2 = __fmul_rn(qh1, kh1);
-                    di = (m1 >= 1.17549435e-38f) ? __fsub_rn(2.0f, __fdiv_rn(__fmul_rn(2.0f, a1), __fsqrt_rn(m1))) : 2.0f;
-                    dj = (m2 >= 1.17549435e-38f) ? __fsub_rn(2.0f, __fdiv_rn(__fmul_rn(2.0f, a2), __fsqrt_rn(m2))) : 2.0f;
+                    const float a1 = __fadd_rn(xk, __fmul_rn(h0v, kh0));
+                    const float m1 = __fmul_rn(h1v, kh1);
+                    dv = (m1 >= 1.17549435e-38f) ? __fsub_rn(2.0f, __fdiv_rn(__fmul_rn(2.0f, a1), __fsqrt_rn(m1))) : 2.0f;
                 }
-                S.res[it & 1][0] = __fmul_rn(ic, di);
-                S.res[it & 1][1] = __fmul_rn(jc, dj);
+                S.res[it & 1][qs ? 1 : 0] = __fmul_rn(qs ? jc : ic, dv);
             }
+            TP_MARK(S, 15);
+        } else if (cosine) {
+            // meanwhile the other warps form k / norm for update_mean (mod.rs:86-94): it does not depend on
+            // the centroids, so the division leaves the critical path
+            const float nrm = S.nk[2 + it];
+            for (int i = tid - 64; i < d; i += CTRL_THREADS - 64) sc1[i] = __fdiv_rn(k[i], nrm);
         }
         p_dirty = false; q_dirty = false;
         __syncthreads();
+        TP_MARK(S, TP_TM_DOT);
         const float di = S.res[it & 1][0], dj = S.res[it & 1][1];
         const float norm = cosine ? S.nk[2 + it] : 1.0f;
         if (norm != norm || norm <= 0.0f) continue;
-        if (di < dj) {        // update_mean(p, k, norm, ic) — mod.rs:86-94; D::init follows in the next dot phase
-            const float c1 = __fadd_rn(ic, 1.0f);
-            for (int i = tid; i < d; i += blockDim.x) p[i] = __fdiv_rn(__fadd_rn(__fmul_rn(p[i], ic), __fdiv_rn(k[i], norm)), c1);
-            ic = c1; p_dirty = cosine;
+        const float* kn = cosine ? sc1 : k;          // k / norm (norm == 1 for Euclidean / Manhattan: k itself)
+        if (di < dj || dj < di) {                    // update_mean(c, k, norm, count) — mod.rs:86-94; D::init follows in the next dot phase
+            const bool up = di < dj;
+            float* cen = up ? p : q;
+            const float cnt = up ? ic : jc, c1 = __fadd_rn(cnt, 1.0f);
+            for (int i0 = tid; i0 < d; i0 += 4 * CTRL_THREADS) {   // four independent chains per thread
+                float v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { const int i = i0 + u * CTRL_THREADS; if (i < d) v[u] = __fdiv_rn(__fadd_rn(__fmul_rn(cen[i], cnt), cosine ? kn[i] : __fdiv_rn(kn[i], norm)), c1); }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { const int i = i0 + u * CTRL_THREADS; if (i < d) cen[i] = v[u]; }
+            }
+            if (up) { ic = c1; p_dirty = cosine; } else { jc = c1; q_dirty = cosine; }
             __syncthreads();
-        } else if (dj < di) {
-            const float c1 = __fadd_rn(jc, 1.0f);
-            for (int i = tid; i < d; i += blockDim.x) q[i] = __fdiv_rn(__fadd_rn(__fmul_rn(q[i], jc), __fdiv_rn(k[i], norm)), c1);
-            jc = c1; q_dirty = cosine;
-            __syncthreads();
+            TP_MARK(S, TP_TM_UPD);
         }
     }
+    }
     __syncthreads();
+    TP_MARK(S, TP_TWOMEANS);
     // normal = normalize(p - q) (+ bias / extra_dim) — euclidean.rs:59-75, manhattan.rs:62-78,
     // cosine.rs:77-83, dot_product.rs:102-111. (A D::init still pending after the last update only
     // touches the centroid's norm header, which create_split does not read.)
@@ -257,6 +350,7 @@ __device__ __forceinline__ void create_split_cta(const BuildParams& P, Rng& rng 
         slot_ptr[1] = 0.f; slot_ptr[2] = 0.f; slot_ptr[3] = 0.f;
     }
     __syncthreads();
+    TP_MARK(S, TP_FINISH_SPLIT);
 }
 
 // CTA-wide stable partition of a whole node (any size) by its flags. Each round handles
@@ -311,6 +405,19 @@ __device__ void partition_inline(const uint32_t* __restrict__ src, const uint8_t
 __device__ uint32_t cta_exclusive_scan(uint32_t* v, uint32_t n, uint32_t* sm_tmp /* blockDim */) {
     const int tid = threadIdx.x, nt = blockDim.x;
     const uint32_t per = (n + nt - 1) / nt;
+    if (per <= 1) {   // one element per thread (small nodes): a single read of v, the value stays in a register
+        const uint32_t x = (uint32_t)tid < n ? v[tid] : 0u;
+        const int lane = tid & 31, w = tid >> 5;
+        uint32_t inc = x;
+        for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += y; }
+        if (lane == 31) sm_tmp[w] = inc;
+        __syncthreads();
+        uint32_t base = 0, total = 0;
+        for (int i = 0; i < nt / 32; ++i) { const uint32_t y = sm_tmp[i]; if (i < w) base += y; total += y; }
+        if ((uint32_t)tid < n) v[tid] = base + inc - x;
+        __syncthreads();
+        return total;
+    }
     const uint32_t b = (uint32_t)tid * per, e = (b + per < n) ? b + per : n;
     uint32_t s = 0;
     for (uint32_t i = b; i < e; ++i) s += v[i];
@@ -336,24 +443,62 @@ __device__ uint32_t cta_exclusive_scan(uint32_t* v, uint32_t n, uint32_t* sm_tmp
 
 enum : int { ACT_NONE = 0, ACT_SPLIT = 1, ACT_PART_INLINE = 2, ACT_RANDOM = 3, ACT_EXIT = 4 };
 
-template <bool SMEM_WS>
+// One tree per launch unit. CS = 1: one CTA; the scan of every attempt is a separate work_kernel
+// launch. CS > 1 (thread-block cluster of CS CTAs, latency-bound regime: few trees per GPU): CTA 0
+// of the cluster runs the state machine; a node of at most P.small_max rows is scanned right here
+// by all CS CTAs between two cluster barriers (the job table, flags and unit counts live in global
+// memory; barrier.cluster has release / acquire semantics), and the state machine goes on to the
+// next attempt without leaving the kernel — no launch gap, no work_kernel start-up for the deep part
+// of the tree, where the chain of attempts is the critical path. Bigger nodes leave through the
+// posted job exactly as with CS = 1.
+template <int CS>
+__device__ __forceinline__ void cluster_scan_share(const BuildParams& P, const Job& jb, float* sm_normal, uint32_t* sm_count, unsigned rank) {
+    for (uint32_t i = threadIdx.x; i < P.ld; i += blockDim.x) sm_normal[i] = jb.normal[NORMAL_HDR + i];
+    const float nh0 = jb.normal[0];
+    __syncthreads();
+    const uint32_t units = (jb.len + SCAN_UNIT - 1) / SCAN_UNIT;
+    for (uint32_t u = rank; u < units; u += CS) scan_unit(jb, u, P.items, P.ih0, P.d, P.ld, P.metric, sm_normal, nh0, sm_count);
+}
+
+template <bool SMEM_WS, int CS>
 __global__ void __launch_bounds__(CTRL_THREADS, 1) control_kernel(BuildParams P, uint32_t tree_base) {
+    static_assert(CS == 1 || SMEM_WS, "the cluster path keeps the normal in the shared-memory workspace");
     extern __shared__ __align__(16) unsigned char ctrl_smem[];
+    __shared__ uint32_t s_scan_count;
     __shared__ TwoMeansShared TM;
     __shared__ uint32_t sm_tmp[CTRL_THREADS + 1];
     __shared__ uint32_t sm_w[2 * PART_BATCH * 8 + 2];
     __shared__ int s_action;
     __shared__ uint32_t s_total_left;
     __shared__ Rng s_rng;  // thread 0 only
+    __shared__ uint32_t s_pref[2][16];
 
     constexpr int SMF = 96;  // DFS frames cached in shared memory (deeper ones stay in global)
     __shared__ Frame sm_frames[SMF];
     __shared__ TreeState S;
 
-    const uint32_t t = blockIdx.x + tree_base;
+    const uint32_t t = blockIdx.x / CS + tree_base;
     Job& job = P.jobs[t];
-    if (P.st[t].phase == PH_DONE) return;  // job.kind already JOB_NONE
-    if (*P.error != ERR_NONE) return;
+    unsigned crank = 0;
+    if (CS > 1) crank = cooperative_groups::this_cluster().block_rank();
+    if (CS > 1 && crank != 0) {
+        // helper CTA: [A] wait for the leader's decision; scan a share; [B]; repeat until released
+        float* sm_normal = reinterpret_cast<float*>(ctrl_smem);
+        for (;;) {
+            cooperative_groups::this_cluster().sync();
+            const volatile Job* vj = &job;
+            if (vj->pad != 1u) return;
+            Job jb;
+            jb.kind = JOB_SCAN; jb.len = vj->len; jb.rows = vj->rows; jb.normal = vj->normal; jb.flags = vj->flags; jb.margins = nullptr;
+            jb.unit_left = vj->unit_left; jb.dst = nullptr; jb.total_left = 0; jb.pad = 1;
+            cluster_scan_share<CS>(P, jb, sm_normal, &s_scan_count, crank);
+            cooperative_groups::this_cluster().sync();
+        }
+    }
+    // job.kind is already JOB_NONE and job.pad 0 for a finished tree / after an error
+    if (P.st[t].phase == PH_DONE || *P.error != ERR_NONE) { if (CS > 1) cooperative_groups::this_cluster().sync(); return; }
+    uint32_t inner = 0;
+    if (P.timing != nullptr && threadIdx.x == 0) { for (int i = 0; i < 16; ++i) TM.tacc[i] = 0; TM.tlast = clock64(); TM.tacc[TP_TOTAL] = -TM.tlast; }
     Frame* gframes = P.frames + (size_t)t * MAX_DEPTH;
     if (threadIdx.x == 0) S = P.st[t];
     __syncthreads();
@@ -374,8 +519,17 @@ __global__ void __launch_bounds__(CTRL_THREADS, 1) control_kernel(BuildParams P,
         total_left = cta_exclusive_scan(unit_left, (f.len + SCAN_UNIT - 1) / SCAN_UNIT, sm_tmp);
     }
     __syncthreads();
+    TP_MARK(TM, TP_PREFIX);
 
     for (;;) {
+        // warp 1 computes the next two ChaCha blocks of this tree's stream (four lanes per block) while
+        // thread 0 walks the DFS
+        if ((tid >> 5) == 1) {
+            const int l = tid & 31, g = l >> 2;
+            uint32_t o[4];
+            chacha12_block_quad(S.key, (s_rng.pos >> 4) + (uint64_t)(g & 1), o);
+            if (g < 2) { s_pref[g][l & 3] = o[0]; s_pref[g][4 + (l & 3)] = o[1]; s_pref[g][8 + (l & 3)] = o[2]; s_pref[g][12 + (l & 3)] = o[3]; }
+        }
         // ---- thread 0: advance the DFS until CTA-wide work is needed --------------------------
         if (tid == 0) {
             int action = ACT_NONE;
@@ -442,14 +596,16 @@ __global__ void __launch_bounds__(CTRL_THREADS, 1) control_kernel(BuildParams P,
                 }
             }
             if (action == ACT_SPLIT && S.cur_slot == NO_SLOT) {
-                uint32_t s = atomicAdd(P.pool_counter, 1u);
-                if (s >= P.pool_cap) { atomicExch(P.error, ERR_POOL); action = ACT_EXIT; }
-                else S.cur_slot = s;
+                if (S.slot_next == S.slot_end) { S.slot_next = atomicAdd(P.pool_counter, 8u); S.slot_end = S.slot_next + 8u; }
+                if (S.slot_next >= P.pool_cap) { atomicExch(P.error, ERR_POOL); action = ACT_EXIT; }
+                else S.cur_slot = S.slot_next++;
             }
             s_action = action;
             s_total_left = total_left;
+            s_rng.pref = &s_pref[0][0]; s_rng.pref_base = s_rng.pos >> 4; s_rng.pref_n = 2;
         }
         __syncthreads();
+        TP_MARK(TM, TP_DECIDE);
         const int action = s_action;
         if (action == ACT_EXIT) break;
         const Frame f = FR(S.sp);
@@ -460,10 +616,25 @@ __global__ void __launch_bounds__(CTRL_THREADS, 1) control_kernel(BuildParams P,
             if (SMEM_WS) create_split_cta(P, s_rng, src, f.len, reinterpret_cast<float*>(ctrl_smem), TM, slot_ptr);
             else create_split_cta(P, s_rng, src, f.len, P.scratch + (size_t)t * WS_VECS * P.ld, TM, slot_ptr);
             if (tid == 0) {
-                S.n_splits_tried += 1;
+                S.n_splits_tried += 1; if (P.timing) TM.tacc[TP_ATTEMPTS] += 1;
                 job.kind = JOB_SCAN; job.len = f.len; job.rows = src; job.normal = slot_ptr;
                 job.flags = flags + f.start; job.margins = nullptr; job.unit_left = unit_left; job.dst = nullptr; job.total_left = 0;
                 S.phase = PH_AWAIT_SCAN;
+                if (CS > 1 && f.len <= P.small_max && inner < P.max_inner) job.pad = 1;
+            }
+            if (CS > 1 && f.len <= P.small_max && inner < P.max_inner) {
+                // cluster-resident attempt: scan here, then straight on to the decision
+                cooperative_groups::this_cluster().sync();                       // [A] job visible to the helpers
+                Job jb = job;
+                cluster_scan_share<CS>(P, jb, reinterpret_cast<float*>(ctrl_smem) + (size_t)12 * P.ld, &s_scan_count, 0);
+                cooperative_groups::this_cluster().sync();                       // [B] flags / unit counts visible to this CTA
+                TP_MARK(TM, TP_CLUSTER_SCAN);
+                if (tid == 0) { job.kind = JOB_NONE; job.pad = 0; if (P.timing) TM.tacc[TP_INNER] += 1; }
+                total_left = cta_exclusive_scan(unit_left, (f.len + SCAN_UNIT - 1) / SCAN_UNIT, sm_tmp);
+                ++inner;
+                __syncthreads();
+                TP_MARK(TM, TP_PREFIX);
+                continue;
             }
             break;
         }
@@ -502,12 +673,18 @@ __global__ void __launch_bounds__(CTRL_THREADS, 1) control_kernel(BuildParams P,
             if (tid == 0) { FR(S.sp).stage = 1; S.phase = PH_AWAIT_PART; }
             total_left = 0;
             __syncthreads();
+            TP_MARK(TM, TP_PARTITION);
             continue;
         }
     }
     __syncthreads();
+    if (CS > 1) cooperative_groups::this_cluster().sync();   // releases the helpers (job.pad == 0)
     for (int i = tid; i <= S.sp && i < SMF; i += blockDim.x) gframes[i] = sm_frames[i];
     if (tid == 0) { S.pos = s_rng.pos; P.st[t] = S; }
+    if (tid == 0 && P.timing) {
+        TM.tacc[TP_TOTAL] += clock64();
+        for (int i = 0; i < 16; ++i) atomicAdd(P.timing + i, (unsigned long long)TM.tacc[i]);
+    }
 }
 
 // Merge the two ping-pong id buffers into `final_ids` following each leaf's parity.
@@ -530,9 +707,10 @@ __global__ void init_trees_kernel(BuildParams P, const uint32_t* __restrict__ ke
         TreeState s;
         for (int i = 0; i < 8; ++i) s.key[i] = keys[t * 8 + i];
         s.pos = 0; s.phase = PH_START; s.sp = -1; s.attempts_left = 0; s.cur_slot = NO_SLOT; s.n_recs = 0;
-        s.n_splits_tried = 0; s.n_random = 0; s.pad = 0; s.scanned = 0;
+        s.n_splits_tried = 0; s.n_random = 0; s.pad = 0; s.scanned = 0; s.slot_next = 0; s.slot_end = 0;
         P.st[t] = s;
         P.jobs[t].kind = JOB_NONE;
+        P.jobs[t].pad = 0;
     }
     uint32_t* perm0 = P.perm[0] + (size_t)t * P.n;
     if (P.sub_off) {
