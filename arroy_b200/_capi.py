@@ -59,6 +59,7 @@ SIGNATURES = [
     ("arroy_b200_counters", C.c_int32, [C.c_void_p, _u64p]),
     ("arroy_b200_rerank_stats", C.c_int32, [C.c_void_p, _u64p]),
     ("arroy_b200_rerank_breakdown", C.c_int32, [C.c_void_p, C.POINTER(C.c_double)]),
+    ("arroy_b200_search_breakdown", C.c_int32, [C.c_void_p, C.POINTER(C.c_double)]),
     ("arroy_b200_prefilter_scores", C.c_int32, [C.c_void_p, C.c_uint32, _f32p, _u32p, C.c_uint64, C.c_int32, _f32p]),
     ("arroy_b200_timer_start", C.c_int32, [C.c_void_p]),
     ("arroy_b200_timer_stop", C.c_int32, [C.c_void_p, _f32p]),
@@ -329,7 +330,7 @@ class Context:
     def counters(self):
         out = (C.c_uint64 * 4)()
         self._ck(self.lib.arroy_b200_counters(self.h, out))
-        return {"launches": out[0], "h2d_bytes": out[1], "d2h_bytes": out[2]}
+        return {"launches": out[0], "h2d_bytes": out[1], "d2h_bytes": out[2], "fused_rerank_batches": out[3] >> 32, "fused_rerank_fallbacks": out[3] & 0xffffffff}
 
     def prefilter_scores(self, queries, rows, engine=0):
         queries = np.ascontiguousarray(queries, dtype=np.float32)
@@ -337,6 +338,11 @@ class Context:
         out = np.empty((queries.shape[0], rows.size), dtype=np.float32)
         self._ck(self.lib.arroy_b200_prefilter_scores(self.h, queries.shape[0], _fp(queries), _up(rows), rows.size, engine, _fp(out)))
         return out
+
+    def search_breakdown(self):
+        out = (C.c_double * 8)()
+        self._ck(self.lib.arroy_b200_search_breakdown(self.h, out))
+        return dict(zip(["walk_ms", "sort_ms", "distance_ms", "topk_ms"], list(out)[:4]))
 
     def rerank_breakdown(self):
         out = (C.c_double * 8)()

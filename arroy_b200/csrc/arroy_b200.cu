@@ -22,6 +22,7 @@
 
 #include "xrerank.cuh"
 #include "tcgemm.cuh"
+#include "frerank.cuh"
 
 using namespace ab;
 
@@ -139,7 +140,12 @@ struct arroy_ctx {
     DevBuf x_gather, x_cnorm, x_ca, x_cb, x_gmax, x_qa, x_qb, x_twoe, x_qnorm, x_S, x_sel, x_beg, x_end, x_flag;
     uint64_t xf_calls = 0, xf_fallbacks = 0, xf_selected = 0, xf_queries = 0;
     cudaEvent_t xev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    double xbreak[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // last rerank_shared call, ms: prep, score GEMM, select, re-score, top-k, exact dense path
+    double xbreak[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    double sbreak[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    // fused re-rank with a bf16 shadow of the items (frerank.cuh); built lazily by the first query after staging
+    DevBuf fr_shadow, fr_norm, fr_gmax, fr_status;
+    bool fr_valid = false;
+    uint64_t fr_batches = 0, fr_fallbacks = 0;   // last search_batch call, ms: bitmap clear + tree walk, candidate sort, distances, top-k   // last rerank_shared call, ms: prep, score GEMM, select, re-score, top-k, exact dense path
 };
 
 namespace {
@@ -181,7 +187,7 @@ void alloc_items(arroy_ctx* c, int metric, uint32_t dim, uint64_t n, const uint3
     if (dim == 0) throw ArgError("dim must be > 0");
     if (n > 0xffffffffull) throw ArgError("too many items");
     for (uint64_t i = 1; i < n; ++i) if (ids[i] <= ids[i - 1]) throw ArgError("ids must be strictly ascending");
-    c->staged = false;
+    c->staged = false; c->fr_valid = false;
     c->metric = metric; c->dim = dim; c->ld = (dim + 31u) & ~31u; c->n = n;
     c->ids.assign(ids, ids + n);
     c->items.ensure(std::max<size_t>(16, (size_t)n * c->ld * 4));
@@ -791,6 +797,59 @@ void xf_scores(arroy_ctx* c, const float* q, uint32_t m, const float* cand, uint
 
 int xf_engine() { const char* e = getenv("ARROY_B200_XGEMM"); return (e && strcmp(e, "cublas") == 0) ? 1 : 0; }
 
+// ---- fused re-rank (frerank.cuh) -------------------------------------------------------------------
+bool frerank_enabled(arroy_ctx* c, uint32_t k) {
+    const char* e = getenv("ARROY_B200_FRERANK");
+    const bool off = e != nullptr && atoi(e) == 0;
+    return !off && c->metric != MANHATTAN && k <= (uint32_t)FR_SURV && frerank_smem(c->ld) <= 200 * 1024;
+}
+
+void frerank_prepare(arroy_ctx* c) {
+    if (c->fr_valid) return;
+    const uint64_t total4 = (uint64_t)c->n * c->ld / 4;
+    c->fr_shadow.ensure(std::max<size_t>(16, (size_t)c->n * c->ld * 2));
+    c->fr_norm.ensure(std::max<size_t>(16, c->n * 4));
+    c->fr_gmax.ensure(4);
+    fr_shadow_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->items.as<float4>(), c->fr_shadow.as<uint2>(), total4);
+    CK(cudaGetLastError());
+    { uint64_t warps = (c->n + 3) / 4; int g = (int)std::max<uint64_t>(1, std::min<uint64_t>((warps + 7) / 8, (uint64_t)c->sm_count * 16));
+      norms_kernel<<<g, 256, 0, c->stream>>>(c->items.as<float>(), c->n, c->dim, c->ld, c->fr_norm.as<float>(), nullptr); CK(cudaGetLastError()); }
+    CK(cudaMemsetAsync(c->fr_gmax.p, 0, 4, c->stream));
+    fr_gmax_kernel<<<(unsigned)((c->n + 255) / 256), 256, 0, c->stream>>>(c->fr_norm.as<float>(), c->h0.as<float>(), c->n, c->metric, c->fr_gmax.as<uint32_t>());
+    CK(cudaGetLastError());
+    c->n_launches += 3;
+    c->fr_valid = true;
+}
+
+// launches the fused kernel for m queries whose sorted candidate rows are rows[beg[q] .. end[q]); results in s_orows / s_odist /
+// s_olen, per-query status in fr_status (0 = done, 1 = needs the plain kernels)
+void frerank_launch(arroy_ctx* c, uint32_t m, const float* d_q, const uint32_t* d_qrows, const float* d_qh0, const uint32_t* d_rows,
+                    const uint64_t* d_beg, const uint64_t* d_end, uint32_t k) {
+    frerank_prepare(c);
+    c->fr_status.ensure(4ull * m);
+    FrParams P{};
+    P.items = c->items.as<float>(); P.shadow = c->fr_shadow.as<__nv_bfloat16>(); P.ih0 = c->h0.as<float>(); P.cnorm = c->fr_norm.as<float>();
+    P.d = c->dim; P.ld = c->ld; P.metric = c->metric;
+    P.queries = d_q; P.qrows = d_qrows; P.qh0 = d_qh0;
+    P.rows = d_rows; P.seg_beg = d_beg; P.seg_end = d_end;
+    P.k = k; P.rel = fr_rel(c->dim); P.gmax_bits = c->fr_gmax.as<uint32_t>();
+    P.out_rows = c->s_orows.as<uint32_t>(); P.out_dist = c->s_odist.as<float>(); P.out_len = c->s_olen.as<uint32_t>(); P.status = c->fr_status.as<int32_t>();
+    const size_t smem = frerank_smem(c->ld);
+    static std::atomic<size_t> configured{0};
+    if (smem > 48 * 1024 && smem > configured.load()) { CK(cudaFuncSetAttribute(frerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured = smem; }
+    frerank_kernel<<<m, FR_THREADS, smem, c->stream>>>(P);
+    CK(cudaGetLastError());
+    c->n_launches += 1;
+    c->fr_batches += 1;
+}
+
+bool frerank_ok(arroy_ctx* c, uint32_t m) {   // after the stream is idle: did every query finish in the fused kernel?
+    std::vector<int32_t> st(m);
+    CK(cudaMemcpy(st.data(), c->fr_status.p, 4ull * m, cudaMemcpyDeviceToHost));
+    for (int32_t x : st) if (x != 0) { c->fr_fallbacks += 1; return false; }
+    return true;
+}
+
 void do_rerank_batch(arroy_ctx* c, uint32_t nq, const float* queries, const float* qh0, const float* /*qh1*/, const uint32_t* rows,
                      const uint64_t* offsets, uint32_t k, uint32_t* out_rows, float* out_dist, uint32_t* out_len) {
     require_staged(c);
@@ -823,6 +882,14 @@ void do_rerank_batch(arroy_ctx* c, uint32_t nq, const float* queries, const floa
     if (total) CK(cudaMemcpyAsync(c->s_rows.p, rows, total * 4, cudaMemcpyHostToDevice, c->stream));
     uint64_t max_c = 0;
     for (uint32_t q = 0; q < nq; ++q) max_c = std::max<uint64_t>(max_c, offsets[q + 1] - offsets[q]);
+    bool fused = false;
+    if (total >= 512ull * nq && max_c <= (uint64_t)FR_CAP && frerank_enabled(c, k)) {
+        // rows of each query must be ascending for the (distance, id) tie-break; the callers of this path pass sorted lists
+        frerank_launch(c, nq, c->s_q.as<float>(), nullptr, c->s_qh0.as<float>(), c->s_rows.as<uint32_t>(), c->s_off.as<uint64_t>(), c->s_off.as<uint64_t>() + 1, k);
+        CK(cudaStreamSynchronize(c->stream));
+        fused = frerank_ok(c, nq);
+    }
+    if (!fused) {
     if (total) {
         uint64_t per = c->metric == MANHATTAN ? 32 : 4;
         uint64_t warps = (max_c + per - 1) / per;
@@ -835,6 +902,7 @@ void do_rerank_batch(arroy_ctx* c, uint32_t nq, const float* queries, const floa
     topk_kernel<<<nq, TOPK_THREADS, 0, c->stream>>>(c->s_keys.as<unsigned long long>(), c->s_dists.as<float>(), c->s_rows.as<uint32_t>(), c->s_off.as<uint64_t>(), c->s_off.as<uint64_t>() + 1, k, c->metric,
                                                     c->s_orows.as<uint32_t>(), c->s_odist.as<float>(), c->s_olen.as<uint32_t>());
     CK(cudaGetLastError());
+    }
     c->n_launches += total ? 2 : 1;
     c->h2d_bytes += (uint64_t)nq * c->dim * 4 + (uint64_t)nq * 4 + (uint64_t)(nq + 1) * 8 + total * 4;
     c->d2h_bytes += (uint64_t)nq * k * 8 + (uint64_t)nq * 4;
@@ -919,7 +987,7 @@ void arroy_b200_destroy(arroy_ctx* c) {
     DevBuf* bufs[] = {&c->items, &c->h0, &c->h1, &c->norms, &c->maxbits, &c->s_rows, &c->s_flags, &c->s_margins, &c->s_normal, &c->s_unit, &c->s_job,
                       &c->s_keys, &c->s_dists, &c->s_q, &c->s_qh0, &c->s_off, &c->s_orows, &c->s_odist, &c->s_olen, &c->s_misc};
     for (auto* b : bufs) b->release();
-    { DevBuf* xb[] = {&c->x_gather, &c->x_cnorm, &c->x_ca, &c->x_cb, &c->x_gmax, &c->x_qa, &c->x_qb, &c->x_twoe, &c->x_qnorm, &c->x_S, &c->x_sel, &c->x_beg, &c->x_end, &c->x_flag}; for (auto* b : xb) b->release(); }
+    { DevBuf* xb[] = {&c->fr_shadow, &c->fr_norm, &c->fr_gmax, &c->fr_status, &c->x_gather, &c->x_cnorm, &c->x_ca, &c->x_cb, &c->x_gmax, &c->x_qa, &c->x_qb, &c->x_twoe, &c->x_qnorm, &c->x_S, &c->x_sel, &c->x_beg, &c->x_end, &c->x_flag}; for (auto* b : xb) b->release(); }
     if (c->blas) cublasDestroy(c->blas);
     for (auto& e : c->xev) if (e) cudaEventDestroy(e);
     if (c->cached_exec) cudaGraphExecDestroy(c->cached_exec);
@@ -1371,6 +1439,9 @@ int32_t arroy_b200_search_batch(arroy_ctx* c, uint32_t nq, const uint32_t* query
         if (cand_cap64 > 0x7fffffffull || heap_cap64 > 0x7fffffffull) throw ArgError("search_k too large for the device walk");
         const uint32_t cand_cap = (uint32_t)std::max<uint64_t>(cand_cap64, 1), heap_cap = (uint32_t)heap_cap64;
         const uint32_t bm_words = (uint32_t)((c->n + 31) / 32);
+        for (double& x : c->sbreak) x = 0;
+        int nte = 0;
+        auto mark = [&]() { if (!c->xev[nte]) CK(cudaEventCreate(&c->xev[nte])); CK(cudaEventRecord(c->xev[nte], c->stream)); ++nte; };
         // process the queries in chunks that keep the scratch memory bounded (~1 GiB)
         const uint64_t per_q = 8ull * heap_cap + 8ull * cand_cap + 4ull * bm_words + 12ull * cand_cap + 64;
         uint32_t chunk = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>({(uint64_t)nq, (1ull << 30) / per_q, 65535ull}));
@@ -1398,11 +1469,13 @@ int32_t arroy_b200_search_batch(arroy_ctx* c, uint32_t nq, const uint32_t* query
                 gather_f32_kernel<<<(m + 255) / 256, 256, 0, c->stream>>>(c->s_qh0.as<float>(), c->h0.as<float>(), d_qrows, m);
                 CK(cudaGetLastError());
             } else CK(cudaMemsetAsync(c->s_qh0.p, 0, 4ull * m, c->stream));
+            nte = 0; mark();
             CK(cudaMemsetAsync(c->w_bitmap.p, 0, 4ull * bm_words * m, c->stream));
             walk_kernel<<<(m + WALK_WARPS - 1) / WALK_WARPS, WALK_WARPS * 32, 0, c->stream>>>(F, c->items.as<float>(), c->dim, ld, c->metric, m, d_qrows, d_q, c->s_qh0.as<float>(),
                                                                                        search_k, c->w_heaps.as<unsigned long long>(), heap_cap, c->w_cand.as<uint32_t>(), cand_cap,
                                                                                        c->w_count.as<uint32_t>(), c->w_bitmap.as<uint32_t>(), bm_words, c->w_status.as<int32_t>());
             CK(cudaGetLastError());
+            mark();
             walk_segments_kernel<<<(m + 256) / 256, 256, 0, c->stream>>>(c->w_count.as<uint32_t>(), m, cand_cap, c->w_beg.as<uint64_t>(), c->w_end.as<uint64_t>());
             CK(cudaGetLastError());
             // sort every query's unique candidates ascending (= ascending item ids): reader.rs:378
@@ -1412,20 +1485,32 @@ int32_t arroy_b200_search_batch(arroy_ctx* c, uint32_t nq, const uint32_t* query
             c->w_tmp.ensure(std::max<size_t>(tmp_bytes, 16));
             CK(cub::DeviceSegmentedSort::SortKeys(c->w_tmp.p, tmp_bytes, c->w_cand.as<uint32_t>(), c->w_cand2.as<uint32_t>(), (int64_t)cand_cap * m, (int64_t)m,
                                                   c->w_beg.as<uint64_t>(), c->w_end.as<uint64_t>(), c->stream));
+            mark();
+            bool fused = frerank_enabled(c, k);
+            if (fused) {   // one fused kernel per query: bf16 pre-filter + exact re-score + top-k (frerank.cuh)
+                frerank_launch(c, m, d_q, d_qrows, c->s_qh0.as<float>(), c->w_cand2.as<uint32_t>(), c->w_beg.as<uint64_t>(), c->w_end.as<uint64_t>(), k);
+                CK(cudaStreamSynchronize(c->stream));
+                fused = frerank_ok(c, m);
+            }
+            if (!fused) {
             uint64_t warps = ((uint64_t)cand_cap + 3) / 4;
             uint32_t gx = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((warps + 7) / 8, std::max<uint64_t>(1, ((uint64_t)c->sm_count * 8) / std::min<uint32_t>(m, c->sm_count * 8u))));
             distance_kernel<<<dim3(gx, m), 256, 0, c->stream>>>(c->items.as<float>(), c->h0.as<float>(), c->dim, ld, c->metric, d_q, d_qrows, c->s_qh0.as<float>(), m,
                                                                c->w_cand2.as<uint32_t>(), c->w_beg.as<uint64_t>(), c->w_end.as<uint64_t>(), c->s_dists.as<float>(), c->s_keys.as<unsigned long long>());
             CK(cudaGetLastError());
+            mark();
             topk_kernel<<<m, TOPK_THREADS, 0, c->stream>>>(c->s_keys.as<unsigned long long>(), c->s_dists.as<float>(), c->w_cand2.as<uint32_t>(), c->w_beg.as<uint64_t>(), c->w_end.as<uint64_t>(), k, c->metric,
                                                            c->s_orows.as<uint32_t>(), c->s_odist.as<float>(), c->s_olen.as<uint32_t>());
             CK(cudaGetLastError());
+            } else mark();
             c->n_launches += 5;
+            mark();
             CK(cudaMemcpyAsync(out_rows + (size_t)q0 * k, c->s_orows.p, 4ull * m * k, cudaMemcpyDeviceToHost, c->stream));
             CK(cudaMemcpyAsync(out_dist + (size_t)q0 * k, c->s_odist.p, 4ull * m * k, cudaMemcpyDeviceToHost, c->stream));
             CK(cudaMemcpyAsync(out_len + q0, c->s_olen.p, 4ull * m, cudaMemcpyDeviceToHost, c->stream));
             if (out_status) CK(cudaMemcpyAsync(out_status + q0, c->w_status.p, 4ull * m, cudaMemcpyDeviceToHost, c->stream));
             CK(cudaStreamSynchronize(c->stream));
+            for (int i = 0; i + 1 < nte; ++i) { float ms = 0; CK(cudaEventElapsedTime(&ms, c->xev[i], c->xev[i + 1])); c->sbreak[i] += ms; }
             c->d2h_bytes += 8ull * m * k + 8ull * m;
         }
     });
@@ -1531,7 +1616,7 @@ int32_t arroy_b200_build_breakdown(arroy_ctx* c, double out[8]) {
 }
 
 int32_t arroy_b200_counters(arroy_ctx* c, uint64_t out[4]) {
-    return guarded(c, [&] { out[0] = c->n_launches; out[1] = c->h2d_bytes; out[2] = c->d2h_bytes; out[3] = 0; });
+    return guarded(c, [&] { out[0] = c->n_launches; out[1] = c->h2d_bytes; out[2] = c->d2h_bytes; out[3] = (c->fr_batches << 32) | (c->fr_fallbacks & 0xffffffffull); });
 }
 
 int32_t arroy_b200_prefilter_scores(arroy_ctx* c, uint32_t nq, const float* queries, const uint32_t* rows, uint64_t n_rows, int32_t engine, float* out_scores) {
@@ -1553,6 +1638,10 @@ int32_t arroy_b200_prefilter_scores(arroy_ctx* c, uint32_t nq, const float* quer
         CK(cudaMemcpy2DAsync(out_scores, 4ull * nc, c->x_S.p, 4ull * lds, 4ull * nc, nq, cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
     });
+}
+
+int32_t arroy_b200_search_breakdown(arroy_ctx* c, double out[8]) {
+    return guarded(c, [&] { for (int i = 0; i < 8; ++i) out[i] = c->sbreak[i]; });
 }
 
 int32_t arroy_b200_rerank_breakdown(arroy_ctx* c, double out[8]) {

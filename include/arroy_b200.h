@@ -261,7 +261,8 @@ int32_t arroy_b200_arena_get(arroy_b200_arena* arena, uint32_t node_id, const ui
 int32_t arroy_b200_build_breakdown(arroy_ctx* ctx, double out[8]);
 
 /* Counters since arroy_b200_create: out[0] = kernel launches issued by this library,
- * out[1] = bytes copied host->device, out[2] = bytes copied device->host, out[3] reserved. */
+ * out[1] = bytes copied host->device, out[2] = bytes copied device->host, out[3] = (query batches re-ranked by
+ * the fused bf16-pre-filter kernel << 32) | batches that fell back to the plain distance + top-k kernels. */
 int32_t arroy_b200_counters(arroy_ctx* ctx, uint64_t out[4]);
 
 /* The score matrix of the pre-filter, for tests and profiling: out_scores[q * n_rows + i] ~ dot(query q,
@@ -276,6 +277,10 @@ int32_t arroy_b200_prefilter_scores(arroy_ctx* ctx, uint32_t nq, const float* qu
  * (more survivors than the per-query cap), out[2] = survivors re-scored exactly (sum over
  * queries), out[3] = queries pre-filtered. */
 int32_t arroy_b200_rerank_stats(arroy_ctx* ctx, uint64_t out[4]);
+
+/* CUDA-event breakdown of the last arroy_b200_search_batch call (ms, summed over its query chunks):
+ * [0] bitmap clear + tree walk, [1] candidate sort, [2] distances, [3] top-k, [4..7] reserved. */
+int32_t arroy_b200_search_breakdown(arroy_ctx* ctx, double out[8]);
 
 /* CUDA-event breakdown of the last arroy_b200_rerank_shared call (ms, summed over its query chunks):
  * [0] norms + bound constants, [1] score contraction on the tensor cores (tcgemm_tf32_kernel),

@@ -18,7 +18,12 @@ os.environ["ARROY_B200_TRACE"] = "1"
 for rep in range(3):
     t0 = time.perf_counter()
     out = r.nns_batch_by_item(q, 100)
-    print("batch 1000: %.1f ms" % ((time.perf_counter() - t0) * 1e3), out[3], flush=True)
+    print("batch 1000: %.1f ms" % ((time.perf_counter() - t0) * 1e3), out[3], ctx.search_breakdown(), flush=True)
+q10 = np.arange(10000, dtype=np.uint32) % n
+for rep in range(2):
+    t0 = time.perf_counter()
+    out = r.nns_batch_by_item(q10, 100)
+    print("batch 10000: %.1f ms" % ((time.perf_counter() - t0) * 1e3), ctx.search_breakdown(), flush=True)
 os.environ["ARROY_B200_HOST_WALK"] = "1"
 for rep in range(2):
     t0 = time.perf_counter()
