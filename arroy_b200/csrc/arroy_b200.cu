@@ -1439,6 +1439,8 @@ int32_t arroy_b200_search_batch(arroy_ctx* c, uint32_t nq, const uint32_t* query
         if (cand_cap64 > 0x7fffffffull || heap_cap64 > 0x7fffffffull) throw ArgError("search_k too large for the device walk");
         const uint32_t cand_cap = (uint32_t)std::max<uint64_t>(cand_cap64, 1), heap_cap = (uint32_t)heap_cap64;
         const uint32_t bm_words = (uint32_t)((c->n + 31) / 32);
+        const size_t walk_smem = (size_t)WALK_WARPS * WALK_SHEAP * 8;
+        { static bool configured = false; if (!configured) { CK(cudaFuncSetAttribute(walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)walk_smem)); configured = true; } }
         for (double& x : c->sbreak) x = 0;
         int nte = 0;
         auto mark = [&]() { if (!c->xev[nte]) CK(cudaEventCreate(&c->xev[nte])); CK(cudaEventRecord(c->xev[nte], c->stream)); ++nte; };
@@ -1471,7 +1473,7 @@ int32_t arroy_b200_search_batch(arroy_ctx* c, uint32_t nq, const uint32_t* query
             } else CK(cudaMemsetAsync(c->s_qh0.p, 0, 4ull * m, c->stream));
             nte = 0; mark();
             CK(cudaMemsetAsync(c->w_bitmap.p, 0, 4ull * bm_words * m, c->stream));
-            walk_kernel<<<(m + WALK_WARPS - 1) / WALK_WARPS, WALK_WARPS * 32, 0, c->stream>>>(F, c->items.as<float>(), c->dim, ld, c->metric, m, d_qrows, d_q, c->s_qh0.as<float>(),
+            walk_kernel<<<(m + WALK_WARPS - 1) / WALK_WARPS, WALK_WARPS * 32, walk_smem, c->stream>>>(F, c->items.as<float>(), c->dim, ld, c->metric, m, d_qrows, d_q, c->s_qh0.as<float>(),
                                                                                        search_k, c->w_heaps.as<unsigned long long>(), heap_cap, c->w_cand.as<uint32_t>(), cand_cap,
                                                                                        c->w_count.as<uint32_t>(), c->w_bitmap.as<uint32_t>(), bm_words, c->w_status.as<int32_t>());
             CK(cudaGetLastError());

@@ -1105,18 +1105,21 @@ int32_t arroy_reader_nns_batch_by_item(arroy_reader* r, uint32_t nq, const uint3
     return hguard([&] {
         const uint32_t d = r->dims;
         const int hf = header_floats(r->metric);
-        std::vector<float> q((size_t)nq * d), qh0(nq), qh1(nq);
-        std::vector<std::vector<uint32_t>> rows(nq);
-        {
+        std::vector<float> q, qh0, qh1;
+        std::vector<std::vector<uint32_t>> rows;
+        for (uint32_t i = 0; i < nq; ++i)
+            if (row_of(r, items[i]) < 0) throw HostError(ARROY_ERR_MISSING_KEY, "Internal error: Item(" + std::to_string(items[i]) + ") is missing in index `" + std::to_string(r->index) + "`");
+        // the query vectors are only needed by the host walk (the device path addresses the staged rows)
+        auto load_queries = [&] {
+            q.resize((size_t)nq * d); qh0.resize(nq); qh1.resize(nq); rows.resize(nq);
             std::lock_guard<std::mutex> lk(r->env->mu);
             for (uint32_t i = 0; i < nq; ++i) {
                 int64_t row = row_of(r, items[i]);
-                if (row < 0) throw HostError(ARROY_ERR_MISSING_KEY, "Internal error: Item(" + std::to_string(items[i]) + ") is missing in index `" + std::to_string(r->index) + "`");
                 const std::string& v = r->env->kv.at(make_key(r->index, MODE_ITEM, items[i]));
                 memcpy(&q[(size_t)i * d], v.data() + 1 + 4 * hf, 4ull * d);
                 qh0[i] = r->hdr0[row]; qh1[i] = r->hdr1[row];
             }
-        }
+        };
         const uint32_t k_dev = (uint32_t)count;
         std::vector<int32_t> status(nq, 0);
         std::vector<uint32_t> orow_dev;
@@ -1142,6 +1145,7 @@ int32_t arroy_reader_nns_batch_by_item(arroy_reader* r, uint32_t nq, const uint3
             if (all_ok) return;
         }
         // host walk (all queries, or only the ones the device walk gave up on)
+        load_queries();
         auto t0 = clk::now();
         std::atomic<uint32_t> next{0};
         std::string err; std::mutex emu;

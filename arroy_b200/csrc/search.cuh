@@ -72,6 +72,7 @@ __device__ __forceinline__ unsigned long long heap_pop(unsigned long long* h, ui
 }
 
 constexpr int WALK_WARPS = 8;
+constexpr uint32_t WALK_SHEAP = 512;    // heap entries per query kept in shared memory (spills to the global heap beyond)
 
 // query q: vector = qrows ? items[qrows[q]] : queries[q] (ld floats); qh0 = extra_dim for DotProduct margins
 __global__ void __launch_bounds__(WALK_WARPS * 32)
@@ -85,13 +86,19 @@ walk_kernel(DevForest F, const float* __restrict__ items, uint32_t d, uint32_t l
     if (q >= nq) return;
     const float* qv = qrows ? items + (size_t)qrows[q] * ld : queries + (size_t)q * ld;
     const float qhdr = qh0 ? qh0[q] : 0.f;
-    unsigned long long* heap = heaps + (size_t)q * heap_cap;
+    // The heap lives in shared memory (a walk pushes two entries per pop: a few hundred in practice) and moves to
+    // its global-memory slot only if it outgrows WALK_SHEAP: every pop / push is a chain of dependent accesses.
+    extern __shared__ unsigned long long walk_sheap[];
+    unsigned long long* gheap = heaps + (size_t)q * heap_cap;
+    unsigned long long* heap = walk_sheap + (size_t)(threadIdx.x >> 5) * WALK_SHEAP;
+    uint32_t cap = WALK_SHEAP < heap_cap ? WALK_SHEAP : heap_cap;
     uint32_t* out = cand + (size_t)q * cand_cap;
     uint32_t* bm = bitmap + (size_t)q * bitmap_words;
     uint32_t size = 0;
+    if (F.n_roots > cap) { heap = gheap; cap = heap_cap; }
     if (lane == 0) {
         const unsigned long long inf_key = (unsigned long long)ordered_key(__uint_as_float(0x7f800000u)) << 32;
-        for (uint32_t r = 0; r < F.n_roots && size < heap_cap; ++r) heap_push(heap, size, inf_key | F.roots[r]);
+        for (uint32_t r = 0; r < F.n_roots && size < cap; ++r) heap_push(heap, size, inf_key | F.roots[r]);
     }
     unsigned long long total = 0;   // nns.len() of the reference (duplicates included)
     uint32_t unique = 0;
@@ -132,8 +139,16 @@ walk_kernel(DevForest F, const float* __restrict__ items, uint32_t d, uint32_t l
                 float dt = exact_warp<false>(nv, qv, (int)d);
                 mg = margin_finish(metric, dt, F.nh0[node], qhdr);
             }
+            // outgrown the shared-memory heap: move it (the array *is* the heap) to the global slot
+            const int spill = __shfl_sync(0xffffffffu, (int)(size + 2 > cap && heap != gheap), 0);
+            if (spill) {
+                const uint32_t sz = __shfl_sync(0xffffffffu, size, 0);
+                for (uint32_t i = lane; i < sz; i += 32) gheap[i] = heap[i];
+                __syncwarp();
+                heap = gheap; cap = heap_cap;
+            }
             if (lane == 0) {
-                if (size + 2 > heap_cap) st = 2;
+                if (size + 2 > cap) st = 2;
                 else {
                     heap_push(heap, size, ((unsigned long long)ordered_key(f32_min_dev(-mg, dist)) << 32) | F.left[node]);
                     heap_push(heap, size, ((unsigned long long)ordered_key(f32_min_dev(mg, dist)) << 32) | F.right[node]);
