@@ -656,7 +656,12 @@ void do_build_emit(arroy_ctx* c, const uint32_t* root_ids, const uint64_t* base,
     const int hdrf = metric_header_floats(c->metric);
     const uint32_t d = c->dim;
     std::mutex sink_mu;
-    std::atomic<uint32_t> next_tree{0};
+    // work items = (tree, block of ENC_BLOCK records): finer than one tree per thread, so that 50 trees keep 64 threads busy
+    constexpr uint32_t ENC_BLOCK = 256;
+    std::vector<uint64_t> blk_off(n_trees + 1, 0);
+    for (uint32_t t = 0; t < n_trees; ++t) blk_off[t + 1] = blk_off[t] + (tree_ptr[t]->n_recs + ENC_BLOCK - 1) / ENC_BLOCK;
+    const uint64_t n_blocks = blk_off[n_trees];
+    std::atomic<uint64_t> next_block{0};
     std::atomic<int> abort_flag{0};
     std::string worker_err;
     auto worker = [&]() {
@@ -664,14 +669,16 @@ void do_build_emit(arroy_ctx* c, const uint32_t* root_ids, const uint64_t* base,
         std::vector<uint32_t> ids;
         try {
             for (;;) {
-                uint32_t t = next_tree.fetch_add(1);
-                if (t >= n_trees || abort_flag.load()) return;
+                const uint64_t w = next_block.fetch_add(1);
+                if (w >= n_blocks || abort_flag.load()) return;
+                const uint32_t t = (uint32_t)(std::upper_bound(blk_off.begin(), blk_off.end(), w) - blk_off.begin() - 1);
                 const BuiltTree& T = *tree_ptr[t];
                 const Record* recs = static_cast<const Record*>(T.recs);
                 const float* pool = T.pool;
                 const uint32_t root_local = T.n_recs - 1;
                 auto gid = [&](uint32_t li) { return li == root_local ? root_ids[t] : (node_ids ? node_ids[id_off[t] + li] : (uint32_t)(base[t] + li)); };
-                for (uint32_t li = 0; li < T.n_recs; ++li) {
+                const uint32_t li0 = (uint32_t)(w - blk_off[t]) * ENC_BLOCK, li1 = std::min<uint32_t>(T.n_recs, li0 + ENC_BLOCK);
+                for (uint32_t li = li0; li < li1; ++li) {
                     const Record& r = recs[li];
                     buf.clear();
                     if (r.kind == REC_DESC) {
@@ -698,7 +705,7 @@ void do_build_emit(arroy_ctx* c, const uint32_t* root_ids, const uint64_t* base,
             }
         } catch (const std::exception& e) { std::lock_guard<std::mutex> lk(sink_mu); worker_err = e.what(); abort_flag = 2; }
     };
-    int nthreads = (int)std::min<uint32_t>(n_trees, std::max(1u, std::min(32u, std::thread::hardware_concurrency())));
+    int nthreads = (int)std::min<uint64_t>(n_blocks, std::max(1u, std::min(64u, std::thread::hardware_concurrency())));
     if (const char* e = getenv("ARROY_B200_ENCODE_THREADS")) nthreads = std::max(1, atoi(e));
     if (c->n < 100000) nthreads = 1;
     if (nthreads <= 1) worker();

@@ -526,7 +526,7 @@ def main():
                     hits += len(set(g_rows[i, :g_len[i]].tolist()) & set(out_ids[i, :out_len[i]].tolist()))
                 line["query"] = {"qps_batched": Q / q_sec, "queries": Q, "k": k, "search_k": k * T, "recall_at_100": hits / (QG * k), "recall_queries": QG,
                                  "tree_walk_ms": qms["tree_walk_ms"], "rerank_ms": qms["rerank_ms"], "qps_one_at_a_time": 1.0 / one_sec,
-                                 "api": "Reader.nns(100).by_item / nns_batch_by_item (host tree walk on %d threads + device re-rank)" % (os.cpu_count() or 1)}
+                                 "api": "Reader.nns_batch_by_item: device tree walk (one warp per query) + fused bf16 pre-filter / exact re-score / top-k kernel; one-at-a-time = Reader.nns(100).by_item"}
                 del reader
             env._ctx = None
             del w, env
