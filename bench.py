@@ -531,6 +531,58 @@ def main():
             env._ctx = None
             del w, env
         del host
+    elif world > 1 and not args.no_e2e and d % 32 == 0 and metric != "dot-product":
+        # ---- e2e at N > 1: rank 0 decodes + uploads the host leaf values, ONE NCCL broadcast straight out of the
+        # library's item buffer, every rank builds and encodes its trees into its own host arena (sharded_build) ------
+        class _DevView:   # zero-copy torch view of the staged item matrix of this context
+            def __init__(self, ptr, shape):
+                self.__cuda_array_interface__ = {"shape": shape, "typestr": "<f4", "data": (int(ptr), False), "version": 2}
+        if rank == 0:
+            host = items.cpu().numpy()
+            ctx.stage_items_device(metric, ids, d, items.data_ptr())
+            h0, _ = ctx.item_headers()
+            stride = 1 + 4 + 4 * d
+            blob = np.zeros(n * stride, dtype=np.uint8)
+            b2 = blob.reshape(n, stride)
+            b2[:, 1:5] = h0.view(np.uint8).reshape(n, 4)
+            b2[:, 5:] = host.view(np.uint8).reshape(n, 4 * d)
+            ptrs = (blob.ctypes.data + np.arange(n, dtype=np.uint64) * np.uint64(stride)).astype(np.uint64)
+            del host
+        arena = ab.Arena()
+        roots = list(range(T))
+        e_ms = []
+        cc0 = None
+        n_warm = 1
+        for step in range(n_warm + args.steps):
+            arena.clear()
+            barrier()
+            if step == n_warm:
+                cc0 = ctx.counters()
+            t0 = time.perf_counter()
+            if rank == 0:
+                ctx.stage_items_ptrs(metric, d, ids, ptrs)
+                (p_items, _, _), ld_items = ctx.device_ptrs()
+                src = torch.as_tensor(_DevView(p_items, (n, ld_items)), device=dev)
+                parallel.broadcast_items(dist, src, src=0)
+            else:
+                parallel.broadcast_items(dist, items, src=0)
+                torch.cuda.synchronize()
+                ctx.stage_items_device(metric, ids, d, items.data_ptr())
+            parallel.sharded_build(ctx, dist, rank, world, seeds, roots, T, arena=arena, device=dev)
+            barrier()
+            if step >= n_warm:
+                e_ms.append((time.perf_counter() - t0) * 1e3)
+        cc1 = ctx.counters()
+        t_e = torch.tensor([sum(e_ms) / len(e_ms), float(cc1["h2d_bytes"] - cc0["h2d_bytes"]) / args.steps, float(cc1["d2h_bytes"] - cc0["d2h_bytes"]) / args.steps],
+                           dtype=torch.float64, device=dev)
+        t_max = t_e.clone()
+        dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t_e, op=dist.ReduceOp.SUM)
+        if rank == 0:
+            e_sec = float(t_max[0].item()) * 1e-3
+            line["e2e"] = {"value": n / e_sec, "unit": "vectors/s", "h2d_bytes_per_step": int(t_e[1].item()), "d2h_bytes_per_step": int(t_e[2].item()), "ms_per_step": e_sec * 1e3,
+                           "api": "rank 0: arroy_b200_stage_items(leaf value pointers); NCCL broadcast of the item buffer; every rank: arroy_b200_build_trees_begin / _emit (arena sink) for its trees",
+                           "timing": "wall clock between barriers, max over ranks"}
     elif rank == 0:
         line["e2e"] = None
     # ---- CPU baseline (oracle port) on a bounded sample, rank 0, N=1 only --------------------------------
