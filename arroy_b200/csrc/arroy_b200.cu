@@ -348,8 +348,9 @@ void build_wave(arroy_ctx* c, size_t wave_no, uint32_t t0, uint32_t tw, const ui
     P.jobs = W.jobs.as<Job>(); P.scratch = W.scratch.as<float>(); P.use_smem_ws = use_smem;
     P.active = W.active.as<uint32_t>(); P.error = W.error.as<int32_t>();
     P.sub_rows = nullptr; P.sub_off = nullptr;
-    P.small_max = getenv("ARROY_B200_SMALL_MAX") ? (uint32_t)atoi(getenv("ARROY_B200_SMALL_MAX")) : 2048u;
-    P.max_inner = 48u;
+    // cluster-resident nodes: up to ~6 MB of item rows per scan (2048 rows at d = 768, every node of a 10k x 64 index)
+    P.small_max = getenv("ARROY_B200_SMALL_MAX") ? (uint32_t)atoi(getenv("ARROY_B200_SMALL_MAX")) : (uint32_t)std::max<uint64_t>(2048, (6ull << 20) / (4ull * ld));
+    P.max_inner = 1024u;   // attempts per launch; `cancel` is polled between launches
     P.timing = nullptr;
     if (getenv("ARROY_B200_CTRL_TIMING")) { W.timing.ensure(16 * 8); CK(cudaMemsetAsync(W.timing.p, 0, 16 * 8, c->stream)); P.timing = W.timing.as<unsigned long long>(); }
     if (sub.rows) {   // this wave's subsets, offsets rebased to the wave
