@@ -789,7 +789,8 @@ const float* xf_candidates(arroy_ctx* c, const uint32_t* rows, uint32_t nc) {
 // kernel of tcgemm.cuh; engine 1: cuBLAS (kept as the cross-check of the hand-written kernel)
 void xf_scores(arroy_ctx* c, const float* q, uint32_t m, const float* cand, uint32_t nc, float* S, uint32_t lds, TgEpilogue ep, int engine) {
     if (engine == 0) {
-        if (!tcgemm_tf32(q, m, cand, nc, c->ld, S, lds, ep, c->sm_count, c->stream)) throw CudaError(std::string("tcgemm_tf32 launch failed: ") + cudaGetErrorString(cudaGetLastError()));
+        const int mc = (getenv("ARROY_B200_XGEMM_MC") && atoi(getenv("ARROY_B200_XGEMM_MC")) == 1) ? 1 : 2;
+        if (!tcgemm_tf32(q, m, cand, nc, c->ld, S, lds, ep, c->sm_count, c->stream, mc)) throw CudaError(std::string("tcgemm_tf32 launch failed: ") + cudaGetErrorString(cudaGetLastError()));
         c->n_launches += 1;
         return;
     }
@@ -1335,6 +1336,7 @@ int32_t arroy_b200_rerank_shared(arroy_ctx* c, uint32_t nq, const float* queries
                 mark();
                 // A (m x nc, row-major) = distance estimates: Q . cand^T on the tensor cores (TF32 inputs, FP32 accumulate) + fused epilogue
                 TgEpilogue ep{c->metric == EUCLIDEAN ? TG_EUCLID : (c->metric == COSINE ? TG_COSINE : TG_NEG), c->x_qa.as<float>(), c->x_qb.as<float>(), c->x_ca.as<float>(), c->x_cb.as<float>()};
+                if (getenv("ARROY_B200_XGEMM_NOSTORE")) ep.mode = 99;   // experiment: GEMM without the stores (results are garbage)
                 xf_scores(c, c->s_q.as<float>(), m, cand, nc, c->x_S.as<float>(), lds, ep, xf_engine());
                 mark();
                 CK(cudaMemsetAsync(c->x_flag.p, 0, 4, c->stream));

@@ -21,6 +21,7 @@
 // candidate rows in L2 and C streams from HBM once.
 #pragma once
 #include <cuda.h>
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -69,6 +70,11 @@ __device__ __forceinline__ void tg_tma_load_2d(uint32_t dst, const CUtensorMap* 
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
+// the same load delivered to the same shared-memory offset (and mbarrier) of every CTA in `mask`
+__device__ __forceinline__ void tg_tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint16_t mask) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(mask) : "memory");
+}
 __device__ __forceinline__ void tg_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tg_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -91,6 +97,9 @@ __device__ __forceinline__ void tg_mma_tf32(uint32_t tmem_d, uint64_t desc_a, ui
 }
 __device__ __forceinline__ void tg_commit(uint32_t bar) {   // arrives on `bar` once every MMA issued so far has completed
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tg_commit_mc(uint32_t bar, uint16_t mask) {   // ... on the barrier at this offset in every CTA of `mask`
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
 }
 __device__ __forceinline__ void tg_tmem_ld32(uint32_t taddr, uint32_t* v) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -132,6 +141,12 @@ __device__ __forceinline__ float tg_finish(int mode, float s, float qa, float qb
     return pnqn == pnqn ? 0.0f : pnqn;
 }
 
+// MC = 1: independent CTAs. MC = 2: clusters of two CTAs that work on the same 256 candidates and two
+// neighbouring blocks of 128 queries; each CTA fetches one half of the candidate tile and TMA-multicasts it
+// into both CTAs' shared memory, so the operand traffic L2 -> SM per CTA drops from 48 to 32 KB per stage (that
+// traffic, not the tensor pipe, limits the MC = 1 kernel). A stage is released to both producers by both MMA
+// warps (tcgen05.commit.multicast on the `empty` barriers, which therefore count two arrivals).
+template <int MC>
 __global__ void __launch_bounds__(TG_THREADS, 1)
 tcgemm_tf32_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_c,
                    float* __restrict__ S, uint32_t m, uint32_t nc, uint32_t lds, uint32_t nk, TgEpilogue ep) {
@@ -148,11 +163,14 @@ tcgemm_tf32_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(tg_raw + (tmem_slot - raw));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t num_m = (m + TG_BM - 1) / TG_BM, num_n = (nc + TG_BN - 1) / TG_BN;
-    const uint32_t tiles = num_m * num_n;
+    const uint32_t crank = MC > 1 ? cooperative_groups::this_cluster().block_rank() : 0u;
+    const uint32_t num_mb = ((m + TG_BM - 1) / TG_BM + MC - 1) / MC, num_n = (nc + TG_BN - 1) / TG_BN;   // m-blocks per cluster step
+    const uint32_t tiles = num_mb * num_n, first = blockIdx.x / MC, stride = gridDim.x / MC;
+    auto tile_m0 = [&](uint32_t t) { return ((t % num_mb) * MC + crank) * TG_BM; };   // may lie beyond m: zero rows, nothing stored
+    auto tile_n0 = [&](uint32_t t) { return (t / num_mb) * TG_BN; };
 
     if (warp == 0 && lane == 0) {
-        for (int s = 0; s < TG_STAGES; ++s) { tg_mbar_init(full(s), 1); tg_mbar_init(empty(s), 1); }
+        for (int s = 0; s < TG_STAGES; ++s) { tg_mbar_init(full(s), 1); tg_mbar_init(empty(s), MC); }
         for (int a = 0; a < 2; ++a) { tg_mbar_init(tfull(a), 1); tg_mbar_init(tempty(a), TG_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
@@ -164,20 +182,22 @@ tcgemm_tf32_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     }
     tg_fence_before();
     __syncthreads();
+    if (MC > 1) cooperative_groups::this_cluster().sync();   // the peer's barriers exist before anything is multicast to them
     tg_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
 
     if (warp == 0) {
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            for (uint32_t t = blockIdx.x; t < tiles; t += gridDim.x) {
-                const int m0 = (int)((t % num_m) * TG_BM), n0 = (int)((t / num_m) * TG_BN);
+            for (uint32_t t = first; t < tiles; t += stride) {
+                const int m0 = (int)tile_m0(t), n0 = (int)tile_n0(t);
                 for (uint32_t kb = 0; kb < nk; ++kb) {
                     tg_mbar_wait(empty(stage), phase ^ 1u);
                     tg_mbar_expect_tx(full(stage), TG_STAGE_BYTES);
                     const uint32_t sa = base + stage * TG_STAGE_BYTES, sb = sa + TG_A_BYTES;
                     tg_tma_load_2d(sa, &map_q, full(stage), (int)(kb * TG_BK), m0);
-                    tg_tma_load_2d(sb, &map_c, full(stage), (int)(kb * TG_BK), n0);
+                    if (MC == 1) tg_tma_load_2d(sb, &map_c, full(stage), (int)(kb * TG_BK), n0);
+                    else tg_tma_load_2d_mc(sb + crank * (TG_B_BYTES / MC), &map_c, full(stage), (int)(kb * TG_BK), n0 + (int)(crank * (TG_BN / MC)), (uint16_t)((1u << MC) - 1u));
                     if (++stage == TG_STAGES) { stage = 0; phase ^= 1u; }
                 }
             }
@@ -185,7 +205,7 @@ tcgemm_tf32_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     } else if (warp == 1) {
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0, it = 0;
-            for (uint32_t t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
+            for (uint32_t t = first; t < tiles; t += stride, ++it) {
                 const uint32_t a = it & 1u, aphase = (it >> 1) & 1u;
                 tg_mbar_wait(tempty(a), aphase ^ 1u);                 // epilogue has drained this accumulator
                 tg_fence_after();
@@ -198,7 +218,8 @@ tcgemm_tf32_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
 #pragma unroll
                     for (int k = 0; k < TG_BK / TG_UK; ++k)            // +32 bytes of K inside the swizzle span per step
                         tg_mma_tf32(d, da + (uint64_t)(k * TG_UK * 4 / 16), db + (uint64_t)(k * TG_UK * 4 / 16), (kb | (uint32_t)k) != 0u);
-                    tg_commit(empty(stage));                           // frees the stage when these MMAs retire
+                    if (MC == 1) tg_commit(empty(stage));              // frees the stage when these MMAs retire
+                    else tg_commit_mc(empty(stage), (uint16_t)((1u << MC) - 1u));   // ... in both CTAs: both producers write into both
                     if (++stage == TG_STAGES) { stage = 0; phase ^= 1u; }
                 }
                 tg_commit(tfull(a));                                   // accumulator complete
@@ -209,9 +230,9 @@ tcgemm_tf32_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         const uint32_t half = (uint32_t)(warp - 2) >> 2;               // which 128 columns of the tile
         const uint32_t et = threadIdx.x - 64u;                         // 0 .. 255 over the epilogue warps
         uint32_t it = 0;
-        for (uint32_t t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
+        for (uint32_t t = first; t < tiles; t += stride, ++it) {
             const uint32_t a = it & 1u, aphase = (it >> 1) & 1u;
-            const uint32_t m0 = (t % num_m) * TG_BM, n0 = (t / num_m) * TG_BN;
+            const uint32_t m0 = tile_m0(t), n0 = tile_n0(t);
             float* ca_s = cst + a * 2 * TG_BN;
             float* cb_s = ca_s + TG_BN;
             if (ep.mode >= TG_EUCLID) {                                // this tile's column constants -> shared memory
@@ -248,7 +269,7 @@ tcgemm_tf32_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                         v[4 * j + 3] = __float_as_uint(tg_finish(ep.mode, __uint_as_float(v[4 * j + 3]), qa, qb, x.w, y.w));
                     }
                 }
-                if (row < m) {
+                if (row < m && ep.mode != 99) {
                     if (col + 32u <= lds) {
 #pragma unroll
                         for (int j = 0; j < 8; ++j)
@@ -266,6 +287,7 @@ tcgemm_tf32_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     }
     tg_fence_before();
     __syncthreads();
+    if (MC > 1) cooperative_groups::this_cluster().sync();   // no CTA leaves while its peer can still multicast into it
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TG_TMEM_COLS) : "memory");
 }
 
@@ -308,18 +330,29 @@ inline bool tg_make_map(CUtensorMap* map, const float* ptr, uint64_t rows, uint3
 }
 
 // S[m x nc] (pitch lds, lds % 4 == 0) = Q[m x ld] . C[nc x ld]^T; false if the tensor maps cannot be built
-inline bool tcgemm_tf32(const float* Q, uint32_t m, const float* C, uint32_t nc, uint32_t ld, float* S, uint32_t lds, TgEpilogue ep, int sm_count, cudaStream_t stream) {
-    CUtensorMap mq, mc;
-    if (!tg_make_map(&mq, Q, m, ld, TG_BM) || !tg_make_map(&mc, C, nc, ld, TG_BN)) return false;
+inline bool tcgemm_tf32(const float* Q, uint32_t m, const float* C, uint32_t nc, uint32_t ld, float* S, uint32_t lds, TgEpilogue ep, int sm_count, cudaStream_t stream, int mc = 2) {
+    if (mc != 1 && mc != 2) mc = 2;
+    CUtensorMap mq, mcand;
+    if (!tg_make_map(&mq, Q, m, ld, TG_BM) || !tg_make_map(&mcand, C, nc, ld, TG_BN / mc)) return false;
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(tcgemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TG_SMEM) != cudaSuccess) return false;
+        if (cudaFuncSetAttribute(tcgemm_tf32_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TG_SMEM) != cudaSuccess) return false;
+        if (cudaFuncSetAttribute(tcgemm_tf32_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TG_SMEM) != cudaSuccess) return false;
         configured = true;
     }
-    const uint32_t tiles = ((m + TG_BM - 1) / TG_BM) * ((nc + TG_BN - 1) / TG_BN);
-    const int grid = (int)(tiles < (uint32_t)sm_count ? tiles : (uint32_t)sm_count);
-    tcgemm_tf32_kernel<<<grid, TG_THREADS, TG_SMEM, stream>>>(mq, mc, S, m, nc, lds, ld / TG_BK, ep);
-    return cudaGetLastError() == cudaSuccess;
+    const uint32_t num_mb = ((m + TG_BM - 1) / TG_BM + mc - 1) / mc;
+    const uint32_t tiles = num_mb * ((nc + TG_BN - 1) / TG_BN);
+    const uint32_t units = (uint32_t)(sm_count / mc);
+    const int grid = (int)((tiles < units ? tiles : units) * mc);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(TG_THREADS); cfg.dynamicSmemBytes = TG_SMEM; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = (unsigned)mc; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    const uint32_t nk = ld / TG_BK;
+    cudaError_t e = mc == 1 ? cudaLaunchKernelEx(&cfg, tcgemm_tf32_kernel<1>, mq, mcand, S, m, nc, lds, nk, ep)
+                            : cudaLaunchKernelEx(&cfg, tcgemm_tf32_kernel<2>, mq, mcand, S, m, nc, lds, nk, ep);
+    return e == cudaSuccess;
 }
 
 }  // namespace ab

@@ -1,5 +1,7 @@
 """rerank_shared: the tensor-core pre-filter + exact re-score must return exactly what the exact
 dense kernel (and the oracle, reader.rs:381-399) returns."""
+import os
+
 import numpy as np
 import pytest
 
@@ -8,6 +10,7 @@ import oracle
 
 pytestmark = pytest.mark.gpu
 SEED = bytes([42] * 32)
+CUBLAS = bool(os.environ.get("ARROY_TEST_CUBLAS"))   # engine 1 is only a cross-check of the hand-written kernel
 
 
 @pytest.fixture(scope="module")
@@ -90,9 +93,10 @@ def test_prefilter_nan_and_inf_inputs(ctx, monkeypatch):
 
 
 @pytest.mark.parametrize("d,nq,nc", [(768, 300, 5001), (33, 7, 258), (100, 129, 1000), (64, 1, 40)])
-def test_tensor_core_scores_are_within_the_bound(ctx, d, nq, nc):
+def test_tensor_core_scores_are_within_the_bound(ctx, monkeypatch, d, nq, nc):
     # the bound the whole pre-filter rests on: |S - q.c| <= 2^-8 |q| |c|, for the hand-written tcgen05
-    # kernel (engine 0) and for cuBLAS (engine 1); ragged tile edges in both directions
+    # kernel (engine 0, single-CTA and 2-CTA multicast variants) and optionally for cuBLAS (engine 1); ragged tile
+    # edges in both directions
     n = nc + 50
     data = oracle.synth_rows(SEED, d, 0, n + nq, 0.5)
     data[3] *= np.float32(1e10)
@@ -102,14 +106,18 @@ def test_tensor_core_scores_are_within_the_bound(ctx, d, nq, nc):
     for rows in (np.arange(10, 10 + nc, dtype=np.uint32), np.sort(np.random.default_rng(1).choice(n, nc, replace=False)).astype(np.uint32)):
         exact = q.astype(np.float64) @ data[rows].astype(np.float64).T
         bound = np.linalg.norm(q.astype(np.float64), axis=1)[:, None] * np.linalg.norm(data[rows].astype(np.float64), axis=1)[None, :] / 256.0
-        own = ctx.prefilter_scores(q, rows, engine=0)
-        lib = ctx.prefilter_scores(q, rows, engine=1)
-        assert np.all(np.abs(own - exact) <= bound), float(np.max(np.abs(own - exact) / bound))
-        assert np.all(np.abs(lib - exact) <= bound)
+        for mc in ("1", "2"):
+            monkeypatch.setenv("ARROY_B200_XGEMM_MC", mc)
+            own = ctx.prefilter_scores(q, rows, engine=0)
+            assert np.all(np.abs(own - exact) <= bound), (mc, float(np.max(np.abs(own - exact) / bound)))
+        if CUBLAS:
+            lib = ctx.prefilter_scores(q, rows, engine=1)
+            assert np.all(np.abs(lib - exact) <= bound)
         # far tighter in practice: the truncation errors are not all aligned
         assert float(np.max(np.abs(own - exact) / bound)) < 0.25
 
 
+@pytest.mark.skipif(not CUBLAS, reason="cuBLAS cross-check engine: set ARROY_TEST_CUBLAS=1 (loading libcublasLt on a fresh box takes minutes)")
 def test_prefilter_engines_agree(ctx, monkeypatch):
     n, d, nq, k = 20_000, 128, 130, 50
     data = oracle.synth_rows(SEED, d, 0, n + nq, 0.5)
