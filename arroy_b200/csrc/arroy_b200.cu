@@ -209,13 +209,14 @@ void default_headers(arroy_ctx* c) {
 // issuing its own cudaMemcpyAsync on its own stream, so decode (host memcpy of unaligned values)
 // and PCIe transfers of different chunks overlap. row_src(i) = address of the dim floats of row i.
 template <class RowSrc>
-void stage_rows_pipeline(arroy_ctx* c, uint64_t n, uint32_t dim, uint32_t ld, RowSrc row_src) {
+void stage_rows_pipeline(arroy_ctx* c, uint64_t n, uint32_t dim, uint32_t ld, RowSrc row_src, float* dst_override = nullptr, size_t chunk_mb_override = 0, bool count_bytes = true) {
     if (n == 0) return;
     unsigned W = 8;   // measured on the B200 box: 8 lanes x 4 MB chunks reach ~48 GB/s (PCIe copy alone: 54 GB/s)
     if (const char* e = getenv("ARROY_B200_STAGE_THREADS")) W = (unsigned)std::max(1, atoi(e));
     W = std::max(1u, std::min(W, std::max(1u, std::thread::hardware_concurrency())));
     size_t chunk_mb = 4;
     if (const char* e = getenv("ARROY_B200_STAGE_CHUNK_MB")) chunk_mb = (size_t)std::max(1, atoi(e));
+    if (chunk_mb_override) chunk_mb = chunk_mb_override;
     const uint64_t chunk_rows = std::max<uint64_t>(1, (chunk_mb << 20) / ((size_t)ld * 4));
     const uint64_t n_chunks = (n + chunk_rows - 1) / chunk_rows;
     W = (unsigned)std::min<uint64_t>(W, n_chunks);
@@ -228,7 +229,7 @@ void stage_rows_pipeline(arroy_ctx* c, uint64_t n, uint32_t dim, uint32_t ld, Ro
     CK(cudaStreamSynchronize(c->stream));  // the destination buffer must not be in use
     std::mutex emu;
     std::string err;
-    float* dst = c->items.as<float>();
+    float* dst = dst_override ? dst_override : c->items.as<float>();
     auto worker = [&](unsigned w) {
         try {
             CK(cudaSetDevice(c->device));
@@ -253,7 +254,7 @@ void stage_rows_pipeline(arroy_ctx* c, uint64_t n, uint32_t dim, uint32_t ld, Ro
     if (W == 1) worker(0);
     else { std::vector<std::thread> th; for (unsigned w = 0; w < W; ++w) th.emplace_back(worker, w); for (auto& x : th) x.join(); }
     if (!err.empty()) throw CudaError(err);
-    c->h2d_bytes += n * (uint64_t)ld * 4;
+    if (count_bytes) c->h2d_bytes += n * (uint64_t)ld * 4;
 }
 
 // ---- RoaringBitmap::serialize_into (roaring 0.10.9, portable format, no run containers) ------
@@ -1315,8 +1316,15 @@ int32_t arroy_b200_rerank_shared(arroy_ctx* c, uint32_t nq, const float* queries
             const uint32_t m = std::min(chunk, nq - q0);
             c->s_q.ensure((size_t)m * ld * 4); c->s_qh0.ensure(4ull * m);
             c->s_orows.ensure(4ull * m * k); c->s_odist.ensure(4ull * m * k); c->s_olen.ensure(4ull * m);
-            if (ld != c->dim) CK(cudaMemsetAsync(c->s_q.p, 0, (size_t)m * ld * 4, c->stream));
-            CK(cudaMemcpy2DAsync(c->s_q.p, (size_t)ld * 4, queries + (size_t)q0 * c->dim, (size_t)c->dim * 4, (size_t)c->dim * 4, m, cudaMemcpyHostToDevice, c->stream));
+            if ((size_t)m * c->dim * 4 >= (4u << 20)) {
+                // big query batch from pageable host memory: the pinned multi-thread pipeline of the item staging (2 MB chunks)
+                const float* qsrc = queries + (size_t)q0 * c->dim;
+                const uint32_t dimq = c->dim;
+                stage_rows_pipeline(c, m, dimq, ld, [&](uint64_t i) { return reinterpret_cast<const uint8_t*>(qsrc + i * dimq); }, c->s_q.as<float>(), 2, false);
+            } else {
+                if (ld != c->dim) CK(cudaMemsetAsync(c->s_q.p, 0, (size_t)m * ld * 4, c->stream));
+                CK(cudaMemcpy2DAsync(c->s_q.p, (size_t)ld * 4, queries + (size_t)q0 * c->dim, (size_t)c->dim * 4, (size_t)c->dim * 4, m, cudaMemcpyHostToDevice, c->stream));
+            }
             if (qhdr0) CK(cudaMemcpyAsync(c->s_qh0.p, qhdr0 + q0, 4ull * m, cudaMemcpyHostToDevice, c->stream));
             else CK(cudaMemsetAsync(c->s_qh0.p, 0, 4ull * m, c->stream));
             bool done = false;
