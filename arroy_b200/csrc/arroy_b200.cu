@@ -1344,7 +1344,6 @@ int32_t arroy_b200_rerank_shared(arroy_ctx* c, uint32_t nq, const float* queries
                 mark();
                 // A (m x nc, row-major) = distance estimates: Q . cand^T on the tensor cores (TF32 inputs, FP32 accumulate) + fused epilogue
                 TgEpilogue ep{c->metric == EUCLIDEAN ? TG_EUCLID : (c->metric == COSINE ? TG_COSINE : TG_NEG), c->x_qa.as<float>(), c->x_qb.as<float>(), c->x_ca.as<float>(), c->x_cb.as<float>()};
-                if (getenv("ARROY_B200_XGEMM_NOSTORE")) ep.mode = 99;   // experiment: GEMM without the stores (results are garbage)
                 xf_scores(c, c->s_q.as<float>(), m, cand, nc, c->x_S.as<float>(), lds, ep, xf_engine());
                 mark();
                 CK(cudaMemsetAsync(c->x_flag.p, 0, 4, c->stream));

@@ -269,7 +269,7 @@ tcgemm_tf32_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                         v[4 * j + 3] = __float_as_uint(tg_finish(ep.mode, __uint_as_float(v[4 * j + 3]), qa, qb, x.w, y.w));
                     }
                 }
-                if (row < m && ep.mode != 99) {
+                if (row < m) {
                     if (col + 32u <= lds) {
 #pragma unroll
                         for (int j = 0; j < 8; ++j)
