@@ -1316,15 +1316,9 @@ int32_t arroy_b200_rerank_shared(arroy_ctx* c, uint32_t nq, const float* queries
             const uint32_t m = std::min(chunk, nq - q0);
             c->s_q.ensure((size_t)m * ld * 4); c->s_qh0.ensure(4ull * m);
             c->s_orows.ensure(4ull * m * k); c->s_odist.ensure(4ull * m * k); c->s_olen.ensure(4ull * m);
-            if ((size_t)m * c->dim * 4 >= (4u << 20)) {
-                // big query batch from pageable host memory: the pinned multi-thread pipeline of the item staging (2 MB chunks)
-                const float* qsrc = queries + (size_t)q0 * c->dim;
-                const uint32_t dimq = c->dim;
-                stage_rows_pipeline(c, m, dimq, ld, [&](uint64_t i) { return reinterpret_cast<const uint8_t*>(qsrc + i * dimq); }, c->s_q.as<float>(), 2, false);
-            } else {
-                if (ld != c->dim) CK(cudaMemsetAsync(c->s_q.p, 0, (size_t)m * ld * 4, c->stream));
-                CK(cudaMemcpy2DAsync(c->s_q.p, (size_t)ld * 4, queries + (size_t)q0 * c->dim, (size_t)c->dim * 4, (size_t)c->dim * 4, m, cudaMemcpyHostToDevice, c->stream));
-            }
+            // (a pinned multi-thread bounce of the 12.6 MB of config 5 was measured: not faster than the driver's own staging)
+            if (ld != c->dim) CK(cudaMemsetAsync(c->s_q.p, 0, (size_t)m * ld * 4, c->stream));
+            CK(cudaMemcpy2DAsync(c->s_q.p, (size_t)ld * 4, queries + (size_t)q0 * c->dim, (size_t)c->dim * 4, (size_t)c->dim * 4, m, cudaMemcpyHostToDevice, c->stream));
             if (qhdr0) CK(cudaMemcpyAsync(c->s_qh0.p, qhdr0 + q0, 4ull * m, cudaMemcpyHostToDevice, c->stream));
             else CK(cudaMemsetAsync(c->s_qh0.p, 0, 4ull * m, c->stream));
             bool done = false;
