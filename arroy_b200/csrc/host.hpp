@@ -363,9 +363,32 @@ struct IncCtx {
     arroy_env* env; arroy_ctx* ctx; uint16_t index; int metric; uint32_t d; size_t K;
     std::map<uint32_t, HNode> tree;                 // the index' tree nodes, kept in sync with env->kv
     const std::vector<uint32_t>* item_ids;          // ascending ids of the staged items (row = rank)
-    void put(uint32_t id, HNode&& n) { env->kv[make_key(index, MODE_TREE, id)] = encode_tree_node(n); tree[id] = std::move(n); }
-    void erase(uint32_t id) { env->kv.erase(make_key(index, MODE_TREE, id)); tree.erase(id); }
-    uint32_t row_of(uint32_t id) const { return (uint32_t)(std::lower_bound(item_ids->begin(), item_ids->end(), id) - item_ids->begin()); }
+    // O(1) lookups for the routing loops (millions of them per update): node id -> decoded node (std::map nodes do
+    // not move), item id -> row when the ids are small enough for a dense table
+    std::vector<const HNode*> by_id;
+    std::vector<uint32_t> dense_row;
+    void index_lookups() {
+        by_id.clear();
+        if (!tree.empty()) { by_id.assign((size_t)tree.rbegin()->first + 1, nullptr); for (auto& kv : tree) by_id[kv.first] = &kv.second; }
+        dense_row.clear();
+        if (!item_ids->empty() && item_ids->back() < (1u << 26)) {
+            dense_row.assign((size_t)item_ids->back() + 1, 0xffffffffu);
+            for (size_t i = 0; i < item_ids->size(); ++i) dense_row[(*item_ids)[i]] = (uint32_t)i;
+        }
+    }
+    const HNode& node(uint32_t id) const { if (id < by_id.size() && by_id[id]) return *by_id[id]; return tree.at(id); }
+    void put(uint32_t id, HNode&& n) {
+        env->kv[make_key(index, MODE_TREE, id)] = encode_tree_node(n);
+        HNode& slot = tree[id];
+        slot = std::move(n);
+        if (id >= by_id.size()) by_id.resize((size_t)id + 1, nullptr);
+        by_id[id] = &slot;
+    }
+    void erase(uint32_t id) { env->kv.erase(make_key(index, MODE_TREE, id)); tree.erase(id); if (id < by_id.size()) by_id[id] = nullptr; }
+    uint32_t row_of(uint32_t id) const {
+        if (id < dense_row.size() && dense_row[id] != 0xffffffffu) return dense_row[id];
+        return (uint32_t)(std::lower_bound(item_ids->begin(), item_ids->end(), id) - item_ids->begin());
+    }
 };
 
 inline void inc_delete_tree(IncCtx& C, uint32_t node) {   // writer.rs:1263-1277
@@ -392,7 +415,7 @@ struct IdSet {  // membership test for the updated item ids: dense marker table 
 
 // delete_items_in_file — writer.rs:1021-1114. second.first = "Some(items)"
 inline std::pair<uint32_t, std::pair<bool, std::vector<uint32_t>>> inc_delete_items(IncCtx& C, uint32_t current, TmpOps& tmp, const IdSet& to_delete) {
-    const HNode& nd = C.tree.at(current);
+    const HNode& nd = C.node(current);
     if (nd.kind == 1) {
         std::vector<uint32_t> nw;
         for (uint32_t id : nd.desc) if (!to_delete.count(id)) nw.push_back(id);
@@ -473,7 +496,7 @@ inline std::vector<char> inc_route_batched(IncCtx& C, const std::vector<uint32_t
         for (size_t i = 0; i < front.size(); ++i) {
             Front& f = front[i];
             if (!ok[f.root_idx]) continue;
-            const HNode& nd = C.tree.at(f.node);
+            const HNode& nd = C.node(f.node);
             if (nd.kind == 1) { leaf_ins[f.node] = std::move(f.ids); continue; }
             if (nd.normal.empty()) { ok[f.root_idx] = 0; continue; }
             float hh = 0.f;
@@ -492,11 +515,11 @@ inline std::vector<char> inc_route_batched(IncCtx& C, const std::vector<uint32_t
             dev_ck(C.ctx, arroy_b200_side_multi(C.ctx, (uint32_t)job_front.size(), normals.data(), h0.data(), nullptr, rows.data(), off.data(), side.data()));
             for (size_t j = 0; j < job_front.size(); ++j) {
                 Front& f = front[job_front[j]];
-                const HNode& nd = C.tree.at(f.node);
+                const HNode& nd = C.node(f.node);
                 Routed rt;
                 for (size_t i = 0; i < f.ids.size(); ++i) { if (side[off[j] + i]) rt.right.push_back(f.ids[i]); else rt.left.push_back(f.ids[i]); }
                 if (!rt.left.empty()) next.push_back({f.root_idx, nd.left, rt.left});
-                if (!rt.right.empty()) next.push_back({f.root_idx, nd.right, rt.right});
+                if (!rt.right.empty()) next.push_back({f.root_idx, nd.right, rt.right});   // (copies: `routed` keeps its own for the replay)
                 routed[f.node] = std::move(rt);
             }
         }
@@ -505,7 +528,7 @@ inline std::vector<char> inc_route_batched(IncCtx& C, const std::vector<uint32_t
     return ok;
 }
 inline void inc_replay(IncCtx& C, uint32_t node, const std::unordered_map<uint32_t, Routed>& routed, std::unordered_map<uint32_t, std::vector<uint32_t>>& leaf_ins, IntMapOrder& out) {
-    const HNode& nd = C.tree.at(node);
+    const HNode& nd = C.node(node);
     if (nd.kind == 1) {
         const std::vector<uint32_t>& ins = leaf_ins.at(node);
         std::vector<uint32_t> merged;
@@ -555,7 +578,13 @@ inline void writer_build(arroy_writer* w, arroy_ctx* ctx, arroy_rng* rng, int64_
     std::lock_guard<std::mutex> lk(env->mu);
     for (auto& t : w->timings) t = 0;
     auto t_all = clk::now();
-    auto step = [&](const char* name) { if (progress) progress(progress_arg, name); };
+    const bool trace_steps = getenv("ARROY_B200_TRACE") != nullptr;
+    auto t_step = clk::now();
+    const char* last_step = "start";
+    auto step = [&](const char* name) {
+        if (trace_steps) { fprintf(stderr, "[trace] build step %-36s %.2f ms\n", last_step, ms_since(t_step)); t_step = clk::now(); last_step = name; }
+        if (progress) progress(progress_arg, name);
+    };
     auto cancelled = [&]() { if (cancel && cancel(cancel_arg)) throw HostError(ARROY_ERR_BUILD_CANCELLED, "The corresponding build process has been cancelled"); };
     const uint16_t index = w->index;
     const uint32_t d = w->dims;
@@ -629,6 +658,7 @@ inline void writer_build(arroy_writer* w, arroy_ctx* ctx, arroy_rng* rng, int64_
             auto it = env->kv.lower_bound(make_key(index, MODE_TREE, 0));
             for (; it != env->kv.end() && it->first[0] == (uint8_t)(index >> 8) && it->first[1] == (uint8_t)index && it->first[2] == MODE_TREE; ++it)
                 C.tree[key_item(it->first)] = decode_tree_node(it->second);
+            C.index_lookups();
         }
         step("RetrievingTheUsedTreeNodes");
         NodeIdAlloc alloc(C.tree);
