@@ -296,10 +296,11 @@ struct IntMapOrder {
         ++items;
         return vals[find(k)];
     }
-    void merge_from(const IntMapOrder& src) {   // for (k, v) in src { self.entry(k).or_default().extend(v) }
+    void merge_from(IntMapOrder& src) {   // for (k, v) in src { self.entry(k).or_default().extend(v) }; src is consumed
         for (size_t b = 0; b < src.keys.size(); ++b) {
             if (src.keys[b] < 0) continue;
             std::vector<uint32_t>& dv = entry((uint32_t)src.keys[b]);
+            if (dv.empty()) { dv = std::move(src.vals[b]); continue; }   // the usual case: the two maps hold different nodes
             std::vector<uint32_t> merged;
             std::set_union(dv.begin(), dv.end(), src.vals[b].begin(), src.vals[b].end(), std::back_inserter(merged));
             dv.swap(merged);
@@ -655,9 +656,22 @@ inline void writer_build(arroy_writer* w, arroy_ctx* ctx, arroy_rng* rng, int64_
         // ---- an index that already has trees: update it in place --------------------------------------
         IncCtx C{env, ctx, index, w->metric, d, (size_t)K, {}, &items.ids};
         {
+            // decode every tree node of the index (threads: the leaves' bitmaps are most of the work)
+            std::vector<std::pair<uint32_t, const std::string*>> raw;
             auto it = env->kv.lower_bound(make_key(index, MODE_TREE, 0));
             for (; it != env->kv.end() && it->first[0] == (uint8_t)(index >> 8) && it->first[1] == (uint8_t)index && it->first[2] == MODE_TREE; ++it)
-                C.tree[key_item(it->first)] = decode_tree_node(it->second);
+                raw.push_back({key_item(it->first), &it->second});
+            std::vector<HNode> dec(raw.size());
+            const unsigned nt = (unsigned)std::max<size_t>(1, std::min<size_t>({(size_t)16, (size_t)std::thread::hardware_concurrency(), raw.size() / 4096 + 1}));
+            std::string derr; std::mutex dmu;
+            auto dwork = [&](unsigned t) {
+                try { for (size_t i = t; i < raw.size(); i += nt) dec[i] = decode_tree_node(*raw[i].second); }
+                catch (const std::exception& e) { std::lock_guard<std::mutex> lk(dmu); derr = e.what(); }
+            };
+            if (nt == 1) dwork(0);
+            else { std::vector<std::thread> th; for (unsigned t = 0; t < nt; ++t) th.emplace_back(dwork, t); for (auto& x : th) x.join(); }
+            if (!derr.empty()) throw HostError(ARROY_ERR_PANIC, derr);
+            for (size_t i = 0; i < raw.size(); ++i) C.tree.emplace_hint(C.tree.end(), raw[i].first, std::move(dec[i]));
             C.index_lookups();
         }
         step("RetrievingTheUsedTreeNodes");
@@ -670,8 +684,22 @@ inline void writer_build(arroy_writer* w, arroy_ctx* ctx, arroy_rng* rng, int64_
         step("RemoveItemsFromExistingTrees");
         const IdSet to_delete(updated);
         {   // writer.rs:978-1015
+            // one recursion per root; they only read the decoded tree, so they run on threads and their puts / removals are
+            // merged afterwards (the final state does not depend on the order)
             TmpOps tmp;
-            for (uint32_t& root : roots) { cancelled(); root = inc_delete_items(C, root, tmp, to_delete).first; }
+            cancelled();
+            std::vector<TmpOps> per(roots.size());
+            const unsigned nt = (unsigned)std::max<size_t>(1, std::min<size_t>({(size_t)16, (size_t)std::thread::hardware_concurrency(), roots.size()}));
+            std::atomic<size_t> next_root{0};
+            std::string derr; std::mutex dmu;
+            auto rwork = [&] {
+                try { for (;;) { size_t i = next_root.fetch_add(1); if (i >= roots.size()) return; roots[i] = inc_delete_items(C, roots[i], per[i], to_delete).first; } }
+                catch (const std::exception& e) { std::lock_guard<std::mutex> lk(dmu); derr = e.what(); }
+            };
+            if (nt == 1) rwork();
+            else { std::vector<std::thread> th; for (unsigned t = 0; t < nt; ++t) th.emplace_back(rwork); for (auto& x : th) x.join(); }
+            if (!derr.empty()) throw HostError(ARROY_ERR_PANIC, derr);
+            for (auto& p : per) { for (auto& pr : p.puts) tmp.puts.push_back(std::move(pr)); tmp.deleted.insert(p.deleted.begin(), p.deleted.end()); }
             std::sort(roots.begin(), roots.end());
             for (uint32_t id : tmp.deleted) C.erase(id);
             for (auto& pr : tmp.puts) if (!tmp.deleted.count(pr.first)) C.put(pr.first, HNode(pr.second));
