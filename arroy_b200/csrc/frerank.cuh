@@ -72,10 +72,13 @@ struct FrParams {
 __global__ void __launch_bounds__(FR_THREADS)
 frerank_kernel(FrParams P) {
     extern __shared__ __align__(16) unsigned char fr_smem[];
-    float* sq = reinterpret_cast<float*>(fr_smem);                                 // ld floats: the query
-    float* est = sq + P.ld;                                                        // FR_CAP estimates
-    uint32_t* hist = reinterpret_cast<uint32_t*>(est + FR_CAP);                    // FR_BINS; later the survivor positions (FR_SURV)
-    unsigned long long* keys = reinterpret_cast<unsigned long long*>(hist + FR_BINS);   // FR_SURV keys
+    // shared memory: [query ld floats][region A: FR_CAP estimates; in phase 4 re-used for FR_SURV keys + FR_SURV distances]
+    //                [FR_BINS histogram words; from phase 3 on the survivor positions] — 43 KB at d = 768, five CTAs per SM
+    float* sq = reinterpret_cast<float*>(fr_smem);
+    float* est = sq + P.ld;
+    unsigned long long* keys = reinterpret_cast<unsigned long long*>(est);          // phase 4 (the estimates are dead by then)
+    float* sdist = est + 2 * FR_SURV;                                               // phase 4: exact distance per survivor
+    uint32_t* hist = reinterpret_cast<uint32_t*>(est + FR_CAP);
     __shared__ uint32_t sm_scan[9];
     __shared__ uint32_t sh_min, sh_max, sh_bin, sh_before;
     const uint32_t q = blockIdx.x;
@@ -247,17 +250,17 @@ frerank_kernel(FrParams P) {
         }
         if (v && g8 == 0) {
             const float dist = built_finish(metric, res, qh, (metric == COSINE) ? P.ih0[r] : 0.f);
-            est[p] = dist;                                                           // the exact distance replaces the estimate
-            keys[s] = ((unsigned long long)ordered_key(dist) << 32) | (unsigned long long)p;
+            sdist[s] = dist;
+            keys[s] = ((unsigned long long)ordered_key(dist) << 32) | (unsigned long long)s;   // s grows with the position: same tie-break
         }
     }
     __syncthreads();
     bitonic_sort_shared(keys, np2);
     if (tid == 0) P.out_len[q] = kk;
     for (uint32_t i = tid; i < kk; i += FR_THREADS) {
-        const uint32_t p = (uint32_t)(keys[i] & 0xffffffffull);
-        P.out_rows[(size_t)q * k + i] = rows[p];
-        P.out_dist[(size_t)q * k + i] = normalized_distance_dev(metric, est[p]);
+        const uint32_t s = (uint32_t)(keys[i] & 0xffffffffull);
+        P.out_rows[(size_t)q * k + i] = rows[surv[s]];
+        P.out_dist[(size_t)q * k + i] = normalized_distance_dev(metric, sdist[s]);
     }
 }
 
@@ -275,6 +278,7 @@ __global__ void fr_gmax_kernel(const float* __restrict__ cnorm, const float* __r
     if ((threadIdx.x & 31) == 0 && bits) atomicMax(gmax_bits, bits);
 }
 
-inline size_t frerank_smem(uint32_t ld) { return (size_t)ld * 4 + (size_t)FR_CAP * 4 + (size_t)FR_BINS * 4 + (size_t)FR_SURV * 8; }
+inline size_t frerank_smem(uint32_t ld) { return (size_t)ld * 4 + (size_t)FR_CAP * 4 + (size_t)FR_BINS * 4; }
+static_assert(FR_CAP * 4 >= FR_SURV * 8 + FR_SURV * 4, "phase-4 buffers must fit in the estimate region");
 
 }  // namespace ab
