@@ -64,6 +64,7 @@ SIGNATURES = [
     ("arroy_b200_timer_start", C.c_int32, [C.c_void_p]),
     ("arroy_b200_timer_stop", C.c_int32, [C.c_void_p, _f32p]),
     ("arroy_b200_device_ptrs", C.c_int32, [C.c_void_p, C.POINTER(C.c_void_p), _u32p]),
+    ("arroy_b200_epochs", C.c_int32, [C.c_void_p, _u64p]),
 ]
 
 _LIB = None
@@ -307,6 +308,32 @@ class Context:
         self._ck(self.lib.arroy_b200_rerank_shared(self.h, nq, _fp(queries), _fp(h0), _up(rows), rows.size, k, _up(out_rows), _fp(out_dist), _up(out_len)))
         return out_rows, out_dist, out_len
 
+    # -- device-resident forest + batched search ----------------------------------------------------
+    def load_forest(self, kind, left, right, normal_idx, normal_hdr0, desc_off, desc_len, normals, desc_rows, roots):
+        a8 = np.ascontiguousarray(kind, dtype=np.uint8)
+        u = lambda x: np.ascontiguousarray(x, dtype=np.uint32)
+        left, right, normal_idx, desc_off, desc_len, desc_rows, roots = map(u, (left, right, normal_idx, desc_off, desc_len, desc_rows, roots))
+        nh0 = np.ascontiguousarray(normal_hdr0, dtype=np.float32)
+        normals = np.ascontiguousarray(normals, dtype=np.float32)
+        self._ck(self.lib.arroy_b200_load_forest(self.h, a8.size, a8.ctypes.data_as(_u8p), _up(left), _up(right), _up(normal_idx), _fp(nh0), _up(desc_off), _up(desc_len),
+                                                 normals.shape[0] if normals.ndim == 2 else 0, _fp(normals), desc_rows.size, _up(desc_rows), roots.size, _up(roots)))
+
+    def search_batch(self, count, query_rows=None, queries=None, qhdr0=None, search_k=0):
+        if query_rows is not None:
+            query_rows = np.ascontiguousarray(query_rows, dtype=np.uint32)
+            nq = query_rows.size
+        else:
+            queries = np.ascontiguousarray(queries, dtype=np.float32)
+            nq = queries.shape[0]
+        h0 = None if qhdr0 is None else np.ascontiguousarray(qhdr0, dtype=np.float32)
+        out_rows = np.empty((nq, max(count, 1)), dtype=np.uint32)
+        out_dist = np.empty((nq, max(count, 1)), dtype=np.float32)
+        out_len = np.zeros(nq, dtype=np.uint32)
+        status = np.zeros(nq, dtype=np.int32)
+        self._ck(self.lib.arroy_b200_search_batch(self.h, nq, _up(query_rows), _fp(queries), _fp(h0), count, search_k, _up(out_rows), _fp(out_dist), _up(out_len),
+                                                  status.ctypes.data_as(C.POINTER(C.c_int32))))
+        return out_rows, out_dist, out_len, status
+
     # -- helpers ---------------------------------------------------------------------------------
     def synth_device(self, seed, dim, row0, rows, centre, device_ptr):
         s = (C.c_uint8 * 32)(*bytes(seed))
@@ -361,6 +388,11 @@ class Context:
         ms = C.c_float(0)
         self._ck(self.lib.arroy_b200_timer_stop(self.h, C.byref(ms)))
         return ms.value
+
+    def epochs(self):
+        out = (C.c_uint64 * 2)()
+        self._ck(self.lib.arroy_b200_epochs(self.h, out))
+        return int(out[0]), int(out[1])
 
     def device_ptrs(self):
         out = (C.c_void_p * 3)()

@@ -110,7 +110,7 @@ struct arroy_ctx {
     DevBuf items, h0, h1, norms, maxbits;
     std::vector<uint32_t> ids;
     // scratch
-    DevBuf s_rows, s_flags, s_margins, s_normal, s_unit, s_job, s_keys, s_dists, s_q, s_qh0, s_off, s_orows, s_odist, s_olen, s_misc;
+    DevBuf s_rows, s_flags, s_margins, s_normal, s_unit, s_job, s_keys, s_keys2, s_dists, s_q, s_qh0, s_off, s_orows, s_odist, s_olen, s_misc;
     PinBuf pin;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -122,6 +122,8 @@ struct arroy_ctx {
     DevForest forest{};
     bool forest_loaded = false;
     uint32_t forest_max_desc = 0;
+    uint64_t forest_n = 0;                       // the item count the loaded forest's rows were validated against
+    uint64_t stage_epoch = 0, forest_epoch = 0;  // bumped by every (re)staging / forest upload: owners compare them (arroy_b200_epochs)
     DevBuf w_heaps, w_cand, w_cand2, w_count, w_bitmap, w_status, w_beg, w_end, w_qrows, w_tmp;
     // results of the last build_trees_begin, waiting for build_trees_emit
     std::vector<std::vector<struct BuiltTreeView>> pending_waves;
@@ -187,7 +189,10 @@ void alloc_items(arroy_ctx* c, int metric, uint32_t dim, uint64_t n, const uint3
     if (dim == 0) throw ArgError("dim must be > 0");
     if (n > 0xffffffffull) throw ArgError("too many items");
     for (uint64_t i = 1; i < n; ++i) if (ids[i] <= ids[i - 1]) throw ArgError("ids must be strictly ascending");
-    c->staged = false; c->fr_valid = false;
+    // a restage invalidates everything derived from the previous items: the bf16 shadow and the device forest
+    // (its descendant rows were validated against the previous item count)
+    c->staged = false; c->fr_valid = false; c->forest_loaded = false;
+    c->stage_epoch += 1;
     c->metric = metric; c->dim = dim; c->ld = (dim + 31u) & ~31u; c->n = n;
     c->ids.assign(ids, ids + n);
     c->items.ensure(std::max<size_t>(16, (size_t)n * c->ld * 4));
@@ -866,9 +871,10 @@ void do_rerank_batch(arroy_ctx* c, uint32_t nq, const float* queries, const floa
     set_device(c);
     if (nq == 0) return;
     if (k == 0) { for (uint32_t q = 0; q < nq; ++q) out_len[q] = 0; return; }
-    if (k > TOPK_CAP / 2) throw ArgError("k larger than the top-k buffer (TOPK_CAP/2 = 2048)");
     if (nq > 65535) throw ArgError("at most 65535 queries per rerank_batch call");
+    const bool big_k = k > TOPK_CAP / 2;   // beyond the streaming top-k buffer: full segmented sort of the keys
     const uint64_t total = offsets[nq];
+    if (total && !rows) throw ArgError("null rows");
     for (uint32_t q = 0; q < nq; ++q) {
         if (offsets[q + 1] < offsets[q]) throw ArgError("row_offsets must be non-decreasing");
         if (offsets[q + 1] - offsets[q] > 0xffffffffull) throw ArgError("too many candidates for one query");
@@ -893,7 +899,7 @@ void do_rerank_batch(arroy_ctx* c, uint32_t nq, const float* queries, const floa
     uint64_t max_c = 0;
     for (uint32_t q = 0; q < nq; ++q) max_c = std::max<uint64_t>(max_c, offsets[q + 1] - offsets[q]);
     bool fused = false;
-    if (total >= 512ull * nq && max_c <= (uint64_t)FR_CAP && frerank_enabled(c, k)) {
+    if (!big_k && total >= 512ull * nq && max_c <= (uint64_t)FR_CAP && frerank_enabled(c, k)) {
         // rows of each query must be ascending for the (distance, id) tie-break; the callers of this path pass sorted lists
         frerank_launch(c, nq, c->s_q.as<float>(), nullptr, c->s_qh0.as<float>(), c->s_rows.as<uint32_t>(), c->s_off.as<uint64_t>(), c->s_off.as<uint64_t>() + 1, k);
         CK(cudaStreamSynchronize(c->stream));
@@ -909,6 +915,17 @@ void do_rerank_batch(arroy_ctx* c, uint32_t nq, const float* queries, const floa
                                                      c->s_rows.as<uint32_t>(), c->s_off.as<uint64_t>(), c->s_off.as<uint64_t>() + 1, c->s_dists.as<float>(), c->s_keys.as<unsigned long long>());
         CK(cudaGetLastError());
     }
+    if (big_k) {
+        c->s_keys2.ensure(std::max<uint64_t>(total, 1) * 8);
+        size_t tmp_bytes = 0;
+        CK(cub::DeviceSegmentedSort::SortKeys(nullptr, tmp_bytes, c->s_keys.as<unsigned long long>(), c->s_keys2.as<unsigned long long>(), (int64_t)total, (int64_t)nq,
+                                              c->s_off.as<uint64_t>(), c->s_off.as<uint64_t>() + 1, c->stream));
+        c->w_tmp.ensure(std::max<size_t>(tmp_bytes, 16));
+        CK(cub::DeviceSegmentedSort::SortKeys(c->w_tmp.p, tmp_bytes, c->s_keys.as<unsigned long long>(), c->s_keys2.as<unsigned long long>(), (int64_t)total, (int64_t)nq,
+                                              c->s_off.as<uint64_t>(), c->s_off.as<uint64_t>() + 1, c->stream));
+        take_sorted_kernel<<<nq, 256, 0, c->stream>>>(c->s_keys2.as<unsigned long long>(), c->s_dists.as<float>(), c->s_rows.as<uint32_t>(), c->s_off.as<uint64_t>(), c->s_off.as<uint64_t>() + 1, k, c->metric,
+                                                      c->s_orows.as<uint32_t>(), c->s_odist.as<float>(), c->s_olen.as<uint32_t>());
+    } else
     topk_kernel<<<nq, TOPK_THREADS, 0, c->stream>>>(c->s_keys.as<unsigned long long>(), c->s_dists.as<float>(), c->s_rows.as<uint32_t>(), c->s_off.as<uint64_t>(), c->s_off.as<uint64_t>() + 1, k, c->metric,
                                                     c->s_orows.as<uint32_t>(), c->s_odist.as<float>(), c->s_olen.as<uint32_t>());
     CK(cudaGetLastError());
@@ -995,7 +1012,7 @@ void arroy_b200_destroy(arroy_ctx* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     DevBuf* bufs[] = {&c->items, &c->h0, &c->h1, &c->norms, &c->maxbits, &c->s_rows, &c->s_flags, &c->s_margins, &c->s_normal, &c->s_unit, &c->s_job,
-                      &c->s_keys, &c->s_dists, &c->s_q, &c->s_qh0, &c->s_off, &c->s_orows, &c->s_odist, &c->s_olen, &c->s_misc};
+                      &c->s_keys, &c->s_keys2, &c->s_dists, &c->s_q, &c->s_qh0, &c->s_off, &c->s_orows, &c->s_odist, &c->s_olen, &c->s_misc};
     for (auto* b : bufs) b->release();
     { DevBuf* xb[] = {&c->fr_shadow, &c->fr_norm, &c->fr_gmax, &c->fr_status, &c->x_gather, &c->x_cnorm, &c->x_ca, &c->x_cb, &c->x_gmax, &c->x_qa, &c->x_qb, &c->x_twoe, &c->x_qnorm, &c->x_S, &c->x_sel, &c->x_beg, &c->x_end, &c->x_flag}; for (auto* b : xb) b->release(); }
     if (c->blas) cublasDestroy(c->blas);
@@ -1274,11 +1291,10 @@ int32_t arroy_b200_rerank_shared(arroy_ctx* c, uint32_t nq, const float* queries
         if (nq == 0) return;
         if (!queries || (n_rows && !rows) || !out_len) throw ArgError("null argument");
         if (k == 0 || n_rows == 0) { for (uint32_t q = 0; q < nq; ++q) out_len[q] = 0; return; }
-        if (k > TOPK_CAP / 2) throw ArgError("k larger than the top-k buffer (TOPK_CAP/2 = 2048)");
         if (n_rows > 0x7fffffffull) throw ArgError("too many candidates");
         for (uint64_t i = 0; i < n_rows; ++i) { if (rows[i] >= c->n) throw ArgError("row index out of range"); if (i && rows[i] <= rows[i - 1]) throw ArgError("rows must be ascending and unique"); }
-        if (c->metric == MANHATTAN || c->dim < 32) {
-            // sequential-sum metric / SSE + scalar paths: generic per-pair kernels over replicated row lists
+        if (c->metric == MANHATTAN || c->dim < 32 || k > TOPK_CAP / 2) {
+            // sequential-sum metric / SSE + scalar paths / k beyond the top-k buffer: generic per-pair kernels over replicated row lists
             if ((uint64_t)nq * n_rows > (1ull << 28)) throw ArgError("rerank_shared: this metric / dimension only supports nq * n_rows <= 2^28");
             std::vector<uint32_t> rep((size_t)nq * n_rows);
             std::vector<uint64_t> offs(nq + 1);
@@ -1428,7 +1444,7 @@ int32_t arroy_b200_load_forest(arroy_ctx* c, uint32_t n_nodes, const uint8_t* ki
         F.kind = c->f_kind.as<uint8_t>(); F.left = c->f_left.as<uint32_t>(); F.right = c->f_right.as<uint32_t>(); F.normal_idx = c->f_nidx.as<uint32_t>();
         F.nh0 = c->f_nh0.as<float>(); F.desc_off = c->f_doff.as<uint32_t>(); F.desc_len = c->f_dlen.as<uint32_t>(); F.normals = c->f_normals.as<float>();
         F.desc_rows = c->f_desc.as<uint32_t>(); F.roots = c->f_roots.as<uint32_t>(); F.n_roots = n_roots; F.n_nodes = n_nodes;
-        c->forest = F; c->forest_max_desc = max_desc; c->forest_loaded = true;
+        c->forest = F; c->forest_max_desc = max_desc; c->forest_n = c->n; c->forest_epoch += 1; c->forest_loaded = true;
     });
 }
 
@@ -1436,7 +1452,7 @@ int32_t arroy_b200_search_batch(arroy_ctx* c, uint32_t nq, const uint32_t* query
                                 uint64_t count, uint64_t search_k, uint32_t* out_rows, float* out_dist, uint32_t* out_len, int32_t* out_status) {
     return guarded(c, [&] {
         require_staged(c); set_device(c);
-        if (!c->forest_loaded) throw NotStaged("no forest loaded on this context (arroy_b200_load_forest)");
+        if (!c->forest_loaded || c->forest_n != c->n) throw NotStaged("no forest loaded on this context for the staged items (arroy_b200_load_forest)");
         if (nq == 0) return;
         if ((!query_rows && !queries) || !out_rows || !out_dist || !out_len) throw ArgError("null argument");
         if (count == 0) { for (uint32_t q = 0; q < nq; ++q) { out_len[q] = 0; if (out_status) out_status[q] = 0; } return; }
@@ -1675,6 +1691,10 @@ int32_t arroy_b200_timer_stop(arroy_ctx* c, float* out_ms) {
         CK(cudaEventSynchronize(c->tev1));
         CK(cudaEventElapsedTime(out_ms, c->tev0, c->tev1));
     });
+}
+
+int32_t arroy_b200_epochs(arroy_ctx* c, uint64_t out[2]) {
+    return guarded(c, [&] { if (!out) throw ArgError("null argument"); out[0] = c->staged ? c->stage_epoch : 0; out[1] = c->forest_loaded ? c->forest_epoch : 0; });
 }
 
 int32_t arroy_b200_device_ptrs(arroy_ctx* c, void* out[3], uint32_t* out_ld) {

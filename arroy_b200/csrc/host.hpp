@@ -130,7 +130,12 @@ inline void roaring_deserialize(const uint8_t* b, size_t len, std::vector<uint32
 struct arroy_env {
     std::map<arroy_host::Key8, std::string> kv;
     std::mutex mu;
-    uint64_t generation = 0;  // bumped on every write; lets a context know its staged items are stale
+    uint64_t generation = 0;                  // bumped on every write
+    std::map<uint16_t, uint64_t> index_gen;   // per index: bumped by every committed write to that index. A Reader remembers the
+                                              // value it was opened at (the table has no RoTxn snapshots: a reader that outlives a
+                                              // write to its index fails with NeedBuild instead of mixing two states)
+    void touch(uint16_t index) { generation++; index_gen[index]++; }
+    uint64_t gen_of(uint16_t index) const { auto it = index_gen.find(index); return it == index_gen.end() ? 0 : it->second; }
 };
 struct arroy_rng {
     ab::Rng r;
@@ -156,8 +161,11 @@ struct arroy_reader {
     std::vector<float> normals;     // d floats per split node with a normal
     std::vector<uint32_t> desc;     // concatenated descendant id lists
     std::vector<float> hdr0, hdr1;  // item headers (query by item)
-    bool staged = false;
-    bool forest_on_device = false;
+    // The device context is shared by every Reader / Writer of the Env, so "I staged my items" is not a fact that stays
+    // true: the epochs of the context's resident items / forest this reader produced (arroy_b200_epochs); anything else
+    // there belongs to somebody else and is replaced before use.
+    uint64_t stage_epoch = 0, forest_epoch = 0;
+    uint64_t gen_at_open = 0;
 };
 
 namespace arroy_host {
@@ -202,7 +210,7 @@ inline void put_item(arroy_writer* w, uint32_t item, const float* v) {  // Write
     new_header(w->metric, v, w->dims, h0, h1);
     w->env->kv[make_key(w->index, MODE_ITEM, item)] = encode_leaf(w->metric, v, w->dims, h0, h1);
     w->env->kv[make_key(w->index, MODE_UPDATED, item)] = std::string();
-    w->env->generation++;
+    w->env->touch(w->index);
 }
 
 struct ItemView { std::vector<uint32_t> ids; std::vector<const uint8_t*> ptrs; std::vector<size_t> sizes; };
@@ -362,7 +370,10 @@ struct NodeIdAlloc {  // ConcurrentNodeIds — src/parallel.rs:207-255
 
 struct IncCtx {
     arroy_env* env; arroy_ctx* ctx; uint16_t index; int metric; uint32_t d; size_t K;
-    std::map<uint32_t, HNode> tree;                 // the index' tree nodes, kept in sync with env->kv
+    std::map<uint32_t, HNode> tree;                 // the index' tree nodes as this build sees them
+    // the build's writes to the tree keys: node id -> (present, NodeCodec bytes). Applied to env->kv only when the whole build
+    // has succeeded — the reference works inside a RwTxn that is dropped on error (writer.rs:487-629)
+    std::map<uint32_t, std::pair<bool, std::string>> pending;
     const std::vector<uint32_t>* item_ids;          // ascending ids of the staged items (row = rank)
     // O(1) lookups for the routing loops (millions of them per update): node id -> decoded node (std::map nodes do
     // not move), item id -> row when the ids are small enough for a dense table
@@ -379,13 +390,20 @@ struct IncCtx {
     }
     const HNode& node(uint32_t id) const { if (id < by_id.size() && by_id[id]) return *by_id[id]; return tree.at(id); }
     void put(uint32_t id, HNode&& n) {
-        env->kv[make_key(index, MODE_TREE, id)] = encode_tree_node(n);
+        pending[id] = {true, encode_tree_node(n)};
         HNode& slot = tree[id];
         slot = std::move(n);
         if (id >= by_id.size()) by_id.resize((size_t)id + 1, nullptr);
         by_id[id] = &slot;
     }
-    void erase(uint32_t id) { env->kv.erase(make_key(index, MODE_TREE, id)); tree.erase(id); if (id < by_id.size()) by_id[id] = nullptr; }
+    void erase(uint32_t id) { pending[id] = {false, std::string()}; tree.erase(id); if (id < by_id.size()) by_id[id] = nullptr; }
+    void commit() {
+        for (auto& kv : pending) {
+            if (kv.second.first) env->kv[make_key(index, MODE_TREE, kv.first)] = std::move(kv.second.second);
+            else env->kv.erase(make_key(index, MODE_TREE, kv.first));
+        }
+        pending.clear();
+    }
     uint32_t row_of(uint32_t id) const {
         if (id < dense_row.size() && dense_row[id] != 0xffffffffu) return dense_row[id];
         return (uint32_t)(std::lower_bound(item_ids->begin(), item_ids->end(), id) - item_ids->begin());
@@ -600,6 +618,18 @@ inline void writer_build(arroy_writer* w, arroy_ctx* ctx, arroy_rng* rng, int64_
     for (uint64_t i = 0; i < n; ++i)
         if (items.sizes[i] != leaf_len) throw HostError(ARROY_ERR_PANIC, "items of different sizes in one index");
     auto t0 = clk::now();
+    // Nothing below touches env->kv until commit(): a cancelled or failed build leaves the table exactly as it was (the
+    // reference's RwTxn is dropped on error), Updated markers included, so need_build() stays true.
+    std::vector<float> dot_extra, dot_norm;   // DotProduct::preprocess results, written back at commit (dot_product.rs:154-160)
+    std::vector<uint32_t> updated;
+    auto commit_common = [&]() {
+        for (uint64_t i = 0; i < dot_extra.size(); ++i) {  // cursor.put_current
+            std::string& v = env->kv[make_key(index, MODE_ITEM, items.ids[i])];
+            memcpy(&v[1], &dot_extra[i], 4);
+            memcpy(&v[5], &dot_norm[i], 4);
+        }
+        erase_mode(env, index, MODE_UPDATED);
+    };
     const uint64_t K_early = split_after ? split_after : d;
     const bool needs_device = n > K_early || (w->metric == ARROY_B200_DOT_PRODUCT && n > 0);
     if (needs_device) {
@@ -610,29 +640,22 @@ inline void writer_build(arroy_writer* w, arroy_ctx* ctx, arroy_rng* rng, int64_
     }
     if (w->metric == ARROY_B200_DOT_PRODUCT && n > 0) {
         t0 = clk::now();
-        std::vector<float> extra(n), norm(n);
-        dev_ck(ctx, arroy_b200_dot_preprocess(ctx, extra.data(), norm.data()));
-        for (uint64_t i = 0; i < n; ++i) {  // cursor.put_current — dot_product.rs:154-160
-            std::string& v = env->kv[make_key(index, MODE_ITEM, items.ids[i])];
-            memcpy(&v[1], &extra[i], 4);
-            memcpy(&v[5], &norm[i], 4);
-        }
+        dot_extra.resize(n); dot_norm.resize(n);
+        dev_ck(ctx, arroy_b200_dot_preprocess(ctx, dot_extra.data(), dot_norm.data()));
         w->timings[1] = ms_since(t0);
     }
     step("RetrievingTheItemsIds");
     cancelled();
     step("RetrieveTheUpdatedItems");
-    std::vector<uint32_t> updated;
     {
-        auto b = env->kv.lower_bound(make_key(index, MODE_UPDATED, 0));
-        auto e = b;
+        auto e = env->kv.lower_bound(make_key(index, MODE_UPDATED, 0));
         while (e != env->kv.end() && e->first[0] == (uint8_t)(index >> 8) && e->first[1] == (uint8_t)index && e->first[2] == MODE_UPDATED) { updated.push_back(key_item(e->first)); ++e; }
-        env->kv.erase(b, e);
     }
-    env->generation++;
     const uint64_t K = split_after ? split_after : d;
     if (n <= K) {  // clear_db_and_create_a_single_leaf — writer.rs:916-962
         step("WritingTheDescendantsAndMetadata");
+        cancelled();
+        commit_common();
         erase_mode(env, index, MODE_TREE);
         std::vector<uint32_t> roots;
         if (n > 0) {
@@ -642,9 +665,9 @@ inline void writer_build(arroy_writer* w, arroy_ctx* ctx, arroy_rng* rng, int64_
             env->kv[make_key(index, MODE_TREE, 0)] = std::string(reinterpret_cast<char*>(buf.data()), buf.size());
             roots.push_back(0);
         }
-        cancelled();
         env->kv[make_key(index, MODE_METADATA, 0)] = encode_metadata(w->metric, d, items.ids, roots);
         write_version(env, index);
+        env->touch(index);
         w->timings[4] = ms_since(t_all);
         return;
     }
@@ -654,7 +677,7 @@ inline void writer_build(arroy_writer* w, arroy_ctx* ctx, arroy_rng* rng, int64_
     const uint64_t target = target_n_trees(n_trees_opt, d, n, roots.size());
     if (!roots.empty()) {
         // ---- an index that already has trees: update it in place --------------------------------------
-        IncCtx C{env, ctx, index, w->metric, d, (size_t)K, {}, &items.ids};
+        IncCtx C{env, ctx, index, w->metric, d, (size_t)K, {}, {}, &items.ids};
         {
             // decode every tree node of the index (threads: the leaves' bitmaps are most of the work)
             std::vector<std::pair<uint32_t, const std::string*>> raw;
@@ -772,14 +795,17 @@ inline void writer_build(arroy_writer* w, arroy_ctx* ctx, arroy_rng* rng, int64_
             dev_ck(ctx, arroy_b200_build_trees_emit_mapped(ctx, task_ids.data(), node_ids.data(), tree_sink, &sa));
             std::vector<std::pair<uint32_t, std::string>> all;
             for (int sh = 0; sh < SinkArg::SHARDS; ++sh) { for (auto& e : sa.nodes[sh]) all.emplace_back(std::move(e)); sa.nodes[sh].clear(); }
-            for (auto& e : all) env->kv[make_key(index, MODE_TREE, e.first)] = std::move(e.second);
+            for (auto& e : all) C.pending[e.first] = {true, std::move(e.second)};
         }
         w->timings[2] = ms_since(t0);
         w->timings[6] = (double)sa.bytes.load();
         step("WriteTheMetadata");
+        cancelled();
+        commit_common();
+        C.commit();
         env->kv[make_key(index, MODE_METADATA, 0)] = encode_metadata(w->metric, d, items.ids, roots);
         write_version(env, index);
-        env->generation++;
+        env->touch(index);
         w->timings[4] = ms_since(t_all);
         return;
     }
@@ -802,6 +828,7 @@ inline void writer_build(arroy_writer* w, arroy_ctx* ctx, arroy_rng* rng, int64_
     uint64_t n_nodes = 0;
     dev_ck(ctx, arroy_b200_build_trees(ctx, (uint32_t)target, reinterpret_cast<const uint8_t(*)[32]>(seeds.data()), roots.data(), (uint32_t)target,
                                        (uint32_t)split_after, cancel, cancel_arg, tree_sink, &sa, &n_nodes));
+    commit_common();
     {   // move the parked nodes into the ordered table, ascending by id
         std::vector<std::pair<uint32_t, std::string>> all;
         for (int sh = 0; sh < SinkArg::SHARDS; ++sh) { for (auto& e : sa.nodes[sh]) all.emplace_back(std::move(e)); sa.nodes[sh].clear(); }
@@ -815,7 +842,7 @@ inline void writer_build(arroy_writer* w, arroy_ctx* ctx, arroy_rng* rng, int64_
     t0 = clk::now();
     env->kv[make_key(index, MODE_METADATA, 0)] = encode_metadata(w->metric, d, items.ids, roots);
     write_version(env, index);
-    env->generation++;
+    env->touch(index);
     w->timings[3] = ms_since(t0);
     w->timings[4] = ms_since(t_all);
 }
@@ -836,6 +863,7 @@ inline void reader_open(arroy_env* env, uint16_t index, int metric, arroy_ctx* c
     auto r = std::unique_ptr<arroy_reader>(new arroy_reader());
     r->env = env; r->ctx = ctx; r->index = index; r->metric = metric; r->dims = md.dims;
     r->roots = md.roots; r->items = md.items;
+    r->gen_at_open = env->gen_of(index);
     const uint32_t d = md.dims;
     const int hf = header_floats(metric);
     // decode the tree nodes once (the reference decodes per access from the LMDB page)
@@ -876,14 +904,27 @@ inline void reader_open(arroy_env* env, uint16_t index, int metric, arroy_ctx* c
     *out = r.release();
 }
 
+// A reader is a snapshot of its index at open time. The in-memory table has no RoTxn, so a reader that outlives a committed
+// write to ITS index (rebuild, add / delete, clear) is refused instead of mixing old tree nodes with new items.
+inline void check_fresh_locked(const arroy_reader* r) {
+    if (r->env->gen_of(r->index) != r->gen_at_open)
+        throw HostError(ARROY_ERR_NEED_BUILD, "index " + std::to_string(r->index) + " was modified after this reader was opened; open a new Reader");
+}
+inline void check_fresh(const arroy_reader* r) { std::lock_guard<std::mutex> lk(r->env->mu); check_fresh_locked(r); }
+
 inline void ensure_staged(arroy_reader* r) {
-    if (r->staged) return;
     if (!r->ctx) throw HostError(ARROY_B200_ERR_CUDA, "no CUDA device context: arroy_b200 has no CPU fallback");
+    uint64_t ep[2] = {0, 0};
+    dev_ck(r->ctx, arroy_b200_epochs(r->ctx, ep));
+    if (r->stage_epoch != 0 && ep[0] == r->stage_epoch) return;   // the resident items are still the ones this reader staged
     std::lock_guard<std::mutex> lk(r->env->mu);
+    check_fresh_locked(r);
     ItemView iv = collect_items(r->env, r->index);
     if (iv.ids != r->items) throw HostError(ARROY_ERR_NEED_BUILD, "The trees have not been built after an update on index " + std::to_string(r->index));
     dev_ck(r->ctx, arroy_b200_stage_items(r->ctx, r->metric, r->dims, iv.ids.size(), iv.ids.data(), iv.ptrs.data()));
-    r->staged = true;
+    dev_ck(r->ctx, arroy_b200_epochs(r->ctx, ep));
+    r->stage_epoch = ep[0];
+    r->forest_epoch = 0;   // staging drops whatever forest was resident
 }
 
 inline int64_t row_of(const arroy_reader* r, uint32_t item);
@@ -891,8 +932,12 @@ inline int64_t row_of(const arroy_reader* r, uint32_t item);
 // Upload the decoded forest for the batched device search (arroy_b200_load_forest); descendants
 // are converted from item ids to rows once.
 inline void ensure_forest(arroy_reader* r) {
-    if (r->forest_on_device) return;
     ensure_staged(r);
+    {
+        uint64_t ep[2] = {0, 0};
+        dev_ck(r->ctx, arroy_b200_epochs(r->ctx, ep));
+        if (r->forest_epoch != 0 && ep[1] == r->forest_epoch) return;   // still this reader's forest, over this reader's items
+    }
     const size_t nn = r->nodes.size();
     std::vector<uint8_t> kind(nn);
     std::vector<uint32_t> left(nn), right(nn), nidx(nn), doff(nn), dlen(nn);
@@ -915,7 +960,9 @@ inline void ensure_forest(arroy_reader* r) {
     dev_ck(r->ctx, arroy_b200_load_forest(r->ctx, (uint32_t)nn, kind.data(), left.data(), right.data(), nidx.data(), nh0.data(), doff.data(), dlen.data(),
                                           (uint32_t)(r->normals.size() / std::max<uint32_t>(r->dims, 1)), r->normals.data(), rows.size(), rows.data(),
                                           (uint32_t)r->roots.size(), r->roots.data()));
-    r->forest_on_device = true;
+    uint64_t ep[2] = {0, 0};
+    dev_ck(r->ctx, arroy_b200_epochs(r->ctx, ep));
+    r->forest_epoch = ep[1];
 }
 
 inline int64_t row_of(const arroy_reader* r, uint32_t item) {
@@ -1063,7 +1110,7 @@ int32_t arroy_writer_del_item(arroy_writer* w, uint32_t item, int32_t* out_exist
     return hguard([&] {
         std::lock_guard<std::mutex> lk(w->env->mu);
         bool ex = w->env->kv.erase(make_key(w->index, MODE_ITEM, item)) > 0;
-        if (ex) { w->env->kv[make_key(w->index, MODE_UPDATED, item)] = std::string(); w->env->generation++; }
+        if (ex) { w->env->kv[make_key(w->index, MODE_UPDATED, item)] = std::string(); w->env->touch(w->index); }
         if (out_existed) *out_existed = ex ? 1 : 0;
     });
 }
@@ -1071,7 +1118,7 @@ int32_t arroy_writer_clear(arroy_writer* w) {  // writer.rs:444-457
     return hguard([&] {
         std::lock_guard<std::mutex> lk(w->env->mu);
         for (uint8_t m = 0; m < 4; ++m) erase_mode(w->env, w->index, m);
-        w->env->generation++;
+        w->env->touch(w->index);
     });
 }
 int32_t arroy_writer_need_build(arroy_writer* w, int32_t* out) {  // writer.rs:343-357
@@ -1117,6 +1164,7 @@ uint64_t arroy_reader_item_ids(arroy_reader* r, uint32_t* out, uint64_t cap) {
 int32_t arroy_reader_item_vector(arroy_reader* r, uint32_t item, float* out, int32_t* out_found) {
     return hguard([&] {
         std::lock_guard<std::mutex> lk(r->env->mu);
+        check_fresh_locked(r);
         auto it = r->env->kv.find(make_key(r->index, MODE_ITEM, item));
         *out_found = it != r->env->kv.end();
         if (*out_found) memcpy(out, it->second.data() + 1 + 4 * header_floats(r->metric), 4ull * r->dims);
@@ -1143,7 +1191,7 @@ int32_t arroy_reader_nns_by_item(arroy_reader* r, uint32_t item, uint64_t count,
         if (row < 0) return;  // Ok(None) — reader.rs:46-51
         std::vector<float> q(r->dims);
         int32_t found = 0;
-        { std::lock_guard<std::mutex> lk(r->env->mu); auto it = r->env->kv.find(make_key(r->index, MODE_ITEM, item)); found = it != r->env->kv.end(); if (found) memcpy(q.data(), it->second.data() + 1 + 4 * header_floats(r->metric), 4ull * r->dims); }
+        { std::lock_guard<std::mutex> lk(r->env->mu); check_fresh_locked(r); auto it = r->env->kv.find(make_key(r->index, MODE_ITEM, item)); found = it != r->env->kv.end(); if (found) memcpy(q.data(), it->second.data() + 1 + 4 * header_floats(r->metric), 4ull * r->dims); }
         if (!found) { *out_found = 0; return; }
         nns_by_leaf(r, q.data(), r->hdr0[row], r->hdr1[row], count, search_k, oversampling, cand, n_cand, out_ids, out_dist, out_len);
     });
@@ -1154,6 +1202,7 @@ int32_t arroy_reader_nns_by_vector(arroy_reader* r, const float* vector, uint32_
         *out_len = 0;
         if (len != r->dims) throw HostError(ARROY_ERR_INVALID_VEC_DIMENSION, "Invalid vector dimensions. Got " + std::to_string(len) + " but expected " + std::to_string(r->dims));
         float h0, h1;
+        check_fresh(r);
         new_header(r->metric, vector, r->dims, h0, h1);  // reader.rs:72-73
         nns_by_leaf(r, vector, h0, h1, count, search_k, oversampling, cand, n_cand, out_ids, out_dist, out_len);
     });
@@ -1163,6 +1212,7 @@ int32_t arroy_reader_nns_batch_by_item(arroy_reader* r, uint32_t nq, const uint3
     return hguard([&] {
         const uint32_t d = r->dims;
         const int hf = header_floats(r->metric);
+        check_fresh(r);
         std::vector<float> q, qh0, qh1;
         std::vector<std::vector<uint32_t>> rows;
         for (uint32_t i = 0; i < nq; ++i)

@@ -452,6 +452,23 @@ topk_kernel(const unsigned long long* __restrict__ keys, const float* __restrict
     }
 }
 
+// k beyond the streaming buffer (k > TOPK_CAP / 2; the reference has no limit, reader.rs:396-399): the keys of every
+// query were sorted completely (CUB segmented sort); this kernel takes the first min(k, n) of each segment.
+__global__ void __launch_bounds__(256)
+take_sorted_kernel(const unsigned long long* __restrict__ sorted_keys, const float* __restrict__ dists, const uint32_t* __restrict__ rows,
+                   const uint64_t* __restrict__ seg_beg, const uint64_t* __restrict__ seg_end, uint32_t k, int metric,
+                   uint32_t* __restrict__ out_rows, float* __restrict__ out_dist, uint32_t* __restrict__ out_len) {
+    const uint32_t q = blockIdx.x;
+    const uint64_t beg = seg_beg[q], n = seg_end[q] - beg;
+    const uint32_t kk = (uint32_t)(n < (uint64_t)k ? n : (uint64_t)k);
+    if (threadIdx.x == 0) out_len[q] = kk;
+    for (uint32_t i = threadIdx.x; i < kk; i += blockDim.x) {
+        const uint32_t p = (uint32_t)(sorted_keys[beg + i] & 0xffffffffull);
+        out_rows[(size_t)q * k + i] = rows[beg + p];
+        out_dist[(size_t)q * k + i] = normalized_distance_dev(metric, dists[beg + p]);
+    }
+}
+
 // ---- synthetic matrix -------------------------------------------------------------------------
 // out[(i, j)] = gen::<f32>() number (row0+i)*d + j of StdRng::from_seed(key) minus centre; one
 // thread per ChaCha block (16 words).

@@ -294,6 +294,14 @@ int32_t arroy_b200_rerank_breakdown(arroy_ctx* ctx, double out[8]);
 int32_t arroy_b200_timer_start(arroy_ctx* ctx);
 int32_t arroy_b200_timer_stop(arroy_ctx* ctx, float* out_ms);
 
+/* Ownership tokens of the device-resident state, for callers that share one context between several
+ * readers / writers (the host keeps one context per heed::Env): out[0] = epoch of the staged items,
+ * out[1] = epoch of the loaded forest; each is bumped by every arroy_b200_stage_items* /
+ * arroy_b200_load_forest call and reads 0 while nothing valid is resident. A caller remembers the
+ * epochs it produced and re-stages / re-loads when they differ, instead of trusting state another
+ * owner has replaced. */
+int32_t arroy_b200_epochs(arroy_ctx* ctx, uint64_t out[2]);
+
 /* Raw device pointers of the staged items (for the NCCL broadcast of the multi-GPU path):
  * out[0] = float[n][ld] matrix, out[1] = hdr0[n], out[2] = hdr1[n] (may be 0); *out_ld = ld. */
 int32_t arroy_b200_device_ptrs(arroy_ctx* ctx, void* out[3], uint32_t* out_ld);

@@ -90,3 +90,45 @@ def test_search_batch_by_vector_and_status(ctx):
         want = odb.nns_by_item(i, 2000)
         assert out_ids[i, :out_len[i]].tolist() == [x[0] for x in want]
     env._ctx = None
+
+
+def test_restage_invalidates_the_device_forest(ctx):
+    # a forest validated against n items must not be walked after a restage with fewer items
+    # (walk_kernel indexes the per-query bitmap and the item matrix by the forest's rows)
+    n, d = 3000, 32
+    data = oracle.synth_rows(SEED, d, 0, n, 0.5)
+    ctx.stage_items_flat("euclidean", np.arange(n, dtype=np.uint32), data)
+    # a one-split forest over all rows: node 0 = split (no normal), nodes 1 / 2 = the two halves
+    rows = np.arange(n, dtype=np.uint32)
+    ctx.load_forest(kind=[2, 1, 1], left=[1, 0, 0], right=[2, 0, 0], normal_idx=[0xffffffff, 0, 0], normal_hdr0=[0, 0, 0],
+                    desc_off=[0, 0, n // 2], desc_len=[0, n // 2, n - n // 2], normals=np.zeros((0, d), np.float32), desc_rows=rows, roots=[0])
+    assert ctx.epochs()[1] != 0
+    out_rows, out_dist, out_len, status = ctx.search_batch(5, query_rows=[0, 1, 2], search_k=n)
+    assert status.tolist() == [0, 0, 0] and out_len.tolist() == [5, 5, 5] and out_rows[:, 0].tolist() == [0, 1, 2]
+    e0 = ctx.epochs()
+    ctx.stage_items_flat("euclidean", np.arange(100, dtype=np.uint32), data[:100])
+    e1 = ctx.epochs()
+    assert e1[0] != e0[0] and e1[1] == 0
+    with pytest.raises(ab.ArroyB200Error) as ei:
+        ctx.search_batch(5, query_rows=[0, 1, 2], search_k=n)
+    assert ei.value.code == 5   # ARROY_B200_ERR_NOT_STAGED
+
+
+@pytest.mark.parametrize("metric", ["euclidean", "cosine", "manhattan"])
+def test_count_beyond_the_topk_buffer(ctx, metric):
+    # the reference has no limit on count (reader.rs:396-399); k > 2048 takes the full segmented sort
+    n, d, k = 6000, 40, 3000
+    data = oracle.synth_rows(SEED, d, 0, n, 0.5)
+    m = oracle.METRICS[metric]
+    ctx.stage_items_flat(metric, np.arange(n, dtype=np.uint32), data)
+    h0, _ = ctx.item_headers()
+    rows = np.arange(n, dtype=np.uint32)
+    for qi in (0, 17):
+        qh = oracle.new_header(m, data[qi])
+        wr, wd = oracle.rerank(m, data[qi], qh, data, h0, None, rows, k)
+        gr, gd = ctx.rerank(data[qi], qh, rows, k)
+        assert gr.tolist() == wr.tolist() and gd.tobytes() == wd.tobytes()
+    out_rows, out_dist, out_len = ctx.rerank_shared(data[:3], h0[:3], rows, k)
+    for i in range(3):
+        wr, wd = oracle.rerank(m, data[i], oracle.new_header(m, data[i]), data, h0, None, rows, k)
+        assert out_len[i] == k and out_rows[i].tolist() == wr.tolist() and out_dist[i].tobytes() == wd.tobytes()

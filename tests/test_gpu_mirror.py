@@ -152,3 +152,79 @@ def test_forest_and_queries_match_the_oracle_end_to_end(env_factory, metric, n, 
         os.environ.pop("ARROY_B200_HOST_WALK")
     d_ids, d_dist, d_len, _ = r.nns_batch_by_item(qitems, 10)
     assert h_len.tolist() == d_len.tolist() and h_ids.tolist() == d_ids.tolist() and h_dist.tobytes() == d_dist.tobytes()
+
+
+def _oracle_db(metric, d, ids, data, trees):
+    odb = oracle.Db(metric, d)
+    odb.set_items(ids, data)
+    odb.build(oracle.StdRng(SEED), n_trees=trees, threads=4)
+    return odb
+
+
+def test_two_indexes_and_a_rebuild_share_one_device_context(env_factory):
+    # the device context is shared by every Reader / Writer of an Env. A reader must never walk or
+    # re-rank another owner's resident items / forest.
+    env = env_factory()
+    d0, n0, d1, n1 = 48, 3000, 64, 1200
+    a = oracle.synth_rows(SEED, d0, 0, n0, 0.5)
+    b = oracle.synth_rows(bytes([7] * 32), d1, 0, n1, 0.5)
+    ids0, ids1 = np.arange(n0, dtype=np.uint32), np.arange(10, 10 + n1, dtype=np.uint32)
+    w0, w1 = ab.Writer(env, 0, d0, "euclidean"), ab.Writer(env, 1, d1, "cosine")
+    w0.add_items(ids0, a)
+    w1.add_items(ids1, b)
+    w0.builder(rng42()).n_trees(4).build()
+    w1.builder(rng42()).n_trees(3).build()
+    o0, o1 = _oracle_db("euclidean", d0, ids0, a, 4), _oracle_db("cosine", d1, ids1, b, 3)
+    r0, r1 = ab.Reader.open(env, 0, "euclidean"), ab.Reader.open(env, 1, "cosine")
+    q0, q1 = [0, 5, 77, 2999], [10, 11, 500, 1209]
+
+    def check(r, o, qs):
+        out_ids, out_dist, out_len, _ = r.nns_batch_by_item(qs, 10)
+        for i, it in enumerate(qs):
+            want = o.nns_by_item(it, 10)
+            assert out_ids[i, :out_len[i]].tolist() == [x[0] for x in want]
+            assert out_dist[i, :out_len[i]].tobytes() == np.array([x[1] for x in want], dtype=np.float32).tobytes()
+            assert r.nns(10).by_item(it) == want
+
+    for _ in range(2):          # alternate: every switch finds the other index resident on the device
+        check(r0, o0, q0)
+        check(r1, o1, q1)
+    # a third index is built on the same context while the readers stay open: its staging replaces theirs
+    w2 = ab.Writer(env, 2, d0, "euclidean")
+    w2.add_items(ids0[:500], a[:500])
+    w2.builder(rng42()).n_trees(2).build()
+    check(r1, o1, q1)
+    check(r0, o0, q0)
+    # a rebuild of index 0 makes its open reader stale (NeedBuild) instead of silently wrong
+    w0.add_item(n0, a[0] * 0.5)
+    w0.builder(rng42()).n_trees(4).build()
+    with pytest.raises(ab.ArroyError) as ei:
+        r0.nns_batch_by_item(q0, 10)
+    assert ei.value.kind == "NeedBuild"
+    check(r1, o1, q1)
+
+
+def test_cancel_in_the_middle_of_a_device_build_rolls_back(env_factory):
+    # BuildCancelled must leave the table as it was (the reference's RwTxn is dropped)
+    env = env_factory()
+    d, n = 32, 4000
+    data = oracle.synth_rows(SEED, d, 0, n, 0.5)
+    w = ab.Writer(env, 0, d, "dot-product")
+    w.add_items(np.arange(n - 500, dtype=np.uint32), data[:n - 500])
+    w.builder(rng42()).n_trees(3).build()
+    w.add_items(np.arange(n - 500, n, dtype=np.uint32), data[n - 500:])
+    w.del_item(3)
+    before = env.items()
+    for after in (1, 2, 4):      # cancel at different polls: before staging, between the host phases, inside the device loop
+        calls = {"n": 0}
+
+        def cancel():
+            calls["n"] += 1
+            return calls["n"] > after
+
+        with pytest.raises(ab.ArroyError) as ei:
+            w.builder(rng42()).n_trees(3).cancel(cancel).build()
+        assert ei.value.kind == "BuildCancelled"
+        assert env.items() == before and w.need_build()
+    w.builder(rng42()).n_trees(3).build()
+    assert not w.need_build() and env.items() != before

@@ -132,3 +132,52 @@ def test_progress_reports_main_steps():
     seen = []
     w.builder(rng42()).progress(seen.append).build()
     assert seen[0] == "PreProcessingTheItems" and "WritingTheDescendantsAndMetadata" in seen
+
+
+def test_failed_or_cancelled_build_leaves_the_table_untouched():
+    # the reference builds inside a RwTxn that is dropped on error (src/writer.rs:487-629): nothing of a failed build may be
+    # visible afterwards — in particular the Updated markers, or need_build() would report a built index
+    env = ab.Env()
+    w = ab.Writer(env, 0, 2, "euclidean")
+    w.add_item(0, [0.0, 0.0])
+    w.add_item(1, [1.0, 0.0])
+    w.builder(rng42()).build()                      # n <= split_after: a single Descendants node, no device needed
+    w.add_item(2, [2.0, 0.0])                       # now n > dimensions: the build needs the device, which this box lacks
+    w.del_item(0)
+    before = env.items()
+    assert w.need_build()
+    with pytest.raises(ab.ArroyError):
+        w.builder(rng42()).cancel(lambda: True).build()
+    assert env.items() == before and w.need_build()
+    try:
+        w.builder(rng42()).build()                  # fails without a CUDA device (no CPU fallback) ...
+        built = True
+    except (ab.ArroyError, Exception):
+        built = False
+    if not built:
+        assert env.items() == before and w.need_build()   # ... and must not leave a half-written index behind
+        with pytest.raises(ab.ArroyError) as ei:
+            ab.Reader.open(env, 0, "euclidean")
+        assert ei.value.kind == "NeedBuild"
+
+
+def test_reader_that_outlives_a_write_to_its_index_is_refused():
+    # the in-memory table has no RoTxn snapshots: a reader must not silently mix its decoded trees with newer items
+    env = ab.Env()
+    w = ab.Writer(env, 0, 2, "euclidean")
+    w.add_item(0, [0.0, 0.0])
+    w.builder(rng42()).build()
+    r = ab.Reader.open(env, 0, "euclidean")
+    other = ab.Writer(env, 1, 2, "euclidean")       # a write to ANOTHER index does not disturb the reader
+    other.add_item(5, [1.0, 1.0])
+    other.builder(rng42()).build()
+    assert list(r.item_vector(0)) == [0.0, 0.0]
+    w.add_item(1, [1.0, 0.0])
+    w.builder(rng42()).build()
+    with pytest.raises(ab.ArroyError) as ei:
+        r.item_vector(0)
+    assert ei.value.kind == "NeedBuild"
+    with pytest.raises(ab.ArroyError) as ei:
+        r.nns(1).by_vector([0.0, 0.0])
+    assert ei.value.kind == "NeedBuild"
+    assert ab.Reader.open(env, 0, "euclidean").n_items() == 2
