@@ -1022,7 +1022,27 @@ inline void tree_walk(const arroy_reader* r, const float* qv, float qh0, uint64_
 }
 
 inline void nns_by_leaf(arroy_reader* r, const float* qv, float qh0, float qh1, uint64_t count, uint64_t search_k, uint64_t oversampling,
-                        const uint32_t* cand, int64_t n_cand, uint32_t* out_ids, float* out_dist, uint64_t* out_len) {
+                        const uint32_t* cand, int64_t n_cand, uint32_t* out_ids, float* out_dist, uint64_t* out_len, int64_t qrow = -1) {
+    *out_len = 0;
+    // One query, whole search on the device (the forest stays resident after the first call): the priority-queue walk, the
+    // candidate sort and the re-rank are one arroy_b200_search_batch call with nq = 1 — no host walk over 50 trees, no candidate
+    // list crossing PCIe. Queries with a `candidates` filter or count > 2048 keep the host walk below.
+    if (n_cand < 0 && count > 0 && count <= 2048 && !r->items.empty() && r->ctx && getenv("ARROY_B200_HOST_WALK") == nullptr) {
+        ensure_forest(r);
+        unsigned __int128 sk = search_k ? (unsigned __int128)search_k : (unsigned __int128)count * r->roots.size();   // reader.rs:330-335
+        sk *= oversampling ? oversampling : 1;
+        const uint64_t eff = sk > (unsigned __int128)UINT64_MAX ? UINT64_MAX : std::max<uint64_t>((uint64_t)sk, 1);
+        std::vector<uint32_t> orow(count);
+        uint32_t olen = 0, qr = (uint32_t)qrow;
+        int32_t status = 0;
+        dev_ck(r->ctx, arroy_b200_search_batch(r->ctx, 1, qrow >= 0 ? &qr : nullptr, qrow >= 0 ? nullptr : qv, qrow >= 0 ? nullptr : &qh0, count, eff,
+                                               orow.data(), out_dist, &olen, &status));
+        if (status == 0) {
+            for (uint32_t i = 0; i < olen; ++i) out_ids[i] = r->items[orow[i]];
+            *out_len = olen;
+            return;
+        }
+    }
     std::vector<uint32_t> cv, rows;
     if (n_cand >= 0) { cv.assign(cand, cand + n_cand); std::sort(cv.begin(), cv.end()); }
     tree_walk(r, qv, qh0, count, search_k, oversampling, n_cand >= 0 ? &cv : nullptr, rows);
@@ -1193,7 +1213,7 @@ int32_t arroy_reader_nns_by_item(arroy_reader* r, uint32_t item, uint64_t count,
         int32_t found = 0;
         { std::lock_guard<std::mutex> lk(r->env->mu); check_fresh_locked(r); auto it = r->env->kv.find(make_key(r->index, MODE_ITEM, item)); found = it != r->env->kv.end(); if (found) memcpy(q.data(), it->second.data() + 1 + 4 * header_floats(r->metric), 4ull * r->dims); }
         if (!found) { *out_found = 0; return; }
-        nns_by_leaf(r, q.data(), r->hdr0[row], r->hdr1[row], count, search_k, oversampling, cand, n_cand, out_ids, out_dist, out_len);
+        nns_by_leaf(r, q.data(), r->hdr0[row], r->hdr1[row], count, search_k, oversampling, cand, n_cand, out_ids, out_dist, out_len, row);
     });
 }
 int32_t arroy_reader_nns_by_vector(arroy_reader* r, const float* vector, uint32_t len, uint64_t count, uint64_t search_k, uint64_t oversampling,
