@@ -271,7 +271,7 @@ class Context:
     def build_stats(self):
         st = (C.c_double * 8)()
         self._ck(self.lib.arroy_b200_build_stats(self.h, st))
-        keys = ["scanned_rows", "steps", "create_split_calls", "random_splits", "build_ms", "scan_ms", "nodes", "reserved"]
+        keys = ["scanned_rows", "steps", "create_split_calls", "random_splits", "build_ms", "scan_ms", "nodes", "misspeculated_splits"]
         return dict(zip(keys, list(st)))
 
     # -- re-rank -------------------------------------------------------------------------------

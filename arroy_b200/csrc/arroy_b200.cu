@@ -343,6 +343,9 @@ void build_wave(arroy_ctx* c, size_t wave_no, uint32_t t0, uint32_t tw, const ui
     size_t ws_bytes = (size_t)WS_VECS * ld * 4;
     int use_smem = ws_bytes <= 200 * 1024 ? 1 : 0;
     if (!use_smem) W.scratch.ensure(ws_bytes * tw);
+    // speculative two_means (build.cuh): needs the 24-vector workspace in shared memory; ARROY_B200_SPEC=0 keeps the sequential loop
+    const int spec = (use_smem && (size_t)WS_VECS_SPEC * ld * 4 <= 200 * 1024 && !(getenv("ARROY_B200_SPEC") && atoi(getenv("ARROY_B200_SPEC")) == 0)) ? 1 : 0;
+    if (spec) ws_bytes = (size_t)WS_VECS_SPEC * ld * 4;
 
     BuildParams P{};
     P.items = c->items.as<float>(); P.ih0 = c->h0.as<float>(); P.ih1 = c->h1.as<float>();
@@ -351,7 +354,7 @@ void build_wave(arroy_ctx* c, size_t wave_no, uint32_t t0, uint32_t tw, const ui
     P.perm[0] = W.perm0.as<uint32_t>(); P.perm[1] = W.perm1.as<uint32_t>();
     P.flags = W.flags.as<uint8_t>(); P.unit_left = W.unit_left.as<uint32_t>(); P.units_per_tree = units;
     P.pool = W.pool.as<float>(); P.pool_stride = pool_stride; P.pool_cap = pool_cap; P.pool_counter = W.pool_counter.as<uint32_t>();
-    P.jobs = W.jobs.as<Job>(); P.scratch = W.scratch.as<float>(); P.use_smem_ws = use_smem;
+    P.jobs = W.jobs.as<Job>(); P.scratch = W.scratch.as<float>(); P.use_smem_ws = use_smem; P.spec = spec;
     P.active = W.active.as<uint32_t>(); P.error = W.error.as<int32_t>();
     P.sub_rows = nullptr; P.sub_off = nullptr;
     // cluster-resident nodes: up to ~6 MB of item rows per scan (2048 rows at d = 768, every node of a 10k x 64 index)
@@ -576,6 +579,7 @@ void build_wave(arroy_ctx* c, size_t wave_no, uint32_t t0, uint32_t tw, const ui
         c->stats[0] += (double)st[t].scanned;
         c->stats[2] += (double)st[t].n_splits_tried;
         c->stats[3] += (double)st[t].n_random;
+        c->stats[7] += (double)st[t].n_misspec;
     }
     CK(cudaStreamSynchronize(c->stream));
     c->d2h_bytes += (uint64_t)pool_used * pool_stride * 4 + sizeof(TreeState) * tw + sizeof(Record) * total_recs + 4ull * n * tw;
@@ -1205,6 +1209,8 @@ int32_t arroy_b200_create_split(arroy_ctx* c, const uint32_t rng_key[8], uint64_
         P.n = (uint32_t)c->n; P.d = c->dim; P.ld = ld; P.metric = c->metric;
         size_t ws_bytes = (size_t)WS_VECS * ld * 4;
         P.use_smem_ws = ws_bytes <= 200 * 1024;
+        P.spec = (P.use_smem_ws && (size_t)WS_VECS_SPEC * ld * 4 <= 200 * 1024 && !(getenv("ARROY_B200_SPEC") && atoi(getenv("ARROY_B200_SPEC")) == 0)) ? 1 : 0;
+        if (P.spec) ws_bytes = (size_t)WS_VECS_SPEC * ld * 4;
         P.scratch = reinterpret_cast<float*>(c->s_misc.as<uint8_t>() + 64);
         size_t smem = P.use_smem_ws ? ws_bytes : 0;
         if (smem > 48 * 1024) CK(cudaFuncSetAttribute(create_split_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

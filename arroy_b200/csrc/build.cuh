@@ -53,7 +53,7 @@ struct TreeState {
     uint32_t slot_next;      // pool slots are taken from the shared counter eight at a time: [slot_next, slot_end)
     uint64_t scanned;        // rows that went through side()
     uint32_t slot_end;
-    uint32_t pad;
+    uint32_t n_misspec;      // create_split calls whose speculative two_means had to be redone sequentially
 };
 
 struct BuildParams {
@@ -69,6 +69,7 @@ struct BuildParams {
     Job* jobs;
     float* scratch;          // n_trees x WS_VECS x ld (two_means workspace when it does not fit in smem)
     int32_t use_smem_ws;
+    int32_t spec;            // speculative two_means: the shared-memory workspace holds WS_VECS_SPEC vectors
     uint32_t* active;        // trees not yet done
     int32_t* error;
     // optional: tree t is built over the ascending row subset sub_rows[sub_off[t] .. sub_off[t+1])
@@ -92,6 +93,9 @@ __device__ __forceinline__ double split_imbalance_dev(uint32_t l, uint32_t r) { 
 // ws: WS_VECS vectors of ld floats: ws[0]=p, ws[1]=q, ws[2..11]=the ten sampled k,
 // ws[12], ws[13] = scratch (normal / bias terms / Manhattan terms / k / norm of the current iteration).
 constexpr int WS_VECS = 14;
+// Speculative two_means (spec_two_means below) keeps every centroid version of the ten iterations: ws[14 + it] = the centroid
+// that iteration `it` produced. 24 vectors in all; used when they fit in shared memory.
+constexpr int WS_VECS_SPEC = 24;
 struct TwoMeansShared {
     uint32_t rows[12];
     float h0[12], h1[12];
@@ -101,6 +105,12 @@ struct TwoMeansShared {
     float misc[2];
     long long tacc[16];     // cycle accumulators of the phases (thread 0; flushed to BuildParams::timing when set)
     long long tlast;
+    // speculative two_means
+    float G[12][12];        // approximate dots between the 12 gathered vectors (0 = p, 1 = q after normalize, 2.. = the ten k)
+    float vdot[32];         // exact dots of the verification pass
+    int choice[10];         // per iteration: 0 = nothing moved, 1 = p moved, 2 = q moved
+    int ready;              // iterations whose choice has been published by the speculating warp
+    int mismatch;
 };
 // phase ids of BuildParams::timing
 enum { TP_DECIDE = 0, TP_RNG = 1, TP_GATHER = 2, TP_NORMS = 3, TP_TWOMEANS = 4, TP_FINISH_SPLIT = 5, TP_CLUSTER_SCAN = 6, TP_PREFIX = 7, TP_PARTITION = 8, TP_ATTEMPTS = 9, TP_INNER = 10, TP_TOTAL = 11, TP_TM_DOT = 12, TP_TM_UPD = 13 };
@@ -141,6 +151,171 @@ __device__ __forceinline__ void exact_warp_ab_aa(const float* a, const float* b,
         if (lane == 0) { r = exact_thread<EUCLID>(a, b, n); if (!EUCLID) r2 = exact_thread<false>(a, a, n); }
         ab = __shfl_sync(0xffffffffu, r, 0); aa = __shfl_sync(0xffffffffu, r2, 0);
     }
+}
+
+
+// ---- speculative two_means ---------------------------------------------------------------------
+// The ten iterations of two_means (src/distance/mod.rs:146-168) form a chain only through ten BRANCHES (which centroid
+// moves); everything else is element-wise. So:
+//  (1) predict the branches with ordinary float arithmetic on the 12 x 12 Gram matrix of the gathered vectors (every centroid
+//      is a linear combination of them, so its dots with the ten k follow a scalar recurrence) — warp 0; meanwhile the other
+//      warps produce the centroid versions element-wise, following the predictions as they are published;
+//  (2) compute the reference's exact dots of ALL ten iterations at once, in the reference's summation order (32 dots, one per
+//      8-lane group), and the exact di / dj from them;
+//  (3) check that they take the predicted branches. If they do, the centroids are the reference's, bit for bit. If one does
+//      not (|di - dj| below the prediction's rounding noise: rare), the caller runs the sequential loop instead.
+// ws: slots 0 / 1 = p / q (normalized for the angular metrics), 2..11 = the ten k, 14 + it = centroid produced by iteration it.
+// On success pslot / qslot are the slots of the final centroids.
+template <bool EUCLID>
+__device__ __forceinline__ bool spec_two_means(const BuildParams& P, float* ws, TwoMeansShared& S, int& pslot, int& qslot) {
+    const unsigned full = 0xffffffffu;
+    const int d = (int)P.d, ld = (int)P.ld, metric = P.metric;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, grp = lane >> 3, g8 = lane & 7;
+    const bool cosine = !EUCLID;
+    for (int i = tid; i < 144; i += CTRL_THREADS) (&S.G[0][0])[i] = 0.f;
+    if (tid == 0) { S.ready = 0; S.mismatch = 0; }
+    __syncthreads();
+    // (1a) Gram matrix, any summation order: 6 pairs of 4-vector blocks x 4 K-slices = 24 jobs of 16 dots each
+    if (warp < 6) {
+        const int job = warp * 4 + grp, pair = job >> 2, slice = job & 3;
+        const int X = pair < 3 ? 0 : (pair < 5 ? 1 : 2);
+        const int Y = pair < 3 ? pair : (pair < 5 ? pair - 2 : 2);
+        float acc[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+        const int nch = ld >> 5;
+        for (int c = slice; c < nch; c += 4) {
+            float4 xa[4], ya[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) xa[i] = *reinterpret_cast<const float4*>(ws + (size_t)(4 * X + i) * ld + c * 32 + g8 * 4);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) ya[j] = *reinterpret_cast<const float4*>(ws + (size_t)(4 * Y + j) * ld + c * 32 + g8 * 4);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    acc[i][j] = fmaf(xa[i].x, ya[j].x, fmaf(xa[i].y, ya[j].y, fmaf(xa[i].z, ya[j].z, fmaf(xa[i].w, ya[j].w, acc[i][j]))));
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float v = acc[i][j];
+                v += __shfl_xor_sync(full, v, 4); v += __shfl_xor_sync(full, v, 2); v += __shfl_xor_sync(full, v, 1);
+                if (g8 == 0) { atomicAdd(&S.G[4 * X + i][4 * Y + j], v); if (X != Y) atomicAdd(&S.G[4 * Y + j][4 * X + i], v); }
+            }
+    }
+    __syncthreads();
+    TP_MARK(S, TP_TM_DOT);
+    if (warp == 0) {
+        // (1b) the recurrence: lane l < 10 carries p.k_l and q.k_l; every lane carries p.p, q.q and the counts
+        float pk = lane < 10 ? S.G[0][2 + lane] : 0.f, qk = lane < 10 ? S.G[1][2 + lane] : 0.f;
+        float pp = S.G[0][0], qq = S.G[1][1], ic = 1.f, jc = 1.f;
+        const float pe = S.php[0], qe = S.phq[0];   // DotProduct: extra_dim of the centroids (update_mean leaves headers alone)
+#pragma unroll 1
+        for (int it = 0; it < 10; ++it) {
+            const float pki = __shfl_sync(full, pk, it), qki = __shfl_sync(full, qk, it);
+            const float kk = S.G[2 + it][2 + it];
+            float di, dj;
+            if (EUCLID) { di = ic * (pp - 2.f * pki + kk); dj = jc * (qq - 2.f * qki + kk); }
+            else if (metric == COSINE) {
+                const float kn0 = S.h0[2 + it];
+                const float dp = sqrtf(pp) * kn0, dq = sqrtf(qq) * kn0;
+                const float cp = fminf(1.f, fmaxf(-1.f, pki / dp)), cq = fminf(1.f, fmaxf(-1.f, qki / dq));
+                di = dp > 1.1920928955078125e-07f ? ic * (1.f - cp) * 0.5f : 0.f;
+                dj = dq > 1.1920928955078125e-07f ? jc * (1.f - cq) * 0.5f : 0.f;
+            } else {
+                const float ke = S.h0[2 + it], kh1 = S.h1[2 + it];
+                const float mp = pp * kh1, mq = qq * kh1;
+                di = mp >= 1.17549435e-38f ? ic * (2.f - 2.f * (pki + pe * ke) / sqrtf(mp)) : ic * 2.f;
+                dj = mq >= 1.17549435e-38f ? jc * (2.f - 2.f * (qki + qe * ke) / sqrtf(mq)) : jc * 2.f;
+            }
+            const float norm = cosine ? S.nk[2 + it] : 1.f;
+            int ch = 0;
+            if (!(norm != norm || norm <= 0.f)) ch = di < dj ? 1 : (dj < di ? 2 : 0);
+            if (ch) {   // c' = (c * cnt + k / norm) / (cnt + 1) — update_mean, mod.rs:86-94
+                const float inv = 1.f / norm;
+                const float g = lane < 10 ? S.G[2 + it][2 + lane] * inv : 0.f;
+                if (ch == 1) { const float c1 = ic + 1.f, r = 1.f / c1; pk = (ic * pk + g) * r; pp = (ic * ic * pp + 2.f * ic * pki * inv + kk * inv * inv) * r * r; ic = c1; }
+                else { const float c1 = jc + 1.f, r = 1.f / c1; qk = (jc * qk + g) * r; qq = (jc * jc * qq + 2.f * jc * qki * inv + kk * inv * inv) * r * r; jc = c1; }
+            }
+            if (lane == 0) { *(volatile int*)&S.choice[it] = ch; __threadfence_block(); *(volatile int*)&S.ready = it + 1; }
+        }
+    } else {
+        // the centroid versions, element-wise and in the reference's exact operations; every thread only re-reads elements it
+        // wrote itself, so the ten steps need no barrier — only the published choice
+        const int nt = CTRL_THREADS - 32, t = tid - 32;
+        float ic = 1.f, jc = 1.f;
+        int ps = 0, qs = 1;
+#pragma unroll 1
+        for (int it = 0; it < 10; ++it) {
+            while (*(volatile int*)&S.ready <= it) { }
+            const int ch = *(volatile int*)&S.choice[it];
+            if (ch == 0) continue;
+            const float* k = ws + (size_t)(2 + it) * ld;
+            const float norm = cosine ? S.nk[2 + it] : 1.0f;
+            const float* cen = ws + (size_t)(ch == 1 ? ps : qs) * ld;
+            float* out = ws + (size_t)(14 + it) * ld;
+            const float cnt = ch == 1 ? ic : jc, c1 = __fadd_rn(cnt, 1.0f);
+            for (int i = t; i < ld; i += nt) out[i] = i < d ? __fdiv_rn(__fadd_rn(__fmul_rn(cen[i], cnt), __fdiv_rn(k[i], norm)), c1) : 0.f;
+            if (ch == 1) { ps = 14 + it; ic = c1; } else { qs = 14 + it; jc = c1; }
+        }
+    }
+    __syncthreads();
+    TP_MARK(S, TP_TM_UPD);
+    // (2) the reference's dots: group j < 10: p_j . k_j, 10 + j: q_j . k_j (Euclidean: squared distances), 20 / 21: the D::init
+    // dots of the initial p / q, 22 + j: of the centroid iteration j produced
+    if (!EUCLID || warp < 5) {
+        const int job = warp * 4 + grp;
+        const float* a = ws; const float* b = ws;
+        if (job < 20) {
+            const int it = job % 10, side = job / 10;
+            int slot = side;
+            for (int j = 0; j < it; ++j) if (S.choice[j] == side + 1) slot = 14 + j;
+            a = ws + (size_t)slot * ld; b = ws + (size_t)(2 + it) * ld;
+        } else {
+            const int v = job - 20;
+            const int slot = v < 2 ? v : (S.choice[v - 2] ? 14 + (v - 2) : 0);
+            a = b = ws + (size_t)slot * ld;
+        }
+        const float r = exact_group8<EUCLID>(a, b, d);
+        if (g8 == 0) S.vdot[job] = r;
+    }
+    __syncthreads();
+    TP_MARK(S, 14);
+    // (3) exact di / dj of every iteration (mod.rs:148-149) against the predicted branch
+    int ps = 0, qs = 1;
+    if (tid < 10) {
+        const int it = tid;
+        float ic = 1.f, jc = 1.f;
+        for (int j = 0; j < it; ++j) { const int c = S.choice[j]; if (c == 1) { ps = 14 + j; ic = __fadd_rn(ic, 1.0f); } else if (c == 2) { qs = 14 + j; jc = __fadd_rn(jc, 1.0f); } }
+        const float xp = S.vdot[it], xq = S.vdot[10 + it];
+        const float sp = S.vdot[ps < 2 ? 20 + ps : 22 + (ps - 14)], sq = S.vdot[qs < 2 ? 20 + qs : 22 + (qs - 14)];   // D::init dots
+        const float kh0 = S.h0[2 + it], kh1 = S.h1[2 + it];
+        float dvp, dvq;
+        if (EUCLID) { dvp = xp; dvq = xq; }
+        else if (metric == COSINE) { dvp = built_finish(COSINE, xp, __fsqrt_rn(sp), kh0); dvq = built_finish(COSINE, xq, __fsqrt_rn(sq), kh0); }
+        else {   // dot_product.rs:58-70
+            const float a1 = __fadd_rn(xp, __fmul_rn(S.php[0], kh0)), m1 = __fmul_rn(sp, kh1);
+            dvp = (m1 >= 1.17549435e-38f) ? __fsub_rn(2.0f, __fdiv_rn(__fmul_rn(2.0f, a1), __fsqrt_rn(m1))) : 2.0f;
+            const float a2 = __fadd_rn(xq, __fmul_rn(S.phq[0], kh0)), m2 = __fmul_rn(sq, kh1);
+            dvq = (m2 >= 1.17549435e-38f) ? __fsub_rn(2.0f, __fdiv_rn(__fmul_rn(2.0f, a2), __fsqrt_rn(m2))) : 2.0f;
+        }
+        const float di = __fmul_rn(ic, dvp), dj = __fmul_rn(jc, dvq);
+        const float norm = cosine ? S.nk[2 + it] : 1.0f;
+        int want = 0;
+        if (!(norm != norm || norm <= 0.0f)) want = di < dj ? 1 : (dj < di ? 2 : 0);
+        if (want != S.choice[it]) S.mismatch = 1;
+    }
+    __syncthreads();
+    TP_MARK(S, 15);
+    if (S.mismatch) return false;
+    ps = 0; qs = 1;
+    for (int j = 0; j < 10; ++j) { const int c = S.choice[j]; if (c == 1) ps = 14 + j; else if (c == 2) qs = 14 + j; }
+    pslot = ps; qslot = qs;
+    return true;
 }
 
 __device__ __forceinline__ float norm_leaf_group(int metric, const float* v, float h0, int d) {
@@ -238,7 +413,13 @@ __device__ __forceinline__ void create_split_cta(const BuildParams& P, Rng& rng 
     }
     __syncthreads();
     TP_MARK(S, TP_NORMS);
-    {
+    bool spec_done = false;
+    if (P.spec && metric != MANHATTAN && d >= 32) {
+        int ps = 0, qs = 1;
+        spec_done = (metric == EUCLIDEAN) ? spec_two_means<true>(P, ws, S, ps, qs) : spec_two_means<false>(P, ws, S, ps, qs);
+        if (spec_done) { p = ws + (size_t)ps * ld; q = ws + (size_t)qs * ld; }
+    }
+    if (!spec_done) {
     float ic = 1.0f, jc = 1.0f;
     bool p_dirty = cosine, q_dirty = cosine;   // D::init pending (cosine.rs:69-71, dot_product.rs:94-96)
     // (kept rolled: the serial path runs on one or two warps, whose speed is set by instruction fetch —
@@ -512,7 +693,7 @@ __global__ void __launch_bounds__(CTRL_THREADS, 1) control_kernel(BuildParams P,
     uint32_t* unit_left = P.unit_left + (size_t)t * P.units_per_tree;
     const int tid = threadIdx.x;
 
-    if (tid == 0) { s_rng.init(S.key, S.pos); job.kind = JOB_NONE; }
+    if (tid == 0) { s_rng.init(S.key, S.pos); job.kind = JOB_NONE; TM.mismatch = 0; }
     uint32_t total_left = 0;
     if (S.phase == PH_AWAIT_SCAN) {
         const Frame f = FR(S.sp);
@@ -616,6 +797,7 @@ __global__ void __launch_bounds__(CTRL_THREADS, 1) control_kernel(BuildParams P,
             if (SMEM_WS) create_split_cta(P, s_rng, src, f.len, reinterpret_cast<float*>(ctrl_smem), TM, slot_ptr);
             else create_split_cta(P, s_rng, src, f.len, P.scratch + (size_t)t * WS_VECS * P.ld, TM, slot_ptr);
             if (tid == 0) {
+                if (TM.mismatch) { S.n_misspec += 1; TM.mismatch = 0; }
                 S.n_splits_tried += 1; if (P.timing) TM.tacc[TP_ATTEMPTS] += 1;
                 job.kind = JOB_SCAN; job.len = f.len; job.rows = src; job.normal = slot_ptr;
                 job.flags = flags + f.start; job.margins = nullptr; job.unit_left = unit_left; job.dst = nullptr; job.total_left = 0;
@@ -707,7 +889,7 @@ __global__ void init_trees_kernel(BuildParams P, const uint32_t* __restrict__ ke
         TreeState s;
         for (int i = 0; i < 8; ++i) s.key[i] = keys[t * 8 + i];
         s.pos = 0; s.phase = PH_START; s.sp = -1; s.attempts_left = 0; s.cur_slot = NO_SLOT; s.n_recs = 0;
-        s.n_splits_tried = 0; s.n_random = 0; s.pad = 0; s.scanned = 0; s.slot_next = 0; s.slot_end = 0;
+        s.n_splits_tried = 0; s.n_random = 0; s.n_misspec = 0; s.scanned = 0; s.slot_next = 0; s.slot_end = 0;
         P.st[t] = s;
         P.jobs[t].kind = JOB_NONE;
         P.jobs[t].pad = 0;

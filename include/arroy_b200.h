@@ -174,7 +174,8 @@ int32_t arroy_b200_build_trees_emit_mapped(arroy_ctx* ctx, const uint32_t* root_
  * stats[0] = rows that went through side() (sum over scans, retries included)
  * stats[1] = device steps, stats[2] = create_split calls, stats[3] = random-fallback splits,
  * stats[4] = device milliseconds of the build loop (CUDA events), stats[5] = ms in scan kernels
- * (only measured when ARROY_B200_PROFILE=1), stats[6] = tree nodes emitted, stats[7] reserved. */
+ * (only measured when ARROY_B200_PROFILE=1), stats[6] = tree nodes emitted, stats[7] = create_split calls whose
+ * speculative two_means was redone sequentially (a mis-predicted branch; results are identical either way). */
 int32_t arroy_b200_build_stats(arroy_ctx* ctx, double stats[8]);
 
 /* ---- re-rank: replaces the loop of src/reader.rs:381-399 ------------------------------- */
