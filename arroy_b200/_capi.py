@@ -65,6 +65,18 @@ SIGNATURES = [
     ("arroy_b200_timer_stop", C.c_int32, [C.c_void_p, _f32p]),
     ("arroy_b200_device_ptrs", C.c_int32, [C.c_void_p, C.POINTER(C.c_void_p), _u32p]),
     ("arroy_b200_epochs", C.c_int32, [C.c_void_p, _u64p]),
+    ("arroy_b200_stage_begin", C.c_int32, [C.c_void_p, C.c_int32, C.c_uint32, C.c_uint64, _u32p]),
+    ("arroy_b200_stage_rows", C.c_int32, [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(C.c_void_p)]),
+    ("arroy_b200_stage_end", C.c_int32, [C.c_void_p, C.c_int32]),
+    ("arroy_b200_create_group", C.c_int32, [C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_void_p)]),
+    ("arroy_b200_destroy_group", None, [C.c_void_p]),
+    ("arroy_b200_group_last_error", C.c_char_p, [C.c_void_p]),
+    ("arroy_b200_group_size", C.c_int32, [C.c_void_p]),
+    ("arroy_b200_group_ctx", C.c_void_p, [C.c_void_p, C.c_int32]),
+    ("arroy_b200_group_stage_items", C.c_int32, [C.c_void_p, C.c_int32, C.c_uint32, C.c_uint64, _u32p, C.POINTER(C.c_void_p)]),
+    ("arroy_b200_group_dot_preprocess", C.c_int32, [C.c_void_p, _f32p, _f32p]),
+    ("arroy_b200_group_build_trees", C.c_int32, [C.c_void_p, C.c_uint32, C.c_void_p, _u32p, C.c_uint32, C.c_uint32, CANCEL_FN, C.c_void_p, NODE_SINK, C.c_void_p, _u64p]),
+    ("arroy_b200_group_stage_breakdown", C.c_int32, [C.c_void_p, C.POINTER(C.c_double)]),
 ]
 
 _LIB = None
@@ -268,6 +280,19 @@ class Context:
         self._ck(self.lib.arroy_b200_stage_items(self.h, metric, dim, ids.size, _up(ids), ptrs.ctypes.data_as(C.POINTER(C.c_void_p))))
         self.n, self.dim, self.metric = ids.size, dim, metric
 
+    def stage_begin(self, metric, dim, ids):
+        metric = METRICS[metric] if isinstance(metric, str) else metric
+        ids = np.ascontiguousarray(ids, dtype=np.uint32)
+        self._ck(self.lib.arroy_b200_stage_begin(self.h, metric, dim, ids.size, _up(ids)))
+        self.n, self.dim, self.metric = ids.size, dim, metric
+
+    def stage_rows(self, row0, ptr_array):
+        ptrs = np.ascontiguousarray(ptr_array, dtype=np.uint64)
+        self._ck(self.lib.arroy_b200_stage_rows(self.h, row0, ptrs.size, ptrs.ctypes.data_as(C.POINTER(C.c_void_p))))
+
+    def stage_end(self, headers_on_device=False):
+        self._ck(self.lib.arroy_b200_stage_end(self.h, 1 if headers_on_device else 0))
+
     def build_stats(self):
         st = (C.c_double * 8)()
         self._ck(self.lib.arroy_b200_build_stats(self.h, st))
@@ -428,3 +453,93 @@ class Arena:
             self.lib.arroy_b200_arena_free(self.h)
         except Exception:
             pass
+
+
+class Group:
+    """Several GPUs of one node behind one handle (arroy_b200_create_group): in-library pipelined H2D + ncclBroadcast of
+    the item buffer, trees sharded t mod n_dev, node ids as a single-device build."""
+
+    def __init__(self, devices):
+        self.lib = load()
+        devs = (C.c_int32 * len(devices))(*devices)
+        h = C.c_void_p()
+        rc = self.lib.arroy_b200_create_group(len(devices), devs, C.byref(h))
+        if rc != OK:
+            raise ArroyB200Error(rc, "arroy_b200_create_group failed (device missing / NCCL not loadable)")
+        self.h = h
+        self.devices = list(devices)
+        self.n = 0
+
+    def _ck(self, rc):
+        if rc != OK:
+            raise ArroyB200Error(rc, self.lib.arroy_b200_group_last_error(self.h).decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.arroy_b200_destroy_group(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def size(self):
+        return self.lib.arroy_b200_group_size(self.h)
+
+    def ctx(self, rank):
+        """The member context of one device (owned by the group: do not close it)."""
+        c = Context.__new__(Context)
+        c.lib = self.lib
+        c.h = C.c_void_p(self.lib.arroy_b200_group_ctx(self.h, rank))
+        c.device = self.devices[rank]
+        c.n, c.dim, c.metric = self.n, getattr(self, "dim", 0), getattr(self, "metric", None)
+        c.close = lambda: None
+        return c
+
+    def stage_items_ptrs(self, metric, dim, ids, ptr_array):
+        metric = METRICS[metric] if isinstance(metric, str) else metric
+        ids = np.ascontiguousarray(ids, dtype=np.uint32)
+        ptrs = np.ascontiguousarray(ptr_array, dtype=np.uint64)
+        self._ck(self.lib.arroy_b200_group_stage_items(self.h, metric, dim, ids.size, _up(ids), ptrs.ctypes.data_as(C.POINTER(C.c_void_p))))
+        self.n, self.dim, self.metric = ids.size, dim, metric
+
+    def dot_preprocess(self):
+        extra = np.empty(self.n, dtype=np.float32)
+        norm = np.empty(self.n, dtype=np.float32)
+        self._ck(self.lib.arroy_b200_group_dot_preprocess(self.h, _fp(extra), _fp(norm)))
+        return extra, norm
+
+    def build_trees(self, tree_seeds, root_ids, first_free_node_id, split_after=0, arena=None):
+        """Returns {node id: bytes}, or the node count when an Arena collects the nodes."""
+        n_trees = len(tree_seeds)
+        seeds = (C.c_uint8 * (32 * max(n_trees, 1)))()
+        for t, s in enumerate(tree_seeds):
+            seeds[32 * t:32 * t + 32] = list(s)
+        roots = np.ascontiguousarray(root_ids, dtype=np.uint32)
+        n_nodes = C.c_uint64(0)
+        if arena is not None:
+            sink = C.cast(self.lib.arroy_b200_arena_sink, NODE_SINK)
+            self._ck(self.lib.arroy_b200_group_build_trees(self.h, n_trees, C.cast(seeds, C.c_void_p), _up(roots), first_free_node_id, split_after,
+                                                           C.cast(None, CANCEL_FN), None, sink, arena.h, C.byref(n_nodes)))
+            return n_nodes.value
+        out = {}
+        import threading
+        lock = threading.Lock()
+
+        def sink(_arg, node_id, ptr, length):
+            b = C.string_at(ptr, length)
+            with lock:
+                out[node_id] = b
+            return 0
+
+        cb = NODE_SINK(sink)
+        self._ck(self.lib.arroy_b200_group_build_trees(self.h, n_trees, C.cast(seeds, C.c_void_p), _up(roots), first_free_node_id, split_after,
+                                                       C.cast(None, CANCEL_FN), None, cb, None, C.byref(n_nodes)))
+        return out
+
+    def stage_breakdown(self):
+        out = (C.c_double * 4)()
+        self._ck(self.lib.arroy_b200_group_stage_breakdown(self.h, out))
+        return {"total_ms": out[0], "tail_ms": out[1]}

@@ -117,6 +117,8 @@ struct arroy_ctx {
     uint64_t n_launches = 0, h2d_bytes = 0, d2h_bytes = 0;  // since create (arroy_b200_counters)
     cudaEvent_t tev0 = nullptr, tev1 = nullptr;
     std::vector<StageWorker> stage_workers;
+    bool staging_open = false;             // between arroy_b200_stage_begin and arroy_b200_stage_end
+    std::vector<float> stage_h0, stage_h1;  // headers decoded from the leaf values staged so far
     // device-resident forest for the batched query path (arroy_b200_load_forest)
     DevBuf f_kind, f_left, f_right, f_nidx, f_nh0, f_doff, f_dlen, f_normals, f_desc, f_roots;
     DevForest forest{};
@@ -191,7 +193,7 @@ void alloc_items(arroy_ctx* c, int metric, uint32_t dim, uint64_t n, const uint3
     for (uint64_t i = 1; i < n; ++i) if (ids[i] <= ids[i - 1]) throw ArgError("ids must be strictly ascending");
     // a restage invalidates everything derived from the previous items: the bf16 shadow and the device forest
     // (its descendant rows were validated against the previous item count)
-    c->staged = false; c->fr_valid = false; c->forest_loaded = false;
+    c->staged = false; c->fr_valid = false; c->forest_loaded = false; c->staging_open = false;
     c->stage_epoch += 1;
     c->metric = metric; c->dim = dim; c->ld = (dim + 31u) & ~31u; c->n = n;
     c->ids.assign(ids, ids + n);
@@ -1078,6 +1080,53 @@ int32_t arroy_b200_stage_items(arroy_ctx* c, int32_t metric, uint32_t dim, uint6
     });
 }
 
+// ---- staging in pieces (multi-GPU: the H2D copy of chunk k + 1 overlaps the broadcast of chunk k) ---------------------------
+int32_t arroy_b200_stage_begin(arroy_ctx* c, int32_t metric, uint32_t dim, uint64_t n, const uint32_t* ids) {
+    return guarded(c, [&] {
+        set_device(c);
+        if (n && !ids) throw ArgError("null ids");
+        alloc_items(c, metric, dim, n, ids);
+        c->stage_h0.assign(n, 0.f); c->stage_h1.assign(n, 0.f);
+        CK(cudaStreamSynchronize(c->stream));
+        c->staging_open = true;
+    });
+}
+
+int32_t arroy_b200_stage_rows(arroy_ctx* c, uint64_t row0, uint64_t n_rows, const uint8_t* const* leaf_values) {
+    return guarded(c, [&] {
+        set_device(c);
+        if (!c->staging_open) throw NotStaged("arroy_b200_stage_rows without arroy_b200_stage_begin");
+        if (row0 > c->n || n_rows > c->n - row0) throw ArgError("row range out of bounds");
+        if (n_rows == 0) return;
+        if (!leaf_values) throw ArgError("null leaf_values");
+        const int hf = metric_header_floats(c->metric);
+        for (uint64_t i = 0; i < n_rows; ++i) {
+            const uint8_t* v = leaf_values[i];
+            if (!v || v[0] != 0) throw ArgError("leaf value does not start with the Leaf tag 0x00");
+            memcpy(&c->stage_h0[row0 + i], v + 1, 4);
+            if (hf == 2) memcpy(&c->stage_h1[row0 + i], v + 5, 4);
+        }
+        const size_t voff = 1 + 4 * (size_t)hf;
+        stage_rows_pipeline(c, n_rows, c->dim, c->ld, [&](uint64_t i) { return leaf_values[i] + voff; }, c->items.as<float>() + (size_t)row0 * c->ld);
+    });
+}
+
+int32_t arroy_b200_stage_end(arroy_ctx* c, int32_t headers_on_device) {
+    return guarded(c, [&] {
+        set_device(c);
+        if (!c->staging_open) throw NotStaged("arroy_b200_stage_end without arroy_b200_stage_begin");
+        if (!headers_on_device && c->n) {
+            CK(cudaMemcpyAsync(c->h0.p, c->stage_h0.data(), c->n * 4, cudaMemcpyHostToDevice, c->stream));
+            CK(cudaMemcpyAsync(c->h1.p, c->stage_h1.data(), c->n * 4, cudaMemcpyHostToDevice, c->stream));
+            c->h2d_bytes += 8 * c->n;
+        }
+        CK(cudaStreamSynchronize(c->stream));
+        c->stage_h0.clear(); c->stage_h0.shrink_to_fit(); c->stage_h1.clear(); c->stage_h1.shrink_to_fit();
+        c->staging_open = false;
+        c->staged = true;
+    });
+}
+
 int32_t arroy_b200_stage_items_flat(arroy_ctx* c, int32_t metric, uint32_t dim, uint64_t n, const uint32_t* ids, const float* vectors, const float* hdr0, const float* hdr1) {
     return guarded(c, [&] {
         set_device(c);
@@ -1477,6 +1526,63 @@ int32_t arroy_b200_search_batch(arroy_ctx* c, uint32_t nq, const uint32_t* query
         for (double& x : c->sbreak) x = 0;
         int nte = 0;
         auto mark = [&]() { if (!c->xev[nte]) CK(cudaEventCreate(&c->xev[nte])); CK(cudaEventRecord(c->xev[nte], c->stream)); ++nte; };
+        // ---- a few queries: latency path, one CTA per query (search.cuh walk1_kernel), then the plain distance + top-k kernels on
+        //      all SMs. Any query it cannot hold (heap / candidate overflow) sends the call through the general path below.
+        if (nq <= 16 && cand_cap64 <= (uint64_t)W1_CAND && getenv("ARROY_B200_NO_WALK1") == nullptr) {
+            const uint32_t m = nq;
+            const size_t w1smem = walk1_smem(ld);
+            { static bool configured = false; if (!configured) { CK(cudaFuncSetAttribute(walk1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(Walk1Shared) + 16 + 4 * 8192))); configured = true; } }
+            if (w1smem <= sizeof(Walk1Shared) + 16 + 4 * 8192) {
+                c->w_cand2.ensure(4ull * cand_cap * m); c->w_count.ensure(4ull * m); c->w_status.ensure(4ull * m);
+                c->w_beg.ensure(8ull * (m + 1)); c->w_end.ensure(8ull * (m + 1));
+                c->s_keys.ensure(8ull * cand_cap * m); c->s_dists.ensure(4ull * cand_cap * m);
+                c->s_orows.ensure(4ull * m * k); c->s_odist.ensure(4ull * m * k); c->s_olen.ensure(4ull * m); c->s_qh0.ensure(4ull * m);
+                const uint32_t* d_qrows = nullptr;
+                const float* d_q = nullptr;
+                if (query_rows) {
+                    c->w_qrows.ensure(4ull * m);
+                    CK(cudaMemcpyAsync(c->w_qrows.p, query_rows, 4ull * m, cudaMemcpyHostToDevice, c->stream));
+                    d_qrows = c->w_qrows.as<uint32_t>();
+                } else {
+                    c->s_q.ensure((size_t)m * ld * 4);
+                    if (ld != c->dim) CK(cudaMemsetAsync(c->s_q.p, 0, (size_t)m * ld * 4, c->stream));
+                    CK(cudaMemcpy2DAsync(c->s_q.p, (size_t)ld * 4, queries, (size_t)c->dim * 4, (size_t)c->dim * 4, m, cudaMemcpyHostToDevice, c->stream));
+                    d_q = c->s_q.as<float>();
+                }
+                if (qhdr0) CK(cudaMemcpyAsync(c->s_qh0.p, qhdr0, 4ull * m, cudaMemcpyHostToDevice, c->stream));
+                else if (query_rows) { gather_f32_kernel<<<(m + 255) / 256, 256, 0, c->stream>>>(c->s_qh0.as<float>(), c->h0.as<float>(), d_qrows, m); CK(cudaGetLastError()); }
+                else CK(cudaMemsetAsync(c->s_qh0.p, 0, 4ull * m, c->stream));
+                walk1_kernel<<<m, W1_THREADS, w1smem, c->stream>>>(F, c->items.as<float>(), c->dim, ld, c->metric, m, d_qrows, d_q, c->s_qh0.as<float>(), search_k,
+                                                                  c->w_cand2.as<uint32_t>(), cand_cap, c->w_count.as<uint32_t>(), c->w_status.as<int32_t>());
+                CK(cudaGetLastError());
+                walk_segments_kernel<<<(m + 256) / 256, 256, 0, c->stream>>>(c->w_count.as<uint32_t>(), m, cand_cap, c->w_beg.as<uint64_t>(), c->w_end.as<uint64_t>());
+                CK(cudaGetLastError());
+                const uint64_t per = c->metric == MANHATTAN ? 32 : 4;
+                const uint64_t warps = ((uint64_t)cand_cap + per - 1) / per;
+                const uint32_t gx = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((warps + 7) / 8, std::max<uint64_t>(1, ((uint64_t)c->sm_count * 8) / m)));
+                distance_kernel<<<dim3(gx, m), 256, 0, c->stream>>>(c->items.as<float>(), c->h0.as<float>(), c->dim, ld, c->metric, d_q, d_qrows, c->s_qh0.as<float>(), m,
+                                                                   c->w_cand2.as<uint32_t>(), c->w_beg.as<uint64_t>(), c->w_end.as<uint64_t>(), c->s_dists.as<float>(), c->s_keys.as<unsigned long long>());
+                CK(cudaGetLastError());
+                topk_kernel<<<m, TOPK_THREADS, 0, c->stream>>>(c->s_keys.as<unsigned long long>(), c->s_dists.as<float>(), c->w_cand2.as<uint32_t>(), c->w_beg.as<uint64_t>(), c->w_end.as<uint64_t>(), k, c->metric,
+                                                               c->s_orows.as<uint32_t>(), c->s_odist.as<float>(), c->s_olen.as<uint32_t>());
+                CK(cudaGetLastError());
+                c->n_launches += 4;
+                c->pin.ensure(std::max<size_t>(c->pin.cap, 4ull * m));
+                int32_t* h_st = c->pin.as<int32_t>();
+                CK(cudaMemcpyAsync(h_st, c->w_status.p, 4ull * m, cudaMemcpyDeviceToHost, c->stream));
+                CK(cudaMemcpyAsync(out_rows, c->s_orows.p, 4ull * m * k, cudaMemcpyDeviceToHost, c->stream));
+                CK(cudaMemcpyAsync(out_dist, c->s_odist.p, 4ull * m * k, cudaMemcpyDeviceToHost, c->stream));
+                CK(cudaMemcpyAsync(out_len, c->s_olen.p, 4ull * m, cudaMemcpyDeviceToHost, c->stream));
+                CK(cudaStreamSynchronize(c->stream));
+                bool all_ok = true;
+                for (uint32_t q = 0; q < m; ++q) all_ok = all_ok && h_st[q] == 0;
+                if (all_ok) {
+                    if (out_status) for (uint32_t q = 0; q < m; ++q) out_status[q] = 0;
+                    c->d2h_bytes += 8ull * m * k + 8ull * m;
+                    return;
+                }
+            }
+        }
         // process the queries in chunks that keep the scratch memory bounded (~1 GiB)
         const uint64_t per_q = 8ull * heap_cap + 8ull * cand_cap + 4ull * bm_words + 12ull * cand_cap + 64;
         uint32_t chunk = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>({(uint64_t)nq, (1ull << 30) / per_q, 65535ull}));
@@ -1705,13 +1811,16 @@ int32_t arroy_b200_epochs(arroy_ctx* c, uint64_t out[2]) {
 
 int32_t arroy_b200_device_ptrs(arroy_ctx* c, void* out[3], uint32_t* out_ld) {
     return guarded(c, [&] {
-        require_staged(c);
+        if (!c->staging_open) require_staged(c);
         out[0] = c->items.p; out[1] = c->h0.p; out[2] = c->h1.p;
         if (out_ld) *out_ld = c->ld;
     });
 }
 
 }  // extern "C"
+
+// several GPUs behind one handle (in-library NCCL broadcast of the item buffer)
+#include "group.hpp"
 
 // C++ host mirror of the reference's Writer / Reader (client of the C ABI above)
 #include "host.hpp"

@@ -338,25 +338,41 @@ __device__ __forceinline__ void create_split_cta(const BuildParams& P, Rng& rng 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, grp = lane >> 3;
     const bool cosine = (metric == COSINE || metric == DOT_PRODUCT);
     // All RNG draws of the attempt first: they do not depend on the data. choose_two = index::sample(len, 2)
-    // = gen_range(0..=len-2), gen_range(0..=len-1); then ten gen_range(0..=len-1). A draw is rejected with
-    // probability ~ len / 2^32, so lanes 0..11 of warp 0 each take one word of the stream (the blocks
-    // were computed ahead, rng.pref) and the serial loop only runs if some lane saw a rejection.
+    // = gen_range(0..=len-2), gen_range(0..=len-1); then ten gen_range(0..=len-1). rand 0.8.5's sample_single_inclusive accepts a
+    // word v iff low32(v * range) <= zone with zone = (range << lzcnt(range)) - 1 — a deliberately loose zone: between half and
+    // all of the words are accepted, so the twelve draws consume ~12-24 words. The stream is a queue: draw 0 takes the first
+    // word acceptable for range len-1, every later draw the next word acceptable for range len. The blocks were computed ahead
+    // (rng.pref, >= 64 words from pos), so both acceptance masks of the next 64 words are two ballots, the twelve words are found
+    // with find-nth-set-bit, and the serial loop only runs when 64 words were not enough.
     if (warp == 0) {
         bool done = false;
         const uint64_t pos = rng.pos;
-        if (rng.pref && (pos >> 4) == rng.pref_base && rng.pref_n >= 2) {
-            const uint32_t range = lane == 0 ? len - 1u : len;
-            const uint32_t zone = (range << __clz((int)range)) - 1u;
-            const uint64_t w = pos + (uint64_t)lane;
-            const uint32_t v = lane < 12 ? rng.pref[(w - (rng.pref_base << 4)) & 31u] : 0u;
-            const unsigned long long m = (unsigned long long)v * (unsigned long long)range;
-            const bool ok = lane >= 12 || (uint32_t)m <= zone;
-            if (__all_sync(0xffffffffu, ok)) {
-                const uint32_t r = (uint32_t)(m >> 32);
-                const uint32_t t0 = __shfl_sync(0xffffffffu, r, 0), t1 = __shfl_sync(0xffffffffu, r, 1);
-                if (lane == 0) { if (t1 == t0) { S.rows[0] = len - 1u; S.rows[1] = t0; } else { S.rows[0] = t0; S.rows[1] = t1; } rng.pos = pos + 12u; }
-                if (lane >= 2 && lane < 12) S.rows[lane] = r;
-                done = true;
+        const uint64_t base16 = rng.pref_base << 4;
+        if (rng.pref && pos >= base16 && pos + 64 <= base16 + ((uint64_t)rng.pref_n << 4)) {
+            const uint32_t r0 = len - 1u, r1 = len;
+            const uint32_t z0 = (r0 << __clz((int)r0)) - 1u, z1 = (r1 << __clz((int)r1)) - 1u;
+            const uint32_t off = (uint32_t)(pos - base16);
+            const uint32_t vlo = rng.pref[off + lane], vhi = rng.pref[off + 32 + lane];
+            const unsigned a0lo = __ballot_sync(0xffffffffu, (uint32_t)((unsigned long long)vlo * r0) <= z0), a0hi = __ballot_sync(0xffffffffu, (uint32_t)((unsigned long long)vhi * r0) <= z0);
+            const unsigned a1lo = __ballot_sync(0xffffffffu, (uint32_t)((unsigned long long)vlo * r1) <= z1), a1hi = __ballot_sync(0xffffffffu, (uint32_t)((unsigned long long)vhi * r1) <= z1);
+            const unsigned long long a0 = (unsigned long long)a0lo | ((unsigned long long)a0hi << 32), a1 = (unsigned long long)a1lo | ((unsigned long long)a1hi << 32);
+            if (r0 != 0u && a0 != 0ull) {
+                const int idx0 = __ffsll((long long)a0) - 1;
+                const unsigned long long rest = idx0 >= 63 ? 0ull : (a1 & ~((2ull << idx0) - 1ull));
+                if (__popcll(rest) >= 11) {
+                    // lane j (1..11): the j-th acceptable word after idx0; lane 0: idx0 itself
+                    const unsigned lo = (unsigned)rest, hi = (unsigned)(rest >> 32);
+                    const int clo = __popc(lo);
+                    int idx = idx0;
+                    if (lane >= 1 && lane < 12) idx = lane <= clo ? (int)__fns(lo, 0, lane) : 32 + (int)__fns(hi, 0, lane - clo);
+                    const uint32_t v = rng.pref[off + (uint32_t)(lane < 12 ? idx : 0)];
+                    const uint32_t r = (uint32_t)(((unsigned long long)v * (unsigned long long)(lane == 0 ? r0 : r1)) >> 32);
+                    const uint32_t t0 = __shfl_sync(0xffffffffu, r, 0), t1 = __shfl_sync(0xffffffffu, r, 1);
+                    if (lane == 0) { if (t1 == t0) { S.rows[0] = len - 1u; S.rows[1] = t0; } else { S.rows[0] = t0; S.rows[1] = t1; } }
+                    if (lane >= 2 && lane < 12) S.rows[lane] = r;
+                    if (lane == 11) rng.pos = pos + (uint64_t)idx + 1u;
+                    done = true;
+                }
             }
         }
         if (!done && lane == 0) {
@@ -652,7 +668,7 @@ __global__ void __launch_bounds__(CTRL_THREADS, 1) control_kernel(BuildParams P,
     __shared__ int s_action;
     __shared__ uint32_t s_total_left;
     __shared__ Rng s_rng;  // thread 0 only
-    __shared__ uint32_t s_pref[2][16];
+    __shared__ uint32_t s_pref[8][16];   // eight ChaCha blocks of this tree's stream computed ahead (one per quad of warp 1)
 
     constexpr int SMF = 96;  // DFS frames cached in shared memory (deeper ones stay in global)
     __shared__ Frame sm_frames[SMF];
@@ -702,14 +718,21 @@ __global__ void __launch_bounds__(CTRL_THREADS, 1) control_kernel(BuildParams P,
     __syncthreads();
     TP_MARK(TM, TP_PREFIX);
 
+    uint64_t pref_base = ~0ull;   // block number held in s_pref[0] (every thread tracks the same value)
     for (;;) {
-        // warp 1 computes the next two ChaCha blocks of this tree's stream (four lanes per block) while
-        // thread 0 walks the DFS
-        if ((tid >> 5) == 1) {
-            const int l = tid & 31, g = l >> 2;
-            uint32_t o[4];
-            chacha12_block_quad(S.key, (s_rng.pos >> 4) + (uint64_t)(g & 1), o);
-            if (g < 2) { s_pref[g][l & 3] = o[0]; s_pref[g][4 + (l & 3)] = o[1]; s_pref[g][8 + (l & 3)] = o[2]; s_pref[g][12 + (l & 3)] = o[3]; }
+        // warp 1 keeps eight ChaCha blocks of this tree's stream computed ahead (four lanes per block, all eight quads at once)
+        // while thread 0 walks the DFS; they are renewed when fewer than 64 words are left ahead of the stream position
+        {
+            const uint64_t blk0 = s_rng.pos >> 4;
+            if (pref_base == ~0ull || blk0 < pref_base || blk0 >= pref_base + 4) {
+                if ((tid >> 5) == 1) {
+                    const int l = tid & 31, g = l >> 2;
+                    uint32_t o[4];
+                    chacha12_block_quad(S.key, blk0 + (uint64_t)g, o);
+                    s_pref[g][l & 3] = o[0]; s_pref[g][4 + (l & 3)] = o[1]; s_pref[g][8 + (l & 3)] = o[2]; s_pref[g][12 + (l & 3)] = o[3];
+                }
+                pref_base = blk0;
+            }
         }
         // ---- thread 0: advance the DFS until CTA-wide work is needed --------------------------
         if (tid == 0) {
@@ -783,7 +806,7 @@ __global__ void __launch_bounds__(CTRL_THREADS, 1) control_kernel(BuildParams P,
             }
             s_action = action;
             s_total_left = total_left;
-            s_rng.pref = &s_pref[0][0]; s_rng.pref_base = s_rng.pos >> 4; s_rng.pref_n = 2;
+            s_rng.pref = &s_pref[0][0]; s_rng.pref_base = pref_base; s_rng.pref_n = 8;
         }
         __syncthreads();
         TP_MARK(TM, TP_DECIDE);

@@ -176,3 +176,140 @@ __global__ void gather_f32_kernel(float* __restrict__ dst, const float* __restri
 }
 
 }  // namespace ab
+
+namespace ab {
+
+// ---- few queries at a time: one CTA per query -------------------------------------------------------------------
+// walk_kernel above is built for throughput (one WARP per query, thousands of queries per launch). A single
+// Reader::nns_by_item / nns_by_vector call is a latency problem instead: the same priority-queue walk runs on warp 0 of a
+// CTA with the query vector and the heap in shared memory, a Descendants node only costs the walker its length (the stop
+// count includes duplicates, reader.rs:344-373) while the other seven warps copy its items into the candidate buffer, and the
+// candidates are sorted + de-duplicated right here (bitonic sort in shared memory; reader.rs:378-379) instead of going
+// through a per-query bitmap and a device-wide segmented sort. The re-rank then uses every SM (distance_kernel + topk_kernel).
+constexpr int W1_THREADS = 256;
+constexpr uint32_t W1_HEAP = 1024;     // heap entries in shared memory
+constexpr uint32_t W1_CAND = 8192;     // candidate slots in shared memory (duplicates included)
+constexpr uint32_t W1_LEAFQ = 128;     // Descendants nodes queued for the copier warps
+
+struct Walk1Shared {
+    unsigned long long heap[W1_HEAP];
+    uint32_t cand[W1_CAND];
+    uint32_t lq_off[W1_LEAFQ], lq_len[W1_LEAFQ], lq_dst[W1_LEAFQ];
+    uint32_t scan[W1_THREADS / 32];
+    volatile uint32_t produced;
+    volatile int done;
+    uint32_t total;
+    int status;
+};
+inline size_t walk1_smem(uint32_t ld) { return sizeof(Walk1Shared) + (size_t)ld * 4 + 16; }
+
+__global__ void __launch_bounds__(W1_THREADS)
+walk1_kernel(DevForest F, const float* __restrict__ items, uint32_t d, uint32_t ld, int metric, uint32_t nq,
+             const uint32_t* __restrict__ qrows, const float* __restrict__ queries, const float* __restrict__ qh0,
+             unsigned long long search_k, uint32_t* __restrict__ out_cand, uint32_t cand_cap, uint32_t* __restrict__ out_count, int32_t* __restrict__ status) {
+    extern __shared__ __align__(16) unsigned char w1_smem[];
+    Walk1Shared& S = *reinterpret_cast<Walk1Shared*>(w1_smem);
+    float* sq = reinterpret_cast<float*>(w1_smem + ((sizeof(Walk1Shared) + 15) & ~(size_t)15));
+    const uint32_t q = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float* qv = qrows ? items + (size_t)qrows[q] * ld : queries + (size_t)q * ld;
+    const float qhdr = qh0 ? qh0[q] : 0.f;
+    for (uint32_t i = tid; i < ld; i += W1_THREADS) sq[i] = qv[i];
+    if (tid == 0) { S.produced = 0; S.done = 0; S.total = 0; S.status = 0; }
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t size = 0, produced = 0, total32 = 0;
+        unsigned long long total = 0;
+        int st = 0;
+        if (lane == 0) {
+            const unsigned long long inf_key = (unsigned long long)ordered_key(__uint_as_float(0x7f800000u)) << 32;
+            for (uint32_t r = 0; r < F.n_roots && size < W1_HEAP; ++r) heap_push(S.heap, size, inf_key | F.roots[r]);
+            if (F.n_roots > W1_HEAP) st = 2;
+        }
+        st = __shfl_sync(0xffffffffu, st, 0);
+        while (!st) {
+            size = __shfl_sync(0xffffffffu, size, 0);
+            if (total >= search_k || size == 0) break;
+            unsigned long long top = 0;
+            if (lane == 0) top = heap_pop(S.heap, size);
+            top = __shfl_sync(0xffffffffu, top, 0);
+            const uint32_t node = (uint32_t)top;
+            const float dist = key_to_dist((uint32_t)(top >> 32));
+            const int kind = node < F.n_nodes ? F.kind[node] : 0;
+            if (kind == 1) {
+                const uint32_t off = F.desc_off[node], len = F.desc_len[node];
+                if (total32 + len > W1_CAND || produced >= W1_LEAFQ) { st = 1; break; }
+                if (lane == 0) { S.lq_off[produced] = off; S.lq_len[produced] = len; S.lq_dst[produced] = total32; __threadfence_block(); S.produced = produced + 1; }
+                produced += 1; total32 += len; total += len;
+            } else if (kind == 2) {
+                const uint32_t ni = F.normal_idx[node];
+                const uint32_t lc = F.left[node], rc = F.right[node];
+                float mg = 0.0f;
+                if (ni != 0xffffffffu) {
+                    const float* nv = F.normals + (size_t)ni * ld;
+                    const float dt = exact_warp<false>(nv, sq, (int)d);
+                    mg = margin_finish(metric, dt, F.nh0[node], qhdr);
+                }
+                if (lane == 0) {
+                    if (size + 2 > W1_HEAP) st = 2;
+                    else {
+                        heap_push(S.heap, size, ((unsigned long long)ordered_key(f32_min_dev(-mg, dist)) << 32) | lc);
+                        heap_push(S.heap, size, ((unsigned long long)ordered_key(f32_min_dev(mg, dist)) << 32) | rc);
+                    }
+                }
+                st = __shfl_sync(0xffffffffu, st, 0);
+            } else st = 3;
+        }
+        if (lane == 0) { S.total = total32; S.status = st; __threadfence_block(); S.done = 1; }
+    } else {
+        // copier warps: Descendants nodes as they are published
+        const int t = tid - 32, nt = W1_THREADS - 32;
+        uint32_t e = 0;
+        for (;;) {
+            const uint32_t p = S.produced;
+            if (e < p) {
+                const uint32_t off = S.lq_off[e], len = S.lq_len[e], dst = S.lq_dst[e];
+                for (uint32_t i = t; i < len; i += nt) S.cand[dst + i] = F.desc_rows[off + i];
+                ++e;
+            } else if (S.done) { if (e >= S.produced) break; }
+            else __nanosleep(100);
+        }
+    }
+    __syncthreads();
+    const int st = S.status;
+    const uint32_t n = S.total;
+    if (st != 0 || n > cand_cap) { if (tid == 0) { status[q] = st ? st : 1; out_count[q] = 0; } return; }
+    uint32_t m = 2;
+    while (m < n) m <<= 1;
+    for (uint32_t i = n + tid; i < m; i += W1_THREADS) S.cand[i] = 0xffffffffu;
+    // bitonic sort, ascending (= ascending item ids)
+    for (uint32_t size = 2; size <= m; size <<= 1) {
+        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+            __syncthreads();
+            for (uint32_t t = tid; t < (m >> 1); t += W1_THREADS) {
+                const uint32_t i = 2 * t - (t & (stride - 1)), j = i + stride;
+                const bool up = ((i & size) == 0);
+                const uint32_t a = S.cand[i], b = S.cand[j];
+                if ((a > b) == up) { S.cand[i] = b; S.cand[j] = a; }
+            }
+        }
+    }
+    __syncthreads();
+    // unique + compaction (stable): every thread owns a contiguous slice
+    const uint32_t per = (n + W1_THREADS - 1) / W1_THREADS;
+    const uint32_t b0 = min(n, (uint32_t)tid * per), e0 = min(n, b0 + per);
+    uint32_t cnt = 0;
+    for (uint32_t i = b0; i < e0; ++i) cnt += (i == 0 || S.cand[i] != S.cand[i - 1]) ? 1u : 0u;
+    uint32_t inc = cnt;
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += y; }
+    if (lane == 31) S.scan[warp] = inc;
+    __syncthreads();
+    uint32_t base = 0, uniq = 0;
+    for (int w = 0; w < W1_THREADS / 32; ++w) { const uint32_t y = S.scan[w]; if (w < warp) base += y; uniq += y; }
+    uint32_t o = base + inc - cnt;
+    uint32_t* out = out_cand + (size_t)q * cand_cap;
+    for (uint32_t i = b0; i < e0; ++i) if (i == 0 || S.cand[i] != S.cand[i - 1]) out[o++] = S.cand[i];
+    if (tid == 0) { out_count[q] = uniq; status[q] = 0; }
+}
+
+}  // namespace ab

@@ -63,3 +63,41 @@ def sharded_build(ctx, dist, rank, world, tree_seeds, root_ids, first_free, spli
     base = node_id_bases(counts_all, first_free)
     nodes = ctx.build_trees_emit([root_ids[t] for t in mine], [base[t] for t in mine], arena=arena)
     return nodes, counts_all
+
+
+class _DevView:
+    """zero-copy torch view of a device buffer of the library"""
+
+    def __init__(self, ptr, shape, typestr="<f4"):
+        self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+def stage_and_broadcast(ctx, dist, rank, metric, dim, ids, leaf_ptrs, device, chunk_mb=256):
+    """Item staging for a multi-process (one rank per GPU) build: rank 0 decodes + uploads its host leaf values chunk by
+    chunk (arroy_b200_stage_begin / _rows / _end) and every chunk is broadcast straight out of / into the library's item
+    buffers while the next one is crossing PCIe. Still ONE logical broadcast of the item buffer, issued in
+    pieces so that only the last piece is not hidden behind the H2D copy. leaf_ptrs is only read on rank 0."""
+    import torch
+    n = len(ids)
+    ctx.stage_begin(metric, dim, ids)
+    (p_items, p_h0, p_h1), ld = ctx.device_ptrs()
+    items = torch.as_tensor(_DevView(p_items, (max(n, 1), ld)), device=device)
+    chunk_rows = max(1, (chunk_mb << 20) // (ld * 4))
+    works = []
+    for a in range(0, n, chunk_rows):
+        b = min(n, a + chunk_rows)
+        if rank == 0:
+            ctx.stage_rows(a, leaf_ptrs[a:b])       # returns when the chunk is in rank 0's HBM
+        works.append(dist.broadcast(items[a:b], src=0, async_op=True))
+    if rank == 0:
+        ctx.stage_end(headers_on_device=False)      # headers decoded from the leaf values
+    if n:
+        h0 = torch.as_tensor(_DevView(p_h0, (n,)), device=device)
+        h1 = torch.as_tensor(_DevView(p_h1, (n,)), device=device)
+        works.append(dist.broadcast(h0, src=0, async_op=True))
+        works.append(dist.broadcast(h1, src=0, async_op=True))
+    for w in works:
+        w.wait()
+    torch.cuda.synchronize()
+    if rank != 0:
+        ctx.stage_end(headers_on_device=True)

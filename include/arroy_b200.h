@@ -70,6 +70,15 @@ const char* arroy_b200_version(void);
 int32_t arroy_b200_stage_items(arroy_ctx* ctx, int32_t metric, uint32_t dim, uint64_t n,
                                const uint32_t* ids_ascending, const uint8_t* const* leaf_values);
 
+/* The same staging in pieces: _begin sizes the device buffers for n items, _rows decodes + uploads the leaf values of rows
+ * [row0, row0 + n_rows) (leaf_values[i] belongs to row row0 + i) and returns when they are in device memory, _end uploads the
+ * headers collected from the leaf values and marks the items staged (headers_on_device != 0: the caller has filled the header
+ * arrays of arroy_b200_device_ptrs itself, e.g. by a broadcast). Between _begin and _end arroy_b200_device_ptrs is valid, so a
+ * multi-GPU host can broadcast chunk k while chunk k + 1 is crossing PCIe (arroy_b200_group_stage_items does exactly that). */
+int32_t arroy_b200_stage_begin(arroy_ctx* ctx, int32_t metric, uint32_t dim, uint64_t n, const uint32_t* ids_ascending);
+int32_t arroy_b200_stage_rows(arroy_ctx* ctx, uint64_t row0, uint64_t n_rows, const uint8_t* const* leaf_values);
+int32_t arroy_b200_stage_end(arroy_ctx* ctx, int32_t headers_on_device);
+
 /* Same, from a dense host matrix (n x dim, row-major f32) and optional header arrays
  * (NULL = header as Writer::add_item would store it, i.e. D::new_header(vector),
  * src/writer.rs:388-390). Copies straight from the caller's buffer (pin it for full PCIe rate). */
@@ -306,6 +315,33 @@ int32_t arroy_b200_epochs(arroy_ctx* ctx, uint64_t out[2]);
 /* Raw device pointers of the staged items (for the NCCL broadcast of the multi-GPU path):
  * out[0] = float[n][ld] matrix, out[1] = hdr0[n], out[2] = hdr1[n] (may be 0); *out_ld = ld. */
 int32_t arroy_b200_device_ptrs(arroy_ctx* ctx, void* out[3], uint32_t* out_ld);
+
+/* ---- several GPUs of one node behind one handle -------------------------------------------------
+ * Replaces the rayon scope of src/writer.rs:568-591 for hosts with more than one device: one process, one context per
+ * device, NCCL (bound at run time) for the single data-path collective.
+ *   create_group      one context per listed device + ncclCommInitAll; fails with ERR_CUDA if a device or NCCL is missing
+ *   group_stage_items ImmutableLeafs::new for all devices: the leaf values are decoded and uploaded to devices[0] in ~256 MB
+ *                     chunks and every chunk is handed to ncclBroadcast (root = devices[0]) while the next one is still
+ *                     crossing PCIe; headers follow the same way
+ *   group_build_trees arroy_b200_build_trees with tree t built by device t mod n_dev, all devices at the same time; node ids
+ *                     and bytes are identical to a single-device build; the sink is called concurrently
+ *   group_ctx         the member context of one device (for arroy_b200_build_stats, arroy_b200_rerank, ... on that device) */
+typedef struct arroy_group arroy_group;
+int32_t arroy_b200_create_group(int32_t n_dev, const int32_t* devices, arroy_group** out);
+void arroy_b200_destroy_group(arroy_group* group);
+const char* arroy_b200_group_last_error(arroy_group* group);
+int32_t arroy_b200_group_size(arroy_group* group);
+arroy_ctx* arroy_b200_group_ctx(arroy_group* group, int32_t rank);
+int32_t arroy_b200_group_stage_items(arroy_group* group, int32_t metric, uint32_t dim, uint64_t n,
+                                     const uint32_t* ids_ascending, const uint8_t* const* leaf_values);
+int32_t arroy_b200_group_dot_preprocess(arroy_group* group, float* out_extra_dim /* n or NULL */, float* out_norm /* n or NULL */);
+int32_t arroy_b200_group_build_trees(arroy_group* group, uint32_t n_trees, const uint8_t (*tree_seeds)[32],
+                                     const uint32_t* root_ids, uint32_t first_free_node_id, uint32_t split_after,
+                                     arroy_b200_cancel_fn cancel, void* cancel_arg,
+                                     arroy_b200_node_sink sink, void* sink_arg, uint64_t* out_n_nodes);
+/* wall-clock of the last group_stage_items (ms): [0] total, [1] tail after the last H2D chunk (headers + the one broadcast
+ * that nothing hides), [2..3] reserved */
+int32_t arroy_b200_group_stage_breakdown(arroy_group* group, double out[4]);
 
 #ifdef __cplusplus
 }
