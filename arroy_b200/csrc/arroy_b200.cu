@@ -312,6 +312,32 @@ using BuiltTree = BuiltTreeView;
 
 struct Subsets { const uint32_t* rows = nullptr; const uint64_t* off = nullptr; };   // host arrays, indexed by global tree
 
+// The control kernel is compiled once per metric (and per cluster size): it is bound by instruction fetch, so every
+// instantiation only carries its own metric's code.
+template <bool SMEM_WS, int CS>
+const void* control_fn(int metric) {
+    switch (metric) {
+        case EUCLIDEAN: return reinterpret_cast<const void*>(&control_kernel<SMEM_WS, CS, EUCLIDEAN>);
+        case COSINE: return reinterpret_cast<const void*>(&control_kernel<SMEM_WS, CS, COSINE>);
+        case DOT_PRODUCT: return reinterpret_cast<const void*>(&control_kernel<SMEM_WS, CS, DOT_PRODUCT>);
+        default: return reinterpret_cast<const void*>(&control_kernel<SMEM_WS, CS, MANHATTAN>);
+    }
+}
+inline const void* control_fn(bool smem_ws, int cs, int metric) {
+    if (!smem_ws) return control_fn<false, 1>(metric);
+    return cs == 16 ? control_fn<true, 16>(metric) : (cs == 8 ? control_fn<true, 8>(metric) : control_fn<true, 1>(metric));
+}
+// launch (cluster dimension cs > 1: thread-block cluster of cs CTAs per tree)
+inline void launch_control(const void* fn, unsigned n_trees, int cs, size_t smem, cudaStream_t s, BuildParams& P, uint32_t tree_base) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(n_trees * (unsigned)cs); cfg.blockDim = dim3(CTRL_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    cfg.attrs = at; cfg.numAttrs = 0;
+    if (cs > 1) { at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = (unsigned)cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1; cfg.numAttrs = 1; }
+    void* args[2] = {&P, &tree_base};
+    CK(cudaLaunchKernelExC(&cfg, fn, args));
+}
+
 void build_wave(arroy_ctx* c, size_t wave_no, uint32_t t0, uint32_t tw, const uint8_t (*seeds)[32], uint32_t K, uint32_t cap_mult,
                 arroy_b200_cancel_fn cancel, void* cancel_arg, std::vector<BuiltTree>& out_trees, uint32_t& out_pool_stride, Subsets sub = Subsets{}) {
     const uint64_t n = c->n;
@@ -391,7 +417,7 @@ void build_wave(arroy_ctx* c, size_t wave_no, uint32_t t0, uint32_t tw, const ui
     c->n_launches += 2;  // + finalize_kernel below
 
     const size_t ctrl_smem = use_smem ? ws_bytes : 0;
-    if (ctrl_smem > 48 * 1024) CK(cudaFuncSetAttribute(control_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctrl_smem));
+    if (ctrl_smem > 48 * 1024) CK(cudaFuncSetAttribute(control_fn(true, 1, c->metric), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctrl_smem));
     const size_t wsmem = work_smem(ld, (int)tw);
     if (wsmem > 48 * 1024) CK(cudaFuncSetAttribute(work_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
     const int work_grid = c->sm_count * 3;
@@ -420,26 +446,18 @@ void build_wave(arroy_ctx* c, size_t wave_no, uint32_t t0, uint32_t tw, const ui
         else if (c->dim <= 256) cluster = tw <= 8 ? 16 : (tw <= 16 ? 8 : 1);
     }
     if (cluster > 1) {
-        if (cluster == 8) CK(cudaFuncSetAttribute(control_kernel<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctrl_smem));
-        else {
-            CK(cudaFuncSetAttribute(control_kernel<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctrl_smem));
-            CK(cudaFuncSetAttribute(control_kernel<true, 16>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-        }
+        CK(cudaFuncSetAttribute(control_fn(true, cluster, c->metric), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctrl_smem));
+        if (cluster == 16) CK(cudaFuncSetAttribute(control_fn(true, 16, c->metric), cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     }
+    const void* ctrl1 = control_fn(use_smem != 0, 1, c->metric);
+    const void* ctrlc = control_fn(use_smem != 0, cluster, c->metric);
 
     auto launch_step = [&](cudaStream_t s) {  // lockstep: all trees per launch
-        if (use_smem) control_kernel<true, 1><<<tw, CTRL_THREADS, ctrl_smem, s>>>(P, 0u); else control_kernel<false, 1><<<tw, CTRL_THREADS, 0, s>>>(P, 0u);
+        launch_control(ctrl1, tw, 1, ctrl_smem, s, P, 0u);
         work_kernel<<<work_grid, WORK_THREADS, wsmem, s>>>(P.jobs, (int)tw, P.items, P.ih0, P.d, P.ld, P.metric, interleave);
     };
     auto launch_tree_step = [&](uint32_t t, cudaStream_t s) {  // async: one tree per launch
-        if (cluster > 1) {
-            cudaLaunchConfig_t cfg{};
-            cfg.gridDim = dim3((unsigned)cluster); cfg.blockDim = dim3(CTRL_THREADS); cfg.dynamicSmemBytes = ctrl_smem; cfg.stream = s;
-            cudaLaunchAttribute at[1];
-            at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = (unsigned)cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-            cfg.attrs = at; cfg.numAttrs = 1;
-            if (cluster == 8) CK(cudaLaunchKernelEx(&cfg, control_kernel<true, 8>, P, t)); else CK(cudaLaunchKernelEx(&cfg, control_kernel<true, 16>, P, t));
-        } else if (use_smem) control_kernel<true, 1><<<1, CTRL_THREADS, ctrl_smem, s>>>(P, t); else control_kernel<false, 1><<<1, CTRL_THREADS, 0, s>>>(P, t);
+        launch_control(ctrlc, 1, cluster, ctrl_smem, s, P, t);
         work_kernel<<<tree_grid, WORK_THREADS, wsmem1, s>>>(P.jobs + t, 1, P.items, P.ih0, P.d, P.ld, P.metric, 0);
     };
     if (!lockstep) {
@@ -502,7 +520,7 @@ void build_wave(arroy_ctx* c, size_t wave_no, uint32_t t0, uint32_t tw, const ui
         if (use_graph) CK(cudaGraphLaunch(gexec, c->stream));
         else if (profile) {
             for (int i = 0; i < steps_per_batch; ++i) {
-                if (use_smem) control_kernel<true, 1><<<tw, CTRL_THREADS, ctrl_smem, c->stream>>>(P, 0u); else control_kernel<false, 1><<<tw, CTRL_THREADS, 0, c->stream>>>(P, 0u);
+                launch_control(ctrl1, tw, 1, ctrl_smem, c->stream, P, 0u);
                 CK(cudaEventRecord(pev[2 * i], c->stream));
                 work_kernel<<<work_grid, WORK_THREADS, wsmem, c->stream>>>(P.jobs, (int)tw, P.items, P.ih0, P.d, P.ld, P.metric, interleave);
                 CK(cudaEventRecord(pev[2 * i + 1], c->stream));
@@ -947,15 +965,15 @@ void do_rerank_batch(arroy_ctx* c, uint32_t nq, const float* queries, const floa
 
 // single-CTA create_split over a host row list (exposes D::create_split for parity tests and for
 // hosts that keep the DFS on their side)
-template <bool SMEM_WS>
+template <bool SMEM_WS, int METRIC>
 __global__ void __launch_bounds__(CTRL_THREADS, 1) create_split_kernel(BuildParams P, const uint32_t* rows, uint32_t len, const uint32_t* key8, uint64_t pos, float* slot, uint64_t* out_pos) {
     extern __shared__ __align__(16) unsigned char cs_smem[];
     __shared__ TwoMeansShared TM;
     __shared__ Rng rng;
     if (threadIdx.x == 0) rng.init(key8, pos);
     __syncthreads();
-    if (SMEM_WS) create_split_cta(P, rng, rows, len, reinterpret_cast<float*>(cs_smem), TM, slot);
-    else create_split_cta(P, rng, rows, len, P.scratch, TM, slot);
+    if (SMEM_WS) create_split_cta<METRIC>(P, rng, rows, len, reinterpret_cast<float*>(cs_smem), TM, slot);
+    else create_split_cta<METRIC>(P, rng, rows, len, P.scratch, TM, slot);
     if (threadIdx.x == 0) *out_pos = rng.pos;
 }
 
@@ -1262,13 +1280,20 @@ int32_t arroy_b200_create_split(arroy_ctx* c, const uint32_t rng_key[8], uint64_
         if (P.spec) ws_bytes = (size_t)WS_VECS_SPEC * ld * 4;
         P.scratch = reinterpret_cast<float*>(c->s_misc.as<uint8_t>() + 64);
         size_t smem = P.use_smem_ws ? ws_bytes : 0;
-        if (smem > 48 * 1024) CK(cudaFuncSetAttribute(create_split_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        if (P.use_smem_ws)
-            create_split_kernel<true><<<1, CTRL_THREADS, smem, c->stream>>>(P, c->s_rows.as<uint32_t>(), (uint32_t)n_rows, c->s_misc.as<uint32_t>(), *rng_word_pos,
-                                                                            c->s_normal.as<float>(), reinterpret_cast<uint64_t*>(c->s_misc.as<uint8_t>() + 32));
-        else
-            create_split_kernel<false><<<1, CTRL_THREADS, 0, c->stream>>>(P, c->s_rows.as<uint32_t>(), (uint32_t)n_rows, c->s_misc.as<uint32_t>(), *rng_word_pos,
-                                                                          c->s_normal.as<float>(), reinterpret_cast<uint64_t*>(c->s_misc.as<uint8_t>() + 32));
+        const void* fn = nullptr;
+        switch (c->metric) {
+            case EUCLIDEAN: fn = P.use_smem_ws ? (const void*)&create_split_kernel<true, EUCLIDEAN> : (const void*)&create_split_kernel<false, EUCLIDEAN>; break;
+            case COSINE: fn = P.use_smem_ws ? (const void*)&create_split_kernel<true, COSINE> : (const void*)&create_split_kernel<false, COSINE>; break;
+            case DOT_PRODUCT: fn = P.use_smem_ws ? (const void*)&create_split_kernel<true, DOT_PRODUCT> : (const void*)&create_split_kernel<false, DOT_PRODUCT>; break;
+            default: fn = P.use_smem_ws ? (const void*)&create_split_kernel<true, MANHATTAN> : (const void*)&create_split_kernel<false, MANHATTAN>; break;
+        }
+        if (smem > 48 * 1024) CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        {
+            const uint32_t* d_rows = c->s_rows.as<uint32_t>(); uint32_t len32 = (uint32_t)n_rows; const uint32_t* d_key = c->s_misc.as<uint32_t>(); uint64_t pos0 = *rng_word_pos;
+            float* d_slot = c->s_normal.as<float>(); uint64_t* d_pos = reinterpret_cast<uint64_t*>(c->s_misc.as<uint8_t>() + 32);
+            void* args[7] = {&P, &d_rows, &len32, &d_key, &pos0, &d_slot, &d_pos};
+            CK(cudaLaunchKernel(fn, dim3(1), dim3(CTRL_THREADS), args, smem, c->stream));
+        }
         CK(cudaGetLastError());
         std::vector<float> slot(ld + NORMAL_HDR);
         uint64_t new_pos = 0;

@@ -107,6 +107,7 @@ struct TwoMeansShared {
     long long tlast;
     // speculative two_means
     float G[12][12];        // approximate dots between the 12 gathered vectors (0 = p, 1 = q after normalize, 2.. = the ten k)
+    float Gp[4][6][16];     // its partial sums: K-slice x block pair x 4 x 4
     float vdot[32];         // exact dots of the verification pass
     int choice[10];         // per iteration: 0 = nothing moved, 1 = p moved, 2 = q moved
     int ready;              // iterations whose choice has been published by the speculating warp
@@ -166,46 +167,64 @@ __device__ __forceinline__ void exact_warp_ab_aa(const float* a, const float* b,
 //      not (|di - dj| below the prediction's rounding noise: rare), the caller runs the sequential loop instead.
 // ws: slots 0 / 1 = p / q (normalized for the angular metrics), 2..11 = the ten k, 14 + it = centroid produced by iteration it.
 // On success pslot / qslot are the slots of the final centroids.
-template <bool EUCLID>
+template <int METRIC>
 __device__ __forceinline__ bool spec_two_means(const BuildParams& P, float* ws, TwoMeansShared& S, int& pslot, int& qslot) {
+    constexpr bool EUCLID = METRIC == EUCLIDEAN;
+    constexpr int metric = METRIC;
     const unsigned full = 0xffffffffu;
-    const int d = (int)P.d, ld = (int)P.ld, metric = P.metric;
+    const int d = (int)P.d, ld = (int)P.ld;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, grp = lane >> 3, g8 = lane & 7;
     const bool cosine = !EUCLID;
-    for (int i = tid; i < 144; i += CTRL_THREADS) (&S.G[0][0])[i] = 0.f;
     if (tid == 0) { S.ready = 0; S.mismatch = 0; }
-    __syncthreads();
-    // (1a) Gram matrix, any summation order: 6 pairs of 4-vector blocks x 4 K-slices = 24 jobs of 16 dots each
+    // (1a) Gram matrix, any summation order: 6 pairs of 4-vector blocks x 4 K-slices = 24 jobs of 16 dots each; the 8 lanes of
+    // a job fold their partial sums with a halving exchange (14 shuffles, every lane ends up with 2 of the 16 sums)
     if (warp < 6) {
         const int job = warp * 4 + grp, pair = job >> 2, slice = job & 3;
         const int X = pair < 3 ? 0 : (pair < 5 ? 1 : 2);
         const int Y = pair < 3 ? pair : (pair < 5 ? pair - 2 : 2);
-        float acc[4][4];
+        float acc[16];
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+        for (int i = 0; i < 16; ++i) acc[i] = 0.f;
         const int nch = ld >> 5;
+        const float* xb = ws + (size_t)(4 * X) * ld + g8 * 4;
+        const float* yb = ws + (size_t)(4 * Y) * ld + g8 * 4;
+#pragma unroll 1
         for (int c = slice; c < nch; c += 4) {
             float4 xa[4], ya[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) xa[i] = *reinterpret_cast<const float4*>(ws + (size_t)(4 * X + i) * ld + c * 32 + g8 * 4);
+            for (int i = 0; i < 4; ++i) xa[i] = *reinterpret_cast<const float4*>(xb + (size_t)i * ld + c * 32);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) ya[j] = *reinterpret_cast<const float4*>(ws + (size_t)(4 * Y + j) * ld + c * 32 + g8 * 4);
+            for (int j = 0; j < 4; ++j) ya[j] = *reinterpret_cast<const float4*>(yb + (size_t)j * ld + c * 32);
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
-                    acc[i][j] = fmaf(xa[i].x, ya[j].x, fmaf(xa[i].y, ya[j].y, fmaf(xa[i].z, ya[j].z, fmaf(xa[i].w, ya[j].w, acc[i][j]))));
+                    acc[i * 4 + j] = fmaf(xa[i].x, ya[j].x, fmaf(xa[i].y, ya[j].y, fmaf(xa[i].z, ya[j].z, fmaf(xa[i].w, ya[j].w, acc[i * 4 + j]))));
         }
+        // halving exchange: after the step with partner distance 4 a lane keeps 8 sums, then 4, then 2
+        {
+            const bool hi4 = (g8 & 4) != 0;
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < 8; ++i) { const float send = hi4 ? acc[i] : acc[8 + i], keep = hi4 ? acc[8 + i] : acc[i]; acc[i] = keep + __shfl_xor_sync(full, send, 4); }
+            const bool hi2 = (g8 & 2) != 0;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                float v = acc[i][j];
-                v += __shfl_xor_sync(full, v, 4); v += __shfl_xor_sync(full, v, 2); v += __shfl_xor_sync(full, v, 1);
-                if (g8 == 0) { atomicAdd(&S.G[4 * X + i][4 * Y + j], v); if (X != Y) atomicAdd(&S.G[4 * Y + j][4 * X + i], v); }
-            }
+            for (int i = 0; i < 4; ++i) { const float send = hi2 ? acc[i] : acc[4 + i], keep = hi2 ? acc[4 + i] : acc[i]; acc[i] = keep + __shfl_xor_sync(full, send, 2); }
+            const bool hi1 = (g8 & 1) != 0;
+#pragma unroll
+            for (int i = 0; i < 2; ++i) { const float send = hi1 ? acc[i] : acc[2 + i], keep = hi1 ? acc[2 + i] : acc[i]; acc[i] = keep + __shfl_xor_sync(full, send, 1); }
+            // lane g8 now holds sums number 8 * bit2 + 4 * bit1 + 2 * bit0 + {0, 1} of its job
+            const int e0 = (hi4 ? 8 : 0) + (hi2 ? 4 : 0) + (hi1 ? 2 : 0);
+            S.Gp[slice][pair][e0] = acc[0]; S.Gp[slice][pair][e0 + 1] = acc[1];
+        }
+    }
+    __syncthreads();
+    if (tid < 96) {   // G[4X + i][4Y + j] (and its mirror) = sum of the four K-slices
+        const int pair = tid >> 4, e = tid & 15, i = e >> 2, j = e & 3;
+        const int X = pair < 3 ? 0 : (pair < 5 ? 1 : 2);
+        const int Y = pair < 3 ? pair : (pair < 5 ? pair - 2 : 2);
+        const float v = (S.Gp[0][pair][e] + S.Gp[1][pair][e]) + (S.Gp[2][pair][e] + S.Gp[3][pair][e]);
+        S.G[4 * X + i][4 * Y + j] = v;
+        if (X != Y) S.G[4 * Y + j][4 * X + i] = v;
     }
     __syncthreads();
     TP_MARK(S, TP_TM_DOT);
@@ -214,32 +233,35 @@ __device__ __forceinline__ bool spec_two_means(const BuildParams& P, float* ws, 
         float pk = lane < 10 ? S.G[0][2 + lane] : 0.f, qk = lane < 10 ? S.G[1][2 + lane] : 0.f;
         float pp = S.G[0][0], qq = S.G[1][1], ic = 1.f, jc = 1.f;
         const float pe = S.php[0], qe = S.phq[0];   // DotProduct: extra_dim of the centroids (update_mean leaves headers alone)
+        // per-iteration constants, one lane each (approximate reciprocals are fine: this only predicts)
+        const int li = lane < 10 ? lane : 0;
+        const float my_norm = cosine ? S.nk[2 + li] : 1.f;
+        const float my_inv = __fdividef(1.f, my_norm);
+        const float my_kk = S.G[2 + li][2 + li];
+        const float my_a = (metric == COSINE) ? __fdividef(1.f, S.h0[2 + li]) : S.h0[2 + li];   // Cosine: 1 / |k| (stored header); DotProduct: k.extra_dim
+        const float my_b = S.h1[2 + li];                                                    // DotProduct: k's norm header
+        const bool my_ok = !(my_norm != my_norm || my_norm <= 0.f);
 #pragma unroll 1
         for (int it = 0; it < 10; ++it) {
             const float pki = __shfl_sync(full, pk, it), qki = __shfl_sync(full, qk, it);
-            const float kk = S.G[2 + it][2 + it];
+            const float kk = __shfl_sync(full, my_kk, it), ka = __shfl_sync(full, my_a, it), inv = __shfl_sync(full, my_inv, it);
             float di, dj;
             if (EUCLID) { di = ic * (pp - 2.f * pki + kk); dj = jc * (qq - 2.f * qki + kk); }
             else if (metric == COSINE) {
-                const float kn0 = S.h0[2 + it];
-                const float dp = sqrtf(pp) * kn0, dq = sqrtf(qq) * kn0;
-                const float cp = fminf(1.f, fmaxf(-1.f, pki / dp)), cq = fminf(1.f, fmaxf(-1.f, qki / dq));
-                di = dp > 1.1920928955078125e-07f ? ic * (1.f - cp) * 0.5f : 0.f;
-                dj = dq > 1.1920928955078125e-07f ? jc * (1.f - cq) * 0.5f : 0.f;
+                const float cp = fminf(1.f, fmaxf(-1.f, pki * rsqrtf(pp) * ka)), cq = fminf(1.f, fmaxf(-1.f, qki * rsqrtf(qq) * ka));
+                di = ic * (1.f - cp); dj = jc * (1.f - cq);
             } else {
-                const float ke = S.h0[2 + it], kh1 = S.h1[2 + it];
-                const float mp = pp * kh1, mq = qq * kh1;
-                di = mp >= 1.17549435e-38f ? ic * (2.f - 2.f * (pki + pe * ke) / sqrtf(mp)) : ic * 2.f;
-                dj = mq >= 1.17549435e-38f ? jc * (2.f - 2.f * (qki + qe * ke) / sqrtf(mq)) : jc * 2.f;
+                const float kb = __shfl_sync(full, my_b, it);
+                const float mp = pp * kb, mq = qq * kb;
+                di = mp >= 1.17549435e-38f ? ic * (2.f - 2.f * (pki + pe * ka) * rsqrtf(mp)) : ic * 2.f;
+                dj = mq >= 1.17549435e-38f ? jc * (2.f - 2.f * (qki + qe * ka) * rsqrtf(mq)) : jc * 2.f;
             }
-            const float norm = cosine ? S.nk[2 + it] : 1.f;
             int ch = 0;
-            if (!(norm != norm || norm <= 0.f)) ch = di < dj ? 1 : (dj < di ? 2 : 0);
+            if (__shfl_sync(full, (int)my_ok, it)) ch = di < dj ? 1 : (dj < di ? 2 : 0);
             if (ch) {   // c' = (c * cnt + k / norm) / (cnt + 1) — update_mean, mod.rs:86-94
-                const float inv = 1.f / norm;
-                const float g = lane < 10 ? S.G[2 + it][2 + lane] * inv : 0.f;
-                if (ch == 1) { const float c1 = ic + 1.f, r = 1.f / c1; pk = (ic * pk + g) * r; pp = (ic * ic * pp + 2.f * ic * pki * inv + kk * inv * inv) * r * r; ic = c1; }
-                else { const float c1 = jc + 1.f, r = 1.f / c1; qk = (jc * qk + g) * r; qq = (jc * jc * qq + 2.f * jc * qki * inv + kk * inv * inv) * r * r; jc = c1; }
+                const float g = S.G[2 + it][2 + li] * inv;
+                if (ch == 1) { const float c1 = ic + 1.f, r = __fdividef(1.f, c1); pk = (ic * pk + g) * r; pp = (ic * ic * pp + 2.f * ic * pki * inv + kk * inv * inv) * r * r; ic = c1; }
+                else { const float c1 = jc + 1.f, r = __fdividef(1.f, c1); qk = (jc * qk + g) * r; qq = (jc * jc * qq + 2.f * jc * qki * inv + kk * inv * inv) * r * r; jc = c1; }
             }
             if (lane == 0) { *(volatile int*)&S.choice[it] = ch; __threadfence_block(); *(volatile int*)&S.ready = it + 1; }
         }
@@ -318,6 +340,95 @@ __device__ __forceinline__ bool spec_two_means(const BuildParams& P, float* ws, 
     return true;
 }
 
+// The sequential two_means loop (src/distance/mod.rs:146-168), in place on ws[0] / ws[1]: Manhattan, d < 32, workspaces too
+// big for the speculative path, and the rare mis-speculation. Each iteration is ONE dot phase: warp 0 computes p.k and — for a
+// centroid that was just moved — its D::init dot, warp 1 the same for q, then one barrier, the element-wise update_mean on all
+// threads, one barrier. Out of line: it is not on the usual path and the control kernel is instruction-fetch bound.
+template <int METRIC>
+__device__ __noinline__ void two_means_sequential(const BuildParams& P, float* ws, TwoMeansShared& S) {
+    constexpr int metric = METRIC;
+    constexpr bool cosine = (METRIC == COSINE || METRIC == DOT_PRODUCT);
+    const int d = (int)P.d, ld = (int)P.ld;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    float* p = ws; float* q = ws + ld;
+    float* sc0 = ws + (size_t)12 * ld; float* sc1 = ws + (size_t)13 * ld;
+    float ic = 1.0f, jc = 1.0f;
+    bool p_dirty = cosine, q_dirty = cosine;   // D::init pending (cosine.rs:69-71, dot_product.rs:94-96)
+    // (kept rolled: the serial path runs on one or two warps, whose speed is set by instruction fetch —
+    // ten unrolled copies of this body never hit the instruction cache)
+#pragma unroll 1
+    for (int it = 0; it < 10; ++it) {
+        const float* k = ws + (size_t)(2 + it) * ld;
+        const float kh0 = S.h0[2 + it], kh1 = S.h1[2 + it];
+        if (metric == MANHATTAN) {  // manhattan.rs:44-46: strictly sequential sum of |p - k|
+            for (int i = tid; i < d; i += blockDim.x) { sc0[i] = fabsf(__fsub_rn(p[i], k[i])); sc1[i] = fabsf(__fsub_rn(q[i], k[i])); }
+            __syncthreads();
+            if (tid < 2) {
+                const float* t = tid ? sc1 : sc0;
+                float s = 0.0f;
+                int i = 0;
+                for (; i + 8 <= d; i += 8) {
+                    float t0 = t[i], t1 = t[i + 1], t2 = t[i + 2], t3 = t[i + 3], t4 = t[i + 4], t5 = t[i + 5], t6 = t[i + 6], t7 = t[i + 7];
+                    s = __fadd_rn(s, t0); s = __fadd_rn(s, t1); s = __fadd_rn(s, t2); s = __fadd_rn(s, t3);
+                    s = __fadd_rn(s, t4); s = __fadd_rn(s, t5); s = __fadd_rn(s, t6); s = __fadd_rn(s, t7);
+                }
+                for (; i < d; ++i) s = __fadd_rn(s, t[i]);
+                S.res[it & 1][tid] = __fmul_rn(tid ? jc : ic, s);
+            }
+        } else if (warp < 2) {
+            // warp 0: p.k and (after a move of p) p.p; warp 1: q.k and q.q — lane l = accumulator lane l, so both
+            // sides run at the same time on two schedulers; lane 0 of each warp finishes its side.
+            const bool qs = warp == 1;
+            const float* a = qs ? q : p;
+            float xk, xx;
+            if (metric == EUCLIDEAN) exact_warp_ab_aa<true>(a, k, d, xk, xx); else exact_warp_ab_aa<false>(a, k, d, xk, xx);
+            TP_MARK(S, 14);
+            if (lane == 0) {
+                float* hdr = qs ? S.phq : S.php;
+                float h0v = hdr[0], h1v = hdr[1];
+                if (qs ? q_dirty : p_dirty) { if (metric == COSINE) h0v = __fsqrt_rn(xx); else h1v = xx; hdr[0] = h0v; hdr[1] = h1v; }
+                float dv;   // D::non_built_distance — mod.rs:54-56 (= built_distance) except dot_product.rs:58-70
+                if (metric == EUCLIDEAN) dv = xk;
+                else if (metric == COSINE) dv = built_finish(COSINE, xk, h0v, kh0);
+                else {
+                    const float a1 = __fadd_rn(xk, __fmul_rn(h0v, kh0));
+                    const float m1 = __fmul_rn(h1v, kh1);
+                    dv = (m1 >= 1.17549435e-38f) ? __fsub_rn(2.0f, __fdiv_rn(__fmul_rn(2.0f, a1), __fsqrt_rn(m1))) : 2.0f;
+                }
+                S.res[it & 1][qs ? 1 : 0] = __fmul_rn(qs ? jc : ic, dv);
+            }
+            TP_MARK(S, 15);
+        } else if (cosine) {
+            // meanwhile the other warps form k / norm for update_mean (mod.rs:86-94): it does not depend on
+            // the centroids, so the division leaves the critical path
+            const float nrm = S.nk[2 + it];
+            for (int i = tid - 64; i < d; i += CTRL_THREADS - 64) sc1[i] = __fdiv_rn(k[i], nrm);
+        }
+        p_dirty = false; q_dirty = false;
+        __syncthreads();
+        TP_MARK(S, TP_TM_DOT);
+        const float di = S.res[it & 1][0], dj = S.res[it & 1][1];
+        const float norm = cosine ? S.nk[2 + it] : 1.0f;
+        if (norm != norm || norm <= 0.0f) continue;
+        const float* kn = cosine ? sc1 : k;          // k / norm (norm == 1 for Euclidean / Manhattan: k itself)
+        if (di < dj || dj < di) {                    // update_mean(c, k, norm, count) — mod.rs:86-94; D::init follows in the next dot phase
+            const bool up = di < dj;
+            float* cen = up ? p : q;
+            const float cnt = up ? ic : jc, c1 = __fadd_rn(cnt, 1.0f);
+            for (int i0 = tid; i0 < d; i0 += 4 * CTRL_THREADS) {   // four independent chains per thread
+                float v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { const int i = i0 + u * CTRL_THREADS; if (i < d) v[u] = __fdiv_rn(__fadd_rn(__fmul_rn(cen[i], cnt), cosine ? kn[i] : __fdiv_rn(kn[i], norm)), c1); }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { const int i = i0 + u * CTRL_THREADS; if (i < d) cen[i] = v[u]; }
+            }
+            if (up) { ic = c1; p_dirty = cosine; } else { jc = c1; q_dirty = cosine; }
+            __syncthreads();
+            TP_MARK(S, TP_TM_UPD);
+        }
+    }
+}
+
 __device__ __forceinline__ float norm_leaf_group(int metric, const float* v, float h0, int d) {
     float dot = exact_group8<false>(v, v, d);
     if (metric == DOT_PRODUCT) return __fsqrt_rn(__fadd_rn(dot, __fmul_rn(h0, h0)));  // dot_product.rs:72-75
@@ -332,11 +443,13 @@ __device__ __forceinline__ float norm_leaf_group(int metric, const float* v, flo
 // is ONE dot phase: warp 0 computes p.k, q.k and — for a centroid that was just moved — its D::init
 // dot (p.p / q.q) on four 8-lane groups at the same time, then one barrier, the element-wise
 // update_mean on all threads, one barrier.
+template <int METRIC>
 __device__ __forceinline__ void create_split_cta(const BuildParams& P, Rng& rng /* thread 0 only */, const uint32_t* seg, uint32_t len,
                                                  float* ws, TwoMeansShared& S, float* slot_ptr) {
-    const int d = (int)P.d, ld = (int)P.ld, metric = P.metric;
+    constexpr int metric = METRIC;
+    constexpr bool cosine = (METRIC == COSINE || METRIC == DOT_PRODUCT);
+    const int d = (int)P.d, ld = (int)P.ld;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, grp = lane >> 3;
-    const bool cosine = (metric == COSINE || metric == DOT_PRODUCT);
     // All RNG draws of the attempt first: they do not depend on the data. choose_two = index::sample(len, 2)
     // = gen_range(0..=len-2), gen_range(0..=len-1); then ten gen_range(0..=len-1). rand 0.8.5's sample_single_inclusive accepts a
     // word v iff low32(v * range) <= zone with zone = (range << lzcnt(range)) - 1 — a deliberately loose zone: between half and
@@ -430,88 +543,14 @@ __device__ __forceinline__ void create_split_cta(const BuildParams& P, Rng& rng 
     __syncthreads();
     TP_MARK(S, TP_NORMS);
     bool spec_done = false;
-    if (P.spec && metric != MANHATTAN && d >= 32) {
-        int ps = 0, qs = 1;
-        spec_done = (metric == EUCLIDEAN) ? spec_two_means<true>(P, ws, S, ps, qs) : spec_two_means<false>(P, ws, S, ps, qs);
-        if (spec_done) { p = ws + (size_t)ps * ld; q = ws + (size_t)qs * ld; }
-    }
-    if (!spec_done) {
-    float ic = 1.0f, jc = 1.0f;
-    bool p_dirty = cosine, q_dirty = cosine;   // D::init pending (cosine.rs:69-71, dot_product.rs:94-96)
-    // (kept rolled: the serial path runs on one or two warps, whose speed is set by instruction fetch —
-    // ten unrolled copies of this body never hit the instruction cache)
-#pragma unroll 1
-    for (int it = 0; it < 10; ++it) {
-        const float* k = ws + (size_t)(2 + it) * ld;
-        const float kh0 = S.h0[2 + it], kh1 = S.h1[2 + it];
-        if (metric == MANHATTAN) {  // manhattan.rs:44-46: strictly sequential sum of |p - k|
-            for (int i = tid; i < d; i += blockDim.x) { sc0[i] = fabsf(__fsub_rn(p[i], k[i])); sc1[i] = fabsf(__fsub_rn(q[i], k[i])); }
-            __syncthreads();
-            if (tid < 2) {
-                const float* t = tid ? sc1 : sc0;
-                float s = 0.0f;
-                int i = 0;
-                for (; i + 8 <= d; i += 8) {
-                    float t0 = t[i], t1 = t[i + 1], t2 = t[i + 2], t3 = t[i + 3], t4 = t[i + 4], t5 = t[i + 5], t6 = t[i + 6], t7 = t[i + 7];
-                    s = __fadd_rn(s, t0); s = __fadd_rn(s, t1); s = __fadd_rn(s, t2); s = __fadd_rn(s, t3);
-                    s = __fadd_rn(s, t4); s = __fadd_rn(s, t5); s = __fadd_rn(s, t6); s = __fadd_rn(s, t7);
-                }
-                for (; i < d; ++i) s = __fadd_rn(s, t[i]);
-                S.res[it & 1][tid] = __fmul_rn(tid ? jc : ic, s);
-            }
-        } else if (warp < 2) {
-            // warp 0: p.k and (after a move of p) p.p; warp 1: q.k and q.q — lane l = accumulator lane l, so both
-            // sides run at the same time on two schedulers; lane 0 of each warp finishes its side.
-            const bool qs = warp == 1;
-            const float* a = qs ? q : p;
-            float xk, xx;
-            if (metric == EUCLIDEAN) exact_warp_ab_aa<true>(a, k, d, xk, xx); else exact_warp_ab_aa<false>(a, k, d, xk, xx);
-            TP_MARK(S, 14);
-            if (lane == 0) {
-                float* hdr = qs ? S.phq : S.php;
-                float h0v = hdr[0], h1v = hdr[1];
-                if (qs ? q_dirty : p_dirty) { if (metric == COSINE) h0v = __fsqrt_rn(xx); else h1v = xx; hdr[0] = h0v; hdr[1] = h1v; }
-                float dv;   // D::non_built_distance — mod.rs:54-56 (= built_distance) except dot_product.rs:58-70
-                if (metric == EUCLIDEAN) dv = xk;
-                else if (metric == COSINE) dv = built_finish(COSINE, xk, h0v, kh0);
-                else {
-                    const float a1 = __fadd_rn(xk, __fmul_rn(h0v, kh0));
-                    const float m1 = __fmul_rn(h1v, kh1);
-                    dv = (m1 >= 1.17549435e-38f) ? __fsub_rn(2.0f, __fdiv_rn(__fmul_rn(2.0f, a1), __fsqrt_rn(m1))) : 2.0f;
-                }
-                S.res[it & 1][qs ? 1 : 0] = __fmul_rn(qs ? jc : ic, dv);
-            }
-            TP_MARK(S, 15);
-        } else if (cosine) {
-            // meanwhile the other warps form k / norm for update_mean (mod.rs:86-94): it does not depend on
-            // the centroids, so the division leaves the critical path
-            const float nrm = S.nk[2 + it];
-            for (int i = tid - 64; i < d; i += CTRL_THREADS - 64) sc1[i] = __fdiv_rn(k[i], nrm);
-        }
-        p_dirty = false; q_dirty = false;
-        __syncthreads();
-        TP_MARK(S, TP_TM_DOT);
-        const float di = S.res[it & 1][0], dj = S.res[it & 1][1];
-        const float norm = cosine ? S.nk[2 + it] : 1.0f;
-        if (norm != norm || norm <= 0.0f) continue;
-        const float* kn = cosine ? sc1 : k;          // k / norm (norm == 1 for Euclidean / Manhattan: k itself)
-        if (di < dj || dj < di) {                    // update_mean(c, k, norm, count) — mod.rs:86-94; D::init follows in the next dot phase
-            const bool up = di < dj;
-            float* cen = up ? p : q;
-            const float cnt = up ? ic : jc, c1 = __fadd_rn(cnt, 1.0f);
-            for (int i0 = tid; i0 < d; i0 += 4 * CTRL_THREADS) {   // four independent chains per thread
-                float v[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) { const int i = i0 + u * CTRL_THREADS; if (i < d) v[u] = __fdiv_rn(__fadd_rn(__fmul_rn(cen[i], cnt), cosine ? kn[i] : __fdiv_rn(kn[i], norm)), c1); }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) { const int i = i0 + u * CTRL_THREADS; if (i < d) cen[i] = v[u]; }
-            }
-            if (up) { ic = c1; p_dirty = cosine; } else { jc = c1; q_dirty = cosine; }
-            __syncthreads();
-            TP_MARK(S, TP_TM_UPD);
+    if constexpr (METRIC != MANHATTAN) {
+        if (P.spec && d >= 32) {
+            int ps = 0, qs = 1;
+            spec_done = spec_two_means<METRIC>(P, ws, S, ps, qs);
+            if (spec_done) { p = ws + (size_t)ps * ld; q = ws + (size_t)qs * ld; }
         }
     }
-    }
+    if (!spec_done) two_means_sequential<METRIC>(P, ws, S);
     __syncthreads();
     TP_MARK(S, TP_TWOMEANS);
     // normal = normalize(p - q) (+ bias / extra_dim) — euclidean.rs:59-75, manhattan.rs:62-78,
@@ -554,7 +593,7 @@ __device__ __forceinline__ void create_split_cta(const BuildParams& P, Rng& rng 
 // PART_BATCH sub-blocks of blockDim ids: all loads of the round are issued before any is used, one
 // barrier per round. sm_pw: 2 * PART_BATCH * 8 + 2 uint32.
 constexpr int PART_BATCH = 8;
-__device__ void partition_inline(const uint32_t* __restrict__ src, const uint8_t* __restrict__ flags, uint32_t* __restrict__ dst, uint32_t len, uint32_t total_left, uint32_t* sm_pw) {
+__device__ __noinline__ void partition_inline(const uint32_t* __restrict__ src, const uint8_t* __restrict__ flags, uint32_t* __restrict__ dst, uint32_t len, uint32_t total_left, uint32_t* sm_pw) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t left_before = 0;
     for (uint32_t base = 0; base < len; base += PART_BATCH * CTRL_THREADS) {
@@ -657,7 +696,7 @@ __device__ __forceinline__ void cluster_scan_share(const BuildParams& P, const J
     for (uint32_t u = rank; u < units; u += CS) scan_unit(jb, u, P.items, P.ih0, P.d, P.ld, P.metric, sm_normal, nh0, sm_count);
 }
 
-template <bool SMEM_WS, int CS>
+template <bool SMEM_WS, int CS, int METRIC>
 __global__ void __launch_bounds__(CTRL_THREADS, 1) control_kernel(BuildParams P, uint32_t tree_base) {
     static_assert(CS == 1 || SMEM_WS, "the cluster path keeps the normal in the shared-memory workspace");
     extern __shared__ __align__(16) unsigned char ctrl_smem[];
@@ -817,8 +856,8 @@ __global__ void __launch_bounds__(CTRL_THREADS, 1) control_kernel(BuildParams P,
         uint32_t* dst = (f.parity ? perm0 : perm1) + f.start;
         if (action == ACT_SPLIT) {
             float* slot_ptr = P.pool + (size_t)S.cur_slot * P.pool_stride;
-            if (SMEM_WS) create_split_cta(P, s_rng, src, f.len, reinterpret_cast<float*>(ctrl_smem), TM, slot_ptr);
-            else create_split_cta(P, s_rng, src, f.len, P.scratch + (size_t)t * WS_VECS * P.ld, TM, slot_ptr);
+            if (SMEM_WS) create_split_cta<METRIC>(P, s_rng, src, f.len, reinterpret_cast<float*>(ctrl_smem), TM, slot_ptr);
+            else create_split_cta<METRIC>(P, s_rng, src, f.len, P.scratch + (size_t)t * WS_VECS * P.ld, TM, slot_ptr);
             if (tid == 0) {
                 if (TM.mismatch) { S.n_misspec += 1; TM.mismatch = 0; }
                 S.n_splits_tried += 1; if (P.timing) TM.tacc[TP_ATTEMPTS] += 1;
