@@ -71,9 +71,9 @@ struct PinBuf {
 };
 
 struct Wave {  // device buffers of one wave of trees; kept across builds
-    DevBuf st, frames, recs, perm0, perm1, flags, unit_left, pool, pool_counter, jobs, scratch, active, error, final_ids, keys, sub_rows, sub_off, timing;
+    DevBuf st, frames, recs, perm0, perm1, flags, unit_left, pool, pool_counter, jobs, scratch, active, error, final_ids, keys, sub_rows, sub_off, timing, slots, abort;
     void release() {
-        sub_rows.release(); sub_off.release(); timing.release();
+        sub_rows.release(); sub_off.release(); timing.release(); slots.release(); abort.release();
         st.release(); frames.release(); recs.release(); perm0.release(); perm1.release(); flags.release(); unit_left.release();
         pool.release(); pool_counter.release(); jobs.release(); scratch.release(); active.release(); error.release(); final_ids.release(); keys.release();
     }
@@ -113,6 +113,8 @@ struct arroy_ctx {
     DevBuf s_rows, s_flags, s_margins, s_normal, s_unit, s_job, s_keys, s_keys2, s_dists, s_q, s_qh0, s_off, s_orows, s_odist, s_olen, s_misc;
     PinBuf pin;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaStream_t side_stream = nullptr;   // host -> device flags while the persistent build kernel occupies `stream`
+    cudaEvent_t ev_done = nullptr;
     double stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     uint64_t n_launches = 0, h2d_bytes = 0, d2h_bytes = 0;  // since create (arroy_b200_counters)
     cudaEvent_t tev0 = nullptr, tev1 = nullptr;
@@ -325,6 +327,7 @@ const void* control_fn(int metric) {
 }
 inline const void* control_fn(bool smem_ws, int cs, int metric) {
     if (!smem_ws) return control_fn<false, 1>(metric);
+    if (cs == 0) return control_fn<true, 0>(metric);   // persistent schedule
     return cs == 16 ? control_fn<true, 16>(metric) : (cs == 8 ? control_fn<true, 8>(metric) : control_fn<true, 1>(metric));
 }
 // launch (cluster dimension cs > 1: thread-block cluster of cs CTAs per tree)
@@ -452,6 +455,34 @@ void build_wave(arroy_ctx* c, size_t wave_no, uint32_t t0, uint32_t tw, const ui
     const void* ctrl1 = control_fn(use_smem != 0, 1, c->metric);
     const void* ctrlc = control_fn(use_smem != 0, cluster, c->metric);
 
+    // Persistent schedule (default): ONE cooperative launch per wave — a control CTA per tree plus worker CTAs on every SM
+    // (build.cuh control_kernel<.., CS = 0>). Needs two CTAs per SM to have enough workers next to the control CTAs; with a big
+    // workspace (d > 1152) that means giving up the speculative two_means. ARROY_B200_PERSIST=0 keeps the per-attempt launches.
+    bool persist = false;
+    int pgrid = 0;
+    size_t psmem = ctrl_smem;
+    const void* ctrlp = nullptr;
+    if (!lockstep && use_smem && !(getenv("ARROY_B200_PERSIST") && atoi(getenv("ARROY_B200_PERSIST")) == 0)) {
+        ctrlp = control_fn(true, 0, c->metric);
+        const size_t cand[2] = {ctrl_smem, (size_t)WS_VECS * ld * 4};
+        for (int k = 0; k < 2 && !persist; ++k) {
+            if (k == 1 && !P.spec) break;
+            CK(cudaFuncSetAttribute(ctrlp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cand[k]));
+            int nb = 0;
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ctrlp, CTRL_THREADS, cand[k]));
+            const int cap = nb * c->sm_count;
+            if ((nb >= 2 || k == 1) && cap >= (int)tw + std::max(16, c->sm_count / 2)) { persist = true; pgrid = cap; psmem = cand[k]; if (k == 1) P.spec = 0; }
+        }
+    }
+    if (persist) {
+        W.slots.ensure(sizeof(PSlot) * tw);
+        W.abort.ensure(4);
+        CK(cudaMemsetAsync(W.slots.p, 0, sizeof(PSlot) * tw, c->stream));
+        CK(cudaMemsetAsync(W.abort.p, 0, 4, c->stream));
+        P.slots = W.slots.as<PSlot>();
+        P.abort = W.abort.as<int>();
+    }
+
     auto launch_step = [&](cudaStream_t s) {  // lockstep: all trees per launch
         launch_control(ctrl1, tw, 1, ctrl_smem, s, P, 0u);
         work_kernel<<<work_grid, WORK_THREADS, wsmem, s>>>(P.jobs, (int)tw, P.items, P.ih0, P.d, P.ld, P.metric, interleave);
@@ -472,7 +503,7 @@ void build_wave(arroy_ctx* c, size_t wave_no, uint32_t t0, uint32_t tw, const ui
     // stable because the wave buffers live in the context) and the schedule, so it is reused by
     // later builds with the same shapes.
     cudaGraphExec_t gexec = nullptr;
-    if (use_graph) {
+    if (use_graph && !persist) {
         std::vector<uint8_t> key(sizeof(BuildParams) + 16);
         memcpy(key.data(), &P, sizeof(BuildParams));
         int32_t sched[4] = {(lockstep ? 1 : 0) | (interleave << 1) | (cluster << 8), steps_per_batch, (int32_t)tw, (int32_t)ctrl_smem};
@@ -515,6 +546,43 @@ void build_wave(arroy_ctx* c, size_t wave_no, uint32_t t0, uint32_t tw, const ui
     // safety net against a stuck state machine (never hit by a correct build): every step each
     // live tree completes one attempt or one partition
     const uint64_t max_steps = 40ull * (8 * leaves_est + 64) + 4096;
+    if (persist) {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)pgrid); cfg.blockDim = dim3(CTRL_THREADS); cfg.dynamicSmemBytes = psmem; cfg.stream = c->stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;   // all CTAs resident together, or the launch fails
+        cfg.attrs = at; cfg.numAttrs = 1;
+        uint32_t tree_base = 0;
+        void* args[2] = {&P, &tree_base};
+        CK(cudaLaunchKernelExC(&cfg, ctrlp, args));
+        CK(cudaEventRecord(c->ev_done, c->stream));
+        if (cancel) {   // polled while the kernel runs (BuildOption::cancel, src/writer.rs:116-124)
+            bool aborted = false;
+            for (;;) {
+                const cudaError_t q = cudaEventQuery(c->ev_done);
+                if (q == cudaSuccess) break;
+                if (q != cudaErrorNotReady) CK(q);
+                if (!aborted && cancel(cancel_arg)) {
+                    const int one = 1;
+                    CK(cudaMemcpyAsync(W.abort.p, &one, 4, cudaMemcpyHostToDevice, c->side_stream));
+                    aborted = true;
+                }
+                std::this_thread::sleep_for(std::chrono::microseconds(aborted ? 50 : 500));
+            }
+        }
+        CK(cudaMemcpyAsync((void*)h_active, W.active.p, 4, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaMemcpyAsync((void*)h_error, W.error.p, 4, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        steps = 1;
+        c->n_launches += 1;
+        if (*h_error != ERR_NONE) {
+            const int e = *h_error;
+            if (e == ERR_ABORT) throw Cancelled("The corresponding build process has been cancelled");
+            if (e == ERR_HANG) throw std::runtime_error("forest build made no progress (persistent schedule watchdog)");
+            throw CapacityError(e == ERR_DEPTH ? "tree deeper than MAX_DEPTH frames" : e == ERR_RECORDS ? "node record table overflow" : "normal pool overflow");
+        }
+        if (*h_active != 0) throw std::runtime_error("forest build ended with unfinished trees (internal state machine error)");
+    } else
     for (;;) {
         if (steps > max_steps) throw std::runtime_error("forest build did not converge (internal state machine error)");
         if (use_graph) CK(cudaGraphLaunch(gexec, c->stream));
@@ -1016,6 +1084,8 @@ int32_t arroy_b200_create(int32_t device, arroy_ctx** out) {
         CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         CK(cudaEventCreate(&c->ev0));
         CK(cudaEventCreate(&c->ev1));
+        CK(cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming));
         CK(cudaEventCreate(&c->tev0));
         CK(cudaEventCreate(&c->tev1));
         // fail loudly if the kernels were not built for this device
@@ -1052,6 +1122,8 @@ void arroy_b200_destroy(arroy_ctx* c) {
     for (auto& hw : c->host_waves) hw.release();
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->ev_done) cudaEventDestroy(c->ev_done);
+    if (c->side_stream) cudaStreamDestroy(c->side_stream);
     if (c->tev0) cudaEventDestroy(c->tev0);
     if (c->tev1) cudaEventDestroy(c->tev1);
     for (auto st : c->tree_streams) cudaStreamDestroy(st);

@@ -24,7 +24,7 @@ constexpr uint32_t NO_SLOT = 0xffffffffu;
 
 enum : int { PH_START = 0, PH_AWAIT_SCAN = 1, PH_AWAIT_PART = 2, PH_DONE = 3 };
 enum : int { REC_DESC = 1, REC_SPLIT = 2 };
-enum : int { ERR_NONE = 0, ERR_DEPTH = 1, ERR_RECORDS = 2, ERR_POOL = 3 };
+enum : int { ERR_NONE = 0, ERR_DEPTH = 1, ERR_RECORDS = 2, ERR_POOL = 3, ERR_HANG = 4, ERR_ABORT = 5 };
 
 struct Frame {
     uint32_t start, len;     // segment of the tree's id permutation
@@ -56,6 +56,18 @@ struct TreeState {
     uint32_t n_misspec;      // create_split calls whose speculative two_means had to be redone sequentially
 };
 
+// Persistent schedule (control_kernel<.., CS = 0>): one launch per wave holds one control CTA per tree and worker CTAs on
+// every SM; a control CTA publishes its scan / wide-partition job in its tree's slot and the workers claim units of it.
+// hdr = seq << 32 | total units, ticket = seq << 32 | next unclaimed unit: a claim (atomicAdd on the ticket) carries the epoch
+// it belongs to, so a worker that raced with the publication of the next job can tell whose units it holds.
+struct __align__(128) PSlot {
+    unsigned long long hdr;
+    unsigned long long ticket;
+    uint32_t done;       // units reported finished in this epoch
+    uint32_t chunk;      // units per claim
+    uint32_t pad[26];
+};
+
 struct BuildParams {
     const float* items; const float* ih0; const float* ih1;
     uint32_t n, d, ld; int32_t metric; uint32_t K;
@@ -80,6 +92,9 @@ struct BuildParams {
     // scanned by the control kernel's own cluster, at most max_inner attempts per launch
     uint32_t small_max, max_inner;
     unsigned long long* timing;   // optional: 16 cycle counters summed over all control launches (ARROY_B200_CTRL_TIMING)
+    // persistent schedule
+    PSlot* slots;                 // n_trees
+    const volatile int* abort;    // set by the host (cancel): control CTAs stop at their next wait
 };
 
 __device__ __forceinline__ double split_imbalance_dev(uint32_t l, uint32_t r) {  // src/writer.rs:1348-1353
@@ -499,7 +514,7 @@ __device__ __forceinline__ void create_split_cta(const BuildParams& P, Rng& rng 
     TP_MARK(S, TP_RNG);
     __syncthreads();
     uint32_t my_row = 0;
-    if (tid < 12) my_row = seg[S.rows[tid]];  // RoaringBitmap::select(rank) on the ascending id list
+    if (tid < 12) my_row = __ldcg(seg + S.rows[tid]);  // RoaringBitmap::select(rank) on the ascending id list
     __syncthreads();
     if (tid < 12) S.rows[tid] = my_row;
     __syncthreads();
@@ -603,8 +618,8 @@ __device__ __noinline__ void partition_inline(const uint32_t* __restrict__ src, 
         for (int j = 0; j < PART_BATCH; ++j) {
             uint32_t p = base + j * CTRL_THREADS + threadIdx.x;
             bool v = p < len;
-            fl[j] = v ? (int)flags[p] : 2;   // 2 = out of range
-            id[j] = v ? src[p] : 0u;
+            fl[j] = v ? (int)__ldcg(flags + p) : 2;   // 2 = out of range
+            id[j] = v ? __ldcg(src + p) : 0u;
         }
         unsigned lm[PART_BATCH], rm[PART_BATCH];
 #pragma unroll
@@ -642,7 +657,7 @@ __device__ uint32_t cta_exclusive_scan(uint32_t* v, uint32_t n, uint32_t* sm_tmp
     const int tid = threadIdx.x, nt = blockDim.x;
     const uint32_t per = (n + nt - 1) / nt;
     if (per <= 1) {   // one element per thread (small nodes): a single read of v, the value stays in a register
-        const uint32_t x = (uint32_t)tid < n ? v[tid] : 0u;
+        const uint32_t x = (uint32_t)tid < n ? __ldcg(v + tid) : 0u;
         const int lane = tid & 31, w = tid >> 5;
         uint32_t inc = x;
         for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += y; }
@@ -656,7 +671,7 @@ __device__ uint32_t cta_exclusive_scan(uint32_t* v, uint32_t n, uint32_t* sm_tmp
     }
     const uint32_t b = (uint32_t)tid * per, e = (b + per < n) ? b + per : n;
     uint32_t s = 0;
-    for (uint32_t i = b; i < e; ++i) s += v[i];
+    for (uint32_t i = b; i < e; ++i) s += __ldcg(v + i);
     sm_tmp[tid] = s;
     __syncthreads();
     if (tid < 32) {  // warp 0: exclusive scan of the nt partials (nt == 8 * 32)
@@ -671,13 +686,121 @@ __device__ uint32_t cta_exclusive_scan(uint32_t* v, uint32_t n, uint32_t* sm_tmp
     }
     __syncthreads();
     uint32_t run = sm_tmp[tid];
-    for (uint32_t i = b; i < e; ++i) { uint32_t x = v[i]; v[i] = run; run += x; }
+    for (uint32_t i = b; i < e; ++i) { uint32_t x = __ldcg(v + i); v[i] = run; run += x; }
     uint32_t total = sm_tmp[nt];
     __syncthreads();
     return total;
 }
 
-enum : int { ACT_NONE = 0, ACT_SPLIT = 1, ACT_PART_INLINE = 2, ACT_RANDOM = 3, ACT_EXIT = 4 };
+enum : int { ACT_NONE = 0, ACT_SPLIT = 1, ACT_PART_INLINE = 2, ACT_RANDOM = 3, ACT_EXIT = 4, ACT_PART_WIDE = 5 };
+
+
+// ---- persistent schedule: job slots between the control CTAs and the worker CTAs of ONE launch -------------------------
+__device__ __forceinline__ unsigned long long ld_vol64(const unsigned long long* p) { return *reinterpret_cast<const volatile unsigned long long*>(p); }
+__device__ __forceinline__ void st_vol64(unsigned long long* p, unsigned long long v) { *reinterpret_cast<volatile unsigned long long*>(p) = v; }
+__device__ __forceinline__ uint32_t ld_vol32(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
+
+// thread 0 of a control CTA, after every thread's writes were fenced and a CTA barrier: open `total` units of the job in P.jobs[t]
+__device__ __forceinline__ void ppublish(PSlot& sl, uint32_t total, uint32_t chunk) {
+    const uint32_t seq = (uint32_t)(ld_vol64(&sl.hdr) >> 32) + 1u;
+    *reinterpret_cast<volatile uint32_t*>(&sl.done) = 0u;
+    *reinterpret_cast<volatile uint32_t*>(&sl.chunk) = chunk;
+    __threadfence();
+    st_vol64(&sl.hdr, ((unsigned long long)seq << 32) | total);     // header first: whoever sees the new ticket also sees it
+    __threadfence();
+    st_vol64(&sl.ticket, (unsigned long long)seq << 32);
+}
+// ... and wait until the workers have reported all of them. false: error / cancel / no progress for ~4 s (never on a sane run)
+__device__ __forceinline__ bool pwait(const BuildParams& P, PSlot& sl, uint32_t total) {
+    const long long t0 = clock64();
+    uint32_t spins = 0;
+    for (;;) {
+        if (ld_vol32(&sl.done) >= total) { __threadfence(); return true; }
+        if ((++spins & 63u) == 0u) {
+            if (*reinterpret_cast<volatile int32_t*>(P.error) != ERR_NONE) return false;
+            if (P.abort != nullptr && *P.abort != 0) { atomicCAS(P.error, ERR_NONE, ERR_ABORT); return false; }
+            if (clock64() - t0 > 8000000000ll) { atomicCAS(P.error, ERR_NONE, ERR_HANG); return false; }
+        }
+        __nanosleep(40);
+    }
+}
+
+// A worker CTA: claims units of whatever the control CTAs have published and runs the same scan / partition code as work_kernel.
+// Returns when every tree is done (or on error). sm_normal: ld floats of dynamic shared memory.
+__device__ __noinline__ void pworker(const BuildParams& P, float* sm_normal) {
+    __shared__ uint32_t w_t, w_u0, w_n, w_seq, w_found, w_exit, w_count;
+    __shared__ uint32_t w_sm[16];
+    const uint32_t T = P.n_trees;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t rot = (blockIdx.x - T) * 7u;
+    uint32_t loaded_t = 0xffffffffu, loaded_seq = 0;
+    float nh0 = 0.f;
+    if (tid == 0) w_exit = 0;
+    for (;;) {
+        if (warp == 0) {
+            uint32_t found = 0;
+            for (uint32_t base = 0; base < T && !found; base += 32) {
+                const uint32_t k = base + lane;
+                const uint32_t t = k < T ? (rot + k) % T : 0u;
+                unsigned long long tk = 0, hdr = 0;
+                if (k < T) { tk = ld_vol64(&P.slots[t].ticket); __threadfence(); hdr = ld_vol64(&P.slots[t].hdr); }
+                const bool cand = k < T && (uint32_t)hdr != 0u && (tk >> 32) == (hdr >> 32) && (uint32_t)tk < (uint32_t)hdr;
+                unsigned m = __ballot_sync(0xffffffffu, cand);
+                while (m != 0u && !found) {
+                    const int src = __ffs((int)m) - 1;
+                    m &= m - 1u;
+                    uint32_t ok = 0;
+                    if (lane == src) {
+                        const uint32_t chunk = max(1u, ld_vol32(&P.slots[t].chunk));
+                        const unsigned long long r = atomicAdd(&P.slots[t].ticket, (unsigned long long)chunk);
+                        __threadfence();
+                        const uint32_t rseq = (uint32_t)(r >> 32), rn = (uint32_t)r;
+                        unsigned long long h2 = ld_vol64(&P.slots[t].hdr);
+                        while ((uint32_t)(h2 >> 32) != rseq) {   // the claim fell into a newer epoch than the header this lane had read: wait for that header
+                            if ((int32_t)((uint32_t)(h2 >> 32) - rseq) > 0) break;   // (cannot happen: an epoch does not end with an unreported claim)
+                            h2 = ld_vol64(&P.slots[t].hdr);
+                        }
+                        const uint32_t total = (uint32_t)h2;
+                        if ((uint32_t)(h2 >> 32) == rseq && rn < total) { w_t = t; w_u0 = rn; w_n = min(chunk, total - rn); w_seq = rseq; ok = 1; }
+                    }
+                    found = __shfl_sync(0xffffffffu, ok, src);
+                }
+            }
+            if (lane == 0) {
+                w_found = found;
+                if (!found) {
+                    if (ld_vol32(P.active) == 0u || *reinterpret_cast<volatile int32_t*>(P.error) != ERR_NONE) w_exit = 1;
+                    else __nanosleep(100);
+                }
+            }
+        }
+        __syncthreads();
+        if (w_exit) return;
+        if (w_found) {
+            const uint32_t t = w_t, u0 = w_u0, nu = w_n, seq = w_seq;
+            const volatile Job* vj = &P.jobs[t];
+            Job jb;
+            jb.kind = vj->kind; jb.len = vj->len; jb.rows = vj->rows; jb.normal = vj->normal; jb.flags = vj->flags; jb.margins = nullptr;
+            jb.unit_left = vj->unit_left; jb.dst = vj->dst; jb.total_left = vj->total_left; jb.pad = 0;
+            if (jb.kind == JOB_SCAN) {
+                if (loaded_t != t || loaded_seq != seq) {
+                    for (uint32_t i = tid; i < P.ld; i += blockDim.x) sm_normal[i] = __ldcg(jb.normal + NORMAL_HDR + i);
+                    nh0 = __ldcg(jb.normal);
+                    loaded_t = t; loaded_seq = seq;
+                    __syncthreads();
+                }
+                for (uint32_t u = u0; u < u0 + nu; ++u) scan_unit(jb, u, P.items, P.ih0, P.d, P.ld, P.metric, sm_normal, nh0, &w_count);
+            } else if (jb.kind == JOB_PARTITION) {
+                for (uint32_t u = u0; u < u0 + nu; ++u)
+                    partition_block(jb.rows, jb.flags, jb.dst, u * PART_UNIT, jb.len, __ldcg(jb.unit_left + u * (PART_UNIT / SCAN_UNIT)), jb.total_left, w_sm);
+            }
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) atomicAdd(&P.slots[t].done, nu);
+        }
+        __syncthreads();
+    }
+}
 
 // One tree per launch unit. CS = 1: one CTA; the scan of every attempt is a separate work_kernel
 // launch. CS > 1 (thread-block cluster of CS CTAs, latency-bound regime: few trees per GPU): CTA 0
@@ -696,10 +819,17 @@ __device__ __forceinline__ void cluster_scan_share(const BuildParams& P, const J
     for (uint32_t u = rank; u < units; u += CS) scan_unit(jb, u, P.items, P.ih0, P.d, P.ld, P.metric, sm_normal, nh0, sm_count);
 }
 
+// CS = 0: the PERSISTENT schedule. One launch per wave: CTAs [0, n_trees) each run one tree's state machine to the end, the other
+// CTAs are workers (pworker). Nothing is launched per attempt: a control CTA publishes its scan (or wide partition) in its slot,
+// the workers on all SMs claim units of it, the control CTA waits for their reports and goes on — the tree's state, its DFS
+// frames and its ChaCha blocks never leave shared memory. All CTAs must be resident together (cooperative launch).
 template <bool SMEM_WS, int CS, int METRIC>
-__global__ void __launch_bounds__(CTRL_THREADS, 1) control_kernel(BuildParams P, uint32_t tree_base) {
-    static_assert(CS == 1 || SMEM_WS, "the cluster path keeps the normal in the shared-memory workspace");
+__global__ void __launch_bounds__(CTRL_THREADS, (CS == 0 ? 2 : 1)) control_kernel(BuildParams P, uint32_t tree_base) {
+    static_assert(CS <= 1 || SMEM_WS, "the cluster path keeps the normal in the shared-memory workspace");
+    constexpr bool PERSIST = CS == 0;
+    constexpr int CSD = CS < 1 ? 1 : CS;
     extern __shared__ __align__(16) unsigned char ctrl_smem[];
+    if (PERSIST && blockIdx.x >= P.n_trees) { pworker(P, reinterpret_cast<float*>(ctrl_smem)); return; }
     __shared__ uint32_t s_scan_count;
     __shared__ TwoMeansShared TM;
     __shared__ uint32_t sm_tmp[CTRL_THREADS + 1];
@@ -713,7 +843,8 @@ __global__ void __launch_bounds__(CTRL_THREADS, 1) control_kernel(BuildParams P,
     __shared__ Frame sm_frames[SMF];
     __shared__ TreeState S;
 
-    const uint32_t t = blockIdx.x / CS + tree_base;
+    __shared__ int s_wait_ok;
+    const uint32_t t = blockIdx.x / CSD + tree_base;
     Job& job = P.jobs[t];
     unsigned crank = 0;
     if (CS > 1) crank = cooperative_groups::this_cluster().block_rank();
@@ -790,13 +921,14 @@ __global__ void __launch_bounds__(CTRL_THREADS, 1) control_kernel(BuildParams P,
                         f.slot = S.cur_slot; S.cur_slot = NO_SLOT;   // the normal is kept
                         f.left_len = left;
                         if (f.len <= INLINE_PART_MAX) action = ACT_PART_INLINE;
-                        else {  // wide partition by all SMs in this step's work kernel
+                        else {  // wide partition by all SMs (this step's work kernel / the workers)
                             job.kind = JOB_PARTITION; job.len = f.len;
                             job.rows = (f.parity ? perm1 : perm0) + f.start;
                             job.dst = (f.parity ? perm0 : perm1) + f.start;
                             job.flags = flags + f.start; job.unit_left = unit_left; job.total_left = left;
                             job.normal = nullptr; job.margins = nullptr;
-                            f.stage = 1; S.phase = PH_AWAIT_PART; action = ACT_EXIT;
+                            if (PERSIST) action = ACT_PART_WIDE;
+                            else { f.stage = 1; S.phase = PH_AWAIT_PART; action = ACT_EXIT; }
                         }
                     }
                 } else { S.attempts_left -= 1; action = ACT_SPLIT; }  // :1215
@@ -866,6 +998,24 @@ __global__ void __launch_bounds__(CTRL_THREADS, 1) control_kernel(BuildParams P,
                 S.phase = PH_AWAIT_SCAN;
                 if (CS > 1 && f.len <= P.small_max && inner < P.max_inner) job.pad = 1;
             }
+            if (PERSIST) {
+                // the normal (written by every thread) and the job fields must be visible device-wide before the job opens
+                __threadfence();
+                __syncthreads();
+                const uint32_t units = (f.len + SCAN_UNIT - 1) / SCAN_UNIT;
+                if (tid == 0) {
+                    ppublish(P.slots[t], units, units > 1024u ? 4u : 1u);
+                    s_wait_ok = pwait(P, P.slots[t], units) ? 1 : 0;
+                    if (P.timing) TM.tacc[TP_INNER] += 1;
+                }
+                __syncthreads();
+                TP_MARK(TM, TP_CLUSTER_SCAN);
+                if (!s_wait_ok) break;
+                total_left = cta_exclusive_scan(unit_left, units, sm_tmp);
+                __syncthreads();
+                TP_MARK(TM, TP_PREFIX);
+                continue;
+            }
             if (CS > 1 && f.len <= P.small_max && inner < P.max_inner) {
                 // cluster-resident attempt: scan here, then straight on to the decision
                 cooperative_groups::this_cluster().sync();                       // [A] job visible to the helpers
@@ -909,6 +1059,20 @@ __global__ void __launch_bounds__(CTRL_THREADS, 1) control_kernel(BuildParams P,
             if (tid == 0) { FR(S.sp).stage = 1; S.phase = PH_AWAIT_PART; }
             total_left = 0;
             __syncthreads();
+            continue;
+        }
+        if (PERSIST && action == ACT_PART_WIDE) {
+            // the exclusive prefix of the unit counts (written by every thread above) feeds the workers' partition blocks
+            __threadfence();
+            __syncthreads();
+            const uint32_t units = (f.len + PART_UNIT - 1) / PART_UNIT;
+            if (tid == 0) { ppublish(P.slots[t], units, 4u); s_wait_ok = pwait(P, P.slots[t], units) ? 1 : 0; }
+            __syncthreads();
+            if (!s_wait_ok) break;
+            if (tid == 0) { FR(S.sp).stage = 1; S.phase = PH_AWAIT_PART; }
+            total_left = 0;
+            __syncthreads();
+            TP_MARK(TM, TP_PARTITION);
             continue;
         }
         if (action == ACT_PART_INLINE) {

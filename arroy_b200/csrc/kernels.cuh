@@ -65,8 +65,9 @@ __device__ __forceinline__ void scan_unit(const Job& jb, uint32_t unit, const fl
         uint32_t pa = base + slot, pb = base + slot + 1;
         const bool va = pa < jb.len, vb = pb < jb.len;
         uint32_t ra = 0, rb = 0;
-        if (va) ra = jb.rows ? jb.rows[pa] : pa;
-        if (vb) rb = jb.rows ? jb.rows[pb] : pb;
+        // (id lists, flags and unit counts change between jobs of ONE persistent kernel: they are read through L2, never L1)
+        if (va) ra = jb.rows ? __ldcg(jb.rows + pa) : pa;
+        if (vb) rb = jb.rows ? __ldcg(jb.rows + pb) : pb;
         const float4* A = reinterpret_cast<const float4*>(items + (size_t)ra * ld);
         const float4* B = reinterpret_cast<const float4*>(items + (size_t)rb * ld);
         const float4* N = reinterpret_cast<const float4*>(sm_normal);
@@ -104,7 +105,7 @@ __device__ __forceinline__ void scan_unit(const Job& jb, uint32_t unit, const fl
         if (threadIdx.x < SCAN_UNIT) {
             uint32_t p = base + threadIdx.x;
             if (p < jb.len) {
-                uint32_t r = jb.rows ? jb.rows[p] : p;
+                uint32_t r = jb.rows ? __ldcg(jb.rows + p) : p;
                 float dt = exact_thread<false>(items + (size_t)r * ld, sm_normal, (int)d);
                 float m = margin_finish(metric, dt, nh0, (metric == DOT_PRODUCT) ? ih0[r] : 0.f);
                 int s = side_of(m);
@@ -127,8 +128,8 @@ __device__ __forceinline__ void partition_block(const uint32_t* __restrict__ src
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t p = base + threadIdx.x;
     bool valid = p < len;
-    int f = valid ? flags[p] : 1;
-    uint32_t id = valid ? src[p] : 0;
+    int f = valid ? (int)__ldcg(flags + p) : 1;
+    uint32_t id = valid ? __ldcg(src + p) : 0;
     unsigned lm = __ballot_sync(0xffffffffu, valid && f == 0);
     unsigned rm = __ballot_sync(0xffffffffu, valid && f != 0);
     if (lane == 0) { sm_w[warp] = __popc(lm); sm_w[8 + warp] = __popc(rm); }
