@@ -71,9 +71,9 @@ struct PinBuf {
 };
 
 struct Wave {  // device buffers of one wave of trees; kept across builds
-    DevBuf st, frames, recs, perm0, perm1, flags, unit_left, pool, pool_counter, jobs, scratch, active, error, final_ids, keys, sub_rows, sub_off, timing, slots, abort;
+    DevBuf st, frames, recs, perm0, perm1, flags, unit_left, pool, pool_counter, jobs, scratch, active, error, final_ids, keys, sub_rows, sub_off, timing, slots, abort, cur_normal;
     void release() {
-        sub_rows.release(); sub_off.release(); timing.release(); slots.release(); abort.release();
+        sub_rows.release(); sub_off.release(); timing.release(); slots.release(); abort.release(); cur_normal.release();
         st.release(); frames.release(); recs.release(); perm0.release(); perm1.release(); flags.release(); unit_left.release();
         pool.release(); pool_counter.release(); jobs.release(); scratch.release(); active.release(); error.release(); final_ids.release(); keys.release();
     }
@@ -462,7 +462,7 @@ void build_wave(arroy_ctx* c, size_t wave_no, uint32_t t0, uint32_t tw, const ui
     int pgrid = 0;
     size_t psmem = ctrl_smem;
     const void* ctrlp = nullptr;
-    if (!lockstep && use_smem && !(getenv("ARROY_B200_PERSIST") && atoi(getenv("ARROY_B200_PERSIST")) == 0)) {
+    if (!lockstep && use_smem && ld <= 8u * CTRL_THREADS && n < (1ull << 29) && !(getenv("ARROY_B200_PERSIST") && atoi(getenv("ARROY_B200_PERSIST")) == 0)) {
         ctrlp = control_fn(true, 0, c->metric);
         const size_t cand[2] = {ctrl_smem, (size_t)WS_VECS * ld * 4};
         for (int k = 0; k < 2 && !persist; ++k) {
@@ -479,7 +479,9 @@ void build_wave(arroy_ctx* c, size_t wave_no, uint32_t t0, uint32_t tw, const ui
         W.abort.ensure(4);
         CK(cudaMemsetAsync(W.slots.p, 0, sizeof(PSlot) * tw, c->stream));
         CK(cudaMemsetAsync(W.abort.p, 0, 4, c->stream));
+        W.cur_normal.ensure(4ull * pool_stride * tw);
         P.slots = W.slots.as<PSlot>();
+        P.cur_normal = W.cur_normal.as<float>();
         P.abort = W.abort.as<int>();
     }
 

@@ -58,15 +58,21 @@ struct TreeState {
 
 // Persistent schedule (control_kernel<.., CS = 0>): one launch per wave holds one control CTA per tree and worker CTAs on
 // every SM; a control CTA publishes its scan / wide-partition job in its tree's slot and the workers claim units of it.
-// hdr = seq << 32 | total units, ticket = seq << 32 | next unclaimed unit: a claim (atomicAdd on the ticket) carries the epoch
-// it belongs to, so a worker that raced with the publication of the next job can tell whose units it holds.
+// Everything a worker needs sits in ONE 128-byte line and the protocol is one word: ticket = seq:16 | total units:24 | next
+// unclaimed unit:24. A claim is one atomicAdd on it and carries the epoch it belongs to, so a worker that raced with the
+// publication of the next job can tell whose units it holds; a global round trip costs ~0.7 us here, so the path from
+// "published" to "reported" is kept to: poll, claim (with the field and normal loads in flight), id list, item rows, report.
 struct __align__(128) PSlot {
-    unsigned long long hdr;
     unsigned long long ticket;
-    uint32_t done;       // units reported finished in this epoch
-    uint32_t chunk;      // units per claim
-    uint32_t pad[26];
+    unsigned long long done;     // seq:32 | units reported finished:32
+    const uint32_t* rows; uint8_t* flags; uint32_t* unit_left; uint32_t* dst;
+    uint32_t len, kind, total_left, chunk;
+    uint32_t pad[16];
 };
+__device__ __forceinline__ unsigned long long pticket(uint32_t seq, uint32_t total, uint32_t next) { return ((unsigned long long)(seq & 0xffffu) << 48) | ((unsigned long long)(total & 0xffffffu) << 24) | (unsigned long long)(next & 0xffffffu); }
+__device__ __forceinline__ uint32_t pt_seq(unsigned long long t) { return (uint32_t)(t >> 48); }
+__device__ __forceinline__ uint32_t pt_total(unsigned long long t) { return (uint32_t)(t >> 24) & 0xffffffu; }
+__device__ __forceinline__ uint32_t pt_next(unsigned long long t) { return (uint32_t)t & 0xffffffu; }
 
 struct BuildParams {
     const float* items; const float* ih0; const float* ih1;
@@ -94,6 +100,7 @@ struct BuildParams {
     unsigned long long* timing;   // optional: 16 cycle counters summed over all control launches (ARROY_B200_CTRL_TIMING)
     // persistent schedule
     PSlot* slots;                 // n_trees
+    float* cur_normal;            // n_trees x pool_stride: the normal of each tree's open scan job, at an address workers know without the job fields
     const volatile int* abort;    // set by the host (cancel): control CTAs stop at their next wait
 };
 
@@ -122,7 +129,9 @@ struct TwoMeansShared {
     long long tlast;
     // speculative two_means
     float G[12][12];        // approximate dots between the 12 gathered vectors (0 = p, 1 = q after normalize, 2.. = the ten k)
-    float Gp[4][6][16];     // its partial sums: K-slice x block pair x 4 x 4
+    float Gp[8][16][16];    // its partial products, one 16 x 16 tile per warp
+    float An[10][10];       // An[it][l] = (k_it / norm_it) . k_l
+    float rc[10][6];        // per-iteration constants of the recurrence
     float vdot[32];         // exact dots of the verification pass
     int choice[10];         // per iteration: 0 = nothing moved, 1 = p moved, 2 = q moved
     int ready;              // iterations whose choice has been published by the speculating warp
@@ -191,93 +200,95 @@ __device__ __forceinline__ bool spec_two_means(const BuildParams& P, float* ws, 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, grp = lane >> 3, g8 = lane & 7;
     const bool cosine = !EUCLID;
     if (tid == 0) { S.ready = 0; S.mismatch = 0; }
-    // (1a) Gram matrix, any summation order: 6 pairs of 4-vector blocks x 4 K-slices = 24 jobs of 16 dots each; the 8 lanes of
-    // a job fold their partial sums with a halving exchange (14 shuffles, every lane ends up with 2 of the 16 sums)
-    if (warp < 6) {
-        const int job = warp * 4 + grp, pair = job >> 2, slice = job & 3;
-        const int X = pair < 3 ? 0 : (pair < 5 ? 1 : 2);
-        const int Y = pair < 3 ? pair : (pair < 5 ? pair - 2 : 2);
-        float acc[16];
+    // (1a) Gram matrix of the 12 gathered vectors on the tensor cores (mma.sync m16n8k8, TF32 inputs, FP32 accumulate): it only
+    // has to PREDICT branches, so ~2^-10 relative input rounding is fine (a wrong prediction costs one sequential re-run). Rows
+    // 12..15 of the 16 x 16 product read the neighbouring workspace slots; their entries are never used. Every warp takes the
+    // 16-float chunks m = warp, warp + 8, ...; a lane (r = lane / 4, c = lane % 4) loads floats 4c..4c+3 of rows r and r + 8 of
+    // the chunk — the SAME registers serve as A fragment (row-major 16 x 8) and as B fragment (col-major 8 x 8 of U^T), because
+    // the k index of a dot product may be permuted freely as long as both operands use the same permutation.
+    {
+        float acc[2][4];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) acc[i] = 0.f;
-        const int nch = ld >> 5;
-        const float* xb = ws + (size_t)(4 * X) * ld + g8 * 4;
-        const float* yb = ws + (size_t)(4 * Y) * ld + g8 * 4;
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+        const float* r0 = ws + (size_t)(lane >> 2) * ld + 4 * (lane & 3);
+        const float* r1 = r0 + (size_t)8 * ld;
+        const int nck = ld >> 4;
 #pragma unroll 1
-        for (int c = slice; c < nch; c += 4) {
-            float4 xa[4], ya[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) xa[i] = *reinterpret_cast<const float4*>(xb + (size_t)i * ld + c * 32);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) ya[j] = *reinterpret_cast<const float4*>(yb + (size_t)j * ld + c * 32);
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    acc[i * 4 + j] = fmaf(xa[i].x, ya[j].x, fmaf(xa[i].y, ya[j].y, fmaf(xa[i].z, ya[j].z, fmaf(xa[i].w, ya[j].w, acc[i * 4 + j]))));
+        for (int m = warp; m < nck; m += CTRL_THREADS / 32) {
+            const float4 x0 = *reinterpret_cast<const float4*>(r0 + 16 * m);
+            const float4 x1 = *reinterpret_cast<const float4*>(r1 + 16 * m);
+            const uint32_t a0 = __float_as_uint(x0.x), a1 = __float_as_uint(x1.x), a2 = __float_as_uint(x0.y), a3 = __float_as_uint(x1.y);
+            const uint32_t e0 = __float_as_uint(x0.z), e1 = __float_as_uint(x1.z), e2 = __float_as_uint(x0.w), e3 = __float_as_uint(x1.w);
+            asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                         : "+f"(acc[0][0]), "+f"(acc[0][1]), "+f"(acc[0][2]), "+f"(acc[0][3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(a0), "r"(a2));
+            asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                         : "+f"(acc[1][0]), "+f"(acc[1][1]), "+f"(acc[1][2]), "+f"(acc[1][3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(a1), "r"(a3));
+            asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                         : "+f"(acc[0][0]), "+f"(acc[0][1]), "+f"(acc[0][2]), "+f"(acc[0][3]) : "r"(e0), "r"(e1), "r"(e2), "r"(e3), "r"(e0), "r"(e2));
+            asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                         : "+f"(acc[1][0]), "+f"(acc[1][1]), "+f"(acc[1][2]), "+f"(acc[1][3]) : "r"(e0), "r"(e1), "r"(e2), "r"(e3), "r"(e1), "r"(e3));
         }
-        // halving exchange: after the step with partner distance 4 a lane keeps 8 sums, then 4, then 2
-        {
-            const bool hi4 = (g8 & 4) != 0;
+        // D fragment: acc[t][0..1] = D[lane / 4][8t + 2 (lane % 4) + {0, 1}], acc[t][2..3] = the same columns of row lane / 4 + 8
+        float* gp = &S.Gp[warp][0][0];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { const float send = hi4 ? acc[i] : acc[8 + i], keep = hi4 ? acc[8 + i] : acc[i]; acc[i] = keep + __shfl_xor_sync(full, send, 4); }
-            const bool hi2 = (g8 & 2) != 0;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) { const float send = hi2 ? acc[i] : acc[4 + i], keep = hi2 ? acc[4 + i] : acc[i]; acc[i] = keep + __shfl_xor_sync(full, send, 2); }
-            const bool hi1 = (g8 & 1) != 0;
-#pragma unroll
-            for (int i = 0; i < 2; ++i) { const float send = hi1 ? acc[i] : acc[2 + i], keep = hi1 ? acc[2 + i] : acc[i]; acc[i] = keep + __shfl_xor_sync(full, send, 1); }
-            // lane g8 now holds sums number 8 * bit2 + 4 * bit1 + 2 * bit0 + {0, 1} of its job
-            const int e0 = (hi4 ? 8 : 0) + (hi2 ? 4 : 0) + (hi1 ? 2 : 0);
-            S.Gp[slice][pair][e0] = acc[0]; S.Gp[slice][pair][e0 + 1] = acc[1];
+        for (int t = 0; t < 2; ++t) {
+            const int col = 8 * t + 2 * (lane & 3), row = lane >> 2;
+            gp[row * 16 + col] = acc[t][0]; gp[row * 16 + col + 1] = acc[t][1];
+            gp[(row + 8) * 16 + col] = acc[t][2]; gp[(row + 8) * 16 + col + 1] = acc[t][3];
         }
     }
     __syncthreads();
-    if (tid < 96) {   // G[4X + i][4Y + j] (and its mirror) = sum of the four K-slices
-        const int pair = tid >> 4, e = tid & 15, i = e >> 2, j = e & 3;
-        const int X = pair < 3 ? 0 : (pair < 5 ? 1 : 2);
-        const int Y = pair < 3 ? pair : (pair < 5 ? pair - 2 : 2);
-        const float v = (S.Gp[0][pair][e] + S.Gp[1][pair][e]) + (S.Gp[2][pair][e] + S.Gp[3][pair][e]);
-        S.G[4 * X + i][4 * Y + j] = v;
-        if (X != Y) S.G[4 * Y + j][4 * X + i] = v;
+    if (tid < 144) {   // G = sum of the eight warps' partial products
+        const int i = tid / 12, j = tid - 12 * i;
+        float v = 0.f;
+#pragma unroll
+        for (int w = 0; w < CTRL_THREADS / 32; ++w) v += S.Gp[w][i][j];
+        S.G[i][j] = v;
     }
+    __syncthreads();
+    // per-iteration constants of the recurrence (tid = iteration, or iteration x lane)
+    if (tid < 10) {
+        const float nrm = cosine ? S.nk[2 + tid] : 1.f;
+        const float inv = __fdividef(1.f, nrm);
+        S.rc[tid][0] = inv;                                      // 1 / norm_it
+        S.rc[tid][1] = S.G[2 + tid][2 + tid] * inv * inv;        // (k / norm)^2
+        S.rc[tid][2] = S.G[2 + tid][2 + tid];                    // k . k
+        S.rc[tid][3] = (metric == COSINE) ? __fdividef(1.f, S.h0[2 + tid]) : S.h0[2 + tid];   // Cosine: 1 / |k| (stored header); DotProduct: k.extra_dim
+        S.rc[tid][4] = S.h1[2 + tid];                            // DotProduct: k's norm header
+        S.rc[tid][5] = (nrm != nrm || nrm <= 0.f) ? 0.f : 1.f;   // the loop's `continue` guard (mod.rs:152-155)
+    }
+    if (tid >= 32 && tid < 132) { const int it = (tid - 32) / 10, l = (tid - 32) - 10 * it; S.An[it][l] = S.G[2 + it][2 + l] * __fdividef(1.f, cosine ? S.nk[2 + it] : 1.f); }
     __syncthreads();
     TP_MARK(S, TP_TM_DOT);
     if (warp == 0) {
-        // (1b) the recurrence: lane l < 10 carries p.k_l and q.k_l; every lane carries p.p, q.q and the counts
-        float pk = lane < 10 ? S.G[0][2 + lane] : 0.f, qk = lane < 10 ? S.G[1][2 + lane] : 0.f;
-        float pp = S.G[0][0], qq = S.G[1][1], ic = 1.f, jc = 1.f;
-        const float pe = S.php[0], qe = S.phq[0];   // DotProduct: extra_dim of the centroids (update_mean leaves headers alone)
-        // per-iteration constants, one lane each (approximate reciprocals are fine: this only predicts)
+        // (1b) the recurrence on SUMS: with Sp = ic * p (the sum of p0 and the k / norm assigned to it), lane l < 10 carries
+        // Sp . k_l and Sq . k_l; every lane carries Sp . Sp, Sq . Sq and the counts. An update is one add per lane.
         const int li = lane < 10 ? lane : 0;
-        const float my_norm = cosine ? S.nk[2 + li] : 1.f;
-        const float my_inv = __fdividef(1.f, my_norm);
-        const float my_kk = S.G[2 + li][2 + li];
-        const float my_a = (metric == COSINE) ? __fdividef(1.f, S.h0[2 + li]) : S.h0[2 + li];   // Cosine: 1 / |k| (stored header); DotProduct: k.extra_dim
-        const float my_b = S.h1[2 + li];                                                    // DotProduct: k's norm header
-        const bool my_ok = !(my_norm != my_norm || my_norm <= 0.f);
+        float spk = S.G[0][2 + li], sqk = S.G[1][2 + li];
+        float spp = S.G[0][0], sqq = S.G[1][1], ic = 1.f, jc = 1.f;
+        const float pe = S.php[0], qe = S.phq[0];   // DotProduct: extra_dim of the centroids (update_mean leaves headers alone)
 #pragma unroll 1
         for (int it = 0; it < 10; ++it) {
-            const float pki = __shfl_sync(full, pk, it), qki = __shfl_sync(full, qk, it);
-            const float kk = __shfl_sync(full, my_kk, it), ka = __shfl_sync(full, my_a, it), inv = __shfl_sync(full, my_inv, it);
+            const float a = __shfl_sync(full, spk, it), b = __shfl_sync(full, sqk, it);
+            const float inv = S.rc[it][0], bb = S.rc[it][1], kk = S.rc[it][2], ka = S.rc[it][3], ok = S.rc[it][5];
+            const float g = S.An[it][li];
             float di, dj;
-            if (EUCLID) { di = ic * (pp - 2.f * pki + kk); dj = jc * (qq - 2.f * qki + kk); }
+            if (EUCLID) { di = spp * __fdividef(1.f, ic) - 2.f * a + ic * kk; dj = sqq * __fdividef(1.f, jc) - 2.f * b + jc * kk; }
             else if (metric == COSINE) {
-                const float cp = fminf(1.f, fmaxf(-1.f, pki * rsqrtf(pp) * ka)), cq = fminf(1.f, fmaxf(-1.f, qki * rsqrtf(qq) * ka));
+                const float cp = fminf(1.f, fmaxf(-1.f, a * rsqrtf(spp) * ka)), cq = fminf(1.f, fmaxf(-1.f, b * rsqrtf(sqq) * ka));
                 di = ic * (1.f - cp); dj = jc * (1.f - cq);
             } else {
-                const float kb = __shfl_sync(full, my_b, it);
-                const float mp = pp * kb, mq = qq * kb;
-                di = mp >= 1.17549435e-38f ? ic * (2.f - 2.f * (pki + pe * ka) * rsqrtf(mp)) : ic * 2.f;
-                dj = mq >= 1.17549435e-38f ? jc * (2.f - 2.f * (qki + qe * ka) * rsqrtf(mq)) : jc * 2.f;
+                const float kb = S.rc[it][4];
+                const float mp = spp * kb, mq = sqq * kb;
+                di = mp >= 1.17549435e-38f * ic * ic ? ic * (2.f - 2.f * (a + ic * pe * ka) * rsqrtf(mp)) : ic * 2.f;
+                dj = mq >= 1.17549435e-38f * jc * jc ? jc * (2.f - 2.f * (b + jc * qe * ka) * rsqrtf(mq)) : jc * 2.f;
             }
             int ch = 0;
-            if (__shfl_sync(full, (int)my_ok, it)) ch = di < dj ? 1 : (dj < di ? 2 : 0);
-            if (ch) {   // c' = (c * cnt + k / norm) / (cnt + 1) — update_mean, mod.rs:86-94
-                const float g = S.G[2 + it][2 + li] * inv;
-                if (ch == 1) { const float c1 = ic + 1.f, r = __fdividef(1.f, c1); pk = (ic * pk + g) * r; pp = (ic * ic * pp + 2.f * ic * pki * inv + kk * inv * inv) * r * r; ic = c1; }
-                else { const float c1 = jc + 1.f, r = __fdividef(1.f, c1); qk = (jc * qk + g) * r; qq = (jc * jc * qq + 2.f * jc * qki * inv + kk * inv * inv) * r * r; jc = c1; }
-            }
+            if (ok != 0.f) ch = di < dj ? 1 : (dj < di ? 2 : 0);
+            if (ch == 1) { spk += g; spp += 2.f * a * inv + bb; ic += 1.f; }
+            else if (ch == 2) { sqk += g; sqq += 2.f * b * inv + bb; jc += 1.f; }
             if (lane == 0) { *(volatile int*)&S.choice[it] = ch; __threadfence_block(); *(volatile int*)&S.ready = it + 1; }
         }
     } else {
@@ -460,7 +471,7 @@ __device__ __forceinline__ float norm_leaf_group(int metric, const float* v, flo
 // update_mean on all threads, one barrier.
 template <int METRIC>
 __device__ __forceinline__ void create_split_cta(const BuildParams& P, Rng& rng /* thread 0 only */, const uint32_t* seg, uint32_t len,
-                                                 float* ws, TwoMeansShared& S, float* slot_ptr) {
+                                                 float* ws, TwoMeansShared& S, float* slot_ptr, float* mirror = nullptr /* second copy of the slot */) {
     constexpr int metric = METRIC;
     constexpr bool cosine = (METRIC == COSINE || METRIC == DOT_PRODUCT);
     const int d = (int)P.d, ld = (int)P.ld;
@@ -581,6 +592,7 @@ __device__ __forceinline__ void create_split_cta(const BuildParams& P, Rng& rng 
     float* out = slot_ptr + NORMAL_HDR;
     if (nn > 0.0f) { for (int i = tid; i < d; i += blockDim.x) nv[i] = __fdiv_rn(nv[i], nn); extra = (metric == DOT_PRODUCT) ? __fdiv_rn(extra, nn) : extra; }
     for (int i = tid; i < ld; i += blockDim.x) out[i] = nv[i];  // each thread re-reads only what it wrote
+    if (mirror != nullptr) for (int i = tid; i < ld; i += blockDim.x) mirror[NORMAL_HDR + i] = nv[i];
     if (metric == EUCLIDEAN || metric == MANHATTAN) {
         // bias = sum over i of ((-n_i) * (p_i + q_i)) / 2, folded left to right from +0.0
         for (int i = tid; i < d; i += blockDim.x) sc1[i] = __fdiv_rn(__fmul_rn(-nv[i], __fadd_rn(p[i], q[i])), 2.0f);
@@ -595,10 +607,12 @@ __device__ __forceinline__ void create_split_cta(const BuildParams& P, Rng& rng 
             }
             for (; i < d; ++i) bias = __fadd_rn(bias, sc1[i]);
             slot_ptr[0] = bias; slot_ptr[1] = 0.f; slot_ptr[2] = 0.f; slot_ptr[3] = 0.f;
+            if (mirror != nullptr) mirror[0] = bias;
         }
     } else if (tid == 0) {
         slot_ptr[0] = (metric == DOT_PRODUCT) ? extra : 0.f;  // Cosine normal header: norm = 0.0; Dot: {extra_dim, norm = 0.0}
         slot_ptr[1] = 0.f; slot_ptr[2] = 0.f; slot_ptr[3] = 0.f;
+        if (mirror != nullptr) mirror[0] = (metric == DOT_PRODUCT) ? extra : 0.f;
     }
     __syncthreads();
     TP_MARK(S, TP_FINISH_SPLIT);
@@ -700,103 +714,125 @@ __device__ __forceinline__ unsigned long long ld_vol64(const unsigned long long*
 __device__ __forceinline__ void st_vol64(unsigned long long* p, unsigned long long v) { *reinterpret_cast<volatile unsigned long long*>(p) = v; }
 __device__ __forceinline__ uint32_t ld_vol32(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
 
-// thread 0 of a control CTA, after every thread's writes were fenced and a CTA barrier: open `total` units of the job in P.jobs[t]
-__device__ __forceinline__ void ppublish(PSlot& sl, uint32_t total, uint32_t chunk) {
-    const uint32_t seq = (uint32_t)(ld_vol64(&sl.hdr) >> 32) + 1u;
-    *reinterpret_cast<volatile uint32_t*>(&sl.done) = 0u;
-    *reinterpret_cast<volatile uint32_t*>(&sl.chunk) = chunk;
+// thread 0 of a control CTA, after every thread's writes were fenced and a CTA barrier: open `total` units of `jb` (epoch seq)
+__device__ __forceinline__ void ppublish(PSlot& sl, const Job& jb, uint32_t seq, uint32_t total, uint32_t chunk) {
+    volatile PSlot* v = &sl;
+    v->rows = jb.rows; v->flags = jb.flags; v->unit_left = jb.unit_left; v->dst = jb.dst;
+    v->len = jb.len; v->kind = (uint32_t)jb.kind; v->total_left = jb.total_left; v->chunk = chunk;
+    v->done = (unsigned long long)seq << 32;
     __threadfence();
-    st_vol64(&sl.hdr, ((unsigned long long)seq << 32) | total);     // header first: whoever sees the new ticket also sees it
-    __threadfence();
-    st_vol64(&sl.ticket, (unsigned long long)seq << 32);
+    v->ticket = pticket(seq, total, 0u);
 }
 // ... and wait until the workers have reported all of them. false: error / cancel / no progress for ~4 s (never on a sane run)
-__device__ __forceinline__ bool pwait(const BuildParams& P, PSlot& sl, uint32_t total) {
+__device__ __forceinline__ bool pwait(const BuildParams& P, PSlot& sl, uint32_t seq, uint32_t total) {
     const long long t0 = clock64();
     uint32_t spins = 0;
+    const unsigned long long want = ((unsigned long long)seq << 32) | total;
     for (;;) {
-        if (ld_vol32(&sl.done) >= total) { __threadfence(); return true; }
+        if (ld_vol64(&sl.done) == want) { __threadfence(); return true; }
         if ((++spins & 63u) == 0u) {
             if (*reinterpret_cast<volatile int32_t*>(P.error) != ERR_NONE) return false;
             if (P.abort != nullptr && *P.abort != 0) { atomicCAS(P.error, ERR_NONE, ERR_ABORT); return false; }
             if (clock64() - t0 > 8000000000ll) { atomicCAS(P.error, ERR_NONE, ERR_HANG); return false; }
         }
-        __nanosleep(40);
+        __nanosleep(20);
     }
 }
 
 // A worker CTA: claims units of whatever the control CTAs have published and runs the same scan / partition code as work_kernel.
 // Returns when every tree is done (or on error). sm_normal: ld floats of dynamic shared memory.
 __device__ __noinline__ void pworker(const BuildParams& P, float* sm_normal) {
-    __shared__ uint32_t w_t, w_u0, w_n, w_seq, w_found, w_exit, w_count;
+    __shared__ uint32_t w_t, w_u0, w_n, w_seq, w_pseq, w_found, w_exit, w_count;
+    __shared__ PSlot w_job;        // fields of the claimed job (first 64 bytes)
     __shared__ uint32_t w_sm[16];
     const uint32_t T = P.n_trees;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t rot = (blockIdx.x - T) * 7u;
-    uint32_t loaded_t = 0xffffffffu, loaded_seq = 0;
+    uint32_t loaded_t = 0xffffffffu, loaded_seq = 0xffffffffu;
     float nh0 = 0.f;
     if (tid == 0) w_exit = 0;
     for (;;) {
+        // ---- poll: one load per slot, 32 slots per pass; pick a slot with unclaimed units ----
         if (warp == 0) {
             uint32_t found = 0;
             for (uint32_t base = 0; base < T && !found; base += 32) {
                 const uint32_t k = base + lane;
                 const uint32_t t = k < T ? (rot + k) % T : 0u;
-                unsigned long long tk = 0, hdr = 0;
-                if (k < T) { tk = ld_vol64(&P.slots[t].ticket); __threadfence(); hdr = ld_vol64(&P.slots[t].hdr); }
-                const bool cand = k < T && (uint32_t)hdr != 0u && (tk >> 32) == (hdr >> 32) && (uint32_t)tk < (uint32_t)hdr;
-                unsigned m = __ballot_sync(0xffffffffu, cand);
-                while (m != 0u && !found) {
+                const unsigned long long tk = k < T ? ld_vol64(&P.slots[t].ticket) : 0ull;
+                const unsigned m = __ballot_sync(0xffffffffu, k < T && pt_next(tk) < pt_total(tk));
+                if (m != 0u) {
                     const int src = __ffs((int)m) - 1;
-                    m &= m - 1u;
-                    uint32_t ok = 0;
-                    if (lane == src) {
-                        const uint32_t chunk = max(1u, ld_vol32(&P.slots[t].chunk));
-                        const unsigned long long r = atomicAdd(&P.slots[t].ticket, (unsigned long long)chunk);
-                        __threadfence();
-                        const uint32_t rseq = (uint32_t)(r >> 32), rn = (uint32_t)r;
-                        unsigned long long h2 = ld_vol64(&P.slots[t].hdr);
-                        while ((uint32_t)(h2 >> 32) != rseq) {   // the claim fell into a newer epoch than the header this lane had read: wait for that header
-                            if ((int32_t)((uint32_t)(h2 >> 32) - rseq) > 0) break;   // (cannot happen: an epoch does not end with an unreported claim)
-                            h2 = ld_vol64(&P.slots[t].hdr);
-                        }
-                        const uint32_t total = (uint32_t)h2;
-                        if ((uint32_t)(h2 >> 32) == rseq && rn < total) { w_t = t; w_u0 = rn; w_n = min(chunk, total - rn); w_seq = rseq; ok = 1; }
-                    }
-                    found = __shfl_sync(0xffffffffu, ok, src);
+                    if (lane == src) { w_t = t; w_pseq = pt_seq(tk); }
+                    found = 1;
                 }
             }
             if (lane == 0) {
                 w_found = found;
                 if (!found) {
                     if (ld_vol32(P.active) == 0u || *reinterpret_cast<volatile int32_t*>(P.error) != ERR_NONE) w_exit = 1;
-                    else __nanosleep(100);
+                    else __nanosleep(60);
                 }
             }
         }
         __syncthreads();
         if (w_exit) return;
-        if (w_found) {
-            const uint32_t t = w_t, u0 = w_u0, nu = w_n, seq = w_seq;
-            const volatile Job* vj = &P.jobs[t];
+        if (!w_found) { __syncthreads(); continue; }
+        // ---- claim; the job fields and (scan jobs) the normal are loaded while the atomic is in flight ----
+        const uint32_t t = w_t;
+        PSlot& sl = P.slots[t];
+        const float* nsrc = P.cur_normal + (size_t)t * P.pool_stride;
+        const bool want_normal = !(loaded_t == t && loaded_seq == w_pseq);
+        float nreg[8];   // ld <= 8 * blockDim is guaranteed by the host for this schedule
+#pragma unroll
+        for (int u = 0; u < 8; ++u) nreg[u] = 0.f;
+        if (want_normal) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { const uint32_t i = tid + u * CTRL_THREADS; if (i < P.ld) nreg[u] = __ldcg(nsrc + NORMAL_HDR + i); }
+        }
+        if (tid == 0) {
+            const unsigned long long r = atomicAdd(&sl.ticket, 1ull);   // a claim is one group of `chunk` units
+            const uint4 f0 = __ldcg(reinterpret_cast<const uint4*>(&sl) + 1), f1 = __ldcg(reinterpret_cast<const uint4*>(&sl) + 2), f2 = __ldcg(reinterpret_cast<const uint4*>(&sl) + 3);
+            uint4* wj = reinterpret_cast<uint4*>(&w_job);
+            wj[1] = f0; wj[2] = f1; wj[3] = f2;
+            w_seq = pt_seq(r);
+            w_u0 = pt_next(r);
+            w_n = pt_next(r) < pt_total(r) ? 1u : 0u;
+        }
+        __syncthreads();
+        const uint32_t seq = w_seq, g0 = w_u0;
+        const bool have = w_n != 0u;
+        if (have && seq != w_pseq) {
+            // The claim fell into a NEWER epoch than the polled one (this CTA raced with the publication of the tree's next job):
+            // the group is real and must be processed — reload the fields and the normal of that epoch. (Its fields were complete
+            // before its ticket was stored, and it cannot end while this claim is unreported.)
+            if (tid == 0) { uint4* wj = reinterpret_cast<uint4*>(&w_job); wj[1] = __ldcg(reinterpret_cast<const uint4*>(&sl) + 1); wj[2] = __ldcg(reinterpret_cast<const uint4*>(&sl) + 2); wj[3] = __ldcg(reinterpret_cast<const uint4*>(&sl) + 3); }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { const uint32_t i = tid + u * CTRL_THREADS; if (i < P.ld) nreg[u] = __ldcg(nsrc + NORMAL_HDR + i); }
+            __syncthreads();
+        }
+        if (have) {
             Job jb;
-            jb.kind = vj->kind; jb.len = vj->len; jb.rows = vj->rows; jb.normal = vj->normal; jb.flags = vj->flags; jb.margins = nullptr;
-            jb.unit_left = vj->unit_left; jb.dst = vj->dst; jb.total_left = vj->total_left; jb.pad = 0;
+            jb.kind = (int)w_job.kind; jb.len = w_job.len; jb.rows = w_job.rows; jb.normal = nullptr; jb.flags = w_job.flags; jb.margins = nullptr;
+            jb.unit_left = w_job.unit_left; jb.dst = w_job.dst; jb.total_left = w_job.total_left; jb.pad = 0;
+            const uint32_t chunk = max(1u, w_job.chunk);
             if (jb.kind == JOB_SCAN) {
-                if (loaded_t != t || loaded_seq != seq) {
-                    for (uint32_t i = tid; i < P.ld; i += blockDim.x) sm_normal[i] = __ldcg(jb.normal + NORMAL_HDR + i);
-                    nh0 = __ldcg(jb.normal);
+                const uint32_t units = (jb.len + SCAN_UNIT - 1) / SCAN_UNIT;
+                if (want_normal || seq != w_pseq) {
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) { const uint32_t i = tid + u * CTRL_THREADS; if (i < P.ld) sm_normal[i] = nreg[u]; }
+                    nh0 = __ldcg(nsrc);
                     loaded_t = t; loaded_seq = seq;
                     __syncthreads();
                 }
-                for (uint32_t u = u0; u < u0 + nu; ++u) scan_unit(jb, u, P.items, P.ih0, P.d, P.ld, P.metric, sm_normal, nh0, &w_count);
+                for (uint32_t u = g0 * chunk; u < min(units, (g0 + 1u) * chunk); ++u) scan_unit(jb, u, P.items, P.ih0, P.d, P.ld, P.metric, sm_normal, nh0, &w_count);
             } else if (jb.kind == JOB_PARTITION) {
-                for (uint32_t u = u0; u < u0 + nu; ++u)
+                const uint32_t units = (jb.len + PART_UNIT - 1) / PART_UNIT;
+                for (uint32_t u = g0 * chunk; u < min(units, (g0 + 1u) * chunk); ++u)
                     partition_block(jb.rows, jb.flags, jb.dst, u * PART_UNIT, jb.len, __ldcg(jb.unit_left + u * (PART_UNIT / SCAN_UNIT)), jb.total_left, w_sm);
             }
             __threadfence();
             __syncthreads();
-            if (tid == 0) atomicAdd(&P.slots[t].done, nu);
+            if (tid == 0) atomicAdd(&sl.done, 1ull);
         }
         __syncthreads();
     }
@@ -844,6 +880,7 @@ __global__ void __launch_bounds__(CTRL_THREADS, (CS == 0 ? 2 : 1)) control_kerne
     __shared__ TreeState S;
 
     __shared__ int s_wait_ok;
+    __shared__ uint32_t s_pseq;   // epoch of this tree's job slot (persistent schedule)
     const uint32_t t = blockIdx.x / CSD + tree_base;
     Job& job = P.jobs[t];
     unsigned crank = 0;
@@ -879,7 +916,7 @@ __global__ void __launch_bounds__(CTRL_THREADS, (CS == 0 ? 2 : 1)) control_kerne
     uint32_t* unit_left = P.unit_left + (size_t)t * P.units_per_tree;
     const int tid = threadIdx.x;
 
-    if (tid == 0) { s_rng.init(S.key, S.pos); job.kind = JOB_NONE; TM.mismatch = 0; }
+    if (tid == 0) { s_rng.init(S.key, S.pos); job.kind = JOB_NONE; TM.mismatch = 0; s_pseq = 0; }
     uint32_t total_left = 0;
     if (S.phase == PH_AWAIT_SCAN) {
         const Frame f = FR(S.sp);
@@ -988,8 +1025,9 @@ __global__ void __launch_bounds__(CTRL_THREADS, (CS == 0 ? 2 : 1)) control_kerne
         uint32_t* dst = (f.parity ? perm0 : perm1) + f.start;
         if (action == ACT_SPLIT) {
             float* slot_ptr = P.pool + (size_t)S.cur_slot * P.pool_stride;
-            if (SMEM_WS) create_split_cta<METRIC>(P, s_rng, src, f.len, reinterpret_cast<float*>(ctrl_smem), TM, slot_ptr);
-            else create_split_cta<METRIC>(P, s_rng, src, f.len, P.scratch + (size_t)t * WS_VECS * P.ld, TM, slot_ptr);
+            float* mirror = PERSIST ? P.cur_normal + (size_t)t * P.pool_stride : nullptr;   // where the workers fetch the open job's normal
+            if (SMEM_WS) create_split_cta<METRIC>(P, s_rng, src, f.len, reinterpret_cast<float*>(ctrl_smem), TM, slot_ptr, mirror);
+            else create_split_cta<METRIC>(P, s_rng, src, f.len, P.scratch + (size_t)t * WS_VECS * P.ld, TM, slot_ptr, mirror);
             if (tid == 0) {
                 if (TM.mismatch) { S.n_misspec += 1; TM.mismatch = 0; }
                 S.n_splits_tried += 1; if (P.timing) TM.tacc[TP_ATTEMPTS] += 1;
@@ -999,13 +1037,16 @@ __global__ void __launch_bounds__(CTRL_THREADS, (CS == 0 ? 2 : 1)) control_kerne
                 if (CS > 1 && f.len <= P.small_max && inner < P.max_inner) job.pad = 1;
             }
             if (PERSIST) {
-                // the normal (written by every thread) and the job fields must be visible device-wide before the job opens
+                // the normal (create_split also wrote it to the tree's fixed place, where workers fetch it while their claim is in
+                // flight) and the job fields must be visible device-wide before the job opens
                 __threadfence();
                 __syncthreads();
                 const uint32_t units = (f.len + SCAN_UNIT - 1) / SCAN_UNIT;
                 if (tid == 0) {
-                    ppublish(P.slots[t], units, units > 1024u ? 4u : 1u);
-                    s_wait_ok = pwait(P, P.slots[t], units) ? 1 : 0;
+                    s_pseq += 1;
+                    const uint32_t chunk = units > 1024u ? 4u : 1u, groups = (units + chunk - 1) / chunk;   // a claim = `chunk` units
+                    ppublish(P.slots[t], job, s_pseq, groups, chunk);
+                    s_wait_ok = pwait(P, P.slots[t], s_pseq, groups) ? 1 : 0;
                     if (P.timing) TM.tacc[TP_INNER] += 1;
                 }
                 __syncthreads();
@@ -1066,7 +1107,7 @@ __global__ void __launch_bounds__(CTRL_THREADS, (CS == 0 ? 2 : 1)) control_kerne
             __threadfence();
             __syncthreads();
             const uint32_t units = (f.len + PART_UNIT - 1) / PART_UNIT;
-            if (tid == 0) { ppublish(P.slots[t], units, 4u); s_wait_ok = pwait(P, P.slots[t], units) ? 1 : 0; }
+            if (tid == 0) { s_pseq += 1; const uint32_t groups = (units + 3u) / 4u; ppublish(P.slots[t], job, s_pseq, groups, 4u); s_wait_ok = pwait(P, P.slots[t], s_pseq, groups) ? 1 : 0; }
             __syncthreads();
             if (!s_wait_ok) break;
             if (tid == 0) { FR(S.sp).stage = 1; S.phase = PH_AWAIT_PART; }
