@@ -289,18 +289,20 @@ __device__ __forceinline__ bool spec_two_means(const BuildParams& P, float* ws, 
             if (ok != 0.f) ch = di < dj ? 1 : (dj < di ? 2 : 0);
             if (ch == 1) { spk += g; spp += 2.f * a * inv + bb; ic += 1.f; }
             else if (ch == 2) { sqk += g; sqq += 2.f * b * inv + bb; jc += 1.f; }
-            if (lane == 0) { *(volatile int*)&S.choice[it] = ch; __threadfence_block(); *(volatile int*)&S.ready = it + 1; }
+            if (lane == 0) S.choice[it] = ch;
         }
-    } else {
+    }
+    // (the other warps wait here without issuing: a spinning warp on warp 0's scheduler would halve the recurrence's speed)
+    __syncthreads();
+    {
         // the centroid versions, element-wise and in the reference's exact operations; every thread only re-reads elements it
-        // wrote itself, so the ten steps need no barrier — only the published choice
-        const int nt = CTRL_THREADS - 32, t = tid - 32;
+        // wrote itself, so the ten steps need no barrier
+        const int nt = CTRL_THREADS, t = tid;
         float ic = 1.f, jc = 1.f;
         int ps = 0, qs = 1;
 #pragma unroll 1
         for (int it = 0; it < 10; ++it) {
-            while (*(volatile int*)&S.ready <= it) { }
-            const int ch = *(volatile int*)&S.choice[it];
+            const int ch = S.choice[it];
             if (ch == 0) continue;
             const float* k = ws + (size_t)(2 + it) * ld;
             const float norm = cosine ? S.nk[2 + it] : 1.0f;
@@ -643,25 +645,28 @@ __device__ __noinline__ void partition_inline(const uint32_t* __restrict__ src, 
             if (lane == 0) { sm_pw[j * 8 + warp] = __popc(lm[j]); sm_pw[PART_BATCH * 8 + j * 8 + warp] = __popc(rm[j]); }
         }
         __syncthreads();
-        // offsets in source order: sub-blocks in order, warps in order inside a sub-block
+        // source order = sub-blocks in order, warps in order inside a sub-block = the index order of sm_pw: warp 0 turns the 64
+        // Left counts and the 64 Right counts into exclusive prefixes (two entries per lane), entry 128 / 129 = the totals
+        if (warp == 0) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const uint32_t a = sm_pw[h * 64 + 2 * lane], b = sm_pw[h * 64 + 2 * lane + 1];
+                uint32_t inc = a + b;
+                for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += y; }
+                const uint32_t ex = inc - (a + b);
+                sm_pw[h * 64 + 2 * lane] = ex; sm_pw[h * 64 + 2 * lane + 1] = ex + a;
+                if (lane == 31) sm_pw[128 + h] = inc;
+            }
+        }
+        __syncthreads();
         const unsigned below = (1u << lane) - 1u;
         const uint32_t right_before = base - left_before;
-        uint32_t run_l = 0, run_r = 0;
 #pragma unroll
         for (int j = 0; j < PART_BATCH; ++j) {
-            uint32_t wl = 0, wr = 0, jl = 0, jr = 0;
-#pragma unroll
-            for (int w = 0; w < 8; ++w) {
-                const uint32_t a = sm_pw[j * 8 + w], b = sm_pw[PART_BATCH * 8 + j * 8 + w];
-                jl += a; jr += b;
-                if (w < warp) { wl += a; wr += b; }
-            }
-            if (fl[j] == 0) dst[left_before + run_l + wl + __popc(lm[j] & below)] = id[j];
-            else if (fl[j] == 1) dst[total_left + right_before + run_r + wr + __popc(rm[j] & below)] = id[j];
-            run_l += jl; run_r += jr;
+            if (fl[j] == 0) dst[left_before + sm_pw[j * 8 + warp] + __popc(lm[j] & below)] = id[j];
+            else if (fl[j] == 1) dst[total_left + right_before + sm_pw[64 + j * 8 + warp] + __popc(rm[j] & below)] = id[j];
         }
-        const uint32_t ltot = run_l;
-        left_before += ltot;
+        left_before += sm_pw[128];
         __syncthreads();
     }
 }
