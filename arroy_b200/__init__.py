@@ -4,4 +4,4 @@
 The compute path is the CUDA library only; importing this package never touches oracle/.
 """
 from ._capi import (Arena, ArroyB200Error, Context, Group, COSINE, DOT_PRODUCT, EUCLIDEAN, MANHATTAN, METRICS, METRIC_NAMES, LIB_PATH, SIGNATURES, load)  # noqa: F401
-from .api import ArroyBuilder, ArroyError, Env, QueryBuilder, Reader, StdRng, Writer  # noqa: F401,E402
+from .api import ArroyBuilder, ArroyError, Env, QueryBuilder, Reader, StdRng, Writer, reencode  # noqa: F401,E402

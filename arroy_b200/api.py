@@ -18,6 +18,8 @@ HOST_SIGNATURES = [
     ("arroy_env_free", None, [C.c_void_p]),
     ("arroy_env_len", C.c_uint64, [C.c_void_p]),
     ("arroy_env_iter", C.c_int32, [C.c_void_p, KV_SINK, C.c_void_p]),
+    ("arroy_env_put_raw", C.c_int32, [C.c_void_p, C.c_char_p, C.c_uint64, C.c_char_p, C.c_uint64]),
+    ("arroy_host_reencode", C.c_int32, [C.c_int32, C.c_char_p, C.c_uint64, C.c_char_p, C.c_uint64, _u64p]),
     ("arroy_rng_from_seed", C.c_void_p, [_u8p]),
     ("arroy_rng_seed_from_u64", C.c_void_p, [C.c_uint64]),
     ("arroy_rng_clone", C.c_void_p, [C.c_void_p]),
@@ -120,6 +122,14 @@ class StdRng:
         return out
 
 
+def reencode(what, value):
+    """Decode `value` with the library's decoders and encode it again ('node' | 'metadata'): a faithful codec returns the input."""
+    out = C.create_string_buffer(len(value) + 64)
+    n = C.c_uint64(0)
+    _ck(_lib().arroy_host_reencode(0 if what == "node" else 1, value, len(value), out, len(value) + 64, C.byref(n)))
+    return out.raw[:n.value]
+
+
 class Env:
     """Stands in for heed::Env + Database<D>: ordered key/value table + the GPU context."""
 
@@ -148,6 +158,10 @@ class Env:
         cb = KV_SINK(sink)
         _ck(_lib().arroy_env_iter(self.h, cb, None))
         return out
+
+    def put_raw(self, key, value):
+        """Insert one (key, value) pair as is (importing the content of a real arroy LMDB file)."""
+        _ck(_lib().arroy_env_put_raw(self.h, key, len(key), value, len(value)))
 
     def tree_nodes(self, index=0):
         """{node id: NodeCodec bytes} of one index."""

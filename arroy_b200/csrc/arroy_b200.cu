@@ -462,7 +462,12 @@ void build_wave(arroy_ctx* c, size_t wave_no, uint32_t t0, uint32_t tw, const ui
     int pgrid = 0;
     size_t psmem = ctrl_smem;
     const void* ctrlp = nullptr;
-    if (!lockstep && use_smem && ld <= 8u * CTRL_THREADS && n < (1ull << 29) && !(getenv("ARROY_B200_PERSIST") && atoi(getenv("ARROY_B200_PERSIST")) == 0)) {
+    // It wins where the chain of attempts is the critical path (few trees per GPU, small indexes); a wave that is bandwidth-bound
+    // from start to end (10M x 100 trees) runs a little faster on work_kernel's three scanning CTAs per SM.
+    // ARROY_B200_PERSIST = 0 | 1 overrides the choice.
+    const char* pe = getenv("ARROY_B200_PERSIST");
+    const bool pwant = pe ? atoi(pe) != 0 : (double)n * (double)tw <= 2.0e8;
+    if (pwant && !lockstep && use_smem && ld <= 8u * CTRL_THREADS && n < (1ull << 29)) {
         ctrlp = control_fn(true, 0, c->metric);
         const size_t cand[2] = {ctrl_smem, (size_t)WS_VECS * ld * 4};
         for (int k = 0; k < 2 && !persist; ++k) {

@@ -829,7 +829,7 @@ __device__ __noinline__ void pworker(const BuildParams& P, float* sm_normal) {
                     loaded_t = t; loaded_seq = seq;
                     __syncthreads();
                 }
-                for (uint32_t u = g0 * chunk; u < min(units, (g0 + 1u) * chunk); ++u) scan_unit(jb, u, P.items, P.ih0, P.d, P.ld, P.metric, sm_normal, nh0, &w_count);
+                for (uint32_t u = g0 * chunk; u < min(units, (g0 + 1u) * chunk); ++u) scan_unit<true>(jb, u, P.items, P.ih0, P.d, P.ld, P.metric, sm_normal, nh0, &w_count);
             } else if (jb.kind == JOB_PARTITION) {
                 const uint32_t units = (jb.len + PART_UNIT - 1) / PART_UNIT;
                 for (uint32_t u = g0 * chunk; u < min(units, (g0 + 1u) * chunk); ++u)

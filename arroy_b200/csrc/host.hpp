@@ -1076,6 +1076,41 @@ int32_t arroy_env_iter(arroy_env* e, arroy_kv_sink sink, void* arg) {
     });
 }
 
+// Raw access to the table (tests: importing the key/value pairs of a real LMDB file; exporting ours).
+int32_t arroy_env_put_raw(arroy_env* e, const uint8_t* key, uint64_t key_len, const uint8_t* val, uint64_t val_len) {
+    return hguard([&] {
+        if (key_len != 8) throw HostError(ARROY_ERR_PANIC, "arroy keys are 8 bytes (src/key.rs:56-68)");
+        std::lock_guard<std::mutex> lk(e->mu);
+        Key8 k;
+        memcpy(k.data(), key, 8);
+        e->kv[k] = std::string(reinterpret_cast<const char*>(val), val_len);
+        e->touch((uint16_t)(((uint16_t)key[0] << 8) | key[1]));
+    });
+}
+
+// Decode a stored value with the product's decoders and encode it again with the product's encoders (what = 0: a tree node,
+// NodeCodec src/node.rs:218-282; 1: Metadata, src/metadata.rs:21-61). A faithful codec returns the input bytes.
+int32_t arroy_host_reencode(int32_t what, const uint8_t* in, uint64_t len, uint8_t* out, uint64_t cap, uint64_t* out_len) {
+    return hguard([&] {
+        std::string res;
+        const std::string v(reinterpret_cast<const char*>(in), len);
+        if (what == 0) res = encode_tree_node(decode_tree_node(v));
+        else {
+            arroy_env tmp;
+            tmp.kv[make_key(0, MODE_METADATA, 0)] = v;
+            Metadata m;
+            read_metadata(&tmp, 0, m);
+            int metric = -1;
+            for (int k = 0; k < 4; ++k) if (m.distance == metric_name(k)) metric = k;
+            if (metric < 0) throw HostError(ARROY_ERR_UNMATCHING_DISTANCE, "unknown distance name " + m.distance);
+            res = encode_metadata(metric, m.dims, m.items, m.roots);
+        }
+        *out_len = res.size();
+        if (res.size() > cap) throw HostError(ARROY_ERR_PANIC, "output buffer too small");
+        memcpy(out, res.data(), res.size());
+    });
+}
+
 arroy_rng* arroy_rng_from_seed(const uint8_t seed[32]) {
     auto* r = new arroy_rng();
     uint32_t key[8];

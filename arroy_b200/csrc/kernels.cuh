@@ -53,6 +53,9 @@ __device__ __forceinline__ float margin_finish(int metric, float dot, float nh0,
 
 // One scan unit: SCAN_UNIT consecutive positions of a job. d >= 32: 8 lanes per row, float4
 // loads, two rows in flight per group. sm_normal: the job's normal vector in shared memory.
+// DEEP: eight 32-float chunks of both rows in flight instead of four (the persistent schedule runs fewer scanning warps per SM
+// than work_kernel's three CTAs, so each warp has to keep more bytes in flight to saturate HBM).
+template <bool DEEP = false>
 __device__ __forceinline__ void scan_unit(const Job& jb, uint32_t unit, const float* __restrict__ items, const float* __restrict__ ih0,
                                           uint32_t d, uint32_t ld, int metric, const float* sm_normal, float nh0, uint32_t* sm_count) {
     const uint32_t base = unit * SCAN_UNIT;
@@ -73,8 +76,24 @@ __device__ __forceinline__ void scan_unit(const Job& jb, uint32_t unit, const fl
         const float4* N = reinterpret_cast<const float4*>(sm_normal);
         float4 acca = make_float4(0.f, 0.f, 0.f, 0.f), accb = acca;
         const int nch = d >> 5;
+        int c = 0;
+        if (DEEP) {
+            for (; c + 8 <= nch; c += 8) {
+                float4 x[8], z[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) { x[u] = ldg_stream(A + (c + u) * 8 + g8); z[u] = ldg_stream(B + (c + u) * 8 + g8); }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const float4 y = N[(c + u) * 8 + g8];
+                    acca.x = fmaf(x[u].x, y.x, acca.x); acca.y = fmaf(x[u].y, y.y, acca.y);
+                    acca.z = fmaf(x[u].z, y.z, acca.z); acca.w = fmaf(x[u].w, y.w, acca.w);
+                    accb.x = fmaf(z[u].x, y.x, accb.x); accb.y = fmaf(z[u].y, y.y, accb.y);
+                    accb.z = fmaf(z[u].z, y.z, accb.z); accb.w = fmaf(z[u].w, y.w, accb.w);
+                }
+            }
+        }
 #pragma unroll 4
-        for (int c = 0; c < nch; ++c) {
+        for (; c < nch; ++c) {
             float4 x = ldg_stream(A + c * 8 + g8);
             float4 z = ldg_stream(B + c * 8 + g8);
             float4 y = N[c * 8 + g8];

@@ -58,6 +58,12 @@ uint64_t arroy_env_len(arroy_env* env);
 typedef int32_t (*arroy_kv_sink)(void* arg, const uint8_t* key, uint64_t key_len, const uint8_t* val, uint64_t val_len);
 int32_t arroy_env_iter(arroy_env* env, arroy_kv_sink sink, void* arg);
 
+/* raw put of one (key, value) pair — importing the content of a real arroy LMDB file (keys are the 8 bytes of src/key.rs:56-68) */
+int32_t arroy_env_put_raw(arroy_env* env, const uint8_t* key, uint64_t key_len, const uint8_t* val, uint64_t val_len);
+/* decode a stored value with the library's decoders and encode it again with its encoders (what = 0: tree node, 1: Metadata);
+ * used to pin the codecs (RoaringBitmap bytes included) against files written by the reference */
+int32_t arroy_host_reencode(int32_t what, const uint8_t* in, uint64_t len, uint8_t* out, uint64_t cap, uint64_t* out_len);
+
 /* ---- StdRng -------------------------------------------------------------------------------- */
 arroy_rng* arroy_rng_from_seed(const uint8_t seed[32]);
 arroy_rng* arroy_rng_seed_from_u64(uint64_t state);

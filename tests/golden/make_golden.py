@@ -135,6 +135,18 @@ def main():
     m = re.search(r"by_vector\(&rtxn, &\[0\.0; 30\]\).*?@r\"(.*?)\"", up, re.S)
     if m:
         g["upgrade_nns_zero"] = [[int(a), b] for a, b in re.findall(r"id\((\d+)\): distance\(([-\d\.eE]+)\)", m.group(1))]
+    # src/tests/upgrade.rs: the two LMDB files the reference ships (written by arroy v0.6 through heed / LMDB / roaring) are
+    # copied as binary fixtures; the post-upgrade dumps and the pre-upgrade query results are the goldens they are checked against
+    import shutil
+    for name in ("smol", "large"):
+        shutil.copyfile(os.path.join(REF, "src/tests/assets/v0_6", name + ".mdb"), os.path.join(OUT, "v0_6_%s.mdb" % name))
+    g["upgrade_large_dump"] = snap_file("arroy__tests__upgrade__large_upgrade_v0_6_to_v0_7-10.snap")
+    for line_no, lines in inline_snapshots("src/tests/upgrade.rs"):
+        if any(l.strip().startswith("Root: Metadata") for l in lines) and any("Version:" in l for l in lines):
+            g["upgrade_smol_dump"] = parse_dump(lines)
+    m = re.search(r"by_vector\(&rtxn, &\[1\.0, 0\.0\]\).*?@r\"(.*?)\"", up, re.S)
+    if m:
+        g["upgrade_smol_nns"] = [[int(a), b] for a, b in re.findall(r"id\((\d+)\): distance\(([-\d\.eE]+)\)", m.group(1))]
     # target_n_trees table — src/tests/writer.rs:14-79
     with open(os.path.join(REF, "src/tests/writer.rs")) as f:
         w = f.read()
