@@ -114,7 +114,7 @@ struct arroy_ctx {
     PinBuf pin;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaStream_t side_stream = nullptr;   // host -> device flags while the persistent build kernel occupies `stream`
-    cudaEvent_t ev_done = nullptr;
+    cudaEvent_t ev_done = nullptr, ev_p0 = nullptr, ev_p1 = nullptr;   // ev_p0 / ev_p1 bracket the persistent build kernel
     double stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     uint64_t n_launches = 0, h2d_bytes = 0, d2h_bytes = 0;  // since create (arroy_b200_counters)
     cudaEvent_t tev0 = nullptr, tev1 = nullptr;
@@ -561,7 +561,9 @@ void build_wave(arroy_ctx* c, size_t wave_no, uint32_t t0, uint32_t tw, const ui
         cfg.attrs = at; cfg.numAttrs = 1;
         uint32_t tree_base = 0;
         void* args[2] = {&P, &tree_base};
+        CK(cudaEventRecord(c->ev_p0, c->stream));
         CK(cudaLaunchKernelExC(&cfg, ctrlp, args));
+        CK(cudaEventRecord(c->ev_p1, c->stream));
         CK(cudaEventRecord(c->ev_done, c->stream));
         if (cancel) {   // polled while the kernel runs (BuildOption::cancel, src/writer.rs:116-124)
             bool aborted = false;
@@ -582,6 +584,7 @@ void build_wave(arroy_ctx* c, size_t wave_no, uint32_t t0, uint32_t tw, const ui
         CK(cudaStreamSynchronize(c->stream));
         steps = 1;
         c->n_launches += 1;
+        { float kms = 0; CK(cudaEventElapsedTime(&kms, c->ev_p0, c->ev_p1)); c->stats[5] += kms; }   // the kernel that holds every scan of the wave
         if (*h_error != ERR_NONE) {
             const int e = *h_error;
             if (e == ERR_ABORT) throw Cancelled("The corresponding build process has been cancelled");
@@ -1093,6 +1096,8 @@ int32_t arroy_b200_create(int32_t device, arroy_ctx** out) {
         CK(cudaEventCreate(&c->ev1));
         CK(cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking));
         CK(cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming));
+        CK(cudaEventCreate(&c->ev_p0));
+        CK(cudaEventCreate(&c->ev_p1));
         CK(cudaEventCreate(&c->tev0));
         CK(cudaEventCreate(&c->tev1));
         // fail loudly if the kernels were not built for this device
@@ -1130,6 +1135,8 @@ void arroy_b200_destroy(arroy_ctx* c) {
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->ev_done) cudaEventDestroy(c->ev_done);
+    if (c->ev_p0) cudaEventDestroy(c->ev_p0);
+    if (c->ev_p1) cudaEventDestroy(c->ev_p1);
     if (c->side_stream) cudaStreamDestroy(c->side_stream);
     if (c->tev0) cudaEventDestroy(c->tev0);
     if (c->tev1) cudaEventDestroy(c->tev1);

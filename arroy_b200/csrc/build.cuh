@@ -764,8 +764,14 @@ __device__ __noinline__ void pworker(const BuildParams& P, float* sm_normal) {
                 const uint32_t k = base + lane;
                 const uint32_t t = k < T ? (rot + k) % T : 0u;
                 const unsigned long long tk = k < T ? ld_vol64(&P.slots[t].ticket) : 0ull;
-                const unsigned m = __ballot_sync(0xffffffffu, k < T && pt_next(tk) < pt_total(tk));
-                if (m != 0u) {
+                // among the open jobs prefer the one with the fewest groups: small nodes sit on their tree's critical path, the
+                // big scans only need bandwidth and are never starved (every worker comes back to them when nothing small is open)
+                uint32_t key = (k < T && pt_next(tk) < pt_total(tk)) ? pt_total(tk) : 0xffffffffu;
+                uint32_t best = key;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+                if (best != 0xffffffffu) {
+                    const unsigned m = __ballot_sync(0xffffffffu, key == best);
                     const int src = __ffs((int)m) - 1;
                     if (lane == src) { w_t = t; w_pseq = pt_seq(tk); }
                     found = 1;

@@ -446,7 +446,8 @@ def build_record(wl, tb, world):
     return {"scanned_rows_per_step": sc, "device_steps": tb["stats"]["steps"], "create_split_calls": tb["stats"]["create_split_calls"],
             "random_splits": tb["stats"]["random_splits"], "algorithmic_GB_per_step": sc * d * 4 / 1e9,
             "whole_build_GBps": sc * d * 4 / 1e9 / (tb["ms_per_step"] * 1e-3),
-            "schedule": "lockstep" if os.environ.get("ARROY_B200_LOCKSTEP") else "async per-tree graph branches", "breakdown_ms_last_step": tb["breakdown"]}
+            "schedule": "lockstep" if os.environ.get("ARROY_B200_LOCKSTEP") else ("persistent: one cooperative launch per wave (control CTA per tree + worker CTAs)" if tb["stats"]["steps"] == 1 else "async per-tree graph branches (control / work kernel per attempt)"),
+            "misspeculated_two_means": tb["stats"].get("misspeculated_splits", 0.0), "breakdown_ms_last_step": tb["breakdown"]}
 
 
 def leaf_blob(rig, wl, items):
@@ -530,15 +531,8 @@ def e2e_multi(rig, wl, items, seeds, steps, n_warm):
         if step == n_warm:
             cc0 = ctx.counters()
         t0 = time.perf_counter()
-        if rig.rank == 0:
-            ctx.stage_items_ptrs(metric, d, ids, ptrs)
-            (p_items, _, _), ld_items = ctx.device_ptrs()
-            src = torch.as_tensor(_DevView(p_items, (n, ld_items)), device=rig.dev)
-            parallel.broadcast_items(dist, src, src=0)
-        else:
-            parallel.broadcast_items(dist, items, src=0)
-            torch.cuda.synchronize()
-            ctx.stage_items_device(metric, ids, d, items.data_ptr())
+        # rank 0 decodes + uploads chunk k + 1 while chunk k is being broadcast out of / into the library's item buffers
+        parallel.stage_and_broadcast(ctx, dist, rig.rank, metric, d, ids, ptrs, rig.dev)
         parallel.sharded_build(ctx, dist, rig.rank, rig.world, seeds, roots, T, arena=arena, device=rig.dev)
         rig.barrier()
         if step >= n_warm:
@@ -549,7 +543,7 @@ def e2e_multi(rig, wl, items, seeds, steps, n_warm):
     d2h = rig.sum_over_ranks(float(cc1["d2h_bytes"] - cc0["d2h_bytes"]) / steps)
     del arena, blob, ptrs
     return {"value": n / e_sec, "unit": "vectors/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e_sec * 1e3, "steps": steps,
-            "api": "rank 0: arroy_b200_stage_items(leaf value pointers); NCCL broadcast of the item buffer; every rank: arroy_b200_build_trees_begin / _emit (arena sink) for its trees",
+            "api": "rank 0: arroy_b200_stage_begin / _rows / _end (leaf value pointers) pipelined chunk by chunk with the NCCL broadcast of the item buffer; every rank: arroy_b200_build_trees_begin / _emit (arena sink) for its trees",
             "timing": "wall clock between barriers, max over ranks"}
 
 
@@ -754,17 +748,34 @@ def main():
         normal = (r.standard_normal(d) / np.sqrt(d)).astype(np.float32)
         root_ms, _ = ctx.time_scan(normal, (0.0, 0.0), n, iters=5, flush_l2=True)
         own_alg = tb["scanned_rows_per_step"] * d * 4 / world
-        line["roofline"] = {
-            "bound": "hbm", "kernel": "work_kernel (side()/margin scan + id partition)", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-            "peak_source": which, "traffic": traffic, "traffic_note": traffic_note,
-            "timing": "SEPARATE untimed build in the lockstep schedule (ARROY_B200_PROFILE: one control + one work launch per step, every work_kernel launch bracketed by "
-                      "CUDA events on its launching stream and running alone); the timed steps use the asynchronous per-tree schedule, whose kernels overlap",
-            "per_launch": {"launches": steps_dev, "avg_ms": scan_ms / max(steps_dev, 1), "avg_algorithmic_GB": alg_bytes / max(steps_dev, 1) / 1e9},
-            "in_timed_schedule": {"GBps": own_alg / (tb["breakdown"]["loop_ms"] * 1e-3) / 1e9, "frac": own_alg / (tb["breakdown"]["loop_ms"] * 1e-3) / 1e9 / hbm,
-                                  "note": "algorithmic scan bytes of the last timed step / its device loop time: all kernels of the step, control kernels and launch gaps included"},
-            "root_scan": {"rows": n, "ms": root_ms, "GBps": n * d * 4 / (root_ms * 1e-3) / 1e9, "frac": n * d * 4 / (root_ms * 1e-3) / 1e9 / hbm},
-            "share_of_step": scan_ms / (st["build_ms"] if st["build_ms"] else 1.0),
-        }
+        lockstep_rec = {"GBps": achieved, "frac": achieved / hbm, "launches": steps_dev, "avg_ms": scan_ms / max(steps_dev, 1), "avg_algorithmic_GB": alg_bytes / max(steps_dev, 1) / 1e9,
+                        "share_of_step": scan_ms / (st["build_ms"] if st["build_ms"] else 1.0),
+                        "note": "SEPARATE untimed build in the lockstep schedule (ARROY_B200_PROFILE: one control + one work_kernel launch per step, every work_kernel launch "
+                                "bracketed by CUDA events on its launching stream and running alone)"}
+        root_rec = {"rows": n, "ms": root_ms, "GBps": n * d * 4 / (root_ms * 1e-3) / 1e9, "frac": n * d * 4 / (root_ms * 1e-3) / 1e9 / hbm}
+        if tb["stats"]["steps"] == 1 and tb["stats"]["scan_ms"] > 0:
+            # persistent schedule: the dominant kernel IS the step — one launch holds every side()/margin scan and wide partition
+            kms = tb["stats"]["scan_ms"]
+            k_alg = tb["stats"]["scanned_rows"] * d * 4
+            line["roofline"] = {
+                "bound": "hbm", "kernel": "control_kernel<persistent> (worker CTAs: side()/margin scan + id partition; control CTAs: two_means / create_split / DFS)",
+                "achieved": k_alg / (kms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s", "frac": k_alg / (kms * 1e-3) / 1e9 / hbm, "peak_source": which,
+                "traffic": (traffic * max(steps_dev, 1) / alg_bytes * k_alg) if traffic else None, "traffic_note": traffic_note,
+                "timing": "live, inside the timed region: CUDA events on the launching stream around the ONE kernel launch of the last timed step; achieved = the step's "
+                          "algorithmic scan bytes (rows that went through side() x d x 4) / that duration — control CTAs' serial work included, so a lower bound of the scan rate",
+                "per_launch": {"launches": 1, "avg_ms": kms, "avg_algorithmic_GB": k_alg / 1e9},
+                "work_kernel_alone": lockstep_rec, "root_scan": root_rec,
+            }
+        else:
+            line["roofline"] = {
+                "bound": "hbm", "kernel": "work_kernel (side()/margin scan + id partition)", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
+                "peak_source": which, "traffic": traffic, "traffic_note": traffic_note,
+                "timing": lockstep_rec["note"] + "; the timed steps use the asynchronous per-tree schedule, whose kernels overlap",
+                "per_launch": {"launches": steps_dev, "avg_ms": scan_ms / max(steps_dev, 1), "avg_algorithmic_GB": alg_bytes / max(steps_dev, 1) / 1e9},
+                "in_timed_schedule": {"GBps": own_alg / (tb["breakdown"]["loop_ms"] * 1e-3) / 1e9, "frac": own_alg / (tb["breakdown"]["loop_ms"] * 1e-3) / 1e9 / hbm,
+                                      "note": "algorithmic scan bytes of the last timed step / its device loop time: all kernels of the step, control kernels and launch gaps included"},
+                "root_scan": root_rec, "share_of_step": scan_ms / (st["build_ms"] if st["build_ms"] else 1.0),
+            }
     # ---- the same step INCLUDING node emission (like-for-like with the CPU arm, which produces complete nodes) -----------------
     if rank == 0 and world == 1 and not args.no_e2e:
         arena = rig.ab.Arena()

@@ -182,8 +182,9 @@ int32_t arroy_b200_build_trees_emit_mapped(arroy_ctx* ctx, const uint32_t* root_
 /* Statistics of the last build on this context (for roofline accounting):
  * stats[0] = rows that went through side() (sum over scans, retries included)
  * stats[1] = device steps, stats[2] = create_split calls, stats[3] = random-fallback splits,
- * stats[4] = device milliseconds of the build loop (CUDA events), stats[5] = ms in scan kernels
- * (only measured when ARROY_B200_PROFILE=1), stats[6] = tree nodes emitted, stats[7] = create_split calls whose
+ * stats[4] = device milliseconds of the build loop (CUDA events), stats[5] = ms in scan kernels (persistent schedule: the
+ * duration of the one kernel that holds every scan and partition of the wave; per-attempt launches: only measured with
+ * ARROY_B200_PROFILE=1), stats[6] = tree nodes emitted, stats[7] = create_split calls whose
  * speculative two_means was redone sequentially (a mis-predicted branch; results are identical either way). */
 int32_t arroy_b200_build_stats(arroy_ctx* ctx, double stats[8]);
 
