@@ -753,6 +753,7 @@ __device__ __noinline__ void pworker(const BuildParams& P, float* sm_normal) {
     const uint32_t T = P.n_trees;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t rot = (blockIdx.x - T) * 7u;
+    const bool latency_class = ((blockIdx.x - T) & 3u) == 0u;
     uint32_t loaded_t = 0xffffffffu, loaded_seq = 0xffffffffu;
     float nh0 = 0.f;
     if (tid == 0) w_exit = 0;
@@ -764,9 +765,12 @@ __device__ __noinline__ void pworker(const BuildParams& P, float* sm_normal) {
                 const uint32_t k = base + lane;
                 const uint32_t t = k < T ? (rot + k) % T : 0u;
                 const unsigned long long tk = k < T ? ld_vol64(&P.slots[t].ticket) : 0ull;
-                // among the open jobs prefer the one with the fewest groups: small nodes sit on their tree's critical path, the
-                // big scans only need bandwidth and are never starved (every worker comes back to them when nothing small is open)
-                uint32_t key = (k < T && pt_next(tk) < pt_total(tk)) ? pt_total(tk) : 0xffffffffu;
+                // Two classes of workers. One in four is a LATENCY worker: among the open jobs it takes the one with the fewest
+                // groups (small nodes sit on their tree's critical path and must not queue behind a root scan). The others are
+                // THROUGHPUT workers: they take the job with the most unclaimed groups, so the big scans keep (almost) all of the
+                // bandwidth and a burst of small jobs does not turn into hundreds of failed claims.
+                const bool open_job = k < T && pt_next(tk) < pt_total(tk);
+                uint32_t key = !open_job ? 0xffffffffu : (latency_class ? pt_total(tk) : 0x00ffffffu - (pt_total(tk) - pt_next(tk)));
                 uint32_t best = key;
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
