@@ -105,7 +105,8 @@ struct arroy_ctx {
     // staged items
     bool staged = false;
     int metric = 0;
-    uint32_t dim = 0, ld = 0;
+    uint32_t dim = 0, ld = 0;   // dim = the vectors' length on the device (binary-quantized metrics: the padded bit count)
+    uint32_t user_dim = 0;      // the index' dimensions (what normalized_distance of the binary-quantized metrics divides by)
     uint64_t n = 0;
     DevBuf items, h0, h1, norms, maxbits;
     std::vector<uint32_t> ids;
@@ -189,8 +190,10 @@ void compute_norms(arroy_ctx* c, bool with_max) {
 }
 
 void alloc_items(arroy_ctx* c, int metric, uint32_t dim, uint64_t n, const uint32_t* ids) {
-    if (metric < 0 || metric > 3) throw ArgError("unknown metric");
+    if (metric < 0 || metric > BQ_MANHATTAN) throw ArgError("unknown metric");
     if (dim == 0) throw ArgError("dim must be > 0");
+    c->user_dim = dim;
+    if (is_bq(metric)) dim = (dim + 63u) / 64u * 64u;   // the bit string's length (binary_quantized.rs:80-92)
     if (n > 0xffffffffull) throw ArgError("too many items");
     for (uint64_t i = 1; i < n; ++i) if (ids[i] <= ids[i - 1]) throw ArgError("ids must be strictly ascending");
     // a restage invalidates everything derived from the previous items: the bf16 shadow and the device forest
@@ -208,7 +211,7 @@ void alloc_items(arroy_ctx* c, int metric, uint32_t dim, uint64_t n, const uint3
 
 // headers as Writer::add_item stores them: D::new_header(vector) (src/writer.rs:388-390)
 void default_headers(arroy_ctx* c) {
-    if (c->metric == COSINE && c->n > 0) {
+    if ((c->metric == COSINE || c->metric == BQ_COSINE) && c->n > 0) {   // BQ cosine: sqrt(popcount-dot(v, v)) = sqrt(dim), exact in f32
         compute_norms(c, false);
         CK(cudaMemcpyAsync(c->h0.p, c->norms.p, c->n * 4, cudaMemcpyDeviceToDevice, c->stream));
     }
@@ -217,8 +220,11 @@ void default_headers(arroy_ctx* c) {
 // Staging pipeline: W host threads, each decoding row chunks into its own pinned bounce buffers and
 // issuing its own cudaMemcpyAsync on its own stream, so decode (host memcpy of unaligned values)
 // and PCIe transfers of different chunks overlap. row_src(i) = address of the dim floats of row i.
+// mode 0: row_src(i) = dim f32 (byte aligned only); mode 1 (binary quantized): row_src(i) = src_dim f32 to be quantized to +-1;
+// mode 2 (binary quantized): row_src(i) = the stored bit string (dim / 8 bytes) to be expanded to +-1
 template <class RowSrc>
-void stage_rows_pipeline(arroy_ctx* c, uint64_t n, uint32_t dim, uint32_t ld, RowSrc row_src, float* dst_override = nullptr, size_t chunk_mb_override = 0, bool count_bytes = true) {
+void stage_rows_pipeline(arroy_ctx* c, uint64_t n, uint32_t dim, uint32_t ld, RowSrc row_src, float* dst_override = nullptr, size_t chunk_mb_override = 0, bool count_bytes = true,
+                         int mode = 0, uint32_t src_dim = 0) {
     if (n == 0) return;
     unsigned W = 8;   // measured on the B200 box: 8 lanes x 4 MB chunks reach ~48 GB/s (PCIe copy alone: 54 GB/s)
     if (const char* e = getenv("ARROY_B200_STAGE_THREADS")) W = (unsigned)std::max(1, atoi(e));
@@ -250,8 +256,17 @@ void stage_rows_pipeline(arroy_ctx* c, uint64_t n, uint32_t dim, uint32_t ld, Ro
                 if (used[k]) CK(cudaEventSynchronize(sw.ev[k]));
                 float* b = sw.pin[k].as<float>();
                 for (uint64_t i = 0; i < rows; ++i) {
-                    memcpy(b + i * ld, row_src(r0 + i), 4ull * dim);
-                    for (uint32_t t = dim; t < ld; ++t) b[i * ld + t] = 0.f;
+                    float* o = b + i * ld;
+                    if (mode == 0) memcpy(o, row_src(r0 + i), 4ull * dim);
+                    else if (mode == 1) {
+                        const uint8_t* sp = row_src(r0 + i);
+                        for (uint32_t t = 0; t < src_dim; ++t) { uint32_t bits; memcpy(&bits, sp + 4ull * t, 4); o[t] = (bits >> 31) ? -1.0f : 1.0f; }
+                        for (uint32_t t = src_dim; t < dim; ++t) o[t] = -1.0f;
+                    } else {
+                        const uint8_t* sp = row_src(r0 + i);
+                        for (uint32_t t = 0; t < dim; ++t) o[t] = ((sp[t >> 3] >> (t & 7)) & 1) ? 1.0f : -1.0f;   // little-endian words: bit t of the string
+                    }
+                    for (uint32_t t = dim; t < ld; ++t) o[t] = 0.f;
                 }
                 CK(cudaMemcpyAsync(dst + r0 * ld, b, rows * ld * 4, cudaMemcpyHostToDevice, sw.st));
                 CK(cudaEventRecord(sw.ev[k], sw.st));
@@ -322,8 +337,18 @@ const void* control_fn(int metric) {
         case EUCLIDEAN: return reinterpret_cast<const void*>(&control_kernel<SMEM_WS, CS, EUCLIDEAN>);
         case COSINE: return reinterpret_cast<const void*>(&control_kernel<SMEM_WS, CS, COSINE>);
         case DOT_PRODUCT: return reinterpret_cast<const void*>(&control_kernel<SMEM_WS, CS, DOT_PRODUCT>);
-        default: return reinterpret_cast<const void*>(&control_kernel<SMEM_WS, CS, MANHATTAN>);
+        case MANHATTAN: return reinterpret_cast<const void*>(&control_kernel<SMEM_WS, CS, MANHATTAN>);
+        default: break;
     }
+    // binary-quantized metrics: persistent, single-CTA and global-workspace variants only (no cluster variants)
+    if constexpr (CS <= 1) {
+        switch (metric) {
+            case BQ_EUCLIDEAN: return reinterpret_cast<const void*>(&control_kernel<SMEM_WS, CS, BQ_EUCLIDEAN>);
+            case BQ_COSINE: return reinterpret_cast<const void*>(&control_kernel<SMEM_WS, CS, BQ_COSINE>);
+            default: return reinterpret_cast<const void*>(&control_kernel<SMEM_WS, CS, BQ_MANHATTAN>);
+        }
+    }
+    return nullptr;
 }
 inline const void* control_fn(bool smem_ws, int cs, int metric) {
     if (!smem_ws) return control_fn<false, 1>(metric);
@@ -447,6 +472,7 @@ void build_wave(arroy_ctx* c, size_t wave_no, uint32_t t0, uint32_t tw, const ui
         if (e) { int v = atoi(e); cluster = (v == 8 || v == 16) ? v : 1; }
         // measured: d = 64, 1-10 trees: 24 -> 20 us per attempt; d = 768: 38 -> 37 us for one tree but slower from ~6 trees on
         else if (c->dim <= 256) cluster = tw <= 8 ? 16 : (tw <= 16 ? 8 : 1);
+        if (is_bq(c->metric)) cluster = 1;
     }
     if (cluster > 1) {
         CK(cudaFuncSetAttribute(control_fn(true, cluster, c->metric), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctrl_smem));
@@ -918,7 +944,7 @@ int xf_engine() { const char* e = getenv("ARROY_B200_XGEMM"); return (e && strcm
 bool frerank_enabled(arroy_ctx* c, uint32_t k) {
     const char* e = getenv("ARROY_B200_FRERANK");
     const bool off = e != nullptr && atoi(e) == 0;
-    return !off && c->metric != MANHATTAN && k <= (uint32_t)FR_SURV && frerank_smem(c->ld) <= 200 * 1024;
+    return !off && c->metric != MANHATTAN && !is_bq(c->metric) && k <= (uint32_t)FR_SURV && frerank_smem(c->ld) <= 200 * 1024;
 }
 
 void frerank_prepare(arroy_ctx* c) {
@@ -1009,7 +1035,7 @@ void do_rerank_batch(arroy_ctx* c, uint32_t nq, const float* queries, const floa
     }
     if (!fused) {
     if (total) {
-        uint64_t per = c->metric == MANHATTAN ? 32 : 4;
+        uint64_t per = (c->metric == MANHATTAN || c->metric == BQ_MANHATTAN) ? 32 : 4;
         uint64_t warps = (max_c + per - 1) / per;
         uint32_t gx = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((warps + 7) / 8, std::max<uint64_t>(1, ((uint64_t)c->sm_count * 8) / std::min<uint32_t>(nq, c->sm_count * 8u))));
         dim3 grid(gx, nq);
@@ -1173,7 +1199,8 @@ int32_t arroy_b200_stage_items(arroy_ctx* c, int32_t metric, uint32_t dim, uint6
             if (bad.load()) throw ArgError("leaf value does not start with the Leaf tag 0x00");
         }
         const size_t voff = 1 + 4 * (size_t)hf;
-        stage_rows_pipeline(c, n, dim, ld, [&](uint64_t i) { return leaf_values[i] + voff; });
+        // binary-quantized leaves store the bit string (node.rs:224-228 with VectorCodec = BinaryQuantized)
+        stage_rows_pipeline(c, n, c->dim, ld, [&](uint64_t i) { return leaf_values[i] + voff; }, nullptr, 0, true, is_bq(metric) ? 2 : 0);
         if (n) {
             CK(cudaMemcpyAsync(c->h0.p, h0.data(), n * 4, cudaMemcpyHostToDevice, c->stream));
             CK(cudaMemcpyAsync(c->h1.p, h1.data(), n * 4, cudaMemcpyHostToDevice, c->stream));
@@ -1211,7 +1238,7 @@ int32_t arroy_b200_stage_rows(arroy_ctx* c, uint64_t row0, uint64_t n_rows, cons
             if (hf == 2) memcpy(&c->stage_h1[row0 + i], v + 5, 4);
         }
         const size_t voff = 1 + 4 * (size_t)hf;
-        stage_rows_pipeline(c, n_rows, c->dim, c->ld, [&](uint64_t i) { return leaf_values[i] + voff; }, c->items.as<float>() + (size_t)row0 * c->ld);
+        stage_rows_pipeline(c, n_rows, c->dim, c->ld, [&](uint64_t i) { return leaf_values[i] + voff; }, c->items.as<float>() + (size_t)row0 * c->ld, 0, true, is_bq(c->metric) ? 2 : 0);
     });
 }
 
@@ -1239,7 +1266,8 @@ int32_t arroy_b200_stage_items_flat(arroy_ctx* c, int32_t metric, uint32_t dim, 
         if (n) {
             const uint8_t* base = reinterpret_cast<const uint8_t*>(vectors);
             const size_t stride = 4ull * dim;
-            stage_rows_pipeline(c, n, dim, c->ld, [&](uint64_t i) { return base + i * stride; });
+            // binary-quantized metrics: the f32 vectors are quantized on the way (Writer::add_item -> UnalignedVector::from_slice)
+            stage_rows_pipeline(c, n, c->dim, c->ld, [&](uint64_t i) { return base + i * stride; }, nullptr, 0, true, is_bq(metric) ? 1 : 0, dim);
             if (hdr0) CK(cudaMemcpyAsync(c->h0.p, hdr0, n * 4, cudaMemcpyHostToDevice, c->stream));
             else default_headers(c);
             if (hdr1) CK(cudaMemcpyAsync(c->h1.p, hdr1, n * 4, cudaMemcpyHostToDevice, c->stream));
@@ -1255,7 +1283,12 @@ int32_t arroy_b200_stage_items_device(arroy_ctx* c, int32_t metric, uint32_t dim
         set_device(c);
         if (n && (!ids || !device_vectors)) throw ArgError("null ids / vectors");
         alloc_items(c, metric, dim, n, ids);
-        if (n) {
+        if (n && is_bq(metric)) {
+            bq_sign_rows_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(static_cast<const float*>(device_vectors), c->items.as<float>(), n, dim, c->dim, c->ld);
+            CK(cudaGetLastError());
+            c->n_launches += 1;
+            default_headers(c);
+        } else if (n) {
             if (c->ld != dim) CK(cudaMemsetAsync(c->items.p, 0, (size_t)n * c->ld * 4, c->stream));
             CK(cudaMemcpy2DAsync(c->items.p, (size_t)c->ld * 4, device_vectors, (size_t)dim * 4, (size_t)dim * 4, n, cudaMemcpyDeviceToDevice, c->stream));
             default_headers(c);
@@ -1459,7 +1492,7 @@ int32_t arroy_b200_rerank_shared(arroy_ctx* c, uint32_t nq, const float* queries
         if (k == 0 || n_rows == 0) { for (uint32_t q = 0; q < nq; ++q) out_len[q] = 0; return; }
         if (n_rows > 0x7fffffffull) throw ArgError("too many candidates");
         for (uint64_t i = 0; i < n_rows; ++i) { if (rows[i] >= c->n) throw ArgError("row index out of range"); if (i && rows[i] <= rows[i - 1]) throw ArgError("rows must be ascending and unique"); }
-        if (c->metric == MANHATTAN || c->dim < 32 || k > TOPK_CAP / 2) {
+        if (c->metric == MANHATTAN || is_bq(c->metric) || c->dim < 32 || k > TOPK_CAP / 2) {
             // sequential-sum metric / SSE + scalar paths / k beyond the top-k buffer: generic per-pair kernels over replicated row lists
             if ((uint64_t)nq * n_rows > (1ull << 28)) throw ArgError("rerank_shared: this metric / dimension only supports nq * n_rows <= 2^28");
             std::vector<uint32_t> rep((size_t)nq * n_rows);
@@ -1668,7 +1701,7 @@ int32_t arroy_b200_search_batch(arroy_ctx* c, uint32_t nq, const uint32_t* query
                 CK(cudaGetLastError());
                 walk_segments_kernel<<<(m + 256) / 256, 256, 0, c->stream>>>(c->w_count.as<uint32_t>(), m, cand_cap, c->w_beg.as<uint64_t>(), c->w_end.as<uint64_t>());
                 CK(cudaGetLastError());
-                const uint64_t per = c->metric == MANHATTAN ? 32 : 4;
+                const uint64_t per = (c->metric == MANHATTAN || c->metric == BQ_MANHATTAN) ? 32 : 4;
                 const uint64_t warps = ((uint64_t)cand_cap + per - 1) / per;
                 const uint32_t gx = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((warps + 7) / 8, std::max<uint64_t>(1, ((uint64_t)c->sm_count * 8) / m)));
                 distance_kernel<<<dim3(gx, m), 256, 0, c->stream>>>(c->items.as<float>(), c->h0.as<float>(), c->dim, ld, c->metric, d_q, d_qrows, c->s_qh0.as<float>(), m,

@@ -46,7 +46,8 @@ __device__ __forceinline__ float4 ldg_stream(const float4* p) {
 __device__ __forceinline__ float margin_finish(int metric, float dot, float nh0, float item_h0) {
     // euclidean.rs:79-81 / manhattan.rs:82-84: bias + dot; cosine.rs:87-89: dot;
     // dot_product.rs:115-117: dot + n.extra_dim * q.extra_dim (two roundings)
-    if (metric == COSINE) return dot;
+    // binary_quantized_euclidean.rs:95-97 / _manhattan.rs:99-101: bias + dot; binary_quantized_cosine.rs:95-97: dot
+    if (metric == COSINE || metric == BQ_COSINE) return dot;
     if (metric == DOT_PRODUCT) return __fadd_rn(dot, __fmul_rn(nh0, item_h0));
     return __fadd_rn(nh0, dot);
 }
@@ -304,6 +305,12 @@ __global__ void dot_header_kernel(const float* __restrict__ norms, uint64_t n, c
 // (read through L1/L2; nq*ld floats). keys[q][i] = ordered_key(dist) << 32 | position.
 __device__ __forceinline__ float built_finish(int metric, float acc, float qh0, float item_h0) {
     if (metric == EUCLIDEAN || metric == MANHATTAN) return acc;      // euclidean.rs:45-47 / manhattan.rs:44-46
+    // binary quantized: sum (a - b)^2 = 4 popcount(a ^ b) (euclidean.rs:117-124), sum |a - b| = 2 popcount (manhattan.rs:113-120)
+    if (metric == BQ_EUCLIDEAN || metric == BQ_MANHATTAN) return acc;
+    if (metric == BQ_COSINE) {                                       // binary_quantized_cosine.rs:51-65: no clamp, `!= 0.0`
+        const float pnqn = __fmul_rn(qh0, item_h0);
+        return pnqn != 0.0f ? __fdiv_rn(__fsub_rn(1.0f, __fdiv_rn(acc, pnqn)), 2.0f) : 0.0f;
+    }
     if (metric == DOT_PRODUCT) return -acc;                          // dot_product.rs:52-56
     float pnqn = __fmul_rn(qh0, item_h0);                            // cosine.rs:43-59
     if (pnqn > 1.1920928955078125e-07f) {
@@ -327,7 +334,7 @@ distance_kernel(const float* __restrict__ items, const float* __restrict__ ih0, 
     const int lane = threadIdx.x & 31;
     const uint64_t warp_global = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const uint64_t nwarps = (uint64_t)gridDim.x * (blockDim.x >> 5);
-    if (metric == MANHATTAN) {
+    if (metric == MANHATTAN || metric == BQ_MANHATTAN) {
         // strictly sequential scalar sum of |p - q| per candidate (manhattan.rs:44-46): one lane per row
         for (uint64_t p0 = beg + warp_global * 32; p0 < end; p0 += nwarps * 32) {
             uint64_t p = p0 + lane;
@@ -356,7 +363,7 @@ distance_kernel(const float* __restrict__ items, const float* __restrict__ ih0, 
             const float4* Q = reinterpret_cast<const float4*>(qv);
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
             const int nch = d >> 5;
-            if (metric == EUCLIDEAN) {
+            if (metric == EUCLIDEAN || metric == BQ_EUCLIDEAN) {
 #pragma unroll 4
                 for (int c = 0; c < nch; ++c) {
                     float4 x = __ldg(Q + c * 8 + g8);
@@ -375,7 +382,7 @@ distance_kernel(const float* __restrict__ items, const float* __restrict__ ih0, 
             res = group8_hsum(acc);
             const float* row = items + (size_t)r * ld;
             for (uint32_t i = nch * 32; i < d; ++i) {
-                if (metric == EUCLIDEAN) { float t = __fsub_rn(qv[i], row[i]); res = __fadd_rn(res, __fmul_rn(t, t)); }
+                if (metric == EUCLIDEAN || metric == BQ_EUCLIDEAN) { float t = __fsub_rn(qv[i], row[i]); res = __fadd_rn(res, __fmul_rn(t, t)); }
                 else res = __fadd_rn(res, __fmul_rn(qv[i], row[i]));
             }
         } else {
@@ -386,11 +393,11 @@ distance_kernel(const float* __restrict__ items, const float* __restrict__ ih0, 
             if (v) {
                 r = rows[p];
                 const float* row = items + (size_t)r * ld;
-                res = (metric == EUCLIDEAN) ? exact_thread<true>(qv, row, (int)d) : exact_thread<false>(qv, row, (int)d);
+                res = (metric == EUCLIDEAN || metric == BQ_EUCLIDEAN) ? exact_thread<true>(qv, row, (int)d) : exact_thread<false>(qv, row, (int)d);
             }
         }
         if (v && writer) {
-            float dist = built_finish(metric, res, qhdr, (metric == COSINE) ? ih0[r] : 0.f);
+            float dist = built_finish(metric, res, qhdr, (metric == COSINE || metric == BQ_COSINE) ? ih0[r] : 0.f);
             dists[p] = dist;
             keys[p] = ((unsigned long long)ordered_key(dist) << 32) | (unsigned long long)(uint32_t)(p - beg);
         }
@@ -423,7 +430,7 @@ __device__ __forceinline__ void bitonic_sort_shared(unsigned long long* buf, int
 
 __device__ __forceinline__ float normalized_distance_dev(int metric, float dist) {
     if (metric == EUCLIDEAN) return __fsqrt_rn(dist);  // mod.rs:59-61
-    if (metric == COSINE) return dist;                 // cosine.rs:61-63
+    if (metric == COSINE || is_bq(metric)) return dist;   // cosine.rs:61-63; binary quantized: see bq_normalize_kernel
     if (metric == DOT_PRODUCT) return -dist;           // dot_product.rs:81-83
     return (dist != dist) ? 0.0f : (dist > 0.0f ? dist : 0.0f);  // manhattan.rs:48-50 (f32::max)
 }
@@ -486,6 +493,30 @@ take_sorted_kernel(const unsigned long long* __restrict__ sorted_keys, const flo
         const uint32_t p = (uint32_t)(sorted_keys[beg + i] & 0xffffffffull);
         out_rows[(size_t)q * k + i] = rows[beg + p];
         out_dist[(size_t)q * k + i] = normalized_distance_dev(metric, dists[beg + p]);
+    }
+}
+
+// binary-quantized distances divide by the index' dimensions (reader.rs:398 -> binary_quantized_euclidean.rs:56-58: d / dims;
+// _manhattan.rs:56-58: d.max(0.0) / dims; _cosine: unchanged): a second pass over the (few) results of the top-k kernels
+__global__ void bq_normalize_kernel(float* __restrict__ dist, uint64_t n, int metric, float dims) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float d = dist[i];
+    if (metric == BQ_MANHATTAN) d = (d != d) ? 0.0f : (d > 0.0f ? d : 0.0f);
+    if (metric != BQ_COSINE) dist[i] = __fdiv_rn(d, dims);
+}
+
+// dense f32 rows (n x d_in) -> the padded +-1 layout (n x ld, the first dpad = 64 * ceil(d_in / 64) columns +-1, the rest 0):
+// BinaryQuantized::from_slice + ::iter (binary_quantized.rs:80-92, :276-289) — bit = is_sign_positive
+__global__ void bq_sign_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, uint64_t n, uint32_t d_in, uint32_t dpad, uint32_t ld) {
+    const uint64_t total = n * ld;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t r = i / ld;
+        const uint32_t c = (uint32_t)(i - r * ld);
+        float v = 0.f;
+        if (c < d_in) v = (__float_as_uint(src[r * d_in + c]) >> 31) ? -1.0f : 1.0f;
+        else if (c < dpad) v = -1.0f;
+        dst[i] = v;
     }
 }
 

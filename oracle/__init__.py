@@ -16,7 +16,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
 EUCLIDEAN, COSINE, DOT_PRODUCT, MANHATTAN = 0, 1, 2, 3
-METRICS = {"euclidean": 0, "cosine": 1, "dot-product": 2, "manhattan": 3}
+BQ_EUCLIDEAN, BQ_COSINE, BQ_MANHATTAN = 4, 5, 6
+METRICS = {"euclidean": 0, "cosine": 1, "dot-product": 2, "manhattan": 3,
+           "binary quantized euclidean": 4, "binary quantized cosine": 5, "binary quantized manhattan": 6}
 
 _f32p = C.POINTER(C.c_float)
 _u32p = C.POINTER(C.c_uint32)
@@ -68,6 +70,9 @@ def lib():
     sig("oracle_create_split", None, i32, vp, _f32p, _f32p, _f32p, u64, _u32p, u32, _f32p, _f32p)
     sig("oracle_rerank", u32, i32, _f32p, f32, f32, _f32p, _f32p, _f32p, u64, _u32p, u64, u32, _u32p, _f32p)
     sig("oracle_dot_preprocess", None, _f32p, u64, u64, _f32p, _f32p)
+    sig("oracle_set_rerank_dims", None, u64)
+    sig("oracle_bq_quantize", u64, _f32p, u64, _f32p)
+    sig("oracle_db_set_user_dims", None, vp, u64)
     sig("oracle_target_n_trees", u64, i64, u64, u64, u64)
     sig("oracle_split_imbalance", C.c_double, u64, u64)
     sig("oracle_db_new", vp, i32, u64)
@@ -228,6 +233,25 @@ def rerank(metric, query, qh, vectors, h0, h1, rows, count):
     return out_rows[:k].copy(), out_dist[:k].copy()
 
 
+def bq_quantize(vectors):
+    """BinaryQuantized::from_slice + ::iter of every row: the +-1.0 values of the quantized vectors, 64 * ceil(d / 64) columns."""
+    vectors = f32c(vectors)
+    squeeze = vectors.ndim == 1
+    v2 = vectors.reshape(1, -1) if squeeze else vectors
+    n, d = v2.shape
+    dp = (d + 63) // 64 * 64
+    out = np.empty((n, dp), dtype=np.float32)
+    for i in range(n):
+        row = np.ascontiguousarray(v2[i])
+        lib().oracle_bq_quantize(_fp(row), d, out[i].ctypes.data_as(_f32p))
+    return out[0] if squeeze else out
+
+
+def set_rerank_dims(dims):
+    """binary-quantized indexes: the `dimensions` normalized_distance divides by in the next rerank() calls (0 = vector length)"""
+    lib().oracle_set_rerank_dims(dims)
+
+
 def dot_preprocess(vectors):
     vectors = f32c(vectors)
     n, d = vectors.shape
@@ -269,6 +293,10 @@ class Db:
         vectors = f32c(vectors)
         self._keep = (ids, vectors)
         lib().oracle_db_set_items(self.h, ids.size, _up(ids), _fp(vectors))
+
+    def set_user_dims(self, dims):
+        """binary-quantized indexes: Reader::dimensions (the vectors handed to set_items are the padded +-1 form)"""
+        lib().oracle_db_set_user_dims(self.h, dims)
 
     def build(self, rng, n_trees=None, split_after=None, threads=1):
         rc = lib().oracle_db_build(self.h, rng.h, -1 if n_trees is None else n_trees, split_after or 0, threads)

@@ -112,6 +112,15 @@ static inline void encode_tree_node(int metric, size_t d, const TreeNode& n, std
         const uint8_t* p = reinterpret_cast<const uint8_t*>(&n.normal.h0);
         out.insert(out.end(), p, p + 4);
         if (header_floats(metric) == 2) { p = reinterpret_cast<const uint8_t*>(&n.normal.h1); out.insert(out.end(), p, p + 4); }
+        if (is_bq(metric)) {   // the vector part is the bit string: 64-bit words, bit i of word w = element 64 w + i (binary_quantized.rs:80-92)
+            for (size_t w = 0; w < d / 64; ++w) {
+                uint64_t word = 0;
+                for (size_t i = 0; i < 64; ++i) if (n.normal.v[64 * w + i] > 0.f) word |= 1ull << i;
+                p = reinterpret_cast<const uint8_t*>(&word);
+                out.insert(out.end(), p, p + 8);
+            }
+            return;
+        }
         p = reinterpret_cast<const uint8_t*>(n.normal.v.data());
         out.insert(out.end(), p, p + 4 * d);
     }
@@ -120,6 +129,7 @@ static inline void encode_tree_node(int metric, size_t d, const TreeNode& n, std
 struct Db {
     int metric;
     size_t d;
+    size_t user_dims = 0;   // binary-quantized indexes: Reader::dimensions (d is the padded bit count); 0 = d
     // staging area of add_item (small tests)
     std::map<uint32_t, std::vector<float>> staged;
     // frozen item table (rows ascending by id)
@@ -154,6 +164,7 @@ struct Db {
         h0_own.assign(n, 0.f);
         h1_own.assign(metric == DOT_PRODUCT ? n : 0, 0.f);
         if (metric == COSINE) for (size_t r = 0; r < n; ++r) h0_own[r] = norm_no_header(vec + r * d, d);
+        if (metric == BQ_COSINE) for (size_t r = 0; r < n; ++r) { float h1; new_header(metric, vec + r * d, d, h0_own[r], h1); }
     }
 
     // DotProduct::preprocess — dot_product.rs:119-165
@@ -688,7 +699,7 @@ struct Db {
         }
         size_t k = std::min(count, dists.size());
         auto top = median_based_top_k(std::move(dists), k);
-        for (auto& pr : top) output.push_back({pr.second, normalized_distance(metric, pr.first)});
+        for (auto& pr : top) output.push_back({pr.second, normalized_distance(metric, pr.first, user_dims ? user_dims : d)});
         return output;
     }
 };

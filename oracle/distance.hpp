@@ -23,7 +23,14 @@
 
 namespace oracle {
 
-enum Metric : int { EUCLIDEAN = 0, COSINE = 1, DOT_PRODUCT = 2, MANHATTAN = 3 };
+enum Metric : int { EUCLIDEAN = 0, COSINE = 1, DOT_PRODUCT = 2, MANHATTAN = 3,
+                    // binary-quantized distances (src/distance/binary_quantized_{euclidean,cosine,manhattan}.rs). Their vectors are
+                    // bit strings (src/unaligned_vector/binary_quantized.rs); this restatement keeps them DEQUANTIZED, as the +-1.0
+                    // values BinaryQuantized::iter yields (bit 1 -> 1.0, bit 0 -> -1.0), 64 * ceil(dims / 64) of them: a partial last
+                    // word is padded with 0 bits = -1.0 and the reference's byte-wise kernels do count those bits.
+                    BQ_EUCLIDEAN = 4, BQ_COSINE = 5, BQ_MANHATTAN = 6 };
+static inline bool is_bq(int m) { return m >= BQ_EUCLIDEAN; }
+static inline int base_metric(int m) { return m == BQ_EUCLIDEAN ? EUCLIDEAN : m == BQ_COSINE ? COSINE : m == BQ_MANHATTAN ? MANHATTAN : m; }
 
 static inline const char* metric_name(int m) {
     switch (m) {  // euclidean.rs:37, cosine.rs:35, dot_product.rs:43, manhattan.rs:36
@@ -34,6 +41,25 @@ static inline const char* metric_name(int m) {
     }
 }
 static inline int header_floats(int m) { return m == DOT_PRODUCT ? 2 : 1; }
+
+// BinaryQuantized::from_slice (binary_quantized.rs:80-92) followed by ::iter (:276-289): bit = is_sign_positive(x) (so +0.0 and
+// +NaN are 1, -0.0 is 0), value = bit * 2 - 1; `out` has 64 * ceil(d / 64) entries.
+static inline size_t bq_padded_dims(size_t d) { return (d + 63) / 64 * 64; }
+static inline void bq_quantize_pm1(const float* in, size_t d, float* out) {
+    const size_t dp = bq_padded_dims(d);
+    for (size_t i = 0; i < dp; ++i) out[i] = (i < d && !std::signbit(in[i])) ? 1.0f : -1.0f;
+}
+// dot_product_binary_quantized (src/spaces/simple.rs:121-131): per byte count_ones(!(u ^ v)) - count_zeros(..), summed as i32
+static inline float dot_bq(const float* a, const float* b, size_t dp) {
+    int32_t s = 0;
+    for (size_t i = 0; i < dp; ++i) s += ((a[i] > 0.f) == (b[i] > 0.f)) ? 1 : -1;
+    return (float)s;
+}
+static inline uint32_t xor_ones_bq(const float* a, const float* b, size_t dp) {
+    uint32_t c = 0;
+    for (size_t i = 0; i < dp; ++i) c += ((a[i] > 0.f) != (b[i] > 0.f)) ? 1u : 0u;
+    return c;
+}
 
 // ---- src/spaces ------------------------------------------------------------------
 
@@ -154,10 +180,20 @@ static inline float norm_no_header(const float* v, size_t d) { return std::sqrt(
 static inline void new_header(int m, const float* v, size_t d, float& h0, float& h1) {
     h0 = 0.f; h1 = 0.f;
     if (m == COSINE) h0 = norm_no_header(v, d);
+    if (m == BQ_COSINE) h0 = std::sqrt(dot_bq(v, v, d));   // binary_quantized_cosine.rs:47-49, :70-72
 }
 
 static inline float built_distance(int m, const Leaf& p, const Leaf& q, size_t d) {
     switch (m) {
+        case BQ_EUCLIDEAN: return (float)(xor_ones_bq(p.v, q.v, d) * 4u);   // binary_quantized_euclidean.rs:117-124
+        case BQ_MANHATTAN: return (float)(xor_ones_bq(p.v, q.v, d) * 2u);   // binary_quantized_manhattan.rs:113-120
+        case BQ_COSINE: {                                                   // binary_quantized_cosine.rs:51-65 (no clamp, `!= 0.0`)
+            float pn = p.h0, qn = q.h0;
+            float pq = dot_bq(p.v, q.v, d);
+            float pnqn = pn * qn;
+            if (pnqn != 0.0f) { float c = pq / pnqn; return (1.0f - c) / 2.0f; }
+            return 0.0f;
+        }
         case EUCLIDEAN: return euclidean_distance(p.v, q.v, d);  // euclidean.rs:45-47
         case COSINE: {                                           // cosine.rs:43-59
             float pn = p.h0, qn = q.h0;
@@ -189,8 +225,12 @@ static inline float non_built_distance(int m, const Leaf& p, const Leaf& q, size
     if (ppqq >= FLT_MIN) return 2.0f - 2.0f * pq / std::sqrt(ppqq);
     return 2.0f;
 }
-static inline float normalized_distance(int m, float dist) {
+// `dims` = the index' dimensions (Reader::dimensions, reader.rs:398) — only the binary-quantized distances use it
+static inline float normalized_distance(int m, float dist, size_t dims = 0) {
     switch (m) {
+        case BQ_EUCLIDEAN: return dist / (float)dims;                                               // binary_quantized_euclidean.rs:56-58
+        case BQ_MANHATTAN: return ((dist != dist) ? 0.0f : (dist > 0.0f ? dist : 0.0f)) / (float)dims;   // binary_quantized_manhattan.rs:56-58
+        case BQ_COSINE: return dist;
         case EUCLIDEAN: return std::sqrt(dist);                    // mod.rs:59-61
         case COSINE: return dist;                                  // cosine.rs:61-63
         case DOT_PRODUCT: return -dist;                            // dot_product.rs:81-83
@@ -198,6 +238,8 @@ static inline float normalized_distance(int m, float dist) {
     }
 }
 static inline float norm_leaf(int m, const Leaf& l, size_t d) {
+    if (m == BQ_EUCLIDEAN || m == BQ_COSINE) return std::sqrt(dot_bq(l.v, l.v, d));   // norm_no_header of the two
+    if (m == BQ_MANHATTAN) { float s = 0.f; for (size_t i = 0; i < d; ++i) s += l.v[i] > 0.f ? 1.f : -1.f; return std::sqrt(s); }   // binary_quantized_manhattan.rs:60-67
     if (m == DOT_PRODUCT) {  // dot_product.rs:72-75
         float dot = dot_product(l.v, l.v, d);
         return std::sqrt(dot + l.h0 * l.h0);
@@ -220,6 +262,9 @@ static inline void update_mean(OwnedLeaf& mean, const Leaf& k, float norm, float
 }
 static inline float margin(int m, const Leaf& n, const Leaf& q, size_t d) {
     switch (m) {
+        case BQ_EUCLIDEAN:
+        case BQ_MANHATTAN: return n.h0 + dot_bq(n.v, q.v, d);   // binary_quantized_euclidean.rs:95-97, _manhattan.rs:99-101
+        case BQ_COSINE: return dot_bq(n.v, q.v, d);             // binary_quantized_cosine.rs:95-97
         case EUCLIDEAN:
         case MANHATTAN: return n.h0 + dot_product(n.v, q.v, d);   // euclidean.rs:79-81, manhattan.rs:82-84
         case COSINE: return dot_product(n.v, q.v, d);              // cosine.rs:87-89
@@ -286,6 +331,28 @@ static inline void two_means(int m, StdRng& rng, const SubsetView& leafs, bool c
 static inline void create_split(int m, StdRng& rng, const SubsetView& children, OwnedLeaf& normal) {
     const size_t d = children.d;
     OwnedLeaf p, q;
+    if (is_bq(m)) {
+        // two_means_binary_quantized (mod.rs:173-223): the sampled leaves become f32 leaves of the NON-quantized distance
+        // (`new_leaf(vector.to_vec())`: header = NonBq::new_header — the Cosine norm of a +-1 vector is the BQ header's value,
+        // the others are 0), then the ordinary loop; the children view already holds exactly those vectors and headers.
+        const int nb = base_metric(m);
+        two_means(nb, rng, children, m == BQ_COSINE, p, q);
+        // create_split (binary_quantized_*.rs): p - q goes through UnalignedVector::<BinaryQuantized>::from_vec = its sign bits.
+        // Self::normalize then divides by a positive norm (or does nothing) and re-quantizes: the bits do not change.
+        normal.h0 = 0.f; normal.h1 = 0.f;
+        normal.v.resize(d);
+        for (size_t i = 0; i < d; ++i) normal.v[i] = std::signbit(p.v[i] - q.v[i]) ? -1.0f : 1.0f;
+        if (m != BQ_COSINE) {
+            // bias = sum of -n * (P + Q) / 2 over the QUANTIZED centroids P, Q (euclidean.rs:83-89)
+            float bias = 0.0f;
+            for (size_t i = 0; i < d; ++i) {
+                const float P = std::signbit(p.v[i]) ? -1.0f : 1.0f, Q = std::signbit(q.v[i]) ? -1.0f : 1.0f;
+                bias += -normal.v[i] * (P + Q) / 2.0f;
+            }
+            normal.h0 = bias;
+        }
+        return;
+    }
     bool cosine = (m == COSINE || m == DOT_PRODUCT);
     two_means(m, rng, children, cosine, p, q);
     normal.h0 = 0.f; normal.h1 = 0.f;

@@ -78,6 +78,7 @@ void oracle_create_split(int metric, void* rng, const float* vectors, const floa
     out_hdr2[0] = nl.h0; out_hdr2[1] = nl.h1;
 }
 
+static uint64_t g_rerank_dims = 0;
 // re-rank loop + top-k + normalized_distance — src/reader.rs:381-399
 uint32_t oracle_rerank(int metric, const float* qv, float qh0, float qh1, const float* vectors, const float* h0, const float* h1,
                        uint64_t d, const uint32_t* rows, uint64_t n_rows, uint32_t count, uint32_t* out_rows, float* out_dist) {
@@ -89,9 +90,14 @@ uint32_t oracle_rerank(int metric, const float* qv, float qh0, float qh1, const 
     }
     size_t k = std::min<size_t>(count, dists.size());
     auto top = Db::median_based_top_k(std::move(dists), k);
-    for (size_t i = 0; i < top.size(); ++i) { out_rows[i] = top[i].second; out_dist[i] = normalized_distance(metric, top[i].first); }
+    for (size_t i = 0; i < top.size(); ++i) { out_rows[i] = top[i].second; out_dist[i] = normalized_distance(metric, top[i].first, g_rerank_dims ? g_rerank_dims : d); }
     return (uint32_t)top.size();
 }
+// binary-quantized indexes: the `dimensions` normalized_distance divides by (reader.rs:398) for the next oracle_rerank calls (0 = d)
+void oracle_set_rerank_dims(uint64_t dims) { g_rerank_dims = dims; }
+// BinaryQuantized::from_slice + ::iter: the +-1.0 values of the quantized vector, 64 * ceil(d / 64) of them
+uint64_t oracle_bq_quantize(const float* v, uint64_t d, float* out) { bq_quantize_pm1(v, d, out); return bq_padded_dims(d); }
+void oracle_db_set_user_dims(void* db, uint64_t dims) { static_cast<Db*>(db)->user_dims = dims; }
 
 void oracle_dot_preprocess(const float* vectors, uint64_t n, uint64_t d, float* out_extra_dim, float* out_norm) {
     Db db(DOT_PRODUCT, d);
