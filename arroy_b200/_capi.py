@@ -10,7 +10,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libarroy_b200.so")
 
 EUCLIDEAN, COSINE, DOT_PRODUCT, MANHATTAN = 0, 1, 2, 3
-METRICS = {"euclidean": 0, "cosine": 1, "dot-product": 2, "manhattan": 3}
+BQ_EUCLIDEAN, BQ_COSINE, BQ_MANHATTAN = 4, 5, 6
+METRICS = {"euclidean": 0, "cosine": 1, "dot-product": 2, "manhattan": 3,
+           "binary quantized euclidean": 4, "binary quantized cosine": 5, "binary quantized manhattan": 6}
 METRIC_NAMES = {v: k for k, v in METRICS.items()}
 
 OK, ERR_CUDA, ERR_INVALID, ERR_CANCELLED, ERR_CAPACITY, ERR_NOT_STAGED, ERR_INTERNAL = range(7)
@@ -65,6 +67,7 @@ SIGNATURES = [
     ("arroy_b200_timer_stop", C.c_int32, [C.c_void_p, _f32p]),
     ("arroy_b200_device_ptrs", C.c_int32, [C.c_void_p, C.POINTER(C.c_void_p), _u32p]),
     ("arroy_b200_epochs", C.c_int32, [C.c_void_p, _u64p]),
+    ("arroy_b200_bq_quantize", C.c_uint32, [_f32p, C.c_uint32, _f32p]),
     ("arroy_b200_stage_begin", C.c_int32, [C.c_void_p, C.c_int32, C.c_uint32, C.c_uint64, _u32p]),
     ("arroy_b200_stage_rows", C.c_int32, [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(C.c_void_p)]),
     ("arroy_b200_stage_end", C.c_int32, [C.c_void_p, C.c_int32]),
@@ -112,6 +115,14 @@ def _up(a):
     return a.ctypes.data_as(_u32p) if a is not None else None
 
 
+def bq_quantize(vector):
+    """BinaryQuantized::from_slice + ::iter of one vector: its +-1.0 values, padded to a multiple of 64 (host helper)."""
+    v = np.ascontiguousarray(vector, dtype=np.float32)
+    out = np.empty((v.size + 63) // 64 * 64, dtype=np.float32)
+    load().arroy_b200_bq_quantize(_fp(v), v.size, _fp(out))
+    return out
+
+
 class Context:
     """One arroy_ctx (one GPU). Thin 1:1 wrapper over the C ABI."""
 
@@ -142,6 +153,11 @@ class Context:
         if rc != OK:
             raise ArroyB200Error(rc, self.lib.arroy_b200_last_error(self.h).decode())
 
+    def _staged(self, n, dim, metric):
+        # binary-quantized metrics: vectors cross the boundary as their +-1 values, padded to a multiple of 64
+        self.n, self.metric, self.user_dim = n, metric, dim
+        self.dim = (dim + 63) // 64 * 64 if metric is not None and metric >= BQ_EUCLIDEAN else dim
+
     # -- staging ---------------------------------------------------------------------------
     def stage_items_flat(self, metric, ids, vectors, hdr0=None, hdr1=None):
         metric = METRICS[metric] if isinstance(metric, str) else metric
@@ -160,7 +176,7 @@ class Context:
         h1 = None if hdr1 is None else np.ascontiguousarray(hdr1, dtype=np.float32)
         self._ck(self.lib.arroy_b200_stage_items_flat(self.h, metric, dim, n, _up(ids), C.c_void_p(ptr), _fp(h0), _fp(h1)))
         del keep
-        self.n, self.dim, self.metric = n, dim, metric
+        self._staged(n, dim, metric)
 
     def stage_items_leaf_values(self, metric, dim, ids, values):
         """values: list of bytes objects = raw stored Leaf values ([0x00][header][dim x f32])."""
@@ -170,13 +186,13 @@ class Context:
         bufs = [C.create_string_buffer(v, len(v)) for v in values]
         arr = (C.c_void_p * max(n, 1))(*[C.cast(b, C.c_void_p) for b in bufs])
         self._ck(self.lib.arroy_b200_stage_items(self.h, metric, dim, n, _up(ids), arr))
-        self.n, self.dim, self.metric = n, dim, metric
+        self._staged(n, dim, metric)
 
     def stage_items_device(self, metric, ids, dim, device_ptr):
         metric = METRICS[metric] if isinstance(metric, str) else metric
         ids = np.ascontiguousarray(ids, dtype=np.uint32)
         self._ck(self.lib.arroy_b200_stage_items_device(self.h, metric, dim, ids.size, _up(ids), C.c_void_p(device_ptr)))
-        self.n, self.dim, self.metric = ids.size, dim, metric
+        self._staged(ids.size, dim, metric)
 
     def item_headers(self):
         h0 = np.empty(self.n, dtype=np.float32)
@@ -278,13 +294,13 @@ class Context:
         ids = np.ascontiguousarray(ids, dtype=np.uint32)
         ptrs = np.ascontiguousarray(ptr_array, dtype=np.uint64)
         self._ck(self.lib.arroy_b200_stage_items(self.h, metric, dim, ids.size, _up(ids), ptrs.ctypes.data_as(C.POINTER(C.c_void_p))))
-        self.n, self.dim, self.metric = ids.size, dim, metric
+        self._staged(ids.size, dim, metric)
 
     def stage_begin(self, metric, dim, ids):
         metric = METRICS[metric] if isinstance(metric, str) else metric
         ids = np.ascontiguousarray(ids, dtype=np.uint32)
         self._ck(self.lib.arroy_b200_stage_begin(self.h, metric, dim, ids.size, _up(ids)))
-        self.n, self.dim, self.metric = ids.size, dim, metric
+        self._staged(ids.size, dim, metric)
 
     def stage_rows(self, row0, ptr_array):
         ptrs = np.ascontiguousarray(ptr_array, dtype=np.uint64)

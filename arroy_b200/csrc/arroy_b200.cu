@@ -826,7 +826,15 @@ void do_build_emit(arroy_ctx* c, const uint32_t* root_ids, const uint64_t* base,
                         uint32_t l = gid(r.a), rr = gid(r.b);
                         for (int k = 3; k >= 0; --k) buf.push_back((uint8_t)(l >> (8 * k)));
                         for (int k = 3; k >= 0; --k) buf.push_back((uint8_t)(rr >> (8 * k)));
-                        if (r.c != NO_SLOT) {
+                        if (r.c != NO_SLOT && is_bq(c->metric)) {
+                            // the vector part of a binary-quantized normal is its bit string: 64-bit words, bit i of word w = element
+                            // 64 w + i positive (binary_quantized.rs:80-92)
+                            const float* s = pool + (size_t)r.c * pool_stride;
+                            size_t o = buf.size();
+                            buf.resize(o + 4 + d / 8, 0);
+                            memcpy(buf.data() + o, s, 4);
+                            for (uint32_t i = 0; i < d; ++i) if (s[NORMAL_HDR + i] > 0.f) buf[o + 4 + (i >> 3)] |= (uint8_t)(1u << (i & 7));
+                        } else if (r.c != NO_SLOT) {
                             const float* s = pool + (size_t)r.c * pool_stride;
                             size_t o = buf.size();
                             buf.resize(o + 4 * hdrf + 4ull * d);
@@ -993,6 +1001,14 @@ bool frerank_ok(arroy_ctx* c, uint32_t m) {   // after the stream is idle: did e
     return true;
 }
 
+// binary-quantized distances: normalized_distance divides by the index' dimensions (reader.rs:398); one pass over the results
+void bq_normalize(arroy_ctx* c, float* d_dist, uint64_t count) {
+    if (!is_bq(c->metric) || c->metric == BQ_COSINE || count == 0) return;
+    bq_normalize_kernel<<<(unsigned)((count + 255) / 256), 256, 0, c->stream>>>(d_dist, count, c->metric, (float)c->user_dim);
+    CK(cudaGetLastError());
+    c->n_launches += 1;
+}
+
 void do_rerank_batch(arroy_ctx* c, uint32_t nq, const float* queries, const float* qh0, const float* /*qh1*/, const uint32_t* rows,
                      const uint64_t* offsets, uint32_t k, uint32_t* out_rows, float* out_dist, uint32_t* out_len) {
     require_staged(c);
@@ -1059,6 +1075,7 @@ void do_rerank_batch(arroy_ctx* c, uint32_t nq, const float* queries, const floa
     CK(cudaGetLastError());
     }
     c->n_launches += total ? 2 : 1;
+    bq_normalize(c, c->s_odist.as<float>(), (uint64_t)nq * k);
     c->h2d_bytes += (uint64_t)nq * c->dim * 4 + (uint64_t)nq * 4 + (uint64_t)(nq + 1) * 8 + total * 4;
     c->d2h_bytes += (uint64_t)nq * k * 8 + (uint64_t)nq * 4;
     CK(cudaMemcpyAsync(out_rows, c->s_orows.p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, c->stream));
@@ -1404,7 +1421,10 @@ int32_t arroy_b200_create_split(arroy_ctx* c, const uint32_t rng_key[8], uint64_
             case EUCLIDEAN: fn = P.use_smem_ws ? (const void*)&create_split_kernel<true, EUCLIDEAN> : (const void*)&create_split_kernel<false, EUCLIDEAN>; break;
             case COSINE: fn = P.use_smem_ws ? (const void*)&create_split_kernel<true, COSINE> : (const void*)&create_split_kernel<false, COSINE>; break;
             case DOT_PRODUCT: fn = P.use_smem_ws ? (const void*)&create_split_kernel<true, DOT_PRODUCT> : (const void*)&create_split_kernel<false, DOT_PRODUCT>; break;
-            default: fn = P.use_smem_ws ? (const void*)&create_split_kernel<true, MANHATTAN> : (const void*)&create_split_kernel<false, MANHATTAN>; break;
+            case MANHATTAN: fn = P.use_smem_ws ? (const void*)&create_split_kernel<true, MANHATTAN> : (const void*)&create_split_kernel<false, MANHATTAN>; break;
+            case BQ_EUCLIDEAN: fn = P.use_smem_ws ? (const void*)&create_split_kernel<true, BQ_EUCLIDEAN> : (const void*)&create_split_kernel<false, BQ_EUCLIDEAN>; break;
+            case BQ_COSINE: fn = P.use_smem_ws ? (const void*)&create_split_kernel<true, BQ_COSINE> : (const void*)&create_split_kernel<false, BQ_COSINE>; break;
+            default: fn = P.use_smem_ws ? (const void*)&create_split_kernel<true, BQ_MANHATTAN> : (const void*)&create_split_kernel<false, BQ_MANHATTAN>; break;
         }
         if (smem > 48 * 1024) CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         {
@@ -1711,6 +1731,7 @@ int32_t arroy_b200_search_batch(arroy_ctx* c, uint32_t nq, const uint32_t* query
                                                                c->s_orows.as<uint32_t>(), c->s_odist.as<float>(), c->s_olen.as<uint32_t>());
                 CK(cudaGetLastError());
                 c->n_launches += 4;
+                bq_normalize(c, c->s_odist.as<float>(), (uint64_t)m * k);
                 c->pin.ensure(std::max<size_t>(c->pin.cap, 4ull * m));
                 int32_t* h_st = c->pin.as<int32_t>();
                 CK(cudaMemcpyAsync(h_st, c->w_status.p, 4ull * m, cudaMemcpyDeviceToHost, c->stream));
@@ -1789,6 +1810,7 @@ int32_t arroy_b200_search_batch(arroy_ctx* c, uint32_t nq, const uint32_t* query
             CK(cudaGetLastError());
             } else mark();
             c->n_launches += 5;
+            bq_normalize(c, c->s_odist.as<float>(), (uint64_t)m * k);
             mark();
             CK(cudaMemcpyAsync(out_rows + (size_t)q0 * k, c->s_orows.p, 4ull * m * k, cudaMemcpyDeviceToHost, c->stream));
             CK(cudaMemcpyAsync(out_dist + (size_t)q0 * k, c->s_odist.p, 4ull * m * k, cudaMemcpyDeviceToHost, c->stream));
@@ -1947,6 +1969,12 @@ int32_t arroy_b200_timer_stop(arroy_ctx* c, float* out_ms) {
         CK(cudaEventSynchronize(c->tev1));
         CK(cudaEventElapsedTime(out_ms, c->tev0, c->tev1));
     });
+}
+
+uint32_t arroy_b200_bq_quantize(const float* in, uint32_t dims, float* out) {
+    const uint32_t dp = (dims + 63u) / 64u * 64u;
+    if (in && out) for (uint32_t i = 0; i < dp; ++i) { uint32_t bits = 0x80000000u; if (i < dims) memcpy(&bits, in + i, 4); out[i] = (bits >> 31) ? -1.0f : 1.0f; }
+    return dp;
 }
 
 int32_t arroy_b200_epochs(arroy_ctx* c, uint64_t out[2]) {

@@ -474,8 +474,12 @@ __device__ __forceinline__ float norm_leaf_group(int metric, const float* v, flo
 template <int METRIC>
 __device__ __forceinline__ void create_split_cta(const BuildParams& P, Rng& rng /* thread 0 only */, const uint32_t* seg, uint32_t len,
                                                  float* ws, TwoMeansShared& S, float* slot_ptr, float* mirror = nullptr /* second copy of the slot */) {
-    constexpr int metric = METRIC;
-    constexpr bool cosine = (METRIC == COSINE || METRIC == DOT_PRODUCT);
+    // Binary-quantized metrics: two_means_binary_quantized (mod.rs:173-223) turns the sampled leaves into f32 leaves of the
+    // NON-quantized distance and runs the ordinary loop — on the device the items already are those +-1 vectors and their headers,
+    // so everything up to the centroids is the base metric's code; only the normal differs (below).
+    constexpr int metric = base_metric(METRIC);
+    constexpr bool BQ = is_bq(METRIC);
+    constexpr bool cosine = (metric == COSINE || metric == DOT_PRODUCT);
     const int d = (int)P.d, ld = (int)P.ld;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, grp = lane >> 3;
     // All RNG draws of the attempt first: they do not depend on the data. choose_two = index::sample(len, 2)
@@ -571,20 +575,46 @@ __device__ __forceinline__ void create_split_cta(const BuildParams& P, Rng& rng 
     __syncthreads();
     TP_MARK(S, TP_NORMS);
     bool spec_done = false;
-    if constexpr (METRIC != MANHATTAN) {
+    if constexpr (metric != MANHATTAN) {
         if (P.spec && d >= 32) {
             int ps = 0, qs = 1;
-            spec_done = spec_two_means<METRIC>(P, ws, S, ps, qs);
+            spec_done = spec_two_means<metric>(P, ws, S, ps, qs);
             if (spec_done) { p = ws + (size_t)ps * ld; q = ws + (size_t)qs * ld; }
         }
     }
-    if (!spec_done) two_means_sequential<METRIC>(P, ws, S);
+    if (!spec_done) two_means_sequential<metric>(P, ws, S);
     __syncthreads();
     TP_MARK(S, TP_TWOMEANS);
     // normal = normalize(p - q) (+ bias / extra_dim) — euclidean.rs:59-75, manhattan.rs:62-78,
     // cosine.rs:77-83, dot_product.rs:102-111. (A D::init still pending after the last update only
     // touches the centroid's norm header, which create_split does not read.)
     float* nv = sc0;
+    if constexpr (BQ) {
+        // create_split of binary_quantized_{euclidean,cosine,manhattan}.rs: p - q goes through UnalignedVector::<BinaryQuantized>::
+        // from_vec, i.e. only its sign bits survive (is_sign_positive -> +1, else -1); Self::normalize then divides by a positive
+        // norm (or does nothing) and re-quantizes, which cannot change a bit. bias (Euclidean / Manhattan) = sum of
+        // -n * (P + Q) / 2 over the QUANTIZED centroids P, Q — every term is -1, 0 or 1, so the sum is exact in any order, and it
+        // is folded left to right like the reference's anyway.
+        float* out = slot_ptr + NORMAL_HDR;
+        for (int i = tid; i < ld; i += blockDim.x) {
+            const float v = i < d ? ((__float_as_uint(__fsub_rn(p[i], q[i])) >> 31) ? -1.0f : 1.0f) : 0.f;
+            nv[i] = v; out[i] = v;
+            if (mirror != nullptr) mirror[NORMAL_HDR + i] = v;
+            if (METRIC != BQ_COSINE && i < d) {
+                const float Pq = (__float_as_uint(p[i]) >> 31) ? -1.0f : 1.0f, Qq = (__float_as_uint(q[i]) >> 31) ? -1.0f : 1.0f;
+                sc1[i] = __fdiv_rn(__fmul_rn(-v, __fadd_rn(Pq, Qq)), 2.0f);
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            float bias = 0.0f;
+            if (METRIC != BQ_COSINE) for (int i = 0; i < d; ++i) bias = __fadd_rn(bias, sc1[i]);
+            slot_ptr[0] = bias; slot_ptr[1] = 0.f; slot_ptr[2] = 0.f; slot_ptr[3] = 0.f;
+            if (mirror != nullptr) mirror[0] = bias;
+        }
+        __syncthreads();
+        TP_MARK(S, TP_FINISH_SPLIT);
+    } else {
     for (int i = tid; i < ld; i += blockDim.x) nv[i] = i < d ? __fsub_rn(p[i], q[i]) : 0.f;
     float extra = (metric == DOT_PRODUCT) ? __fsub_rn(S.php[0], S.phq[0]) : 0.f;
     __syncthreads();
@@ -618,6 +648,7 @@ __device__ __forceinline__ void create_split_cta(const BuildParams& P, Rng& rng 
     }
     __syncthreads();
     TP_MARK(S, TP_FINISH_SPLIT);
+    }
 }
 
 // CTA-wide stable partition of a whole node (any size) by its flags. Each round handles

@@ -48,7 +48,15 @@ enum {
     ARROY_B200_EUCLIDEAN = 0,
     ARROY_B200_COSINE = 1,
     ARROY_B200_DOT_PRODUCT = 2,
-    ARROY_B200_MANHATTAN = 3
+    ARROY_B200_MANHATTAN = 3,
+    /* src/distance/binary_quantized_{euclidean,cosine,manhattan}.rs. Their vectors are bit strings (BinaryQuantized,
+     * src/unaligned_vector/binary_quantized.rs); across this boundary — normals, queries, split results — they travel
+     * DEQUANTIZED, as the +-1.0 values BinaryQuantized::iter yields, 64 * ceil(dims / 64) of them (padding bits are 0 = -1.0;
+     * the reference's byte-wise popcount kernels count them). Staging quantizes: arroy_b200_stage_items takes the stored
+     * bit strings, _flat / _device take f32 vectors of `dim` = the index' dimensions. arroy_b200_bq_quantize makes a query. */
+    ARROY_B200_BQ_EUCLIDEAN = 4,
+    ARROY_B200_BQ_COSINE = 5,
+    ARROY_B200_BQ_MANHATTAN = 6
 };
 
 /* ---- context ----------------------------------------------------------------------- */
@@ -304,6 +312,10 @@ int32_t arroy_b200_rerank_breakdown(arroy_ctx* ctx, double out[8]);
  * it and returns the elapsed milliseconds between the two. */
 int32_t arroy_b200_timer_start(arroy_ctx* ctx);
 int32_t arroy_b200_timer_stop(arroy_ctx* ctx, float* out_ms);
+
+/* BinaryQuantized::from_slice + ::iter of one vector (host helper, no device): out[i] = is_sign_positive(in[i]) ? 1 : -1 for
+ * i < dims, -1 up to the next multiple of 64. Returns that padded length; in / out may be NULL to query it. */
+uint32_t arroy_b200_bq_quantize(const float* in, uint32_t dims, float* out);
 
 /* Ownership tokens of the device-resident state, for callers that share one context between several
  * readers / writers (the host keeps one context per heed::Env): out[0] = epoch of the staged items,
