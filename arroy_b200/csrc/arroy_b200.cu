@@ -1102,6 +1102,10 @@ template <class F>
 int32_t guarded(arroy_ctx* c, F&& f) {
     if (!c) return ARROY_B200_ERR_INVALID;
     std::lock_guard<std::mutex> lk(c->mu);
+    {   // an asynchronous fault of an EARLIER call must not be blamed on this one
+        const cudaError_t pending = cudaPeekAtLastError();
+        if (pending != cudaSuccess) { c->err = std::string("a CUDA error was already pending when this call started: ") + cudaGetErrorString(pending); return ARROY_B200_ERR_CUDA; }
+    }
     try { f(); return ARROY_B200_OK; }
     catch (const CudaError& e) { c->err = e.what(); cudaGetLastError(); return ARROY_B200_ERR_CUDA; }
     catch (const ArgError& e) { c->err = e.what(); return ARROY_B200_ERR_INVALID; }

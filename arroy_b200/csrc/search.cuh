@@ -194,7 +194,7 @@ constexpr uint32_t W1_LEAFQ = 128;     // Descendants nodes queued for the copie
 struct Walk1Shared {
     unsigned long long heap[W1_HEAP];
     uint32_t cand[W1_CAND];
-    uint32_t lq_off[W1_LEAFQ], lq_len[W1_LEAFQ], lq_dst[W1_LEAFQ];
+    volatile uint32_t lq_off[W1_LEAFQ], lq_len[W1_LEAFQ], lq_dst[W1_LEAFQ];   // (volatile: read by the copier warps right after `produced`)
     uint32_t scan[W1_THREADS / 32];
     volatile uint32_t produced;
     volatile int done;
