@@ -1720,22 +1720,30 @@ int32_t arroy_b200_search_batch(arroy_ctx* c, uint32_t nq, const uint32_t* query
                 if (qhdr0) CK(cudaMemcpyAsync(c->s_qh0.p, qhdr0, 4ull * m, cudaMemcpyHostToDevice, c->stream));
                 else if (query_rows) { gather_f32_kernel<<<(m + 255) / 256, 256, 0, c->stream>>>(c->s_qh0.as<float>(), c->h0.as<float>(), d_qrows, m); CK(cudaGetLastError()); }
                 else CK(cudaMemsetAsync(c->s_qh0.p, 0, 4ull * m, c->stream));
+                for (double& x : c->sbreak) x = 0;
+                int nte1 = 0;
+                auto mark1 = [&]() { if (!c->xev[nte1]) CK(cudaEventCreate(&c->xev[nte1])); CK(cudaEventRecord(c->xev[nte1], c->stream)); ++nte1; };
+                mark1();
                 walk1_kernel<<<m, W1_THREADS, w1smem, c->stream>>>(F, c->items.as<float>(), c->dim, ld, c->metric, m, d_qrows, d_q, c->s_qh0.as<float>(), search_k,
                                                                   c->w_cand2.as<uint32_t>(), cand_cap, c->w_count.as<uint32_t>(), c->w_status.as<int32_t>());
                 CK(cudaGetLastError());
+                mark1();
                 walk_segments_kernel<<<(m + 256) / 256, 256, 0, c->stream>>>(c->w_count.as<uint32_t>(), m, cand_cap, c->w_beg.as<uint64_t>(), c->w_end.as<uint64_t>());
                 CK(cudaGetLastError());
+                mark1();
                 const uint64_t per = (c->metric == MANHATTAN || c->metric == BQ_MANHATTAN) ? 32 : 4;
                 const uint64_t warps = ((uint64_t)cand_cap + per - 1) / per;
                 const uint32_t gx = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((warps + 7) / 8, std::max<uint64_t>(1, ((uint64_t)c->sm_count * 8) / m)));
                 distance_kernel<<<dim3(gx, m), 256, 0, c->stream>>>(c->items.as<float>(), c->h0.as<float>(), c->dim, ld, c->metric, d_q, d_qrows, c->s_qh0.as<float>(), m,
                                                                    c->w_cand2.as<uint32_t>(), c->w_beg.as<uint64_t>(), c->w_end.as<uint64_t>(), c->s_dists.as<float>(), c->s_keys.as<unsigned long long>());
                 CK(cudaGetLastError());
+                mark1();
                 topk_kernel<<<m, TOPK_THREADS, 0, c->stream>>>(c->s_keys.as<unsigned long long>(), c->s_dists.as<float>(), c->w_cand2.as<uint32_t>(), c->w_beg.as<uint64_t>(), c->w_end.as<uint64_t>(), k, c->metric,
                                                                c->s_orows.as<uint32_t>(), c->s_odist.as<float>(), c->s_olen.as<uint32_t>());
                 CK(cudaGetLastError());
                 c->n_launches += 4;
                 bq_normalize(c, c->s_odist.as<float>(), (uint64_t)m * k);
+                mark1();
                 c->pin.ensure(std::max<size_t>(c->pin.cap, 4ull * m));
                 int32_t* h_st = c->pin.as<int32_t>();
                 CK(cudaMemcpyAsync(h_st, c->w_status.p, 4ull * m, cudaMemcpyDeviceToHost, c->stream));
@@ -1743,6 +1751,7 @@ int32_t arroy_b200_search_batch(arroy_ctx* c, uint32_t nq, const uint32_t* query
                 CK(cudaMemcpyAsync(out_dist, c->s_odist.p, 4ull * m * k, cudaMemcpyDeviceToHost, c->stream));
                 CK(cudaMemcpyAsync(out_len, c->s_olen.p, 4ull * m, cudaMemcpyDeviceToHost, c->stream));
                 CK(cudaStreamSynchronize(c->stream));
+                for (int i = 0; i + 1 < nte1; ++i) { float ms = 0; CK(cudaEventElapsedTime(&ms, c->xev[i], c->xev[i + 1])); c->sbreak[i] += ms; }
                 bool all_ok = true;
                 for (uint32_t q = 0; q < m; ++q) all_ok = all_ok && h_st[q] == 0;
                 if (all_ok) {
