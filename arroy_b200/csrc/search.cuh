@@ -191,49 +191,11 @@ constexpr uint32_t W1_HEAP = 1024;     // heap entries in shared memory
 constexpr uint32_t W1_CAND = 8192;     // candidate slots in shared memory (duplicates included)
 constexpr uint32_t W1_LEAFQ = 128;     // Descendants nodes queued for the copier warps
 
-// one field of one node (lane f of a warp fetches field f: the seven loads of a node are ONE round trip, not a chain)
-__device__ __forceinline__ uint32_t walk_field(const DevForest& F, uint32_t node, int f) {
-    if (node >= F.n_nodes) return 0u;
-    switch (f) {
-        case 0: return (uint32_t)F.kind[node];
-        case 1: return F.left[node];
-        case 2: return F.right[node];
-        case 3: return F.normal_idx[node];
-        case 4: return __float_as_uint(F.nh0[node]);
-        case 5: return F.desc_off[node];
-        default: return F.desc_len[node];
-    }
-}
-// D::margin's dot product with every load of the normal in flight at once (lane l owns AVX accumulator lane l: elements l, l + 32,
-// ...; up to 24 chunks = 768 floats per batch), then the reference's hsum + tail — the same value as exact_warp<false>
-__device__ __forceinline__ float exact_warp_prefetched(const float* __restrict__ nv, const float* sq, int n) {
-    const int lane = threadIdx.x & 31;
-    if (n < 32) return exact_warp<false>(nv, sq, n);
-    const int nch = n >> 5;
-    float acc = 0.f;
-    for (int c0 = 0; c0 < nch; c0 += 24) {
-        float x[24];
-#pragma unroll
-        for (int u = 0; u < 24; ++u) x[u] = (c0 + u < nch) ? __ldg(nv + (size_t)(c0 + u) * 32 + lane) : 0.f;
-#pragma unroll
-        for (int u = 0; u < 24; ++u) if (c0 + u < nch) acc = fmaf(x[u], sq[(c0 + u) * 32 + lane], acc);
-    }
-    acc = __fadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, 4));
-    acc = __fadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, 2));
-    acc = __fadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, 1));
-    const float h1 = __shfl_sync(0xffffffffu, acc, 0), h2 = __shfl_sync(0xffffffffu, acc, 8), h3 = __shfl_sync(0xffffffffu, acc, 16), h4 = __shfl_sync(0xffffffffu, acc, 24);
-    float r = __fadd_rn(__fadd_rn(__fadd_rn(h1, h2), h3), h4);
-    for (int i = nch * 32; i < n; ++i) r = __fadd_rn(r, __fmul_rn(__ldg(nv + i), sq[i]));
-    return r;
-}
-
 struct Walk1Shared {
     unsigned long long heap[W1_HEAP];
     uint32_t cand[W1_CAND];
     volatile uint32_t lq_off[W1_LEAFQ], lq_len[W1_LEAFQ], lq_dst[W1_LEAFQ];   // (volatile: read by the copier warps right after `produced`)
     uint32_t scan[W1_THREADS / 32];
-    uint32_t mc_id[2];          // the two children of the split node processed last ...
-    uint32_t mc[2][8];          // ... and their seven fields, fetched while that node's normal was in flight
     volatile uint32_t produced;
     volatile int done;
     uint32_t total;
@@ -253,7 +215,7 @@ walk1_kernel(DevForest F, const float* __restrict__ items, uint32_t d, uint32_t 
     const float* qv = qrows ? items + (size_t)qrows[q] * ld : queries + (size_t)q * ld;
     const float qhdr = qh0 ? qh0[q] : 0.f;
     for (uint32_t i = tid; i < ld; i += W1_THREADS) sq[i] = qv[i];
-    if (tid == 0) { S.produced = 0; S.done = 0; S.total = 0; S.status = 0; S.mc_id[0] = 0xffffffffu; S.mc_id[1] = 0xffffffffu; }
+    if (tid == 0) { S.produced = 0; S.done = 0; S.total = 0; S.status = 0; }
     __syncthreads();
     if (warp == 0) {
         uint32_t size = 0, produced = 0, total32 = 0;
@@ -273,30 +235,21 @@ walk1_kernel(DevForest F, const float* __restrict__ items, uint32_t d, uint32_t 
             top = __shfl_sync(0xffffffffu, top, 0);
             const uint32_t node = (uint32_t)top;
             const float dist = key_to_dist((uint32_t)(top >> 32));
-            // the node's fields: usually prefetched as a child of the node before; else one round trip (lane f loads field f)
-            uint32_t fv;
-            if (node == S.mc_id[0]) fv = S.mc[0][lane & 7];
-            else if (node == S.mc_id[1]) fv = S.mc[1][lane & 7];
-            else fv = lane < 7 ? walk_field(F, node, lane) : 0u;
-            const int kind = (int)__shfl_sync(0xffffffffu, fv, 0);
+            const int kind = node < F.n_nodes ? F.kind[node] : 0;
             if (kind == 1) {
-                const uint32_t off = __shfl_sync(0xffffffffu, fv, 5), len = __shfl_sync(0xffffffffu, fv, 6);
+                const uint32_t off = F.desc_off[node], len = F.desc_len[node];
                 if (total32 + len > W1_CAND || produced >= W1_LEAFQ) { st = 1; break; }
                 if (lane == 0) { S.lq_off[produced] = off; S.lq_len[produced] = len; S.lq_dst[produced] = total32; __threadfence_block(); S.produced = produced + 1; }
                 produced += 1; total32 += len; total += len;
             } else if (kind == 2) {
-                const uint32_t lc = __shfl_sync(0xffffffffu, fv, 1), rc = __shfl_sync(0xffffffffu, fv, 2), ni = __shfl_sync(0xffffffffu, fv, 3);
-                const float nh0 = __uint_as_float(__shfl_sync(0xffffffffu, fv, 4));
-                // both children's fields go out with the normal's loads: whichever child is popped next costs no extra round trip
-                uint32_t cf = 0u;
-                if (lane < 14) cf = walk_field(F, lane < 7 ? lc : rc, lane < 7 ? lane : lane - 7);
+                const uint32_t ni = F.normal_idx[node];
+                const uint32_t lc = F.left[node], rc = F.right[node];
                 float mg = 0.0f;
                 if (ni != 0xffffffffu) {
-                    const float dt = exact_warp_prefetched(F.normals + (size_t)ni * ld, sq, (int)d);
-                    mg = margin_finish(metric, dt, nh0, qhdr);
+                    const float* nv = F.normals + (size_t)ni * ld;
+                    const float dt = exact_warp<false>(nv, sq, (int)d);
+                    mg = margin_finish(metric, dt, F.nh0[node], qhdr);
                 }
-                if (lane < 14) S.mc[lane < 7 ? 0 : 1][lane < 7 ? lane : lane - 7] = cf;
-                if (lane == 0) { S.mc_id[0] = lc; S.mc_id[1] = rc; }
                 if (lane == 0) {
                     if (size + 2 > W1_HEAP) st = 2;
                     else {
@@ -304,7 +257,6 @@ walk1_kernel(DevForest F, const float* __restrict__ items, uint32_t d, uint32_t 
                         heap_push(S.heap, size, ((unsigned long long)ordered_key(f32_min_dev(mg, dist)) << 32) | rc);
                     }
                 }
-                __syncwarp();
                 st = __shfl_sync(0xffffffffu, st, 0);
             } else st = 3;
         }
