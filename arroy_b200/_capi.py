@@ -42,6 +42,7 @@ SIGNATURES = [
     ("arroy_b200_build_trees_begin", C.c_int32, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, CANCEL_FN, C.c_void_p, _u32p]),
     ("arroy_b200_build_trees_emit", C.c_int32, [C.c_void_p, _u32p, _u64p, NODE_SINK, C.c_void_p]),
     ("arroy_b200_build_subtrees_begin", C.c_int32, [C.c_void_p, C.c_uint32, C.c_void_p, _u32p, _u64p, C.c_uint32, CANCEL_FN, C.c_void_p, _u32p]),
+    ("arroy_b200_build_subtrees_begin_at", C.c_int32, [C.c_void_p, C.c_uint32, C.c_void_p, _u64p, _u32p, _u64p, C.c_uint32, CANCEL_FN, C.c_void_p, _u32p, _u64p]),
     ("arroy_b200_build_trees_emit_mapped", C.c_int32, [C.c_void_p, _u32p, _u32p, NODE_SINK, C.c_void_p]),
     ("arroy_b200_build_stats", C.c_int32, [C.c_void_p, C.POINTER(C.c_double)]),
     ("arroy_b200_rerank", C.c_int32, [C.c_void_p, _f32p, C.c_float, C.c_float, _u32p, C.c_uint64, C.c_uint32, _u32p, _f32p, _u32p]),

@@ -235,7 +235,7 @@ class ArroyBuilder:
         except _capi.ArroyB200Error:
             ctx_h = None
         _ck(_lib().arroy_writer_build(w.h, ctx_h, self.rng.h, -1 if self._n_trees is None else self._n_trees, self._split_after or 0,
-                                      self._available_memory or 0, ccb, None, pcb, None))
+                                      (2**64 - 1) if self._available_memory is None else self._available_memory, ccb, None, pcb, None))
 
 
 class Writer:

@@ -71,9 +71,9 @@ struct PinBuf {
 };
 
 struct Wave {  // device buffers of one wave of trees; kept across builds
-    DevBuf st, frames, recs, perm0, perm1, flags, unit_left, pool, pool_counter, jobs, scratch, active, error, final_ids, keys, sub_rows, sub_off, timing, slots, abort, cur_normal;
+    DevBuf st, frames, recs, perm0, perm1, flags, unit_left, pool, pool_counter, jobs, scratch, active, error, final_ids, keys, sub_rows, sub_off, timing, slots, abort, cur_normal, start_pos;
     void release() {
-        sub_rows.release(); sub_off.release(); timing.release(); slots.release(); abort.release(); cur_normal.release();
+        sub_rows.release(); sub_off.release(); timing.release(); slots.release(); abort.release(); cur_normal.release(); start_pos.release();
         st.release(); frames.release(); recs.release(); perm0.release(); perm1.release(); flags.release(); unit_left.release();
         pool.release(); pool_counter.release(); jobs.release(); scratch.release(); active.release(); error.release(); final_ids.release(); keys.release();
     }
@@ -327,7 +327,11 @@ namespace {
 
 using BuiltTree = BuiltTreeView;
 
-struct Subsets { const uint32_t* rows = nullptr; const uint64_t* off = nullptr; };   // host arrays, indexed by global tree
+struct Subsets {   // host arrays, indexed by global tree
+    const uint32_t* rows = nullptr; const uint64_t* off = nullptr;
+    const uint64_t* start_pos = nullptr;   // optional: StdRng words each tree's stream has already consumed
+    uint64_t* end_pos = nullptr;           // optional: ... and has consumed when its tree is finished
+};
 
 // The control kernel is compiled once per metric (and per cluster size): it is bound by instruction fetch, so every
 // instantiation only carries its own metric's code.
@@ -440,7 +444,13 @@ void build_wave(arroy_ctx* c, size_t wave_no, uint32_t t0, uint32_t tw, const ui
     CK(cudaMemsetAsync(W.pool_counter.p, 0, 4, c->stream));
     CK(cudaMemsetAsync(W.error.p, 0, 4, c->stream));
     CK(cudaMemcpyAsync(W.active.p, &tw, 4, cudaMemcpyHostToDevice, c->stream));
-    init_trees_kernel<<<tw, 256, 0, c->stream>>>(P, W.keys.as<uint32_t>());
+    const uint64_t* d_start = nullptr;
+    if (sub.start_pos) {
+        W.start_pos.ensure(8ull * tw);
+        CK(cudaMemcpyAsync(W.start_pos.p, sub.start_pos + t0, 8ull * tw, cudaMemcpyHostToDevice, c->stream));
+        d_start = W.start_pos.as<uint64_t>();
+    }
+    init_trees_kernel<<<tw, 256, 0, c->stream>>>(P, W.keys.as<uint32_t>(), d_start);
     CK(cudaGetLastError());
     c->n_launches += 2;  // + finalize_kernel below
 
@@ -704,6 +714,7 @@ void build_wave(arroy_ctx* c, size_t wave_no, uint32_t t0, uint32_t tw, const ui
         c->stats[2] += (double)st[t].n_splits_tried;
         c->stats[3] += (double)st[t].n_random;
         c->stats[7] += (double)st[t].n_misspec;
+        if (sub.end_pos) sub.end_pos[t0 + t] = st[t].pos;
     }
     CK(cudaStreamSynchronize(c->stream));
     c->d2h_bytes += (uint64_t)pool_used * pool_stride * 4 + sizeof(TreeState) * tw + sizeof(Record) * total_recs + 4ull * n * tw;
@@ -1476,6 +1487,15 @@ int32_t arroy_b200_build_subtrees_begin(arroy_ctx* c, uint32_t n_subtrees, const
     return guarded(c, [&] {
         if (n_subtrees && (!seeds || !rows || !row_offsets)) throw ArgError("null argument");
         Subsets sub; sub.rows = rows; sub.off = row_offsets;
+        do_build_begin(c, n_subtrees, seeds, split_after, cancel, cancel_arg, out_node_counts, sub);
+    });
+}
+int32_t arroy_b200_build_subtrees_begin_at(arroy_ctx* c, uint32_t n_subtrees, const uint8_t (*seeds)[32], const uint64_t* start_pos, const uint32_t* rows,
+                                           const uint64_t* row_offsets, uint32_t split_after, arroy_b200_cancel_fn cancel, void* cancel_arg,
+                                           uint32_t* out_node_counts, uint64_t* out_end_pos) {
+    return guarded(c, [&] {
+        if (n_subtrees && (!seeds || !rows || !row_offsets)) throw ArgError("null argument");
+        Subsets sub; sub.rows = rows; sub.off = row_offsets; sub.start_pos = start_pos; sub.end_pos = out_end_pos;
         do_build_begin(c, n_subtrees, seeds, split_after, cancel, cancel_arg, out_node_counts, sub);
     });
 }

@@ -1196,12 +1196,12 @@ __global__ void finalize_kernel(BuildParams P, uint32_t* __restrict__ final_ids)
     }
 }
 
-__global__ void init_trees_kernel(BuildParams P, const uint32_t* __restrict__ keys /* n_trees x 8 */) {
+__global__ void init_trees_kernel(BuildParams P, const uint32_t* __restrict__ keys /* n_trees x 8 */, const uint64_t* __restrict__ start_pos /* words already consumed, or NULL */) {
     const uint32_t t = blockIdx.x;
     if (threadIdx.x == 0) {
         TreeState s;
         for (int i = 0; i < 8; ++i) s.key[i] = keys[t * 8 + i];
-        s.pos = 0; s.phase = PH_START; s.sp = -1; s.attempts_left = 0; s.cur_slot = NO_SLOT; s.n_recs = 0;
+        s.pos = start_pos ? start_pos[t] : 0; s.phase = PH_START; s.sp = -1; s.attempts_left = 0; s.cur_slot = NO_SLOT; s.n_recs = 0;
         s.n_splits_tried = 0; s.n_random = 0; s.n_misspec = 0; s.scanned = 0; s.slot_next = 0; s.slot_end = 0;
         P.st[t] = s;
         P.jobs[t].kind = JOB_NONE;

@@ -591,7 +591,155 @@ inline int32_t tree_sink(void* arg, uint32_t node_id, const uint8_t* bytes, uint
     return 0;
 }
 
-inline void writer_build(arroy_writer* w, arroy_ctx* ctx, arroy_rng* rng, int64_t n_trees_opt, uint64_t split_after,
+// ---- memory-limited builds (ArroyBuilder::available_memory) ---------------------------------------------------------
+// The reference indexes a large descendant in pieces when the items do not fit in the memory it was given
+// (incremental_index_large_descendant, writer.rs:660-739): a random sample that fits is turned into a tree, the rest is routed
+// through that tree chunk by chunk (insert_items_in_descendants_from_tmpfile, :1463-1531), and every leaf that ended up larger
+// than split_after becomes a new task with its own forked rng (insert_descendants_in_file_and_spawn_tasks, :744-844). The item
+// matrix of this library is resident in HBM either way; what is reproduced is the SHAPE of the forest that such a build
+// produces — the same draws from the same StdRng streams, the same node ids — so that an index built here with a given
+// available_memory equals the reference's. One subtree per device call: arroy_b200_build_subtrees_begin_at continues the
+// task's rng at the word position the host reached and hands back the position the tree ended at.
+struct LmTask { ab::Rng rng; uint32_t id; std::vector<uint32_t> items; };
+
+inline ab::Rng rng_fork(ab::Rng& r) {   // StdRng::from_seed(rng.gen())
+    uint8_t s[32];
+    r.gen_seed(s);
+    uint32_t key[8];
+    for (int i = 0; i < 8; ++i) key[i] = (uint32_t)s[4 * i] | ((uint32_t)s[4 * i + 1] << 8) | ((uint32_t)s[4 * i + 2] << 16) | ((uint32_t)s[4 * i + 3] << 24);
+    ab::Rng out;
+    out.init(key, 0);
+    return out;
+}
+inline uint64_t rng_below_u64(ab::Rng& r, uint64_t high) {   // rng.gen_range(0..high) for usize: UniformInt<u64>::sample_single (rand 0.8.5)
+    const uint64_t range = high;
+    if (range == 0) return r.next_u64();
+    const uint64_t zone = (range << __builtin_clzll(range)) - 1ull;
+    for (;;) {
+        uint64_t v = r.next_u64();
+        unsigned __int128 m = (unsigned __int128)v * (unsigned __int128)range;
+        if ((uint64_t)m <= zone) return (uint64_t)(m >> 64);
+    }
+}
+// how many items fit_in_memory lets through at once — writer.rs:1536-1566 (page_size = 4096, D::size_of_item)
+inline uint64_t lm_items_that_fit(int metric, uint32_t d, uint64_t memory) {
+    const uint64_t page_size = 4096;
+    const uint64_t nb_page_allowed = (uint64_t)std::floor((double)memory / (double)page_size);
+    const uint64_t largest_item_size = 4ull * header_floats(metric) + 4ull * d;
+    const uint64_t nb_items_per_page = page_size / largest_item_size;
+    const uint64_t nb_page_per_item = (uint64_t)std::ceil((double)largest_item_size / (double)page_size);
+    uint64_t nb_items = nb_items_per_page > 1 ? nb_page_allowed * nb_items_per_page : (nb_page_per_item > 1 ? nb_page_allowed / nb_page_per_item : nb_page_allowed);
+    if (nb_items <= d) nb_items = (uint64_t)d + 1;
+    return nb_items;
+}
+
+struct LmMachine {
+    IncCtx& C; NodeIdAlloc& alloc;
+    uint64_t memory; uint32_t split_after;
+    arroy_b200_cancel_fn cancel; void* cancel_arg;
+    std::vector<LmTask> stack;              // the 1-thread rayon pool's local deque: popped LIFO
+    std::map<uint32_t, HNode> tmp;          // the split nodes make_tree_in_file wrote to the thread's TmpNodes
+    uint64_t emitted_bytes = 0;
+
+    // fit_in_memory — writer.rs:1536-1584. `to_insert` ascending ids (RoaringBitmap::select(idx) = idx-th smallest)
+    bool fit_in_memory(std::vector<uint32_t>& to_insert, ab::Rng& rng, std::vector<uint32_t>& out) {
+        out.clear();
+        if (to_insert.empty()) return false;
+        if (to_insert.size() <= C.d) { out.swap(to_insert); return true; }
+        const uint64_t nb_items = lm_items_that_fit(C.metric, C.d, memory);
+        if (nb_items >= to_insert.size()) { out.swap(to_insert); return true; }
+        for (uint64_t i = 0; i < nb_items; ++i) {
+            const uint64_t idx = rng_below_u64(rng, to_insert.size());
+            const uint32_t item = to_insert[idx];
+            out.insert(std::lower_bound(out.begin(), out.end(), item), item);
+            to_insert.erase(to_insert.begin() + idx);
+        }
+        return true;
+    }
+    // make_tree_in_file — writer.rs:1586-1668, on the device, continuing `rng`
+    void make_tree(ab::Rng& rng, const std::vector<uint32_t>& items, uint32_t root_id, IntMapOrder& descendants) {
+        if (items.size() <= C.K) { descendants.entry(root_id) = items; return; }
+        std::vector<uint32_t> rows(items.size());
+        for (size_t i = 0; i < rows.size(); ++i) rows[i] = C.row_of(items[i]);
+        uint8_t seed[32];
+        for (int i = 0; i < 8; ++i) for (int b = 0; b < 4; ++b) seed[4 * i + b] = (uint8_t)(rng.key[i] >> (8 * b));
+        const uint64_t start = rng.pos, off[2] = {0, rows.size()};
+        uint64_t end = 0;
+        uint32_t count = 0;
+        dev_ck(C.ctx, arroy_b200_build_subtrees_begin_at(C.ctx, 1, reinterpret_cast<const uint8_t(*)[32]>(seed), &start, rows.data(), off, split_after,
+                                                        cancel, cancel_arg, &count, &end));
+        uint32_t key[8];
+        memcpy(key, rng.key, sizeof key);
+        rng.init(key, end);
+        std::vector<uint32_t> node_ids(count ? count - 1 : 0);
+        for (auto& id : node_ids) id = alloc.next();   // post-order, the order the recursion takes them in
+        SinkArg sa;
+        dev_ck(C.ctx, arroy_b200_build_trees_emit_mapped(C.ctx, &root_id, node_ids.data(), tree_sink, &sa));
+        emitted_bytes += sa.bytes.load();
+        std::unordered_map<uint32_t, std::string> got;
+        for (int sh = 0; sh < SinkArg::SHARDS; ++sh) for (auto& e : sa.nodes[sh]) got.emplace(e.first, std::move(e.second));
+        node_ids.push_back(root_id);
+        for (uint32_t id : node_ids) {
+            HNode h = decode_tree_node(got.at(id));
+            if (h.kind == 1) descendants.entry(id) = std::move(h.desc);   // pending: it may still grow and become a task
+            else { tmp[id] = h; C.put(id, std::move(h)); }
+        }
+    }
+    // insert_items_in_descendants_from_tmpfile — writer.rs:1463-1531
+    void route(ab::Rng& rng, uint32_t node, const std::vector<uint32_t>& to_insert, IntMapOrder& descendants) {
+        auto it = tmp.find(node);
+        if (it == tmp.end()) {   // not in the tmp file: a pending descendants entry of this task
+            std::vector<uint32_t>& dst = descendants.entry(node);
+            std::vector<uint32_t> merged;
+            std::set_union(dst.begin(), dst.end(), to_insert.begin(), to_insert.end(), std::back_inserter(merged));
+            dst.swap(merged);
+            return;
+        }
+        const HNode& nd = it->second;
+        std::vector<uint32_t> left, right;
+        if (nd.normal.empty()) {
+            for (uint32_t id : to_insert) { if ((int32_t)rng.next_u32() < 0) left.push_back(id); else right.push_back(id); }
+        } else {
+            const int hf = header_floats(C.metric);
+            float h0 = 0.f, h1 = 0.f;
+            memcpy(&h0, nd.normal.data(), 4);
+            if (hf == 2) memcpy(&h1, nd.normal.data() + 4, 4);
+            std::vector<float> nv(C.d);
+            memcpy(nv.data(), nd.normal.data() + 4 * hf, 4ull * C.d);
+            std::vector<uint32_t> rows(to_insert.size());
+            for (size_t i = 0; i < rows.size(); ++i) rows[i] = C.row_of(to_insert[i]);
+            std::vector<uint8_t> side(rows.size());
+            dev_ck(C.ctx, arroy_b200_side_batch(C.ctx, nv.data(), h0, h1, rows.data(), rows.size(), side.data(), nullptr));
+            for (size_t i = 0; i < rows.size(); ++i) { if (side[i]) right.push_back(to_insert[i]); else left.push_back(to_insert[i]); }
+        }
+        const uint32_t l = nd.left, r = nd.right;
+        if (!left.empty()) route(rng, l, left, descendants);
+        if (!right.empty()) route(rng, r, right, descendants);
+    }
+    // insert_descendants_in_file_and_spawn_tasks — writer.rs:744-844, in hashbrown iteration order
+    void process_descendants(ab::Rng& rng, IntMapOrder& descendants) {
+        for (size_t b = 0; b < descendants.keys.size(); ++b) {
+            if (descendants.keys[b] < 0) continue;
+            const uint32_t id = (uint32_t)descendants.keys[b];
+            std::vector<uint32_t>& ids_v = descendants.vals[b];
+            if (ids_v.size() <= C.K) { HNode t; t.kind = 1; t.desc = ids_v; C.put(id, std::move(t)); }
+            else stack.push_back(LmTask{rng_fork(rng), id, std::move(ids_v)});
+        }
+    }
+    // incremental_index_large_descendant — writer.rs:660-739
+    void run_task(LmTask& task) {
+        if (cancel && cancel(cancel_arg)) throw HostError(ARROY_ERR_BUILD_CANCELLED, "The corresponding build process has been cancelled");
+        IntMapOrder descendants;
+        std::vector<uint32_t> to_insert = std::move(task.items), chunk;
+        fit_in_memory(to_insert, task.rng, chunk);
+        make_tree(task.rng, chunk, task.id, descendants);
+        while (fit_in_memory(to_insert, task.rng, chunk)) route(task.rng, task.id, chunk, descendants);
+        process_descendants(task.rng, descendants);
+    }
+    void run() { while (!stack.empty()) { LmTask t = std::move(stack.back()); stack.pop_back(); run_task(t); } }
+};
+
+inline void writer_build(arroy_writer* w, arroy_ctx* ctx, arroy_rng* rng, int64_t n_trees_opt, uint64_t split_after, uint64_t available_memory,
                          arroy_b200_cancel_fn cancel, void* cancel_arg, arroy_progress_fn progress, void* progress_arg) {
     arroy_env* env = w->env;
     std::lock_guard<std::mutex> lk(env->mu);
@@ -675,7 +823,10 @@ inline void writer_build(arroy_writer* w, arroy_ctx* ctx, arroy_rng* rng, int64_
     bool had = read_metadata(env, index, old);
     std::vector<uint32_t> roots = had ? old.roots : std::vector<uint32_t>();
     const uint64_t target = target_n_trees(n_trees_opt, d, n, roots.size());
-    if (!roots.empty()) {
+    // available_memory (UINT64_MAX = not set; the reference divides it by the number of threads of its pool, 1 here): when the
+    // items of one tree do not fit, the whole build goes through the task machine of the update path, as in the reference
+    const uint64_t fit = available_memory == UINT64_MAX ? UINT64_MAX : lm_items_that_fit(w->metric, d, available_memory);
+    if (!roots.empty() || n > fit) {
         // ---- an index that already has trees: update it in place --------------------------------------
         IncCtx C{env, ctx, index, w->metric, d, (size_t)K, {}, {}, &items.ids};
         {
@@ -765,6 +916,17 @@ inline void writer_build(arroy_writer* w, arroy_ctx* ctx, arroy_rng* rng, int64_
         std::vector<std::array<uint8_t, 32>> task_seeds;
         std::vector<uint32_t> task_ids, sub_rows;
         std::vector<uint64_t> sub_off(1, 0);
+        bool limited = false;
+        for (size_t b = 0; b < top.keys.size(); ++b) if (top.keys[b] >= 0 && top.vals[b].size() > fit) limited = true;
+        SinkArg sa;
+        if (limited) {
+            step("CreateTreesForItems");
+            t0 = clk::now();
+            LmMachine M{C, alloc, available_memory, (uint32_t)split_after, cancel, cancel_arg, {}, {}, 0};
+            M.process_descendants(rng1, top);
+            M.run();
+            sa.bytes += M.emitted_bytes;
+        } else {
         for (size_t b = 0; b < top.keys.size(); ++b) {
             if (top.keys[b] < 0) continue;
             cancelled();
@@ -781,7 +943,6 @@ inline void writer_build(arroy_writer* w, arroy_ctx* ctx, arroy_rng* rng, int64_
         }
         step("CreateTreesForItems");
         t0 = clk::now();
-        SinkArg sa;
         if (!task_ids.empty()) {
             const uint32_t ns = (uint32_t)task_ids.size();
             std::vector<uint32_t> counts(ns, 0);
@@ -796,6 +957,7 @@ inline void writer_build(arroy_writer* w, arroy_ctx* ctx, arroy_rng* rng, int64_
             std::vector<std::pair<uint32_t, std::string>> all;
             for (int sh = 0; sh < SinkArg::SHARDS; ++sh) { for (auto& e : sa.nodes[sh]) all.emplace_back(std::move(e)); sa.nodes[sh].clear(); }
             for (auto& e : all) C.pending[e.first] = {true, std::move(e.second)};
+        }
         }
         w->timings[2] = ms_since(t0);
         w->timings[6] = (double)sa.bytes.load();
@@ -1198,9 +1360,9 @@ int32_t arroy_writer_item_vector(arroy_writer* w, uint32_t item, float* out, int
         if (*out_found) memcpy(out, it->second.data() + 1 + 4 * header_floats(w->metric), 4ull * w->dims);
     });
 }
-int32_t arroy_writer_build(arroy_writer* w, arroy_ctx* ctx, arroy_rng* rng, int64_t n_trees, uint64_t split_after, uint64_t /*available_memory*/,
+int32_t arroy_writer_build(arroy_writer* w, arroy_ctx* ctx, arroy_rng* rng, int64_t n_trees, uint64_t split_after, uint64_t available_memory,
                            arroy_b200_cancel_fn cancel, void* cancel_arg, arroy_progress_fn progress, void* progress_arg) {
-    return hguard([&] { writer_build(w, ctx, rng, n_trees, split_after, cancel, cancel_arg, progress, progress_arg); });
+    return hguard([&] { writer_build(w, ctx, rng, n_trees, split_after, available_memory, cancel, cancel_arg, progress, progress_arg); });
 }
 int32_t arroy_writer_build_timings(arroy_writer* w, double out[8]) { for (int i = 0; i < 8; ++i) out[i] = w->timings[i]; return 0; }
 

@@ -184,6 +184,13 @@ int32_t arroy_b200_build_trees_emit(arroy_ctx* ctx, const uint32_t* root_ids, co
 int32_t arroy_b200_build_subtrees_begin(arroy_ctx* ctx, uint32_t n_subtrees, const uint8_t (*seeds)[32],
                                         const uint32_t* rows, const uint64_t* row_offsets, uint32_t split_after,
                                         arroy_b200_cancel_fn cancel, void* cancel_arg, uint32_t* out_node_counts);
+/* The same for hosts that keep using a task's StdRng before and after its tree (memory-limited builds, src/writer.rs:660-739:
+ * fit_in_memory draws from the task rng, make_tree_in_file continues the same stream, the routing and the spawned sub-tasks
+ * continue it again): seeds[s] is the KEY of subtree s' StdRng, start_pos[s] the number of u32 words already consumed (NULL = 0),
+ * out_end_pos[s] (optional) the number consumed when the subtree is finished. */
+int32_t arroy_b200_build_subtrees_begin_at(arroy_ctx* ctx, uint32_t n_subtrees, const uint8_t (*seeds)[32], const uint64_t* start_pos,
+                                           const uint32_t* rows, const uint64_t* row_offsets, uint32_t split_after,
+                                           arroy_b200_cancel_fn cancel, void* cancel_arg, uint32_t* out_node_counts, uint64_t* out_end_pos);
 int32_t arroy_b200_build_trees_emit_mapped(arroy_ctx* ctx, const uint32_t* root_ids, const uint32_t* node_ids,
                                            arroy_b200_node_sink sink, void* sink_arg);
 

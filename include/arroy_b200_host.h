@@ -88,9 +88,11 @@ int32_t arroy_writer_is_empty(arroy_writer* w, int32_t* out);
 int32_t arroy_writer_item_vector(arroy_writer* w, uint32_t item, float* out /* dimensions */, int32_t* out_found);
 
 /* ArroyBuilder::build. n_trees < 0 = not set (target_n_trees formula, src/writer.rs:1358-1394);
- * split_after 0 = not set; available_memory is accepted for interface parity and ignored (the
- * device holds all items, the reference's "everything fits" case). progress receives the
- * MainStep name (src/writer.rs:44-70). */
+ * split_after 0 = not set; available_memory UINT64_MAX = not set. With a value, trees whose items do not "fit"
+ * (fit_in_memory, src/writer.rs:1536-1584) are built the way the reference builds them — a sampled chunk becomes a tree, the
+ * rest is routed through it, oversized leaves become new tasks (src/writer.rs:660-844) — so the forest equals the one the
+ * reference produces with the same setting on a 1-thread pool; the items stay resident in HBM regardless. progress receives
+ * the MainStep name (src/writer.rs:44-70). */
 typedef void (*arroy_progress_fn)(void* arg, const char* main_step);
 int32_t arroy_writer_build(arroy_writer* w, arroy_ctx* ctx, arroy_rng* rng, int64_t n_trees, uint64_t split_after,
                            uint64_t available_memory, arroy_b200_cancel_fn cancel, void* cancel_arg,

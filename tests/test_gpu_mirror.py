@@ -228,3 +228,47 @@ def test_cancel_in_the_middle_of_a_device_build_rolls_back(env_factory):
         assert env.items() == before and w.need_build()
     w.builder(rng42()).n_trees(3).build()
     assert not w.need_build() and env.items() != before
+
+
+def test_little_memory_golden_through_the_writer(env_factory):
+    # src/tests/writer.rs:1377-1391 (write_and_update_lot_of_random_points_with_little_memory): 100 x 3 Cosine, available_memory(0),
+    # 2 trees — every tree is built from sampled chunks + routing + re-spawned tasks; all 188 nodes of the reference's snapshot
+    gold = G["little_memory"]
+    env = env_factory()
+    w = ab.Writer(env, 0, 3, "cosine")
+    rng = rng42()
+    for i in range(100):
+        w.add_item(i, rng.fill_f32(3))
+    w.builder(rng).available_memory(0).n_trees(2).build()
+    r = ab.Reader.open(env, 0, "cosine")
+    assert len(env.tree_nodes()) == 188
+    check_dump(gold, env.tree_nodes(), r._roots(), oracle.COSINE, 3, oracle.decode_node)
+
+
+@pytest.mark.parametrize("metric,n,d,trees,pages", [
+    ("euclidean", 3000, 16, 3, 8),      # 60 items per page -> chunks of 480 items
+    ("cosine", 2500, 40, 2, 20),        # 24 per page -> 480
+    ("dot-product", 2000, 24, 2, 6),    # 39 per page -> 234
+    ("manhattan", 1500, 1200, 2, 300),  # an item spans 2 pages -> 150 items -> raised to d + 1
+])
+def test_memory_limited_build_matches_the_oracle(env_factory, metric, n, d, trees, pages):
+    data = oracle.synth_rows(SEED, d, 0, n, 0.5, threads=4)
+    ids = np.arange(0, 2 * n, 2, dtype=np.uint32)   # sparse ids: rows != ids
+    odb = oracle.Db(metric, d)
+    odb.set_items(ids, data)
+    odb.build_memory_limited(oracle.StdRng(SEED), n_trees=trees, available_memory=pages * 4096)
+    env = env_factory()
+    w = ab.Writer(env, 0, d, metric)
+    w.add_items(ids, data)
+    w.builder(rng42()).available_memory(pages * 4096).n_trees(trees).build()
+    assert env.tree_nodes() == odb.nodes()
+    assert ab.Reader.open(env, 0, metric)._roots() == odb.roots
+    # with enough memory the same call is the plain build
+    env2 = env_factory()
+    w2 = ab.Writer(env2, 0, d, metric)
+    w2.add_items(ids, data)
+    w2.builder(rng42()).available_memory(1 << 40).n_trees(trees).build()
+    full = oracle.Db(metric, d)
+    full.set_items(ids, data)
+    full.build(oracle.StdRng(SEED), n_trees=trees, threads=4)
+    assert env2.tree_nodes() == full.nodes()
