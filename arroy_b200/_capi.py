@@ -7,7 +7,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libarroy_b200.so")
+LIB_PATH = os.environ.get("ARROY_B200_LIB") or os.path.join(_HERE, "libarroy_b200.so")   # (override: A/B runs of two builds)
 
 EUCLIDEAN, COSINE, DOT_PRODUCT, MANHATTAN = 0, 1, 2, 3
 BQ_EUCLIDEAN, BQ_COSINE, BQ_MANHATTAN = 4, 5, 6
@@ -69,6 +69,7 @@ SIGNATURES = [
     ("arroy_b200_device_ptrs", C.c_int32, [C.c_void_p, C.POINTER(C.c_void_p), _u32p]),
     ("arroy_b200_epochs", C.c_int32, [C.c_void_p, _u64p]),
     ("arroy_b200_bq_quantize", C.c_uint32, [_f32p, C.c_uint32, _f32p]),
+    ("arroy_b200_selftest_udiv", C.c_int32, [C.c_void_p, C.c_uint64, C.c_uint64, _u64p, _u64p]),
     ("arroy_b200_stage_begin", C.c_int32, [C.c_void_p, C.c_int32, C.c_uint32, C.c_uint64, _u32p]),
     ("arroy_b200_stage_rows", C.c_int32, [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(C.c_void_p)]),
     ("arroy_b200_stage_end", C.c_int32, [C.c_void_p, C.c_int32]),
@@ -101,6 +102,8 @@ def load():
             raise ImportError("%s is missing — run `python -c 'import __graft_entry__ as g; g.build()'`" % LIB_PATH)
         lib = C.CDLL(LIB_PATH)
         for name, res, args in SIGNATURES:
+            if os.environ.get("ARROY_B200_LIB") and not hasattr(lib, name):
+                continue   # an older build loaded for an A/B run
             fn = getattr(lib, name)
             fn.restype = res
             fn.argtypes = args
@@ -430,6 +433,11 @@ class Context:
         ms = C.c_float(0)
         self._ck(self.lib.arroy_b200_timer_stop(self.h, C.byref(ms)))
         return ms.value
+
+    def selftest_udiv(self, n_groups, seed=1):
+        mism, fb = C.c_uint64(0), C.c_uint64(0)
+        self._ck(self.lib.arroy_b200_selftest_udiv(self.h, n_groups, seed, C.byref(mism), C.byref(fb)))
+        return int(mism.value), int(fb.value)
 
     def epochs(self):
         out = (C.c_uint64 * 2)()

@@ -418,10 +418,11 @@ void build_wave(arroy_ctx* c, size_t wave_no, uint32_t t0, uint32_t tw, const ui
     P.active = W.active.as<uint32_t>(); P.error = W.error.as<int32_t>();
     P.sub_rows = nullptr; P.sub_off = nullptr;
     // cluster-resident nodes: up to ~6 MB of item rows per scan (2048 rows at d = 768, every node of a 10k x 64 index)
+    P.lat_mask = getenv("ARROY_B200_LATMASK") ? (uint32_t)atoi(getenv("ARROY_B200_LATMASK")) : 3u;
     P.small_max = getenv("ARROY_B200_SMALL_MAX") ? (uint32_t)atoi(getenv("ARROY_B200_SMALL_MAX")) : (uint32_t)std::max<uint64_t>(2048, (6ull << 20) / (4ull * ld));
     P.max_inner = 1024u;   // attempts per launch; `cancel` is polled between launches
     P.timing = nullptr;
-    if (getenv("ARROY_B200_CTRL_TIMING")) { W.timing.ensure(16 * 8); CK(cudaMemsetAsync(W.timing.p, 0, 16 * 8, c->stream)); P.timing = W.timing.as<unsigned long long>(); }
+    if (getenv("ARROY_B200_CTRL_TIMING")) { W.timing.ensure(24 * 8); CK(cudaMemsetAsync(W.timing.p, 0, 24 * 8, c->stream)); P.timing = W.timing.as<unsigned long long>(); }
     if (sub.rows) {   // this wave's subsets, offsets rebased to the wave
         const uint64_t b = sub.off[t0], e = sub.off[t0 + tw];
         std::vector<uint64_t> off(tw + 1);
@@ -513,6 +514,7 @@ void build_wave(arroy_ctx* c, size_t wave_no, uint32_t t0, uint32_t tw, const ui
             CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ctrlp, CTRL_THREADS, cand[k]));
             const int cap = nb * c->sm_count;
             if ((nb >= 2 || k == 1) && cap >= (int)tw + std::max(16, c->sm_count / 2)) { persist = true; pgrid = cap; psmem = cand[k]; if (k == 1) P.spec = 0; }
+            if (persist) if (const char* ge = getenv("ARROY_B200_PGRID")) pgrid = std::max((int)tw + 16, std::min(pgrid, atoi(ge)));   // experiments: fewer resident CTAs
         }
     }
     if (persist) {
@@ -672,11 +674,13 @@ void build_wave(arroy_ctx* c, size_t wave_no, uint32_t t0, uint32_t tw, const ui
     c->stats[1] += (double)steps;
     c->breakdown[2] += ms_since(t_loop);
     if (P.timing) {
-        unsigned long long tv[16]; CK(cudaMemcpy(tv, P.timing, sizeof(tv), cudaMemcpyDeviceToHost));
-        const char* nm[16] = {"decide", "rng", "gather", "norms", "two_means_rest", "finish_split", "cluster_scan", "prefix", "partition", "attempts", "inner", "total", "tm_dot_rest", "tm_update", "tm_dots", "tm_finish"};
+        unsigned long long tv[24]; CK(cudaMemcpy(tv, P.timing, sizeof(tv), cudaMemcpyDeviceToHost));
+        const char* nm[20] = {"decide", "rng", "gather", "norms", "two_means_rest", "finish_split", "cluster_scan", "prefix", "partition", "attempts", "inner", "total", "tm_dot_rest", "tm_update", "tm_dots", "tm_finish", "tm_recurrence", "publish_fence", "recur_it0", "recur_it1_9"};
         const double att = (double)std::max<unsigned long long>(tv[9], 1);
         fprintf(stderr, "[ctrl timing] attempts %llu, in-cluster %llu; cycles per attempt:", tv[9], tv[10]);
-        for (int i = 0; i < 16; ++i) if (i != 9 && i != 10) fprintf(stderr, " %s %.0f", nm[i], (double)tv[i] / att);
+        for (int i = 0; i < 20; ++i) if (i != 9 && i != 10) fprintf(stderr, " %s %.0f", nm[i], (double)tv[i] / att);
+        if (tv[22]) fprintf(stderr, "; workers: %llu scan claims (%.1f per attempt), cycles per claim: claim %.0f scan %.0f report %.0f", tv[22], (double)tv[22] / att,
+                            (double)tv[20] / (double)tv[22], (double)tv[21] / (double)tv[22], (double)tv[23] / (double)tv[22]);
         fprintf(stderr, "\n");
     }
     c->breakdown[5] += (double)(steps / steps_per_batch);
@@ -2001,6 +2005,59 @@ int32_t arroy_b200_timer_stop(arroy_ctx* c, float* out_ms) {
         CK(cudaEventRecord(c->tev1, c->stream));
         CK(cudaEventSynchronize(c->tev1));
         CK(cudaEventElapsedTime(out_ms, c->tev0, c->tev1));
+    });
+}
+
+// ---- self-test of UDiv (exact.cuh) against div.rn.f32 -------------------------------------------------------------
+namespace {
+__device__ __forceinline__ uint32_t st_mix(uint64_t x) { x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33; return (uint32_t)x; }
+__global__ void udiv_selftest_kernel(uint64_t n_groups, uint64_t seed, unsigned long long* mismatches, unsigned long long* fallbacks) {
+    const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_groups) return;
+    // divisor classes: the counts 2..11 of two_means, random norms around 1, random positive floats of any exponent
+    const uint32_t r0 = st_mix(seed + 5 * g);
+    float b;
+    switch (r0 & 3u) {
+        case 0: b = (float)(2 + (r0 >> 8) % 10); break;
+        case 1: b = __uint_as_float(0x3f000000u + ((r0 >> 2) & 0x00ffffffu)); break;             // [0.5, 2)
+        case 2: b = __uint_as_float(0x30000000u + ((r0 >> 2) % 0x20000000u)); break;             // 2^-31 .. 2^33
+        default: b = __uint_as_float((r0 >> 1) & 0x7fffffffu); if (!(b > 0.0f) || b > 3.0e38f) b = 1.5f; break;   // anything positive (denormals included)
+    }
+    float a[4];
+    for (int u = 0; u < 4; ++u) {
+        const uint32_t r = st_mix(seed + 5 * g + 1 + u);
+        const uint32_t cls = st_mix(r) & 7u;
+        if (cls < 5) a[u] = __uint_as_float((r & 0x80ffffffu) | ((100u + (r >> 24) % 56u) << 23));   // 2^-27 .. 2^28
+        else if (cls == 5) a[u] = __uint_as_float(r);                                                  // any bit pattern
+        else if (cls == 6) a[u] = __uint_as_float(r & 0x80000000u);                                    // +-0
+        else a[u] = __uint_as_float((r & 0x807fffffu) | ((r >> 23 & 1u) ? 0x7f000000u : 0x00000000u)); // huge / denormal
+    }
+    const ab::UDiv D(b);
+    float q[4];
+    bool bad = !D.ok;
+    for (int u = 0; u < 4; ++u) q[u] = D.fast(a[u], bad);
+    if (bad) { for (int u = 0; u < 4; ++u) q[u] = __fdiv_rn(a[u], b); atomicAdd(fallbacks, 1ull); }
+    for (int u = 0; u < 4; ++u) {
+        const float want = __fdiv_rn(a[u], b);
+        const bool same = __float_as_uint(want) == __float_as_uint(q[u]) || (want != want && q[u] != q[u]);
+        if (!same) atomicAdd(mismatches, 1ull);
+        if (D.ok && !ab::UDiv::suspect(a[u]) && __float_as_uint(D.quot(a[u])) != __float_as_uint(want)) atomicAdd(mismatches, 1ull);   // the bare quotient where it is trusted
+    }
+}
+}  // namespace
+int32_t arroy_b200_selftest_udiv(arroy_ctx* c, uint64_t n_groups, uint64_t seed, uint64_t* out_mismatches, uint64_t* out_fallbacks) {
+    return guarded(c, [&] {
+        if (!out_mismatches || !out_fallbacks) throw ArgError("null argument");
+        set_device(c);
+        c->s_misc.ensure(64);
+        CK(cudaMemsetAsync(c->s_misc.p, 0, 16, c->stream));
+        unsigned long long* d = c->s_misc.as<unsigned long long>();
+        if (n_groups) udiv_selftest_kernel<<<(unsigned)((n_groups + 255) / 256), 256, 0, c->stream>>>(n_groups, seed, d, d + 1);
+        CK(cudaGetLastError());
+        unsigned long long h[2];
+        CK(cudaMemcpyAsync(h, d, 16, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        *out_mismatches = h[0]; *out_fallbacks = h[1];
     });
 }
 

@@ -97,6 +97,7 @@ struct BuildParams {
     // cluster-resident small nodes (control_kernel<.., CS > 1>): nodes of at most small_max rows are
     // scanned by the control kernel's own cluster, at most max_inner attempts per launch
     uint32_t small_max, max_inner;
+    uint32_t lat_mask;      // persistent schedule: worker w is a latency worker when (w & lat_mask) == 0
     unsigned long long* timing;   // optional: 16 cycle counters summed over all control launches (ARROY_B200_CTRL_TIMING)
     // persistent schedule
     PSlot* slots;                 // n_trees
@@ -125,13 +126,13 @@ struct TwoMeansShared {
     float res[2][2];        // di, dj, double buffered by iteration parity
     float php[2], phq[2];   // headers of p and q
     float misc[2];
-    long long tacc[16];     // cycle accumulators of the phases (thread 0; flushed to BuildParams::timing when set)
+    long long tacc[24];     // cycle accumulators of the phases (thread 0; flushed to BuildParams::timing when set)
     long long tlast;
     // speculative two_means
     float G[12][12];        // approximate dots between the 12 gathered vectors (0 = p, 1 = q after normalize, 2.. = the ten k)
     float Gp[8][16][16];    // its partial products, one 16 x 16 tile per warp
     float An[10][10];       // An[it][l] = (k_it / norm_it) . k_l
-    float rc[10][6];        // per-iteration constants of the recurrence
+    float rc[10][7];        // per-iteration constants of the recurrence
     float vdot[32];         // exact dots of the verification pass
     int choice[10];         // per iteration: 0 = nothing moved, 1 = p moved, 2 = q moved
     int ready;              // iterations whose choice has been published by the speculating warp
@@ -139,7 +140,9 @@ struct TwoMeansShared {
 };
 // phase ids of BuildParams::timing
 enum { TP_DECIDE = 0, TP_RNG = 1, TP_GATHER = 2, TP_NORMS = 3, TP_TWOMEANS = 4, TP_FINISH_SPLIT = 5, TP_CLUSTER_SCAN = 6, TP_PREFIX = 7, TP_PARTITION = 8, TP_ATTEMPTS = 9, TP_INNER = 10, TP_TOTAL = 11, TP_TM_DOT = 12, TP_TM_UPD = 13 };
-#define TP_MARK(S_, id_) do { if (P.timing != nullptr && threadIdx.x == 0) { long long now_ = clock64(); (S_).tacc[id_] += now_ - (S_).tlast; (S_).tlast = now_; } } while (0)
+// (thread 0 records; the WARPSYNC afterwards merges it with the rest of warp 0 again — without it the warp stays split behind
+// every mark and the phase that follows is measured several times slower than it runs)
+#define TP_MARK(S_, id_) do { if (P.timing != nullptr && threadIdx.x < 32) { if (threadIdx.x == 0) { long long now_ = clock64(); (S_).tacc[id_] += now_ - (S_).tlast; (S_).tlast = now_; } __syncwarp(); } } while (0)
 
 // hsum256 of the four accumulators + ((h1+h2)+h3)+h4 when lane l holds accumulator lane l (simple_avx.rs:6-13)
 __device__ __forceinline__ float warp_hsum_exact(float acc) {
@@ -258,58 +261,99 @@ __device__ __forceinline__ bool spec_two_means(const BuildParams& P, float* ws, 
         S.rc[tid][3] = (metric == COSINE) ? __fdividef(1.f, S.h0[2 + tid]) : S.h0[2 + tid];   // Cosine: 1 / |k| (stored header); DotProduct: k.extra_dim
         S.rc[tid][4] = S.h1[2 + tid];                            // DotProduct: k's norm header
         S.rc[tid][5] = (nrm != nrm || nrm <= 0.f) ? 0.f : 1.f;   // the loop's `continue` guard (mod.rs:152-155)
+        S.rc[tid][6] = rsqrtf(S.h1[2 + tid]);                    // DotProduct: 1 / sqrt(k's norm header)
     }
     if (tid >= 32 && tid < 132) { const int it = (tid - 32) / 10, l = (tid - 32) - 10 * it; S.An[it][l] = S.G[2 + it][2 + l] * __fdividef(1.f, cosine ? S.nk[2 + it] : 1.f); }
     __syncthreads();
     TP_MARK(S, TP_TM_DOT);
     if (warp == 0) {
         // (1b) the recurrence on SUMS: with Sp = ic * p (the sum of p0 and the k / norm assigned to it), lane l < 10 carries
-        // Sp . k_l and Sq . k_l; every lane carries Sp . Sp, Sq . Sq and the counts. An update is one add per lane.
+        // Sp . k_l and Sq . k_l; every lane carries Sp . Sp, Sq . Sq and the counts. The warp runs alone, so what counts is the
+        // length of the dependent chain from one branch to the next: the dots of the NEXT iteration are fetched from their lanes
+        // before this iteration's branch is known (and patched with one add afterwards), and everything a branch changes — the
+        // new Sp . Sp, its rsqrt / reciprocal, the new count — is computed for both outcomes ahead of the comparison.
         const int li = lane < 10 ? lane : 0;
+        long long tw0 = 0;
+        if (P.timing != nullptr) tw0 = clock64();
         float spk = S.G[0][2 + li], sqk = S.G[1][2 + li];
         float spp = S.G[0][0], sqq = S.G[1][1], ic = 1.f, jc = 1.f;
+        float a = __shfl_sync(full, spk, 0), b = __shfl_sync(full, sqk, 0);
+        float rp = EUCLID ? 1.f : rsqrtf(spp), rq = EUCLID ? 1.f : rsqrtf(sqq);   // Euclidean: 1 / count; angular: 1 / |Sp|
         const float pe = S.php[0], qe = S.phq[0];   // DotProduct: extra_dim of the centroids (update_mean leaves headers alone)
-#pragma unroll 1
+#pragma unroll
         for (int it = 0; it < 10; ++it) {
-            const float a = __shfl_sync(full, spk, it), b = __shfl_sync(full, sqk, it);
             const float inv = S.rc[it][0], bb = S.rc[it][1], kk = S.rc[it][2], ka = S.rc[it][3], ok = S.rc[it][5];
             const float g = S.An[it][li];
+            float a_nb = 0.f, b_nb = 0.f, g_n = 0.f;
+            if (it < 9) { a_nb = __shfl_sync(full, spk, it + 1); b_nb = __shfl_sync(full, sqk, it + 1); g_n = S.An[it][it + 1]; }
+            const float spp_n = spp + (2.f * a * inv + bb), sqq_n = sqq + (2.f * b * inv + bb);
+            const float ic_n = ic + 1.f, jc_n = jc + 1.f;
+            const float rp_n = EUCLID ? __fdividef(1.f, ic_n) : rsqrtf(spp_n), rq_n = EUCLID ? __fdividef(1.f, jc_n) : rsqrtf(sqq_n);
             float di, dj;
-            if (EUCLID) { di = spp * __fdividef(1.f, ic) - 2.f * a + ic * kk; dj = sqq * __fdividef(1.f, jc) - 2.f * b + jc * kk; }
+            if (EUCLID) { di = spp * rp - 2.f * a + ic * kk; dj = sqq * rq - 2.f * b + jc * kk; }
             else if (metric == COSINE) {
-                const float cp = fminf(1.f, fmaxf(-1.f, a * rsqrtf(spp) * ka)), cq = fminf(1.f, fmaxf(-1.f, b * rsqrtf(sqq) * ka));
+                const float cp = fminf(1.f, fmaxf(-1.f, a * rp * ka)), cq = fminf(1.f, fmaxf(-1.f, b * rq * ka));
                 di = ic * (1.f - cp); dj = jc * (1.f - cq);
             } else {
-                const float kb = S.rc[it][4];
+                const float kb = S.rc[it][4], rkb = S.rc[it][6];   // (slot 6 of rc: 1 / sqrt(k's norm header))
                 const float mp = spp * kb, mq = sqq * kb;
-                di = mp >= 1.17549435e-38f * ic * ic ? ic * (2.f - 2.f * (a + ic * pe * ka) * rsqrtf(mp)) : ic * 2.f;
-                dj = mq >= 1.17549435e-38f * jc * jc ? jc * (2.f - 2.f * (b + jc * qe * ka) * rsqrtf(mq)) : jc * 2.f;
+                di = mp >= 1.17549435e-38f * ic * ic ? ic * (2.f - 2.f * (a + ic * pe * ka) * rp * rkb) : ic * 2.f;
+                dj = mq >= 1.17549435e-38f * jc * jc ? jc * (2.f - 2.f * (b + jc * qe * ka) * rq * rkb) : jc * 2.f;
             }
-            int ch = 0;
-            if (ok != 0.f) ch = di < dj ? 1 : (dj < di ? 2 : 0);
-            if (ch == 1) { spk += g; spp += 2.f * a * inv + bb; ic += 1.f; }
-            else if (ch == 2) { sqk += g; sqq += 2.f * b * inv + bb; jc += 1.f; }
-            if (lane == 0) S.choice[it] = ch;
+            const bool c1 = ok != 0.f && di < dj, c2 = ok != 0.f && dj < di;
+            spk += c1 ? g : 0.f; sqk += c2 ? g : 0.f;
+            a = a_nb + (c1 ? g_n : 0.f); b = b_nb + (c2 ? g_n : 0.f);
+            spp = c1 ? spp_n : spp; rp = c1 ? rp_n : rp; ic = c1 ? ic_n : ic;
+            sqq = c2 ? sqq_n : sqq; rq = c2 ? rq_n : rq; jc = c2 ? jc_n : jc;
+            if (lane == 0) S.choice[it] = c1 ? 1 : (c2 ? 2 : 0);
+        }
+        asm volatile("" :: "f"(spk), "f"(sqk), "f"(spp), "f"(sqq), "f"(a), "f"(b) : "memory");
+        if (P.timing != nullptr && lane == 0) S.tacc[18] += clock64() - tw0;
+    } else if (cosine) {
+        // meanwhile the other warps divide the ten k by their norms (the k / norm term of update_mean, mod.rs:172-180) into the
+        // slots the centroid versions will be produced in; element i belongs to thread (i mod 224) + 32 from here on
+        for (int it = 0; it < 10; ++it) {
+            const float* k = ws + (size_t)(2 + it) * ld;
+            float* out = ws + (size_t)(14 + it) * ld;
+            const float norm = S.nk[2 + it];
+            const UDiv D(norm);
+            if (!(norm > 0.0f)) continue;                       // the iteration is skipped (mod.rs:152-155): nothing reads the slot
+            bool bad = !D.ok;
+            for (int i0 = tid - 32; i0 < ld; i0 += 4 * (CTRL_THREADS - 32)) {
+                float a[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { const int i = i0 + u * (CTRL_THREADS - 32); a[u] = i < d ? k[i] : 0.f; }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { const int i = i0 + u * (CTRL_THREADS - 32); bad = bad || UDiv::suspect(a[u]); if (i < ld) out[i] = D.quot(a[u]); }
+            }
+            if (bad) S.mismatch = 1;                            // out of the fast division's range: the sequential loop decides
         }
     }
-    // (the other warps wait here without issuing: a spinning warp on warp 0's scheduler would halve the recurrence's speed)
     __syncthreads();
-    {
+    TP_MARK(S, 16);
+    if (warp != 0) {
         // the centroid versions, element-wise and in the reference's exact operations; every thread only re-reads elements it
         // wrote itself, so the ten steps need no barrier
-        const int nt = CTRL_THREADS, t = tid;
         float ic = 1.f, jc = 1.f;
         int ps = 0, qs = 1;
 #pragma unroll 1
         for (int it = 0; it < 10; ++it) {
             const int ch = S.choice[it];
             if (ch == 0) continue;
-            const float* k = ws + (size_t)(2 + it) * ld;
-            const float norm = cosine ? S.nk[2 + it] : 1.0f;
+            const float* kn = ws + (size_t)(cosine ? 14 + it : 2 + it) * ld;   // norm = 1: k / norm = k
             const float* cen = ws + (size_t)(ch == 1 ? ps : qs) * ld;
             float* out = ws + (size_t)(14 + it) * ld;
             const float cnt = ch == 1 ? ic : jc, c1 = __fadd_rn(cnt, 1.0f);
-            for (int i = t; i < ld; i += nt) out[i] = i < d ? __fdiv_rn(__fadd_rn(__fmul_rn(cen[i], cnt), __fdiv_rn(k[i], norm)), c1) : 0.f;
+            const UDiv D(c1);                                   // c1 = 2 .. 11
+            bool bad = false;
+            for (int i0 = tid - 32; i0 < ld; i0 += 4 * (CTRL_THREADS - 32)) {
+                float a[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { const int i = i0 + u * (CTRL_THREADS - 32); a[u] = i < d ? __fadd_rn(__fmul_rn(cen[i], cnt), kn[i]) : 0.f; }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { const int i = i0 + u * (CTRL_THREADS - 32); bad = bad || UDiv::suspect(a[u]); if (i < ld) out[i] = D.quot(a[u]); }
+            }
+            if (bad) S.mismatch = 1;
             if (ch == 1) { ps = 14 + it; ic = c1; } else { qs = 14 + it; jc = c1; }
         }
     }
@@ -565,8 +609,8 @@ __device__ __forceinline__ void create_split_cta(const BuildParams& P, Rng& rng 
         if (gi < 12 && (lane & 7) == 0) S.nk[gi] = x;
         __syncthreads();
         const float np = S.nk[0], nq = S.nk[1];
-        if (np > 0.0f) for (int i = tid; i < d; i += blockDim.x) p[i] = __fdiv_rn(p[i], np);
-        if (nq > 0.0f) for (int i = tid; i < d; i += blockDim.x) q[i] = __fdiv_rn(q[i], nq);
+        if (np > 0.0f) udiv_loop(tid, CTRL_THREADS, d, np, [&](int i) { return p[i]; }, [&](int i, float v) { p[i] = v; });
+        if (nq > 0.0f) udiv_loop(tid, CTRL_THREADS, d, nq, [&](int i) { return q[i]; }, [&](int i, float v) { q[i] = v; });
         if (tid == 0 && metric == DOT_PRODUCT) {
             if (np > 0.0f) S.php[0] = __fdiv_rn(S.php[0], np);
             if (nq > 0.0f) S.phq[0] = __fdiv_rn(S.phq[0], nq);
@@ -622,12 +666,12 @@ __device__ __forceinline__ void create_split_cta(const BuildParams& P, Rng& rng 
     __syncthreads();
     const float nn = S.misc[0];
     float* out = slot_ptr + NORMAL_HDR;
-    if (nn > 0.0f) { for (int i = tid; i < d; i += blockDim.x) nv[i] = __fdiv_rn(nv[i], nn); extra = (metric == DOT_PRODUCT) ? __fdiv_rn(extra, nn) : extra; }
+    if (nn > 0.0f) { udiv_loop(tid, CTRL_THREADS, d, nn, [&](int i) { return nv[i]; }, [&](int i, float v) { nv[i] = v; }); extra = (metric == DOT_PRODUCT) ? __fdiv_rn(extra, nn) : extra; }
     for (int i = tid; i < ld; i += blockDim.x) out[i] = nv[i];  // each thread re-reads only what it wrote
     if (mirror != nullptr) for (int i = tid; i < ld; i += blockDim.x) mirror[NORMAL_HDR + i] = nv[i];
     if (metric == EUCLIDEAN || metric == MANHATTAN) {
         // bias = sum over i of ((-n_i) * (p_i + q_i)) / 2, folded left to right from +0.0
-        for (int i = tid; i < d; i += blockDim.x) sc1[i] = __fdiv_rn(__fmul_rn(-nv[i], __fadd_rn(p[i], q[i])), 2.0f);
+        for (int i = tid; i < d; i += blockDim.x) sc1[i] = __fmul_rn(__fmul_rn(-nv[i], __fadd_rn(p[i], q[i])), 0.5f);   // x / 2 == x * 0.5 in every rounding case
         __syncthreads();
         if (tid == 0) {
             float bias = 0.0f;
@@ -784,7 +828,7 @@ __device__ __noinline__ void pworker(const BuildParams& P, float* sm_normal) {
     const uint32_t T = P.n_trees;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t rot = (blockIdx.x - T) * 7u;
-    const bool latency_class = ((blockIdx.x - T) & 3u) == 0u;
+    const bool latency_class = ((blockIdx.x - T) & P.lat_mask) == 0u;
     uint32_t loaded_t = 0xffffffffu, loaded_seq = 0xffffffffu;
     float nh0 = 0.f;
     if (tid == 0) w_exit = 0;
@@ -948,7 +992,7 @@ __global__ void __launch_bounds__(CTRL_THREADS, (CS == 0 ? 2 : 1)) control_kerne
     // job.kind is already JOB_NONE and job.pad 0 for a finished tree / after an error
     if (P.st[t].phase == PH_DONE || *P.error != ERR_NONE) { if (CS > 1) cooperative_groups::this_cluster().sync(); return; }
     uint32_t inner = 0;
-    if (P.timing != nullptr && threadIdx.x == 0) { for (int i = 0; i < 16; ++i) TM.tacc[i] = 0; TM.tlast = clock64(); TM.tacc[TP_TOTAL] = -TM.tlast; }
+    if (P.timing != nullptr && threadIdx.x == 0) { for (int i = 0; i < 24; ++i) TM.tacc[i] = 0; TM.tlast = clock64(); TM.tacc[TP_TOTAL] = -TM.tlast; }
     Frame* gframes = P.frames + (size_t)t * MAX_DEPTH;
     if (threadIdx.x == 0) S = P.st[t];
     __syncthreads();
@@ -1087,6 +1131,7 @@ __global__ void __launch_bounds__(CTRL_THREADS, (CS == 0 ? 2 : 1)) control_kerne
                 // flight) and the job fields must be visible device-wide before the job opens
                 __threadfence();
                 __syncthreads();
+                TP_MARK(TM, 17);
                 const uint32_t units = (f.len + SCAN_UNIT - 1) / SCAN_UNIT;
                 if (tid == 0) {
                     s_pseq += 1;
@@ -1178,7 +1223,7 @@ __global__ void __launch_bounds__(CTRL_THREADS, (CS == 0 ? 2 : 1)) control_kerne
     if (tid == 0) { S.pos = s_rng.pos; P.st[t] = S; }
     if (tid == 0 && P.timing) {
         TM.tacc[TP_TOTAL] += clock64();
-        for (int i = 0; i < 16; ++i) atomicAdd(P.timing + i, (unsigned long long)TM.tacc[i]);
+        for (int i = 0; i < 20; ++i) atomicAdd(P.timing + i, (unsigned long long)TM.tacc[i]);
     }
 }
 

@@ -320,6 +320,11 @@ int32_t arroy_b200_rerank_breakdown(arroy_ctx* ctx, double out[8]);
 int32_t arroy_b200_timer_start(arroy_ctx* ctx);
 int32_t arroy_b200_timer_stop(arroy_ctx* ctx, float* out_ms);
 
+/* Self-test of the library's branch-free f32 division (used inside create_split / two_means for x / norm and x / count, which
+ * the reference computes with IEEE division — src/distance/mod.rs:86-94, :76-82): n_groups x 4 quotients over every operand
+ * class against div.rn.f32; *out_mismatches must come back 0. out_fallbacks = groups that took the div.rn path. */
+int32_t arroy_b200_selftest_udiv(arroy_ctx* ctx, uint64_t n_groups, uint64_t seed, uint64_t* out_mismatches, uint64_t* out_fallbacks);
+
 /* BinaryQuantized::from_slice + ::iter of one vector (host helper, no device): out[i] = is_sign_positive(in[i]) ? 1 : -1 for
  * i < dims, -1 up to the next multiple of 64. Returns that padded length; in / out may be NULL to query it. */
 uint32_t arroy_b200_bq_quantize(const float* in, uint32_t dims, float* out);

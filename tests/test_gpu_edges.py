@@ -132,3 +132,15 @@ def test_count_beyond_the_topk_buffer(ctx, metric):
     for i in range(3):
         wr, wd = oracle.rerank(m, data[i], oracle.new_header(m, data[i]), data, h0, None, rows, k)
         assert out_len[i] == k and out_rows[i].tolist() == wr.tolist() and out_dist[i].tobytes() == wd.tobytes()
+
+
+def test_branch_free_division_equals_div_rn(ctx):
+    # create_split / two_means divide by a loop-invariant norm or count; the library does that with the refinement of div.rn's own
+    # fast path hoisted out of the loop (exact.cuh UDiv). 2^28 quotients over every operand class (normal, +-0, denormal, huge,
+    # NaN / Inf patterns; divisors 2..11, around 1, any exponent) must equal div.rn.f32 bit for bit.
+    total_fb = 0
+    for seed in (1, 2, 3, 4):
+        mism, fb = ctx.selftest_udiv(1 << 24, seed * 0x9E3779B97F4A7C15 % (1 << 63))
+        assert mism == 0
+        total_fb += fb
+    assert 0 < total_fb < 4 * (1 << 24)   # both paths were exercised
