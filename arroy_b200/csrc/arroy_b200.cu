@@ -71,9 +71,9 @@ struct PinBuf {
 };
 
 struct Wave {  // device buffers of one wave of trees; kept across builds
-    DevBuf st, frames, recs, perm0, perm1, flags, unit_left, pool, pool_counter, jobs, scratch, active, error, final_ids, keys, sub_rows, sub_off, timing, slots, abort, cur_normal, start_pos;
+    DevBuf st, frames, recs, perm0, perm1, flags, unit_left, pool, pool_counter, jobs, scratch, active, error, final_ids, keys, sub_rows, sub_off, timing, slots, abort, cur_normal, start_pos, root;
     void release() {
-        sub_rows.release(); sub_off.release(); timing.release(); slots.release(); abort.release(); cur_normal.release(); start_pos.release();
+        sub_rows.release(); sub_off.release(); timing.release(); slots.release(); abort.release(); cur_normal.release(); start_pos.release(); root.release();
         st.release(); frames.release(); recs.release(); perm0.release(); perm1.release(); flags.release(); unit_left.release();
         pool.release(); pool_counter.release(); jobs.release(); scratch.release(); active.release(); error.release(); final_ids.release(); keys.release();
     }
@@ -526,6 +526,13 @@ void build_wave(arroy_ctx* c, size_t wave_no, uint32_t t0, uint32_t tw, const ui
         P.slots = W.slots.as<PSlot>();
         P.cur_normal = W.cur_normal.as<float>();
         P.abort = W.abort.as<int>();
+        // fused root scan: every tree of the wave starts at the root of the whole index (no subtree mode), rows go through the
+        // 8-lanes-per-row path, and a batch of normals fits next to nothing else in the workers' shared memory
+        const char* rf = getenv("ARROY_B200_ROOT_FUSE");
+        P.root_fused = (!sub.rows && tw >= 2 && P.d >= 32 && (size_t)ROOT_TB * ld * 4 <= psmem && !(rf && atoi(rf) == 0)) ? 1 : 0;
+        W.root.ensure(8);
+        CK(cudaMemsetAsync(W.root.p, 0, 8, c->stream));
+        P.root_ready = W.root.as<uint32_t>(); P.root_ticket = W.root.as<uint32_t>() + 1;
     }
 
     auto launch_step = [&](cudaStream_t s) {  // lockstep: all trees per launch
@@ -679,8 +686,7 @@ void build_wave(arroy_ctx* c, size_t wave_no, uint32_t t0, uint32_t tw, const ui
         const double att = (double)std::max<unsigned long long>(tv[9], 1);
         fprintf(stderr, "[ctrl timing] attempts %llu, in-cluster %llu; cycles per attempt:", tv[9], tv[10]);
         for (int i = 0; i < 20; ++i) if (i != 9 && i != 10) fprintf(stderr, " %s %.0f", nm[i], (double)tv[i] / att);
-        if (tv[22]) fprintf(stderr, "; workers: %llu scan claims (%.1f per attempt), cycles per claim: claim %.0f scan %.0f report %.0f", tv[22], (double)tv[22] / att,
-                            (double)tv[20] / (double)tv[22], (double)tv[21] / (double)tv[22], (double)tv[23] / (double)tv[22]);
+        if (tv[20]) fprintf(stderr, "; fused root pass: %llu cycles on the slowest worker", tv[20]);
         fprintf(stderr, "\n");
     }
     c->breakdown[5] += (double)(steps / steps_per_batch);

@@ -103,6 +103,11 @@ struct BuildParams {
     PSlot* slots;                 // n_trees
     float* cur_normal;            // n_trees x pool_stride: the normal of each tree's open scan job, at an address workers know without the job fields
     const volatile int* abort;    // set by the host (cancel): control CTAs stop at their next wait
+    // fused root scan: when every tree of the wave starts at the root of the whole index, the first split's side() scans of all
+    // trees read the same rows — the workers do them in ONE pass over the item matrix (proot below)
+    int32_t root_fused;
+    uint32_t* root_ready;         // number of trees whose root normal is published
+    uint32_t* root_ticket;        // next unclaimed chunk of the fused pass
 };
 
 __device__ __forceinline__ double split_imbalance_dev(uint32_t l, uint32_t r) {  // src/writer.rs:1348-1353
@@ -819,6 +824,163 @@ __device__ __forceinline__ bool pwait(const BuildParams& P, PSlot& sl, uint32_t 
     }
 }
 
+// ---- fused root scan -------------------------------------------------------------------------------------------------------
+// The root of every tree is the whole index, so the first side() scan of each of the wave's T trees reads all n rows: T passes
+// over the item matrix (at 50 trees, one eleventh of all the bytes a C2 build reads). Here the workers wait until the T root
+// normals are published and make ONE pass: a claim is ROOT_CHUNK scan units; for every batch of ROOT_TB normals (staged in
+// shared memory) its rows are dotted with all of them — the first batch streams the rows from HBM, the others find them in
+// L2 — in exactly scan_unit's summation order, so flags and unit counts are the ones T separate scans would have written.
+constexpr int ROOT_TB = 8;       // normals per pass over a claim's rows (8 x 2 rows x float4 accumulators = 64 registers)
+constexpr uint32_t ROOT_CHUNK = 8;   // scan units per claim (measured: 8 -> 18.8M cycles for 50 roots of 1M x 768, 4 -> 20.3M, 1 -> 21.3M)
+
+// units [u0, u1) of the root against the NB normals staged in smN (trees tb .. tb + NB - 1). The next chunk of the two rows
+// and the next normal's chunk are requested before the current one is used: the loop has to run at the FMA rate, not at the
+// latency of a load.
+// ask L2 for the rows of one scan unit of the root (identity id list): one bulk prefetch per row, no register is tied up
+__device__ __forceinline__ void proot_prefetch(const BuildParams& P, uint32_t unit) {
+    const uint32_t r = unit * SCAN_UNIT + threadIdx.x;
+    if (threadIdx.x < SCAN_UNIT && r < P.n) {
+        const float* row = P.items + (size_t)r * P.ld;
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(row), "r"(P.ld * 4u) : "memory");
+    }
+}
+template <int NB>
+__device__ __forceinline__ void proot_units(const BuildParams& P, uint32_t u0, uint32_t u1, uint32_t tb, uint32_t next_u0, const float* smN, const float* r_h0, uint32_t* r_cnt) {
+    const uint32_t n = P.n, d = P.d, ld = P.ld;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g8 = lane & 7, grp = lane >> 3;
+    const int nch = (int)(d >> 5);
+    const uint32_t units_all = (n + SCAN_UNIT - 1) / SCAN_UNIT;
+    for (uint32_t unit = u0; unit < u1; ++unit) {
+        if (tid < NB) r_cnt[tid] = 0;
+        if (tb == 0) {   // the first batch meets the rows in HBM: have the next unit (of this claim, then of the next one) on its way to L2
+            const uint32_t nu = unit + 1 < u1 ? unit + 1 : next_u0;
+            if (nu < units_all) proot_prefetch(P, nu);
+        }
+        __syncthreads();
+        const uint32_t pa = unit * SCAN_UNIT + warp * 8 + grp * 2, pb = pa + 1;
+        const bool va = pa < n, vb = pb < n;
+        const uint32_t ra = va ? pa : 0u, rb = vb ? pb : 0u;   // the root's id list is the identity
+        const float4* A = reinterpret_cast<const float4*>(P.items + (size_t)ra * ld) + g8;
+        const float4* B = reinterpret_cast<const float4*>(P.items + (size_t)rb * ld) + g8;
+        const float4* N = reinterpret_cast<const float4*>(smN) + g8;
+        const int nstride = (int)(ld >> 2);   // float4 per normal
+        float4 acc[NB][2];
+#pragma unroll
+        for (int j = 0; j < NB; ++j) { acc[j][0] = make_float4(0.f, 0.f, 0.f, 0.f); acc[j][1] = acc[j][0]; }
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f), z = x, x1 = x, z1 = x;
+        if (nch > 0) { x = ldg_stream(A); z = ldg_stream(B); }
+        if (nch > 1) { x1 = ldg_stream(A + 8); z1 = ldg_stream(B + 8); }
+#pragma unroll 1
+        for (int c = 0; c < nch; ++c) {
+            float4 xn = x1, zn = z1;
+            if (c + 2 < nch) { x1 = ldg_stream(A + (c + 2) * 8); z1 = ldg_stream(B + (c + 2) * 8); }
+            float4 y = N[c * 8];
+#pragma unroll
+            for (int j = 0; j < NB; ++j) {
+                float4 yn = y;
+                if (j + 1 < NB) yn = N[(j + 1) * nstride + c * 8];
+                acc[j][0].x = fmaf(x.x, y.x, acc[j][0].x); acc[j][0].y = fmaf(x.y, y.y, acc[j][0].y);
+                acc[j][0].z = fmaf(x.z, y.z, acc[j][0].z); acc[j][0].w = fmaf(x.w, y.w, acc[j][0].w);
+                acc[j][1].x = fmaf(z.x, y.x, acc[j][1].x); acc[j][1].y = fmaf(z.y, y.y, acc[j][1].y);
+                acc[j][1].z = fmaf(z.z, y.z, acc[j][1].z); acc[j][1].w = fmaf(z.w, y.w, acc[j][1].w);
+                y = yn;
+            }
+            x = xn; z = zn;
+        }
+        const float* rowa = P.items + (size_t)ra * ld;
+        const float* rowb = P.items + (size_t)rb * ld;
+        const float iha = (P.metric == DOT_PRODUCT) ? P.ih0[ra] : 0.f, ihb = (P.metric == DOT_PRODUCT) ? P.ih0[rb] : 0.f;
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+            float da = group8_hsum(acc[j][0]), db = group8_hsum(acc[j][1]);
+            const float* nv = smN + (size_t)j * ld;
+            for (uint32_t i = (uint32_t)nch * 32; i < d; ++i) {   // len % 32 tail: separately rounded mul, add
+                da = __fadd_rn(da, __fmul_rn(rowa[i], nv[i]));
+                db = __fadd_rn(db, __fmul_rn(rowb[i], nv[i]));
+            }
+            const int sa = side_of(margin_finish(P.metric, da, r_h0[j], iha)), sb = side_of(margin_finish(P.metric, db, r_h0[j], ihb));
+            uint8_t* fl = P.flags + (size_t)(tb + j) * n;
+            const bool leader = g8 == 0;
+            if (leader && va) fl[pa] = (uint8_t)sa;
+            if (leader && vb) fl[pb] = (uint8_t)sb;
+            const unsigned la = __ballot_sync(0xffffffffu, leader && va && sa == 0), lb = __ballot_sync(0xffffffffu, leader && vb && sb == 0);
+            if (lane == 0) { const int cn = __popc(la) + __popc(lb); if (cn) atomicAdd(&r_cnt[j], (uint32_t)cn); }
+        }
+        __syncthreads();
+        if (tid < NB) (P.unit_left + (size_t)(tb + tid) * P.units_per_tree)[unit] = r_cnt[tid];
+    }
+}
+
+__device__ __noinline__ void proot(const BuildParams& P, float* smN) {
+    __shared__ uint32_t r_claim, r_ok;
+    __shared__ uint32_t r_cnt[ROOT_TB];
+    __shared__ float r_h0[ROOT_TB];
+    const uint32_t T = P.n_trees, n = P.n, ld = P.ld;
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        uint32_t ok = 1;
+        while (ld_vol32(P.root_ready) < T) {
+            if (*reinterpret_cast<volatile int32_t*>(P.error) != ERR_NONE || (P.abort != nullptr && *P.abort != 0)) { ok = 0; break; }
+            __nanosleep(200);
+        }
+        r_ok = ok;
+    }
+    __syncthreads();
+    if (!r_ok) return;
+    __threadfence();
+    long long rt0 = 0;
+    if (P.timing != nullptr && tid == 0) rt0 = clock64();
+    const uint32_t units = (n + SCAN_UNIT - 1) / SCAN_UNIT;
+    // claims are taken one ahead, so that the first unit of the next claim can be prefetched during the last unit of this one
+    if (tid == 0) r_claim = atomicAdd(P.root_ticket, 1u);
+    __syncthreads();
+    uint32_t u0 = r_claim * ROOT_CHUNK;
+    if (u0 < units) proot_prefetch(P, u0);
+    for (;;) {
+        if (u0 >= units) break;
+        __syncthreads();
+        if (tid == 0) r_claim = atomicAdd(P.root_ticket, 1u);
+        __syncthreads();
+        const uint32_t nu0 = r_claim * ROOT_CHUNK;
+        const uint32_t u1 = min(units, u0 + ROOT_CHUNK);
+        for (uint32_t tb = 0; tb < T; tb += ROOT_TB) {
+            const int nb = (int)min((uint32_t)ROOT_TB, T - tb);
+            __syncthreads();   // the previous batch's normals are no longer read
+            {   // stage the batch's normals: all of a thread's loads are issued before the first store
+                const uint32_t per = ld / 4u, total = (uint32_t)nb * per;   // float4 units
+                for (uint32_t i0 = tid; i0 < total; i0 += 8u * CTRL_THREADS) {
+                    float4 v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const uint32_t i = i0 + (uint32_t)u * CTRL_THREADS;
+                        if (i < total) { const uint32_t j = i / per, e = i - j * per; v[u] = __ldcg(reinterpret_cast<const float4*>(P.cur_normal + (size_t)(tb + j) * P.pool_stride + NORMAL_HDR) + e); }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) { const uint32_t i = i0 + (uint32_t)u * CTRL_THREADS; if (i < total) reinterpret_cast<float4*>(smN)[i] = v[u]; }
+                }
+                if (tid < nb) r_h0[tid] = __ldcg(P.cur_normal + (size_t)(tb + tid) * P.pool_stride);
+            }
+            __syncthreads();
+            switch (nb) {
+                case 8: proot_units<8>(P, u0, u1, tb, nu0, smN, r_h0, r_cnt); break;
+                case 7: proot_units<7>(P, u0, u1, tb, nu0, smN, r_h0, r_cnt); break;
+                case 6: proot_units<6>(P, u0, u1, tb, nu0, smN, r_h0, r_cnt); break;
+                case 5: proot_units<5>(P, u0, u1, tb, nu0, smN, r_h0, r_cnt); break;
+                case 4: proot_units<4>(P, u0, u1, tb, nu0, smN, r_h0, r_cnt); break;
+                case 3: proot_units<3>(P, u0, u1, tb, nu0, smN, r_h0, r_cnt); break;
+                case 2: proot_units<2>(P, u0, u1, tb, nu0, smN, r_h0, r_cnt); break;
+                default: proot_units<1>(P, u0, u1, tb, nu0, smN, r_h0, r_cnt); break;
+            }
+        }
+        // report the claim to every tree
+        __threadfence();
+        __syncthreads();
+        for (uint32_t t = tid; t < T; t += CTRL_THREADS) atomicAdd(&P.slots[t].done, (unsigned long long)(u1 - u0));
+        u0 = nu0;
+    }
+    if (P.timing != nullptr && tid == 0) atomicMax(P.timing + 20, (unsigned long long)(clock64() - rt0));   // the slowest worker's pass
+}
+
 // A worker CTA: claims units of whatever the control CTAs have published and runs the same scan / partition code as work_kernel.
 // Returns when every tree is done (or on error). sm_normal: ld floats of dynamic shared memory.
 __device__ __noinline__ void pworker(const BuildParams& P, float* sm_normal) {
@@ -832,6 +994,7 @@ __device__ __noinline__ void pworker(const BuildParams& P, float* sm_normal) {
     uint32_t loaded_t = 0xffffffffu, loaded_seq = 0xffffffffu;
     float nh0 = 0.f;
     if (tid == 0) w_exit = 0;
+    if (P.root_fused) proot(P, sm_normal);
     for (;;) {
         // ---- poll: one load per slot, 32 slots per pass; pick a slot with unclaimed units ----
         if (warp == 0) {
@@ -1135,9 +1298,21 @@ __global__ void __launch_bounds__(CTRL_THREADS, (CS == 0 ? 2 : 1)) control_kerne
                 const uint32_t units = (f.len + SCAN_UNIT - 1) / SCAN_UNIT;
                 if (tid == 0) {
                     s_pseq += 1;
+                    if (P.root_fused && s_pseq == 1u && f.len == P.n) {
+                        // the tree's first scan is its root's: the workers take it in their fused pass over all trees' roots
+                        // (proot). The slot shows a job whose units are all claimed; each fused claim reports its units here.
+                        volatile PSlot* v = &P.slots[t];
+                        v->len = job.len; v->kind = (uint32_t)JOB_SCAN; v->chunk = 1u;
+                        v->done = (unsigned long long)s_pseq << 32;
+                        v->ticket = pticket(s_pseq, units, units);
+                        __threadfence();
+                        atomicAdd(P.root_ready, 1u);
+                        s_wait_ok = pwait(P, P.slots[t], s_pseq, units) ? 1 : 0;
+                    } else {
                     const uint32_t chunk = units > 1024u ? 4u : 1u, groups = (units + chunk - 1) / chunk;   // a claim = `chunk` units
                     ppublish(P.slots[t], job, s_pseq, groups, chunk);
                     s_wait_ok = pwait(P, P.slots[t], s_pseq, groups) ? 1 : 0;
+                    }
                     if (P.timing) TM.tacc[TP_INNER] += 1;
                 }
                 __syncthreads();
