@@ -152,6 +152,7 @@ struct arroy_ctx {
     // fused re-rank with a bf16 shadow of the items (frerank.cuh); built lazily by the first query after staging
     DevBuf fr_shadow, fr_norm, fr_gmax, fr_status;
     bool fr_valid = false;
+    bool shadow_valid = false;   // fr_shadow holds the bf16 copy of the staged items (also used by the build's scans)
     uint64_t fr_batches = 0, fr_fallbacks = 0;   // last search_batch call, ms: bitmap clear + tree walk, candidate sort, distances, top-k   // last rerank_shared call, ms: prep, score GEMM, select, re-score, top-k, exact dense path
 };
 
@@ -198,7 +199,7 @@ void alloc_items(arroy_ctx* c, int metric, uint32_t dim, uint64_t n, const uint3
     for (uint64_t i = 1; i < n; ++i) if (ids[i] <= ids[i - 1]) throw ArgError("ids must be strictly ascending");
     // a restage invalidates everything derived from the previous items: the bf16 shadow and the device forest
     // (its descendant rows were validated against the previous item count)
-    c->staged = false; c->fr_valid = false; c->forest_loaded = false; c->staging_open = false;
+    c->staged = false; c->fr_valid = false; c->shadow_valid = false; c->forest_loaded = false; c->staging_open = false;
     c->stage_epoch += 1;
     c->metric = metric; c->dim = dim; c->ld = (dim + 31u) & ~31u; c->n = n;
     c->ids.assign(ids, ids + n);
@@ -370,6 +371,7 @@ inline void launch_control(const void* fn, unsigned n_trees, int cs, size_t smem
     CK(cudaLaunchKernelExC(&cfg, fn, args));
 }
 
+void shadow_prepare(arroy_ctx* c);
 void build_wave(arroy_ctx* c, size_t wave_no, uint32_t t0, uint32_t tw, const uint8_t (*seeds)[32], uint32_t K, uint32_t cap_mult,
                 arroy_b200_cancel_fn cancel, void* cancel_arg, std::vector<BuiltTree>& out_trees, uint32_t& out_pool_stride, Subsets sub = Subsets{}) {
     const uint64_t n = c->n;
@@ -526,6 +528,16 @@ void build_wave(arroy_ctx* c, size_t wave_no, uint32_t t0, uint32_t tw, const ui
         P.slots = W.slots.as<PSlot>();
         P.cur_normal = W.cur_normal.as<float>();
         P.abort = W.abort.as<int>();
+        // scans through the bf16 shadow of the items (kernels.cuh scan_claim_shadow): nodes of more than shadow_min_units units
+        {
+            const char* se = getenv("ARROY_B200_SHADOW");
+            const bool want = !(se && atoi(se) == 0) && !is_bq(c->metric) && P.d >= 64 && P.d <= SHADOW_MAX_D && 2ull * ld * 4 <= psmem && n * (uint64_t)ld >= (1ull << 22);
+            if (want) {
+                shadow_prepare(c);
+                P.shadow = c->fr_shadow.as<uint16_t>();
+                P.shadow_min_units = getenv("ARROY_B200_SHADOW_MIN") ? (uint32_t)atoi(getenv("ARROY_B200_SHADOW_MIN")) : 64u;
+            }
+        }
         // fused root scan: every tree of the wave starts at the root of the whole index (no subtree mode), rows go through the
         // 8-lanes-per-row path, and a batch of normals fits next to nothing else in the workers' shared memory
         const char* rf = getenv("ARROY_B200_ROOT_FUSE");
@@ -976,20 +988,28 @@ bool frerank_enabled(arroy_ctx* c, uint32_t k) {
     return !off && c->metric != MANHATTAN && !is_bq(c->metric) && k <= (uint32_t)FR_SURV && frerank_smem(c->ld) <= 200 * 1024;
 }
 
-void frerank_prepare(arroy_ctx* c) {
-    if (c->fr_valid) return;
+// bf16 copy of the staged items (round to nearest even; padding stays zero), shared by the fused re-rank and the build's scans
+void shadow_prepare(arroy_ctx* c) {
+    if (c->shadow_valid) return;
     const uint64_t total4 = (uint64_t)c->n * c->ld / 4;
     c->fr_shadow.ensure(std::max<size_t>(16, (size_t)c->n * c->ld * 2));
-    c->fr_norm.ensure(std::max<size_t>(16, c->n * 4));
-    c->fr_gmax.ensure(4);
     fr_shadow_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->items.as<float4>(), c->fr_shadow.as<uint2>(), total4);
     CK(cudaGetLastError());
+    c->n_launches += 1;
+    c->shadow_valid = true;
+}
+
+void frerank_prepare(arroy_ctx* c) {
+    if (c->fr_valid) return;
+    shadow_prepare(c);
+    c->fr_norm.ensure(std::max<size_t>(16, c->n * 4));
+    c->fr_gmax.ensure(4);
     { uint64_t warps = (c->n + 3) / 4; int g = (int)std::max<uint64_t>(1, std::min<uint64_t>((warps + 7) / 8, (uint64_t)c->sm_count * 16));
       norms_kernel<<<g, 256, 0, c->stream>>>(c->items.as<float>(), c->n, c->dim, c->ld, c->fr_norm.as<float>(), nullptr); CK(cudaGetLastError()); }
     CK(cudaMemsetAsync(c->fr_gmax.p, 0, 4, c->stream));
     fr_gmax_kernel<<<(unsigned)((c->n + 255) / 256), 256, 0, c->stream>>>(c->fr_norm.as<float>(), c->h0.as<float>(), c->n, c->metric, c->fr_gmax.as<uint32_t>());
     CK(cudaGetLastError());
-    c->n_launches += 3;
+    c->n_launches += 2;
     c->fr_valid = true;
 }
 

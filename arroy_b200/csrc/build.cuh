@@ -105,6 +105,9 @@ struct BuildParams {
     const volatile int* abort;    // set by the host (cancel): control CTAs stop at their next wait
     // fused root scan: when every tree of the wave starts at the root of the whole index, the first split's side() scans of all
     // trees read the same rows — the workers do them in ONE pass over the item matrix (proot below)
+    // bf16 copy of the item matrix (n x ld), or NULL: scans of more than shadow_min_units units go through it (scan_claim_shadow)
+    const uint16_t* shadow;
+    uint32_t shadow_min_units;
     int32_t root_fused;
     uint32_t* root_ready;         // number of trees whose root normal is published
     uint32_t* root_ticket;        // next unclaimed chunk of the fused pass
@@ -987,6 +990,9 @@ __device__ __noinline__ void pworker(const BuildParams& P, float* sm_normal) {
     __shared__ uint32_t w_t, w_u0, w_n, w_seq, w_pseq, w_found, w_exit, w_count;
     __shared__ PSlot w_job;        // fields of the claimed job (first 64 bytes)
     __shared__ uint32_t w_sm[16];
+    __shared__ uint32_t w_list[SCAN_UNIT * SHADOW_CHUNK];   // positions the bf16 pass could not decide
+    __shared__ uint32_t w_cnt[SHADOW_CHUNK + 1];
+    float* sm_perm = sm_normal + P.ld;                      // the normal in the bf16 rows' lane order
     const uint32_t T = P.n_trees;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t rot = (blockIdx.x - T) * 7u;
@@ -1072,12 +1078,21 @@ __device__ __noinline__ void pworker(const BuildParams& P, float* sm_normal) {
                 const uint32_t units = (jb.len + SCAN_UNIT - 1) / SCAN_UNIT;
                 if (want_normal || seq != w_pseq) {
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) { const uint32_t i = tid + u * CTRL_THREADS; if (i < P.ld) sm_normal[i] = nreg[u]; }
+                    for (int u = 0; u < 8; ++u) {
+                        const uint32_t i = tid + u * CTRL_THREADS;
+                        if (i < P.ld) {
+                            sm_normal[i] = nreg[u];
+                            if (P.shadow != nullptr) { const uint32_t q = i >> 3, w = i & 7u; sm_perm[(((q >> 3) * 16u + (w >> 2) * 8u + (q & 7u)) << 2) + (w & 3u)] = nreg[u]; }
+                        }
+                    }
                     nh0 = __ldcg(nsrc);
                     loaded_t = t; loaded_seq = seq;
                     __syncthreads();
                 }
-                for (uint32_t u = g0 * chunk; u < min(units, (g0 + 1u) * chunk); ++u) scan_unit<true>(jb, u, P.items, P.ih0, P.d, P.ld, P.metric, sm_normal, nh0, &w_count);
+                if (P.shadow != nullptr && chunk == SHADOW_CHUNK && units > P.shadow_min_units)
+                    scan_claim_shadow(jb, g0 * chunk, min(units, (g0 + 1u) * chunk), P.items, P.shadow, P.ih0, P.d, P.ld, P.metric, sm_normal, sm_perm, nh0, w_list, w_cnt);
+                else
+                    for (uint32_t u = g0 * chunk; u < min(units, (g0 + 1u) * chunk); ++u) scan_unit<true>(jb, u, P.items, P.ih0, P.d, P.ld, P.metric, sm_normal, nh0, &w_count);
             } else if (jb.kind == JOB_PARTITION) {
                 const uint32_t units = (jb.len + PART_UNIT - 1) / PART_UNIT;
                 for (uint32_t u = g0 * chunk; u < min(units, (g0 + 1u) * chunk); ++u)
@@ -1309,7 +1324,8 @@ __global__ void __launch_bounds__(CTRL_THREADS, (CS == 0 ? 2 : 1)) control_kerne
                         atomicAdd(P.root_ready, 1u);
                         s_wait_ok = pwait(P, P.slots[t], s_pseq, units) ? 1 : 0;
                     } else {
-                    const uint32_t chunk = units > 1024u ? 4u : 1u, groups = (units + chunk - 1) / chunk;   // a claim = `chunk` units
+                    // a claim = `chunk` units: four for the big scans (and for everything that goes through the bf16 shadow)
+                    const uint32_t chunk = (units > 1024u || (P.shadow != nullptr && units > P.shadow_min_units)) ? 4u : 1u, groups = (units + chunk - 1) / chunk;
                     ppublish(P.slots[t], job, s_pseq, groups, chunk);
                     s_wait_ok = pwait(P, P.slots[t], s_pseq, groups) ? 1 : 0;
                     }

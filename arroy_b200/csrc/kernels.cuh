@@ -141,6 +141,133 @@ __device__ __forceinline__ void scan_unit(const Job& jb, uint32_t unit, const fl
     if (threadIdx.x == 0 && jb.unit_left) jb.unit_left[unit] = *sm_count;
 }
 
+// ---- side() through a bf16 shadow of the items --------------------------------------------------------------------------
+// side() only needs the SIGN of the margin, and a scan is bound by the bytes of the rows it reads. The claim's rows are first
+// read from a bf16 copy of the item matrix (half the bytes): with x~ = bf16(x) (round to nearest: |x~ - x| <= 2^-9 |x|) an
+// ordinary f32 dot m~ = sum n_i x~_i and A~ = sum |n_i| |x~_i| satisfy, against the margin m_ref the reference computes in its
+// own order (|m_ref - sum n_i x_i| <= gamma A, gamma ~ d 2^-24, A = sum |n_i x_i|),
+//        |m~ + c - (m_ref's exact value)| <= (2^-9 + 2 gamma) A / (1 - 2^-9 - gamma) < 2^-8 A~     for d <= 8192
+// (c = the bias / extra_dim term, formed exactly as the reference forms it; fl(a + b) has the sign of a + b). So when
+// |m~ + c| > 2^-8 A~ the side is certain; every other row — near the hyperplane, zero, non-finite — is put on a list and scored
+// from the f32 row in the reference's summation order (the code of scan_unit). Flags and unit counts are the exact scan's.
+// sm_perm: the normal re-laid for the bf16 row layout: the 8 elements of 16-byte word q = 8 c + g of a row sit at float4
+// 16 c + g and 16 c + 8 + g, so that the eight lanes of a row read consecutive float4s.
+constexpr float SHADOW_REL = 0.00390625f;   // 2^-8
+constexpr uint32_t SHADOW_MAX_D = 8192;
+constexpr uint32_t SHADOW_CHUNK = 4;         // scan units per claim on this path (256 rows)
+
+__device__ __forceinline__ uint4 ldg_stream_u4(const uint4* p) {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void shadow_fma8(const uint4 v, const float4 y0, const float4 y1, float& m0, float& m1, float& a0, float& a1) {
+    const float x0 = __uint_as_float(v.x << 16), x1 = __uint_as_float(v.x & 0xffff0000u), x2 = __uint_as_float(v.y << 16), x3 = __uint_as_float(v.y & 0xffff0000u);
+    const float x4 = __uint_as_float(v.z << 16), x5 = __uint_as_float(v.z & 0xffff0000u), x6 = __uint_as_float(v.w << 16), x7 = __uint_as_float(v.w & 0xffff0000u);
+    m0 = fmaf(x0, y0.x, m0); m1 = fmaf(x1, y0.y, m1); m0 = fmaf(x2, y0.z, m0); m1 = fmaf(x3, y0.w, m1);
+    m0 = fmaf(x4, y1.x, m0); m1 = fmaf(x5, y1.y, m1); m0 = fmaf(x6, y1.z, m0); m1 = fmaf(x7, y1.w, m1);
+    a0 = fmaf(fabsf(x0), fabsf(y0.x), a0); a1 = fmaf(fabsf(x1), fabsf(y0.y), a1); a0 = fmaf(fabsf(x2), fabsf(y0.z), a0); a1 = fmaf(fabsf(x3), fabsf(y0.w), a1);
+    a0 = fmaf(fabsf(x4), fabsf(y1.x), a0); a1 = fmaf(fabsf(x5), fabsf(y1.y), a1); a0 = fmaf(fabsf(x6), fabsf(y1.z), a0); a1 = fmaf(fabsf(x7), fabsf(y1.w), a1);
+}
+
+// scan units [u0, u1) (at most SHADOW_CHUNK) of a job. sm_list: 64 * SHADOW_CHUNK positions; sm_cnt: SHADOW_CHUNK + 1 counters.
+__device__ __forceinline__ void scan_claim_shadow(const Job& jb, uint32_t u0, uint32_t u1, const float* __restrict__ items, const uint16_t* __restrict__ shadow,
+                                                  const float* __restrict__ ih0, uint32_t d, uint32_t ld, int metric, const float* sm_normal, const float* sm_perm,
+                                                  float nh0, uint32_t* sm_list, uint32_t* sm_cnt) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g8 = lane & 7, grp = lane >> 3;
+    if (tid <= (int)SHADOW_CHUNK) sm_cnt[tid] = 0;
+    __syncthreads();
+    const uint32_t base = u0 * SCAN_UNIT, end = min(jb.len, u1 * SCAN_UNIT);
+    const uint32_t nq = ld >> 3;                       // 16-byte words per shadow row
+    const int nsteps = (int)((nq + 7) >> 3);
+    const float4* PN = reinterpret_cast<const float4*>(sm_perm);
+    for (uint32_t pbase = base; pbase < end; pbase += 128) {
+        uint32_t pos[4], rid[4];
+        const uint4* S[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            pos[r] = pbase + warp * 16 + grp * 4 + r;
+            rid[r] = pos[r] < end ? (jb.rows ? __ldcg(jb.rows + pos[r]) : pos[r]) : 0u;
+            S[r] = reinterpret_cast<const uint4*>(shadow + (size_t)rid[r] * ld) + g8;
+        }
+        float m0[4], m1[4], a0[4], a1[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) { m0[r] = 0.f; m1[r] = 0.f; a0[r] = 0.f; a1[r] = 0.f; }
+        for (int c0 = 0; c0 < nsteps; c0 += 3) {
+            uint4 v[3][4];
+#pragma unroll
+            for (int sidx = 0; sidx < 3; ++sidx)
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const uint32_t q = (uint32_t)(c0 + sidx) * 8u + (uint32_t)g8;
+                    v[sidx][r] = q < nq ? ldg_stream_u4(S[r] + (c0 + sidx) * 8) : make_uint4(0u, 0u, 0u, 0u);
+                }
+#pragma unroll
+            for (int sidx = 0; sidx < 3; ++sidx) {
+                const uint32_t q = (uint32_t)(c0 + sidx) * 8u + (uint32_t)g8;
+                float4 y0 = make_float4(0.f, 0.f, 0.f, 0.f), y1 = y0;
+                if (q < nq) { y0 = PN[(c0 + sidx) * 16 + g8]; y1 = PN[(c0 + sidx) * 16 + 8 + g8]; }
+#pragma unroll
+                for (int r = 0; r < 4; ++r) shadow_fma8(v[sidx][r], y0, y1, m0[r], m1[r], a0[r], a1[r]);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            float m = m0[r] + m1[r], a = a0[r] + a1[r];
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) { m += __shfl_xor_sync(0xffffffffu, m, o); a += __shfl_xor_sync(0xffffffffu, a, o); }
+            const bool valid = pos[r] < end;
+            float mt;
+            if (metric == COSINE) mt = m;
+            else if (metric == DOT_PRODUCT) mt = m + __fmul_rn(nh0, valid ? ih0[rid[r]] : 0.f);
+            else mt = nh0 + m;
+            const bool certain = fabsf(mt) > SHADOW_REL * a;          // false for NaN / Inf / an all-zero row
+            const bool leader = g8 == 0 && valid;
+            const int side = mt > 0.f ? 1 : 0;
+            if (leader && certain) jb.flags[pos[r]] = (uint8_t)side;
+            if (leader && !certain) sm_list[atomicAdd(&sm_cnt[SHADOW_CHUNK], 1u)] = pos[r];
+            const unsigned lefts = __ballot_sync(0xffffffffu, leader && certain && side == 0);
+            // the four groups of a warp hold positions of the same unit (16 consecutive positions per warp)
+            if (lane == 0 && lefts) atomicAdd(&sm_cnt[(pbase + warp * 16 - base) / SCAN_UNIT], (uint32_t)__popc(lefts));
+        }
+    }
+    __syncthreads();
+    // the uncertain rows, exactly: one 8-lane group per row, scan_unit's arithmetic
+    const uint32_t nl = sm_cnt[SHADOW_CHUNK];
+    const int nch = (int)(d >> 5);
+    const float4* N = reinterpret_cast<const float4*>(sm_normal);
+    for (uint32_t it = 0; it * 32u < nl; ++it) {
+        const uint32_t idx = it * 32u + (uint32_t)(warp * 4 + grp);
+        const bool act = idx < nl;
+        const uint32_t p = act ? sm_list[idx] : base;
+        const uint32_t r = jb.rows ? __ldcg(jb.rows + p) : p;
+        const float4* A = reinterpret_cast<const float4*>(items + (size_t)r * ld);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        int c = 0;
+        for (; c + 8 <= nch; c += 8) {
+            float4 x[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) x[u] = ldg_stream(A + (c + u) * 8 + g8);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const float4 y = N[(c + u) * 8 + g8];
+                acc.x = fmaf(x[u].x, y.x, acc.x); acc.y = fmaf(x[u].y, y.y, acc.y); acc.z = fmaf(x[u].z, y.z, acc.z); acc.w = fmaf(x[u].w, y.w, acc.w);
+            }
+        }
+        for (; c < nch; ++c) {
+            const float4 x = ldg_stream(A + c * 8 + g8), y = N[c * 8 + g8];
+            acc.x = fmaf(x.x, y.x, acc.x); acc.y = fmaf(x.y, y.y, acc.y); acc.z = fmaf(x.z, y.z, acc.z); acc.w = fmaf(x.w, y.w, acc.w);
+        }
+        float da = group8_hsum(acc);
+        const float* row = items + (size_t)r * ld;
+        for (uint32_t i = (uint32_t)nch * 32u; i < d; ++i) da = __fadd_rn(da, __fmul_rn(row[i], sm_normal[i]));
+        const int sa = side_of(margin_finish(metric, da, nh0, (metric == DOT_PRODUCT) ? ih0[r] : 0.f));
+        if (act && g8 == 0) { jb.flags[p] = (uint8_t)sa; if (sa == 0) atomicAdd(&sm_cnt[(p - base) / SCAN_UNIT], 1u); }
+    }
+    __syncthreads();
+    if (tid < (int)(u1 - u0)) jb.unit_left[u0 + tid] = sm_cnt[tid];
+}
+
 // Stable partition of one PART_UNIT block of ids. left_before = number of Left flags in all
 // earlier positions of the node. sm_w: 2*8 uint32 scratch.
 __device__ __forceinline__ void partition_block(const uint32_t* __restrict__ src, const uint8_t* __restrict__ flags, uint32_t* __restrict__ dst,
