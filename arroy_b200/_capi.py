@@ -69,6 +69,7 @@ SIGNATURES = [
     ("arroy_b200_device_ptrs", C.c_int32, [C.c_void_p, C.POINTER(C.c_void_p), _u32p]),
     ("arroy_b200_epochs", C.c_int32, [C.c_void_p, _u64p]),
     ("arroy_b200_bq_quantize", C.c_uint32, [_f32p, C.c_uint32, _f32p]),
+    ("arroy_b200_build_shadow_stats", C.c_int32, [C.c_void_p, _u64p]),
     ("arroy_b200_selftest_udiv", C.c_int32, [C.c_void_p, C.c_uint64, C.c_uint64, _u64p, _u64p]),
     ("arroy_b200_stage_begin", C.c_int32, [C.c_void_p, C.c_int32, C.c_uint32, C.c_uint64, _u32p]),
     ("arroy_b200_stage_rows", C.c_int32, [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(C.c_void_p)]),
@@ -312,6 +313,11 @@ class Context:
 
     def stage_end(self, headers_on_device=False):
         self._ck(self.lib.arroy_b200_stage_end(self.h, 1 if headers_on_device else 0))
+
+    def build_shadow_stats(self):
+        out = (C.c_uint64 * 4)()
+        self._ck(self.lib.arroy_b200_build_shadow_stats(self.h, out))
+        return {"rows_via_bf16_shadow": int(out[0]), "rows_rescored_f32": int(out[1]), "rows_in_fused_root_pass": int(out[2]), "fused_root_rows_read": int(out[3])}
 
     def build_stats(self):
         st = (C.c_double * 8)()

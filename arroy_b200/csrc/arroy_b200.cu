@@ -71,9 +71,9 @@ struct PinBuf {
 };
 
 struct Wave {  // device buffers of one wave of trees; kept across builds
-    DevBuf st, frames, recs, perm0, perm1, flags, unit_left, pool, pool_counter, jobs, scratch, active, error, final_ids, keys, sub_rows, sub_off, timing, slots, abort, cur_normal, start_pos, root;
+    DevBuf st, frames, recs, perm0, perm1, flags, unit_left, pool, pool_counter, jobs, scratch, active, error, final_ids, keys, sub_rows, sub_off, timing, slots, abort, cur_normal, start_pos, root, shadow_stats;
     void release() {
-        sub_rows.release(); sub_off.release(); timing.release(); slots.release(); abort.release(); cur_normal.release(); start_pos.release(); root.release();
+        sub_rows.release(); sub_off.release(); timing.release(); slots.release(); abort.release(); cur_normal.release(); start_pos.release(); root.release(); shadow_stats.release();
         st.release(); frames.release(); recs.release(); perm0.release(); perm1.release(); flags.release(); unit_left.release();
         pool.release(); pool_counter.release(); jobs.release(); scratch.release(); active.release(); error.release(); final_ids.release(); keys.release();
     }
@@ -117,6 +117,7 @@ struct arroy_ctx {
     cudaStream_t side_stream = nullptr;   // host -> device flags while the persistent build kernel occupies `stream`
     cudaEvent_t ev_done = nullptr, ev_p0 = nullptr, ev_p1 = nullptr;   // ev_p0 / ev_p1 bracket the persistent build kernel
     double stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    uint64_t shadow_rows = 0, shadow_rescored = 0, fused_root_rows = 0, fused_root_read = 0;   // last build: rows scanned through the bf16 shadow / re-scored from f32
     uint64_t n_launches = 0, h2d_bytes = 0, d2h_bytes = 0;  // since create (arroy_b200_counters)
     cudaEvent_t tev0 = nullptr, tev1 = nullptr;
     std::vector<StageWorker> stage_workers;
@@ -461,6 +462,7 @@ void build_wave(arroy_ctx* c, size_t wave_no, uint32_t t0, uint32_t tw, const ui
     if (ctrl_smem > 48 * 1024) CK(cudaFuncSetAttribute(control_fn(true, 1, c->metric), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctrl_smem));
     const size_t wsmem = work_smem(ld, (int)tw);
     if (wsmem > 48 * 1024) CK(cudaFuncSetAttribute(work_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
+    if (wsmem + 4ull * ld > 48 * 1024) CK(cudaFuncSetAttribute(work_kernel_shadow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(wsmem + 4ull * ld)));
     const int work_grid = c->sm_count * 3;
 
     // Two schedules over the same kernels:
@@ -519,6 +521,22 @@ void build_wave(arroy_ctx* c, size_t wave_no, uint32_t t0, uint32_t tw, const ui
             if (persist) if (const char* ge = getenv("ARROY_B200_PGRID")) pgrid = std::max((int)tw + 16, std::min(pgrid, atoi(ge)));   // experiments: fewer resident CTAs
         }
     }
+    // scans through the bf16 shadow of the items (kernels.cuh scan_claim_shadow): nodes of more than shadow_min_units units
+    {
+        const char* se = getenv("ARROY_B200_SHADOW");
+        const bool want = !(se && atoi(se) == 0) && !is_bq(c->metric) && P.d >= 64 && P.d <= SHADOW_MAX_D && n * (uint64_t)ld >= (1ull << 22);
+        if (want) {
+            shadow_prepare(c);
+            P.shadow = c->fr_shadow.as<uint16_t>();
+            W.shadow_stats.ensure(16);
+            CK(cudaMemsetAsync(W.shadow_stats.p, 0, 16, c->stream));
+            P.shadow_stats = W.shadow_stats.as<unsigned long long>();
+            // many trees per GPU: bandwidth decides, every node goes through the shadow; few: the chain of attempts decides and
+            // small nodes keep the one-unit claims of the exact scan (more CTAs per node)
+            P.shadow_min_units = getenv("ARROY_B200_SHADOW_MIN") ? (uint32_t)atoi(getenv("ARROY_B200_SHADOW_MIN")) : ((!persist || tw >= 32) ? 16u : (tw >= 12 ? 64u : 128u));
+            P.shadow_small_chunk = getenv("ARROY_B200_SHADOW_CHUNK") ? (uint32_t)std::min(4, std::max(1, atoi(getenv("ARROY_B200_SHADOW_CHUNK")))) : 4u;
+        }
+    }
     if (persist) {
         W.slots.ensure(sizeof(PSlot) * tw);
         W.abort.ensure(4);
@@ -528,16 +546,6 @@ void build_wave(arroy_ctx* c, size_t wave_no, uint32_t t0, uint32_t tw, const ui
         P.slots = W.slots.as<PSlot>();
         P.cur_normal = W.cur_normal.as<float>();
         P.abort = W.abort.as<int>();
-        // scans through the bf16 shadow of the items (kernels.cuh scan_claim_shadow): nodes of more than shadow_min_units units
-        {
-            const char* se = getenv("ARROY_B200_SHADOW");
-            const bool want = !(se && atoi(se) == 0) && !is_bq(c->metric) && P.d >= 64 && P.d <= SHADOW_MAX_D && 2ull * ld * 4 <= psmem && n * (uint64_t)ld >= (1ull << 22);
-            if (want) {
-                shadow_prepare(c);
-                P.shadow = c->fr_shadow.as<uint16_t>();
-                P.shadow_min_units = getenv("ARROY_B200_SHADOW_MIN") ? (uint32_t)atoi(getenv("ARROY_B200_SHADOW_MIN")) : 64u;
-            }
-        }
         // fused root scan: every tree of the wave starts at the root of the whole index (no subtree mode), rows go through the
         // 8-lanes-per-row path, and a batch of normals fits next to nothing else in the workers' shared memory
         const char* rf = getenv("ARROY_B200_ROOT_FUSE");
@@ -549,11 +557,13 @@ void build_wave(arroy_ctx* c, size_t wave_no, uint32_t t0, uint32_t tw, const ui
 
     auto launch_step = [&](cudaStream_t s) {  // lockstep: all trees per launch
         launch_control(ctrl1, tw, 1, ctrl_smem, s, P, 0u);
-        work_kernel<<<work_grid, WORK_THREADS, wsmem, s>>>(P.jobs, (int)tw, P.items, P.ih0, P.d, P.ld, P.metric, interleave);
+        if (P.shadow) work_kernel_shadow<<<c->sm_count * 2, WORK_THREADS, wsmem + 4ull * ld, s>>>(P.jobs, (int)tw, P.items, P.shadow, P.ih0, P.d, P.ld, P.metric, P.shadow_min_units, P.shadow_stats);
+        else work_kernel<<<work_grid, WORK_THREADS, wsmem, s>>>(P.jobs, (int)tw, P.items, P.ih0, P.d, P.ld, P.metric, interleave);
     };
     auto launch_tree_step = [&](uint32_t t, cudaStream_t s) {  // async: one tree per launch
         launch_control(ctrlc, 1, cluster, ctrl_smem, s, P, t);
-        work_kernel<<<tree_grid, WORK_THREADS, wsmem1, s>>>(P.jobs + t, 1, P.items, P.ih0, P.d, P.ld, P.metric, 0);
+        if (P.shadow) work_kernel_shadow<<<tree_grid, WORK_THREADS, wsmem1 + 4ull * ld, s>>>(P.jobs + t, 1, P.items, P.shadow, P.ih0, P.d, P.ld, P.metric, P.shadow_min_units, P.shadow_stats);
+        else work_kernel<<<tree_grid, WORK_THREADS, wsmem1, s>>>(P.jobs + t, 1, P.items, P.ih0, P.d, P.ld, P.metric, 0);
     };
     if (!lockstep) {
         while (c->tree_streams.size() < tw) { cudaStream_t st; CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking)); c->tree_streams.push_back(st); }
@@ -657,7 +667,8 @@ void build_wave(arroy_ctx* c, size_t wave_no, uint32_t t0, uint32_t tw, const ui
             for (int i = 0; i < steps_per_batch; ++i) {
                 launch_control(ctrl1, tw, 1, ctrl_smem, c->stream, P, 0u);
                 CK(cudaEventRecord(pev[2 * i], c->stream));
-                work_kernel<<<work_grid, WORK_THREADS, wsmem, c->stream>>>(P.jobs, (int)tw, P.items, P.ih0, P.d, P.ld, P.metric, interleave);
+                if (P.shadow) work_kernel_shadow<<<c->sm_count * 2, WORK_THREADS, wsmem + 4ull * ld, c->stream>>>(P.jobs, (int)tw, P.items, P.shadow, P.ih0, P.d, P.ld, P.metric, P.shadow_min_units, P.shadow_stats);
+                else work_kernel<<<work_grid, WORK_THREADS, wsmem, c->stream>>>(P.jobs, (int)tw, P.items, P.ih0, P.d, P.ld, P.metric, interleave);
                 CK(cudaEventRecord(pev[2 * i + 1], c->stream));
             }
             CK(cudaStreamSynchronize(c->stream));
@@ -738,6 +749,13 @@ void build_wave(arroy_ctx* c, size_t wave_no, uint32_t t0, uint32_t tw, const ui
         c->stats[7] += (double)st[t].n_misspec;
         if (sub.end_pos) sub.end_pos[t0 + t] = st[t].pos;
     }
+    if (persist && P.root_fused) { c->fused_root_rows += (uint64_t)tw * n; c->fused_root_read += n; }
+    if (P.shadow_stats) {
+        unsigned long long hs[2] = {0, 0};
+        CK(cudaMemcpyAsync(hs, P.shadow_stats, 16, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        c->shadow_rows += hs[0]; c->shadow_rescored += hs[1];
+    }
     CK(cudaStreamSynchronize(c->stream));
     c->d2h_bytes += (uint64_t)pool_used * pool_stride * 4 + sizeof(TreeState) * tw + sizeof(Record) * total_recs + 4ull * n * tw;
     c->breakdown[3] += ms_since(t_d2h);
@@ -749,6 +767,7 @@ void do_build_begin(arroy_ctx* c, uint32_t n_trees, const uint8_t (*seeds)[32], 
     require_staged(c);
     set_device(c);
     for (auto& s : c->stats) s = 0;
+    c->shadow_rows = 0; c->shadow_rescored = 0; c->fused_root_rows = 0; c->fused_root_read = 0;
     c->pending_waves.clear(); c->pending_wave_t0.clear(); c->pending_n_trees = 0;
     const uint32_t K = split_after ? split_after : c->dim;
     if (!sub.rows && c->n <= K) throw ArgError("build_trees needs more items than split_after (a single Descendants node is the caller's job, src/writer.rs:499-501)");
@@ -1538,6 +1557,9 @@ int32_t arroy_b200_build_trees_emit_mapped(arroy_ctx* c, const uint32_t* root_id
 
 int32_t arroy_b200_build_stats(arroy_ctx* c, double stats[8]) {
     return guarded(c, [&] { for (int i = 0; i < 8; ++i) stats[i] = c->stats[i]; });
+}
+int32_t arroy_b200_build_shadow_stats(arroy_ctx* c, uint64_t out[4]) {
+    return guarded(c, [&] { if (!out) throw ArgError("null argument"); out[0] = c->shadow_rows; out[1] = c->shadow_rescored; out[2] = c->fused_root_rows; out[3] = c->fused_root_read; });
 }
 
 int32_t arroy_b200_rerank(arroy_ctx* c, const float* query, float qhdr0, float qhdr1, const uint32_t* rows, uint64_t n_rows, uint32_t k,

@@ -146,13 +146,13 @@ __device__ __forceinline__ void scan_unit(const Job& jb, uint32_t unit, const fl
 // read from a bf16 copy of the item matrix (half the bytes): with x~ = bf16(x) (round to nearest: |x~ - x| <= 2^-9 |x|) an
 // ordinary f32 dot m~ = sum n_i x~_i and A~ = sum |n_i| |x~_i| satisfy, against the margin m_ref the reference computes in its
 // own order (|m_ref - sum n_i x_i| <= gamma A, gamma ~ d 2^-24, A = sum |n_i x_i|),
-//        |m~ + c - (m_ref's exact value)| <= (2^-9 + 2 gamma) A / (1 - 2^-9 - gamma) < 2^-8 A~     for d <= 8192
-// (c = the bias / extra_dim term, formed exactly as the reference forms it; fl(a + b) has the sign of a + b). So when
-// |m~ + c| > 2^-8 A~ the side is certain; every other row — near the hyperplane, zero, non-finite — is put on a list and scored
+//        |m~ + c - (m_ref's exact value)| <= (2^-9 + 2 gamma) A~ / (1 - 2^-9 - gamma) < (2^-9 (1 + 2^-8) + 2.5 d 2^-24) A~ =: rel(d) A~
+// (c = the bias / extra_dim term, formed exactly as the reference forms it; fl(a + b) has the sign of a + b; rel(768) = 0.00208,
+// rel(8192) = 0.0033). So when |m~ + c| > rel(d) A~ the side is certain; every other row — near the hyperplane, zero, non-finite — is put on a list and scored
 // from the f32 row in the reference's summation order (the code of scan_unit). Flags and unit counts are the exact scan's.
 // sm_perm: the normal re-laid for the bf16 row layout: the 8 elements of 16-byte word q = 8 c + g of a row sit at float4
 // 16 c + g and 16 c + 8 + g, so that the eight lanes of a row read consecutive float4s.
-constexpr float SHADOW_REL = 0.00390625f;   // 2^-8
+__host__ __device__ __forceinline__ float shadow_rel(uint32_t d) { return 0.001962f + (float)d * 1.6e-7f; }   // both constants rounded up
 constexpr uint32_t SHADOW_MAX_D = 8192;
 constexpr uint32_t SHADOW_CHUNK = 4;         // scan units per claim on this path (256 rows)
 
@@ -173,7 +173,7 @@ __device__ __forceinline__ void shadow_fma8(const uint4 v, const float4 y0, cons
 // scan units [u0, u1) (at most SHADOW_CHUNK) of a job. sm_list: 64 * SHADOW_CHUNK positions; sm_cnt: SHADOW_CHUNK + 1 counters.
 __device__ __forceinline__ void scan_claim_shadow(const Job& jb, uint32_t u0, uint32_t u1, const float* __restrict__ items, const uint16_t* __restrict__ shadow,
                                                   const float* __restrict__ ih0, uint32_t d, uint32_t ld, int metric, const float* sm_normal, const float* sm_perm,
-                                                  float nh0, uint32_t* sm_list, uint32_t* sm_cnt) {
+                                                  float nh0, uint32_t* sm_list, uint32_t* sm_cnt, unsigned long long* stats) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g8 = lane & 7, grp = lane >> 3;
     if (tid <= (int)SHADOW_CHUNK) sm_cnt[tid] = 0;
     __syncthreads();
@@ -181,6 +181,7 @@ __device__ __forceinline__ void scan_claim_shadow(const Job& jb, uint32_t u0, ui
     const uint32_t nq = ld >> 3;                       // 16-byte words per shadow row
     const int nsteps = (int)((nq + 7) >> 3);
     const float4* PN = reinterpret_cast<const float4*>(sm_perm);
+    const float rel = shadow_rel(d);
     for (uint32_t pbase = base; pbase < end; pbase += 128) {
         uint32_t pos[4], rid[4];
         const uint4* S[4];
@@ -221,7 +222,7 @@ __device__ __forceinline__ void scan_claim_shadow(const Job& jb, uint32_t u0, ui
             if (metric == COSINE) mt = m;
             else if (metric == DOT_PRODUCT) mt = m + __fmul_rn(nh0, valid ? ih0[rid[r]] : 0.f);
             else mt = nh0 + m;
-            const bool certain = fabsf(mt) > SHADOW_REL * a;          // false for NaN / Inf / an all-zero row
+            const bool certain = fabsf(mt) > rel * a;                 // false for NaN / Inf / an all-zero row
             const bool leader = g8 == 0 && valid;
             const int side = mt > 0.f ? 1 : 0;
             if (leader && certain) jb.flags[pos[r]] = (uint8_t)side;
@@ -234,6 +235,7 @@ __device__ __forceinline__ void scan_claim_shadow(const Job& jb, uint32_t u0, ui
     __syncthreads();
     // the uncertain rows, exactly: one 8-lane group per row, scan_unit's arithmetic
     const uint32_t nl = sm_cnt[SHADOW_CHUNK];
+    if (stats != nullptr && tid == 0) { atomicAdd(stats, (unsigned long long)(end - base)); if (nl) atomicAdd(stats + 1, (unsigned long long)nl); }   // rows through the shadow / re-scored
     const int nch = (int)(d >> 5);
     const float4* N = reinterpret_cast<const float4*>(sm_normal);
     for (uint32_t it = 0; it * 32u < nl; ++it) {
@@ -368,6 +370,71 @@ work_kernel(const Job* __restrict__ jobs, int njobs, const float* __restrict__ i
             scan_unit(jb, unit, items, ih0, d, ld, metric, sm_normal, nh0, &sm_count);
         } else {
             partition_block(jb.rows, jb.flags, jb.dst, unit * PART_UNIT, jb.len, jb.unit_left[unit * (PART_UNIT / SCAN_UNIT)], jb.total_left, sm_w);
+        }
+    }
+}
+
+// work_kernel for contexts that hold the bf16 shadow of the items: scan jobs of more than min_units units are cut into items of
+// SHADOW_CHUNK units and go through scan_claim_shadow; everything else is work_kernel's. Shared memory: two normals (plain and in
+// the shadow rows' lane order) + the prefix table.
+__global__ void __launch_bounds__(WORK_THREADS, 2)
+work_kernel_shadow(const Job* __restrict__ jobs, int njobs, const float* __restrict__ items, const uint16_t* __restrict__ shadow, const float* __restrict__ ih0,
+                   uint32_t d, uint32_t ld, int metric, uint32_t min_units, unsigned long long* stats) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* sm_normal = reinterpret_cast<float*>(smem_raw);
+    float* sm_perm = sm_normal + ld;
+    uint32_t* sm_prefix = reinterpret_cast<uint32_t*>(sm_perm + ld);
+    __shared__ uint32_t sm_count;
+    __shared__ uint32_t sm_w[16];
+    __shared__ uint32_t sm_list[SCAN_UNIT * SHADOW_CHUNK];
+    __shared__ uint32_t sm_cnt[SHADOW_CHUNK + 1];
+    auto via_shadow = [&](const Job& jb) { return jb.kind == JOB_SCAN && jb.margins == nullptr && (jb.len + SCAN_UNIT - 1) / SCAN_UNIT > min_units; };
+    for (int j = threadIdx.x; j < njobs; j += blockDim.x) {
+        const Job jb = jobs[j];
+        const uint32_t units = (jb.len + SCAN_UNIT - 1) / SCAN_UNIT;
+        sm_prefix[j] = jb.kind == JOB_SCAN ? (via_shadow(jb) ? (units + SHADOW_CHUNK - 1) / SHADOW_CHUNK : units) : (jb.kind == JOB_PARTITION ? (jb.len + PART_UNIT - 1) / PART_UNIT : 0u);
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const int per = (njobs + 31) / 32;
+        const int b = threadIdx.x * per, e = min(b + per, njobs);
+        uint32_t loc = 0;
+        for (int i = b; i < e; ++i) loc += sm_prefix[i];
+        uint32_t inc = loc;
+        for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, inc, o); if ((int)threadIdx.x >= o) inc += y; }
+        uint32_t run = inc - loc;
+        for (int i = b; i < e; ++i) { uint32_t x = sm_prefix[i]; sm_prefix[i] = run; run += x; }
+        if (threadIdx.x == 31) sm_prefix[njobs] = inc;
+    }
+    __syncthreads();
+    const uint32_t total = sm_prefix[njobs];
+    int loaded_job = -1;
+    float nh0 = 0.f;
+    for (uint32_t u = blockIdx.x; u < total; u += gridDim.x) {
+        int lo = 0, hi = njobs;  // last j with prefix[j] <= u
+        while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (sm_prefix[mid] <= u) lo = mid; else hi = mid; }
+        const int j = lo;
+        const Job jb = jobs[j];
+        const uint32_t item = u - sm_prefix[j];
+        if (jb.kind == JOB_SCAN) {
+            if (loaded_job != j) {
+                __syncthreads();
+                for (uint32_t i = threadIdx.x; i < ld; i += blockDim.x) {
+                    const float v = jb.normal[NORMAL_HDR + i];
+                    sm_normal[i] = v;
+                    const uint32_t q = i >> 3, w = i & 7u;
+                    sm_perm[(((q >> 3) * 16u + (w >> 2) * 8u + (q & 7u)) << 2) + (w & 3u)] = v;
+                }
+                nh0 = jb.normal[0];
+                loaded_job = j;
+                __syncthreads();
+            }
+            if (via_shadow(jb)) {
+                const uint32_t units = (jb.len + SCAN_UNIT - 1) / SCAN_UNIT;
+                scan_claim_shadow(jb, item * SHADOW_CHUNK, min(units, (item + 1u) * SHADOW_CHUNK), items, shadow, ih0, d, ld, metric, sm_normal, sm_perm, nh0, sm_list, sm_cnt, stats);
+            } else scan_unit<true>(jb, item, items, ih0, d, ld, metric, sm_normal, nh0, &sm_count);
+        } else {
+            partition_block(jb.rows, jb.flags, jb.dst, item * PART_UNIT, jb.len, jb.unit_left[item * (PART_UNIT / SCAN_UNIT)], jb.total_left, sm_w);
         }
     }
 }

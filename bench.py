@@ -393,6 +393,15 @@ def synth_items(rig, wl, dataset="uniform", only_rank0=True):
     return items
 
 
+def scan_bytes(scanned_rows, sh, d):
+    """Bytes the side() scans of a build have to read BY THEIR OWN ALGORITHM ("side() through a bf16 shadow"): 2 bytes per
+    element for rows that go through the bf16 pre-filter, plus the f32 row of those its error bound could not decide; 4 bytes per
+    element for rows on the plain f32 path; the fused root pass reads each item row once for all trees of the wave."""
+    via, resc = sh["rows_via_bf16_shadow"], sh["rows_rescored_f32"]
+    f32_rows = scanned_rows - via - sh["rows_in_fused_root_pass"]
+    return via * 2 * d + (resc + f32_rows + sh["fused_root_rows_read"]) * 4 * d
+
+
 def timed_builds(rig, wl, items, seeds, steps, warmup):
     """`steps` timed forest builds with the items resident in HBM (device time, max over ranks)."""
     from arroy_b200 import parallel
@@ -425,9 +434,16 @@ def timed_builds(rig, wl, items, seeds, steps, warmup):
     ctx.timer_start()
     t0 = time.perf_counter()
     scanned = 0
+    alg_bytes = 0
+    shadow_acc = {}
     for _ in range(steps):
         one_step()
-        scanned += ctx.build_stats()["scanned_rows"]
+        sr = ctx.build_stats()["scanned_rows"]
+        sh = ctx.build_shadow_stats()
+        scanned += sr
+        alg_bytes += scan_bytes(sr, sh, d)
+        for k, v in sh.items():
+            shadow_acc[k] = shadow_acc.get(k, 0) + v
     dev_ms = ctx.timer_stop()   # CUDA events on the library's stream (the launching stream)
     rig.barrier()
     wall = time.perf_counter() - t0
@@ -435,8 +451,10 @@ def timed_builds(rig, wl, items, seeds, steps, warmup):
     c1 = ctx.counters()
     ms_per_step = rig.max_over_ranks(max(dev_ms, 0.0)) / steps
     sc = rig.sum_over_ranks(scanned) / steps
+    ab_step = rig.sum_over_ranks(alg_bytes) / steps
     st, bd = ctx.build_stats(), ctx.build_breakdown()
-    return {"ms_per_step": ms_per_step, "value": n / (ms_per_step * 1e-3), "wall_ms_per_step": wall * 1e3 / steps, "clocks": clocks,
+    return {"alg_bytes_per_step": ab_step, "shadow_rows_per_step": {k: v / steps for k, v in shadow_acc.items()}, "last_step_alg_bytes": scan_bytes(st["scanned_rows"], ctx.build_shadow_stats(), d),
+            "ms_per_step": ms_per_step, "value": n / (ms_per_step * 1e-3), "wall_ms_per_step": wall * 1e3 / steps, "clocks": clocks,
             "launches": int(c1["launches"] - c0["launches"]), "scanned_rows_per_step": sc, "stats": st, "breakdown": bd, "my_trees": my_trees}
 
 
@@ -444,8 +462,11 @@ def build_record(wl, tb, world):
     d = wl["d"]
     sc = tb["scanned_rows_per_step"]
     return {"scanned_rows_per_step": sc, "device_steps": tb["stats"]["steps"], "create_split_calls": tb["stats"]["create_split_calls"],
-            "random_splits": tb["stats"]["random_splits"], "algorithmic_GB_per_step": sc * d * 4 / 1e9,
-            "whole_build_GBps": sc * d * 4 / 1e9 / (tb["ms_per_step"] * 1e-3),
+            "random_splits": tb["stats"]["random_splits"], "algorithmic_GB_per_step": tb["alg_bytes_per_step"] / 1e9,
+            "whole_build_GBps": tb["alg_bytes_per_step"] / 1e9 / (tb["ms_per_step"] * 1e-3),
+            "f32_rows_equivalent": {"GB_per_step": sc * d * 4 / 1e9, "GBps": sc * d * 4 / 1e9 / (tb["ms_per_step"] * 1e-3),
+                                    "note": "scanned rows x d x 4: what the same scans read without the bf16 pre-filter and the fused root pass (round-1 accounting)"},
+            "scan_rows_per_step": tb["shadow_rows_per_step"],
             "schedule": "lockstep" if os.environ.get("ARROY_B200_LOCKSTEP") else ("persistent: one cooperative launch per wave (control CTA per tree + worker CTAs)" if tb["stats"]["steps"] == 1 else "async per-tree graph branches (control / work kernel per attempt)"),
             "misspeculated_two_means": tb["stats"].get("misspeculated_splits", 0.0), "breakdown_ms_last_step": tb["breakdown"]}
 
@@ -659,17 +680,17 @@ def headline_10m(rig, args):
     if rig.rank == 0:
         import numpy as np
         hbm, which = peaks()
-        alg = tb["scanned_rows_per_step"] * d * 4 / rig.world   # this rank's share (trees are spread evenly)
+        alg = tb["alg_bytes_per_step"] / rig.world   # this rank's share (trees are spread evenly)
         loop_ms = tb["breakdown"]["loop_ms"]
         r = np.random.default_rng(0)
         normal = (r.standard_normal(d) / np.sqrt(d)).astype(np.float32)
         root_ms, _ = ctx.time_scan(normal, (0.0, 0.0), n, iters=3, flush_l2=False)
-        rec["roofline"] = {"bound": "hbm", "kernel": "work_kernel (side()/margin scan + id partition)", "achieved": alg / (loop_ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+        rec["roofline"] = {"bound": "hbm", "kernel": "work_kernel_shadow (side() through the bf16 shadow + exact re-score of undecided rows + id partition)", "achieved": alg / (loop_ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
                            "frac": alg / (loop_ms * 1e-3) / 1e9 / hbm, "peak_source": which, "traffic": None,
                            "timing": "in the timed schedule: algorithmic scan bytes of one step / the device loop time of that step (all work_kernel launches run concurrently on 100 "
                                      "streams next to the control kernels, so this is a LOWER bound of the kernel's own rate)",
                            "root_scan": {"rows": n, "ms": root_ms, "GBps": n * d * 4 / (root_ms * 1e-3) / 1e9, "frac": n * d * 4 / (root_ms * 1e-3) / 1e9 / hbm,
-                                         "note": "one work_kernel launch over all 10M rows, timed alone with CUDA events (30.7 GB: larger than L2)"}}
+                                         "note": "one plain f32 work_kernel launch over all 10M rows, timed alone with CUDA events (30.7 GB: larger than L2)"}}
     if not args.no_e2e:
         e = e2e_single(rig, wl, items, seeds, steps=2, n_warm=1) if rig.world == 1 else e2e_multi(rig, wl, items, seeds, steps=2, n_warm=1)
         rec["e2e"] = e
@@ -733,10 +754,10 @@ def main():
         os.environ.pop("ARROY_B200_PROFILE")
         st = ctx.build_stats()
         scan_ms, steps_dev = st["scan_ms"], st["steps"]
-        alg_bytes = st["scanned_rows"] * d * 4
+        alg_bytes = scan_bytes(st["scanned_rows"], ctx.build_shadow_stats(), d)
         achieved = alg_bytes / (scan_ms * 1e-3) / 1e9 if scan_ms > 0 else 0.0
-        traffic, traffic_note = None, "no ncu capture committed"
-        for tp_name in ("r02_work_kernel_traffic.json", "r01_work_kernel_traffic.json"):
+        traffic, traffic_note = None, "no ncu capture of this build of the kernel committed"
+        for tp_name in ("r02_shadow_kernel_traffic.json",):
             tp = os.path.join(ROOT, "profiles", tp_name)
             if os.path.exists(tp):
                 tj = json.load(open(tp))
@@ -747,7 +768,7 @@ def main():
         r = np.random.default_rng(0)
         normal = (r.standard_normal(d) / np.sqrt(d)).astype(np.float32)
         root_ms, _ = ctx.time_scan(normal, (0.0, 0.0), n, iters=5, flush_l2=True)
-        own_alg = tb["scanned_rows_per_step"] * d * 4 / world
+        own_alg = tb["alg_bytes_per_step"] / world
         lockstep_rec = {"GBps": achieved, "frac": achieved / hbm, "launches": steps_dev, "avg_ms": scan_ms / max(steps_dev, 1), "avg_algorithmic_GB": alg_bytes / max(steps_dev, 1) / 1e9,
                         "share_of_step": scan_ms / (st["build_ms"] if st["build_ms"] else 1.0),
                         "note": "SEPARATE untimed build in the lockstep schedule (ARROY_B200_PROFILE: one control + one work_kernel launch per step, every work_kernel launch "
@@ -756,14 +777,17 @@ def main():
         if tb["stats"]["steps"] == 1 and tb["stats"]["scan_ms"] > 0:
             # persistent schedule: the dominant kernel IS the step — one launch holds every side()/margin scan and wide partition
             kms = tb["stats"]["scan_ms"]
-            k_alg = tb["stats"]["scanned_rows"] * d * 4
+            k_alg = tb["last_step_alg_bytes"]
+            k_f32 = tb["stats"]["scanned_rows"] * d * 4
             line["roofline"] = {
-                "bound": "hbm", "kernel": "control_kernel<persistent> (worker CTAs: side()/margin scan + id partition; control CTAs: two_means / create_split / DFS)",
+                "bound": "hbm", "kernel": "control_kernel<persistent> (worker CTAs: side() through the bf16 shadow + exact re-score, fused root pass, id partition; control CTAs: two_means / create_split / DFS)",
                 "achieved": k_alg / (kms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s", "frac": k_alg / (kms * 1e-3) / 1e9 / hbm, "peak_source": which,
                 "traffic": (traffic * max(steps_dev, 1) / alg_bytes * k_alg) if traffic else None, "traffic_note": traffic_note,
                 "timing": "live, inside the timed region: CUDA events on the launching stream around the ONE kernel launch of the last timed step; achieved = the step's "
-                          "algorithmic scan bytes (rows that went through side() x d x 4) / that duration — control CTAs' serial work included, so a lower bound of the scan rate",
+                          "algorithmic scan bytes (bench.py scan_bytes: 2 B per element of the rows that went through the bf16 pre-filter, 4 B per element of the rows scored in f32, "
+                          "the fused root pass counted once) / that duration — control CTAs' serial work included, so a lower bound of the scan rate",
                 "per_launch": {"launches": 1, "avg_ms": kms, "avg_algorithmic_GB": k_alg / 1e9},
+                "f32_rows_equivalent_GBps": k_f32 / (kms * 1e-3) / 1e9,
                 "work_kernel_alone": lockstep_rec, "root_scan": root_rec,
             }
         else:

@@ -202,6 +202,11 @@ int32_t arroy_b200_build_trees_emit_mapped(arroy_ctx* ctx, const uint32_t* root_
  * ARROY_B200_PROFILE=1), stats[6] = tree nodes emitted, stats[7] = create_split calls whose
  * speculative two_means was redone sequentially (a mis-predicted branch; results are identical either way). */
 int32_t arroy_b200_build_stats(arroy_ctx* ctx, double stats[8]);
+/* Of the rows counted in stats[0], how many went through side()'s bf16 pre-filter (out[0]: the shadow copy of the items, half the
+ * bytes per row) and how many of those could not be decided by its error bound and were scored from the f32 row (out[1]). The
+ * other rows took the plain f32 scan. out[2]: rows of stats[0] that were covered by the fused root pass (trees x items), which
+ * read out[3] rows from the item matrix for all of them. Flags are identical either way. */
+int32_t arroy_b200_build_shadow_stats(arroy_ctx* ctx, uint64_t out[4]);
 
 /* ---- re-rank: replaces the loop of src/reader.rs:381-399 ------------------------------- */
 
