@@ -533,8 +533,10 @@ void build_wave(arroy_ctx* c, size_t wave_no, uint32_t t0, uint32_t tw, const ui
             P.shadow_stats = W.shadow_stats.as<unsigned long long>();
             // many trees per GPU: bandwidth decides, every node goes through the shadow; few: the chain of attempts decides and
             // small nodes keep the one-unit claims of the exact scan (more CTAs per node)
-            P.shadow_min_units = getenv("ARROY_B200_SHADOW_MIN") ? (uint32_t)atoi(getenv("ARROY_B200_SHADOW_MIN")) : ((!persist || tw >= 32) ? 16u : (tw >= 12 ? 64u : 128u));
+            P.shadow_min_units = getenv("ARROY_B200_SHADOW_MIN") ? (uint32_t)atoi(getenv("ARROY_B200_SHADOW_MIN")) : ((!persist || tw >= 32) ? 12u : (tw >= 12 ? 64u : 128u));
             P.shadow_small_chunk = getenv("ARROY_B200_SHADOW_CHUNK") ? (uint32_t)std::min(4, std::max(1, atoi(getenv("ARROY_B200_SHADOW_CHUNK")))) : 4u;
+            P.shadow_big_units = getenv("ARROY_B200_SHADOW_BIG") ? (uint32_t)atoi(getenv("ARROY_B200_SHADOW_BIG")) : 512u;
+            P.shadow_big_chunk = getenv("ARROY_B200_SHADOW_BIGCHUNK") ? (uint32_t)std::max(4, atoi(getenv("ARROY_B200_SHADOW_BIGCHUNK"))) : 8u;
         }
     }
     if (persist) {

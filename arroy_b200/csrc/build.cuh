@@ -107,7 +107,7 @@ struct BuildParams {
     // trees read the same rows — the workers do them in ONE pass over the item matrix (proot below)
     // bf16 copy of the item matrix (n x ld), or NULL: scans of more than shadow_min_units units go through it (scan_claim_shadow)
     const uint16_t* shadow;
-    uint32_t shadow_min_units, shadow_small_chunk;
+    uint32_t shadow_min_units, shadow_small_chunk, shadow_big_units, shadow_big_chunk;
     unsigned long long* shadow_stats;   // [0] rows scanned through the shadow, [1] of them re-scored from the f32 row
     int32_t root_fused;
     uint32_t* root_ready;         // number of trees whose root normal is published
@@ -1091,7 +1091,8 @@ __device__ __noinline__ void pworker(const BuildParams& P, float* sm_normal) {
                     __syncthreads();
                 }
                 if (P.shadow != nullptr && units > P.shadow_min_units)
-                    scan_claim_shadow(jb, g0 * chunk, min(units, (g0 + 1u) * chunk), P.items, P.shadow, P.ih0, P.d, P.ld, P.metric, sm_normal, sm_perm, nh0, w_list, w_cnt, P.shadow_stats);
+                    for (uint32_t u = g0 * chunk; u < min(units, (g0 + 1u) * chunk); u += SHADOW_CHUNK)
+                        scan_claim_shadow(jb, u, min(min(units, (g0 + 1u) * chunk), u + SHADOW_CHUNK), P.items, P.shadow, P.ih0, P.d, P.ld, P.metric, sm_normal, sm_perm, nh0, w_list, w_cnt, P.shadow_stats);
                 else
                     for (uint32_t u = g0 * chunk; u < min(units, (g0 + 1u) * chunk); ++u) scan_unit<true>(jb, u, P.items, P.ih0, P.d, P.ld, P.metric, sm_normal, nh0, &w_count);
             } else if (jb.kind == JOB_PARTITION) {
@@ -1327,7 +1328,7 @@ __global__ void __launch_bounds__(CTRL_THREADS, (CS == 0 ? 2 : 1)) control_kerne
                     } else {
                     // a claim = `chunk` units: four for the big scans (and for everything that goes through the bf16 shadow)
                     const bool via_shadow = P.shadow != nullptr && units > P.shadow_min_units;
-                    const uint32_t chunk = units > 1024u ? 4u : (via_shadow ? (units > 128u ? 4u : P.shadow_small_chunk) : 1u), groups = (units + chunk - 1) / chunk;
+                    const uint32_t chunk = via_shadow ? (units > P.shadow_big_units ? P.shadow_big_chunk : (units > 128u ? 4u : P.shadow_small_chunk)) : (units > 1024u ? 4u : 1u), groups = (units + chunk - 1) / chunk;
                     ppublish(P.slots[t], job, s_pseq, groups, chunk);
                     s_wait_ok = pwait(P, P.slots[t], s_pseq, groups) ? 1 : 0;
                     }
