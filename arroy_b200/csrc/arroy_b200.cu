@@ -124,13 +124,14 @@ struct arroy_ctx {
     bool staging_open = false;             // between arroy_b200_stage_begin and arroy_b200_stage_end
     std::vector<float> stage_h0, stage_h1;  // headers decoded from the leaf values staged so far
     // device-resident forest for the batched query path (arroy_b200_load_forest)
-    DevBuf f_kind, f_left, f_right, f_nidx, f_nh0, f_doff, f_dlen, f_normals, f_desc, f_roots;
+    DevBuf f_kind, f_left, f_right, f_nidx, f_nh0, f_doff, f_dlen, f_normals, f_desc, f_roots, f_rec, f_nofn;
     DevForest forest{};
     bool forest_loaded = false;
     uint32_t forest_max_desc = 0;
     uint64_t forest_n = 0;                       // the item count the loaded forest's rows were validated against
     uint64_t stage_epoch = 0, forest_epoch = 0;  // bumped by every (re)staging / forest upload: owners compare them (arroy_b200_epochs)
-    DevBuf w_heaps, w_cand, w_cand2, w_count, w_bitmap, w_status, w_beg, w_end, w_qrows, w_tmp;
+    DevBuf w_heaps, w_cand, w_cand2, w_count, w_bitmap, w_status, w_beg, w_end, w_qrows, w_tmp, w_pre;
+    uint32_t f_n_normals = 0;
     // results of the last build_trees_begin, waiting for build_trees_emit
     std::vector<std::vector<struct BuiltTreeView>> pending_waves;
     std::vector<uint32_t> pending_wave_t0;
@@ -1235,8 +1236,8 @@ void arroy_b200_destroy(arroy_ctx* c) {
     if (c->cached_exec) cudaGraphExecDestroy(c->cached_exec);
     if (c->cached_graph) cudaGraphDestroy(c->cached_graph);
     for (auto& sw : c->stage_workers) { sw.pin[0].release(); sw.pin[1].release(); if (sw.ev[0]) cudaEventDestroy(sw.ev[0]); if (sw.ev[1]) cudaEventDestroy(sw.ev[1]); if (sw.st) cudaStreamDestroy(sw.st); }
-    { DevBuf* fb[] = {&c->f_kind, &c->f_left, &c->f_right, &c->f_nidx, &c->f_nh0, &c->f_doff, &c->f_dlen, &c->f_normals, &c->f_desc, &c->f_roots,
-                      &c->w_heaps, &c->w_cand, &c->w_cand2, &c->w_count, &c->w_bitmap, &c->w_status, &c->w_beg, &c->w_end, &c->w_qrows, &c->w_tmp};
+    { DevBuf* fb[] = {&c->f_kind, &c->f_left, &c->f_right, &c->f_nidx, &c->f_nh0, &c->f_doff, &c->f_dlen, &c->f_normals, &c->f_desc, &c->f_roots, &c->f_rec, &c->f_nofn,
+                      &c->w_heaps, &c->w_cand, &c->w_cand2, &c->w_count, &c->w_bitmap, &c->w_status, &c->w_beg, &c->w_end, &c->w_qrows, &c->w_tmp, &c->w_pre};
       for (auto* b : fb) b->release(); }
     c->pin.release();
     c->wave.release();
@@ -1730,6 +1731,7 @@ int32_t arroy_b200_load_forest(arroy_ctx* c, uint32_t n_nodes, const uint8_t* ki
         up(c->f_kind, kind, n_nodes); up(c->f_left, left, 4ull * n_nodes); up(c->f_right, right, 4ull * n_nodes); up(c->f_nidx, normal_idx, 4ull * n_nodes);
         up(c->f_nh0, normal_hdr0, 4ull * n_nodes); up(c->f_doff, desc_off, 4ull * n_nodes); up(c->f_dlen, desc_len, 4ull * n_nodes);
         up(c->f_desc, desc_rows, 4ull * n_desc); up(c->f_roots, roots, 4ull * n_roots);
+        c->f_n_normals = n_normals;
         c->f_normals.ensure(std::max<size_t>(16, (size_t)n_normals * ld * 4));
         if (n_normals) {
             if (ld != c->dim) CK(cudaMemsetAsync(c->f_normals.p, 0, (size_t)n_normals * ld * 4, c->stream));
@@ -1741,6 +1743,9 @@ int32_t arroy_b200_load_forest(arroy_ctx* c, uint32_t n_nodes, const uint8_t* ki
         F.kind = c->f_kind.as<uint8_t>(); F.left = c->f_left.as<uint32_t>(); F.right = c->f_right.as<uint32_t>(); F.normal_idx = c->f_nidx.as<uint32_t>();
         F.nh0 = c->f_nh0.as<float>(); F.desc_off = c->f_doff.as<uint32_t>(); F.desc_len = c->f_dlen.as<uint32_t>(); F.normals = c->f_normals.as<float>();
         F.desc_rows = c->f_desc.as<uint32_t>(); F.roots = c->f_roots.as<uint32_t>(); F.n_roots = n_roots; F.n_nodes = n_nodes;
+        c->f_rec.ensure(std::max<size_t>(32, 32ull * n_nodes)); c->f_nofn.ensure(std::max<size_t>(16, 4ull * n_normals));
+        if (n_nodes) { forest_pack_kernel<<<(n_nodes + 255) / 256, 256, 0, c->stream>>>(F, c->f_rec.as<uint4>(), c->f_nofn.as<uint32_t>()); CK(cudaGetLastError()); CK(cudaStreamSynchronize(c->stream)); }
+        F.rec = c->f_rec.as<uint4>(); F.node_of_normal = c->f_nofn.as<uint32_t>();
         c->forest = F; c->forest_max_desc = max_desc; c->forest_n = c->n; c->forest_epoch += 1; c->forest_loaded = true;
     });
 }
@@ -1798,7 +1803,23 @@ int32_t arroy_b200_search_batch(arroy_ctx* c, uint32_t nq, const uint32_t* query
                 int nte1 = 0;
                 auto mark1 = [&]() { if (!c->xev[nte1]) CK(cudaEventCreate(&c->xev[nte1])); CK(cudaEventRecord(c->xev[nte1], c->stream)); ++nte1; };
                 mark1();
-                walk1_kernel<<<m, W1_THREADS, w1smem, c->stream>>>(F, c->items.as<float>(), c->dim, ld, c->metric, m, d_qrows, d_q, c->s_qh0.as<float>(), search_k,
+                // every split normal's dot with the query in one pass over the forest's normals, when that is cheaper than the
+                // walker's chain of per-pop reductions (ARROY_B200_WALK1_DOTS_MB: largest normals matrix it is done for; 0 = never)
+                const float* d_pre = nullptr;
+                {
+                    const char* pe = getenv("ARROY_B200_WALK1_DOTS_MB");
+                    const uint64_t cap_mb = pe ? (uint64_t)atoll(pe) : 768ull;
+                    const uint64_t nbytes = (uint64_t)c->f_n_normals * ld * 4;
+                    if (c->f_n_normals > 0 && m <= 4 && nbytes <= cap_mb << 20 && c->dim >= 32) {
+                        c->w_pre.ensure(4ull * F.n_nodes * m);
+                        const uint32_t gx = (uint32_t)std::min<uint64_t>(((uint64_t)c->f_n_normals + 7) / 8, (uint64_t)c->sm_count * 8);
+                        forest_dots_kernel<<<dim3(gx, m), 256, (size_t)ld * 4, c->stream>>>(F, c->f_n_normals, c->items.as<float>(), c->dim, ld, d_qrows, d_q, c->w_pre.as<float>());
+                        CK(cudaGetLastError());
+                        c->n_launches += 1;
+                        d_pre = c->w_pre.as<float>();
+                    }
+                }
+                walk1_kernel<<<m, W1_THREADS, w1smem, c->stream>>>(F, c->items.as<float>(), c->dim, ld, c->metric, m, d_qrows, d_q, c->s_qh0.as<float>(), d_pre, c->f_n_normals, getenv("ARROY_B200_WALK1_DEBUG") ? 1 : 0, search_k,
                                                                   c->w_cand2.as<uint32_t>(), cand_cap, c->w_count.as<uint32_t>(), c->w_status.as<int32_t>());
                 CK(cudaGetLastError());
                 mark1();

@@ -28,7 +28,20 @@ struct DevForest {
     const uint32_t* desc_rows;  // concatenated descendant lists, as ROW indices
     const uint32_t* roots;
     uint32_t n_roots, n_nodes;
+    // the same per-node fields packed for the latency path (walk1_kernel): two 16-byte words per node
+    //   [kind, left, right, normal_idx] [bits(nh0), desc_off, desc_len, 0]  — one round trip per pop, prefetchable at push time
+    const uint4* rec;
+    const uint32_t* node_of_normal;   // split node that owns normal ni
 };
+
+__global__ void forest_pack_kernel(DevForest F, uint4* __restrict__ rec, uint32_t* __restrict__ node_of_normal) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= F.n_nodes) return;
+    const uint32_t k = F.kind[i], ni = F.normal_idx[i];
+    rec[2 * (size_t)i] = make_uint4(k, F.left[i], F.right[i], ni);
+    rec[2 * (size_t)i + 1] = make_uint4(__float_as_uint(F.nh0[i]), F.desc_off[i], F.desc_len[i], 0u);
+    if (k == 2u && ni != 0xffffffffu) node_of_normal[ni] = i;
+}
 
 __device__ __forceinline__ float key_to_dist(uint32_t k) {  // inverse of ordered_key (canonical +0 / NaN)
     if (k == 0xffffffffu) return __uint_as_float(0x7fc00000u);
@@ -203,10 +216,29 @@ struct Walk1Shared {
 };
 inline size_t walk1_smem(uint32_t ld) { return sizeof(Walk1Shared) + (size_t)ld * 4 + 16; }
 
+// dots[q][node] = the reference's dot of query q with the normal of split node `node`, for EVERY normal of the forest (one warp per pair, the same
+// exact_warp the walker would call). A single query's walk is a chain of ~160 dependent pops, each of which would otherwise load
+// a 3 KB normal and reduce it on one warp; reading the whole forest's normals once (C2: 313 MB = 50 us of HBM) turns every pop
+// into a table lookup. Only worth it while the forest's normals are a few hundred MB (the caller decides).
+__global__ void __launch_bounds__(256)
+forest_dots_kernel(DevForest F, uint32_t n_normals, const float* __restrict__ items, uint32_t d, uint32_t ld,
+                   const uint32_t* __restrict__ qrows, const float* __restrict__ queries, float* __restrict__ dots) {
+    extern __shared__ __align__(16) float fd_q[];
+    const uint32_t q = blockIdx.y;
+    const float* qv = qrows ? items + (size_t)qrows[q] * ld : queries + (size_t)q * ld;
+    for (uint32_t i = threadIdx.x; i < ld; i += blockDim.x) fd_q[i] = qv[i];
+    __syncthreads();
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (uint32_t ni = blockIdx.x * 8u + warp; ni < n_normals; ni += gridDim.x * 8u) {
+        const float dt = exact_warp<false>(F.normals + (size_t)ni * ld, fd_q, (int)d);
+        if (lane == 0) dots[(size_t)q * F.n_nodes + F.node_of_normal[ni]] = dt;   // indexed by NODE: the walker can prefetch it when it pushes the node
+    }
+}
+
 __global__ void __launch_bounds__(W1_THREADS)
 walk1_kernel(DevForest F, const float* __restrict__ items, uint32_t d, uint32_t ld, int metric, uint32_t nq,
              const uint32_t* __restrict__ qrows, const float* __restrict__ queries, const float* __restrict__ qh0,
-             unsigned long long search_k, uint32_t* __restrict__ out_cand, uint32_t cand_cap, uint32_t* __restrict__ out_count, int32_t* __restrict__ status) {
+             const float* __restrict__ pre_dots, uint32_t n_normals, int debug, unsigned long long search_k, uint32_t* __restrict__ out_cand, uint32_t cand_cap, uint32_t* __restrict__ out_count, int32_t* __restrict__ status) {
     extern __shared__ __align__(16) unsigned char w1_smem[];
     Walk1Shared& S = *reinterpret_cast<Walk1Shared*>(w1_smem);
     float* sq = reinterpret_cast<float*>(w1_smem + ((sizeof(Walk1Shared) + 15) & ~(size_t)15));
@@ -217,44 +249,74 @@ walk1_kernel(DevForest F, const float* __restrict__ items, uint32_t d, uint32_t 
     for (uint32_t i = tid; i < ld; i += W1_THREADS) sq[i] = qv[i];
     if (tid == 0) { S.produced = 0; S.done = 0; S.total = 0; S.status = 0; }
     __syncthreads();
+    const long long dbg_t0 = clock64();
+    uint32_t dbg_pops = 0, dbg_leaves = 0;
     if (warp == 0) {
         uint32_t size = 0, produced = 0, total32 = 0;
         unsigned long long total = 0;
         int st = 0;
         if (lane == 0) {
             const unsigned long long inf_key = (unsigned long long)ordered_key(__uint_as_float(0x7f800000u)) << 32;
-            for (uint32_t r = 0; r < F.n_roots && size < W1_HEAP; ++r) heap_push(S.heap, size, inf_key | F.roots[r]);
+            for (uint32_t r = 0; r < F.n_roots && size < W1_HEAP; ++r) S.heap[size++] = inf_key | F.roots[r];
             if (F.n_roots > W1_HEAP) st = 2;
         }
         st = __shfl_sync(0xffffffffu, st, 0);
+        // The priority queue is an UNSORTED array: a push appends (lane 0), a pop is a warp-wide arg-max over the <= 1024 entries
+        // (every key is distinct — the node id is its low half — so the pop sequence is the BinaryHeap's of the reference whatever
+        // the container). On one lane a binary heap costs ~1300 cycles per pop + two pushes; this is ~300.
         while (!st) {
             size = __shfl_sync(0xffffffffu, size, 0);
             if (total >= search_k || size == 0) break;
+            __syncwarp();
             unsigned long long top = 0;
-            if (lane == 0) top = heap_pop(S.heap, size);
-            top = __shfl_sync(0xffffffffu, top, 0);
+            uint32_t ti = 0xffffffffu;
+            for (uint32_t i = lane; i < size; i += 32) { const unsigned long long v = S.heap[i]; if (ti == 0xffffffffu || v > top) { top = v; ti = i; } }
+            {   // warp arg-max of a 64-bit key in two REDUX steps: the high halves, then the low halves among the lanes that hold the
+                // winning high half (a lane without an entry contributes 0 / loses the ballot)
+                const uint32_t hi = ti != 0xffffffffu ? (uint32_t)(top >> 32) : 0u;
+                const uint32_t mh = __reduce_max_sync(0xffffffffu, hi);
+                const bool in = ti != 0xffffffffu && hi == mh;
+                const uint32_t ml = __reduce_max_sync(0xffffffffu, in ? (uint32_t)top : 0u);
+                const unsigned win = __ballot_sync(0xffffffffu, in && (uint32_t)top == ml);
+                const int src = __ffs((int)win) - 1;
+                ti = __shfl_sync(0xffffffffu, ti, src);
+                top = ((unsigned long long)mh << 32) | ml;
+            }
+            if (lane == 0) { S.heap[ti] = S.heap[size - 1]; size -= 1; }
+            __syncwarp();
+            dbg_pops += 1;
             const uint32_t node = (uint32_t)top;
             const float dist = key_to_dist((uint32_t)(top >> 32));
-            const int kind = node < F.n_nodes ? F.kind[node] : 0;
+            uint4 r0 = make_uint4(0u, 0u, 0u, 0u), r1 = r0;
+            if (node < F.n_nodes) { r0 = F.rec[2 * (size_t)node]; r1 = F.rec[2 * (size_t)node + 1]; }
+            const int kind = (int)r0.x;
             if (kind == 1) {
-                const uint32_t off = F.desc_off[node], len = F.desc_len[node];
+                const uint32_t off = r1.y, len = r1.z;
                 if (total32 + len > W1_CAND || produced >= W1_LEAFQ) { st = 1; break; }
                 if (lane == 0) { S.lq_off[produced] = off; S.lq_len[produced] = len; S.lq_dst[produced] = total32; __threadfence_block(); S.produced = produced + 1; }
-                produced += 1; total32 += len; total += len;
+                produced += 1; total32 += len; total += len; dbg_leaves += 1;
             } else if (kind == 2) {
-                const uint32_t ni = F.normal_idx[node];
-                const uint32_t lc = F.left[node], rc = F.right[node];
+                const uint32_t ni = r0.w;
+                const uint32_t lc = r0.y, rc = r0.z;
+                // the children will be popped soon (one of them usually next): have their records and dots on the way
+                if (lane < 2) {
+                    const uint32_t ch = lane == 0 ? lc : rc;
+                    if (ch < F.n_nodes) {
+                        asm volatile("prefetch.global.L1 [%0];" :: "l"(F.rec + 2 * (size_t)ch));
+                        if (pre_dots) asm volatile("prefetch.global.L1 [%0];" :: "l"(pre_dots + (size_t)q * F.n_nodes + ch));
+                    }
+                }
                 float mg = 0.0f;
                 if (ni != 0xffffffffu) {
                     const float* nv = F.normals + (size_t)ni * ld;
-                    const float dt = exact_warp<false>(nv, sq, (int)d);
-                    mg = margin_finish(metric, dt, F.nh0[node], qhdr);
+                    const float dt = pre_dots ? pre_dots[(size_t)q * F.n_nodes + node] : exact_warp<false>(nv, sq, (int)d);
+                    mg = margin_finish(metric, dt, __uint_as_float(r1.x), qhdr);
                 }
                 if (lane == 0) {
                     if (size + 2 > W1_HEAP) st = 2;
                     else {
-                        heap_push(S.heap, size, ((unsigned long long)ordered_key(f32_min_dev(-mg, dist)) << 32) | lc);
-                        heap_push(S.heap, size, ((unsigned long long)ordered_key(f32_min_dev(mg, dist)) << 32) | rc);
+                        S.heap[size++] = ((unsigned long long)ordered_key(f32_min_dev(-mg, dist)) << 32) | lc;
+                        S.heap[size++] = ((unsigned long long)ordered_key(f32_min_dev(mg, dist)) << 32) | rc;
                     }
                 }
                 st = __shfl_sync(0xffffffffu, st, 0);
@@ -276,6 +338,7 @@ walk1_kernel(DevForest F, const float* __restrict__ items, uint32_t d, uint32_t 
         }
     }
     __syncthreads();
+    const long long dbg_t1 = clock64();
     const int st = S.status;
     const uint32_t n = S.total;
     if (st != 0 || n > cand_cap) { if (tid == 0) { status[q] = st ? st : 1; out_count[q] = 0; } return; }
@@ -310,6 +373,7 @@ walk1_kernel(DevForest F, const float* __restrict__ items, uint32_t d, uint32_t 
     uint32_t* out = out_cand + (size_t)q * cand_cap;
     for (uint32_t i = b0; i < e0; ++i) if (i == 0 || S.cand[i] != S.cand[i - 1]) out[o++] = S.cand[i];
     if (tid == 0) { out_count[q] = uniq; status[q] = 0; }
+    if (debug && tid == 0) printf("[walk1] q %u: %u pops (%u leaves), walk %lld cycles, sort + unique %lld cycles, %u candidates (%u unique)\n", q, dbg_pops, dbg_leaves, dbg_t1 - dbg_t0, clock64() - dbg_t1, n, uniq);
 }
 
 }  // namespace ab
