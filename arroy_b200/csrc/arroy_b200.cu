@@ -117,7 +117,8 @@ struct arroy_ctx {
     cudaStream_t side_stream = nullptr;   // host -> device flags while the persistent build kernel occupies `stream`
     cudaEvent_t ev_done = nullptr, ev_p0 = nullptr, ev_p1 = nullptr;   // ev_p0 / ev_p1 bracket the persistent build kernel
     double stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    uint64_t shadow_rows = 0, shadow_rescored = 0, fused_root_rows = 0, fused_root_read = 0;   // last build: rows scanned through the bf16 shadow / re-scored from f32
+    uint64_t shadow_rows = 0, shadow_rescored = 0, fused_root_rows = 0, fused_root_read = 0;
+    uint64_t wave_key[4] = {0, 0, 0, 0}, wave_max = 0, wave_trees_ok = 0; bool wave_key_valid = false;   // shapes of the last successful build (do_build_begin)   // last build: rows scanned through the bf16 shadow / re-scored from f32
     uint64_t n_launches = 0, h2d_bytes = 0, d2h_bytes = 0;  // since create (arroy_b200_counters)
     cudaEvent_t tev0 = nullptr, tev1 = nullptr;
     std::vector<StageWorker> stage_workers;
@@ -782,15 +783,19 @@ void do_build_begin(arroy_ctx* c, uint32_t n_trees, const uint8_t (*seeds)[32], 
     if (n_trees == 0) return;
     if (cancel && cancel(cancel_arg)) throw Cancelled("The corresponding build process has been cancelled");
 
-    // wave size from free memory
-    size_t free_b = 0, total_b = 0;
-    CK(cudaMemGetInfo(&free_b, &total_b));
+    // wave size from free memory. cudaMemGetInfo is a driver round trip that takes anything from 0.5 to 30 ms on this part: a
+    // rebuild with the shapes of the previous build (whose wave buffers are still held by the context) reuses its answer.
     const uint64_t n = c->n;
+    const uint64_t wave_key[4] = {n, K, c->ld, (uint64_t)(sub.rows ? 1 : 0)};
+    const bool same_shape = c->wave_key_valid && memcmp(wave_key, c->wave_key, sizeof wave_key) == 0 && n_trees <= c->wave_trees_ok;
+    size_t free_b = 0, total_b = 0;
+    if (!same_shape) CK(cudaMemGetInfo(&free_b, &total_b));
     const uint64_t leaves_est = n / K + 1;
     const uint64_t per_tree = n * (4 + 4 + 1 + 4) + (n / SCAN_UNIT + 1) * 4 + sizeof(Frame) * (uint64_t)MAX_DEPTH + 16ull * 8 * leaves_est +
                               4ull * (c->ld + NORMAL_HDR) * 4 * leaves_est + 4096;
     uint64_t reusable = c->wave.perm0.cap + c->wave.perm1.cap + c->wave.flags.cap + c->wave.final_ids.cap + c->wave.pool.cap + c->wave.recs.cap;
-    uint64_t max_wave = (uint64_t)((free_b + reusable) * 0.7) / std::max<uint64_t>(per_tree, 1);
+    uint64_t max_wave = same_shape ? c->wave_max : (uint64_t)((free_b + reusable) * 0.7) / std::max<uint64_t>(per_tree, 1);
+    if (!same_shape) c->wave_max = max_wave;
     if (const char* e = getenv("ARROY_B200_MAX_WAVE")) max_wave = std::min<uint64_t>(max_wave, (uint64_t)atoi(e));
     max_wave = std::max<uint64_t>(1, std::min<uint64_t>(max_wave, 120));  // <= 128 concurrent kernels
 
@@ -816,6 +821,7 @@ void do_build_begin(arroy_ctx* c, uint32_t n_trees, const uint8_t (*seeds)[32], 
     c->stats[4] = ms;
     c->pending_pool_stride = pool_stride;
     c->pending_n_trees = n_trees;
+    memcpy(c->wave_key, wave_key, sizeof wave_key); c->wave_key_valid = true; c->wave_trees_ok = std::max<uint64_t>(same_shape ? c->wave_trees_ok : 0, n_trees);
     uint64_t total_nodes = 0;
     for (size_t w = 0; w < c->pending_waves.size(); ++w)
         for (size_t i = 0; i < c->pending_waves[w].size(); ++i) {
@@ -1240,7 +1246,7 @@ void arroy_b200_destroy(arroy_ctx* c) {
                       &c->w_heaps, &c->w_cand, &c->w_cand2, &c->w_count, &c->w_bitmap, &c->w_status, &c->w_beg, &c->w_end, &c->w_qrows, &c->w_tmp, &c->w_pre};
       for (auto* b : fb) b->release(); }
     c->pin.release();
-    c->wave.release();
+    c->wave.release(); c->wave_key_valid = false;
     for (auto& hw : c->host_waves) hw.release();
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
